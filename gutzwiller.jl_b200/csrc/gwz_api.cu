@@ -1,0 +1,1051 @@
+// gwz_api.cu -- the C ABI of libgutzwiller_b200.so (see include/gutzwiller_b200.h).
+//
+// Host-side orchestration only: handles, HBM buffers, kernel launches on the context's stream,
+// the NCCL all-reduce of the accumulator vector, and the (host, O(parameters)) AMSGrad update.
+// There is no CPU implementation of any sampled or swept quantity in this file.
+#include "gutzwiller_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "gwz_internal.h"
+#include "gwz_nccl.h"
+
+using namespace gwz;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define GWZ_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(GWZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+#define GWZ_NCCL(api, expr)                                                                         \
+    do {                                                                                            \
+        int _r = (expr);                                                                            \
+        if (_r != kNcclSuccess)                                                                     \
+            return fail(GWZ_ERR_NCCL, std::string(#expr) + ": " + (api)->GetErrorString(_r));       \
+    } while (0)
+#define GWZ_REQUIRE(cond, msg)                                   \
+    do {                                                         \
+        if (!(cond)) return fail(GWZ_ERR_INVALID, (msg));        \
+    } while (0)
+
+extern "C" const char* gwz_last_error(void) { return g_last_error.c_str(); }
+extern "C" int gwz_version(void) { return GWZ_VERSION; }
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+constexpr int GROUP_ROWS = 64;
+
+struct gwz_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    int clock_khz = 0;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    double* d_acc = nullptr;    // NUM_ACC doubles: send/recv buffer of the all-reduce
+    double* d_group = nullptr;  // GROUP_ROWS x NUM_ACC scratch
+    double* h_acc = nullptr;    // pinned
+    int* d_err = nullptr;
+    int* h_err = nullptr;  // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct gwz_model {
+    gwz_context* ctx;
+    int N, M, B, W, nw;
+    double u, t;
+    DevModel dm;
+};
+
+struct gwz_walkers {
+    gwz_model* m;
+    size_t n;
+    uint64_t offset, seed;
+    uint64_t steps_done;  // Philox step counter
+    uint64_t acc_steps;   // steps currently held in the estimators (per walker)
+    uint64_t* d_addr = nullptr;
+    double* d_acc = nullptr;
+    double* d_partials = nullptr;
+    int partials_cap = 0;
+    double* d_vec = nullptr;  // NUM_ACC doubles: this set's reduced vector
+};
+
+struct gwz_sweep {
+    gwz_model* m;
+    uint64_t* d_basis = nullptr;  // SoA [W][dim], null => ranked
+    uint64_t dim = 0, rank_begin = 0;
+    uint64_t* d_binom = nullptr;
+    double* d_partials = nullptr;
+    int grid = 0;
+    uint64_t chunk = 1;
+    float last_ms = 0.f;
+};
+
+static int use_device(const gwz_context* ctx) {
+    GWZ_CUDA(cudaSetDevice(ctx->device));
+    return GWZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int gwz_context_create(int device, gwz_context** out) {
+    GWZ_REQUIRE(out != nullptr, "gwz_context_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GWZ_ERR_CUDA, std::string("no CUDA device available (this library has no CPU path): ") +
+                                      cudaGetErrorString(e));
+    GWZ_REQUIRE(device >= 0 && device < count, "gwz_context_create: device index out of range");
+    gwz_context* c = new gwz_context();
+    c->device = device;
+    GWZ_CUDA(cudaSetDevice(device));
+    GWZ_CUDA(cudaGetDeviceProperties(&c->prop, device));
+    GWZ_CUDA(cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device));
+    GWZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    GWZ_CUDA(cudaMalloc(&c->d_acc, sizeof(double) * NUM_ACC));
+    GWZ_CUDA(cudaMalloc(&c->d_group, sizeof(double) * NUM_ACC * GROUP_ROWS));
+    GWZ_CUDA(cudaMallocHost(&c->h_acc, sizeof(double) * NUM_ACC));
+    GWZ_CUDA(cudaMalloc(&c->d_err, sizeof(int)));
+    GWZ_CUDA(cudaMallocHost(&c->h_err, sizeof(int)));
+    GWZ_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    GWZ_CUDA(cudaEventCreate(&c->ev0));
+    GWZ_CUDA(cudaEventCreate(&c->ev1));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_destroy(gwz_context* c) {
+    if (!c) return GWZ_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) {
+        const NcclApi* api = nccl_api(nullptr);
+        if (api) api->CommDestroy(c->comm);
+    }
+    cudaFree(c->d_acc);
+    cudaFree(c->d_group);
+    cudaFreeHost(c->h_acc);
+    cudaFree(c->d_err);
+    cudaFreeHost(c->h_err);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_info(const gwz_context* c, int* device, int* sm_count, int* sm_clock_khz, int* cc_major,
+                                int* cc_minor, size_t* global_mem_bytes) {
+    GWZ_REQUIRE(c != nullptr, "gwz_context_info: ctx is NULL");
+    if (device) *device = c->device;
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (sm_clock_khz) *sm_clock_khz = c->clock_khz;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (global_mem_bytes) *global_mem_bytes = c->prop.totalGlobalMem;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_stream(const gwz_context* c, void** cuda_stream) {
+    GWZ_REQUIRE(c && cuda_stream, "gwz_context_stream: NULL argument");
+    *cuda_stream = (void*)c->stream;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_synchronize(gwz_context* c) {
+    GWZ_REQUIRE(c != nullptr, "gwz_context_synchronize: ctx is NULL");
+    if (int rc = use_device(c)) return rc;
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_nccl_unique_id(uint8_t id[GWZ_NCCL_ID_BYTES]) {
+    GWZ_REQUIRE(id != nullptr, "gwz_nccl_unique_id: id is NULL");
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) return fail(GWZ_ERR_NCCL, why ? why : "NCCL unavailable");
+    ncclUniqueId uid;
+    static_assert(sizeof(uid) == GWZ_NCCL_ID_BYTES, "ncclUniqueId size");
+    GWZ_NCCL(api, api->GetUniqueId(&uid));
+    std::memcpy(id, &uid, sizeof(uid));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_comm_init(gwz_context* c, int world_size, int rank, const uint8_t id[GWZ_NCCL_ID_BYTES]) {
+    GWZ_REQUIRE(c && id, "gwz_context_comm_init: NULL argument");
+    GWZ_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "gwz_context_comm_init: bad rank/world_size");
+    GWZ_REQUIRE(c->comm == nullptr, "gwz_context_comm_init: communicator already initialised");
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) return fail(GWZ_ERR_NCCL, why ? why : "NCCL unavailable");
+    if (int rc = use_device(c)) return rc;
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    GWZ_NCCL(api, api->CommInitRank(&c->comm, world_size, uid, rank));
+    c->world = world_size;
+    c->rank = rank;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_comm_init_all(gwz_context* const* ctxs, int n) {
+    GWZ_REQUIRE(ctxs && n >= 1, "gwz_context_comm_init_all: bad arguments");
+    const char* why = nullptr;
+    const NcclApi* api = nccl_api(&why);
+    if (!api) return fail(GWZ_ERR_NCCL, why ? why : "NCCL unavailable");
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) {
+        GWZ_REQUIRE(ctxs[i] && ctxs[i]->comm == nullptr, "gwz_context_comm_init_all: NULL or already joined context");
+        devs[i] = ctxs[i]->device;
+    }
+    GWZ_NCCL(api, api->CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) {
+        ctxs[i]->comm = comms[i];
+        ctxs[i]->world = n;
+        ctxs[i]->rank = i;
+    }
+    return GWZ_OK;
+}
+
+extern "C" int gwz_context_comm_info(const gwz_context* c, int* world_size, int* rank) {
+    GWZ_REQUIRE(c != nullptr, "gwz_context_comm_info: ctx is NULL");
+    if (world_size) *world_size = c->world;
+    if (rank) *rank = c->rank;
+    return GWZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+extern "C" int gwz_model_create_hubbard1d_gutzwiller(gwz_context* ctx, int N, int M, double u, double t,
+                                                     gwz_model** out) {
+    GWZ_REQUIRE(ctx && out, "gwz_model_create: NULL argument");
+    GWZ_REQUIRE(N >= 1 && M >= 2, "gwz_model_create: need N >= 1 particles and M >= 2 modes");
+    const int B = N + M - 1;
+    GWZ_REQUIRE(B + 1 + KCAP <= 32 * MAXNW, "gwz_model_create: N+M-1 must be <= 251 bits");
+    gwz_model* m = new gwz_model();
+    m->ctx = ctx;
+    m->N = N;
+    m->M = M;
+    m->B = B;
+    m->W = (B + 63) / 64;
+    m->nw = (B + 1 + KCAP + 31) / 32;
+    m->u = u;
+    m->t = t;
+    DevModel& dm = m->dm;
+    std::memset(&dm, 0, sizeof(dm));
+    dm.N = N;
+    dm.M = M;
+    dm.B = B;
+    dm.W = m->W;
+    dm.ext_ws = (B + 1) >> 5;
+    dm.ext_bs = (B + 1) & 31;
+    dm.u = u;
+    dm.t = t;
+    for (int p = 0; p <= B; ++p) dm.zmask[p >> 5] |= 1u << (p & 31);
+    for (int p = 0; p < B; ++p) dm.amask[p >> 5] |= 1u << (p & 31);
+    *out = m;
+    return GWZ_OK;
+}
+extern "C" int gwz_model_destroy(gwz_model* m) {
+    delete m;
+    return GWZ_OK;
+}
+extern "C" int gwz_model_info(const gwz_model* m, int* N, int* M, double* u, double* t, int* bits, int* words) {
+    GWZ_REQUIRE(m != nullptr, "gwz_model_info: model is NULL");
+    if (N) *N = m->N;
+    if (M) *M = m->M;
+    if (u) *u = m->u;
+    if (t) *t = m->t;
+    if (bits) *bits = m->B;
+    if (words) *words = m->W;
+    return GWZ_OK;
+}
+extern "C" int gwz_model_from_onr(const gwz_model* m, const int32_t* onr, uint64_t* a) {
+    GWZ_REQUIRE(m && onr && a, "gwz_model_from_onr: NULL argument");
+    int total = 0;
+    for (int i = 0; i < m->M; ++i) {
+        GWZ_REQUIRE(onr[i] >= 0, "gwz_model_from_onr: negative occupation");
+        total += onr[i];
+    }
+    GWZ_REQUIRE(total == m->N, "gwz_model_from_onr: occupations do not sum to N");
+    for (int w = 0; w < m->W; ++w) a[w] = 0;
+    int pos = 0;
+    for (int i = 0; i < m->M; ++i) {
+        for (int k = 0; k < onr[i]; ++k, ++pos) a[pos >> 6] |= 1ull << (pos & 63);
+        ++pos;
+    }
+    return GWZ_OK;
+}
+extern "C" int gwz_model_to_onr(const gwz_model* m, const uint64_t* a, int32_t* onr) {
+    GWZ_REQUIRE(m && onr && a, "gwz_model_to_onr: NULL argument");
+    int mode = 0;
+    for (int i = 0; i < m->M; ++i) onr[i] = 0;
+    for (int p = 0; p < m->B; ++p) {
+        if ((a[p >> 6] >> (p & 63)) & 1ull) {
+            GWZ_REQUIRE(mode < m->M, "gwz_model_to_onr: malformed address");
+            onr[mode]++;
+        } else {
+            ++mode;
+        }
+    }
+    return GWZ_OK;
+}
+extern "C" int gwz_model_near_uniform(const gwz_model* m, uint64_t* a) {
+    GWZ_REQUIRE(m && a, "gwz_model_near_uniform: NULL argument");
+    std::vector<int32_t> onr(m->M);
+    const int ff = m->N / m->M, extras = m->N % m->M;
+    for (int i = 0; i < m->M; ++i) onr[i] = ff + (i < extras ? 1 : 0);
+    return gwz_model_from_onr(m, onr.data(), a);
+}
+static void binomial_table(std::vector<uint64_t>& tab) {
+    tab.assign(65 * 65, 0);
+    for (int n = 0; n <= 64; ++n) {
+        tab[n * 65 + 0] = 1;
+        for (int k = 1; k <= n; ++k) {
+            const uint64_t a = tab[(n - 1) * 65 + k - 1], b = (k <= n - 1) ? tab[(n - 1) * 65 + k] : 0;
+            tab[n * 65 + k] = (a > UINT64_MAX - b) ? UINT64_MAX : a + b;
+        }
+    }
+}
+extern "C" int gwz_model_dimension(const gwz_model* m, double* dim, uint64_t* dim_exact) {
+    GWZ_REQUIRE(m != nullptr, "gwz_model_dimension: model is NULL");
+    double r = 1.0;
+    const int n = m->B, k = (m->N < m->M - 1) ? m->N : m->M - 1;
+    for (int i = 1; i <= k; ++i) r = r * (double)(n - k + i) / (double)i;
+    if (dim) *dim = std::floor(r + 0.5);
+    if (dim_exact) {
+        *dim_exact = 0;
+        if (m->B <= 64) {
+            std::vector<uint64_t> tab;
+            binomial_table(tab);
+            const uint64_t v = tab[m->B * 65 + m->N];
+            *dim_exact = (v == UINT64_MAX) ? 0 : v;
+        }
+    }
+    return GWZ_OK;
+}
+
+// parameter-dependent tables (O(KCAP^2) host work per call)
+static void make_tables(const gwz_model* m, double g, DevTables* tb) {
+    std::memset(tb, 0, sizeof(*tb));
+    tb->g = g;
+    tb->c = g * m->u;
+    for (int L = 0; L < KCAP; ++L)
+        for (int R = 0; R < KCAP; ++R) {
+            const int k = L * KCAP + R;
+            const double rr = (L > 0) ? std::exp(-tb->c * (double)(R - L + 1)) : 0.0;
+            const double rl = (R > 0) ? std::exp(-tb->c * (double)(L - R + 1)) : 0.0;
+            const double er = (L > 0) ? std::sqrt((double)L * (double)(R + 1)) * rr : 0.0;
+            const double el = (R > 0) ? std::sqrt((double)R * (double)(L + 1)) * rl : 0.0;
+            tb->RR[k] = rr;
+            tb->RL[k] = rl;
+            tb->IRR[k] = rr > 0 ? 1.0 / rr : 0.0;
+            tb->IRL[k] = rl > 0 ? 1.0 / rl : 0.0;
+            tb->FS[k] = rr + rl;
+            tb->FE[k] = er + el;
+            tb->FD[k] = er * (double)(R - L + 1) + el * (double)(L - R + 1);
+        }
+}
+
+static int check_err_flag(gwz_context* c) {
+    // caller has synchronised the stream after copying d_err -> h_err
+    if (*c->h_err) {
+        *c->h_err = 0;
+        cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
+        cudaStreamSynchronize(c->stream);
+        return fail(GWZ_ERR_NONFINITE, "Infinite residence time");
+    }
+    return GWZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// probe
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+};
+
+extern "C" int gwz_probe_addresses(gwz_model* m, const uint64_t* addr_words, size_t n, const double* params,
+                                   const double* u01, int kernel_kind, double* e_loc, double* residence_time,
+                                   double* grad_ratio, int32_t* n_hops, double* rates, int32_t* chosen,
+                                   uint64_t* next_addr) {
+    GWZ_REQUIRE(m && params, "gwz_probe_addresses: NULL argument");
+    GWZ_REQUIRE(n == 0 || addr_words, "gwz_probe_addresses: addr_words is NULL");
+    GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
+                "gwz_probe_addresses: unknown kernel_kind");
+    GWZ_REQUIRE(!(rates && kernel_kind != GWZ_KERNEL_ENUMERATE),
+                "gwz_probe_addresses: per-hop rates are only produced by GWZ_KERNEL_ENUMERATE");
+    if (n == 0) return GWZ_OK;
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    cudaStream_t s = c->stream;
+    const size_t W = m->W, twoM = 2 * (size_t)m->M;
+    DevBuf<uint64_t> d_addr, d_next;
+    DevBuf<double> d_u, d_e, d_t, d_g, d_r;
+    DevBuf<int32_t> d_h, d_c;
+    GWZ_CUDA(d_addr.alloc(n * W));
+    GWZ_CUDA(cudaMemcpyAsync(d_addr.p, addr_words, sizeof(uint64_t) * n * W, cudaMemcpyHostToDevice, s));
+    if (u01) {
+        GWZ_CUDA(d_u.alloc(n));
+        GWZ_CUDA(cudaMemcpyAsync(d_u.p, u01, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    }
+    GWZ_CUDA(d_e.alloc(n));
+    GWZ_CUDA(d_t.alloc(n));
+    GWZ_CUDA(d_g.alloc(n));
+    GWZ_CUDA(d_h.alloc(n));
+    GWZ_CUDA(d_c.alloc(n));
+    GWZ_CUDA(d_next.alloc(n * W));
+    if (rates) GWZ_CUDA(d_r.alloc(n * twoM));
+    ProbeLaunch L;
+    L.dm = m->dm;
+    make_tables(m, params[0], &L.tb);
+    L.nw = m->nw;
+    L.kind = kernel_kind;
+    L.addr = d_addr.p;
+    L.n = n;
+    L.u01 = u01 ? d_u.p : nullptr;
+    L.e_loc = d_e.p;
+    L.tau = d_t.p;
+    L.grad = d_g.p;
+    L.n_hops = d_h.p;
+    L.rates = rates ? d_r.p : nullptr;
+    L.chosen = d_c.p;
+    L.next_addr = d_next.p;
+    L.err_flag = c->d_err;
+    GWZ_CUDA(launch_probe(L, s));
+    if (e_loc) GWZ_CUDA(cudaMemcpyAsync(e_loc, d_e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (residence_time) GWZ_CUDA(cudaMemcpyAsync(residence_time, d_t.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (grad_ratio) GWZ_CUDA(cudaMemcpyAsync(grad_ratio, d_g.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (n_hops) GWZ_CUDA(cudaMemcpyAsync(n_hops, d_h.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    if (chosen) GWZ_CUDA(cudaMemcpyAsync(chosen, d_c.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    if (rates) GWZ_CUDA(cudaMemcpyAsync(rates, d_r.p, sizeof(double) * n * twoM, cudaMemcpyDeviceToHost, s));
+    if (next_addr) GWZ_CUDA(cudaMemcpyAsync(next_addr, d_next.p, sizeof(uint64_t) * n * W, cudaMemcpyDeviceToHost, s));
+    GWZ_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GWZ_CUDA(cudaStreamSynchronize(s));
+    return check_err_flag(c);
+}
+
+extern "C" int gwz_ansatz_val_and_grad(gwz_model* m, const uint64_t* addr_words, size_t n, const double* params,
+                                       double* val, double* grad) {
+    GWZ_REQUIRE(m && params, "gwz_ansatz_val_and_grad: NULL argument");
+    GWZ_REQUIRE(n == 0 || addr_words, "gwz_ansatz_val_and_grad: addr_words is NULL");
+    if (n == 0) return GWZ_OK;
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    cudaStream_t s = c->stream;
+    DevBuf<uint64_t> d_addr;
+    DevBuf<double> d_v, d_g;
+    GWZ_CUDA(d_addr.alloc(n * m->W));
+    GWZ_CUDA(d_v.alloc(n));
+    GWZ_CUDA(d_g.alloc(n));
+    GWZ_CUDA(cudaMemcpyAsync(d_addr.p, addr_words, sizeof(uint64_t) * n * m->W, cudaMemcpyHostToDevice, s));
+    GWZ_CUDA(launch_ansatz(m->dm, params[0], m->nw, d_addr.p, n, d_v.p, d_g.p, s));
+    if (val) GWZ_CUDA(cudaMemcpyAsync(val, d_v.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (grad) GWZ_CUDA(cudaMemcpyAsync(grad, d_g.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    GWZ_CUDA(cudaStreamSynchronize(s));
+    return GWZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// walkers
+// ------------------------------------------------------------------------------------------
+extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t global_offset, const uint64_t* start_addr,
+                                  uint64_t seed, gwz_walkers** out) {
+    GWZ_REQUIRE(m && start_addr && out, "gwz_walkers_create: NULL argument");
+    GWZ_REQUIRE(n_walkers >= 1, "gwz_walkers_create: need at least one walker");
+    // validate the start address: exactly N ones within B bits
+    {
+        int ones = 0;
+        for (int p = 0; p < 64 * m->W; ++p) {
+            const int bit = (int)((start_addr[p >> 6] >> (p & 63)) & 1ull);
+            GWZ_REQUIRE(!(bit && p >= m->B), "gwz_walkers_create: start address has bits beyond N+M-1");
+            ones += bit;
+        }
+        GWZ_REQUIRE(ones == m->N, "gwz_walkers_create: start address does not hold N particles");
+    }
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    gwz_walkers* w = new gwz_walkers();
+    w->m = m;
+    w->n = (size_t)n_walkers;
+    w->offset = global_offset;
+    w->seed = seed;
+    w->steps_done = 0;
+    w->acc_steps = 0;
+    GWZ_CUDA(cudaMalloc(&w->d_addr, sizeof(uint64_t) * w->n * m->W));
+    GWZ_CUDA(cudaMalloc(&w->d_acc, sizeof(double) * w->n * NUM_WALKER_ACC));
+    GWZ_CUDA(cudaMalloc(&w->d_vec, sizeof(double) * NUM_ACC));
+    DevBuf<uint64_t> d_start;
+    GWZ_CUDA(d_start.alloc(m->W));
+    GWZ_CUDA(cudaMemcpyAsync(d_start.p, start_addr, sizeof(uint64_t) * m->W, cudaMemcpyHostToDevice, c->stream));
+    GWZ_CUDA(launch_walker_init(w->d_addr, w->d_acc, w->n, m->W, d_start.p, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    *out = w;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
+    if (!w) return GWZ_OK;
+    cudaSetDevice(w->m->ctx->device);
+    cudaFree(w->d_addr);
+    cudaFree(w->d_acc);
+    cudaFree(w->d_partials);
+    cudaFree(w->d_vec);
+    delete w;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_walkers_count(const gwz_walkers* w, uint64_t* n_walkers, uint64_t* steps_done) {
+    GWZ_REQUIRE(w != nullptr, "gwz_walkers_count: NULL handle");
+    if (n_walkers) *n_walkers = w->n;
+    if (steps_done) *steps_done = w->steps_done;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_walkers_get_addresses(gwz_walkers* w, uint64_t* addr_words) {
+    GWZ_REQUIRE(w && addr_words, "gwz_walkers_get_addresses: NULL argument");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const int W = w->m->W;
+    DevBuf<uint64_t> tmp;
+    GWZ_CUDA(tmp.alloc(w->n * W));
+    GWZ_CUDA(launch_transpose_addr(w->d_addr, tmp.p, w->n, W, false, c->stream));
+    GWZ_CUDA(cudaMemcpyAsync(addr_words, tmp.p, sizeof(uint64_t) * w->n * W, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_walkers_set_addresses(gwz_walkers* w, const uint64_t* addr_words) {
+    GWZ_REQUIRE(w && addr_words, "gwz_walkers_set_addresses: NULL argument");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const int W = w->m->W;
+    DevBuf<uint64_t> tmp;
+    GWZ_CUDA(tmp.alloc(w->n * W));
+    GWZ_CUDA(cudaMemcpyAsync(tmp.p, addr_words, sizeof(uint64_t) * w->n * W, cudaMemcpyHostToDevice, c->stream));
+    GWZ_CUDA(launch_transpose_addr(tmp.p, w->d_addr, w->n, W, true, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_walkers_set_step_counter(gwz_walkers* w, uint64_t steps_done) {
+    GWZ_REQUIRE(w != nullptr, "gwz_walkers_set_step_counter: NULL handle");
+    w->steps_done = steps_done;
+    return GWZ_OK;
+}
+
+static int ensure_partials(gwz_walkers* w, int grid) {
+    if (grid > w->partials_cap) {
+        if (w->d_partials) cudaFree(w->d_partials);
+        w->d_partials = nullptr;
+        GWZ_CUDA(cudaMalloc(&w->d_partials, sizeof(double) * NUM_ACC * (size_t)grid));
+        w->partials_cap = grid;
+    }
+    return GWZ_OK;
+}
+
+// enqueue burn-in + sampling + per-set reduction on the set's stream (no sync)
+static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint64_t burn_in, int kind, unsigned flags,
+                       double* rec_tau, double* rec_eloc, uint64_t* rec_addr, bool time_it) {
+    gwz_model* m = w->m;
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const bool record = rec_tau != nullptr;
+    int grid = 0;
+    GWZ_CUDA(walker_grid(m->nw, kind, record, w->n, c->prop.multiProcessorCount, &grid));
+    if (int rc = ensure_partials(w, grid)) return rc;
+    WalkerLaunch L;
+    L.dm = m->dm;
+    L.tb = tb;
+    L.nw = m->nw;
+    L.kind = kind;
+    L.addr = w->d_addr;
+    L.acc = w->d_acc;
+    L.n = w->n;
+    L.global_offset = w->offset;
+    L.seed = w->seed;
+    L.partials = w->d_partials;
+    L.grid = grid;
+    L.err_flag = c->d_err;
+    L.rec_tau = nullptr;
+    L.rec_eloc = nullptr;
+    L.rec_addr = nullptr;
+    if (time_it) GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (burn_in > 0) {
+        L.step0 = w->steps_done;
+        L.steps = burn_in;
+        L.accumulate = 0;
+        L.reset_acc = 0;
+        int g2 = 0;
+        GWZ_CUDA(walker_grid(m->nw, kind, false, w->n, c->prop.multiProcessorCount, &g2));
+        L.grid = g2;
+        GWZ_CUDA(launch_walkers(L, c->stream));
+        w->steps_done += burn_in;
+        L.grid = grid;
+    }
+    const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
+    L.step0 = w->steps_done;
+    L.steps = steps;
+    L.accumulate = 1;
+    L.reset_acc = keep ? 0 : 1;
+    L.rec_tau = rec_tau;
+    L.rec_eloc = rec_eloc;
+    L.rec_addr = rec_addr;
+    GWZ_CUDA(launch_walkers(L, c->stream));
+    if (time_it) GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
+    w->steps_done += steps;
+    w->acc_steps = keep ? w->acc_steps + steps : steps;
+    GWZ_CUDA(launch_reduce_partials(w->d_partials, grid, NUM_ACC, w->d_vec, c->stream));
+    return GWZ_OK;
+}
+
+static void fill_result(const double* a, float ms, gwz_vqmc_result* out) {
+    const double nw = a[ACC_WALKERS];
+    const double val = a[ACC_VAL] / nw, grad = a[ACC_GRAD] / nw;
+    out->val = val;
+    out->grad[0] = grad;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    if (nw > 1.5) {
+        const double vv = (a[ACC_VAL2] / nw - val * val) * nw / (nw - 1.0);
+        const double gg = (a[ACC_GRAD2] / nw - grad * grad) * nw / (nw - 1.0);
+        out->err = std::sqrt(std::fmax(vv, 0.0) / nw);
+        out->grad_err[0] = std::sqrt(std::fmax(gg, 0.0) / nw);
+    } else {
+        out->err = nan;
+        out->grad_err[0] = nan;
+    }
+    const double T = a[ACC_T];
+    const double pe = a[ACC_TE] / T, pg = a[ACC_TG] / T;
+    out->pooled_val = pe;
+    out->pooled_grad[0] = 2.0 * (a[ACC_TGE] / T - pe * pg);
+    out->pooled_var = a[ACC_TEE] / T - pe * pe;
+    out->total_time = T;
+    out->walkers = (uint64_t)std::llround(nw);
+    out->steps = (uint64_t)std::llround(a[ACC_STEPS]);
+    out->hops = (uint64_t)std::llround(a[ACC_HOPS]);
+    for (int i = 0; i < NUM_ACC; ++i) out->acc[i] = a[i];
+    out->kernel_ms = ms;
+}
+
+// combine the per-set vectors: device sum within a context, NCCL all-reduce across contexts/ranks
+static int combine_and_fetch(gwz_walkers* const* ws, int n, gwz_vqmc_result* out) {
+    // group the sets by context (order of first appearance)
+    std::vector<gwz_context*> ctxs;
+    for (int i = 0; i < n; ++i) {
+        gwz_context* c = ws[i]->m->ctx;
+        bool seen = false;
+        for (auto* x : ctxs) seen |= (x == c);
+        if (!seen) ctxs.push_back(c);
+    }
+    for (gwz_context* c : ctxs) {
+        if (int rc = use_device(c)) return rc;
+        int rows = 0;
+        for (int i = 0; i < n; ++i)
+            if (ws[i]->m->ctx == c) {
+                GWZ_REQUIRE(rows < GROUP_ROWS, "gwz_vqmc_run_group: too many walker sets on one device");
+                GWZ_CUDA(cudaMemcpyAsync(c->d_group + (size_t)rows * NUM_ACC, ws[i]->d_vec, sizeof(double) * NUM_ACC,
+                                         cudaMemcpyDeviceToDevice, c->stream));
+                ++rows;
+            }
+        GWZ_CUDA(launch_reduce_partials(c->d_group, rows, NUM_ACC, c->d_acc, c->stream));
+    }
+    bool any_comm = false;
+    for (gwz_context* c : ctxs) any_comm |= (c->comm != nullptr);
+    GWZ_REQUIRE(ctxs.size() == 1 || any_comm,
+                "gwz_vqmc_run_group: walker sets on several devices need gwz_context_comm_init_all first");
+    if (any_comm) {
+        const NcclApi* api = nccl_api(nullptr);
+        if (!api) return fail(GWZ_ERR_NCCL, "NCCL unavailable");
+        for (gwz_context* c : ctxs) GWZ_REQUIRE(c->comm != nullptr, "gwz_vqmc_run_group: context without communicator");
+        GWZ_NCCL(api, api->GroupStart());
+        for (gwz_context* c : ctxs) {
+            // one ncclAllReduce(sum, float64, NUM_ACC) per run, on the sampling stream
+            int r = api->AllReduce(c->d_acc, c->d_acc, NUM_ACC, kNcclFloat64, kNcclSum, c->comm, c->stream);
+            if (r != kNcclSuccess) {
+                api->GroupEnd();
+                return fail(GWZ_ERR_NCCL, std::string("ncclAllReduce: ") + api->GetErrorString(r));
+            }
+        }
+        GWZ_NCCL(api, api->GroupEnd());
+    }
+    for (gwz_context* c : ctxs) {
+        if (int rc = use_device(c)) return rc;
+        GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * NUM_ACC, cudaMemcpyDeviceToHost, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    int status = GWZ_OK;
+    for (gwz_context* c : ctxs) {
+        if (int rc = use_device(c)) return rc;
+        GWZ_CUDA(cudaStreamSynchronize(c->stream));
+        if (int rc = check_err_flag(c)) status = rc;
+    }
+    if (status) return status;
+    float ms = 0.f;
+    {
+        gwz_context* c0 = ws[0]->m->ctx;
+        if (int rc = use_device(c0)) return rc;
+        GWZ_CUDA(cudaEventElapsedTime(&ms, c0->ev0, c0->ev1));
+    }
+    if (out) fill_result(ctxs[0]->h_acc, ms, out);
+    return GWZ_OK;
+}
+
+extern "C" int gwz_vqmc_run_group(gwz_walkers* const* ws, int n, const double* params, uint64_t steps_per_walker,
+                                  uint64_t burn_in, int kernel_kind, unsigned flags, gwz_vqmc_result* out) {
+    GWZ_REQUIRE(ws && n >= 1 && params, "gwz_vqmc_run_group: bad arguments");
+    GWZ_REQUIRE(steps_per_walker >= 1, "gwz_vqmc_run: steps_per_walker must be >= 1");
+    GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
+                "gwz_vqmc_run: unknown kernel_kind");
+    for (int i = 0; i < n; ++i) GWZ_REQUIRE(ws[i] != nullptr, "gwz_vqmc_run_group: NULL walker set");
+    GWZ_REQUIRE(std::isfinite(params[0]), "gwz_vqmc_run: non-finite parameter");
+    DevTables tb;
+    make_tables(ws[0]->m, params[0], &tb);
+    bool timed_first = false;
+    std::vector<gwz_context*> timed;
+    for (int i = 0; i < n; ++i) {
+        GWZ_REQUIRE(ws[i]->m->N == ws[0]->m->N && ws[i]->m->M == ws[0]->m->M && ws[i]->m->u == ws[0]->m->u &&
+                        ws[i]->m->t == ws[0]->m->t,
+                    "gwz_vqmc_run_group: walker sets belong to different models");
+        const bool time_it = (i == 0);
+        timed_first |= time_it;
+        if (int rc = enqueue_run(ws[i], tb, steps_per_walker, burn_in, kernel_kind, flags, nullptr, nullptr, nullptr,
+                                 time_it))
+            return rc;
+    }
+    return combine_and_fetch(ws, n, out);
+}
+
+extern "C" int gwz_vqmc_run(gwz_walkers* w, const double* params, uint64_t steps_per_walker, uint64_t burn_in,
+                            int kernel_kind, unsigned flags, gwz_vqmc_result* out) {
+    gwz_walkers* one[1] = {w};
+    return gwz_vqmc_run_group(one, 1, params, steps_per_walker, burn_in, kernel_kind, flags, out);
+}
+
+extern "C" int gwz_walkers_estimates(gwz_walkers* w, double* val_w, double* grad_w) {
+    GWZ_REQUIRE(w != nullptr, "gwz_walkers_estimates: NULL handle");
+    GWZ_REQUIRE(w->acc_steps > 0, "gwz_walkers_estimates: no steps accumulated yet");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    DevBuf<double> d_v, d_g;
+    GWZ_CUDA(d_v.alloc(w->n));
+    GWZ_CUDA(d_g.alloc(w->n));
+    GWZ_CUDA(launch_walker_estimates(w->d_acc, w->n, d_v.p, d_g.p, c->stream));
+    if (val_w) GWZ_CUDA(cudaMemcpyAsync(val_w, d_v.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
+    if (grad_w) GWZ_CUDA(cudaMemcpyAsync(grad_w, d_g.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_t steps, int kernel_kind, unsigned flags,
+                                   double* tau, double* eloc, uint64_t* addr, gwz_vqmc_result* out) {
+    GWZ_REQUIRE(w && params && tau && eloc, "gwz_vqmc_run_record: NULL argument");
+    GWZ_REQUIRE(steps >= 1, "gwz_vqmc_run_record: steps_per_walker must be >= 1");
+    GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
+                "gwz_vqmc_run_record: unknown kernel_kind");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const size_t cells = (size_t)steps * w->n;
+    DevBuf<double> d_tau, d_eloc;
+    DevBuf<uint64_t> d_addr;
+    GWZ_CUDA(d_tau.alloc(cells));
+    GWZ_CUDA(d_eloc.alloc(cells));
+    if (addr) GWZ_CUDA(d_addr.alloc(cells * w->m->W));
+    DevTables tb;
+    make_tables(w->m, params[0], &tb);
+    if (int rc = enqueue_run(w, tb, steps, 0, kernel_kind, flags, d_tau.p, d_eloc.p, addr ? d_addr.p : nullptr, true))
+        return rc;
+    GWZ_CUDA(cudaMemcpyAsync(tau, d_tau.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaMemcpyAsync(eloc, d_eloc.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
+    if (addr)
+        GWZ_CUDA(cudaMemcpyAsync(addr, d_addr.p, sizeof(uint64_t) * cells * w->m->W, cudaMemcpyDeviceToHost, c->stream));
+    gwz_walkers* one[1] = {w};
+    return combine_and_fetch(one, 1, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// sweep
+// ------------------------------------------------------------------------------------------
+extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint64_t dim, uint64_t rank_begin,
+                                uint64_t rank_end, gwz_sweep** out) {
+    GWZ_REQUIRE(m && out, "gwz_sweep_create: NULL argument");
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    gwz_sweep* s = new gwz_sweep();
+    s->m = m;
+    if (basis_words) {
+        GWZ_REQUIRE(dim >= 1, "gwz_sweep_create: empty basis");
+        s->dim = dim;
+        const int W = m->W;
+        GWZ_CUDA(cudaMalloc(&s->d_basis, sizeof(uint64_t) * dim * W));
+        if (W == 1) {
+            GWZ_CUDA(cudaMemcpyAsync(s->d_basis, basis_words, sizeof(uint64_t) * dim, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            DevBuf<uint64_t> tmp;
+            GWZ_CUDA(tmp.alloc(dim * W));
+            GWZ_CUDA(cudaMemcpyAsync(tmp.p, basis_words, sizeof(uint64_t) * dim * W, cudaMemcpyHostToDevice, c->stream));
+            GWZ_CUDA(launch_transpose_addr(tmp.p, s->d_basis, dim, W, true, c->stream));
+            GWZ_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    } else {
+        GWZ_REQUIRE(m->B <= 64, "gwz_sweep_create: ranked enumeration needs N+M-1 <= 64 bits");
+        std::vector<uint64_t> tab;
+        binomial_table(tab);
+        const uint64_t total = tab[m->B * 65 + m->N];
+        GWZ_REQUIRE(total != UINT64_MAX, "gwz_sweep_create: dimension overflows 64 bits");
+        if (rank_end == 0) rank_end = total;
+        GWZ_REQUIRE(rank_begin < rank_end && rank_end <= total, "gwz_sweep_create: bad rank range");
+        s->dim = rank_end - rank_begin;
+        s->rank_begin = rank_begin;
+        GWZ_CUDA(cudaMalloc(&s->d_binom, sizeof(uint64_t) * 65 * 65));
+        GWZ_CUDA(cudaMemcpyAsync(s->d_binom, tab.data(), sizeof(uint64_t) * 65 * 65, cudaMemcpyHostToDevice, c->stream));
+    }
+    GWZ_CUDA(sweep_grid(m->nw, s->d_basis == nullptr, s->dim, c->prop.multiProcessorCount, &s->grid, &s->chunk));
+    GWZ_CUDA(cudaMalloc(&s->d_partials, sizeof(double) * 4 * (size_t)s->grid));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    *out = s;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
+    if (!s) return GWZ_OK;
+    cudaSetDevice(s->m->ctx->device);
+    cudaFree(s->d_basis);
+    cudaFree(s->d_binom);
+    cudaFree(s->d_partials);
+    delete s;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_sweep_dim(const gwz_sweep* s, uint64_t* dim) {
+    GWZ_REQUIRE(s && dim, "gwz_sweep_dim: NULL argument");
+    *dim = s->dim;
+    return GWZ_OK;
+}
+
+static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
+    gwz_model* m = s->m;
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    GWZ_REQUIRE(std::isfinite(params[0]), "gwz_sweep: non-finite parameter");
+    SweepLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    L.dm = m->dm;
+    make_tables(m, params[0], &L.tb);
+    L.nw = m->nw;
+    L.basis = s->d_basis;
+    L.dim = s->dim;
+    L.rank_begin = s->rank_begin;
+    L.binom = s->d_binom;
+    L.with_grad = 1;
+    L.partials = s->d_partials;
+    L.grid = s->grid;
+    L.chunk = s->chunk;
+    GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    GWZ_CUDA(launch_sweep(L, c->stream));
+    GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
+    GWZ_CUDA(launch_reduce_partials(s->d_partials, s->grid, 4, c->d_acc, c->stream));
+    if (c->comm) {
+        const NcclApi* api = nccl_api(nullptr);
+        if (!api) return fail(GWZ_ERR_NCCL, "NCCL unavailable");
+        GWZ_NCCL(api, api->AllReduce(c->d_acc, c->d_acc, 4, kNcclFloat64, kNcclSum, c->comm, c->stream));
+    }
+    GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    GWZ_CUDA(cudaEventElapsedTime(&s->last_ms, c->ev0, c->ev1));
+    for (int i = 0; i < 4; ++i) acc4[i] = c->h_acc[i];
+    return GWZ_OK;
+}
+
+extern "C" int gwz_sweep_val_and_grad(gwz_sweep* s, const double* params, double* val, double* grad, double* acc4) {
+    GWZ_REQUIRE(s && params, "gwz_sweep_val_and_grad: NULL argument");
+    double a[4];
+    if (int rc = sweep_run(s, params, a)) return rc;
+    const double num = a[0], den = a[1], ng = a[2], dg = a[3];
+    if (val) *val = num / den;                                   // localenergy.jl:126
+    if (grad) grad[0] = (ng * den - num * dg) / (den * den);      // localenergy.jl:127
+    if (acc4)
+        for (int i = 0; i < 4; ++i) acc4[i] = a[i];
+    return GWZ_OK;
+}
+
+extern "C" int gwz_sweep_val(gwz_sweep* s, const double* params, double* val) {
+    GWZ_REQUIRE(val != nullptr, "gwz_sweep_val: val is NULL");
+    return gwz_sweep_val_and_grad(s, params, val, nullptr, nullptr);
+}
+
+static int sweep_terms_impl(gwz_sweep* s, const double* params, uint64_t first, uint64_t count, double* out,
+                            uint64_t* states) {
+    GWZ_REQUIRE(first <= s->dim && count <= s->dim - first, "gwz_sweep_terms: range outside the sweep");
+    if (count == 0) return GWZ_OK;
+    gwz_model* m = s->m;
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    DevBuf<double> d_out;
+    DevBuf<uint64_t> d_states;
+    if (out) GWZ_CUDA(d_out.alloc(count * 4));
+    if (states) GWZ_CUDA(d_states.alloc(count * m->W));
+    SweepLaunch L;
+    std::memset(&L, 0, sizeof(L));
+    L.dm = m->dm;
+    make_tables(m, params ? params[0] : 0.0, &L.tb);
+    L.nw = m->nw;
+    L.basis = s->d_basis;
+    L.dim = s->dim;
+    L.rank_begin = s->rank_begin;
+    L.binom = s->d_binom;
+    L.first = first;
+    L.count = count;
+    L.terms_out = out ? d_out.p : nullptr;
+    L.states_out = states ? d_states.p : nullptr;
+    GWZ_CUDA(launch_sweep_terms(L, c->stream));
+    if (out) GWZ_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * count * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (states)
+        GWZ_CUDA(cudaMemcpyAsync(states, d_states.p, sizeof(uint64_t) * count * m->W, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_sweep_terms(gwz_sweep* s, const double* params, uint64_t first, uint64_t count, double* out) {
+    GWZ_REQUIRE(s && params && out, "gwz_sweep_terms: NULL argument");
+    return sweep_terms_impl(s, params, first, count, out, nullptr);
+}
+extern "C" int gwz_sweep_states(gwz_sweep* s, uint64_t first, uint64_t count, uint64_t* out) {
+    GWZ_REQUIRE(s && out, "gwz_sweep_states: NULL argument");
+    return sweep_terms_impl(s, nullptr, first, count, nullptr, out);
+}
+extern "C" int gwz_sweep_last_kernel_ms(const gwz_sweep* s, float* ms) {
+    GWZ_REQUIRE(s && ms, "gwz_sweep_last_kernel_ms: NULL argument");
+    *ms = s->last_ms;
+    return GWZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// optimiser driver (src/amsgrad.jl:117-226): O(np) host arithmetic around the GPU objective
+// ------------------------------------------------------------------------------------------
+extern "C" int gwz_gd_opts_default(gwz_gd_opts* o) {
+    GWZ_REQUIRE(o != nullptr, "gwz_gd_opts_default: NULL argument");
+    std::memset(o, 0, sizeof(*o));
+    o->maxiter = 100;
+    o->use_amsgrad = 1;
+    o->early_stop = 1;
+    o->alpha = 0.01;
+    o->beta1 = 0.1;
+    o->beta2 = 0.01;
+    const double tol = std::sqrt(std::numeric_limits<double>::epsilon());
+    o->grad_tol = o->param_tol = o->val_tol = tol;
+    o->err_tol = 0.0;
+    return GWZ_OK;
+}
+
+extern "C" int gwz_adaptive_gradient_descent(gwz_objective_fn f_vg, gwz_objective_fn f_veg, void* user, const double* p0,
+                                             int np, const gwz_gd_opts* o, gwz_gd_trace* tr) {
+    GWZ_REQUIRE(f_vg && f_veg && p0 && o && tr && np >= 1, "gwz_adaptive_gradient_descent: bad arguments");
+    GWZ_REQUIRE(tr->param && tr->value && tr->error && tr->gradient && tr->first_moment && tr->second_moment &&
+                    tr->param_delta,
+                "gwz_adaptive_gradient_descent: trace buffers must be allocated by the caller");
+    GWZ_REQUIRE(o->maxiter >= 0, "gwz_adaptive_gradient_descent: maxiter < 0");
+    std::vector<double> p(p0, p0 + np), grad(np), m1(np), m2(np), dp(np);
+    double val = 0.0, err = 0.0, old_val = std::numeric_limits<double>::infinity();
+    if (int rc = f_vg(user, p.data(), np, &val, &err, grad.data())) return rc;  // amsgrad.jl:136
+    for (int i = 0; i < np; ++i) {
+        m1[i] = o->first_moment_init ? o->first_moment_init[i] : grad[i];
+        m2[i] = o->second_moment_init ? o->second_moment_init[i] : 0.0;
+    }
+    int iter = 0, rows = 0;
+    tr->converged = 0;
+    tr->reason = 0;
+    tr->np = np;
+    while (iter <= o->maxiter) {  // amsgrad.jl:166 (maxiter+1 evaluations)
+        ++iter;
+        if (int rc = f_veg(user, p.data(), np, &val, &err, grad.data())) return rc;  // :168
+        double ndp = 0.0, ngrad = 0.0;
+        for (int i = 0; i < np; ++i) {
+            if (o->use_amsgrad) {  // :260-261
+                m1[i] = (1 - o->beta1) * m1[i] + o->beta1 * grad[i];
+                const double cand = (1 - o->beta2) * m2[i] + o->beta2 * (grad[i] * grad[i]);
+                m2[i] = cand > m2[i] ? cand : m2[i];
+            } else {  // :241-242
+                m1[i] = grad[i];
+                m2[i] = 1.0;
+            }
+            const double nf = (o->fix_params && o->fix_params[i]) ? 0.0 : 1.0;
+            grad[i] = grad[i] * nf;                                  // :171
+            dp[i] = nf * -(o->alpha * m1[i] / std::sqrt(m2[i]));     // :173
+            ndp += dp[i] * dp[i];
+            ngrad += grad[i] * grad[i];
+        }
+        const double dval = old_val - val;
+        old_val = val;
+        std::memcpy(tr->param + (size_t)rows * np, p.data(), sizeof(double) * np);
+        tr->value[rows] = val;
+        tr->error[rows] = err;
+        std::memcpy(tr->gradient + (size_t)rows * np, grad.data(), sizeof(double) * np);
+        std::memcpy(tr->first_moment + (size_t)rows * np, m1.data(), sizeof(double) * np);
+        std::memcpy(tr->second_moment + (size_t)rows * np, m2.data(), sizeof(double) * np);
+        std::memcpy(tr->param_delta + (size_t)rows * np, dp.data(), sizeof(double) * np);
+        ++rows;
+        if (o->early_stop) {  // :185-210
+            if (std::sqrt(ndp) < o->param_tol) { tr->reason = 1; tr->converged = 1; break; }
+            if (std::sqrt(ngrad) < o->grad_tol) { tr->reason = 2; tr->converged = 1; break; }
+            if (std::fabs(dval) < o->val_tol) { tr->reason = 3; tr->converged = 1; break; }
+            if (std::fabs(dval) < err * o->err_tol) { tr->reason = 4; tr->converged = 1; break; }
+        }
+        for (int i = 0; i < np; ++i) p[i] = p[i] + dp[i];  // :212
+    }
+    tr->iterations = rows;
+    return GWZ_OK;
+}
+
+struct VqmcObjective {
+    gwz_walkers* w;
+    uint64_t steps;
+    int kind;
+};
+static int vqmc_objective(void* user, const double* p, int, double* val, double* err, double* grad) {
+    // val_err_and_grad(qmc::KineticVQMC, p): _reset! keeps walker positions, clears the estimators
+    // (wrapper.jl:74-79,98-105)
+    VqmcObjective* o = (VqmcObjective*)user;
+    gwz_vqmc_result r;
+    if (int rc = gwz_vqmc_run(o->w, p, o->steps, 0, o->kind, 0u, &r)) return rc;
+    *val = r.val;
+    *err = std::isnan(r.err) ? 0.0 : r.err;
+    grad[0] = r.grad[0];
+    return GWZ_OK;
+}
+extern "C" int gwz_amsgrad_vqmc(gwz_walkers* w, const double* p0, const gwz_gd_opts* opts, uint64_t steps_per_walker,
+                                int kernel_kind, gwz_gd_trace* trace) {
+    GWZ_REQUIRE(w && p0 && opts && trace, "gwz_amsgrad_vqmc: NULL argument");
+    VqmcObjective o{w, steps_per_walker, kernel_kind};
+    return gwz_adaptive_gradient_descent(vqmc_objective, vqmc_objective, &o, p0, GWZ_NUM_PARAMS, opts, trace);
+}
+static int sweep_objective(void* user, const double* p, int, double* val, double* err, double* grad) {
+    *err = 0.0;  // abstract.jl:59-62
+    return gwz_sweep_val_and_grad((gwz_sweep*)user, p, val, grad, nullptr);
+}
+extern "C" int gwz_amsgrad_sweep(gwz_sweep* s, const double* p0, const gwz_gd_opts* opts, gwz_gd_trace* trace) {
+    GWZ_REQUIRE(s && p0 && opts && trace, "gwz_amsgrad_sweep: NULL argument");
+    return gwz_adaptive_gradient_descent(sweep_objective, sweep_objective, s, p0, GWZ_NUM_PARAMS, opts, trace);
+}

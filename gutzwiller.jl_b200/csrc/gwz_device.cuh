@@ -1,0 +1,557 @@
+// gwz_device.cuh -- device-side building blocks shared by the probe, walker and sweep kernels.
+//
+// State representation: a BoseFS{N,M} address is a unary ("stars and bars") bitstring of
+// B = N+M-1 bits (Rimu BitString).  On the device it lives in NW 32-bit
+// registers per thread (statically indexed, fully unrolled), extended to
+//     e = a | bit B = 0 (virtual separator closing mode M) | K low bits of a above it
+// so that the periodic bond (M,1) looks like any other bond.
+//
+// A *bond* is a 0 bit of e at position z in [0,B]: L(z) = run of ones directly below it =
+// occupation of mode i, R(z) = run directly above = occupation of mode i+1.  The two hops of
+// offdiagonals(H,a) (Rimu hopnextneighbour; App. A.4) that cross the bond are
+//     right  i -> i+1   if L>0:  Delta = R-L+1,  melem = -t*sqrt(L*(R+1))
+//     left   i+1 -> i   if R>0:  Delta = L-R+1,  melem = -t*sqrt(R*(L+1))
+// and for GutzwillerAnsatz psi(new)/psi(a) = exp(-g*u*Delta) (gutzwiller.jl:34-36 with
+// diagonal_element = u*sum n(n-1)/2).  kinetic_sample! (qmc.jl:14-44) then reduces to sums over
+// bonds of functions of (L,R).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gwz {
+
+constexpr int KCAP = 4;             // bond classes with L,R in 0..KCAP-1 are counted bit-parallel
+constexpr int NCLS = KCAP * KCAP;   // class id = L*KCAP + R
+constexpr int MAXNW = 8;            // 32-bit words of the extended string (B + 1 + KCAP <= 256)
+
+struct DevModel {
+    int N, M, B;   // particles, modes, bits
+    int W;         // 64-bit words per stored address
+    int ext_ws;    // (B+1) >> 5 : word of the first extension bit
+    int ext_bs;    // (B+1) & 31
+    double u, t;
+    uint32_t zmask[MAXNW];  // bits 0..B   (bond positions)
+    uint32_t amask[MAXNW];  // bits 0..B-1 (address bits)
+};
+
+// Everything that depends on the variational parameter g; passed by value as a kernel
+// argument so that statically indexed entries become constant-bank operands.
+struct DevTables {
+    double g;            // params[1]
+    double c;            // g*u
+    double FS[NCLS];     // sum of the (<=2) hop rates of a bond of class (L,R)
+    double FE[NCLS];     // sum of sqrt(n_src*(n_dst+1))*rate
+    double FD[NCLS];     // sum of sqrt(..)*rate*Delta        (gradient of the sweep)
+    double RR[NCLS];     // rate of the right hop (0 if L==0)
+    double RL[NCLS];     // rate of the left hop  (0 if R==0)
+    double IRR[NCLS];    // 1/RR (0 if RR==0)
+    double IRL[NCLS];
+};
+
+// ------------------------------------------------------------------------------------------
+// multi-word helpers (NW compile-time, arrays stay in registers)
+// ------------------------------------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void shl1(const uint32_t (&x)[NW], uint32_t (&o)[NW]) {
+#pragma unroll
+    for (int i = NW - 1; i > 0; --i) o[i] = __funnelshift_l(x[i - 1], x[i], 1);
+    o[0] = x[0] << 1;
+}
+template <int NW>
+__device__ __forceinline__ void shr1(const uint32_t (&x)[NW], uint32_t (&o)[NW]) {
+#pragma unroll
+    for (int i = 0; i < NW - 1; ++i) o[i] = __funnelshift_r(x[i], x[i + 1], 1);
+    o[NW - 1] = x[NW - 1] >> 1;
+}
+// flip bit p (dynamic) of a register array
+template <int NW>
+__device__ __forceinline__ void flip_bit(uint32_t (&x)[NW], int p) {
+    const int w = p >> 5;
+    const uint32_t m = 1u << (p & 31);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) x[i] ^= (i == w) ? m : 0u;
+}
+template <int NW>
+__device__ __forceinline__ int get_bit(const uint32_t (&x)[NW], int p) {
+    const int w = p >> 5;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) v = (i == w) ? x[i] : v;
+    return (v >> (p & 31)) & 1;
+}
+// j-th (0-based) set bit of a 32-bit word; requires j < popc(x)
+__device__ __forceinline__ int nth_set_bit32(uint32_t x, int j) {
+    int pos = 0;
+    int c;
+    c = __popc(x & 0xFFFFu); if (j >= c) { j -= c; pos += 16; x >>= 16; }
+    c = __popc(x & 0xFFu);   if (j >= c) { j -= c; pos += 8;  x >>= 8; }
+    c = __popc(x & 0xFu);    if (j >= c) { j -= c; pos += 4;  x >>= 4; }
+    c = __popc(x & 0x3u);    if (j >= c) { j -= c; pos += 2;  x >>= 2; }
+    c = x & 1u;              if (j >= c) { pos += 1; }
+    return pos;
+}
+__device__ __forceinline__ double int_to_double_fast(int c) {
+    // exact for 0 <= c < 2^31: one DADD instead of an XU-pipe I2F.F64
+    return __hiloint2double(0x43300000, c) - 4503599627370496.0;
+}
+
+// load a stored address (W 64-bit words, word-major SoA: words[w*stride + idx]) into NW regs
+template <int NW>
+__device__ __forceinline__ void load_addr_soa(const uint64_t* __restrict__ words, size_t stride, size_t idx,
+                                              int W, uint32_t (&a)[NW]) {
+#pragma unroll
+    for (int i = 0; i < (NW + 1) / 2; ++i) {
+        uint64_t v = (i < W) ? words[(size_t)i * stride + idx] : 0ull;
+        a[2 * i] = (uint32_t)v;
+        if (2 * i + 1 < NW) a[2 * i + 1] = (uint32_t)(v >> 32);
+    }
+}
+template <int NW>
+__device__ __forceinline__ void store_addr_soa(uint64_t* __restrict__ words, size_t stride, size_t idx, int W,
+                                               const uint32_t (&a)[NW]) {
+#pragma unroll
+    for (int i = 0; i < (NW + 1) / 2; ++i) {
+        uint64_t v = a[2 * i];
+        if (2 * i + 1 < NW) v |= (uint64_t)a[2 * i + 1] << 32;
+        if (i < W) words[(size_t)i * stride + idx] = v;
+    }
+}
+// array-of-addresses layout (n x W), used at the API boundary
+template <int NW>
+__device__ __forceinline__ void load_addr_aos(const uint64_t* __restrict__ words, size_t idx, int W,
+                                              uint32_t (&a)[NW]) {
+#pragma unroll
+    for (int i = 0; i < (NW + 1) / 2; ++i) {
+        uint64_t v = (i < W) ? words[idx * (size_t)W + i] : 0ull;
+        a[2 * i] = (uint32_t)v;
+        if (2 * i + 1 < NW) a[2 * i + 1] = (uint32_t)(v >> 32);
+    }
+}
+template <int NW>
+__device__ __forceinline__ void store_addr_aos(uint64_t* __restrict__ words, size_t idx, int W,
+                                               const uint32_t (&a)[NW]) {
+#pragma unroll
+    for (int i = 0; i < (NW + 1) / 2; ++i) {
+        uint64_t v = a[2 * i];
+        if (2 * i + 1 < NW) v |= (uint64_t)a[2 * i + 1] << 32;
+        if (i < W) words[idx * (size_t)W + i] = v;
+    }
+}
+
+// e = a with the K low bits of a replicated above the virtual separator at bit B
+template <int NW>
+__device__ __forceinline__ void extend(const uint32_t (&a)[NW], const DevModel& dm, uint32_t (&e)[NW]) {
+    const uint32_t low = a[0] & ((1u << KCAP) - 1u);
+    const uint32_t lo_part = low << dm.ext_bs;
+    const uint32_t hi_part = dm.ext_bs ? (low >> (32 - dm.ext_bs)) : 0u;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        uint32_t v = a[i];
+        v |= (i == dm.ext_ws) ? lo_part : 0u;
+        v |= (i == dm.ext_ws + 1) ? hi_part : 0u;
+        e[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// hop application (App. A.1): bond at zero position z, direction right (i -> i+1) or left
+// ------------------------------------------------------------------------------------------
+template <int NW>
+__device__ __forceinline__ void apply_hop(uint32_t (&a)[NW], const DevModel& dm, int z, bool right) {
+    if (z != dm.B) {
+        // right: bits (z-1, z) = (1,0) -> (0,1);  left: bits (z, z+1) = (0,1) -> (1,0)
+        const int p = right ? z - 1 : z;
+        flip_bit<NW>(a, p);
+        flip_bit<NW>(a, p + 1);
+    } else if (right) {
+        // mode M -> mode 1: ((a << 1) | 1) & mask(B)
+        uint32_t o[NW];
+        shl1<NW>(a, o);
+        o[0] |= 1u;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a[i] = o[i] & dm.amask[i];
+    } else {
+        // mode 1 -> mode M: (a >> 1) | (1 << (B-1))
+        uint32_t o[NW];
+        shr1<NW>(a, o);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a[i] = o[i];
+        flip_bit<NW>(a, dm.B - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic run lengths around a bond (slow path, any occupation): operate on a local copy so
+// that the register-resident arrays never get dynamically indexed
+// ------------------------------------------------------------------------------------------
+static __device__ __noinline__ void bond_runs_generic(const uint32_t* t, int B, int z, int& L, int& R) {
+    // ones directly below z
+    int n = 0;
+    int p = z - 1;
+    while (p >= 0) {
+        const int w = p >> 5, b = p & 31;
+        const uint32_t x = ~(t[w] << (31 - b));      // leading zeros of x = leading ones of the window
+        int c = x ? __clz(x) : 32;
+        c = min(c, b + 1);
+        n += c;
+        if (c < b + 1) break;
+        p -= c;
+    }
+    L = n;
+    // ones directly above z; for the virtual separator (z == B) this is mode 1 = trailing ones of a.
+    // e has bit B == 0, so the scan stops at B at the latest.
+    n = 0;
+    p = (z == B) ? 0 : z + 1;
+    while (p < B) {
+        const int w = p >> 5, b = p & 31;
+        const uint32_t x = ~(t[w] >> b);             // trailing zeros of x = trailing ones of the window
+        int c = x ? (__ffs(x) - 1) : 32;
+        c = min(c, 32 - b);
+        c = min(c, B - p);
+        n += c;
+        if (c < 32 - b || p + c >= B) break;
+        p += c;
+    }
+    R = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bond classification: EL[l] / ER[r] = bonds whose lower / upper run has length exactly l / r
+// (l, r < KCAP); big = bonds with a run >= KCAP on either side.
+// ------------------------------------------------------------------------------------------
+template <int NW>
+struct BondMasks {
+    uint32_t EL[KCAP][NW];
+    uint32_t ER[KCAP][NW];
+    uint32_t big[NW];
+};
+
+template <int NW>
+__device__ __forceinline__ void classify_bonds(const uint32_t (&e)[NW], const DevModel& dm, BondMasks<NW>& bm) {
+    uint32_t Z[NW], cur[NW], nxt[NW], sh[NW], bigL[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) Z[i] = ~e[i] & dm.zmask[i];
+    // lower runs: L_1 = e << 1, L_{k+1} = L_k & (L_k << 1)
+    shl1<NW>(e, cur);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) bm.EL[0][i] = Z[i] & ~cur[i];
+#pragma unroll
+    for (int k = 1; k < KCAP; ++k) {
+        shl1<NW>(cur, sh);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            nxt[i] = cur[i] & sh[i];
+            bm.EL[k][i] = Z[i] & cur[i] & ~nxt[i];
+            cur[i] = nxt[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) bigL[i] = Z[i] & cur[i];
+    // upper runs
+    shr1<NW>(e, cur);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) bm.ER[0][i] = Z[i] & ~cur[i];
+#pragma unroll
+    for (int k = 1; k < KCAP; ++k) {
+        shr1<NW>(cur, sh);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            nxt[i] = cur[i] & sh[i];
+            bm.ER[k][i] = Z[i] & cur[i] & ~nxt[i];
+            cur[i] = nxt[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) bm.big[i] = bigL[i] | (Z[i] & cur[i]);
+}
+
+// Per-address quantities of kinetic_sample! / LocalEnergyEvaluator
+struct BondSums {
+    double S;        // sum of hop rates             -> residence time 1/S      (qmc.jl:27,33)
+    double E;        // sum sqrt(n_src (n_dst+1)) * rate -> E_loc = D - t*E     (qmc.jl:28,37)
+    double ED;       // sum sqrt(..) * rate * Delta  (sweep gradient only)
+    long long d;     // sum_i n_i (n_i - 1) / 2      -> D = u*d                 (App. A.3)
+    int nocc;        // occupied modes, n_hops = 2*nocc                         (qmc.jl:15)
+};
+
+// rates of one generic bond
+__device__ __forceinline__ void generic_bond_terms(int L, int R, double c, double& rr, double& rl, double& er,
+                                                   double& el) {
+    rr = (L > 0) ? exp(-c * (double)(R - L + 1)) : 0.0;
+    rl = (R > 0) ? exp(-c * (double)(L - R + 1)) : 0.0;
+    er = (L > 0) ? sqrt((double)L * (double)(R + 1)) * rr : 0.0;
+    el = (R > 0) ? sqrt((double)R * (double)(L + 1)) * rl : 0.0;
+}
+
+// Sum over all bonds.  cum[k] = running sum of class weights cnt[k]*FS[k] (k ascending), kept for
+// the class-ordered move selection.  WITH_GRAD adds the ED sum needed by the sweep gradient.
+template <int NW, bool WITH_GRAD>
+__device__ __forceinline__ void bond_sums(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
+                                          const BondMasks<NW>& bm, double (&cum)[NCLS], BondSums& out,
+                                          double& big_S) {
+    double S = 0.0, E = 0.0, ED = 0.0;
+    int nocc = 0;
+    int dd = 0;
+#pragma unroll
+    for (int l = 0; l < KCAP; ++l) {
+        int rowcnt = 0;
+#pragma unroll
+        for (int r = 0; r < KCAP; ++r) {
+            const int k = l * KCAP + r;
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) c += __popc(bm.EL[l][i] & bm.ER[r][i]);
+            const double cd = int_to_double_fast(c);
+            S = fma(cd, tb.FS[k], S);
+            E = fma(cd, tb.FE[k], E);
+            if (WITH_GRAD) ED = fma(cd, tb.FD[k], ED);
+            cum[k] = S;
+            rowcnt += c;
+        }
+        if (l > 0) nocc += rowcnt;
+        dd += rowcnt * (l * (l - 1) / 2);
+    }
+    long long d = dd;
+    // rare: bonds next to a mode with >= KCAP particles
+    double bS = 0.0;
+    uint32_t any_big = 0u;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) any_big |= bm.big[i];
+    if (any_big) {
+        uint32_t tmp[NW];  // local copy: only this array gets dynamically indexed
+#pragma unroll
+        for (int i = 0; i < NW; ++i) tmp[i] = e[i];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t m = bm.big[i];
+            while (m) {
+                const int z = 32 * i + (__ffs(m) - 1);
+                m &= m - 1;
+                int L, R;
+                bond_runs_generic(tmp, dm.B, z, L, R);
+                double rr, rl, er, el;
+                generic_bond_terms(L, R, tb.c, rr, rl, er, el);
+                bS += rr;
+                bS += rl;
+                E += er + el;
+                if (WITH_GRAD) ED += er * (double)(R - L + 1) + el * (double)(L - R + 1);
+                nocc += (L > 0);
+                d += (long long)L * (L - 1) / 2;
+            }
+        }
+    }
+    big_S = bS;
+    out.S = S + bS;
+    out.E = E;
+    out.ED = ED;
+    out.d = d;
+    out.nocc = nocc;
+}
+
+// Class-ordered move selection: partition [0,S) into consecutive intervals, one per hop, ordered
+// by (class id, direction right-then-left, bond position), big bonds last.  T in [0,S).
+// Returns the bond position z and the direction.
+template <int NW>
+__device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
+                                            const BondMasks<NW>& bm, const double (&cum)[NCLS], double big_S,
+                                            double T, int& z_out, bool& right_out) {
+    const double reg_total = cum[NCLS - 1];
+    if (T < reg_total || !(big_S > 0.0)) {
+        if (!(T < reg_total)) T = __longlong_as_double(__double_as_longlong(reg_total) - 1);
+        int idx = 0;
+        double base = 0.0;
+#pragma unroll
+        for (int k = 0; k < NCLS - 1; ++k) {
+            const bool ge = (T >= cum[k]);
+            idx += ge ? 1 : 0;
+            base = ge ? cum[k] : base;
+        }
+        const int l = idx >> 2, r = idx & 3;  // KCAP == 4
+        static_assert(KCAP == 4, "class id decoding assumes KCAP == 4");
+        // masks of class (l,r), their popcounts
+        uint32_t m[NW];
+        int pc[NW];
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t el = bm.EL[0][i], er = bm.ER[0][i];
+#pragma unroll
+            for (int q = 1; q < KCAP; ++q) {
+                el = (l == q) ? bm.EL[q][i] : el;
+                er = (r == q) ? bm.ER[q][i] : er;
+            }
+            m[i] = el & er;
+            pc[i] = __popc(m[i]);
+            c += pc[i];
+        }
+        const double cd = int_to_double_fast(c);
+        const double t = T - base;
+        const double wR = cd * tb.RR[idx];
+        const bool right = (t < wR) || (r == 0);
+        int j = right ? (int)(t * tb.IRR[idx]) : (int)((t - wR) * tb.IRL[idx]);
+        j = max(0, min(j, c - 1));
+        // j-th bond of the class
+        int pos = 0;
+        uint32_t word = m[NW - 1];
+        bool found = false;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const bool here = !found && (j < pc[i]);
+            word = here ? m[i] : word;
+            pos = here ? 32 * i : pos;
+            found = found || here;
+            j -= found ? 0 : pc[i];
+        }
+        z_out = pos + nth_set_bit32(word, j);
+        right_out = right;
+    } else {
+        // walk the big bonds in the same order as bond_sums
+        const double t = T - reg_total;
+        double acc = 0.0;
+        int zsel = -1;
+        bool rsel = true;
+        bool done = false;
+        uint32_t tmp[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) tmp[i] = e[i];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t mm = bm.big[i];
+            while (mm && !done) {
+                const int z = 32 * i + (__ffs(mm) - 1);
+                mm &= mm - 1;
+                int L, R;
+                bond_runs_generic(tmp, dm.B, z, L, R);
+                double rr, rl, er, el;
+                generic_bond_terms(L, R, tb.c, rr, rl, er, el);
+                if (rr > 0.0) {
+                    acc += rr;
+                    zsel = z;
+                    rsel = true;
+                    if (t < acc) done = true;
+                }
+                if (!done && rl > 0.0) {
+                    acc += rl;
+                    zsel = z;
+                    rsel = false;
+                    if (t < acc) done = true;
+                }
+            }
+        }
+        z_out = zsel;
+        right_out = rsel;
+    }
+}
+
+// 1-based reference hop index (Rimu offdiagonals order) of the hop (z, right) -- probe only
+template <int NW>
+__device__ __forceinline__ int reference_hop_index(const uint32_t (&e)[NW], const DevModel& dm, int z, bool right) {
+    // tops of runs: e(p)=1 and e(p+1)=0, p in [0,B-1]
+    uint32_t sh[NW];
+    shr1<NW>(e, sh);
+    int rank = 0;  // occupied modes whose top is below the limit
+    const int limit = right ? z - 1 : z;  // tops at positions <= limit belong to modes <= i
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        uint32_t tops = e[i] & ~sh[i] & dm.amask[i];
+        const int lo = 32 * i;
+        uint32_t keep;
+        if (limit < lo) keep = 0u;
+        else if (limit >= lo + 31) keep = 0xFFFFFFFFu;
+        else keep = (2u << (limit - lo)) - 1u;
+        rank += __popc(tops & keep);
+    }
+    if (right) return 2 * rank - 1;          // source = mode i (its top is at z-1, counted)
+    if (z == dm.B) return 2;                 // source = mode 1 hopping left (wraps to M)
+    return 2 * (rank + 1);                   // source = mode i+1 = next occupied mode after the tops <= z
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11): key = seed, counter = (step >> 1, walker id)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01_from_words(uint32_t lo, uint32_t hi) {
+    const uint64_t r = ((uint64_t)hi << 32) | lo;
+    return (double)(r >> 11) * 0x1.0p-53;
+}
+
+// ------------------------------------------------------------------------------------------
+// Enumerating evaluation in the reference's offdiagonals order (Rimu hopnextneighbour order:
+// occupied modes ascending, right hop then left hop; App. A.4).  Calls
+//     f(hop_index_1based, z, right, n_src, n_dst) -> bool (true = stop)
+// for every hop.  Walks the address bit by bit (uniform trip count); generic in the occupations.
+// ------------------------------------------------------------------------------------------
+template <int NW, typename F>
+__device__ __forceinline__ void enumerate_hops(const uint32_t (&a)[NW], const DevModel& dm, F&& f) {
+    // occupation of mode M (ones directly below bit B) and of mode 1 (trailing ones)
+    int nM = 0, n1 = 0;
+    {
+        bool run = true;
+        for (int p = dm.B - 1; p >= 0 && run; --p) {
+            run = get_bit<NW>(a, p) != 0;
+            nM += run ? 1 : 0;
+        }
+        run = true;
+        for (int p = 0; p < dm.B && run; ++p) {
+            run = get_bit<NW>(a, p) != 0;
+            n1 += run ? 1 : 0;
+        }
+    }
+    // stream the modes with a one-mode delay so that (n_prev, n_cur, n_next) are all known
+    int n_run = 0;    // ones read so far in the run being scanned
+    int n_prev = nM;  // occupation of the mode before the pending one
+    int n_pend = -1;  // occupation of the pending mode, -1 = none yet
+    int z_pend = 0;   // separator that closes the pending mode
+    int hop = 0;
+    bool stop = false;
+    auto emit = [&](int nprev, int ncur, int nnext, int zc) {
+        // the pending mode's run sits at bits zc-ncur .. zc-1; the bond below it is the separator
+        // at zc-ncur-1, or the periodic bond B for mode 1
+        if (ncur > 0 && !stop) {
+            ++hop;
+            stop = f(hop, zc, true, ncur, nnext);
+            if (!stop) {
+                ++hop;
+                const int zl = zc - ncur - 1;
+                stop = f(hop, zl < 0 ? dm.B : zl, false, ncur, nprev);
+            }
+        }
+    };
+    for (int p = 0; p <= dm.B && !stop; ++p) {
+        const int bit = (p < dm.B) ? get_bit<NW>(a, p) : 0;
+        if (bit) {
+            ++n_run;
+        } else {
+            if (n_pend >= 0) {
+                emit(n_prev, n_pend, n_run, z_pend);
+                n_prev = n_pend;
+            }
+            n_pend = n_run;
+            z_pend = p;
+            n_run = 0;
+        }
+    }
+    // the last pending mode is mode M; its right neighbour is mode 1
+    if (!stop && n_pend >= 0) emit(n_prev, n_pend, n1, z_pend);
+}
+
+// warp / block reductions of doubles (deterministic order)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace gwz

@@ -1,0 +1,103 @@
+// gwz_internal.h -- host-side interface between the C ABI (gwz_api.cu) and the kernel launchers.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gwz_device.cuh"
+
+namespace gwz {
+
+constexpr int NUM_ACC = 12;        // doubles in the cross-device accumulator vector (GWZ_NUM_ACC)
+constexpr int NUM_WALKER_ACC = 7;  // per-walker running sums kept in HBM: st, stE, stG, stGE, stEE, E0, G0
+constexpr int WALKER_BLOCK = 128;
+constexpr int SWEEP_BLOCK = 128;
+
+// accumulator vector layout (all-reduced with ncclSum)
+enum AccSlot {
+    ACC_WALKERS = 0,  // number of walkers
+    ACC_VAL = 1,      // sum_w val_w                      (state.jl:137-149)
+    ACC_VAL2 = 2,     // sum_w val_w^2                    (cross-walker error)
+    ACC_GRAD = 3,     // sum_w grad_w
+    ACC_GRAD2 = 4,    // sum_w grad_w^2
+    ACC_T = 5,        // sum tau
+    ACC_TE = 6,       // sum tau*E
+    ACC_TG = 7,       // sum tau*G
+    ACC_TGE = 8,      // sum tau*G*E
+    ACC_TEE = 9,      // sum tau*E^2
+    ACC_HOPS = 10,    // hop evaluations of this call
+    ACC_STEPS = 11    // walker-steps of this call
+};
+
+struct WalkerLaunch {
+    DevModel dm;
+    DevTables tb;
+    int nw;    // 32-bit words of the extended string
+    int kind;  // gwz_kernel_kind
+    // walker state (SoA in HBM)
+    uint64_t* addr;  // [W][n]
+    double* acc;     // [NUM_WALKER_ACC][n]
+    size_t n;
+    uint64_t global_offset, seed, step0, steps;
+    int accumulate;  // 0: burn-in (no estimator update, no reduction)
+    int reset_acc;   // 1: clear the per-walker sums before the first step
+    // optional per-step series [steps][n] (recording run)
+    double* rec_tau;
+    double* rec_eloc;
+    uint64_t* rec_addr;  // [steps][n][W]
+    // per-block partial accumulator vectors [grid][NUM_ACC]
+    double* partials;
+    int grid;
+    int* err_flag;
+};
+
+// occupancy-derived persistent grid for the walker kernel of this (nw, kind, record)
+cudaError_t walker_grid(int nw, int kind, bool record, size_t n, int sm_count, int* grid);
+cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s);
+// out[ncomp] = sum over blocks of partials[block][ncomp], fixed order
+cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s);
+cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, const uint64_t* start_dev, cudaStream_t s);
+cudaError_t launch_walker_estimates(const double* acc, size_t n, double* val_w, double* grad_w, cudaStream_t s);
+// AoS (n x W) <-> SoA ([W][n]) address layout conversion
+cudaError_t launch_transpose_addr(const uint64_t* src, uint64_t* dst, size_t n, int W, bool to_soa, cudaStream_t s);
+
+struct ProbeLaunch {
+    DevModel dm;
+    DevTables tb;
+    int nw, kind;
+    const uint64_t* addr;  // AoS n x W
+    size_t n;
+    const double* u01;  // may be null
+    double *e_loc, *tau, *grad;
+    int32_t* n_hops;
+    double* rates;  // n x 2M or null
+    int32_t* chosen;
+    uint64_t* next_addr;  // AoS
+    int* err_flag;
+};
+cudaError_t launch_probe(const ProbeLaunch& L, cudaStream_t s);
+cudaError_t launch_ansatz(const DevModel& dm, double g, int nw, const uint64_t* addr, size_t n, double* val,
+                          double* grad, cudaStream_t s);
+
+struct SweepLaunch {
+    DevModel dm;
+    DevTables tb;
+    int nw;
+    const uint64_t* basis;  // SoA [W][dim] or null => ranked enumeration
+    uint64_t dim;           // states handled by this sweep
+    uint64_t rank_begin;    // first rank (ranked mode)
+    const uint64_t* binom;  // [65][65] binomial table in HBM (ranked mode)
+    int with_grad;
+    double* partials;  // [grid][4]
+    int grid;
+    uint64_t chunk;  // consecutive ranks per thread (ranked mode)
+    // optional per-state output (terms kernel): out[count][4] for states first..first+count-1
+    double* terms_out;
+    uint64_t* states_out;  // AoS count x W
+    uint64_t first, count;
+};
+cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk);
+cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s);
+cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s);
+
+}  // namespace gwz

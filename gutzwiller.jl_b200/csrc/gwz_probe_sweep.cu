@@ -1,0 +1,302 @@
+// gwz_probe_sweep.cu -- per-address probe (kinetic_sample! for a batch of addresses) and the
+// LocalEnergyEvaluator full-basis sweep (src/localenergy.jl:94-155).
+#include "gwz_internal.h"
+#include "gwz_steps.cuh"
+
+namespace gwz {
+
+// ------------------------------------------------------------------------------------------
+// probe: one thread per address
+// ------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(128)
+probe_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, int kind,
+             const uint64_t* __restrict__ addr, size_t n, const double* __restrict__ u01,
+             double* __restrict__ e_loc, double* __restrict__ tau_out, double* __restrict__ grad_out,
+             int32_t* __restrict__ n_hops, double* __restrict__ rates, int32_t* __restrict__ chosen_out,
+             uint64_t* __restrict__ next_addr, int* __restrict__ err_flag) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a[NW];
+    load_addr_aos<NW>(addr, i, dm.W, a);
+    const double u = u01 ? u01[i] : 0.5;
+    double tau, eloc, gr;
+    int nh, chosen = 0;
+    if (kind == 1) {
+        // production path; recover the reference hop index of the selected move afterwards
+        uint32_t e[NW];
+        extend<NW>(a, dm, e);
+        BondMasks<NW> bm;
+        classify_bonds<NW>(e, dm, bm);
+        double cum[NCLS];
+        BondSums bs;
+        double bigS;
+        bond_sums<NW, false>(e, dm, tb, bm, cum, bs, bigS);
+        const double D = dm.u * (double)bs.d;
+        tau = 1.0 / bs.S;
+        eloc = D - dm.t * bs.E;
+        gr = -D;
+        nh = 2 * bs.nocc;
+        double T = u * bs.S;
+        if (!(T < bs.S)) T = __longlong_as_double(__double_as_longlong(bs.S) - 1);
+        int z;
+        bool right;
+        select_move<NW>(e, dm, tb, bm, cum, bigS, T, z, right);
+        if (z >= 0) {
+            chosen = reference_hop_index<NW>(e, dm, z, right);
+            apply_hop<NW>(a, dm, z, right);
+        }
+    } else {
+        double* r = rates ? rates + i * (size_t)(2 * dm.M) : nullptr;
+        if (r)
+            for (int k = 0; k < 2 * dm.M; ++k) r[k] = 0.0;
+        step_enumerate<NW>(a, dm, tb, u, tau, eloc, gr, nh, chosen, r);
+    }
+    if (!(tau < 1.0e300)) atomicOr(err_flag, 1);
+    if (e_loc) e_loc[i] = eloc;
+    if (tau_out) tau_out[i] = tau;
+    if (grad_out) grad_out[i] = gr;
+    if (n_hops) n_hops[i] = nh;
+    if (chosen_out) chosen_out[i] = chosen;
+    if (next_addr) store_addr_aos<NW>(next_addr, i, dm.W, a);
+}
+
+// GutzwillerAnsatz value and gradient (gutzwiller.jl:25-36): val = exp(-g*diag), der = -diag*val
+template <int NW>
+__global__ void __launch_bounds__(128)
+ansatz_kernel(const __grid_constant__ DevModel dm, double g, const uint64_t* __restrict__ addr, size_t n,
+              double* __restrict__ val, double* __restrict__ grad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a[NW];
+    load_addr_aos<NW>(addr, i, dm.W, a);
+    long long d = 0;
+    enumerate_hops<NW>(a, dm, [&](int, int, bool right, int nsrc, int) {
+        if (right) d += (long long)nsrc * (nsrc - 1) / 2;
+        return false;
+    });
+    const double diag = dm.u * (double)d;
+    const double v = exp(-g * diag);
+    if (val) val[i] = v;
+    if (grad) grad[i] = -diag * v;
+}
+
+// ------------------------------------------------------------------------------------------
+// sweep
+// ------------------------------------------------------------------------------------------
+// per-state terms of localenergy.jl:105-120 in closed form.  With r_l = psi_l/psi_k,
+// Emat = sum_l melem_l r_l = -t*E and sum_l melem_l r_l Delta_l = -t*ED:
+//   num      = psi_k^2 (D + Emat)
+//   den      = psi_k^2
+//   num_grad = psi_k^2 (-2 D (D + Emat) + u t ED)       [grad psi = -D psi, D_l = D + u Delta_l]
+//   den_grad = -2 D psi_k^2
+template <int NW>
+__device__ __forceinline__ void state_terms(const uint32_t (&a)[NW], const DevModel& dm, const DevTables& tb,
+                                            double& num, double& den, double& num_grad, double& den_grad) {
+    uint32_t e[NW];
+    extend<NW>(a, dm, e);
+    BondMasks<NW> bm;
+    classify_bonds<NW>(e, dm, bm);
+    double cum[NCLS];
+    BondSums bs;
+    double bigS;
+    bond_sums<NW, true>(e, dm, tb, bm, cum, bs, bigS);
+    const double D = dm.u * (double)bs.d;
+    const double psi2 = exp(-2.0 * tb.g * D);  // abs2(exp(-g*diag))  (localenergy.jl:108,111)
+    const double eloc = D - dm.t * bs.E;
+    num = psi2 * eloc;
+    den = psi2;
+    num_grad = psi2 * (-2.0 * D * eloc + dm.u * dm.t * bs.ED);
+    den_grad = -2.0 * D * psi2;
+}
+
+// colex unranking: the rank-th N-subset of bit positions, as a 64-bit word
+__device__ __forceinline__ uint64_t unrank_colex(uint64_t rank, int N, int B, const uint64_t* __restrict__ binom) {
+    uint64_t x = 0;
+    int p = B - 1;
+    for (int i = N; i >= 1; --i) {
+        while (binom[p * 65 + i] > rank) --p;  // largest p with C(p,i) <= rank
+        x |= 1ull << p;
+        rank -= binom[p * 65 + i];
+        --p;
+    }
+    return x;
+}
+// next integer with the same popcount (Gosper)
+__device__ __forceinline__ uint64_t next_same_popcount(uint64_t x) {
+    const uint64_t t = x | (x - 1);
+    return (t + 1) | (((~t & (0 - ~t)) - 1) >> (__ffsll((long long)x)));
+}
+
+template <int NW, bool RANKED>
+__global__ void __launch_bounds__(SWEEP_BLOCK)
+sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
+             const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
+             const uint64_t* __restrict__ binom, double* __restrict__ partials) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (RANKED) {
+        // each thread owns runs of `chunk` consecutive ranks: unrank once, then Gosper steps
+        for (uint64_t first = tid * chunk; first < dim; first += nthreads * chunk) {
+            const uint64_t cnt = min(chunk, dim - first);
+            uint64_t x = unrank_colex(rank_begin + first, dm.N, dm.B, binom);
+            for (uint64_t k = 0; k < cnt; ++k) {
+                uint32_t a[NW];
+                a[0] = (uint32_t)x;
+                if (NW > 1) a[1] = (uint32_t)(x >> 32);
+#pragma unroll
+                for (int i = 2; i < NW; ++i) a[i] = 0u;
+                double num, den, ng, dg;
+                state_terms<NW>(a, dm, tb, num, den, ng, dg);
+                s0 += num;
+                s1 += den;
+                s2 += ng;
+                s3 += dg;
+                x = next_same_popcount(x);
+            }
+        }
+    } else {
+        for (uint64_t idx = tid; idx < dim; idx += nthreads) {
+            uint32_t a[NW];
+            load_addr_soa<NW>(basis, dim, idx, dm.W, a);
+            double num, den, ng, dg;
+            state_terms<NW>(a, dm, tb, num, den, ng, dg);
+            s0 += num;
+            s1 += den;
+            s2 += ng;
+            s3 += dg;
+        }
+    }
+    __shared__ double sm[SWEEP_BLOCK / 32][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    s3 = warp_sum(s3);
+    if (lane == 0) {
+        sm[warp][0] = s0;
+        sm[warp][1] = s1;
+        sm[warp][2] = s2;
+        sm[warp][3] = s3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < SWEEP_BLOCK / 32; ++q) v += sm[q][threadIdx.x];
+        partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+
+// per-state outputs for parity tests: states first..first+count-1
+template <int NW, bool RANKED>
+__global__ void __launch_bounds__(SWEEP_BLOCK)
+sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
+                   const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin,
+                   const uint64_t* __restrict__ binom, uint64_t first, uint64_t count,
+                   double* __restrict__ out, uint64_t* __restrict__ states_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t a[NW];
+    if (RANKED) {
+        const uint64_t x = unrank_colex(rank_begin + first + i, dm.N, dm.B, binom);
+        a[0] = (uint32_t)x;
+        if (NW > 1) a[1] = (uint32_t)(x >> 32);
+#pragma unroll
+        for (int q = 2; q < NW; ++q) a[q] = 0u;
+    } else {
+        load_addr_soa<NW>(basis, dim, first + i, dm.W, a);
+    }
+    if (out) {
+        double num, den, ng, dg;
+        state_terms<NW>(a, dm, tb, num, den, ng, dg);
+        out[i * 4 + 0] = num;
+        out[i * 4 + 1] = den;
+        out[i * 4 + 2] = ng;
+        out[i * 4 + 3] = dg;
+    }
+    if (states_out) store_addr_aos<NW>(states_out, i, dm.W, a);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+#define GWZ_DISPATCH_NW(nw, CALL)                \
+    switch (nw) {                                \
+        case 1: { constexpr int NW = 1; CALL; } break; \
+        case 2: { constexpr int NW = 2; CALL; } break; \
+        case 3: { constexpr int NW = 3; CALL; } break; \
+        case 4: { constexpr int NW = 4; CALL; } break; \
+        case 5: { constexpr int NW = 5; CALL; } break; \
+        case 6: { constexpr int NW = 6; CALL; } break; \
+        case 7: { constexpr int NW = 7; CALL; } break; \
+        case 8: { constexpr int NW = 8; CALL; } break; \
+        default: return cudaErrorInvalidValue;   \
+    }
+
+cudaError_t launch_probe(const ProbeLaunch& L, cudaStream_t s) {
+    if (L.n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((L.n + 127) / 128);
+    GWZ_DISPATCH_NW(L.nw, (probe_kernel<NW><<<grid, 128, 0, s>>>(L.dm, L.tb, L.kind, L.addr, L.n, L.u01, L.e_loc, L.tau,
+                                                               L.grad, L.n_hops, L.rates, L.chosen, L.next_addr,
+                                                               L.err_flag)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ansatz(const DevModel& dm, double g, int nw, const uint64_t* addr, size_t n, double* val,
+                          double* grad, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    GWZ_DISPATCH_NW(nw, (ansatz_kernel<NW><<<grid, 128, 0, s>>>(dm, g, addr, n, val, grad)));
+    return cudaGetLastError();
+}
+
+cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk) {
+    (void)nw;
+    // aim at >= 8 resident CTAs per SM; in ranked mode amortise the unranking over `chunk` states
+    const uint64_t max_threads = (uint64_t)sm_count * 16 * SWEEP_BLOCK;
+    uint64_t c = 1;
+    if (ranked) {
+        c = (dim + max_threads - 1) / max_threads;
+        if (c < 8) c = 8;
+        if (c > 1024) c = 1024;
+    }
+    uint64_t threads = (dim + c - 1) / c;
+    if (threads > max_threads) threads = max_threads;
+    uint64_t g = (threads + SWEEP_BLOCK - 1) / SWEEP_BLOCK;
+    if (g < 1) g = 1;
+    *grid = (int)g;
+    *chunk = c;
+    return cudaSuccess;
+}
+
+cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
+    const bool ranked = (L.basis == nullptr);
+    if (ranked) {
+        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, true><<<L.grid, SWEEP_BLOCK, 0, s>>>(
+                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk, L.binom, L.partials)));
+    } else {
+        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, false><<<L.grid, SWEEP_BLOCK, 0, s>>>(
+                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk, L.binom, L.partials)));
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s) {
+    if (L.count == 0) return cudaSuccess;
+    const bool ranked = (L.basis == nullptr);
+    const unsigned grid = (unsigned)((L.count + SWEEP_BLOCK - 1) / SWEEP_BLOCK);
+    if (ranked) {
+        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, true><<<grid, SWEEP_BLOCK, 0, s>>>(
+                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom, L.first, L.count, L.terms_out,
+                                  L.states_out)));
+    } else {
+        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, false><<<grid, SWEEP_BLOCK, 0, s>>>(
+                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom, L.first, L.count, L.terms_out,
+                                  L.states_out)));
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace gwz

@@ -1,0 +1,274 @@
+// gwz_walker.cu -- persistent kinetic-VQMC walker kernel (one walker per thread).
+//
+// Implements kinetic_vqmc!(st; steps) (src/kinetic-vqmc/qmc.jl:73-97) for every walker in
+// parallel (the reference's Threads.@threads loop, qmc.jl:99-106), with kinetic_sample!
+// (qmc.jl:14-44) evaluated in closed form for HubbardReal1D + GutzwillerAnsatz, and the
+// per-walker estimator of state.jl:42-49 kept as running sums instead of per-step arrays.
+#include "gwz_internal.h"
+#include "gwz_steps.cuh"
+
+namespace gwz {
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int NW, int KIND, bool RECORD>
+__global__ void __launch_bounds__(WALKER_BLOCK)
+walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
+              uint64_t* __restrict__ addr, double* __restrict__ acc, size_t n, uint64_t global_offset,
+              uint64_t seed, uint64_t step0, uint64_t steps, int accumulate, int reset_acc,
+              double* __restrict__ rec_tau, double* __restrict__ rec_eloc, uint64_t* __restrict__ rec_addr,
+              double* __restrict__ partials, int* __restrict__ err_flag) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+
+    double p[NUM_ACC];
+#pragma unroll
+    for (int i = 0; i < NUM_ACC; ++i) p[i] = 0.0;
+    bool bad = false;
+
+    for (size_t w = tid; w < n; w += nthreads) {
+        uint32_t a[NW];
+        load_addr_soa<NW>(addr, n, w, dm.W, a);
+        double st, ste, stg, stge, stee, E0, G0;
+        if (reset_acc) {
+            st = ste = stg = stge = stee = E0 = G0 = 0.0;
+        } else {
+            st = acc[0 * n + w];
+            ste = acc[1 * n + w];
+            stg = acc[2 * n + w];
+            stge = acc[3 * n + w];
+            stee = acc[4 * n + w];
+            E0 = acc[5 * n + w];
+            G0 = acc[6 * n + w];
+        }
+        bool have_ref = (st > 0.0);
+        const uint64_t wid = global_offset + (uint64_t)w;
+        const uint32_t c2 = (uint32_t)wid, c3 = (uint32_t)(wid >> 32);
+        uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+        unsigned long long hops = 0ull;
+
+        for (uint64_t k = 0; k < steps; ++k) {
+            const uint64_t step = step0 + k;
+            if (k == 0 || (step & 1ull) == 0ull) {
+                const uint64_t blk = step >> 1;
+                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, k0, k1, rnd);
+            }
+            const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
+            if (RECORD && rec_addr) store_addr_aos<NW>(rec_addr, (size_t)k * n + w, dm.W, a);
+            double tau, eloc, gr;
+            int nh;
+            if (KIND == 1) {
+                step_bitparallel<NW>(a, dm, tb, u01, tau, eloc, gr, nh);
+            } else {
+                int chosen;
+                step_enumerate<NW>(a, dm, tb, u01, tau, eloc, gr, nh, chosen, nullptr);
+            }
+            bad |= !(tau < 1.0e300);  // isfinite(residence_time)  (qmc.jl:34-36)
+            hops += (unsigned)nh;
+            if (RECORD) {
+                rec_tau[(size_t)k * n + w] = tau;
+                rec_eloc[(size_t)k * n + w] = eloc;
+            }
+            if (accumulate) {
+                if (!have_ref) {
+                    E0 = eloc;
+                    G0 = gr;
+                    have_ref = true;
+                }
+                // shifted running sums: weights = residence times (state.jl:43-46)
+                const double dE = eloc - E0, dG = gr - G0;
+                const double tE = tau * dE;
+                st += tau;
+                ste += tE;
+                stg = fma(tau, dG, stg);
+                stge = fma(tE, dG, stge);
+                stee = fma(tE, dE, stee);
+            }
+        }
+
+        store_addr_soa<NW>(addr, n, w, dm.W, a);
+        if (accumulate) {
+            acc[0 * n + w] = st;
+            acc[1 * n + w] = ste;
+            acc[2 * n + w] = stg;
+            acc[3 * n + w] = stge;
+            acc[4 * n + w] = stee;
+            acc[5 * n + w] = E0;
+            acc[6 * n + w] = G0;
+            // per-walker estimates (state.jl:42-49)
+            const double inv = 1.0 / st;
+            const double mE = ste * inv, mG = stg * inv;
+            const double val_w = E0 + mE;
+            const double grad_w = 2.0 * (stge * inv - mE * mG);
+            p[ACC_WALKERS] += 1.0;
+            p[ACC_VAL] += val_w;
+            p[ACC_VAL2] = fma(val_w, val_w, p[ACC_VAL2]);
+            p[ACC_GRAD] += grad_w;
+            p[ACC_GRAD2] = fma(grad_w, grad_w, p[ACC_GRAD2]);
+            // pooled sums, un-shifted
+            p[ACC_T] += st;
+            p[ACC_TE] += st * val_w;
+            p[ACC_TG] += st * (G0 + mG);
+            p[ACC_TGE] += st * G0 * E0 + G0 * ste + E0 * stg + stge;
+            p[ACC_TEE] += st * E0 * E0 + 2.0 * E0 * ste + stee;
+            p[ACC_HOPS] += (double)hops;
+            p[ACC_STEPS] += (double)steps;
+        }
+    }
+
+    if (bad) atomicOr(err_flag, 1);
+    if (!accumulate || partials == nullptr) return;
+
+    // block reduction in fixed order: lanes -> warps -> block
+    __shared__ double sm[WALKER_BLOCK / 32][NUM_ACC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NUM_ACC; ++i) {
+        const double v = warp_sum(p[i]);
+        if (lane == 0) sm[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_ACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < WALKER_BLOCK / 32; ++q) v += sm[q][threadIdx.x];
+        partials[(size_t)blockIdx.x * NUM_ACC + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int ncomp,
+                                       double* __restrict__ out) {
+    // one warp per component, fixed summation order
+    __shared__ double sm[32];
+    const int comp = blockIdx.x;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partials[(size_t)b * ncomp + comp];
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += sm[q];
+        out[comp] = t;
+    }
+}
+
+__global__ void walker_init_kernel(uint64_t* __restrict__ addr, double* __restrict__ acc, size_t n, int W,
+                                   const uint64_t* __restrict__ start) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < W; ++w) addr[(size_t)w * n + i] = start[w];  // starting_address(H) (state.jl:26)
+    for (int c = 0; c < NUM_WALKER_ACC; ++c) acc[(size_t)c * n + i] = 0.0;
+}
+
+__global__ void walker_estimates_kernel(const double* __restrict__ acc, size_t n, double* __restrict__ val_w,
+                                        double* __restrict__ grad_w) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double st = acc[0 * n + i], ste = acc[1 * n + i], stg = acc[2 * n + i], stge = acc[3 * n + i];
+    const double E0 = acc[5 * n + i];
+    const double inv = 1.0 / st;
+    const double mE = ste * inv, mG = stg * inv;
+    val_w[i] = E0 + mE;
+    grad_w[i] = 2.0 * (stge * inv - mE * mG);
+}
+
+__global__ void transpose_addr_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, size_t n,
+                                      int W, int to_soa) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < W; ++w) {
+        if (to_soa) dst[(size_t)w * n + i] = src[i * (size_t)W + w];
+        else dst[i * (size_t)W + w] = src[(size_t)w * n + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <int NW, int KIND, bool RECORD>
+static cudaError_t launch_one(const WalkerLaunch& L, cudaStream_t s) {
+    walker_kernel<NW, KIND, RECORD><<<L.grid, WALKER_BLOCK, 0, s>>>(
+        L.dm, L.tb, L.addr, L.acc, L.n, L.global_offset, L.seed, L.step0, L.steps, L.accumulate, L.reset_acc,
+        L.rec_tau, L.rec_eloc, L.rec_addr, L.partials, L.err_flag);
+    return cudaGetLastError();
+}
+template <int NW>
+static cudaError_t launch_nw(const WalkerLaunch& L, cudaStream_t s) {
+    const bool rec = (L.rec_tau != nullptr);
+    if (L.kind == 1) return rec ? launch_one<NW, 1, true>(L, s) : launch_one<NW, 1, false>(L, s);
+    return rec ? launch_one<NW, 0, true>(L, s) : launch_one<NW, 0, false>(L, s);
+}
+cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s) {
+    switch (L.nw) {
+        case 1: return launch_nw<1>(L, s);
+        case 2: return launch_nw<2>(L, s);
+        case 3: return launch_nw<3>(L, s);
+        case 4: return launch_nw<4>(L, s);
+        case 5: return launch_nw<5>(L, s);
+        case 6: return launch_nw<6>(L, s);
+        case 7: return launch_nw<7>(L, s);
+        case 8: return launch_nw<8>(L, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NW, int KIND, bool RECORD>
+static cudaError_t occ_one(int* blocks) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, walker_kernel<NW, KIND, RECORD>, WALKER_BLOCK, 0);
+}
+template <int NW>
+static cudaError_t occ_nw(int kind, bool rec, int* blocks) {
+    if (kind == 1) return rec ? occ_one<NW, 1, true>(blocks) : occ_one<NW, 1, false>(blocks);
+    return rec ? occ_one<NW, 0, true>(blocks) : occ_one<NW, 0, false>(blocks);
+}
+cudaError_t walker_grid(int nw, int kind, bool record, size_t n, int sm_count, int* grid) {
+    int blocks = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (nw) {
+        case 1: e = occ_nw<1>(kind, record, &blocks); break;
+        case 2: e = occ_nw<2>(kind, record, &blocks); break;
+        case 3: e = occ_nw<3>(kind, record, &blocks); break;
+        case 4: e = occ_nw<4>(kind, record, &blocks); break;
+        case 5: e = occ_nw<5>(kind, record, &blocks); break;
+        case 6: e = occ_nw<6>(kind, record, &blocks); break;
+        case 7: e = occ_nw<7>(kind, record, &blocks); break;
+        case 8: e = occ_nw<8>(kind, record, &blocks); break;
+    }
+    if (e != cudaSuccess) return e;
+    if (blocks < 1) blocks = 1;
+    // persistent grid: one full wave of resident CTAs (multiple of the SM count), fewer if the
+    // walkers do not fill it
+    size_t resident = (size_t)blocks * (size_t)sm_count;
+    size_t need = (n + WALKER_BLOCK - 1) / WALKER_BLOCK;
+    *grid = (int)(need < resident ? need : resident);
+    if (*grid < 1) *grid = 1;
+    return cudaSuccess;
+}
+
+cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s) {
+    reduce_partials_kernel<<<ncomp, 256, 0, s>>>(partials, nblocks, ncomp, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, const uint64_t* start_dev,
+                               cudaStream_t s) {
+    walker_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(addr, acc, n, W, start_dev);
+    return cudaGetLastError();
+}
+cudaError_t launch_walker_estimates(const double* acc, size_t n, double* val_w, double* grad_w, cudaStream_t s) {
+    walker_estimates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(acc, n, val_w, grad_w);
+    return cudaGetLastError();
+}
+cudaError_t launch_transpose_addr(const uint64_t* src, uint64_t* dst, size_t n, int W, bool to_soa, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    transpose_addr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n, W, to_soa ? 1 : 0);
+    return cudaGetLastError();
+}
+
+}  // namespace gwz

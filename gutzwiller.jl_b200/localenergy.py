@@ -1,0 +1,103 @@
+"""LocalEnergyEvaluator -- host mirror of src/localenergy.jl:81-173 over the CUDA sweep kernel."""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from ._capi import check, lib
+from .hamiltonian import AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1D, as_params
+from .runtime import Context, distributed_state, shard_range
+
+
+class LocalEnergyEvaluator:
+    """``LocalEnergyEvaluator(hamiltonian, ansatz; basis=build_basis(hamiltonian))`` (localenergy.jl:81-88).
+
+    ``basis`` may be a sequence of :class:`BoseFS` or a ``uint64[dim, W]`` array (uploaded to HBM once,
+    the reference's ``basis::Vector{A}``).  Without a basis all C(N+M-1, N) Fock states are enumerated
+    on the GPU by rank (needs N+M-1 <= 64); across several GPUs each rank sweeps its share of the
+    rank range and the four sums are all-reduced.
+    """
+
+    def __init__(self, hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, *, basis=None, ctx: Context | None = None):
+        if not isinstance(ansatz, GutzwillerAnsatz):
+            raise TypeError("this build covers GutzwillerAnsatz only")
+        self.hamiltonian, self.ansatz = hamiltonian, ansatz
+        self.model = hamiltonian.model(ctx)
+        self._h = C.c_void_p()
+        if basis is not None:
+            if len(basis) and isinstance(basis[0], BoseFS):
+                basis = np.stack([b.words for b in basis])
+            arr = np.ascontiguousarray(basis, dtype=np.uint64).reshape(-1, self.model.words)
+            if arr.shape[0] == 0:
+                raise ValueError("empty basis")
+            check(lib().gwz_sweep_create(self.model.handle, arr.ctypes.data_as(C.c_void_p), arr.shape[0], 0, 0,
+                                         C.byref(self._h)))
+        else:
+            world, rank = distributed_state() if ctx is None else (1, 0)
+            begin, end = shard_range(self.model.dimension(), world, rank)
+            check(lib().gwz_sweep_create(self.model.handle, None, 0, begin, end, C.byref(self._h)))
+        self._finalizer = weakref.finalize(self, lib().gwz_sweep_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def dim(self) -> int:
+        d = C.c_uint64()
+        check(lib().gwz_sweep_dim(self._h, C.byref(d)))
+        return d.value
+
+    def val_and_grad(self, params):
+        """``val_and_grad(le, params)`` (localenergy.jl:94-129)."""
+        p = as_params(params, 1)
+        val, grad = C.c_double(), (C.c_double * 1)()
+        check(lib().gwz_sweep_val_and_grad(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(val), grad, None))
+        return val.value, np.array([grad[0]])
+
+    def accumulators(self, params) -> np.ndarray:
+        """(numerator, denominator, numerator_grad, denominator_grad) of localenergy.jl:121."""
+        p = as_params(params, 1)
+        val, grad, acc = C.c_double(), (C.c_double * 1)(), (C.c_double * 4)()
+        check(lib().gwz_sweep_val_and_grad(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(val), grad, acc))
+        return np.array(acc[:])
+
+    def __call__(self, *args):
+        if len(args) == 3:  # one-parameter ansatz: three arguments can only be (F, G, params)
+            F, G, params = args  # le(F, G, params): Optim.only_fg! protocol (localenergy.jl:157-169)
+            if G is not None:
+                val, grad = self.val_and_grad(params)
+                G[...] = grad
+            else:
+                val = self(params)
+            return val if F is not None else None
+        params = args[0] if len(args) == 1 else args  # le(p...) (localenergy.jl:171-173)
+        p = as_params(params, 1)
+        val = C.c_double()
+        check(lib().gwz_sweep_val(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(val)))
+        return val.value  # localenergy.jl:131-155
+
+    def terms(self, params, first: int = 0, count: int | None = None) -> np.ndarray:
+        """Per-state (num, den, num_grad, den_grad) of localenergy.jl:105-120: float64[count, 4]."""
+        p = as_params(params, 1)
+        count = self.dim - first if count is None else int(count)
+        out = np.zeros((count, 4))
+        check(lib().gwz_sweep_terms(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), int(first), count,
+                                    out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def states(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.dim - first if count is None else int(count)
+        out = np.zeros((count, self.model.words), dtype=np.uint64)
+        check(lib().gwz_sweep_states(self._h, int(first), count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().gwz_sweep_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def __repr__(self):
+        return f"LocalEnergyEvaluator({self.hamiltonian!r}, {self.ansatz!r})"

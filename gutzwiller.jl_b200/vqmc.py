@@ -1,0 +1,397 @@
+"""kinetic_vqmc / KineticVQMC / KineticVQMCResult -- host mirror of src/kinetic-vqmc/*.jl.
+
+Same names, argument meaning and error behaviour as the reference; the walkers live in HBM behind
+a ``gwz_walkers`` handle and every step runs in the persistent CUDA walker kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+from .hamiltonian import AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1D, as_params
+from .runtime import Context, default_context, distributed_state, shard_range
+
+DEFAULT_SEED = 0x9E3779B97F4A7C15
+RECORD_LIMIT_BYTES = 256 << 20  # kinetic_vqmc keeps per-step series (like the reference) up to this size
+
+
+def default_walkers(samples: float) -> int:
+    """GPU default for the `walkers` keyword.
+
+    The reference derives its default from the thread count (qmc.jl:132).  Here it is the largest
+    power of two that still leaves every walker >= 1024 steps (all walkers start at the same
+    address and the reference has no burn-in, so short walkers bias the estimate), capped at 2^20.
+    An explicit ``walkers=`` is always honoured exactly.
+    """
+    w = max(1, int(samples) // 1024)
+    return min(1 << 20, 1 << (w.bit_length() - 1))
+
+
+@dataclass
+class BlockingResult:
+    mean: float
+    err: float
+    err_err: float
+    p_cov: float
+    k: int
+    blocks: int
+
+
+@dataclass
+class CombinedBlockingResult:
+    """state.jl:238-256"""
+    mean: float
+    err: float
+    err_err: float
+    results: list
+
+
+def resample(residence_times, values, len=None) -> np.ndarray:  # noqa: A002 - keyword name of the reference
+    """``resample(residence_times, values; len)`` (state.jl:183-231)."""
+    t = np.ascontiguousarray(residence_times, dtype=np.float64).ravel()
+    v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    if t.size != v.size:
+        raise ValueError("Lengths of `residence_times` and `values` do not match!")  # state.jl:195-197
+    n_out = t.size if len is None else int(len)
+    out = np.zeros(n_out)
+    check(lib().gwz_resample(out.ctypes.data_as(C.c_void_p), n_out, t.ctypes.data_as(C.c_void_p),
+                             v.ctypes.data_as(C.c_void_p), t.size))
+    return out
+
+
+def blocking_analysis(v) -> BlockingResult:
+    """Rimu.StatsTools.blocking_analysis (used at state.jl:53,273)."""
+    v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    r = _capi.BlockingResult()
+    check(lib().gwz_blocking_analysis(v.ctypes.data_as(C.c_void_p), v.size, C.byref(r)))
+    return BlockingResult(r.mean, r.err, r.err_err, r.p_cov, r.k, r.blocks)
+
+
+class Walkers:
+    """gwz_walkers: n walkers (global ids offset..offset+n-1) resident on one device."""
+
+    def __init__(self, model, n_walkers: int, start_words, seed: int = DEFAULT_SEED, global_offset: int = 0):
+        self.model = model
+        self.n = int(n_walkers)
+        self.offset = int(global_offset)
+        self._h = C.c_void_p()
+        sw = np.ascontiguousarray(start_words, dtype=np.uint64)
+        check(lib().gwz_walkers_create(model.handle, self.n, self.offset, sw.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(self._h)))
+        self._finalizer = weakref.finalize(self, lib().gwz_walkers_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def steps_done(self) -> int:
+        n, s = C.c_uint64(), C.c_uint64()
+        check(lib().gwz_walkers_count(self._h, C.byref(n), C.byref(s)))
+        return s.value
+
+    def addresses(self) -> np.ndarray:
+        out = np.zeros((self.n, self.model.words), dtype=np.uint64)
+        check(lib().gwz_walkers_get_addresses(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_addresses(self, addrs) -> None:
+        a = np.ascontiguousarray(addrs, dtype=np.uint64).reshape(self.n, self.model.words)
+        check(lib().gwz_walkers_set_addresses(self._h, a.ctypes.data_as(C.c_void_p)))
+
+    def set_step_counter(self, steps_done: int) -> None:
+        check(lib().gwz_walkers_set_step_counter(self._h, int(steps_done)))
+
+    def run(self, params, steps: int, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
+            keep_acc: bool = False) -> _capi.VqmcResult:
+        p = as_params(params, 1)
+        r = _capi.VqmcResult()
+        check(lib().gwz_vqmc_run(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), int(steps), int(burn_in),
+                                 int(kernel), _capi.RUN_KEEP_ACC if keep_acc else 0, C.byref(r)))
+        return r
+
+    def run_record(self, params, steps: int, kernel: int = _capi.KERNEL_BITPARALLEL, keep_acc: bool = False,
+                   want_addresses: bool = True):
+        p = as_params(params, 1)
+        steps = int(steps)
+        tau = np.zeros((steps, self.n))
+        eloc = np.zeros((steps, self.n))
+        addr = np.zeros((steps, self.n, self.model.words), dtype=np.uint64) if want_addresses else None
+        r = _capi.VqmcResult()
+        check(lib().gwz_vqmc_run_record(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), steps, int(kernel),
+                                        _capi.RUN_KEEP_ACC if keep_acc else 0, tau.ctypes.data_as(C.c_void_p),
+                                        eloc.ctypes.data_as(C.c_void_p),
+                                        None if addr is None else addr.ctypes.data_as(C.c_void_p), C.byref(r)))
+        return r, tau, eloc, addr
+
+    def estimates(self):
+        v, g = np.zeros(self.n), np.zeros((self.n, 1))
+        check(lib().gwz_walkers_estimates(self._h, v.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p)))
+        return v, g
+
+
+def run_group(walker_sets, params, steps: int, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
+              keep_acc: bool = False) -> _capi.VqmcResult:
+    """gwz_vqmc_run_group: several walker sets (logical shards / several devices of one process)."""
+    p = as_params(params, 1)
+    arr = (C.c_void_p * len(walker_sets))(*[w.handle for w in walker_sets])
+    r = _capi.VqmcResult()
+    check(lib().gwz_vqmc_run_group(arr, len(walker_sets), p.ctypes.data_as(C.POINTER(C.c_double)), int(steps),
+                                   int(burn_in), int(kernel), _capi.RUN_KEEP_ACC if keep_acc else 0, C.byref(r)))
+    return r
+
+
+class KineticVQMCResult:
+    """``KineticVQMCResult`` (state.jl:75-77): the walkers plus what has been sampled so far.
+
+    ``val_and_grad(res)``, ``val_err_and_grad(res)``, ``mean(res)``, ``var(res)``,
+    ``local_energy_estimator(res)`` and ``rows()`` follow state.jl:137-164,265-298,91-132.
+    """
+
+    def __init__(self, hamiltonian, ansatz, params, walkers: Walkers, record: bool, kernel: int, burn_in: int = 0):
+        self.hamiltonian, self.ansatz = hamiltonian, ansatz
+        self.params = as_params(params, ansatz.N_PARAMS)
+        self.walkers_handle = walkers
+        self.record = record
+        self.kernel = kernel
+        self.burn_in = int(burn_in)
+        self.last: _capi.VqmcResult | None = None
+        self.steps = 0  # per walker
+        self._tau: list[np.ndarray] = []
+        self._eloc: list[np.ndarray] = []
+        self._addr: list[np.ndarray] = []
+
+    # -- sampling --
+    def _run(self, steps: int, keep: bool):
+        steps = int(steps)
+        w = self.walkers_handle
+        burn = self.burn_in if self.steps == 0 or not keep else 0
+        if self.record:
+            if burn:
+                w.run(self.params, burn, kernel=self.kernel)  # thermalise; estimators are cleared next
+            r, tau, eloc, addr = w.run_record(self.params, steps, kernel=self.kernel, keep_acc=keep)
+            if not keep:
+                self._tau, self._eloc, self._addr = [], [], []
+            self._tau.append(tau)
+            self._eloc.append(eloc)
+            self._addr.append(addr)
+        else:
+            if burn:
+                w.run(self.params, max(burn, 1), kernel=self.kernel)
+            r = w.run(self.params, steps, kernel=self.kernel, keep_acc=keep)
+        self.steps = self.steps + steps if keep else steps
+        self.last = r
+        return self
+
+    # -- series access (reference: per-walker vectors, state.jl:15-18) --
+    @property
+    def n_walkers(self) -> int:
+        return int(self.last.walkers) if self.last is not None else self.walkers_handle.n
+
+    def __len__(self):  # sum(length, res.states), the row count of the Tables.jl view
+        return self.steps * self.walkers_handle.n
+
+    def _need_series(self):
+        if not self.record or not self._tau:
+            raise RuntimeError("per-step series were not recorded for this run (record=False)")
+
+    def residence_times(self) -> np.ndarray:
+        """[walker, step]"""
+        self._need_series()
+        return np.concatenate(self._tau, axis=0).T
+
+    def local_energies(self) -> np.ndarray:
+        self._need_series()
+        return np.concatenate(self._eloc, axis=0).T
+
+    def addresses(self) -> np.ndarray:
+        """[walker, step, word]"""
+        self._need_series()
+        return np.concatenate(self._addr, axis=0).transpose(1, 0, 2)
+
+    def rows(self):
+        """Tables.jl rows (state.jl:91-132): (walker, step, address, residence_time, local_energy)."""
+        tau, el, ad = self.residence_times(), self.local_energies(), self.addresses()
+        N, M = self.hamiltonian.address.N, self.hamiltonian.address.M
+        for w in range(tau.shape[0]):
+            for k in range(tau.shape[1]):
+                yield dict(walker=w + 1, step=k + 1, address=BoseFS.from_words(N, M, ad[w, k]),
+                           residence_time=tau[w, k], local_energy=el[w, k])
+
+    def curr_addresses(self) -> np.ndarray:
+        return self.walkers_handle.addresses()
+
+    def __repr__(self):
+        try:
+            est = local_energy_estimator(self)
+            le = f"{est.mean:.5g} ± {est.err:.5g}"
+        except Exception:  # pragma: no cover - cosmetic
+            le = "n/a"
+        return f"KineticVQMCResult\n  walkers:      {self.n_walkers}\n  samples:      {len(self)}\n  local energy: {le}"
+
+
+def kinetic_vqmc(hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, params, *, samples=1e6, walkers=None,
+                 steps=None, seed: int = DEFAULT_SEED, record=None, burn_in: int = 0,
+                 kernel: int = _capi.KERNEL_BITPARALLEL, ctx: Context | None = None) -> KineticVQMCResult:
+    """``kinetic_vqmc(hamiltonian, ansatz, params; samples=1e6, walkers, steps=round(Int, samples/walkers))``
+    (qmc.jl:129-146).  Extra keywords: seed (Philox key), record (keep per-step series; default: when
+    they fit in 256 MiB), burn_in (default 0 = reference behaviour), kernel, ctx."""
+    if not isinstance(ansatz, GutzwillerAnsatz) or ansatz.hamiltonian is not hamiltonian and \
+            (ansatz.hamiltonian.u, ansatz.hamiltonian.t) != (hamiltonian.u, hamiltonian.t):
+        raise TypeError("this build covers GutzwillerAnsatz(H) with H::HubbardReal1D")
+    if walkers is None:
+        walkers = default_walkers(samples)
+    walkers = int(walkers)
+    if steps is None:
+        steps = int(round(samples / walkers))  # qmc.jl:133
+    steps = int(steps)
+    res = _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx)
+    return res._run(steps, keep=False)
+
+
+def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx):
+    model = hamiltonian.model(ctx)
+    world, rank = distributed_state() if (ctx is None) else (1, 0)
+    begin, end = shard_range(walkers, world, rank)
+    if end <= begin:
+        raise ValueError("fewer walkers than GPUs")
+    if record is None:
+        record = (end - begin) * max(steps, 1) * (16 + 8 * model.words) <= RECORD_LIMIT_BYTES and world == 1
+    w = Walkers(model, end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
+    return KineticVQMCResult(hamiltonian, ansatz, params, w, bool(record), kernel, burn_in)
+
+
+def kinetic_vqmc_continue(res: KineticVQMCResult, *, steps=None) -> KineticVQMCResult:
+    """``kinetic_vqmc!(res; steps=length(res.states[1]))`` (qmc.jl:108-111): append `steps` more steps."""
+    steps = res.steps if steps is None else int(steps)
+    return res._run(steps, keep=True)
+
+
+def _per_walker_estimates(res: KineticVQMCResult):
+    return res.walkers_handle.estimates()
+
+
+def val_and_grad_result(res: KineticVQMCResult):
+    """state.jl:137-149: mean over walkers of the per-walker (val, grad) of state.jl:42-49."""
+    r = res.last
+    return r.val, np.array([r.grad[0]])
+
+
+def val_err_and_grad_result(res: KineticVQMCResult):
+    """state.jl:150-164.  With recorded series: per-walker blocking of the resampled local energies,
+    combined as sqrt(sum e_w^2)/walkers (Appendix B.6).  Without series (large runs): the
+    cross-walker standard error of the per-walker estimates (needs >= 2 walkers)."""
+    r = res.last
+    if res.record and res._tau:
+        tau, el = res.residence_times(), res.local_energies()
+        gr = None
+        vals = errs2 = 0.0
+        grads = 0.0
+        for w in range(tau.shape[0]):
+            b = blocking_analysis(resample(tau[w], el[w]))
+            vals += b.mean
+            errs2 += b.err ** 2
+            if gr is None:
+                gr = _grad_ratio_series(res)
+            grads += 2.0 * float(np.sum(tau[w] * gr[w] * (el[w] - b.mean)) / np.sum(tau[w]))  # state.jl:57-58
+        nw = tau.shape[0]
+        return vals / nw, math.sqrt(errs2) / nw, np.array([grads / nw])
+    return r.val, (r.err if r.walkers > 1 else float("nan")), np.array([r.grad[0]])
+
+
+def _grad_ratio_series(res: KineticVQMCResult) -> np.ndarray:
+    """grad_ratios[walker, step] = grad psi / psi = -diagonal_element for the Gutzwiller ansatz
+    (gutzwiller.jl:30, qmc.jl:38), recomputed on the GPU from the recorded addresses."""
+    ad = res.addresses()
+    nw, ns, W = ad.shape
+    out = res.hamiltonian.model(res.walkers_handle.model.ctx).probe(ad.reshape(-1, W), res.params)
+    return out["grad_ratio"][:, 0].reshape(nw, ns)
+
+
+def local_energy_estimator(res: KineticVQMCResult, resample_length=None) -> CombinedBlockingResult:
+    """``local_energy_estimator(res; resample_length)`` (state.jl:265-285)."""
+    if res.record and res._tau:
+        tau, el = res.residence_times(), res.local_energies()
+        n_out = tau.shape[1] if resample_length is None else int(resample_length)
+        results = [blocking_analysis(resample(tau[w], el[w], len=n_out)) for w in range(tau.shape[0])]
+        n = len(results)
+        return CombinedBlockingResult(
+            float(np.mean([b.mean for b in results])),
+            math.sqrt(float(np.mean([b.err ** 2 for b in results])) / n),
+            math.sqrt(float(np.mean([b.err_err ** 2 for b in results])) / n), results)
+    r = res.last
+    return CombinedBlockingResult(r.val, r.err if r.walkers > 1 else float("nan"), float("nan"), [])
+
+
+def mean(res: KineticVQMCResult) -> float:
+    """``Statistics.mean(res)`` (state.jl:287-292)."""
+    return res.last.val
+
+
+def var(res: KineticVQMCResult) -> float:
+    """``Statistics.var(res)`` (state.jl:293-298): mean over walkers of the time-weighted variance."""
+    if res.record and res._tau:
+        tau, el = res.residence_times(), res.local_energies()
+        out = 0.0
+        for w in range(tau.shape[0]):
+            m = np.sum(tau[w] * el[w]) / np.sum(tau[w])
+            sw = np.sum(tau[w])
+            out += np.sum(tau[w] * (el[w] - m) ** 2) / (sw - 1.0)  # StatsBase FrequencyWeights, corrected
+        return out / tau.shape[0]
+    return res.last.pooled_var
+
+
+class KineticVQMC:
+    """``KineticVQMC(hamiltonian, ansatz; samples=1e6, walkers, steps)`` (wrapper.jl:45-63).
+
+    Walkers persist between calls (warm start, wrapper.jl:74-79): each call resets the estimators,
+    keeps the positions, runs ``steps = samples ÷ walkers`` steps per walker and reduces.
+    """
+
+    def __init__(self, hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, *, samples=1e6, walkers=None, steps=None,
+                 seed: int = DEFAULT_SEED, record=None, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
+                 ctx: Context | None = None):
+        if walkers is None:
+            walkers = default_walkers(samples)
+        self.hamiltonian, self.ansatz = hamiltonian, ansatz
+        self.walkers = int(walkers)
+        self.steps = int(round(samples / self.walkers)) if steps is None else int(steps)  # wrapper.jl:56
+        if record is None:
+            record = self.walkers == 1  # a single walker has no cross-walker error bar: keep its series
+        self.result = _make_result(hamiltonian, ansatz, np.zeros(ansatz.N_PARAMS), self.walkers, self.steps, seed,
+                                   record, burn_in, kernel, ctx)
+
+    def _reset_and_run(self, params, samples, steps):
+        if steps is None:
+            steps = (self.steps * self.walkers if samples is None else int(samples)) // self.walkers  # wrapper.jl:83
+        res = self.result
+        res.params = as_params(params, self.ansatz.N_PARAMS)  # _reset! (wrapper.jl:74-79)
+        return res._run(int(steps), keep=False)
+
+    def __call__(self, *args, samples=None, steps=None):
+        if len(args) == 3:  # qmc(F, G, params): Optim.only_fg! protocol (wrapper.jl:107-121)
+            F, G, params = args
+            res = self._reset_and_run(params, None, self.steps)
+            if G is not None:
+                val, grad = val_and_grad_result(res)
+                G[...] = grad
+            else:
+                val = mean(res)
+            return val if F is not None else None
+        (params,) = args
+        return mean(self._reset_and_run(params, samples, steps))  # wrapper.jl:81-88
+
+    def val_and_grad(self, params, *, samples=None, steps=None):
+        return val_and_grad_result(self._reset_and_run(params, samples, steps))  # wrapper.jl:90-97
+
+    def val_err_and_grad(self, params, *, samples=None, steps=None):
+        return val_err_and_grad_result(self._reset_and_run(params, samples, steps))  # wrapper.jl:98-105
+
+    def __repr__(self):
+        return (f"KineticVQMC(\n  {self.hamiltonian!r},\n  {self.ansatz!r};\n  steps={self.steps},\n"
+                f"  walkers={self.walkers},\n)")

@@ -1,0 +1,218 @@
+/*
+ * gutzwiller_b200.h -- C ABI of libgutzwiller_b200.so
+ *
+ * B200 (sm_100a) implementation of the kinetic variational-QMC hot path of mtsch/Gutzwiller.jl
+ * for HubbardReal1D + GutzwillerAnsatz.  The reference has no FFI layer (it is pure Julia); the
+ * drop-in boundary is its exported Julia API, and every entry point below names the reference
+ * definition it stands behind (paths relative to the reference repository root).  A Julia host
+ * binds these with `ccall` (see INTEGRATION.md and gutzwiller.jl_b200/julia/GutzwillerB200.jl); the
+ * Python mirror in gutzwiller.jl_b200/ binds the same symbols with ctypes.
+ *
+ * Conventions
+ *  - every function returns an int status (GWZ_OK = 0); gwz_last_error() gives the message of
+ *    the last failure on the calling thread.  No C++ exception crosses this boundary.
+ *  - the caller owns all in/out buffers (plain host pointers); the library owns the opaque
+ *    handles.  Calls block until the device work they issued is complete.
+ *  - a handle may be used by one host thread at a time; distinct handles concurrently.
+ *  - addresses are BoseFS{N,M} unary bitstrings (Rimu BitString semantics): W = ceil((N+M-1)/64)
+ *    64-bit words per address, word 0 = least significant, mode 1 at bit 0, n_i ones followed
+ *    by one 0 separator per mode.
+ *  - all floating point is FP64 (eltype(H) = Float64, src/ansatz/gutzwiller.jl:18).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    GWZ_ERR_CUDA.
+ */
+#ifndef GUTZWILLER_B200_H
+#define GUTZWILLER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWZ_VERSION 100
+#define GWZ_MAX_WORDS 4       /* 64-bit words per address (N+M-1 <= 251) */
+#define GWZ_NUM_PARAMS 1      /* GutzwillerAnsatz has one parameter g (gutzwiller.jl:14) */
+#define GWZ_NCCL_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+#define GWZ_NUM_ACC 12        /* doubles in the cross-device accumulator vector */
+
+enum gwz_status {
+    GWZ_OK = 0,
+    GWZ_ERR_INVALID = 1,   /* bad argument (Julia: ArgumentError) */
+    GWZ_ERR_CUDA = 2,      /* CUDA runtime failure / no device */
+    GWZ_ERR_NCCL = 3,      /* NCCL failure / libnccl not loadable */
+    GWZ_ERR_NONFINITE = 4, /* "Infinite residence time" (src/kinetic-vqmc/qmc.jl:34-36) */
+    GWZ_ERR_NOMEM = 5
+};
+
+/* which device code evaluates a step */
+enum gwz_kernel_kind {
+    GWZ_KERNEL_ENUMERATE = 0, /* walks the hops in the reference's offdiagonals order (qmc.jl:25-31);
+                                 move = first i with u*S < cumsum_i (qmc.jl:52-61) */
+    GWZ_KERNEL_BITPARALLEL = 1 /* production path: bond classes by popcount, class-ordered move
+                                  selection (same distribution, different u -> hop map) */
+};
+
+/* flags of gwz_vqmc_run */
+#define GWZ_RUN_KEEP_ACC 1u /* continue the estimators (kinetic_vqmc!(res), qmc.jl:108-111) instead of
+                               clearing them first (KineticVQMC `_reset!`, wrapper.jl:74-79) */
+
+typedef struct gwz_context gwz_context;
+typedef struct gwz_model gwz_model;
+typedef struct gwz_walkers gwz_walkers;
+typedef struct gwz_sweep gwz_sweep;
+
+const char *gwz_last_error(void);
+int gwz_version(void);
+
+/* ---- context: one CUDA device + stream (+ optional NCCL communicator) --------------------- */
+int gwz_context_create(int device, gwz_context **out);
+int gwz_context_destroy(gwz_context *ctx);
+int gwz_context_info(const gwz_context *ctx, int *device, int *sm_count, int *sm_clock_khz,
+                     int *cc_major, int *cc_minor, size_t *global_mem_bytes);
+/* raw cudaStream_t of the context, for timing with CUDA events on the launching stream */
+int gwz_context_stream(const gwz_context *ctx, void **cuda_stream);
+int gwz_context_synchronize(gwz_context *ctx);
+/* Multi-GPU (replaces Threads.@threads over walkers, qmc.jl:99-106, across devices).
+ * One process per GPU: rank 0 calls gwz_nccl_unique_id, ships the bytes to the other ranks,
+ * every rank calls gwz_context_comm_init.  One process driving several GPUs (a Julia host):
+ * create one context per device and call gwz_context_comm_init_all once. */
+int gwz_nccl_unique_id(uint8_t id[GWZ_NCCL_ID_BYTES]);
+int gwz_context_comm_init(gwz_context *ctx, int world_size, int rank, const uint8_t id[GWZ_NCCL_ID_BYTES]);
+int gwz_context_comm_init_all(gwz_context *const *ctxs, int n);
+int gwz_context_comm_info(const gwz_context *ctx, int *world_size, int *rank);
+
+/* ---- model: HubbardReal1D(BoseFS{N,M}; u, t) + GutzwillerAnsatz(H) ------------------------- */
+/* replaces `H = HubbardReal1D(addr; u, t); ansatz = GutzwillerAnsatz(H)` (gutzwiller.jl:14-21) */
+int gwz_model_create_hubbard1d_gutzwiller(gwz_context *ctx, int N, int M, double u, double t, gwz_model **out);
+int gwz_model_destroy(gwz_model *m);
+int gwz_model_info(const gwz_model *m, int *N, int *M, double *u, double *t, int *bits, int *words);
+/* Rimu `near_uniform(BoseFS{N,M})`, `BoseFS(onr)`, `onr(addr)` -- host helpers, W words per address */
+int gwz_model_near_uniform(const gwz_model *m, uint64_t *addr_words);
+int gwz_model_from_onr(const gwz_model *m, const int32_t *onr, uint64_t *addr_words);
+int gwz_model_to_onr(const gwz_model *m, const uint64_t *addr_words, int32_t *onr);
+/* number of Fock states C(N+M-1, N) as a double, and exactly when it fits in 64 bits (else 0) */
+int gwz_model_dimension(const gwz_model *m, double *dim, uint64_t *dim_exact);
+
+/* ---- per-address probe: one kinetic_sample! per address (qmc.jl:14-44) --------------------- */
+/* addr_words: n x W.  params: GWZ_NUM_PARAMS doubles.  u01: n uniforms in [0,1) or NULL (0.5).
+ * Outputs (each may be NULL): e_loc[n] (qmc.jl:37), residence_time[n] (:33), grad_ratio[n x P]
+ * (:38), n_hops[n] (:15), rates[n x 2M] = |psi(addr2)|/|psi(addr1)| in reference hop order,
+ * zero padded (ENUMERATE only), chosen[n] 1-based reference hop index of the selected move,
+ * next_addr[n x W] (:40-41). */
+int gwz_probe_addresses(gwz_model *m, const uint64_t *addr_words, size_t n, const double *params,
+                        const double *u01, int kernel_kind, double *e_loc, double *residence_time,
+                        double *grad_ratio, int32_t *n_hops, double *rates, int32_t *chosen,
+                        uint64_t *next_addr);
+/* GutzwillerAnsatz value and gradient per address (gutzwiller.jl:25-36): val[n], grad[n x P] */
+int gwz_ansatz_val_and_grad(gwz_model *m, const uint64_t *addr_words, size_t n, const double *params,
+                            double *val, double *grad);
+
+/* ---- walkers: KineticVQMCWalkerState x n (state.jl:10-28), resident in HBM ------------------ */
+/* n_walkers local walkers whose global ids are global_offset .. global_offset+n_walkers-1 (the
+ * Philox stream of a walker depends only on (seed, global id, step), so results do not depend on
+ * how walkers are sharded).  start_addr: W words, broadcast to all walkers (state.jl:26). */
+int gwz_walkers_create(gwz_model *m, uint64_t n_walkers, uint64_t global_offset, const uint64_t *start_addr,
+                       uint64_t seed, gwz_walkers **out);
+int gwz_walkers_destroy(gwz_walkers *w);
+int gwz_walkers_count(const gwz_walkers *w, uint64_t *n_walkers, uint64_t *steps_done);
+/* curr_address of every walker (n x W) -- continuation / checkpoint (state.jl:14, qmc.jl:95) */
+int gwz_walkers_get_addresses(gwz_walkers *w, uint64_t *addr_words);
+int gwz_walkers_set_addresses(gwz_walkers *w, const uint64_t *addr_words);
+int gwz_walkers_set_step_counter(gwz_walkers *w, uint64_t steps_done);
+
+typedef struct gwz_vqmc_result {
+    double val;                      /* mean over walkers of per-walker ratio estimates (state.jl:137-149) */
+    double err;                      /* standard error of that mean across walkers (NaN for 1 walker) */
+    double grad[GWZ_NUM_PARAMS];     /* state.jl:42-49 then :137-149 */
+    double grad_err[GWZ_NUM_PARAMS]; /* cross-walker standard error of grad */
+    double pooled_val;               /* sum tau E / sum tau over all walkers and steps */
+    double pooled_grad[GWZ_NUM_PARAMS];
+    double pooled_var;               /* time-weighted variance of E_loc (state.jl:293-298 pooled) */
+    double total_time;               /* sum of residence times */
+    uint64_t walkers;                /* global walker count (all ranks) */
+    uint64_t steps;                  /* global walker-steps accumulated in the estimators */
+    uint64_t hops;                   /* global hop evaluations = sum over steps of length(offdiagonals) */
+    double acc[GWZ_NUM_ACC];         /* raw all-reduced accumulator vector */
+    float kernel_ms;                 /* device time of the sampling kernel(s) of this call (this rank) */
+} gwz_vqmc_result;
+
+/* kinetic_vqmc!(states; steps) (qmc.jl:73-106) + val_and_grad(result) (state.jl:137-149) + the
+ * cross-device all-reduce.  burn_in steps are sampled first without accumulating (0 = reference
+ * behaviour).  Collective when the context has a communicator: every rank must call it. */
+int gwz_vqmc_run(gwz_walkers *w, const double *params, uint64_t steps_per_walker, uint64_t burn_in,
+                 int kernel_kind, unsigned flags, gwz_vqmc_result *out);
+/* same, for several walker sets living on different devices of ONE process (contexts joined by
+ * gwz_context_comm_init_all); out receives the global result */
+int gwz_vqmc_run_group(gwz_walkers *const *ws, int n, const double *params, uint64_t steps_per_walker,
+                       uint64_t burn_in, int kernel_kind, unsigned flags, gwz_vqmc_result *out);
+/* per-walker estimates of the estimators accumulated so far: val_w[n], grad_w[n x P] (state.jl:42-49) */
+int gwz_walkers_estimates(gwz_walkers *w, double *val_w, double *grad_w);
+/* Recording run: like gwz_vqmc_run but also returns the per-step series the reference stores
+ * (qmc.jl:89-92): tau[steps x n], eloc[steps x n] (step-major), addr[steps x n x W] (may be NULL). */
+int gwz_vqmc_run_record(gwz_walkers *w, const double *params, uint64_t steps_per_walker, int kernel_kind,
+                        unsigned flags, double *tau, double *eloc, uint64_t *addr, gwz_vqmc_result *out);
+
+/* ---- LocalEnergyEvaluator (src/localenergy.jl:81-173) --------------------------------------- */
+/* basis_words: dim x W stored basis (reference layout `basis::Vector{A}`, localenergy.jl:84), copied
+ * to HBM once; or NULL => all C(N+M-1,N) states enumerated on the fly by rank in [rank_begin,
+ * rank_end) (rank_end = 0 => dimension), requires N+M-1 <= 64. */
+int gwz_sweep_create(gwz_model *m, const uint64_t *basis_words, uint64_t dim, uint64_t rank_begin,
+                     uint64_t rank_end, gwz_sweep **out);
+int gwz_sweep_destroy(gwz_sweep *s);
+int gwz_sweep_dim(const gwz_sweep *s, uint64_t *dim);
+/* le(p) (localenergy.jl:131-155) */
+int gwz_sweep_val(gwz_sweep *s, const double *params, double *val);
+/* val_and_grad(le, p) (localenergy.jl:94-129); acc4 (may be NULL) = (num, den, num_grad, den_grad)
+ * after the cross-device all-reduce */
+int gwz_sweep_val_and_grad(gwz_sweep *s, const double *params, double *val, double *grad, double *acc4);
+/* per-state (num, den, num_grad, den_grad) of localenergy.jl:105-120 for states first..first+count-1
+ * of this sweep: out[count x 4] */
+int gwz_sweep_terms(gwz_sweep *s, const double *params, uint64_t first, uint64_t count, double *out);
+/* the states themselves (enumeration order of this sweep): out[count x W] */
+int gwz_sweep_states(gwz_sweep *s, uint64_t first, uint64_t count, uint64_t *out);
+/* device time (ms) of the last sweep kernel */
+int gwz_sweep_last_kernel_ms(const gwz_sweep *s, float *ms);
+
+/* ---- error bars: resample! (state.jl:194-231) + Rimu.StatsTools.blocking_analysis ---------- */
+int gwz_resample(double *result, size_t len, const double *residence_times, const double *values, size_t n);
+typedef struct gwz_blocking_result {
+    double mean, err, err_err, p_cov;
+    int32_t k; /* -1: blocking unsuccessful (state.jl:250-253) */
+    int64_t blocks;
+} gwz_blocking_result;
+int gwz_blocking_analysis(const double *v, size_t n, gwz_blocking_result *out);
+
+/* ---- adaptive_gradient_descent / gradient_descent / amsgrad (src/amsgrad.jl:105-263) -------- */
+typedef int (*gwz_objective_fn)(void *user, const double *p, int np, double *val, double *err, double *grad);
+typedef struct gwz_gd_opts {
+    int32_t maxiter;     /* 100 */
+    int32_t use_amsgrad; /* 1: amsgrad (amsgrad.jl:259-263), 0: gradient_descent (:240-244) */
+    int32_t early_stop;  /* 1 */
+    int32_t reserved;
+    double alpha, beta1, beta2;                   /* 0.01, 0.1, 0.01 */
+    double grad_tol, param_tol, val_tol, err_tol; /* sqrt(eps) x3, 0.0 */
+    const double *first_moment_init;              /* NULL: gradient at p0 (amsgrad.jl:138-142) */
+    const double *second_moment_init;             /* NULL: zeros (:143-147) */
+    const uint8_t *fix_params;                    /* NULL: none */
+} gwz_gd_opts;
+int gwz_gd_opts_default(gwz_gd_opts *o);
+/* rows = maxiter + 1; vector traces hold rows x np doubles, scalar traces rows doubles */
+typedef struct gwz_gd_trace {
+    int32_t iterations, converged, reason; /* reason: 0 iterations 1 params 2 gradient 3 value 4 errorbars */
+    int32_t np;
+    double *param, *value, *error, *gradient, *first_moment, *second_moment, *param_delta;
+} gwz_gd_trace;
+/* generic driver: any objective (amsgrad.jl:117-226) */
+int gwz_adaptive_gradient_descent(gwz_objective_fn val_and_grad, gwz_objective_fn val_err_and_grad, void *user,
+                                  const double *p0, int np, const gwz_gd_opts *opts, gwz_gd_trace *trace);
+/* built-in objectives: amsgrad(qmc::KineticVQMC, p0) and amsgrad(le::LocalEnergyEvaluator, p0) */
+int gwz_amsgrad_vqmc(gwz_walkers *w, const double *p0, const gwz_gd_opts *opts, uint64_t steps_per_walker,
+                     int kernel_kind, gwz_gd_trace *trace);
+int gwz_amsgrad_sweep(gwz_sweep *s, const double *p0, const gwz_gd_opts *opts, gwz_gd_trace *trace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUTZWILLER_B200_H */

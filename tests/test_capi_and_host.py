@@ -1,0 +1,203 @@
+"""CPU tests of the drop-in boundary and the host logic (no compute calls: there is no GPU here)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gutzwiller_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(gwz_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol(gw):
+    import ctypes
+    L = ctypes.CDLL(gw.capi.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/gutzwiller_b200.h but not exported"
+    # and the Python binding covers exactly the declared set
+    assert sorted(gw.capi.SIGNATURES) == declared
+
+
+def test_no_torch_types_in_abi():
+    text = open(HEADER).read()
+    assert "torch" not in text.lower() and "at::" not in text
+    assert 'extern "C"' in text
+
+
+def test_version_and_error_channel(gw):
+    L = gw.lib()
+    assert L.gwz_version() == 100
+    import ctypes as C
+    h = C.c_void_p()
+    rc = L.gwz_context_create(0, None)
+    assert rc == gw.capi.ERR_INVALID and b"NULL" in L.gwz_last_error()
+    del h
+
+
+def test_no_cpu_fallback_without_gpu(gw):
+    """Without a CUDA device every compute entry point must fail loudly (no CPU path)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(gw.GutzwillerError, match="no CUDA device"):
+        gw.Context(0)
+    H = gw.HubbardReal1D(gw.near_uniform(4, 4))
+    with pytest.raises(gw.GutzwillerError):
+        gw.kinetic_vqmc(H, gw.GutzwillerAnsatz(H), [0.5], samples=100, walkers=1)
+    with pytest.raises(gw.GutzwillerError):
+        gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gutzwiller.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+    assert "oracle" not in open(os.path.join(ROOT, "gutzwiller_b200.py")).read().lower()
+
+
+def test_bosefs_and_near_uniform(gw, oracle_mod):
+    a = gw.near_uniform(10, 10)
+    assert int(a.words[0]) == 0b1010101010101010101 and a.onr() == (1,) * 10
+    assert repr(a) == 'fs"|1 1 1 1 1 1 1 1 1 1⟩"'
+    b = gw.BoseFS((2, 0, 1))
+    assert int(b.words[0]) == 0b10011 and b.N == 3 and b.M == 3  # SURVEY App. A.1 example
+    assert gw.BoseFS(1, 1, 1, 1) == gw.BoseFS((1, 1, 1, 1))
+    rng = np.random.default_rng(3)
+    for N, M in [(7, 3), (50, 50), (100, 100), (33, 32), (13, 40)]:
+        o = oracle_mod.Oracle(N, M)
+        onr = rng.multinomial(N, rng.dirichlet(np.ones(M)))
+        fs = gw.BoseFS(onr)
+        assert np.array_equal(fs.words, o.from_onr(onr)[: fs.words.size])
+        assert fs.onr() == tuple(int(x) for x in onr)
+        assert gw.BoseFS.from_words(N, M, fs.words) == fs
+        nu = gw.near_uniform(N, M)
+        assert np.array_equal(nu.words, o.near_uniform()[: nu.words.size])
+    with pytest.raises(ValueError):
+        gw.BoseFS.from_words(3, 3, [0b111111])
+
+
+def test_ansatz_traits(gw):
+    H = gw.HubbardReal1D(gw.near_uniform(5, 5), t=0.1)
+    ans = gw.GutzwillerAnsatz(H)
+    assert gw.num_parameters(ans) == 1 and gw.keytype(ans) is gw.BoseFS and gw.valtype(ans) is float
+    assert gw.starting_address(H) == gw.near_uniform(5, 5)
+    assert H.u == 1.0 and H.t == 0.1
+    with pytest.raises(TypeError):
+        gw.GutzwillerAnsatz("not a hamiltonian")
+
+
+def test_shard_range_partitions(gw):
+    for total in (1, 7, 2 ** 24, 1352078):
+        for world in (1, 2, 3, 4, 8):
+            spans = [gw.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        gw.shard_range(10, 2, 2)
+
+
+def test_default_walkers_and_steps_rule(gw):
+    assert gw.default_walkers(1e6) == 512 and gw.default_walkers(1e8) == 65536 and gw.default_walkers(100) == 1
+    assert gw.default_walkers(1e12) == 1 << 20
+
+
+def test_resample_and_blocking_host_functions(gw, oracle_mod):
+    o = oracle_mod.Oracle(2, 2)
+    rng = np.random.default_rng(11)
+    t, v = rng.random(257) + 0.01, rng.standard_normal(257)
+    for k in (1, 2, 7, 64, 257, 1000):
+        got, ref = gw.resample(t, v, len=k), o.resample(t, v, k)
+        assert np.allclose(got, ref, rtol=0, atol=1e-13)
+        assert abs(got.mean() - np.sum(t * v) / np.sum(t)) < 1e-12  # test/runtests.jl:10-19
+    with pytest.raises(ValueError, match="do not match"):
+        gw.resample(t, v[:-1])
+    x = np.cumsum(rng.standard_normal(5000)) * 0.01 + rng.standard_normal(5000)
+    a, b = gw.blocking_analysis(x), o.blocking_analysis(x)
+    assert (a.k, a.blocks) == (b.k, b.blocks) and abs(a.err - b.err) < 1e-14 and abs(a.mean - b.mean) < 1e-14
+    one = gw.blocking_analysis([3.0])
+    assert one.k == 0 and one.mean == 3.0
+
+
+def test_generic_gradient_descent_driver_on_python_objective(gw):
+    """amsgrad.jl:117-226 driven through the C callback ABI with a plain quadratic objective."""
+    class Quad:
+        def val_and_grad(self, p):
+            return float(np.sum((p - 1.5) ** 2)), 2 * (p - 1.5)
+    gd = gw.gradient_descent(Quad(), [0.0, 3.0], α=0.1, maxiter=200)
+    assert gd.converged and np.allclose(gd.param[-1], 1.5, atol=1e-3)  # stops on val_tol
+    ams = gw.amsgrad(Quad(), [0.0, 3.0], maxiter=30, early_stop=False)
+    assert ams.iterations == 31 and not ams.converged and ams.reason == "iterations"  # maxiter+1 rows
+    # first row reproduces the update rule: m1 = 0.9*g0 + 0.1*g, m2 = 0.01*g^2, dp = -0.01*m1/sqrt(m2)
+    g0 = 2 * (np.array([0.0, 3.0]) - 1.5)
+    assert np.allclose(ams.first_moment[0], g0) and np.allclose(ams.second_moment[0], 0.01 * g0 ** 2)
+    assert np.allclose(ams.param_delta[0], -0.01 * g0 / np.sqrt(0.01 * g0 ** 2))
+    # fix_params keeps a coordinate (test/amsgrad.jl:38-50)
+    fx = gw.amsgrad(Quad(), [0.0, 3.0], fix_params=(False, True), maxiter=50, early_stop=False)
+    assert np.all(fx.param[:, 1] == 3.0) and fx.param[-1, 0] > 0.0
+    # continuation from a result == passing its last moments (test/amsgrad.jl:52-77, exact)
+    a = gw.amsgrad(Quad(), [0.0, 3.0], maxiter=20, early_stop=False)
+    b = gw.amsgrad(Quad(), a.param[-1], first_moment_init=a.first_moment[-1], second_moment_init=a.second_moment[-1],
+                   maxiter=10, early_stop=False)
+    d = gw.amsgrad(Quad(), a, maxiter=10, early_stop=False)
+    assert np.array_equal(b.param, d.param)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle.oracle import Oracle
+    import gutzwiller_b200 as gw
+    o = Oracle(6, 6, 2.0, 1.0)
+    total, steps = 10, 300
+    b, e = gw.shard_range(total, world, rank)
+    addrs = np.stack([o.near_uniform()] * (e - b))
+    out = o.kinetic_vqmc(0.7, addrs, steps, seed=99, walker0=b)
+    # the accumulator vector the GPU path all-reduces (walkers, sum val_w, sum grad_w)
+    acc = torch.tensor([e - b, out["val_w"].sum(), out["grad_w"].sum()], dtype=torch.float64)
+    dist.all_reduce(acc)
+    q.put((rank, acc.tolist()))
+    dist.destroy_process_group()
+
+
+def test_sharding_is_invariant_under_world_size_gloo(oracle_mod):
+    """World-size-2 gloo run of the N>1 host logic: contiguous shards by global walker id, Philox
+    keyed by the global id, one sum all-reduce of the accumulator vector => same result as 1 rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = oracle_mod.Oracle(6, 6, 2.0, 1.0)
+    single = o.kinetic_vqmc(0.7, np.stack([o.near_uniform()] * 10), 300, seed=99, walker0=0)
+    for _, acc in res:
+        assert acc[0] == 10
+        assert abs(acc[1] / 10 - single["val"]) < 1e-12 and abs(acc[2] / 10 - single["grad"]) < 1e-11
