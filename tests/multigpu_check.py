@@ -1,0 +1,74 @@
+"""Multi-GPU parity script (needs >= 2 GPUs; not collected by pytest).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py            # one process per GPU, NCCL all-reduce of the accumulators
+    python tests/multigpu_check.py --single-process 2   # one process, several devices (what a Julia host does)
+
+Checks that the sharded run (global walker ids, one ncclAllReduce per run) reproduces the single-GPU run
+of the same global walkers to FP reduction order, for the VQMC estimators and for the sweep.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gutzwiller_b200 as gw  # noqa: E402
+
+N, M, U, G, TOTAL, STEPS = 50, 50, 2.0, 0.5, 1 << 16, 200
+
+
+def reference_single_gpu(device):
+    ctx = gw.Context(device)  # fresh context without communicator
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=U)
+    w = gw.Walkers(H.model(ctx), TOTAL, H.address.words, seed=123)
+    r = w.run([G], STEPS)
+    H12 = gw.HubbardReal1D(gw.near_uniform(12, 12), u=U)
+    le = gw.LocalEnergyEvaluator(H12, gw.GutzwillerAnsatz(H12), ctx=ctx)
+    return r, le.accumulators(0.4)
+
+
+def check(r, ref, acc, ref_acc, tag):
+    assert r.walkers == TOTAL and r.steps == TOTAL * STEPS and r.hops == ref.hops, (tag, r.walkers, r.steps)
+    assert abs(r.val - ref.val) <= 1e-13 * abs(ref.val), (tag, r.val, ref.val)
+    assert abs(r.grad[0] - ref.grad[0]) <= 1e-10 * abs(ref.grad[0]), (tag, r.grad[0], ref.grad[0])
+    assert abs(r.pooled_val - ref.pooled_val) <= 1e-13 * abs(ref.pooled_val), tag
+    assert abs(r.err - ref.err) <= 1e-9 * ref.err, tag
+    assert np.all(np.abs(acc - ref_acc) <= 1e-13 * np.abs(ref_acc)), (tag, acc, ref_acc)
+    print(f"[{tag}] OK val={r.val:.12f} grad={r.grad[0]:.9f} pooled={r.pooled_val:.12f} sweep_num={acc[0]:.12e}", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--single-process", type=int, default=0)
+    a = ap.parse_args()
+    if a.single_process:
+        n = a.single_process
+        ctxs = [gw.Context(d) for d in range(n)]
+        gw.comm_init_all(ctxs)
+        H = gw.HubbardReal1D(gw.near_uniform(N, M), u=U)
+        sets = []
+        for d in range(n):
+            b, e = gw.shard_range(TOTAL, n, d)
+            sets.append(gw.Walkers(H.model(ctxs[d]), e - b, H.address.words, seed=123, global_offset=b))
+        r = gw.run_group(sets, [G], STEPS)
+        ref, ref_acc = reference_single_gpu(0)
+        check(r, ref, ref_acc, ref_acc, f"single-process x{n}")
+        return
+    world, rank = gw.init_distributed()
+    assert world > 1, "launch with torch.distributed.run"
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=U)
+    res = gw.kinetic_vqmc(H, gw.GutzwillerAnsatz(H), [G], walkers=TOTAL, steps=STEPS, seed=123, record=False)
+    H12 = gw.HubbardReal1D(gw.near_uniform(12, 12), u=U)
+    acc = gw.LocalEnergyEvaluator(H12, gw.GutzwillerAnsatz(H12)).accumulators(0.4)  # rank-range shards + all-reduce
+    ref, ref_acc = reference_single_gpu(int(os.environ.get("LOCAL_RANK", "0")))
+    check(res.last, ref, acc, ref_acc, f"rank {rank}/{world}")
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
