@@ -83,6 +83,7 @@ struct gwz_walkers {
     double* d_partials = nullptr;
     int partials_cap = 0;
     double* d_vec = nullptr;  // NUM_ACC doubles: this set's reduced vector
+    double* d_shift = nullptr;  // (E_ref, G_ref): reference point of the shifted running sums
 };
 
 struct gwz_sweep {
@@ -259,6 +260,8 @@ extern "C" int gwz_model_create_hubbard1d_gutzwiller(gwz_context* ctx, int N, in
     dm.ext_bs = (B + 1) & 31;
     dm.u = u;
     dm.t = t;
+    dm.extmask_lo[dm.ext_ws] = 0xFFFFFFFFu;
+    if (dm.ext_bs != 0 && dm.ext_ws + 1 < MAXNW) dm.extmask_hi[dm.ext_ws + 1] = 0xFFFFFFFFu;
     for (int p = 0; p <= B; ++p) dm.zmask[p >> 5] |= 1u << (p & 31);
     for (int p = 0; p < B; ++p) dm.amask[p >> 5] |= 1u << (p & 31);
     *out = m;
@@ -498,6 +501,8 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     GWZ_CUDA(cudaMalloc(&w->d_addr, sizeof(uint64_t) * w->n * m->W));
     GWZ_CUDA(cudaMalloc(&w->d_acc, sizeof(double) * w->n * NUM_WALKER_ACC));
     GWZ_CUDA(cudaMalloc(&w->d_vec, sizeof(double) * NUM_ACC));
+    GWZ_CUDA(cudaMalloc(&w->d_shift, sizeof(double) * 2));
+    GWZ_CUDA(cudaMemsetAsync(w->d_shift, 0, sizeof(double) * 2, c->stream));
     DevBuf<uint64_t> d_start;
     GWZ_CUDA(d_start.alloc(m->W));
     GWZ_CUDA(cudaMemcpyAsync(d_start.p, start_addr, sizeof(uint64_t) * m->W, cudaMemcpyHostToDevice, c->stream));
@@ -514,6 +519,7 @@ extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
     cudaFree(w->d_acc);
     cudaFree(w->d_partials);
     cudaFree(w->d_vec);
+    cudaFree(w->d_shift);
     delete w;
     return GWZ_OK;
 }
@@ -575,7 +581,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     if (int rc = use_device(c)) return rc;
     const bool record = rec_tau != nullptr;
     int grid = 0;
-    GWZ_CUDA(walker_grid(m->nw, kind, record, w->n, c->prop.multiProcessorCount, &grid));
+    GWZ_CUDA(walker_grid(m->nw, m->N, kind, record, w->n, c->prop.multiProcessorCount, &grid));
     if (int rc = ensure_partials(w, grid)) return rc;
     WalkerLaunch L;
     L.dm = m->dm;
@@ -590,6 +596,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.partials = w->d_partials;
     L.grid = grid;
     L.err_flag = c->d_err;
+    L.shift = w->d_shift;
     L.rec_tau = nullptr;
     L.rec_eloc = nullptr;
     L.rec_addr = nullptr;
@@ -600,13 +607,15 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         L.accumulate = 0;
         L.reset_acc = 0;
         int g2 = 0;
-        GWZ_CUDA(walker_grid(m->nw, kind, false, w->n, c->prop.multiProcessorCount, &g2));
+        GWZ_CUDA(walker_grid(m->nw, m->N, kind, false, w->n, c->prop.multiProcessorCount, &g2));
         L.grid = g2;
         GWZ_CUDA(launch_walkers(L, c->stream));
         w->steps_done += burn_in;
         L.grid = grid;
     }
     const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
+    if (!keep)  // new estimator: pick its reference point from where the walkers are now
+        GWZ_CUDA(launch_walker_ref(m->dm, tb, m->nw, w->d_addr, w->n, w->d_shift, c->stream));
     L.step0 = w->steps_done;
     L.steps = steps;
     L.accumulate = 1;
@@ -752,7 +761,7 @@ extern "C" int gwz_walkers_estimates(gwz_walkers* w, double* val_w, double* grad
     DevBuf<double> d_v, d_g;
     GWZ_CUDA(d_v.alloc(w->n));
     GWZ_CUDA(d_g.alloc(w->n));
-    GWZ_CUDA(launch_walker_estimates(w->d_acc, w->n, d_v.p, d_g.p, c->stream));
+    GWZ_CUDA(launch_walker_estimates(w->d_acc, w->n, w->d_shift, d_v.p, d_g.p, c->stream));
     if (val_w) GWZ_CUDA(cudaMemcpyAsync(val_w, d_v.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
     if (grad_w) GWZ_CUDA(cudaMemcpyAsync(grad_w, d_g.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));

@@ -32,7 +32,11 @@ struct DevModel {
     double u, t;
     uint32_t zmask[MAXNW];  // bits 0..B   (bond positions)
     uint32_t amask[MAXNW];  // bits 0..B-1 (address bits)
+    uint32_t extmask_lo[MAXNW];  // all ones for word ext_ws, else 0
+    uint32_t extmask_hi[MAXNW];  // all ones for word ext_ws+1 (if ext_bs != 0), else 0
 };
+
+constexpr int STEP_BLOCK = 128;  // threads per CTA of every kernel that selects moves (scratch layout)
 
 // Everything that depends on the variational parameter g; passed by value as a kernel
 // argument so that statically indexed entries become constant-bank operands.
@@ -46,6 +50,38 @@ struct DevTables {
     double RL[NCLS];     // rate of the left hop  (0 if R==0)
     double IRR[NCLS];    // 1/RR (0 if RR==0)
     double IRL[NCLS];
+};
+
+// Per-CTA shared-memory scratch of the bond evaluation.  Values that are *dynamically indexed* (class
+// prefix sums and class masks during move selection; the bitstring itself in the rare generic-bond
+// path) are staged here so that the register arrays stay statically indexed.  Per-thread entries use
+// the layout [entry][thread] (conflict-free); exptab is shared by the CTA.
+template <int NW>
+struct StepScratch {
+    double* exptab;  // [2N+2]: exp(-c*(i-N)), i.e. the hop rate for Delta = i-N in [-N+1, N+1]
+    double* cum;     // [NCLS][STEP_BLOCK]
+    uint32_t* el;    // [KCAP][NW][STEP_BLOCK]
+    uint32_t* er;    // [KCAP][NW][STEP_BLOCK]
+    uint32_t* ew;    // [NW][STEP_BLOCK] extended bitstring   (staged only when a generic bond exists)
+    uint32_t* bw;    // [NW][STEP_BLOCK] generic-bond mask
+    __host__ __device__ static constexpr size_t exptab_bytes(int N) { return sizeof(double) * (size_t)(2 * N + 2); }
+    __host__ __device__ static constexpr size_t bytes(int N) {
+        return exptab_bytes(N) + sizeof(double) * NCLS * STEP_BLOCK +
+               sizeof(uint32_t) * (2 * KCAP * NW + 2 * NW) * STEP_BLOCK;
+    }
+    __device__ __forceinline__ StepScratch(unsigned char* base, int N) {
+        exptab = reinterpret_cast<double*>(base);
+        cum = exptab + (2 * N + 2);
+        el = reinterpret_cast<uint32_t*>(cum + NCLS * STEP_BLOCK);
+        er = el + KCAP * NW * STEP_BLOCK;
+        ew = er + KCAP * NW * STEP_BLOCK;
+        bw = ew + NW * STEP_BLOCK;
+    }
+    // CTA-wide: tabulate the hop rates once per launch (keeps exp() out of the step loop)
+    __device__ __forceinline__ void fill_exptab(int N, double c) const {
+        for (int i = threadIdx.x; i < 2 * N + 2; i += blockDim.x) exptab[i] = exp(-c * (double)(i - N));
+        __syncthreads();
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -143,14 +179,9 @@ template <int NW>
 __device__ __forceinline__ void extend(const uint32_t (&a)[NW], const DevModel& dm, uint32_t (&e)[NW]) {
     const uint32_t low = a[0] & ((1u << KCAP) - 1u);
     const uint32_t lo_part = low << dm.ext_bs;
-    const uint32_t hi_part = dm.ext_bs ? (low >> (32 - dm.ext_bs)) : 0u;
+    const uint32_t hi_part = __funnelshift_l(low, 0u, dm.ext_bs);  // low >> (32 - ext_bs), 0 when ext_bs == 0
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        uint32_t v = a[i];
-        v |= (i == dm.ext_ws) ? lo_part : 0u;
-        v |= (i == dm.ext_ws + 1) ? hi_part : 0u;
-        e[i] = v;
-    }
+    for (int i = 0; i < NW; ++i) e[i] = a[i] | (lo_part & dm.extmask_lo[i]) | (hi_part & dm.extmask_hi[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -181,38 +212,85 @@ __device__ __forceinline__ void apply_hop(uint32_t (&a)[NW], const DevModel& dm,
 }
 
 // ------------------------------------------------------------------------------------------
-// generic run lengths around a bond (slow path, any occupation): operate on a local copy so
-// that the register-resident arrays never get dynamically indexed
+// Generic bonds (a run of >= KCAP particles on either side): rare, so they are handled by ONE small
+// out-of-line routine that reads the staged bitstring from shared memory (dynamic indexing is free
+// there) and the tabulated rates.  Keeping this path compact matters: the step loop must stay
+// resident in the 32 KB L1.5 instruction cache even when some warps take it.
 // ------------------------------------------------------------------------------------------
-static __device__ __noinline__ void bond_runs_generic(const uint32_t* t, int B, int z, int& L, int& R) {
-    // ones directly below z
-    int n = 0;
-    int p = z - 1;
-    while (p >= 0) {
-        const int w = p >> 5, b = p & 31;
-        const uint32_t x = ~(t[w] << (31 - b));      // leading zeros of x = leading ones of the window
-        int c = x ? __clz(x) : 32;
-        c = min(c, b + 1);
-        n += c;
-        if (c < b + 1) break;
-        p -= c;
+struct BigOut {
+    double S, E, ED;  // mode 0: sums over the generic bonds
+    long long d;
+    int nocc;
+    int z, right;     // mode 1: selected hop
+};
+
+// ew/bw/exptab: shared memory (ew, bw already offset by threadIdx.x; stride STEP_BLOCK).
+// mode 0: accumulate; mode 1: find the hop whose interval of the running sum contains t.
+static __device__ __noinline__ BigOut big_pass(const uint32_t* ew, const uint32_t* bw, int nw, int B, int N,
+                                               const double* exptab, int mode, double t) {
+    BigOut o;
+    o.S = o.E = o.ED = 0.0;
+    o.d = 0;
+    o.nocc = 0;
+    o.z = -1;
+    o.right = 1;
+    double acc = 0.0;
+    for (int i = 0; i < nw; ++i) {
+        uint32_t m = bw[i * STEP_BLOCK];
+        while (m) {
+            const int z = 32 * i + (__ffs(m) - 1);
+            m &= m - 1;
+            // ones directly below z
+            int L = 0;
+            for (int p = z - 1; p >= 0;) {
+                const int b = p & 31;
+                const uint32_t x = ~(ew[(p >> 5) * STEP_BLOCK] << (31 - b));
+                int c = x ? __clz(x) : 32;
+                c = min(c, b + 1);
+                L += c;
+                if (c < b + 1) break;
+                p -= c;
+            }
+            // ones directly above z; for the periodic bond (z == B) that is mode 1 = trailing ones.
+            // Bit B of the staged string is 0, so the scan stops at B at the latest.
+            int R = 0;
+            for (int p = (z == B) ? 0 : z + 1; p < B;) {
+                const int b = p & 31;
+                const uint32_t x = ~(ew[(p >> 5) * STEP_BLOCK] >> b);
+                int c = x ? (__ffs(x) - 1) : 32;
+                c = min(min(c, 32 - b), B - p);
+                R += c;
+                if (c < 32 - b || p + c >= B) break;
+                p += c;
+            }
+            const double rr = (L > 0) ? exptab[(R - L + 1) + N] : 0.0;
+            const double rl = (R > 0) ? exptab[(L - R + 1) + N] : 0.0;
+            if (mode == 0) {
+                const double er = sqrt((double)L * (double)(R + 1)) * rr;
+                const double el = sqrt((double)R * (double)(L + 1)) * rl;
+                o.S += rr;
+                o.S += rl;
+                o.E += er + el;
+                o.ED += er * (double)(R - L + 1) + el * (double)(L - R + 1);
+                o.nocc += (L > 0);
+                o.d += (long long)L * (L - 1) / 2;
+            } else {
+                if (rr > 0.0) {
+                    acc += rr;
+                    o.z = z;
+                    o.right = 1;
+                    if (t < acc) return o;
+                }
+                if (rl > 0.0) {
+                    acc += rl;
+                    o.z = z;
+                    o.right = 0;
+                    if (t < acc) return o;
+                }
+            }
+        }
     }
-    L = n;
-    // ones directly above z; for the virtual separator (z == B) this is mode 1 = trailing ones of a.
-    // e has bit B == 0, so the scan stops at B at the latest.
-    n = 0;
-    p = (z == B) ? 0 : z + 1;
-    while (p < B) {
-        const int w = p >> 5, b = p & 31;
-        const uint32_t x = ~(t[w] >> b);             // trailing zeros of x = trailing ones of the window
-        int c = x ? (__ffs(x) - 1) : 32;
-        c = min(c, 32 - b);
-        c = min(c, B - p);
-        n += c;
-        if (c < 32 - b || p + c >= B) break;
-        p += c;
-    }
-    R = n;
+    return o;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -274,30 +352,33 @@ struct BondSums {
     int nocc;        // occupied modes, n_hops = 2*nocc                         (qmc.jl:15)
 };
 
-// rates of one generic bond
-__device__ __forceinline__ void generic_bond_terms(int L, int R, double c, double& rr, double& rl, double& er,
-                                                   double& el) {
-    rr = (L > 0) ? exp(-c * (double)(R - L + 1)) : 0.0;
-    rl = (R > 0) ? exp(-c * (double)(L - R + 1)) : 0.0;
-    er = (L > 0) ? sqrt((double)L * (double)(R + 1)) * rr : 0.0;
-    el = (R > 0) ? sqrt((double)R * (double)(L + 1)) * rl : 0.0;
-}
+// Sum over all bonds.  The running sum of class weights cnt[k]*FS[k] (k ascending) after class k is
+// handed to `sink(k, S)` (kept for the class-ordered move selection; a no-op for the sweep).  Class 0
+// (L = R = 0: an empty bond) carries no hop and is skipped.  WITH_GRAD adds the ED sum needed by
+// the sweep gradient.  Returns the total weight of the regular classes.
+struct NoCumSink {
+    __device__ __forceinline__ void operator()(int, double) const {}
+};
+struct SmemCumSink {
+    double* cum;  // already offset by threadIdx.x
+    __device__ __forceinline__ void operator()(int k, double v) const { cum[k * STEP_BLOCK] = v; }
+};
 
-// Sum over all bonds.  cum[k] = running sum of class weights cnt[k]*FS[k] (k ascending), kept for
-// the class-ordered move selection.  WITH_GRAD adds the ED sum needed by the sweep gradient.
-template <int NW, bool WITH_GRAD>
-__device__ __forceinline__ void bond_sums(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
-                                          const BondMasks<NW>& bm, double (&cum)[NCLS], BondSums& out,
-                                          double& big_S) {
+template <int NW, bool WITH_GRAD, typename SINK>
+__device__ __forceinline__ double bond_sums(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
+                                            const BondMasks<NW>& bm, const StepScratch<NW>& sc, SINK&& sink,
+                                            BondSums& out, double& big_S) {
     double S = 0.0, E = 0.0, ED = 0.0;
     int nocc = 0;
     int dd = 0;
+    sink(0, 0.0);
 #pragma unroll
     for (int l = 0; l < KCAP; ++l) {
         int rowcnt = 0;
 #pragma unroll
         for (int r = 0; r < KCAP; ++r) {
             const int k = l * KCAP + r;
+            if (k == 0) continue;
             int c = 0;
 #pragma unroll
             for (int i = 0; i < NW; ++i) c += __popc(bm.EL[l][i] & bm.ER[r][i]);
@@ -305,12 +386,13 @@ __device__ __forceinline__ void bond_sums(const uint32_t (&e)[NW], const DevMode
             S = fma(cd, tb.FS[k], S);
             E = fma(cd, tb.FE[k], E);
             if (WITH_GRAD) ED = fma(cd, tb.FD[k], ED);
-            cum[k] = S;
+            sink(k, S);
             rowcnt += c;
         }
         if (l > 0) nocc += rowcnt;
         dd += rowcnt * (l * (l - 1) / 2);
     }
+    const double reg_total = S;
     long long d = dd;
     // rare: bonds next to a mode with >= KCAP particles
     double bS = 0.0;
@@ -318,69 +400,72 @@ __device__ __forceinline__ void bond_sums(const uint32_t (&e)[NW], const DevMode
 #pragma unroll
     for (int i = 0; i < NW; ++i) any_big |= bm.big[i];
     if (any_big) {
-        uint32_t tmp[NW];  // local copy: only this array gets dynamically indexed
-#pragma unroll
-        for (int i = 0; i < NW; ++i) tmp[i] = e[i];
+        const int t = threadIdx.x;
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            uint32_t m = bm.big[i];
-            while (m) {
-                const int z = 32 * i + (__ffs(m) - 1);
-                m &= m - 1;
-                int L, R;
-                bond_runs_generic(tmp, dm.B, z, L, R);
-                double rr, rl, er, el;
-                generic_bond_terms(L, R, tb.c, rr, rl, er, el);
-                bS += rr;
-                bS += rl;
-                E += er + el;
-                if (WITH_GRAD) ED += er * (double)(R - L + 1) + el * (double)(L - R + 1);
-                nocc += (L > 0);
-                d += (long long)L * (L - 1) / 2;
-            }
+            sc.ew[i * STEP_BLOCK + t] = e[i];
+            sc.bw[i * STEP_BLOCK + t] = bm.big[i];
         }
+        const BigOut o = big_pass(sc.ew + t, sc.bw + t, NW, dm.B, dm.N, sc.exptab, 0, 0.0);
+        bS = o.S;
+        E += o.E;
+        if (WITH_GRAD) ED += o.ED;
+        nocc += o.nocc;
+        d += o.d;
     }
     big_S = bS;
-    out.S = S + bS;
+    out.S = reg_total + bS;
     out.E = E;
     out.ED = ED;
     out.d = d;
     out.nocc = nocc;
+    return reg_total;
+}
+
+// stage the class masks for the dynamic (l, r) lookup of the move selection
+template <int NW>
+__device__ __forceinline__ void stage_masks(const BondMasks<NW>& bm, const StepScratch<NW>& sc) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < KCAP; ++q)
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            sc.el[(q * NW + i) * STEP_BLOCK + t] = bm.EL[q][i];
+            sc.er[(q * NW + i) * STEP_BLOCK + t] = bm.ER[q][i];
+        }
 }
 
 // Class-ordered move selection: partition [0,S) into consecutive intervals, one per hop, ordered
 // by (class id, direction right-then-left, bond position), big bonds last.  T in [0,S).
+// Needs the prefix sums (SmemCumSink) and masks (stage_masks) of this thread in `sc`.
 // Returns the bond position z and the direction.
 template <int NW>
 __device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
-                                            const BondMasks<NW>& bm, const double (&cum)[NCLS], double big_S,
-                                            double T, int& z_out, bool& right_out) {
-    const double reg_total = cum[NCLS - 1];
+                                            const BondMasks<NW>& bm, const StepScratch<NW>& sc, double reg_total,
+                                            double big_S, double T, int& z_out, bool& right_out) {
+    static_assert(KCAP == 4 && NCLS == 16, "class id decoding assumes KCAP == 4");
     if (T < reg_total || !(big_S > 0.0)) {
         if (!(T < reg_total)) T = __longlong_as_double(__double_as_longlong(reg_total) - 1);
-        int idx = 0;
-        double base = 0.0;
+        const double* cum = sc.cum + threadIdx.x;
+        // first class k in [1,15] with T < cum[k] (cum[15] = reg_total > T): 4 bisection steps
+        int lo = 1, hi = NCLS - 1;
 #pragma unroll
-        for (int k = 0; k < NCLS - 1; ++k) {
-            const bool ge = (T >= cum[k]);
-            idx += ge ? 1 : 0;
-            base = ge ? cum[k] : base;
+        for (int it = 0; it < 4; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const bool below = T < cum[mid * STEP_BLOCK];
+            hi = below ? mid : hi;
+            lo = below ? lo : mid + 1;
         }
-        const int l = idx >> 2, r = idx & 3;  // KCAP == 4
-        static_assert(KCAP == 4, "class id decoding assumes KCAP == 4");
+        const int idx = lo;
+        const double base = cum[(idx - 1) * STEP_BLOCK];
+        const int l = idx >> 2, r = idx & 3;
         // masks of class (l,r), their popcounts
         uint32_t m[NW];
         int pc[NW];
         int c = 0;
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
-            uint32_t el = bm.EL[0][i], er = bm.ER[0][i];
-#pragma unroll
-            for (int q = 1; q < KCAP; ++q) {
-                el = (l == q) ? bm.EL[q][i] : el;
-                er = (r == q) ? bm.ER[q][i] : er;
-            }
-            m[i] = el & er;
+            m[i] = sc.el[(l * NW + i) * STEP_BLOCK + threadIdx.x] & sc.er[(r * NW + i) * STEP_BLOCK + threadIdx.x];
             pc[i] = __popc(m[i]);
             c += pc[i];
         }
@@ -405,41 +490,10 @@ __device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevMo
         z_out = pos + nth_set_bit32(word, j);
         right_out = right;
     } else {
-        // walk the big bonds in the same order as bond_sums
-        const double t = T - reg_total;
-        double acc = 0.0;
-        int zsel = -1;
-        bool rsel = true;
-        bool done = false;
-        uint32_t tmp[NW];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) tmp[i] = e[i];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            uint32_t mm = bm.big[i];
-            while (mm && !done) {
-                const int z = 32 * i + (__ffs(mm) - 1);
-                mm &= mm - 1;
-                int L, R;
-                bond_runs_generic(tmp, dm.B, z, L, R);
-                double rr, rl, er, el;
-                generic_bond_terms(L, R, tb.c, rr, rl, er, el);
-                if (rr > 0.0) {
-                    acc += rr;
-                    zsel = z;
-                    rsel = true;
-                    if (t < acc) done = true;
-                }
-                if (!done && rl > 0.0) {
-                    acc += rl;
-                    zsel = z;
-                    rsel = false;
-                    if (t < acc) done = true;
-                }
-            }
-        }
-        z_out = zsel;
-        right_out = rsel;
+        // walk the generic bonds in the same order as bond_sums (their words are still staged)
+        const BigOut o = big_pass(sc.ew + threadIdx.x, sc.bw + threadIdx.x, NW, dm.B, dm.N, sc.exptab, 1, T - reg_total);
+        z_out = o.z;
+        right_out = o.right != 0;
     }
 }
 

@@ -9,8 +9,8 @@
 namespace gwz {
 
 constexpr int NUM_ACC = 12;        // doubles in the cross-device accumulator vector (GWZ_NUM_ACC)
-constexpr int NUM_WALKER_ACC = 7;  // per-walker running sums kept in HBM: st, stE, stG, stGE, stEE, E0, G0
-constexpr int WALKER_BLOCK = 128;
+constexpr int NUM_WALKER_ACC = 5;  // per-walker running sums kept in HBM: st, stE, stG, stGE, stEE (shifted)
+constexpr int WALKER_BLOCK = STEP_BLOCK;
 constexpr int SWEEP_BLOCK = 128;
 
 // accumulator vector layout (all-reduced with ncclSum)
@@ -41,6 +41,7 @@ struct WalkerLaunch {
     uint64_t global_offset, seed, step0, steps;
     int accumulate;  // 0: burn-in (no estimator update, no reduction)
     int reset_acc;   // 1: clear the per-walker sums before the first step
+    const double* shift;  // device: (E_ref, G_ref) reference point of the shifted sums
     // optional per-step series [steps][n] (recording run)
     double* rec_tau;
     double* rec_eloc;
@@ -52,12 +53,16 @@ struct WalkerLaunch {
 };
 
 // occupancy-derived persistent grid for the walker kernel of this (nw, kind, record)
-cudaError_t walker_grid(int nw, int kind, bool record, size_t n, int sm_count, int* grid);
+cudaError_t walker_grid(int nw, int N, int kind, bool record, size_t n, int sm_count, int* grid);
 cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s);
 // out[ncomp] = sum over blocks of partials[block][ncomp], fixed order
 cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s);
 cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, const uint64_t* start_dev, cudaStream_t s);
-cudaError_t launch_walker_estimates(const double* acc, size_t n, double* val_w, double* grad_w, cudaStream_t s);
+cudaError_t launch_walker_estimates(const double* acc, size_t n, const double* shift, double* val_w, double* grad_w,
+                                    cudaStream_t s);
+// shift[0..1] = (E_loc, grad ratio) of walker 0's current address
+cudaError_t launch_walker_ref(const DevModel& dm, const DevTables& tb, int nw, const uint64_t* addr, size_t n,
+                              double* shift, cudaStream_t s);
 // AoS (n x W) <-> SoA ([W][n]) address layout conversion
 cudaError_t launch_transpose_addr(const uint64_t* src, uint64_t* dst, size_t n, int W, bool to_soa, cudaStream_t s);
 

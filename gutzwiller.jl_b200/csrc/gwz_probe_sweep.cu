@@ -9,12 +9,15 @@ namespace gwz {
 // probe: one thread per address
 // ------------------------------------------------------------------------------------------
 template <int NW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(STEP_BLOCK)
 probe_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, int kind,
              const uint64_t* __restrict__ addr, size_t n, const double* __restrict__ u01,
              double* __restrict__ e_loc, double* __restrict__ tau_out, double* __restrict__ grad_out,
              int32_t* __restrict__ n_hops, double* __restrict__ rates, int32_t* __restrict__ chosen_out,
              uint64_t* __restrict__ next_addr, int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepScratch<NW> sc(smem_raw, dm.N);
+    sc.fill_exptab(dm.N, tb.c);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t a[NW];
@@ -23,29 +26,8 @@ probe_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
     double tau, eloc, gr;
     int nh, chosen = 0;
     if (kind == 1) {
-        // production path; recover the reference hop index of the selected move afterwards
-        uint32_t e[NW];
-        extend<NW>(a, dm, e);
-        BondMasks<NW> bm;
-        classify_bonds<NW>(e, dm, bm);
-        double cum[NCLS];
-        BondSums bs;
-        double bigS;
-        bond_sums<NW, false>(e, dm, tb, bm, cum, bs, bigS);
-        const double D = dm.u * (double)bs.d;
-        tau = 1.0 / bs.S;
-        eloc = D - dm.t * bs.E;
-        gr = -D;
-        nh = 2 * bs.nocc;
-        double T = u * bs.S;
-        if (!(T < bs.S)) T = __longlong_as_double(__double_as_longlong(bs.S) - 1);
-        int z;
-        bool right;
-        select_move<NW>(e, dm, tb, bm, cum, bigS, T, z, right);
-        if (z >= 0) {
-            chosen = reference_hop_index<NW>(e, dm, z, right);
-            apply_hop<NW>(a, dm, z, right);
-        }
+        // production path; the reference hop index of the selected move is recovered afterwards
+        step_bitparallel<NW>(a, dm, tb, sc, u, tau, eloc, gr, nh, &chosen);
     } else {
         double* r = rates ? rates + i * (size_t)(2 * dm.M) : nullptr;
         if (r)
@@ -92,15 +74,15 @@ ansatz_kernel(const __grid_constant__ DevModel dm, double g, const uint64_t* __r
 //   den_grad = -2 D psi_k^2
 template <int NW>
 __device__ __forceinline__ void state_terms(const uint32_t (&a)[NW], const DevModel& dm, const DevTables& tb,
-                                            double& num, double& den, double& num_grad, double& den_grad) {
+                                            const StepScratch<NW>& sc, double& num, double& den, double& num_grad,
+                                            double& den_grad) {
     uint32_t e[NW];
     extend<NW>(a, dm, e);
     BondMasks<NW> bm;
     classify_bonds<NW>(e, dm, bm);
-    double cum[NCLS];
     BondSums bs;
     double bigS;
-    bond_sums<NW, true>(e, dm, tb, bm, cum, bs, bigS);
+    bond_sums<NW, true>(e, dm, tb, bm, sc, NoCumSink{}, bs, bigS);
     const double D = dm.u * (double)bs.d;
     const double psi2 = exp(-2.0 * tb.g * D);  // abs2(exp(-g*diag))  (localenergy.jl:108,111)
     const double eloc = D - dm.t * bs.E;
@@ -133,6 +115,9 @@ __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
              const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
              const uint64_t* __restrict__ binom, double* __restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepScratch<NW> sc(smem_raw, dm.N);
+    sc.fill_exptab(dm.N, tb.c);
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -148,7 +133,7 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
 #pragma unroll
                 for (int i = 2; i < NW; ++i) a[i] = 0u;
                 double num, den, ng, dg;
-                state_terms<NW>(a, dm, tb, num, den, ng, dg);
+                state_terms<NW>(a, dm, tb, sc, num, den, ng, dg);
                 s0 += num;
                 s1 += den;
                 s2 += ng;
@@ -161,7 +146,7 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
             uint32_t a[NW];
             load_addr_soa<NW>(basis, dim, idx, dm.W, a);
             double num, den, ng, dg;
-            state_terms<NW>(a, dm, tb, num, den, ng, dg);
+            state_terms<NW>(a, dm, tb, sc, num, den, ng, dg);
             s0 += num;
             s1 += den;
             s2 += ng;
@@ -196,6 +181,9 @@ sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                    const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin,
                    const uint64_t* __restrict__ binom, uint64_t first, uint64_t count,
                    double* __restrict__ out, uint64_t* __restrict__ states_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepScratch<NW> sc(smem_raw, dm.N);
+    sc.fill_exptab(dm.N, tb.c);
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     uint32_t a[NW];
@@ -210,7 +198,7 @@ sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
     }
     if (out) {
         double num, den, ng, dg;
-        state_terms<NW>(a, dm, tb, num, den, ng, dg);
+        state_terms<NW>(a, dm, tb, sc, num, den, ng, dg);
         out[i * 4 + 0] = num;
         out[i * 4 + 1] = den;
         out[i * 4 + 2] = ng;
@@ -222,6 +210,13 @@ sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+// opt in to > 48 KB of dynamic shared memory where the scratch needs it
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 #define GWZ_DISPATCH_NW(nw, CALL)                \
     switch (nw) {                                \
         case 1: { constexpr int NW = 1; CALL; } break; \
@@ -237,8 +232,9 @@ sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
 
 cudaError_t launch_probe(const ProbeLaunch& L, cudaStream_t s) {
     if (L.n == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((L.n + 127) / 128);
-    GWZ_DISPATCH_NW(L.nw, (probe_kernel<NW><<<grid, 128, 0, s>>>(L.dm, L.tb, L.kind, L.addr, L.n, L.u01, L.e_loc, L.tau,
+    const unsigned grid = (unsigned)((L.n + STEP_BLOCK - 1) / STEP_BLOCK);
+    GWZ_DISPATCH_NW(L.nw, if (cudaError_t e = ensure_smem(probe_kernel<NW>, StepScratch<NW>::bytes(L.dm.N))) return e);
+    GWZ_DISPATCH_NW(L.nw, (probe_kernel<NW><<<grid, STEP_BLOCK, StepScratch<NW>::bytes(L.dm.N), s>>>(L.dm, L.tb, L.kind, L.addr, L.n, L.u01, L.e_loc, L.tau,
                                                                L.grad, L.n_hops, L.rates, L.chosen, L.next_addr,
                                                                L.err_flag)));
     return cudaGetLastError();
@@ -250,6 +246,13 @@ cudaError_t launch_ansatz(const DevModel& dm, double g, int nw, const uint64_t* 
     const unsigned grid = (unsigned)((n + 127) / 128);
     GWZ_DISPATCH_NW(nw, (ansatz_kernel<NW><<<grid, 128, 0, s>>>(dm, g, addr, n, val, grad)));
     return cudaGetLastError();
+}
+
+// the sweep only needs the generic-bond part of the scratch (exp table + staged words); the layout is
+// the common one, the prefix-sum / class-mask regions are simply never touched
+static size_t sweep_smem_bytes(int N, int nw) {
+    return sizeof(double) * (size_t)(2 * N + 2) + sizeof(double) * NCLS * STEP_BLOCK +
+           sizeof(uint32_t) * (size_t)(2 * KCAP * nw + 2 * nw) * STEP_BLOCK;
 }
 
 cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk) {
@@ -273,11 +276,14 @@ cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* gri
 
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
     const bool ranked = (L.basis == nullptr);
+    const size_t sweep_smem = sweep_smem_bytes(L.dm.N, L.nw);
+    GWZ_DISPATCH_NW(L.nw, if (cudaError_t e = ensure_smem(sweep_kernel<NW, true>, sweep_smem)) return e;
+                          if (cudaError_t e2 = ensure_smem(sweep_kernel<NW, false>, sweep_smem)) return e2);
     if (ranked) {
-        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, true><<<L.grid, SWEEP_BLOCK, 0, s>>>(
+        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, true><<<L.grid, SWEEP_BLOCK, sweep_smem, s>>>(
                                   L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk, L.binom, L.partials)));
     } else {
-        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, false><<<L.grid, SWEEP_BLOCK, 0, s>>>(
+        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, false><<<L.grid, SWEEP_BLOCK, sweep_smem, s>>>(
                                   L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk, L.binom, L.partials)));
     }
     return cudaGetLastError();
@@ -286,13 +292,16 @@ cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s) {
     if (L.count == 0) return cudaSuccess;
     const bool ranked = (L.basis == nullptr);
+    const size_t sweep_smem = sweep_smem_bytes(L.dm.N, L.nw);
     const unsigned grid = (unsigned)((L.count + SWEEP_BLOCK - 1) / SWEEP_BLOCK);
+    GWZ_DISPATCH_NW(L.nw, if (cudaError_t e = ensure_smem(sweep_terms_kernel<NW, true>, sweep_smem)) return e;
+                          if (cudaError_t e2 = ensure_smem(sweep_terms_kernel<NW, false>, sweep_smem)) return e2);
     if (ranked) {
-        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, true><<<grid, SWEEP_BLOCK, 0, s>>>(
+        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, true><<<grid, SWEEP_BLOCK, sweep_smem, s>>>(
                                   L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom, L.first, L.count, L.terms_out,
                                   L.states_out)));
     } else {
-        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, false><<<grid, SWEEP_BLOCK, 0, s>>>(
+        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, false><<<grid, SWEEP_BLOCK, sweep_smem, s>>>(
                                   L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom, L.first, L.count, L.terms_out,
                                   L.states_out)));
     }
