@@ -19,6 +19,7 @@ NUM_ACC = 12
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NONFINITE, ERR_NOMEM = range(6)
 KERNEL_ENUMERATE, KERNEL_BITPARALLEL = 0, 1
 RUN_KEEP_ACC = 1
+RUN_POOLED = 2
 
 ACC_NAMES = ("walkers", "sum_val", "sum_val2", "sum_grad", "sum_grad2", "sum_t", "sum_tE", "sum_tG",
              "sum_tGE", "sum_tEE", "hops", "steps")
@@ -112,7 +113,7 @@ SIGNATURES = {
     "gwz_gd_opts_default": (C.c_int, [C.POINTER(GdOpts)]),
     "gwz_adaptive_gradient_descent": (C.c_int, [OBJECTIVE_FN, OBJECTIVE_FN, _vp, _dp, C.c_int, C.POINTER(GdOpts),
                                                 C.POINTER(GdTrace)]),
-    "gwz_amsgrad_vqmc": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.c_uint64, C.c_int, C.POINTER(GdTrace)]),
+    "gwz_amsgrad_vqmc": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.c_uint64, C.c_int, C.c_uint, C.POINTER(GdTrace)]),
     "gwz_amsgrad_sweep": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.POINTER(GdTrace)]),
 }
 

@@ -123,7 +123,7 @@ def adaptive_gradient_descent(use_amsgrad: bool, f, params, *, maxiter=100, verb
 
     if isinstance(f, KineticVQMC) and not fkwargs and not f.result.record and n == 1:
         check(lib().gwz_amsgrad_vqmc(f.result.walkers_handle.handle, p0c, C.byref(o), f.steps, f.result.kernel,
-                                     C.byref(tr)))
+                                     _capi.RUN_POOLED if f.result.estimator == "pooled" else 0, C.byref(tr)))
         f.result.steps = f.steps
     elif isinstance(f, LocalEnergyEvaluator) and not fkwargs and n == 1:
         check(lib().gwz_amsgrad_sweep(f.handle, p0c, C.byref(o), C.byref(tr)))

@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -240,14 +241,14 @@ extern "C" int gwz_model_create_hubbard1d_gutzwiller(gwz_context* ctx, int N, in
     GWZ_REQUIRE(ctx && out, "gwz_model_create: NULL argument");
     GWZ_REQUIRE(N >= 1 && M >= 2, "gwz_model_create: need N >= 1 particles and M >= 2 modes");
     const int B = N + M - 1;
-    GWZ_REQUIRE(B + 1 + KCAP <= 32 * MAXNW, "gwz_model_create: N+M-1 must be <= 251 bits");
+    GWZ_REQUIRE(B + 1 + KCAP_MAX <= 32 * MAXNW, "gwz_model_create: N+M-1 must be <= 250 bits");
     gwz_model* m = new gwz_model();
     m->ctx = ctx;
     m->N = N;
     m->M = M;
     m->B = B;
     m->W = (B + 63) / 64;
-    m->nw = (B + 1 + KCAP + 31) / 32;
+    m->nw = (B + 1 + KCAP_MAX + 31) / 32;
     m->u = u;
     m->t = t;
     DevModel& dm = m->dm;
@@ -346,14 +347,30 @@ extern "C" int gwz_model_dimension(const gwz_model* m, double* dim, uint64_t* di
     return GWZ_OK;
 }
 
-// parameter-dependent tables (O(KCAP^2) host work per call)
-static void make_tables(const gwz_model* m, double g, DevTables* tb) {
+// KC = bond classes per side handled by popcounts (4 or 5).  Measured on B200 (tools/quick_bench.py):
+// for sampled walkers KC = 4 plus the compact generic-bond path is never slower than KC = 5 (whose 25
+// pair-popcounts cost 1.45x), even at g*u ~ 0.66 where ~0.1 % of the sites hold >= 4 particles; a
+// full-basis sweep visits every occupation pattern uniformly and is slightly faster with KC = 5.
+// GWZ_KCAP=4|5 overrides (experiments).
+static int choose_kc(const gwz_model* m, double g, bool uniform_measure) {
+    (void)m;
+    (void)g;
+    if (const char* e = std::getenv("GWZ_KCAP")) {
+        const int v = std::atoi(e);
+        if (v == 4 || v == 5) return v;
+    }
+    return uniform_measure ? 5 : 4;
+}
+
+// parameter-dependent tables (O(KC^2) host work per call)
+static void make_tables(const gwz_model* m, double g, int kc, DevTables* tb) {
     std::memset(tb, 0, sizeof(*tb));
     tb->g = g;
     tb->c = g * m->u;
-    for (int L = 0; L < KCAP; ++L)
-        for (int R = 0; R < KCAP; ++R) {
-            const int k = L * KCAP + R;
+    tb->kc = kc;
+    for (int L = 0; L < kc; ++L)
+        for (int R = 0; R < kc; ++R) {
+            const int k = L * kc + R;
             const double rr = (L > 0) ? std::exp(-tb->c * (double)(R - L + 1)) : 0.0;
             const double rl = (R > 0) ? std::exp(-tb->c * (double)(L - R + 1)) : 0.0;
             const double er = (L > 0) ? std::sqrt((double)L * (double)(R + 1)) * rr : 0.0;
@@ -424,7 +441,7 @@ extern "C" int gwz_probe_addresses(gwz_model* m, const uint64_t* addr_words, siz
     if (rates) GWZ_CUDA(d_r.alloc(n * twoM));
     ProbeLaunch L;
     L.dm = m->dm;
-    make_tables(m, params[0], &L.tb);
+    make_tables(m, params[0], choose_kc(m, params[0], true), &L.tb);
     L.nw = m->nw;
     L.kind = kernel_kind;
     L.addr = d_addr.p;
@@ -581,7 +598,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     if (int rc = use_device(c)) return rc;
     const bool record = rec_tau != nullptr;
     int grid = 0;
-    GWZ_CUDA(walker_grid(m->nw, m->N, kind, record, w->n, c->prop.multiProcessorCount, &grid));
+    GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
     if (int rc = ensure_partials(w, grid)) return rc;
     WalkerLaunch L;
     L.dm = m->dm;
@@ -607,7 +624,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         L.accumulate = 0;
         L.reset_acc = 0;
         int g2 = 0;
-        GWZ_CUDA(walker_grid(m->nw, m->N, kind, false, w->n, c->prop.multiProcessorCount, &g2));
+        GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, false, w->n, c->prop.multiProcessorCount, &g2));
         L.grid = g2;
         GWZ_CUDA(launch_walkers(L, c->stream));
         w->steps_done += burn_in;
@@ -631,7 +648,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     return GWZ_OK;
 }
 
-static void fill_result(const double* a, float ms, gwz_vqmc_result* out) {
+static void fill_result(const double* a, float ms, unsigned flags, gwz_vqmc_result* out) {
     const double nw = a[ACC_WALKERS];
     const double val = a[ACC_VAL] / nw, grad = a[ACC_GRAD] / nw;
     out->val = val;
@@ -657,10 +674,14 @@ static void fill_result(const double* a, float ms, gwz_vqmc_result* out) {
     out->hops = (uint64_t)std::llround(a[ACC_HOPS]);
     for (int i = 0; i < NUM_ACC; ++i) out->acc[i] = a[i];
     out->kernel_ms = ms;
+    if (flags & GWZ_RUN_POOLED) {  // report the pooled ratio estimator as (val, grad)
+        out->val = out->pooled_val;
+        out->grad[0] = out->pooled_grad[0];
+    }
 }
 
 // combine the per-set vectors: device sum within a context, NCCL all-reduce across contexts/ranks
-static int combine_and_fetch(gwz_walkers* const* ws, int n, gwz_vqmc_result* out) {
+static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_vqmc_result* out) {
     // group the sets by context (order of first appearance)
     std::vector<gwz_context*> ctxs;
     for (int i = 0; i < n; ++i) {
@@ -718,7 +739,7 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, gwz_vqmc_result* out
         if (int rc = use_device(c0)) return rc;
         GWZ_CUDA(cudaEventElapsedTime(&ms, c0->ev0, c0->ev1));
     }
-    if (out) fill_result(ctxs[0]->h_acc, ms, out);
+    if (out) fill_result(ctxs[0]->h_acc, ms, flags, out);
     return GWZ_OK;
 }
 
@@ -731,7 +752,7 @@ extern "C" int gwz_vqmc_run_group(gwz_walkers* const* ws, int n, const double* p
     for (int i = 0; i < n; ++i) GWZ_REQUIRE(ws[i] != nullptr, "gwz_vqmc_run_group: NULL walker set");
     GWZ_REQUIRE(std::isfinite(params[0]), "gwz_vqmc_run: non-finite parameter");
     DevTables tb;
-    make_tables(ws[0]->m, params[0], &tb);
+    make_tables(ws[0]->m, params[0], choose_kc(ws[0]->m, params[0], false), &tb);
     bool timed_first = false;
     std::vector<gwz_context*> timed;
     for (int i = 0; i < n; ++i) {
@@ -744,7 +765,7 @@ extern "C" int gwz_vqmc_run_group(gwz_walkers* const* ws, int n, const double* p
                                  time_it))
             return rc;
     }
-    return combine_and_fetch(ws, n, out);
+    return combine_and_fetch(ws, n, flags, out);
 }
 
 extern "C" int gwz_vqmc_run(gwz_walkers* w, const double* params, uint64_t steps_per_walker, uint64_t burn_in,
@@ -783,7 +804,7 @@ extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_
     GWZ_CUDA(d_eloc.alloc(cells));
     if (addr) GWZ_CUDA(d_addr.alloc(cells * w->m->W));
     DevTables tb;
-    make_tables(w->m, params[0], &tb);
+    make_tables(w->m, params[0], choose_kc(w->m, params[0], false), &tb);
     if (int rc = enqueue_run(w, tb, steps, 0, kernel_kind, flags, d_tau.p, d_eloc.p, addr ? d_addr.p : nullptr, true))
         return rc;
     GWZ_CUDA(cudaMemcpyAsync(tau, d_tau.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
@@ -791,7 +812,7 @@ extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_
     if (addr)
         GWZ_CUDA(cudaMemcpyAsync(addr, d_addr.p, sizeof(uint64_t) * cells * w->m->W, cudaMemcpyDeviceToHost, c->stream));
     gwz_walkers* one[1] = {w};
-    return combine_and_fetch(one, 1, out);
+    return combine_and_fetch(one, 1, flags, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -862,7 +883,7 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     SweepLaunch L;
     std::memset(&L, 0, sizeof(L));
     L.dm = m->dm;
-    make_tables(m, params[0], &L.tb);
+    make_tables(m, params[0], choose_kc(m, params[0], true), &L.tb);
     L.nw = m->nw;
     L.basis = s->d_basis;
     L.dim = s->dim;
@@ -919,7 +940,7 @@ static int sweep_terms_impl(gwz_sweep* s, const double* params, uint64_t first, 
     SweepLaunch L;
     std::memset(&L, 0, sizeof(L));
     L.dm = m->dm;
-    make_tables(m, params ? params[0] : 0.0, &L.tb);
+    make_tables(m, params ? params[0] : 0.0, choose_kc(m, params ? params[0] : 0.0, true), &L.tb);
     L.nw = m->nw;
     L.basis = s->d_basis;
     L.dim = s->dim;
@@ -1032,22 +1053,23 @@ struct VqmcObjective {
     gwz_walkers* w;
     uint64_t steps;
     int kind;
+    unsigned flags;
 };
 static int vqmc_objective(void* user, const double* p, int, double* val, double* err, double* grad) {
     // val_err_and_grad(qmc::KineticVQMC, p): _reset! keeps walker positions, clears the estimators
     // (wrapper.jl:74-79,98-105)
     VqmcObjective* o = (VqmcObjective*)user;
     gwz_vqmc_result r;
-    if (int rc = gwz_vqmc_run(o->w, p, o->steps, 0, o->kind, 0u, &r)) return rc;
+    if (int rc = gwz_vqmc_run(o->w, p, o->steps, 0, o->kind, o->flags & ~GWZ_RUN_KEEP_ACC, &r)) return rc;
     *val = r.val;
     *err = std::isnan(r.err) ? 0.0 : r.err;
     grad[0] = r.grad[0];
     return GWZ_OK;
 }
 extern "C" int gwz_amsgrad_vqmc(gwz_walkers* w, const double* p0, const gwz_gd_opts* opts, uint64_t steps_per_walker,
-                                int kernel_kind, gwz_gd_trace* trace) {
+                                int kernel_kind, unsigned flags, gwz_gd_trace* trace) {
     GWZ_REQUIRE(w && p0 && opts && trace, "gwz_amsgrad_vqmc: NULL argument");
-    VqmcObjective o{w, steps_per_walker, kernel_kind};
+    VqmcObjective o{w, steps_per_walker, kernel_kind, flags};
     return gwz_adaptive_gradient_descent(vqmc_objective, vqmc_objective, &o, p0, GWZ_NUM_PARAMS, opts, trace);
 }
 static int sweep_objective(void* user, const double* p, int, double* val, double* err, double* grad) {

@@ -20,9 +20,11 @@
 
 namespace gwz {
 
-constexpr int KCAP = 4;             // bond classes with L,R in 0..KCAP-1 are counted bit-parallel
-constexpr int NCLS = KCAP * KCAP;   // class id = L*KCAP + R
-constexpr int MAXNW = 8;            // 32-bit words of the extended string (B + 1 + KCAP <= 256)
+// Bond classes with L,R in 0..KC-1 are counted bit-parallel; KC (4 or 5) is a template parameter
+// chosen per launch from the expected occupation statistics (class id = L*KC + R).
+constexpr int KCAP_MAX = 5;
+constexpr int MAXCLS = KCAP_MAX * KCAP_MAX;
+constexpr int MAXNW = 8;            // 32-bit words of the extended string (B + 1 + KCAP_MAX <= 256)
 
 struct DevModel {
     int N, M, B;   // particles, modes, bits
@@ -43,43 +45,49 @@ constexpr int STEP_BLOCK = 128;  // threads per CTA of every kernel that selects
 struct DevTables {
     double g;            // params[1]
     double c;            // g*u
-    double FS[NCLS];     // sum of the (<=2) hop rates of a bond of class (L,R)
-    double FE[NCLS];     // sum of sqrt(n_src*(n_dst+1))*rate
-    double FD[NCLS];     // sum of sqrt(..)*rate*Delta        (gradient of the sweep)
-    double RR[NCLS];     // rate of the right hop (0 if L==0)
-    double RL[NCLS];     // rate of the left hop  (0 if R==0)
-    double IRR[NCLS];    // 1/RR (0 if RR==0)
-    double IRL[NCLS];
+    int kc;              // the KC these tables are laid out for (index = L*kc + R)
+    int pad_;
+    double FS[MAXCLS];     // sum of the (<=2) hop rates of a bond of class (L,R)
+    double FE[MAXCLS];     // sum of sqrt(n_src*(n_dst+1))*rate
+    double FD[MAXCLS];     // sum of sqrt(..)*rate*Delta        (gradient of the sweep)
+    double RR[MAXCLS];     // rate of the right hop (0 if L==0)
+    double RL[MAXCLS];     // rate of the left hop  (0 if R==0)
+    double IRR[MAXCLS];    // 1/RR (0 if RR==0)
+    double IRL[MAXCLS];
 };
 
 // Per-CTA shared-memory scratch of the bond evaluation.  Values that are *dynamically indexed* (class
 // prefix sums and class masks during move selection; the bitstring itself in the rare generic-bond
 // path) are staged here so that the register arrays stay statically indexed.  Per-thread entries use
 // the layout [entry][thread] (conflict-free); exptab is shared by the CTA.
-template <int NW>
+template <int NW, int KC>
 struct StepScratch {
+    static constexpr int NC = KC * KC;
     double* exptab;  // [2N+2]: exp(-c*(i-N)), i.e. the hop rate for Delta = i-N in [-N+1, N+1]
-    double* cum;     // [NCLS][STEP_BLOCK]
-    uint32_t* el;    // [KCAP][NW][STEP_BLOCK]
-    uint32_t* er;    // [KCAP][NW][STEP_BLOCK]
+    double* sqrtab;  // [N+2]:  sqrt(i)
+    double* cum;     // [NC][STEP_BLOCK]
+    uint32_t* el;    // [KC][NW][STEP_BLOCK]
+    uint32_t* er;    // [KC][NW][STEP_BLOCK]
     uint32_t* ew;    // [NW][STEP_BLOCK] extended bitstring   (staged only when a generic bond exists)
     uint32_t* bw;    // [NW][STEP_BLOCK] generic-bond mask
-    __host__ __device__ static constexpr size_t exptab_bytes(int N) { return sizeof(double) * (size_t)(2 * N + 2); }
+    __host__ __device__ static constexpr size_t exptab_bytes(int N) { return sizeof(double) * (size_t)(3 * N + 4); }
     __host__ __device__ static constexpr size_t bytes(int N) {
-        return exptab_bytes(N) + sizeof(double) * NCLS * STEP_BLOCK +
-               sizeof(uint32_t) * (2 * KCAP * NW + 2 * NW) * STEP_BLOCK;
+        return exptab_bytes(N) + sizeof(double) * NC * STEP_BLOCK +
+               sizeof(uint32_t) * (2 * KC * NW + 2 * NW) * STEP_BLOCK;
     }
     __device__ __forceinline__ StepScratch(unsigned char* base, int N) {
         exptab = reinterpret_cast<double*>(base);
-        cum = exptab + (2 * N + 2);
-        el = reinterpret_cast<uint32_t*>(cum + NCLS * STEP_BLOCK);
-        er = el + KCAP * NW * STEP_BLOCK;
-        ew = er + KCAP * NW * STEP_BLOCK;
+        sqrtab = exptab + (2 * N + 2);
+        cum = sqrtab + (N + 2);
+        el = reinterpret_cast<uint32_t*>(cum + NC * STEP_BLOCK);
+        er = el + KC * NW * STEP_BLOCK;
+        ew = er + KC * NW * STEP_BLOCK;
         bw = ew + NW * STEP_BLOCK;
     }
     // CTA-wide: tabulate the hop rates once per launch (keeps exp() out of the step loop)
     __device__ __forceinline__ void fill_exptab(int N, double c) const {
         for (int i = threadIdx.x; i < 2 * N + 2; i += blockDim.x) exptab[i] = exp(-c * (double)(i - N));
+        for (int i = threadIdx.x; i < N + 2; i += blockDim.x) sqrtab[i] = sqrt((double)i);
         __syncthreads();
     }
 };
@@ -175,9 +183,9 @@ __device__ __forceinline__ void store_addr_aos(uint64_t* __restrict__ words, siz
 }
 
 // e = a with the K low bits of a replicated above the virtual separator at bit B
-template <int NW>
+template <int NW, int KC>
 __device__ __forceinline__ void extend(const uint32_t (&a)[NW], const DevModel& dm, uint32_t (&e)[NW]) {
-    const uint32_t low = a[0] & ((1u << KCAP) - 1u);
+    const uint32_t low = a[0] & ((1u << KC) - 1u);
     const uint32_t lo_part = low << dm.ext_bs;
     const uint32_t hi_part = __funnelshift_l(low, 0u, dm.ext_bs);  // low >> (32 - ext_bs), 0 when ext_bs == 0
 #pragma unroll
@@ -217,6 +225,9 @@ __device__ __forceinline__ void apply_hop(uint32_t (&a)[NW], const DevModel& dm,
 // there) and the tabulated rates.  Keeping this path compact matters: the step loop must stay
 // resident in the 32 KB L1.5 instruction cache even when some warps take it.
 // ------------------------------------------------------------------------------------------
+#ifndef GWZ_BIGPASS_INLINE
+#define GWZ_BIGPASS_INLINE __forceinline__
+#endif
 struct BigOut {
     double S, E, ED;  // mode 0: sums over the generic bonds
     long long d;
@@ -226,8 +237,8 @@ struct BigOut {
 
 // ew/bw/exptab: shared memory (ew, bw already offset by threadIdx.x; stride STEP_BLOCK).
 // mode 0: accumulate; mode 1: find the hop whose interval of the running sum contains t.
-static __device__ __noinline__ BigOut big_pass(const uint32_t* ew, const uint32_t* bw, int nw, int B, int N,
-                                               const double* exptab, int mode, double t) {
+static __device__ GWZ_BIGPASS_INLINE BigOut big_pass(const uint32_t* ew, const uint32_t* bw, int nw, int B, int N,
+                                                      const double* exptab, const double* sqrtab, int mode, double t) {
     BigOut o;
     o.S = o.E = o.ED = 0.0;
     o.d = 0;
@@ -266,8 +277,9 @@ static __device__ __noinline__ BigOut big_pass(const uint32_t* ew, const uint32_
             const double rr = (L > 0) ? exptab[(R - L + 1) + N] : 0.0;
             const double rl = (R > 0) ? exptab[(L - R + 1) + N] : 0.0;
             if (mode == 0) {
-                const double er = sqrt((double)L * (double)(R + 1)) * rr;
-                const double el = sqrt((double)R * (double)(L + 1)) * rl;
+                // sqrt(n_src (n_dst+1)) as a product of tabulated roots (<= 1 ulp from the fused root)
+                const double er = sqrtab[L] * sqrtab[R + 1] * rr;
+                const double el = sqrtab[R] * sqrtab[L + 1] * rl;
                 o.S += rr;
                 o.S += rl;
                 o.E += er + el;
@@ -297,15 +309,15 @@ static __device__ __noinline__ BigOut big_pass(const uint32_t* ew, const uint32_
 // Bond classification: EL[l] / ER[r] = bonds whose lower / upper run has length exactly l / r
 // (l, r < KCAP); big = bonds with a run >= KCAP on either side.
 // ------------------------------------------------------------------------------------------
-template <int NW>
+template <int NW, int KC>
 struct BondMasks {
-    uint32_t EL[KCAP][NW];
-    uint32_t ER[KCAP][NW];
+    uint32_t EL[KC][NW];
+    uint32_t ER[KC][NW];
     uint32_t big[NW];
 };
 
-template <int NW>
-__device__ __forceinline__ void classify_bonds(const uint32_t (&e)[NW], const DevModel& dm, BondMasks<NW>& bm) {
+template <int NW, int KC>
+__device__ __forceinline__ void classify_bonds(const uint32_t (&e)[NW], const DevModel& dm, BondMasks<NW, KC>& bm) {
     uint32_t Z[NW], cur[NW], nxt[NW], sh[NW], bigL[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) Z[i] = ~e[i] & dm.zmask[i];
@@ -314,7 +326,7 @@ __device__ __forceinline__ void classify_bonds(const uint32_t (&e)[NW], const De
 #pragma unroll
     for (int i = 0; i < NW; ++i) bm.EL[0][i] = Z[i] & ~cur[i];
 #pragma unroll
-    for (int k = 1; k < KCAP; ++k) {
+    for (int k = 1; k < KC; ++k) {
         shl1<NW>(cur, sh);
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
@@ -330,7 +342,7 @@ __device__ __forceinline__ void classify_bonds(const uint32_t (&e)[NW], const De
 #pragma unroll
     for (int i = 0; i < NW; ++i) bm.ER[0][i] = Z[i] & ~cur[i];
 #pragma unroll
-    for (int k = 1; k < KCAP; ++k) {
+    for (int k = 1; k < KC; ++k) {
         shr1<NW>(cur, sh);
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
@@ -364,20 +376,20 @@ struct SmemCumSink {
     __device__ __forceinline__ void operator()(int k, double v) const { cum[k * STEP_BLOCK] = v; }
 };
 
-template <int NW, bool WITH_GRAD, typename SINK>
+template <int NW, int KC, bool WITH_GRAD, typename SINK>
 __device__ __forceinline__ double bond_sums(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
-                                            const BondMasks<NW>& bm, const StepScratch<NW>& sc, SINK&& sink,
+                                            const BondMasks<NW, KC>& bm, const StepScratch<NW, KC>& sc, SINK&& sink,
                                             BondSums& out, double& big_S) {
     double S = 0.0, E = 0.0, ED = 0.0;
     int nocc = 0;
     int dd = 0;
     sink(0, 0.0);
 #pragma unroll
-    for (int l = 0; l < KCAP; ++l) {
+    for (int l = 0; l < KC; ++l) {
         int rowcnt = 0;
 #pragma unroll
-        for (int r = 0; r < KCAP; ++r) {
-            const int k = l * KCAP + r;
+        for (int r = 0; r < KC; ++r) {
+            const int k = l * KC + r;
             if (k == 0) continue;
             int c = 0;
 #pragma unroll
@@ -406,7 +418,7 @@ __device__ __forceinline__ double bond_sums(const uint32_t (&e)[NW], const DevMo
             sc.ew[i * STEP_BLOCK + t] = e[i];
             sc.bw[i * STEP_BLOCK + t] = bm.big[i];
         }
-        const BigOut o = big_pass(sc.ew + t, sc.bw + t, NW, dm.B, dm.N, sc.exptab, 0, 0.0);
+        const BigOut o = big_pass(sc.ew + t, sc.bw + t, NW, dm.B, dm.N, sc.exptab, sc.sqrtab, 0, 0.0);
         bS = o.S;
         E += o.E;
         if (WITH_GRAD) ED += o.ED;
@@ -423,11 +435,11 @@ __device__ __forceinline__ double bond_sums(const uint32_t (&e)[NW], const DevMo
 }
 
 // stage the class masks for the dynamic (l, r) lookup of the move selection
-template <int NW>
-__device__ __forceinline__ void stage_masks(const BondMasks<NW>& bm, const StepScratch<NW>& sc) {
+template <int NW, int KC>
+__device__ __forceinline__ void stage_masks(const BondMasks<NW, KC>& bm, const StepScratch<NW, KC>& sc) {
     const int t = threadIdx.x;
 #pragma unroll
-    for (int q = 0; q < KCAP; ++q)
+    for (int q = 0; q < KC; ++q)
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
             sc.el[(q * NW + i) * STEP_BLOCK + t] = bm.EL[q][i];
@@ -439,26 +451,28 @@ __device__ __forceinline__ void stage_masks(const BondMasks<NW>& bm, const StepS
 // by (class id, direction right-then-left, bond position), big bonds last.  T in [0,S).
 // Needs the prefix sums (SmemCumSink) and masks (stage_masks) of this thread in `sc`.
 // Returns the bond position z and the direction.
-template <int NW>
+template <int NW, int KC>
 __device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
-                                            const BondMasks<NW>& bm, const StepScratch<NW>& sc, double reg_total,
-                                            double big_S, double T, int& z_out, bool& right_out) {
-    static_assert(KCAP == 4 && NCLS == 16, "class id decoding assumes KCAP == 4");
+                                            const BondMasks<NW, KC>& bm, const StepScratch<NW, KC>& sc,
+                                            double reg_total, double big_S, double T, int& z_out, bool& right_out) {
+    constexpr int NC = KC * KC;
+    constexpr int BISECT = (NC - 1 <= 16) ? 4 : 5;  // ceil(log2(NC-1)) for KC = 4, 5
+    static_assert(NC - 1 <= 32, "bisection depth");
     if (T < reg_total || !(big_S > 0.0)) {
         if (!(T < reg_total)) T = __longlong_as_double(__double_as_longlong(reg_total) - 1);
         const double* cum = sc.cum + threadIdx.x;
-        // first class k in [1,15] with T < cum[k] (cum[15] = reg_total > T): 4 bisection steps
-        int lo = 1, hi = NCLS - 1;
+        // first class k in [1,NC-1] with T < cum[k] (cum[NC-1] = reg_total > T) by bisection
+        int lo = 1, hi = NC - 1;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < BISECT; ++it) {
             const int mid = (lo + hi) >> 1;
             const bool below = T < cum[mid * STEP_BLOCK];
             hi = below ? mid : hi;
-            lo = below ? lo : mid + 1;
+            lo = below ? lo : min(mid + 1, hi);
         }
         const int idx = lo;
         const double base = cum[(idx - 1) * STEP_BLOCK];
-        const int l = idx >> 2, r = idx & 3;
+        const int l = idx / KC, r = idx - l * KC;
         // masks of class (l,r), their popcounts
         uint32_t m[NW];
         int pc[NW];
@@ -491,7 +505,7 @@ __device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevMo
         right_out = right;
     } else {
         // walk the generic bonds in the same order as bond_sums (their words are still staged)
-        const BigOut o = big_pass(sc.ew + threadIdx.x, sc.bw + threadIdx.x, NW, dm.B, dm.N, sc.exptab, 1, T - reg_total);
+        const BigOut o = big_pass(sc.ew + threadIdx.x, sc.bw + threadIdx.x, NW, dm.B, dm.N, sc.exptab, sc.sqrtab, 1, T - reg_total);
         z_out = o.z;
         right_out = o.right != 0;
     }

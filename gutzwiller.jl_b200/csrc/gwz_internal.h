@@ -53,7 +53,7 @@ struct WalkerLaunch {
 };
 
 // occupancy-derived persistent grid for the walker kernel of this (nw, kind, record)
-cudaError_t walker_grid(int nw, int N, int kind, bool record, size_t n, int sm_count, int* grid);
+cudaError_t walker_grid(int nw, int N, int kind, int kc, bool record, size_t n, int sm_count, int* grid);
 cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s);
 // out[ncomp] = sum over blocks of partials[block][ncomp], fixed order
 cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s);

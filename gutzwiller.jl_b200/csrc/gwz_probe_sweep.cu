@@ -8,7 +8,7 @@ namespace gwz {
 // ------------------------------------------------------------------------------------------
 // probe: one thread per address
 // ------------------------------------------------------------------------------------------
-template <int NW>
+template <int NW, int KC>
 __global__ void __launch_bounds__(STEP_BLOCK)
 probe_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, int kind,
              const uint64_t* __restrict__ addr, size_t n, const double* __restrict__ u01,
@@ -16,7 +16,7 @@ probe_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
              int32_t* __restrict__ n_hops, double* __restrict__ rates, int32_t* __restrict__ chosen_out,
              uint64_t* __restrict__ next_addr, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW> sc(smem_raw, dm.N);
+    const StepScratch<NW, KC> sc(smem_raw, dm.N);
     sc.fill_exptab(dm.N, tb.c);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -27,7 +27,7 @@ probe_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
     int nh, chosen = 0;
     if (kind == 1) {
         // production path; the reference hop index of the selected move is recovered afterwards
-        step_bitparallel<NW>(a, dm, tb, sc, u, tau, eloc, gr, nh, &chosen);
+        step_bitparallel<NW, KC>(a, dm, tb, sc, u, tau, eloc, gr, nh, &chosen);
     } else {
         double* r = rates ? rates + i * (size_t)(2 * dm.M) : nullptr;
         if (r)
@@ -72,17 +72,17 @@ ansatz_kernel(const __grid_constant__ DevModel dm, double g, const uint64_t* __r
 //   den      = psi_k^2
 //   num_grad = psi_k^2 (-2 D (D + Emat) + u t ED)       [grad psi = -D psi, D_l = D + u Delta_l]
 //   den_grad = -2 D psi_k^2
-template <int NW>
+template <int NW, int KC>
 __device__ __forceinline__ void state_terms(const uint32_t (&a)[NW], const DevModel& dm, const DevTables& tb,
-                                            const StepScratch<NW>& sc, double& num, double& den, double& num_grad,
+                                            const StepScratch<NW, KC>& sc, double& num, double& den, double& num_grad,
                                             double& den_grad) {
     uint32_t e[NW];
-    extend<NW>(a, dm, e);
-    BondMasks<NW> bm;
-    classify_bonds<NW>(e, dm, bm);
+    extend<NW, KC>(a, dm, e);
+    BondMasks<NW, KC> bm;
+    classify_bonds<NW, KC>(e, dm, bm);
     BondSums bs;
     double bigS;
-    bond_sums<NW, true>(e, dm, tb, bm, sc, NoCumSink{}, bs, bigS);
+    bond_sums<NW, KC, true>(e, dm, tb, bm, sc, NoCumSink{}, bs, bigS);
     const double D = dm.u * (double)bs.d;
     const double psi2 = exp(-2.0 * tb.g * D);  // abs2(exp(-g*diag))  (localenergy.jl:108,111)
     const double eloc = D - dm.t * bs.E;
@@ -110,13 +110,13 @@ __device__ __forceinline__ uint64_t next_same_popcount(uint64_t x) {
     return (t + 1) | (((~t & (0 - ~t)) - 1) >> (__ffsll((long long)x)));
 }
 
-template <int NW, bool RANKED>
+template <int NW, int KC, bool RANKED>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
              const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
              const uint64_t* __restrict__ binom, double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW> sc(smem_raw, dm.N);
+    const StepScratch<NW, KC> sc(smem_raw, dm.N);
     sc.fill_exptab(dm.N, tb.c);
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -133,7 +133,7 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
 #pragma unroll
                 for (int i = 2; i < NW; ++i) a[i] = 0u;
                 double num, den, ng, dg;
-                state_terms<NW>(a, dm, tb, sc, num, den, ng, dg);
+                state_terms<NW, KC>(a, dm, tb, sc, num, den, ng, dg);
                 s0 += num;
                 s1 += den;
                 s2 += ng;
@@ -146,7 +146,7 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
             uint32_t a[NW];
             load_addr_soa<NW>(basis, dim, idx, dm.W, a);
             double num, den, ng, dg;
-            state_terms<NW>(a, dm, tb, sc, num, den, ng, dg);
+            state_terms<NW, KC>(a, dm, tb, sc, num, den, ng, dg);
             s0 += num;
             s1 += den;
             s2 += ng;
@@ -175,14 +175,14 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
 }
 
 // per-state outputs for parity tests: states first..first+count-1
-template <int NW, bool RANKED>
+template <int NW, int KC, bool RANKED>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
                    const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin,
                    const uint64_t* __restrict__ binom, uint64_t first, uint64_t count,
                    double* __restrict__ out, uint64_t* __restrict__ states_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW> sc(smem_raw, dm.N);
+    const StepScratch<NW, KC> sc(smem_raw, dm.N);
     sc.fill_exptab(dm.N, tb.c);
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -198,7 +198,7 @@ sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
     }
     if (out) {
         double num, den, ng, dg;
-        state_terms<NW>(a, dm, tb, sc, num, den, ng, dg);
+        state_terms<NW, KC>(a, dm, tb, sc, num, den, ng, dg);
         out[i * 4 + 0] = num;
         out[i * 4 + 1] = den;
         out[i * 4 + 2] = ng;
@@ -217,26 +217,32 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-#define GWZ_DISPATCH_NW(nw, CALL)                \
-    switch (nw) {                                \
-        case 1: { constexpr int NW = 1; CALL; } break; \
-        case 2: { constexpr int NW = 2; CALL; } break; \
-        case 3: { constexpr int NW = 3; CALL; } break; \
-        case 4: { constexpr int NW = 4; CALL; } break; \
-        case 5: { constexpr int NW = 5; CALL; } break; \
-        case 6: { constexpr int NW = 6; CALL; } break; \
-        case 7: { constexpr int NW = 7; CALL; } break; \
-        case 8: { constexpr int NW = 8; CALL; } break; \
-        default: return cudaErrorInvalidValue;   \
+// CALL sees `NW` and `KC` as compile-time constants
+#define GWZ_DISPATCH_KC(kc, ...)                              \
+    if ((kc) == 5) { constexpr int KC = 5; __VA_ARGS__; }     \
+    else { constexpr int KC = 4; __VA_ARGS__; }
+#define GWZ_DISPATCH_NW(nw, kc, ...)                                               \
+    switch (nw) {                                                                  \
+        case 1: { constexpr int NW = 1; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 2: { constexpr int NW = 2; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 3: { constexpr int NW = 3; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 4: { constexpr int NW = 4; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 5: { constexpr int NW = 5; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 6: { constexpr int NW = 6; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 7: { constexpr int NW = 7; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        case 8: { constexpr int NW = 8; GWZ_DISPATCH_KC(kc, __VA_ARGS__) } break;  \
+        default: return cudaErrorInvalidValue;                                     \
     }
 
 cudaError_t launch_probe(const ProbeLaunch& L, cudaStream_t s) {
     if (L.n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((L.n + STEP_BLOCK - 1) / STEP_BLOCK);
-    GWZ_DISPATCH_NW(L.nw, if (cudaError_t e = ensure_smem(probe_kernel<NW>, StepScratch<NW>::bytes(L.dm.N))) return e);
-    GWZ_DISPATCH_NW(L.nw, (probe_kernel<NW><<<grid, STEP_BLOCK, StepScratch<NW>::bytes(L.dm.N), s>>>(L.dm, L.tb, L.kind, L.addr, L.n, L.u01, L.e_loc, L.tau,
-                                                               L.grad, L.n_hops, L.rates, L.chosen, L.next_addr,
-                                                               L.err_flag)));
+    GWZ_DISPATCH_NW(L.nw, L.tb.kc, {
+        const size_t smem = StepScratch<NW, KC>::bytes(L.dm.N);
+        if (cudaError_t e = ensure_smem(probe_kernel<NW, KC>, smem)) return e;
+        probe_kernel<NW, KC><<<grid, STEP_BLOCK, smem, s>>>(L.dm, L.tb, L.kind, L.addr, L.n, L.u01, L.e_loc, L.tau, L.grad,
+                                                            L.n_hops, L.rates, L.chosen, L.next_addr, L.err_flag);
+    });
     return cudaGetLastError();
 }
 
@@ -244,15 +250,8 @@ cudaError_t launch_ansatz(const DevModel& dm, double g, int nw, const uint64_t* 
                           double* grad, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((n + 127) / 128);
-    GWZ_DISPATCH_NW(nw, (ansatz_kernel<NW><<<grid, 128, 0, s>>>(dm, g, addr, n, val, grad)));
+    GWZ_DISPATCH_NW(nw, 4, { if (KC == 4) ansatz_kernel<NW><<<grid, 128, 0, s>>>(dm, g, addr, n, val, grad); });
     return cudaGetLastError();
-}
-
-// the sweep only needs the generic-bond part of the scratch (exp table + staged words); the layout is
-// the common one, the prefix-sum / class-mask regions are simply never touched
-static size_t sweep_smem_bytes(int N, int nw) {
-    return sizeof(double) * (size_t)(2 * N + 2) + sizeof(double) * NCLS * STEP_BLOCK +
-           sizeof(uint32_t) * (size_t)(2 * KCAP * nw + 2 * nw) * STEP_BLOCK;
 }
 
 cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk) {
@@ -276,35 +275,38 @@ cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* gri
 
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
     const bool ranked = (L.basis == nullptr);
-    const size_t sweep_smem = sweep_smem_bytes(L.dm.N, L.nw);
-    GWZ_DISPATCH_NW(L.nw, if (cudaError_t e = ensure_smem(sweep_kernel<NW, true>, sweep_smem)) return e;
-                          if (cudaError_t e2 = ensure_smem(sweep_kernel<NW, false>, sweep_smem)) return e2);
-    if (ranked) {
-        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, true><<<L.grid, SWEEP_BLOCK, sweep_smem, s>>>(
-                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk, L.binom, L.partials)));
-    } else {
-        GWZ_DISPATCH_NW(L.nw, (sweep_kernel<NW, false><<<L.grid, SWEEP_BLOCK, sweep_smem, s>>>(
-                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk, L.binom, L.partials)));
-    }
+    GWZ_DISPATCH_NW(L.nw, L.tb.kc, {
+        const size_t smem = StepScratch<NW, KC>::bytes(L.dm.N);
+        if (ranked) {
+            if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, true>, smem)) return e;
+            sweep_kernel<NW, KC, true><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
+                                                                         L.binom, L.partials);
+        } else {
+            if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, false>, smem)) return e;
+            sweep_kernel<NW, KC, false><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
+                                                                          L.binom, L.partials);
+        }
+    });
     return cudaGetLastError();
 }
 
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s) {
     if (L.count == 0) return cudaSuccess;
     const bool ranked = (L.basis == nullptr);
-    const size_t sweep_smem = sweep_smem_bytes(L.dm.N, L.nw);
     const unsigned grid = (unsigned)((L.count + SWEEP_BLOCK - 1) / SWEEP_BLOCK);
-    GWZ_DISPATCH_NW(L.nw, if (cudaError_t e = ensure_smem(sweep_terms_kernel<NW, true>, sweep_smem)) return e;
-                          if (cudaError_t e2 = ensure_smem(sweep_terms_kernel<NW, false>, sweep_smem)) return e2);
-    if (ranked) {
-        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, true><<<grid, SWEEP_BLOCK, sweep_smem, s>>>(
-                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom, L.first, L.count, L.terms_out,
-                                  L.states_out)));
-    } else {
-        GWZ_DISPATCH_NW(L.nw, (sweep_terms_kernel<NW, false><<<grid, SWEEP_BLOCK, sweep_smem, s>>>(
-                                  L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom, L.first, L.count, L.terms_out,
-                                  L.states_out)));
-    }
+    GWZ_DISPATCH_NW(L.nw, L.tb.kc, {
+        const size_t smem = StepScratch<NW, KC>::bytes(L.dm.N);
+        if (ranked) {
+            if (cudaError_t e = ensure_smem(sweep_terms_kernel<NW, KC, true>, smem)) return e;
+            sweep_terms_kernel<NW, KC, true><<<grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom,
+                                                                             L.first, L.count, L.terms_out, L.states_out);
+        } else {
+            if (cudaError_t e = ensure_smem(sweep_terms_kernel<NW, KC, false>, smem)) return e;
+            sweep_terms_kernel<NW, KC, false><<<grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin,
+                                                                              L.binom, L.first, L.count, L.terms_out,
+                                                                              L.states_out);
+        }
+    });
     return cudaGetLastError();
 }
 

@@ -7,18 +7,19 @@ namespace gwz {
 // ------------------------------------------------------------------------------------------
 // one continuous-time step, production path (bond classes by popcount)
 // ------------------------------------------------------------------------------------------
-template <int NW>
+template <int NW, int KC>
 __device__ __forceinline__ void step_bitparallel(uint32_t (&a)[NW], const DevModel& dm, const DevTables& tb,
-                                                 const StepScratch<NW>& sc, double u01, double& tau, double& eloc,
+                                                 const StepScratch<NW, KC>& sc, double u01, double& tau, double& eloc,
                                                  double& gratio, int& nhops, int* ref_hop_index = nullptr) {
     uint32_t e[NW];
-    extend<NW>(a, dm, e);
-    BondMasks<NW> bm;
-    classify_bonds<NW>(e, dm, bm);
+    extend<NW, KC>(a, dm, e);
+    BondMasks<NW, KC> bm;
+    classify_bonds<NW, KC>(e, dm, bm);
     BondSums bs;
     double bigS;
-    const double reg_total = bond_sums<NW, false>(e, dm, tb, bm, sc, SmemCumSink{sc.cum + threadIdx.x}, bs, bigS);
-    stage_masks<NW>(bm, sc);
+    const double reg_total =
+        bond_sums<NW, KC, false>(e, dm, tb, bm, sc, SmemCumSink{sc.cum + threadIdx.x}, bs, bigS);
+    stage_masks<NW, KC>(bm, sc);
     const double D = dm.u * (double)bs.d;  // diagonal_element (qmc.jl:20)
     tau = 1.0 / bs.S;                      // |psi1| / sum |psi2|   (qmc.jl:33)
     eloc = D - dm.t * bs.E;                // (diag*psi1 + sum melem*psi2)/psi1  (qmc.jl:21,28,37)
@@ -28,7 +29,7 @@ __device__ __forceinline__ void step_bitparallel(uint32_t (&a)[NW], const DevMod
     if (!(T < bs.S)) T = __longlong_as_double(__double_as_longlong(bs.S) - 1);
     int z;
     bool right;
-    select_move<NW>(e, dm, tb, bm, sc, reg_total, bigS, T, z, right);
+    select_move<NW, KC>(e, dm, tb, bm, sc, reg_total, bigS, T, z, right);
     if (z >= 0) {
         if (ref_hop_index) *ref_hop_index = reference_hop_index<NW>(e, dm, z, right);
         apply_hop<NW>(a, dm, z, right);

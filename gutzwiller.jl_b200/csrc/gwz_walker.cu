@@ -11,9 +11,10 @@ namespace gwz {
 
 // dynamic shared memory: [selection scratch (production kernel) | per-thread partial vectors]; the
 // block-reduction buffer aliases the scratch region
+// KIND: 0 = enumerate (reference hop order); 4 / 5 = bit-parallel with KC = KIND bond classes per side
 template <int NW, int KIND>
 __host__ __device__ constexpr size_t walker_scratch_bytes(int N) {
-    return KIND == 1 ? StepScratch<NW>::bytes(N) : sizeof(double) * (WALKER_BLOCK / 32) * NUM_ACC;
+    return KIND != 0 ? StepScratch<NW, (KIND ? KIND : 4)>::bytes(N) : sizeof(double) * (WALKER_BLOCK / 32) * NUM_ACC;
 }
 template <int NW, int KIND>
 __host__ __device__ constexpr size_t walker_smem_bytes(int N) {
@@ -30,15 +31,16 @@ __host__ __device__ constexpr size_t walker_smem_bytes(int N) {
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int NW, int KIND, bool RECORD>
-__global__ void __launch_bounds__(WALKER_BLOCK, KIND != 1 ? 1 : (NW <= 4 ? GWZ_WALKER_MIN_BLOCKS : GWZ_WALKER_MIN_BLOCKS_WIDE))
+__global__ void __launch_bounds__(WALKER_BLOCK, KIND == 0 ? 1 : ((NW <= 4 ? GWZ_WALKER_MIN_BLOCKS : GWZ_WALKER_MIN_BLOCKS_WIDE) - (KIND == 5 ? 1 : 0)))
 walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
               uint64_t* __restrict__ addr, double* __restrict__ acc, size_t n, uint64_t global_offset,
               uint64_t seed, uint64_t step0, uint64_t steps, int accumulate, int reset_acc,
               const double* __restrict__ shift, double* __restrict__ rec_tau, double* __restrict__ rec_eloc,
               uint64_t* __restrict__ rec_addr, double* __restrict__ partials, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW> sc(smem_raw, dm.N);
-    if (KIND == 1) sc.fill_exptab(dm.N, tb.c);
+    constexpr int KC = KIND ? KIND : 4;
+    const StepScratch<NW, KC> sc(smem_raw, dm.N);
+    if (KIND != 0) sc.fill_exptab(dm.N, tb.c);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -82,8 +84,8 @@ walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTa
             if (RECORD && rec_addr) store_addr_aos<NW>(rec_addr, (size_t)k * n + w, dm.W, a);
             double tau, eloc, gr;
             int nh;
-            if (KIND == 1) {
-                step_bitparallel<NW>(a, dm, tb, sc, u01, tau, eloc, gr, nh);
+            if (KIND != 0) {
+                step_bitparallel<NW, KC>(a, dm, tb, sc, u01, tau, eloc, gr, nh);
             } else {
                 int chosen;
                 step_enumerate<NW>(a, dm, tb, u01, tau, eloc, gr, nh, chosen, nullptr);
@@ -138,7 +140,7 @@ walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTa
 
     // block reduction in fixed order: lanes -> warps -> block (reuses the per-thread scratch region)
     __syncthreads();
-    double(*sm)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(KIND == 1 ? (unsigned char*)sc.cum : smem_raw);
+    double(*sm)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(KIND != 0 ? (unsigned char*)sc.cum : smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NUM_ACC; ++i) {
@@ -239,7 +241,8 @@ static cudaError_t launch_one(const WalkerLaunch& L, cudaStream_t s) {
 template <int NW>
 static cudaError_t launch_nw(const WalkerLaunch& L, cudaStream_t s) {
     const bool rec = (L.rec_tau != nullptr);
-    if (L.kind == 1) return rec ? launch_one<NW, 1, true>(L, s) : launch_one<NW, 1, false>(L, s);
+    if (L.kind == 1 && L.tb.kc == 5) return rec ? launch_one<NW, 5, true>(L, s) : launch_one<NW, 5, false>(L, s);
+    if (L.kind == 1) return rec ? launch_one<NW, 4, true>(L, s) : launch_one<NW, 4, false>(L, s);
     return rec ? launch_one<NW, 0, true>(L, s) : launch_one<NW, 0, false>(L, s);
 }
 cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s) {
@@ -263,22 +266,23 @@ static cudaError_t occ_one(int N, int* blocks) {
                                                          walker_smem_bytes<NW, KIND>(N));
 }
 template <int NW>
-static cudaError_t occ_nw(int N, int kind, bool rec, int* blocks) {
-    if (kind == 1) return rec ? occ_one<NW, 1, true>(N, blocks) : occ_one<NW, 1, false>(N, blocks);
+static cudaError_t occ_nw(int N, int kind, int kc, bool rec, int* blocks) {
+    if (kind == 1 && kc == 5) return rec ? occ_one<NW, 5, true>(N, blocks) : occ_one<NW, 5, false>(N, blocks);
+    if (kind == 1) return rec ? occ_one<NW, 4, true>(N, blocks) : occ_one<NW, 4, false>(N, blocks);
     return rec ? occ_one<NW, 0, true>(N, blocks) : occ_one<NW, 0, false>(N, blocks);
 }
-cudaError_t walker_grid(int nw, int N, int kind, bool record, size_t n, int sm_count, int* grid) {
+cudaError_t walker_grid(int nw, int N, int kind, int kc, bool record, size_t n, int sm_count, int* grid) {
     int blocks = 0;
     cudaError_t e = cudaErrorInvalidValue;
     switch (nw) {
-        case 1: e = occ_nw<1>(N, kind, record, &blocks); break;
-        case 2: e = occ_nw<2>(N, kind, record, &blocks); break;
-        case 3: e = occ_nw<3>(N, kind, record, &blocks); break;
-        case 4: e = occ_nw<4>(N, kind, record, &blocks); break;
-        case 5: e = occ_nw<5>(N, kind, record, &blocks); break;
-        case 6: e = occ_nw<6>(N, kind, record, &blocks); break;
-        case 7: e = occ_nw<7>(N, kind, record, &blocks); break;
-        case 8: e = occ_nw<8>(N, kind, record, &blocks); break;
+        case 1: e = occ_nw<1>(N, kind, kc, record, &blocks); break;
+        case 2: e = occ_nw<2>(N, kind, kc, record, &blocks); break;
+        case 3: e = occ_nw<3>(N, kind, kc, record, &blocks); break;
+        case 4: e = occ_nw<4>(N, kind, kc, record, &blocks); break;
+        case 5: e = occ_nw<5>(N, kind, kc, record, &blocks); break;
+        case 6: e = occ_nw<6>(N, kind, kc, record, &blocks); break;
+        case 7: e = occ_nw<7>(N, kind, kc, record, &blocks); break;
+        case 8: e = occ_nw<8>(N, kind, kc, record, &blocks); break;
     }
     if (e != cudaSuccess) return e;
     if (blocks < 1) blocks = 1;

@@ -292,8 +292,8 @@ function _descend(f, p0; use_amsgrad, maxiter=100, α=0.01, β1=0.1, β2=0.01, e
         p = Float64[only(p0)]
         if f isa GPUKineticVQMC
             check(ccall((:gwz_amsgrad_vqmc, LIB), Cint,
-                        (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, UInt64, Cint, Ref{GdTrace}),
-                        f.result.walkers, p, opts, f.steps, GWZ_KERNEL_BITPARALLEL, tr))
+                        (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, UInt64, Cint, Cuint, Ref{GdTrace}),
+                        f.result.walkers, p, opts, f.steps, GWZ_KERNEL_BITPARALLEL, Cuint(0), tr))
         else
             check(ccall((:gwz_amsgrad_sweep, LIB), Cint,
                         (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, Ref{GdTrace}), f.sweep, p, opts, tr))

@@ -108,11 +108,12 @@ class Walkers:
         check(lib().gwz_walkers_set_step_counter(self._h, int(steps_done)))
 
     def run(self, params, steps: int, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
-            keep_acc: bool = False) -> _capi.VqmcResult:
+            keep_acc: bool = False, pooled: bool = False) -> _capi.VqmcResult:
         p = as_params(params, 1)
         r = _capi.VqmcResult()
+        flags = (_capi.RUN_KEEP_ACC if keep_acc else 0) | (_capi.RUN_POOLED if pooled else 0)
         check(lib().gwz_vqmc_run(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), int(steps), int(burn_in),
-                                 int(kernel), _capi.RUN_KEEP_ACC if keep_acc else 0, C.byref(r)))
+                                 int(kernel), flags, C.byref(r)))
         return r
 
     def run_record(self, params, steps: int, kernel: int = _capi.KERNEL_BITPARALLEL, keep_acc: bool = False,
@@ -153,7 +154,11 @@ class KineticVQMCResult:
     ``local_energy_estimator(res)`` and ``rows()`` follow state.jl:137-164,265-298,91-132.
     """
 
-    def __init__(self, hamiltonian, ansatz, params, walkers: Walkers, record: bool, kernel: int, burn_in: int = 0):
+    def __init__(self, hamiltonian, ansatz, params, walkers: Walkers, record: bool, kernel: int, burn_in: int = 0,
+                 estimator: str = "walker_mean"):
+        if estimator not in ("walker_mean", "pooled"):
+            raise ValueError("estimator must be 'walker_mean' (reference, state.jl:137-149) or 'pooled'")
+        self.estimator = estimator
         self.hamiltonian, self.ansatz = hamiltonian, ansatz
         self.params = as_params(params, ansatz.N_PARAMS)
         self.walkers_handle = walkers
@@ -183,7 +188,7 @@ class KineticVQMCResult:
         else:
             if burn:
                 w.run(self.params, max(burn, 1), kernel=self.kernel)
-            r = w.run(self.params, steps, kernel=self.kernel, keep_acc=keep)
+            r = w.run(self.params, steps, kernel=self.kernel, keep_acc=keep, pooled=self.estimator == "pooled")
         self.steps = self.steps + steps if keep else steps
         self.last = r
         return self
@@ -237,10 +242,13 @@ class KineticVQMCResult:
 
 def kinetic_vqmc(hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, params, *, samples=1e6, walkers=None,
                  steps=None, seed: int = DEFAULT_SEED, record=None, burn_in: int = 0,
-                 kernel: int = _capi.KERNEL_BITPARALLEL, ctx: Context | None = None) -> KineticVQMCResult:
+                 kernel: int = _capi.KERNEL_BITPARALLEL, ctx: Context | None = None,
+                 estimator: str = "walker_mean") -> KineticVQMCResult:
     """``kinetic_vqmc(hamiltonian, ansatz, params; samples=1e6, walkers, steps=round(Int, samples/walkers))``
     (qmc.jl:129-146).  Extra keywords: seed (Philox key), record (keep per-step series; default: when
-    they fit in 256 MiB), burn_in (default 0 = reference behaviour), kernel, ctx."""
+    they fit in 256 MiB), burn_in (default 0 = reference behaviour), kernel, ctx, estimator ('walker_mean' =
+    the reference's mean of per-walker ratio estimates; 'pooled' = one ratio over all walkers and steps, which
+    has no per-walker O(tau_corr/steps) bias -- preferable for many short walkers; needs record=False)."""
     if not isinstance(ansatz, GutzwillerAnsatz) or ansatz.hamiltonian is not hamiltonian and \
             (ansatz.hamiltonian.u, ansatz.hamiltonian.t) != (hamiltonian.u, hamiltonian.t):
         raise TypeError("this build covers GutzwillerAnsatz(H) with H::HubbardReal1D")
@@ -250,20 +258,25 @@ def kinetic_vqmc(hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, params, *, 
     if steps is None:
         steps = int(round(samples / walkers))  # qmc.jl:133
     steps = int(steps)
-    res = _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx)
+    res = _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx, estimator)
     return res._run(steps, keep=False)
 
 
-def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx):
+def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx,
+                 estimator="walker_mean"):
     model = hamiltonian.model(ctx)
     world, rank = distributed_state() if (ctx is None) else (1, 0)
     begin, end = shard_range(walkers, world, rank)
     if end <= begin:
         raise ValueError("fewer walkers than GPUs")
+    if estimator == "pooled":
+        if record:
+            raise ValueError("estimator='pooled' works on the running sums; use record=False")
+        record = False
     if record is None:
         record = (end - begin) * max(steps, 1) * (16 + 8 * model.words) <= RECORD_LIMIT_BYTES and world == 1
     w = Walkers(model, end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
-    return KineticVQMCResult(hamiltonian, ansatz, params, w, bool(record), kernel, burn_in)
+    return KineticVQMCResult(hamiltonian, ansatz, params, w, bool(record), kernel, burn_in, estimator)
 
 
 def kinetic_vqmc_continue(res: KineticVQMCResult, *, steps=None) -> KineticVQMCResult:
@@ -355,16 +368,16 @@ class KineticVQMC:
 
     def __init__(self, hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, *, samples=1e6, walkers=None, steps=None,
                  seed: int = DEFAULT_SEED, record=None, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
-                 ctx: Context | None = None):
+                 ctx: Context | None = None, estimator: str = "walker_mean"):
         if walkers is None:
             walkers = default_walkers(samples)
         self.hamiltonian, self.ansatz = hamiltonian, ansatz
         self.walkers = int(walkers)
         self.steps = int(round(samples / self.walkers)) if steps is None else int(steps)  # wrapper.jl:56
         if record is None:
-            record = self.walkers == 1  # a single walker has no cross-walker error bar: keep its series
+            record = self.walkers == 1 and estimator != "pooled"  # one walker has no cross-walker error bar
         self.result = _make_result(hamiltonian, ansatz, np.zeros(ansatz.N_PARAMS), self.walkers, self.steps, seed,
-                                   record, burn_in, kernel, ctx)
+                                   record, burn_in, kernel, ctx, estimator)
 
     def _reset_and_run(self, params, samples, steps):
         if steps is None:

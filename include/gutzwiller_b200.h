@@ -57,6 +57,10 @@ enum gwz_kernel_kind {
 /* flags of gwz_vqmc_run */
 #define GWZ_RUN_KEEP_ACC 1u /* continue the estimators (kinetic_vqmc!(res), qmc.jl:108-111) instead of
                                clearing them first (KineticVQMC `_reset!`, wrapper.jl:74-79) */
+#define GWZ_RUN_POOLED 2u   /* report the pooled ratio estimator (sum over ALL walkers and steps) in val/grad
+                               instead of the reference's mean of per-walker estimates (state.jl:137-149);
+                               the latter carries an O(tau_corr/steps) bias per walker that does not average
+                               out over walkers, which matters for many short walkers */
 
 typedef struct gwz_context gwz_context;
 typedef struct gwz_model gwz_model;
@@ -209,7 +213,7 @@ int gwz_adaptive_gradient_descent(gwz_objective_fn val_and_grad, gwz_objective_f
                                   const double *p0, int np, const gwz_gd_opts *opts, gwz_gd_trace *trace);
 /* built-in objectives: amsgrad(qmc::KineticVQMC, p0) and amsgrad(le::LocalEnergyEvaluator, p0) */
 int gwz_amsgrad_vqmc(gwz_walkers *w, const double *p0, const gwz_gd_opts *opts, uint64_t steps_per_walker,
-                     int kernel_kind, gwz_gd_trace *trace);
+                     int kernel_kind, unsigned flags, gwz_gd_trace *trace);
 int gwz_amsgrad_sweep(gwz_sweep *s, const double *p0, const gwz_gd_opts *opts, gwz_gd_trace *trace);
 
 #ifdef __cplusplus

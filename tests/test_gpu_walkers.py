@@ -165,8 +165,15 @@ def test_bigger_system_energy_vs_sweep(gw):
     r = res.last
     assert abs(r.val - exact) < 4 * r.err and r.err < 0.01
     assert abs(r.pooled_val - exact) < 4 * r.err
-    assert abs(r.grad[0] - egrad[0]) < 5 * r.grad_err[0] + 0.02
+    # The reference's estimator (mean over walkers of per-walker covariances, state.jl:42-49,137-149) is
+    # biased by O(tau_corr/steps) per walker, and that does not average out over walkers (SURVEY.md 7,
+    # "Estimator fidelity"); the pooled covariance is the unbiased comparison with the sweep gradient.
+    assert abs(r.pooled_grad[0] - egrad[0]) < 5 * r.grad_err[0] + 0.005
+    assert abs(r.grad[0] - egrad[0]) < 0.15
     assert r.walkers == 8192 and r.steps == 8192 * 2000
+    pooled = gw.kinetic_vqmc(H, ans, 0.3331889106855026, walkers=8192, steps=2000, burn_in=240, estimator="pooled")
+    assert pooled.last.val == pooled.last.pooled_val and pooled.last.grad[0] == pooled.last.pooled_grad[0]
+    assert abs(gw.val_and_grad(pooled)[1][0] - egrad[0]) < 5 * r.grad_err[0] + 0.005
 
 
 def test_sharding_invariance_logical_shards(gw, oracle_mod):
