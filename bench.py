@@ -168,6 +168,7 @@ def run_ours(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    launches0 = gw.launch_count()
     kernel_ms = []
     hops = 0
     for _ in range(args.steps):
@@ -175,6 +176,7 @@ def run_ours(args):
         kernel_ms.append(last.kernel_ms)
         hops += last.hops
     ev1.record(stream)
+    launches = gw.launch_count() - launches0
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
@@ -234,7 +236,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": 8 + 1040, "d2h_bytes_per_step": 8 * 12 + 4,
                 "note": "val_and_grad(qmc, p) from host params to host (val, grad); inputs are one double plus the "
                         "kernel-argument tables, outputs the 12-double accumulator vector"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                      "traffic": None, "peak_source": peak_src,
                      "note": "walker kernel keeps its state in registers: HBM traffic is one load+store of the walker "

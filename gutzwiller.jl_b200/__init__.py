@@ -17,10 +17,10 @@ from .hamiltonian import (AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1
                           num_modes, num_parameters, starting_address, valtype)
 from .localenergy import LocalEnergyEvaluator
 from .runtime import (Context, Model, comm_init_all, default_context, distributed_state, init_distributed,
-                      nccl_unique_id, shard_range)
+                      launch_count, nccl_unique_id, shard_range)
 from .vqmc import (BlockingResult, CombinedBlockingResult, KineticVQMC, KineticVQMCResult, Walkers,
                    blocking_analysis, default_walkers, kinetic_vqmc, kinetic_vqmc_continue,
-                   local_energy_estimator, mean, resample, run_group, var)
+                   local_energy_estimator, mean, resample, run_group, sampled_vector, var)
 
 lib()  # fail at import time if the CUDA library is missing
 

@@ -67,6 +67,7 @@ _vp, _dp, _u64p, _i32p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64
 SIGNATURES = {
     "gwz_last_error": (C.c_char_p, []),
     "gwz_version": (C.c_int, []),
+    "gwz_launch_count": (C.c_int, [_u64p]),
     "gwz_context_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "gwz_context_destroy": (C.c_int, [_vp]),
     "gwz_context_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

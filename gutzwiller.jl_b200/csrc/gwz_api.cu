@@ -5,6 +5,7 @@
 // There is no CPU implementation of any sampled or swept quantity in this file.
 #include "gutzwiller_b200.h"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +43,19 @@ static int fail(int code, const std::string& msg) {
     do {                                                         \
         if (!(cond)) return fail(GWZ_ERR_INVALID, (msg));        \
     } while (0)
+
+// number of kernels this library has launched (every launch goes through GWZ_LAUNCH)
+static std::atomic<uint64_t> g_launches{0};
+#define GWZ_LAUNCH(expr)   \
+    do {                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed); \
+        GWZ_CUDA(expr);    \
+    } while (0)
+extern "C" int gwz_launch_count(uint64_t* n) {
+    if (!n) return fail(GWZ_ERR_INVALID, "gwz_launch_count: NULL argument");
+    *n = g_launches.load(std::memory_order_relaxed);
+    return GWZ_OK;
+}
 
 extern "C" const char* gwz_last_error(void) { return g_last_error.c_str(); }
 extern "C" int gwz_version(void) { return GWZ_VERSION; }
@@ -455,7 +469,7 @@ extern "C" int gwz_probe_addresses(gwz_model* m, const uint64_t* addr_words, siz
     L.chosen = d_c.p;
     L.next_addr = d_next.p;
     L.err_flag = c->d_err;
-    GWZ_CUDA(launch_probe(L, s));
+    GWZ_LAUNCH(launch_probe(L, s));
     if (e_loc) GWZ_CUDA(cudaMemcpyAsync(e_loc, d_e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     if (residence_time) GWZ_CUDA(cudaMemcpyAsync(residence_time, d_t.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     if (grad_ratio) GWZ_CUDA(cudaMemcpyAsync(grad_ratio, d_g.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -482,7 +496,7 @@ extern "C" int gwz_ansatz_val_and_grad(gwz_model* m, const uint64_t* addr_words,
     GWZ_CUDA(d_v.alloc(n));
     GWZ_CUDA(d_g.alloc(n));
     GWZ_CUDA(cudaMemcpyAsync(d_addr.p, addr_words, sizeof(uint64_t) * n * m->W, cudaMemcpyHostToDevice, s));
-    GWZ_CUDA(launch_ansatz(m->dm, params[0], m->nw, d_addr.p, n, d_v.p, d_g.p, s));
+    GWZ_LAUNCH(launch_ansatz(m->dm, params[0], m->nw, d_addr.p, n, d_v.p, d_g.p, s));
     if (val) GWZ_CUDA(cudaMemcpyAsync(val, d_v.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     if (grad) GWZ_CUDA(cudaMemcpyAsync(grad, d_g.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     GWZ_CUDA(cudaStreamSynchronize(s));
@@ -523,7 +537,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     DevBuf<uint64_t> d_start;
     GWZ_CUDA(d_start.alloc(m->W));
     GWZ_CUDA(cudaMemcpyAsync(d_start.p, start_addr, sizeof(uint64_t) * m->W, cudaMemcpyHostToDevice, c->stream));
-    GWZ_CUDA(launch_walker_init(w->d_addr, w->d_acc, w->n, m->W, d_start.p, c->stream));
+    GWZ_LAUNCH(launch_walker_init(w->d_addr, w->d_acc, w->n, m->W, d_start.p, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     *out = w;
     return GWZ_OK;
@@ -555,7 +569,7 @@ extern "C" int gwz_walkers_get_addresses(gwz_walkers* w, uint64_t* addr_words) {
     const int W = w->m->W;
     DevBuf<uint64_t> tmp;
     GWZ_CUDA(tmp.alloc(w->n * W));
-    GWZ_CUDA(launch_transpose_addr(w->d_addr, tmp.p, w->n, W, false, c->stream));
+    GWZ_LAUNCH(launch_transpose_addr(w->d_addr, tmp.p, w->n, W, false, c->stream));
     GWZ_CUDA(cudaMemcpyAsync(addr_words, tmp.p, sizeof(uint64_t) * w->n * W, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     return GWZ_OK;
@@ -569,7 +583,7 @@ extern "C" int gwz_walkers_set_addresses(gwz_walkers* w, const uint64_t* addr_wo
     DevBuf<uint64_t> tmp;
     GWZ_CUDA(tmp.alloc(w->n * W));
     GWZ_CUDA(cudaMemcpyAsync(tmp.p, addr_words, sizeof(uint64_t) * w->n * W, cudaMemcpyHostToDevice, c->stream));
-    GWZ_CUDA(launch_transpose_addr(tmp.p, w->d_addr, w->n, W, true, c->stream));
+    GWZ_LAUNCH(launch_transpose_addr(tmp.p, w->d_addr, w->n, W, true, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     return GWZ_OK;
 }
@@ -626,13 +640,13 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         int g2 = 0;
         GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, false, w->n, c->prop.multiProcessorCount, &g2));
         L.grid = g2;
-        GWZ_CUDA(launch_walkers(L, c->stream));
+        GWZ_LAUNCH(launch_walkers(L, c->stream));
         w->steps_done += burn_in;
         L.grid = grid;
     }
     const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
     if (!keep)  // new estimator: pick its reference point from where the walkers are now
-        GWZ_CUDA(launch_walker_ref(m->dm, tb, m->nw, w->d_addr, w->n, w->d_shift, c->stream));
+        GWZ_LAUNCH(launch_walker_ref(m->dm, tb, m->nw, w->d_addr, w->n, w->d_shift, c->stream));
     L.step0 = w->steps_done;
     L.steps = steps;
     L.accumulate = 1;
@@ -640,11 +654,11 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.rec_tau = rec_tau;
     L.rec_eloc = rec_eloc;
     L.rec_addr = rec_addr;
-    GWZ_CUDA(launch_walkers(L, c->stream));
+    GWZ_LAUNCH(launch_walkers(L, c->stream));
     if (time_it) GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
     w->steps_done += steps;
     w->acc_steps = keep ? w->acc_steps + steps : steps;
-    GWZ_CUDA(launch_reduce_partials(w->d_partials, grid, NUM_ACC, w->d_vec, c->stream));
+    GWZ_LAUNCH(launch_reduce_partials(w->d_partials, grid, NUM_ACC, w->d_vec, c->stream));
     return GWZ_OK;
 }
 
@@ -700,7 +714,7 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
                                          cudaMemcpyDeviceToDevice, c->stream));
                 ++rows;
             }
-        GWZ_CUDA(launch_reduce_partials(c->d_group, rows, NUM_ACC, c->d_acc, c->stream));
+        GWZ_LAUNCH(launch_reduce_partials(c->d_group, rows, NUM_ACC, c->d_acc, c->stream));
     }
     bool any_comm = false;
     for (gwz_context* c : ctxs) any_comm |= (c->comm != nullptr);
@@ -782,7 +796,7 @@ extern "C" int gwz_walkers_estimates(gwz_walkers* w, double* val_w, double* grad
     DevBuf<double> d_v, d_g;
     GWZ_CUDA(d_v.alloc(w->n));
     GWZ_CUDA(d_g.alloc(w->n));
-    GWZ_CUDA(launch_walker_estimates(w->d_acc, w->n, w->d_shift, d_v.p, d_g.p, c->stream));
+    GWZ_LAUNCH(launch_walker_estimates(w->d_acc, w->n, w->d_shift, d_v.p, d_g.p, c->stream));
     if (val_w) GWZ_CUDA(cudaMemcpyAsync(val_w, d_v.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
     if (grad_w) GWZ_CUDA(cudaMemcpyAsync(grad_w, d_g.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
@@ -836,7 +850,7 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
             DevBuf<uint64_t> tmp;
             GWZ_CUDA(tmp.alloc(dim * W));
             GWZ_CUDA(cudaMemcpyAsync(tmp.p, basis_words, sizeof(uint64_t) * dim * W, cudaMemcpyHostToDevice, c->stream));
-            GWZ_CUDA(launch_transpose_addr(tmp.p, s->d_basis, dim, W, true, c->stream));
+            GWZ_LAUNCH(launch_transpose_addr(tmp.p, s->d_basis, dim, W, true, c->stream));
             GWZ_CUDA(cudaStreamSynchronize(c->stream));
         }
     } else {
@@ -894,9 +908,9 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     L.grid = s->grid;
     L.chunk = s->chunk;
     GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
-    GWZ_CUDA(launch_sweep(L, c->stream));
+    GWZ_LAUNCH(launch_sweep(L, c->stream));
     GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
-    GWZ_CUDA(launch_reduce_partials(s->d_partials, s->grid, 4, c->d_acc, c->stream));
+    GWZ_LAUNCH(launch_reduce_partials(s->d_partials, s->grid, 4, c->d_acc, c->stream));
     if (c->comm) {
         const NcclApi* api = nccl_api(nullptr);
         if (!api) return fail(GWZ_ERR_NCCL, "NCCL unavailable");
@@ -950,7 +964,7 @@ static int sweep_terms_impl(gwz_sweep* s, const double* params, uint64_t first, 
     L.count = count;
     L.terms_out = out ? d_out.p : nullptr;
     L.states_out = states ? d_states.p : nullptr;
-    GWZ_CUDA(launch_sweep_terms(L, c->stream));
+    GWZ_LAUNCH(launch_sweep_terms(L, c->stream));
     if (out) GWZ_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * count * 4, cudaMemcpyDeviceToHost, c->stream));
     if (states)
         GWZ_CUDA(cudaMemcpyAsync(states, d_states.p, sizeof(uint64_t) * count * m->W, cudaMemcpyDeviceToHost, c->stream));

@@ -54,6 +54,13 @@ class Context:
         check(lib().gwz_context_comm_init(self._h, world_size, rank, buf))
 
 
+def launch_count() -> int:
+    """Kernels launched by the library so far (process-wide)."""
+    n = C.c_uint64()
+    check(lib().gwz_launch_count(C.byref(n)))
+    return n.value
+
+
 def nccl_unique_id() -> bytes:
     buf = (C.c_uint8 * _capi.NCCL_ID_BYTES)()
     check(lib().gwz_nccl_unique_id(buf))

@@ -359,6 +359,20 @@ def var(res: KineticVQMCResult) -> float:
     return res.last.pooled_var
 
 
+def sampled_vector(res: KineticVQMCResult):
+    """``DVec(res)`` (state.jl:303-319): deposit every recorded row's residence time on its address and
+    normalise (2-norm).  Returns ``(addresses uint64[k, W], values float64[k])`` sorted by address."""
+    tau, ad = res.residence_times(), res.addresses()
+    W = ad.shape[-1]
+    flat = np.ascontiguousarray(ad.reshape(-1, W))
+    keys = flat.view([("w", np.uint64, (W,))]).ravel() if W > 1 else flat[:, 0]
+    uniq, inverse = np.unique(keys, return_inverse=True)
+    vals = np.bincount(inverse.ravel(), weights=tau.reshape(-1), minlength=len(uniq))
+    vals = vals / np.linalg.norm(vals)  # normalize!(dv)
+    addrs = uniq["w"] if W > 1 else uniq.reshape(-1, 1)
+    return np.ascontiguousarray(addrs, dtype=np.uint64), vals
+
+
 class KineticVQMC:
     """``KineticVQMC(hamiltonian, ansatz; samples=1e6, walkers, steps)`` (wrapper.jl:45-63).
 

@@ -69,6 +69,8 @@ typedef struct gwz_sweep gwz_sweep;
 
 const char *gwz_last_error(void);
 int gwz_version(void);
+/* number of CUDA kernels launched by this library so far (process-wide; for benchmarks) */
+int gwz_launch_count(uint64_t *n);
 
 /* ---- context: one CUDA device + stream (+ optional NCCL communicator) --------------------- */
 int gwz_context_create(int device, gwz_context **out);

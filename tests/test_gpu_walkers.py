@@ -242,3 +242,27 @@ def test_walker_argument_errors(gw):
         w.run([float("nan")], 10)
     with pytest.raises(ValueError):
         w.estimates()
+
+
+@pytest.mark.parametrize("kernel", ["bitparallel", "enumerate"])
+def test_sampler_draws_from_psi_squared(gw, kernel):
+    """test/qmc.jl:53-75 ("Sampling vector squared"): the residence-time histogram of the sampled addresses
+    converges to |psi|^2 = normalize(abs2(ansatz)): dot(sampled, vector_sq) ~ 1 (rtol 1e-4 at 1e6 samples)."""
+    H = gw.HubbardReal1D(gw.near_uniform(5, 5), t=0.1)  # the reference's test Hamiltonian (test/qmc.jl:11)
+    ans = gw.GutzwillerAnsatz(H)
+    kind = gw.KERNEL_BITPARALLEL if kernel == "bitparallel" else gw.KERNEL_ENUMERATE
+    res = gw.kinetic_vqmc(H, ans, 0.5, samples=2e6, walkers=256, record=True, kernel=kind)
+    addrs, vals = gw.sampled_vector(res)
+    le = gw.LocalEnergyEvaluator(H, ans)
+    states = le.states()[:, 0]
+    psi2 = le.terms(0.5)[:, 1]  # den = psi^2 per state (localenergy.jl:111)
+    psi2 = psi2 / np.linalg.norm(psi2)
+    assert len(states) == 126 and set(int(a) for a in addrs[:, 0]) <= set(int(s) for s in states)
+    lookup = {int(s): p for s, p in zip(states, psi2)}
+    dot = sum(v * lookup[int(a)] for a, v in zip(addrs[:, 0], vals))
+    assert abs(dot - 1.0) < 1e-4
+    assert len(addrs) == 126  # every basis state visited
+    # exact energy within 3 sigma of the blocked estimate (test/qmc.jl:69-70)
+    est = gw.local_energy_estimator(res)
+    exact = le(0.5)
+    assert est.mean - 3.5 * est.err < exact < est.mean + 3.5 * est.err
