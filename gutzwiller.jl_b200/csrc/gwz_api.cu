@@ -99,7 +99,40 @@ struct gwz_walkers {
     int partials_cap = 0;
     double* d_vec = nullptr;  // NUM_ACC doubles: this set's reduced vector
     double* d_shift = nullptr;  // (E_ref, G_ref): reference point of the shifted running sums
+    // Where the walkers currently live: unary bitstrings (d_addr) or occupation bit-planes (d_planes).
+    // The production kernel works on planes; everything that needs addresses converts back first.
+    uint32_t* d_planes = nullptr;
+    uint64_t* d_ref_addr = nullptr;  // W words: unary copy of walker 0 for the reference-point kernel
+    bool in_planes = false;
 };
+
+static bool planes_enabled() {
+    const char* e = std::getenv("GWZ_PLANES");
+    return !(e && e[0] == '0');
+}
+
+// make d_addr (unary) the valid copy
+static int to_unary(gwz_walkers* w) {
+    if (!w->in_planes) return GWZ_OK;
+    gwz_context* c = w->m->ctx;
+    GWZ_LAUNCH(launch_planes_to_unary(w->d_planes, w->n, w->m->dm, 0, w->n, w->d_addr, c->stream));
+    w->in_planes = false;
+    return GWZ_OK;
+}
+// make d_planes the valid copy
+static int to_planes(gwz_walkers* w) {
+    if (w->in_planes) return GWZ_OK;
+    gwz_context* c = w->m->ctx;
+    if (!w->d_planes) {
+        int nwm, np;
+        planes_shape(w->m->N, w->m->M, &nwm, &np);
+        GWZ_CUDA(cudaMalloc(&w->d_planes, sizeof(uint32_t) * (size_t)nwm * np * w->n));
+        GWZ_CUDA(cudaMalloc(&w->d_ref_addr, sizeof(uint64_t) * w->m->W));
+    }
+    GWZ_LAUNCH(launch_unary_to_planes(w->d_addr, w->n, w->m->dm, w->d_planes, c->stream));
+    w->in_planes = true;
+    return GWZ_OK;
+}
 
 struct gwz_sweep {
     gwz_model* m;
@@ -275,6 +308,9 @@ extern "C" int gwz_model_create_hubbard1d_gutzwiller(gwz_context* ctx, int N, in
     dm.ext_bs = (B + 1) & 31;
     dm.u = u;
     dm.t = t;
+    for (int p = 0; p < M; ++p) dm.mmask[p >> 5] |= 1u << (p & 31);
+    dm.mtopmask[(M - 1) >> 5] = 0xFFFFFFFFu;
+    dm.mtop_b = (M - 1) & 31;
     dm.extmask_lo[dm.ext_ws] = 0xFFFFFFFFu;
     if (dm.ext_bs != 0 && dm.ext_ws + 1 < MAXNW) dm.extmask_hi[dm.ext_ws + 1] = 0xFFFFFFFFu;
     for (int p = 0; p <= B; ++p) dm.zmask[p >> 5] |= 1u << (p & 31);
@@ -551,6 +587,8 @@ extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
     cudaFree(w->d_partials);
     cudaFree(w->d_vec);
     cudaFree(w->d_shift);
+    cudaFree(w->d_planes);
+    cudaFree(w->d_ref_addr);
     delete w;
     return GWZ_OK;
 }
@@ -566,6 +604,7 @@ extern "C" int gwz_walkers_get_addresses(gwz_walkers* w, uint64_t* addr_words) {
     GWZ_REQUIRE(w && addr_words, "gwz_walkers_get_addresses: NULL argument");
     gwz_context* c = w->m->ctx;
     if (int rc = use_device(c)) return rc;
+    if (int rc = to_unary(w)) return rc;
     const int W = w->m->W;
     DevBuf<uint64_t> tmp;
     GWZ_CUDA(tmp.alloc(w->n * W));
@@ -585,6 +624,7 @@ extern "C" int gwz_walkers_set_addresses(gwz_walkers* w, const uint64_t* addr_wo
     GWZ_CUDA(cudaMemcpyAsync(tmp.p, addr_words, sizeof(uint64_t) * w->n * W, cudaMemcpyHostToDevice, c->stream));
     GWZ_LAUNCH(launch_transpose_addr(tmp.p, w->d_addr, w->n, W, true, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    w->in_planes = false;  // the unary copy is now the valid one
     return GWZ_OK;
 }
 
@@ -611,8 +651,13 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
     const bool record = rec_tau != nullptr;
+    // production sampling runs on the occupation bit-plane representation; recording runs and the
+    // reference-order kernel need the unary addresses step by step
+    const bool planes = (kind == GWZ_KERNEL_BITPARALLEL) && !record && tb.kc == 4 && planes_enabled();
+    if (int rc = planes ? to_planes(w) : to_unary(w)) return rc;
     int grid = 0;
-    GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
+    if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+    else GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
     if (int rc = ensure_partials(w, grid)) return rc;
     WalkerLaunch L;
     L.dm = m->dm;
@@ -620,6 +665,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.nw = m->nw;
     L.kind = kind;
     L.addr = w->d_addr;
+    L.planes = w->d_planes;
     L.acc = w->d_acc;
     L.n = w->n;
     L.global_offset = w->offset;
@@ -637,16 +683,28 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         L.steps = burn_in;
         L.accumulate = 0;
         L.reset_acc = 0;
-        int g2 = 0;
-        GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, false, w->n, c->prop.multiProcessorCount, &g2));
-        L.grid = g2;
-        GWZ_LAUNCH(launch_walkers(L, c->stream));
+        if (planes) {
+            GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
+        } else {
+            int g2 = 0;
+            GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, false, w->n, c->prop.multiProcessorCount, &g2));
+            L.grid = g2;
+            GWZ_LAUNCH(launch_walkers(L, c->stream));
+            L.grid = grid;
+        }
         w->steps_done += burn_in;
-        L.grid = grid;
     }
     const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
-    if (!keep)  // new estimator: pick its reference point from where the walkers are now
-        GWZ_LAUNCH(launch_walker_ref(m->dm, tb, m->nw, w->d_addr, w->n, w->d_shift, c->stream));
+    if (!keep) {  // new estimator: pick its reference point from where walker 0 is now
+        const uint64_t* ref = w->d_addr;
+        size_t stride = w->n;
+        if (planes) {
+            GWZ_LAUNCH(launch_planes_to_unary(w->d_planes, w->n, m->dm, 0, 1, w->d_ref_addr, c->stream));
+            ref = w->d_ref_addr;
+            stride = 1;
+        }
+        GWZ_LAUNCH(launch_walker_ref(m->dm, tb, m->nw, ref, stride, w->d_shift, c->stream));
+    }
     L.step0 = w->steps_done;
     L.steps = steps;
     L.accumulate = 1;
@@ -654,7 +712,8 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.rec_tau = rec_tau;
     L.rec_eloc = rec_eloc;
     L.rec_addr = rec_addr;
-    GWZ_LAUNCH(launch_walkers(L, c->stream));
+    if (planes) GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
+    else GWZ_LAUNCH(launch_walkers(L, c->stream));
     if (time_it) GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
     w->steps_done += steps;
     w->acc_steps = keep ? w->acc_steps + steps : steps;

@@ -36,6 +36,11 @@ struct DevModel {
     uint32_t amask[MAXNW];  // bits 0..B-1 (address bits)
     uint32_t extmask_lo[MAXNW];  // all ones for word ext_ws, else 0
     uint32_t extmask_hi[MAXNW];  // all ones for word ext_ws+1 (if ext_bs != 0), else 0
+    // occupation bit-plane representation (gwz_planes.cuh): M bits per plane
+    uint32_t mmask[MAXNW];     // bits 0..M-1
+    uint32_t mtopmask[MAXNW];  // all ones for the word holding bit M-1, else 0
+    int mtop_b;                // (M-1) & 31
+    int pad_;
 };
 
 constexpr int STEP_BLOCK = 128;  // threads per CTA of every kernel that selects moves (scratch layout)
@@ -364,6 +369,34 @@ struct BondSums {
     int nocc;        // occupied modes, n_hops = 2*nocc                         (qmc.jl:15)
 };
 
+// How the rare generic bonds are evaluated is a policy of the state representation.  Unary bitstring:
+// stage the extended string + generic-bond mask of this thread in shared memory, run big_pass.
+template <int NW, int KC>
+struct UnaryBig {
+    const uint32_t (&e)[NW];
+    const uint32_t (&big)[NW];
+    const DevModel& dm;
+    const StepScratch<NW, KC>& sc;
+    __device__ __forceinline__ bool any() const {
+        uint32_t a = 0u;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a |= big[i];
+        return a != 0u;
+    }
+    // mode 0: stage + sums; mode 1: selection (words are still staged from mode 0 of the same step)
+    __device__ __forceinline__ BigOut pass(int mode, double t) const {
+        const int tid = threadIdx.x;
+        if (mode == 0) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                sc.ew[i * STEP_BLOCK + tid] = e[i];
+                sc.bw[i * STEP_BLOCK + tid] = big[i];
+            }
+        }
+        return big_pass(sc.ew + tid, sc.bw + tid, NW, dm.B, dm.N, sc.exptab, sc.sqrtab, mode, t);
+    }
+};
+
 // Sum over all bonds.  The running sum of class weights cnt[k]*FS[k] (k ascending) after class k is
 // handed to `sink(k, S)` (kept for the class-ordered move selection; a no-op for the sweep).  Class 0
 // (L = R = 0: an empty bond) carries no hop and is skipped.  WITH_GRAD adds the ED sum needed by
@@ -376,10 +409,9 @@ struct SmemCumSink {
     __device__ __forceinline__ void operator()(int k, double v) const { cum[k * STEP_BLOCK] = v; }
 };
 
-template <int NW, int KC, bool WITH_GRAD, typename SINK>
-__device__ __forceinline__ double bond_sums(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
-                                            const BondMasks<NW, KC>& bm, const StepScratch<NW, KC>& sc, SINK&& sink,
-                                            BondSums& out, double& big_S) {
+template <int NW, int KC, bool WITH_GRAD, typename SINK, typename BIG>
+__device__ __forceinline__ double bond_sums(const DevTables& tb, const BondMasks<NW, KC>& bm, SINK&& sink,
+                                            const BIG& big, BondSums& out, double& big_S) {
     double S = 0.0, E = 0.0, ED = 0.0;
     int nocc = 0;
     int dd = 0;
@@ -406,19 +438,10 @@ __device__ __forceinline__ double bond_sums(const uint32_t (&e)[NW], const DevMo
     }
     const double reg_total = S;
     long long d = dd;
-    // rare: bonds next to a mode with >= KCAP particles
+    // rare: bonds next to a mode with >= KC particles
     double bS = 0.0;
-    uint32_t any_big = 0u;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) any_big |= bm.big[i];
-    if (any_big) {
-        const int t = threadIdx.x;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            sc.ew[i * STEP_BLOCK + t] = e[i];
-            sc.bw[i * STEP_BLOCK + t] = bm.big[i];
-        }
-        const BigOut o = big_pass(sc.ew + t, sc.bw + t, NW, dm.B, dm.N, sc.exptab, sc.sqrtab, 0, 0.0);
+    if (big.any()) {
+        const BigOut o = big.pass(0, 0.0);
         bS = o.S;
         E += o.E;
         if (WITH_GRAD) ED += o.ED;
@@ -451,9 +474,8 @@ __device__ __forceinline__ void stage_masks(const BondMasks<NW, KC>& bm, const S
 // by (class id, direction right-then-left, bond position), big bonds last.  T in [0,S).
 // Needs the prefix sums (SmemCumSink) and masks (stage_masks) of this thread in `sc`.
 // Returns the bond position z and the direction.
-template <int NW, int KC>
-__device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevModel& dm, const DevTables& tb,
-                                            const BondMasks<NW, KC>& bm, const StepScratch<NW, KC>& sc,
+template <int NW, int KC, typename BIG>
+__device__ __forceinline__ void select_move(const DevTables& tb, const StepScratch<NW, KC>& sc, const BIG& big,
                                             double reg_total, double big_S, double T, int& z_out, bool& right_out) {
     constexpr int NC = KC * KC;
     constexpr int BISECT = (NC - 1 <= 16) ? 4 : 5;  // ceil(log2(NC-1)) for KC = 4, 5
@@ -505,7 +527,7 @@ __device__ __forceinline__ void select_move(const uint32_t (&e)[NW], const DevMo
         right_out = right;
     } else {
         // walk the generic bonds in the same order as bond_sums (their words are still staged)
-        const BigOut o = big_pass(sc.ew + threadIdx.x, sc.bw + threadIdx.x, NW, dm.B, dm.N, sc.exptab, sc.sqrtab, 1, T - reg_total);
+        const BigOut o = big.pass(1, T - reg_total);
         z_out = o.z;
         right_out = o.right != 0;
     }

@@ -35,8 +35,9 @@ struct WalkerLaunch {
     int nw;    // 32-bit words of the extended string
     int kind;  // gwz_kernel_kind
     // walker state (SoA in HBM)
-    uint64_t* addr;  // [W][n]
-    double* acc;     // [NUM_WALKER_ACC][n]
+    uint64_t* addr;    // [W][n] unary bitstrings
+    uint32_t* planes;  // [(NP)(NWM)][n] occupation bit-planes (gwz_planes.cuh), when the walkers live there
+    double* acc;       // [NUM_WALKER_ACC][n]
     size_t n;
     uint64_t global_offset, seed, step0, steps;
     int accumulate;  // 0: burn-in (no estimator update, no reduction)
@@ -63,6 +64,14 @@ cudaError_t launch_walker_estimates(const double* acc, size_t n, const double* s
 // shift[0..1] = (E_loc, grad ratio) of walker 0's current address
 cudaError_t launch_walker_ref(const DevModel& dm, const DevTables& tb, int nw, const uint64_t* addr, size_t n,
                               double* shift, cudaStream_t s);
+// occupation bit-plane path (gwz_walker_planes.cu)
+void planes_shape(int N, int M, int* nwm, int* np);
+cudaError_t walker_planes_grid(int N, int M, size_t n, int sm_count, int* grid);
+cudaError_t launch_walkers_planes(const WalkerLaunch& L, cudaStream_t s);
+cudaError_t launch_unary_to_planes(const uint64_t* addr, size_t n, const DevModel& dm, uint32_t* planes, cudaStream_t s);
+// walkers first..first+count-1 -> unary SoA addr[W][count]
+cudaError_t launch_planes_to_unary(const uint32_t* planes, size_t n, const DevModel& dm, size_t first, size_t count,
+                                   uint64_t* addr, cudaStream_t s);
 // AoS (n x W) <-> SoA ([W][n]) address layout conversion
 cudaError_t launch_transpose_addr(const uint64_t* src, uint64_t* dst, size_t n, int W, bool to_soa, cudaStream_t s);
 

@@ -82,7 +82,8 @@ __device__ __forceinline__ void state_terms(const uint32_t (&a)[NW], const DevMo
     classify_bonds<NW, KC>(e, dm, bm);
     BondSums bs;
     double bigS;
-    bond_sums<NW, KC, true>(e, dm, tb, bm, sc, NoCumSink{}, bs, bigS);
+    const UnaryBig<NW, KC> big{e, bm.big, dm, sc};
+    bond_sums<NW, KC, true>(tb, bm, NoCumSink{}, big, bs, bigS);
     const double D = dm.u * (double)bs.d;
     const double psi2 = exp(-2.0 * tb.g * D);  // abs2(exp(-g*diag))  (localenergy.jl:108,111)
     const double eloc = D - dm.t * bs.E;

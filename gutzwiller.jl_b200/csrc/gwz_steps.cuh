@@ -17,8 +17,8 @@ __device__ __forceinline__ void step_bitparallel(uint32_t (&a)[NW], const DevMod
     classify_bonds<NW, KC>(e, dm, bm);
     BondSums bs;
     double bigS;
-    const double reg_total =
-        bond_sums<NW, KC, false>(e, dm, tb, bm, sc, SmemCumSink{sc.cum + threadIdx.x}, bs, bigS);
+    const UnaryBig<NW, KC> big{e, bm.big, dm, sc};
+    const double reg_total = bond_sums<NW, KC, false>(tb, bm, SmemCumSink{sc.cum + threadIdx.x}, big, bs, bigS);
     stage_masks<NW, KC>(bm, sc);
     const double D = dm.u * (double)bs.d;  // diagonal_element (qmc.jl:20)
     tau = 1.0 / bs.S;                      // |psi1| / sum |psi2|   (qmc.jl:33)
@@ -29,7 +29,7 @@ __device__ __forceinline__ void step_bitparallel(uint32_t (&a)[NW], const DevMod
     if (!(T < bs.S)) T = __longlong_as_double(__double_as_longlong(bs.S) - 1);
     int z;
     bool right;
-    select_move<NW, KC>(e, dm, tb, bm, sc, reg_total, bigS, T, z, right);
+    select_move<NW, KC>(tb, sc, big, reg_total, bigS, T, z, right);
     if (z >= 0) {
         if (ref_hop_index) *ref_hop_index = reference_hop_index<NW>(e, dm, z, right);
         apply_hop<NW>(a, dm, z, right);

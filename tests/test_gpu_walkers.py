@@ -266,3 +266,30 @@ def test_sampler_draws_from_psi_squared(gw, kernel):
     est = gw.local_energy_estimator(res)
     exact = le(0.5)
     assert est.mean - 3.5 * est.err < exact < est.mean + 3.5 * est.err
+
+
+@pytest.mark.parametrize("N,M,u,g", [(10, 10, 2.0, 1.0), (50, 50, 2.0, 0.33), (100, 100, 2.0, 0.33), (9, 6, 0.5, 0.05),
+                                     (7, 3, 1.0, 0.3), (33, 32, 2.0, 0.2), (64, 65, 1.0, 0.1), (120, 131, 2.0, 0.1),
+                                     (2, 2, 1.0, 0.3), (17, 40, 3.0, 0.2)])
+def test_planes_kernel_is_bitwise_identical_to_unary(gw, oracle_mod, N, M, u, g, monkeypatch):
+    """The production kernel keeps walkers as occupation bit-planes; class order, bond order and the
+    floating-point summation order are the same as on the unary bitstring, so trajectories and every
+    accumulator must agree bit for bit with the unary kernel (which is checked per step against the oracle)."""
+    o = oracle_mod.Oracle(N, M, u, 1.0)
+    model = gw.Model(N, M, u, 1.0)
+    onr = [0] * M
+    onr[M - 1] = N  # all bosons on the last site: exercises the generic (occupation >= 4) path and the ripple
+    starts = [o.near_uniform()[: o.W], o.from_onr(onr)[: o.W]]
+    for start in starts:
+        out = {}
+        for planes in ("1", "0"):
+            monkeypatch.setenv("GWZ_PLANES", planes)
+            w = gw.Walkers(model, 777, start, seed=21, global_offset=3)
+            r1 = w.run([g], 97, burn_in=5)
+            r2 = w.run([g], 40, keep_acc=True)
+            vals, grads = w.estimates()
+            out[planes] = (w.addresses(), np.array(r1.acc[:]), np.array(r2.acc[:]), vals, grads, w.steps_done())
+        a, b = out["1"], out["0"]
+        assert np.array_equal(a[0], b[0])
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and a[5] == b[5] == 142
