@@ -55,61 +55,6 @@ __device__ __forceinline__ void classify_planes(const uint32_t (&p)[NP][NWM], co
     }
 }
 
-// generic bonds on staged planes: st[(k*nwm + w) * STEP_BLOCK] = word w of plane k, then the big mask
-static __device__ __forceinline__ int staged_occupation(const uint32_t* st, int nwm, int np, int pos) {
-    const int w = pos >> 5, b = pos & 31;
-    int n = 0;
-    for (int k = 0; k < np; ++k) n |= (int)((st[(k * nwm + w) * STEP_BLOCK] >> b) & 1u) << k;
-    return n;
-}
-static __device__ __forceinline__ BigOut big_pass_planes(const uint32_t* st, int nwm, int np, int M, int N,
-                                                         const double* exptab, const double* sqrtab, int mode,
-                                                         double t) {
-    BigOut o;
-    o.S = o.E = o.ED = 0.0;
-    o.d = 0;
-    o.nocc = 0;
-    o.z = -1;
-    o.right = 1;
-    double acc = 0.0;
-    const uint32_t* bw = st + (size_t)np * nwm * STEP_BLOCK;
-    for (int i = 0; i < nwm; ++i) {
-        uint32_t m = bw[i * STEP_BLOCK];
-        while (m) {
-            const int z = 32 * i + (__ffs(m) - 1);
-            m &= m - 1;
-            const int L = staged_occupation(st, nwm, np, z);
-            const int R = staged_occupation(st, nwm, np, (z + 1 == M) ? 0 : z + 1);
-            const double rr = (L > 0) ? exptab[(R - L + 1) + N] : 0.0;
-            const double rl = (R > 0) ? exptab[(L - R + 1) + N] : 0.0;
-            if (mode == 0) {
-                const double er = sqrtab[L] * sqrtab[R + 1] * rr;
-                const double el = sqrtab[R] * sqrtab[L + 1] * rl;
-                o.S += rr;
-                o.S += rl;
-                o.E += er + el;
-                o.ED += er * (double)(R - L + 1) + el * (double)(L - R + 1);
-                o.nocc += (L > 0);
-                o.d += (long long)L * (L - 1) / 2;
-            } else {
-                if (rr > 0.0) {
-                    acc += rr;
-                    o.z = z;
-                    o.right = 1;
-                    if (t < acc) return o;
-                }
-                if (rl > 0.0) {
-                    acc += rl;
-                    o.z = z;
-                    o.right = 0;
-                    if (t < acc) return o;
-                }
-            }
-        }
-    }
-    return o;
-}
-
 template <int NWM, int NP>
 struct PlanesBig {
     const uint32_t (&p)[NP][NWM];
@@ -124,16 +69,63 @@ struct PlanesBig {
         for (int i = 0; i < NWM; ++i) a |= big[i];
         return a != 0u;
     }
+    // Register-only evaluation: the word index is static (unrolled), the bit index comes from ffs; the
+    // right neighbour's occupation is read from the ring-rotated planes at the same bit.
     __device__ __forceinline__ BigOut pass(int mode, double t) const {
-        if (mode == 0) {
+        uint32_t q[NP][NWM];
 #pragma unroll
-            for (int k = 0; k < NP; ++k)
+        for (int k = 0; k < NP; ++k) ring_next<NWM>(p[k], dm, q[k]);
+        BigOut o;
+        o.S = o.E = o.ED = 0.0;
+        o.d = 0;
+        o.nocc = 0;
+        o.z = -1;
+        o.right = 1;
+        double acc = 0.0;
+        bool done = false;
+        int dsum = 0;
+        const int N = dm.N;
 #pragma unroll
-                for (int i = 0; i < NWM; ++i) stage[(k * NWM + i) * STEP_BLOCK] = p[k][i];
+        for (int i = 0; i < NWM; ++i) {
+            uint32_t m = big[i];
+            while (m && !done) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                int L = 0, R = 0;
 #pragma unroll
-            for (int i = 0; i < NWM; ++i) stage[(NP * NWM + i) * STEP_BLOCK] = big[i];
+                for (int k = 0; k < NP; ++k) {
+                    L |= (int)((p[k][i] >> b) & 1u) << k;
+                    R |= (int)((q[k][i] >> b) & 1u) << k;
+                }
+                const double rr = (L > 0) ? exptab[(R - L + 1) + N] : 0.0;
+                const double rl = (R > 0) ? exptab[(L - R + 1) + N] : 0.0;
+                if (mode == 0) {
+                    const double er = sqrtab[L] * sqrtab[R + 1] * rr;
+                    const double el = sqrtab[R] * sqrtab[L + 1] * rl;
+                    o.S += rr;
+                    o.S += rl;
+                    o.E += er + el;
+                    o.ED += er * (double)(R - L + 1) + el * (double)(L - R + 1);
+                    o.nocc += (L > 0);
+                    dsum += L * (L - 1) / 2;  // N <= 250: fits easily
+                } else {
+                    if (rr > 0.0) {
+                        acc += rr;
+                        o.z = 32 * i + b;
+                        o.right = 1;
+                        if (t < acc) done = true;
+                    }
+                    if (!done && rl > 0.0) {
+                        acc += rl;
+                        o.z = 32 * i + b;
+                        o.right = 0;
+                        if (t < acc) done = true;
+                    }
+                }
+            }
         }
-        return big_pass_planes(stage, NWM, NP, dm.M, dm.N, exptab, sqrtab, mode, t);
+        o.d = dsum;
+        return o;
     }
 };
 
