@@ -98,7 +98,11 @@ struct gwz_walkers {
     double* d_partials = nullptr;
     int partials_cap = 0;
     double* d_vec = nullptr;  // NUM_ACC doubles: this set's reduced vector
-    double* d_shift = nullptr;  // (E_ref, G_ref): reference point of the shifted running sums
+    double* d_shift = nullptr;  // scratch for the reference-point kernel (first estimator only)
+    double* h_shift = nullptr;  // pinned
+    double shift_e = 0.0, shift_g = 0.0;  // (E_ref, G_ref): reference point of the current estimator's sums
+    double next_e = 0.0, next_g = 0.0;    // pooled (E, G) of the last run: reference point of the next estimator
+    bool have_next = false;
     // Where the walkers currently live: unary bitstrings (d_addr) or occupation bit-planes (d_planes).
     // The production kernel works on planes; everything that needs addresses converts back first.
     uint32_t* d_planes = nullptr;
@@ -569,7 +573,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     GWZ_CUDA(cudaMalloc(&w->d_acc, sizeof(double) * w->n * NUM_WALKER_ACC));
     GWZ_CUDA(cudaMalloc(&w->d_vec, sizeof(double) * NUM_ACC));
     GWZ_CUDA(cudaMalloc(&w->d_shift, sizeof(double) * 2));
-    GWZ_CUDA(cudaMemsetAsync(w->d_shift, 0, sizeof(double) * 2, c->stream));
+    GWZ_CUDA(cudaMallocHost(&w->h_shift, sizeof(double) * 2));
     DevBuf<uint64_t> d_start;
     GWZ_CUDA(d_start.alloc(m->W));
     GWZ_CUDA(cudaMemcpyAsync(d_start.p, start_addr, sizeof(uint64_t) * m->W, cudaMemcpyHostToDevice, c->stream));
@@ -587,6 +591,7 @@ extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
     cudaFree(w->d_partials);
     cudaFree(w->d_vec);
     cudaFree(w->d_shift);
+    cudaFreeHost(w->h_shift);
     cudaFree(w->d_planes);
     cudaFree(w->d_ref_addr);
     delete w;
@@ -673,7 +678,7 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.partials = w->d_partials;
     L.grid = grid;
     L.err_flag = c->d_err;
-    L.shift = w->d_shift;
+    L.shift_e = L.shift_g = 0.0;
     L.rec_tau = nullptr;
     L.rec_eloc = nullptr;
     L.rec_addr = nullptr;
@@ -695,16 +700,31 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         w->steps_done += burn_in;
     }
     const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
-    if (!keep) {  // new estimator: pick its reference point from where walker 0 is now
-        const uint64_t* ref = w->d_addr;
-        size_t stride = w->n;
-        if (planes) {
-            GWZ_LAUNCH(launch_planes_to_unary(w->d_planes, w->n, m->dm, 0, 1, w->d_ref_addr, c->stream));
-            ref = w->d_ref_addr;
-            stride = 1;
+    if (!keep) {
+        // New estimator: its reference point (any constant near the mean; it only limits cancellation in
+        // the covariance) is the pooled (E, G) of the previous run, or -- the first time -- E_loc and the
+        // grad ratio of walker 0's current address, evaluated by a one-thread kernel.
+        if (w->have_next) {
+            w->shift_e = w->next_e;
+            w->shift_g = w->next_g;
+        } else {
+            const uint64_t* ref = w->d_addr;
+            size_t stride = w->n;
+            if (planes) {
+                GWZ_LAUNCH(launch_planes_to_unary(w->d_planes, w->n, m->dm, 0, 1, w->d_ref_addr, c->stream));
+                ref = w->d_ref_addr;
+                stride = 1;
+            }
+            GWZ_LAUNCH(launch_walker_ref(m->dm, tb, m->nw, ref, stride, w->d_shift, c->stream));
+            GWZ_CUDA(cudaMemcpyAsync(w->h_shift, w->d_shift, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+            GWZ_CUDA(cudaStreamSynchronize(c->stream));
+            w->shift_e = w->h_shift[0];
+            w->shift_g = w->h_shift[1];
+            if (time_it) GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
         }
-        GWZ_LAUNCH(launch_walker_ref(m->dm, tb, m->nw, ref, stride, w->d_shift, c->stream));
     }
+    L.shift_e = w->shift_e;
+    L.shift_g = w->shift_g;
     L.step0 = w->steps_done;
     L.steps = steps;
     L.accumulate = 1;
@@ -766,9 +786,20 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
     for (gwz_context* c : ctxs) {
         if (int rc = use_device(c)) return rc;
         int rows = 0;
+        const gwz_walkers* only = nullptr;
         for (int i = 0; i < n; ++i)
             if (ws[i]->m->ctx == c) {
-                GWZ_REQUIRE(rows < GROUP_ROWS, "gwz_vqmc_run_group: too many walker sets on one device");
+                only = ws[i];
+                ++rows;
+            }
+        GWZ_REQUIRE(rows <= GROUP_ROWS, "gwz_vqmc_run_group: too many walker sets on one device");
+        if (rows == 1) {  // the usual case: no second reduction stage
+            GWZ_CUDA(cudaMemcpyAsync(c->d_acc, only->d_vec, sizeof(double) * NUM_ACC, cudaMemcpyDeviceToDevice, c->stream));
+            continue;
+        }
+        rows = 0;
+        for (int i = 0; i < n; ++i)
+            if (ws[i]->m->ctx == c) {
                 GWZ_CUDA(cudaMemcpyAsync(c->d_group + (size_t)rows * NUM_ACC, ws[i]->d_vec, sizeof(double) * NUM_ACC,
                                          cudaMemcpyDeviceToDevice, c->stream));
                 ++rows;
@@ -811,6 +842,15 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
         gwz_context* c0 = ws[0]->m->ctx;
         if (int rc = use_device(c0)) return rc;
         GWZ_CUDA(cudaEventElapsedTime(&ms, c0->ev0, c0->ev1));
+    }
+    {
+        // pooled means of this run seed the reference point of the next estimator of every set
+        const double* a = ctxs[0]->h_acc;
+        for (int i = 0; i < n; ++i) {
+            ws[i]->next_e = a[ACC_TE] / a[ACC_T];
+            ws[i]->next_g = a[ACC_TG] / a[ACC_T];
+            ws[i]->have_next = std::isfinite(ws[i]->next_e) && std::isfinite(ws[i]->next_g);
+        }
     }
     if (out) fill_result(ctxs[0]->h_acc, ms, flags, out);
     return GWZ_OK;
@@ -855,7 +895,7 @@ extern "C" int gwz_walkers_estimates(gwz_walkers* w, double* val_w, double* grad
     DevBuf<double> d_v, d_g;
     GWZ_CUDA(d_v.alloc(w->n));
     GWZ_CUDA(d_g.alloc(w->n));
-    GWZ_LAUNCH(launch_walker_estimates(w->d_acc, w->n, w->d_shift, d_v.p, d_g.p, c->stream));
+    GWZ_LAUNCH(launch_walker_estimates(w->d_acc, w->n, w->shift_e, d_v.p, d_g.p, c->stream));
     if (val_w) GWZ_CUDA(cudaMemcpyAsync(val_w, d_v.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
     if (grad_w) GWZ_CUDA(cudaMemcpyAsync(grad_w, d_g.p, sizeof(double) * w->n, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));

@@ -42,7 +42,7 @@ struct WalkerLaunch {
     uint64_t global_offset, seed, step0, steps;
     int accumulate;  // 0: burn-in (no estimator update, no reduction)
     int reset_acc;   // 1: clear the per-walker sums before the first step
-    const double* shift;  // device: (E_ref, G_ref) reference point of the shifted sums
+    double shift_e, shift_g;  // (E_ref, G_ref): reference point of the shifted running sums
     // optional per-step series [steps][n] (recording run)
     double* rec_tau;
     double* rec_eloc;
@@ -59,7 +59,7 @@ cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s);
 // out[ncomp] = sum over blocks of partials[block][ncomp], fixed order
 cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s);
 cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, const uint64_t* start_dev, cudaStream_t s);
-cudaError_t launch_walker_estimates(const double* acc, size_t n, const double* shift, double* val_w, double* grad_w,
+cudaError_t launch_walker_estimates(const double* acc, size_t n, double shift_e, double* val_w, double* grad_w,
                                     cudaStream_t s);
 // shift[0..1] = (E_loc, grad ratio) of walker 0's current address
 cudaError_t launch_walker_ref(const DevModel& dm, const DevTables& tb, int nw, const uint64_t* addr, size_t n,

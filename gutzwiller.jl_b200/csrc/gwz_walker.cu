@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(WALKER_BLOCK, KIND == 0 ? 1 : ((NW <= 4 ? GWZ_
 walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
               uint64_t* __restrict__ addr, double* __restrict__ acc, size_t n, uint64_t global_offset,
               uint64_t seed, uint64_t step0, uint64_t steps, int accumulate, int reset_acc,
-              const double* __restrict__ shift, double* __restrict__ rec_tau, double* __restrict__ rec_eloc,
+              double shift_e, double shift_g, double* __restrict__ rec_tau, double* __restrict__ rec_eloc,
               uint64_t* __restrict__ rec_addr, double* __restrict__ partials, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int KC = KIND ? KIND : 4;
@@ -46,7 +46,7 @@ walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTa
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     // common reference point of the running sums (any constant works; it only limits cancellation
     // in the covariance): E_loc and grad ratio of a representative address, see walker_ref_kernel
-    const double E0 = accumulate ? shift[0] : 0.0, G0 = accumulate ? shift[1] : 0.0;
+    const double E0 = accumulate ? shift_e : 0.0, G0 = accumulate ? shift_g : 0.0;
 
     // this thread's partial accumulator vector lives in shared memory (touched once per walker, not per
     // step) so that it does not occupy 24 registers across the step loop
@@ -199,14 +199,14 @@ __global__ void walker_init_kernel(uint64_t* __restrict__ addr, double* __restri
     for (int c = 0; c < NUM_WALKER_ACC; ++c) acc[(size_t)c * n + i] = 0.0;
 }
 
-__global__ void walker_estimates_kernel(const double* __restrict__ acc, size_t n, const double* __restrict__ shift,
+__global__ void walker_estimates_kernel(const double* __restrict__ acc, size_t n, double shift_e,
                                         double* __restrict__ val_w, double* __restrict__ grad_w) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double st = acc[0 * n + i], ste = acc[1 * n + i], stg = acc[2 * n + i], stge = acc[3 * n + i];
     const double inv = 1.0 / st;
     const double mE = ste * inv, mG = stg * inv;
-    val_w[i] = shift[0] + mE;
+    val_w[i] = shift_e + mE;
     grad_w[i] = 2.0 * (stge * inv - mE * mG);
 }
 
@@ -235,7 +235,7 @@ static cudaError_t launch_one(const WalkerLaunch& L, cudaStream_t s) {
     if (cudaError_t e = walker_prepare<NW, KIND, RECORD>(L.dm.N); e != cudaSuccess) return e;
     walker_kernel<NW, KIND, RECORD><<<L.grid, WALKER_BLOCK, walker_smem_bytes<NW, KIND>(L.dm.N), s>>>(
         L.dm, L.tb, L.addr, L.acc, L.n, L.global_offset, L.seed, L.step0, L.steps, L.accumulate, L.reset_acc,
-        L.shift, L.rec_tau, L.rec_eloc, L.rec_addr, L.partials, L.err_flag);
+        L.shift_e, L.shift_g, L.rec_tau, L.rec_eloc, L.rec_addr, L.partials, L.err_flag);
     return cudaGetLastError();
 }
 template <int NW>
@@ -320,9 +320,9 @@ cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, con
     walker_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(addr, acc, n, W, start_dev);
     return cudaGetLastError();
 }
-cudaError_t launch_walker_estimates(const double* acc, size_t n, const double* shift, double* val_w, double* grad_w,
+cudaError_t launch_walker_estimates(const double* acc, size_t n, double shift_e, double* val_w, double* grad_w,
                                     cudaStream_t s) {
-    walker_estimates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(acc, n, shift, val_w, grad_w);
+    walker_estimates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(acc, n, shift_e, val_w, grad_w);
     return cudaGetLastError();
 }
 cudaError_t launch_transpose_addr(const uint64_t* src, uint64_t* dst, size_t n, int W, bool to_soa, cudaStream_t s) {

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, NWM <= 2 ? 4 : 3)
 walker_planes_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
                      uint32_t* __restrict__ planes, double* __restrict__ acc, size_t n, uint64_t global_offset,
                      uint64_t seed, uint64_t step0, uint64_t steps, int accumulate, int reset_acc,
-                     const double* __restrict__ shift, double* __restrict__ partials, int* __restrict__ err_flag) {
+                     double shift_e, double shift_g, double* __restrict__ partials, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StepScratch<NWM, 4> sc(smem_raw, dm.N);
     sc.fill_exptab(dm.N, tb.c);
@@ -31,7 +31,7 @@ walker_planes_kernel(const __grid_constant__ DevModel dm, const __grid_constant_
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const double E0 = accumulate ? shift[0] : 0.0, G0 = accumulate ? shift[1] : 0.0;
+    const double E0 = accumulate ? shift_e : 0.0, G0 = accumulate ? shift_g : 0.0;
 #pragma unroll
     for (int i = 0; i < NUM_ACC; ++i) p[i * STEP_BLOCK] = 0.0;
     bool bad = false;
@@ -187,7 +187,7 @@ template <int NWM, int NP>
 static cudaError_t planes_launch(const WalkerLaunch& L, cudaStream_t s) {
     if (cudaError_t e = planes_prepare<NWM, NP>(L.dm.N)) return e;
     walker_planes_kernel<NWM, NP><<<L.grid, STEP_BLOCK, planes_smem_bytes<NWM, NP>(L.dm.N), s>>>(
-        L.dm, L.tb, L.planes, L.acc, L.n, L.global_offset, L.seed, L.step0, L.steps, L.accumulate, L.reset_acc, L.shift,
+        L.dm, L.tb, L.planes, L.acc, L.n, L.global_offset, L.seed, L.step0, L.steps, L.accumulate, L.reset_acc, L.shift_e, L.shift_g,
         L.partials, L.err_flag);
     return cudaGetLastError();
 }
