@@ -140,8 +140,12 @@ __device__ __forceinline__ int nth_set_bit32(uint32_t x, int j) {
     return pos;
 }
 __device__ __forceinline__ double int_to_double_fast(int c) {
+#ifdef GWZ_I2F_CONVERT
+    return (double)c;  // I2F.F64.S32 on the XU pipe
+#else
     // exact for 0 <= c < 2^31: one DADD instead of an XU-pipe I2F.F64
     return __hiloint2double(0x43300000, c) - 4503599627370496.0;
+#endif
 }
 
 // load a stored address (W 64-bit words, word-major SoA: words[w*stride + idx]) into NW regs

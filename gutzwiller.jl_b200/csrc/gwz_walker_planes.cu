@@ -5,11 +5,15 @@
 #include "gwz_internal.h"
 #include "gwz_planes.cuh"
 
+#ifndef GWZ_PLANES_MIN_BLOCKS
+#define GWZ_PLANES_MIN_BLOCKS 4
+#endif
+
 namespace gwz {
 
 template <int NWM, int NP>
 __host__ __device__ constexpr size_t planes_stage_bytes() {
-    return sizeof(uint32_t) * (size_t)(NP + 1) * NWM * STEP_BLOCK;
+    return 0;  // the generic-bond path of the plane representation works from registers
 }
 template <int NWM, int NP>
 __host__ __device__ constexpr size_t planes_smem_bytes(int N) {
@@ -17,7 +21,7 @@ __host__ __device__ constexpr size_t planes_smem_bytes(int N) {
 }
 
 template <int NWM, int NP>
-__global__ void __launch_bounds__(STEP_BLOCK, NWM <= 2 ? 4 : 3)
+__global__ void __launch_bounds__(STEP_BLOCK, NWM == 1 ? 5 : (NWM == 2 ? GWZ_PLANES_MIN_BLOCKS : 3))
 walker_planes_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
                      uint32_t* __restrict__ planes, double* __restrict__ acc, size_t n, uint64_t global_offset,
                      uint64_t seed, uint64_t step0, uint64_t steps, int accumulate, int reset_acc,
