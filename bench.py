@@ -202,8 +202,11 @@ def run_ours(args):
     e2e = total_steps / (e2e_ms * 1e-3)
     local_walkers = wh.n
     W = wh.model.words
-    # algorithmic HBM bytes of one walker-kernel launch: address + 7 running sums, loaded and stored once
-    alg_bytes = local_walkers * (2 * 8 * W + 2 * 8 * 7)
+    # algorithmic HBM bytes of one walker-kernel launch: the resident walker state (occupation bit-planes:
+    # NP planes x ceil(M/32) words) and the 5 running sums, loaded and stored once per launch
+    n_planes = 4 if N_PART <= 15 else (6 if N_PART <= 63 else 8)
+    state_bytes = 4 * n_planes * ((N_MODES + 31) // 32)
+    alg_bytes = local_walkers * (2 * state_bytes + 2 * 8 * 5)
     hbm_peak, peak_src = _peaks()
     hbm_ach = alg_bytes / (kavg * 1e-3) / 1e9
     hops_per_step = hops / total_steps
@@ -230,7 +233,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "walkers_per_gpu": local_walkers, "steps_per_call": STEPS_PER_CALL,
-                   "kernel": "bit-parallel bond classes (GWZ_KERNEL_BITPARALLEL)", "parallelism": f"walker-shard x{args.gpus}",
+                   "kernel": "walker_planes_kernel: occupation bit-planes, bit-parallel bond classes (GWZ_KERNEL_BITPARALLEL)", "parallelism": f"walker-shard x{args.gpus}",
                    "l2": f"walker state {alg_bytes / 2 / 2**20:.0f} MiB per GPU > 126 MB L2 (inputs larger than L2)"
                    if alg_bytes / 2 > 126e6 else "walker state fits in L2; kernel is register-resident (not HBM bound)"},
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": 8 + 1040, "d2h_bytes_per_step": 8 * 12 + 4,
