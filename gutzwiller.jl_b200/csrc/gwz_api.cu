@@ -114,6 +114,12 @@ static bool planes_enabled() {
     const char* e = std::getenv("GWZ_PLANES");
     return !(e && e[0] == '0');
 }
+// GWZ_INCR=0 falls back from the incremental class-count kernel to the full re-count per step
+// (same plane format, bitwise identical results; kept for A/B measurements and cross-checks)
+static bool incr_enabled() {
+    const char* e = std::getenv("GWZ_INCR");
+    return !(e && e[0] == '0');
+}
 
 // make d_addr (unary) the valid copy
 static int to_unary(gwz_walkers* w) {
@@ -661,7 +667,9 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     const bool planes = (kind == GWZ_KERNEL_BITPARALLEL) && !record && tb.kc == 4 && planes_enabled();
     if (int rc = planes ? to_planes(w) : to_unary(w)) return rc;
     int grid = 0;
-    if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+    const bool incr = planes && incr_enabled() && walker_incr_supported(m->N, m->M);
+    if (incr) GWZ_CUDA(walker_incr_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+    else if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
     else GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
     if (int rc = ensure_partials(w, grid)) return rc;
     WalkerLaunch L;
@@ -688,7 +696,9 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         L.steps = burn_in;
         L.accumulate = 0;
         L.reset_acc = 0;
-        if (planes) {
+        if (incr) {
+            GWZ_LAUNCH(launch_walkers_incr(L, c->stream));
+        } else if (planes) {
             GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
         } else {
             int g2 = 0;
@@ -732,7 +742,8 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.rec_tau = rec_tau;
     L.rec_eloc = rec_eloc;
     L.rec_addr = rec_addr;
-    if (planes) GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
+    if (incr) GWZ_LAUNCH(launch_walkers_incr(L, c->stream));
+    else if (planes) GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
     else GWZ_LAUNCH(launch_walkers(L, c->stream));
     if (time_it) GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
     w->steps_done += steps;

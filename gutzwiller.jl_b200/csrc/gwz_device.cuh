@@ -576,6 +576,33 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// same generator with the ten round keys precomputed on the host (kernel-argument constant bank):
+// removes the key schedule from the step loop
+struct PhiloxKeys {
+    uint32_t k[20];  // k[2r], k[2r+1] = round-r keys
+};
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys pk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        pk.k[2 * r] = k0;
+        pk.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return pk;
+}
+__device__ __forceinline__ void philox4x32_10_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    const PhiloxKeys& pk, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ pk.k[2 * r], n2 = hi0 ^ c3 ^ pk.k[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
 __device__ __forceinline__ double u01_from_words(uint32_t lo, uint32_t hi) {
     const uint64_t r = ((uint64_t)hi << 32) | lo;
     return (double)(r >> 11) * 0x1.0p-53;

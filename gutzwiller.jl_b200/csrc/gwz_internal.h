@@ -68,6 +68,10 @@ cudaError_t launch_walker_ref(const DevModel& dm, const DevTables& tb, int nw, c
 void planes_shape(int N, int M, int* nwm, int* np);
 cudaError_t walker_planes_grid(int N, int M, size_t n, int sm_count, int* grid);
 cudaError_t launch_walkers_planes(const WalkerLaunch& L, cudaStream_t s);
+// incremental class-count path on the same plane format (gwz_walker_incr.cu)
+bool walker_incr_supported(int N, int M);
+cudaError_t walker_incr_grid(int N, int M, size_t n, int sm_count, int* grid);
+cudaError_t launch_walkers_incr(const WalkerLaunch& L, cudaStream_t s);
 cudaError_t launch_unary_to_planes(const uint64_t* addr, size_t n, const DevModel& dm, uint32_t* planes, cudaStream_t s);
 // walkers first..first+count-1 -> unary SoA addr[W][count]
 cudaError_t launch_planes_to_unary(const uint32_t* planes, size_t n, const DevModel& dm, size_t first, size_t count,

@@ -129,14 +129,28 @@ struct PlanesBig {
     }
 };
 
+// the single bit `pos` as a register array
+template <int NWM>
+__device__ __forceinline__ void bit_words(int pos, uint32_t (&c)[NWM]) {
+    if (NWM == 1) {
+        c[0] = 1u << pos;
+    } else if (NWM == 2) {
+        const unsigned long long m = 1ull << pos;
+        c[0] = (uint32_t)m;
+        c[NWM - 1] = (uint32_t)(m >> 32);
+    } else {
+        const int w = pos >> 5;
+        const uint32_t b = 1u << (pos & 31);
+#pragma unroll
+        for (int i = 0; i < NWM; ++i) c[i] = (i == w) ? b : 0u;
+    }
+}
+
 // n_pos += 1 / -= 1 by a bit-sliced ripple; the carry rarely travels beyond plane 1
 template <int NWM, int NP>
 __device__ __forceinline__ void planes_inc(uint32_t (&p)[NP][NWM], int pos) {
     uint32_t c[NWM];
-    const int w = pos >> 5;
-    const uint32_t b = 1u << (pos & 31);
-#pragma unroll
-    for (int i = 0; i < NWM; ++i) c[i] = (i == w) ? b : 0u;
+    bit_words<NWM>(pos, c);
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         if (k >= 2) {
@@ -156,10 +170,7 @@ __device__ __forceinline__ void planes_inc(uint32_t (&p)[NP][NWM], int pos) {
 template <int NWM, int NP>
 __device__ __forceinline__ void planes_dec(uint32_t (&p)[NP][NWM], int pos) {
     uint32_t c[NWM];
-    const int w = pos >> 5;
-    const uint32_t b = 1u << (pos & 31);
-#pragma unroll
-    for (int i = 0; i < NWM; ++i) c[i] = (i == w) ? b : 0u;
+    bit_words<NWM>(pos, c);
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         if (k >= 2) {
