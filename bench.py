@@ -206,7 +206,8 @@ def run_ours(args):
     # NP planes x ceil(M/32) words) and the 5 running sums, loaded and stored once per launch
     n_planes = 4 if N_PART <= 15 else (6 if N_PART <= 63 else 8)
     state_bytes = 4 * n_planes * ((N_MODES + 31) // 32)
-    alg_bytes = local_walkers * (2 * state_bytes + 2 * 8 * 5)
+    # (val_and_grad(qmc, p) starts a new estimator, so the sums are written but not read)
+    alg_bytes = local_walkers * (2 * state_bytes + 8 * 5)
     hbm_peak, peak_src = _peaks()
     hbm_ach = alg_bytes / (kavg * 1e-3) / 1e9
     hops_per_step = hops / total_steps
@@ -233,7 +234,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "walkers_per_gpu": local_walkers, "steps_per_call": STEPS_PER_CALL,
-                   "kernel": "walker_planes_kernel: occupation bit-planes, bit-parallel bond classes (GWZ_KERNEL_BITPARALLEL)", "parallelism": f"walker-shard x{args.gpus}",
+                   "kernel": "walker_incr_kernel: occupation bit-planes + incremental bond-class counts (GWZ_KERNEL_BITPARALLEL)", "parallelism": f"walker-shard x{args.gpus}",
                    "l2": f"walker state {alg_bytes / 2 / 2**20:.0f} MiB per GPU > 126 MB L2 (inputs larger than L2)"
                    if alg_bytes / 2 > 126e6 else "walker state fits in L2; kernel is register-resident (not HBM bound)"},
         "e2e": {"value": e2e, "unit": "walker-steps/s", "h2d_bytes_per_step": 8 + 1040, "d2h_bytes_per_step": 8 * 12 + 4,
@@ -241,7 +242,7 @@ def run_ours(args):
                         "kernel-argument tables, outputs the 12-double accumulator vector"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": _dram_traffic(local_walkers), "peak_source": peak_src,
                      "note": "walker kernel keeps its state in registers: HBM traffic is one load+store of the walker "
                              "state per launch; the binding limit is instruction issue, see issue_roofline"},
         "issue_roofline": issue,
@@ -255,6 +256,16 @@ def run_ours(args):
     if args.extra:
         line["extra"] = extra_workloads(gw, np)
     print(json.dumps(line), flush=True)
+
+
+def _dram_traffic(walkers):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one walker-kernel launch, from the committed ncu --set full
+    capture (taken on 2^22 walkers of the same shape), scaled to this launch's walker count."""
+    p = os.path.join(ROOT, "profiles", "walker_inst_per_step.json")
+    try:
+        return float(json.load(open(p))[f"dram_bytes_per_walker_N{N_PART}M{N_MODES}"]) * walkers
+    except Exception:
+        return None
 
 
 def _inst_per_walker_step():

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgutzwiller_b200.so")
+# GWZ_LIB_PATH: developer override (kernel variants built side by side for A/B timing)
+LIB_PATH = os.environ.get("GWZ_LIB_PATH") or os.path.join(_HERE, "lib", "libgutzwiller_b200.so")
 
 MAX_WORDS = 4
 NUM_PARAMS = 1
