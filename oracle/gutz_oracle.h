@@ -145,6 +145,38 @@ typedef struct {
 int go_lee_objective_val_and_grad(void *user, const double *p, int np, double *val, double *err,
                                   double *grad);
 
+/* ---- part 2 (gutz_oracle_ansatz.c): the other single-component ansaetze, generic in P -------- */
+enum go_ansatz_kind {
+    GO_ANSATZ_GUTZWILLER = 0,       /* src/ansatz/gutzwiller.jl */
+    GO_ANSATZ_EXT_GUTZWILLER = 1,   /* src/ansatz/extgutzwiller.jl (call operator) */
+    GO_ANSATZ_MULTINOMIAL = 2,      /* src/ansatz/multinomial.jl */
+    GO_ANSATZ_DENSITY_PROFILE = 3,  /* src/ansatz/densityprofile.jl */
+    GO_ANSATZ_RELATIVE_JASTROW = 4, /* src/ansatz/jastrow.jl:60-103 */
+    GO_ANSATZ_JASTROW = 5           /* src/ansatz/jastrow.jl:4-58 */
+};
+typedef struct {
+    go_model m;
+    double v;             /* ExtendedHubbardReal1D nearest-neighbour interaction (0: HubbardReal1D) */
+    int kind, P;          /* ansatz kind, num_parameters */
+    double normalization; /* MultinomialAnsatz(H; normalize) */
+} go_ansatz;
+int go_ansatz_init(go_ansatz *a, const go_model *m, double v, int kind, int normalize);
+double go_gen_diagonal(const go_ansatz *a, const go_addr *addr);
+/* grad (P doubles) may be NULL: the ansatz call operator */
+void go_gen_val_and_grad(const go_ansatz *a, const go_addr *addr, const double *params, double *val, double *grad);
+int go_gen_kinetic_sample(const go_ansatz *a, const double *params, const go_addr *a1, double u01,
+                          double *prob_buffer, go_addr *new_addr, double *residence_time, double *local_energy,
+                          double *grad_ratio, int *chosen, int *n_hops);
+int go_gen_hop_rates(const go_ansatz *a, const double *params, const go_addr *a1, double *rates);
+/* out = (num, den, num_grad[P], den_grad[P]) */
+void go_gen_lee_terms(const go_ansatz *a, const go_addr *k, const double *params, double *out);
+void go_gen_lee_val_and_grad(const go_ansatz *a, const go_addr *basis, int64_t dim, const double *params,
+                             double *val, double *grad);
+int go_gen_kinetic_vqmc(const go_ansatz *a, const double *params, go_addr *addrs, int64_t n_walkers, int64_t steps,
+                        uint64_t seed, uint64_t walker0, uint64_t step0, int n_threads, double *series_tau,
+                        double *series_eloc, go_addr *series_addr, double *val_w, double *grad_w,
+                        int64_t *total_hops);
+
 #ifdef __cplusplus
 }
 #endif

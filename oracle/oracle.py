@@ -17,7 +17,7 @@ MAXW = 4
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("gutz_oracle.c", "gutz_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("gutz_oracle.c", "gutz_oracle_ansatz.c", "gutz_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -49,6 +49,14 @@ class GdOpts(C.Structure):
                 ("param_tol", C.c_double), ("val_tol", C.c_double), ("err_tol", C.c_double),
                 ("first_moment_init", C.POINTER(C.c_double)), ("second_moment_init", C.POINTER(C.c_double)),
                 ("fix_params", C.POINTER(C.c_uint8))]
+
+
+class Ansatz(C.Structure):
+    _fields_ = [("m", Model), ("v", C.c_double), ("kind", C.c_int), ("P", C.c_int), ("normalization", C.c_double)]
+
+
+ANSATZ_KINDS = {"gutzwiller": 0, "ext_gutzwiller": 1, "multinomial": 2, "density_profile": 3,
+                "relative_jastrow": 4, "jastrow": 5}
 
 
 class LeeObjective(C.Structure):
@@ -101,6 +109,18 @@ def lib():
         L.go_adaptive_gradient_descent.argtypes = [OBJECTIVE, OBJECTIVE, C.c_void_p, dp, C.c_int,
                                                    C.POINTER(GdOpts), dp, dp, dp, dp, dp, dp, dp, ip, ip]
         L.go_lee_objective_val_and_grad.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp]
+        anp = C.POINTER(Ansatz)
+        L.go_ansatz_init.argtypes = [anp, mp, C.c_double, C.c_int, C.c_int]
+        L.go_gen_diagonal.argtypes = [anp, ap]
+        L.go_gen_diagonal.restype = C.c_double
+        L.go_gen_val_and_grad.argtypes = [anp, ap, C.c_void_p, dp, C.c_void_p]
+        L.go_gen_kinetic_sample.argtypes = [anp, C.c_void_p, ap, C.c_double, C.c_void_p, ap, dp, dp, C.c_void_p, ip, ip]
+        L.go_gen_hop_rates.argtypes = [anp, C.c_void_p, ap, C.c_void_p]
+        L.go_gen_lee_terms.argtypes = [anp, ap, C.c_void_p, C.c_void_p]
+        L.go_gen_lee_val_and_grad.argtypes = [anp, C.c_void_p, C.c_int64, C.c_void_p, dp, C.c_void_p]
+        L.go_gen_kinetic_vqmc.argtypes = [anp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
+                                          C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -299,3 +319,78 @@ class Oracle:
         r = BlockingResult()
         self.L.go_blocking_analysis(_vp(v), len(v), 0.01, C.byref(r))
         return r
+
+
+class AnsatzOracle:
+    """(Extended)HubbardReal1D + one of the reference's single-component ansaetze, CPU restatement
+    (oracle/gutz_oracle_ansatz.c).  `base` is an Oracle (model + address helpers)."""
+
+    def __init__(self, base: Oracle, kind: str, v: float = 0.0, normalize: bool = False):
+        self.base, self.L = base, base.L
+        self.a = Ansatz()
+        if self.L.go_ansatz_init(C.byref(self.a), C.byref(base.m), v, ANSATZ_KINDS[kind], int(normalize)):
+            raise ValueError(f"unknown ansatz kind {kind}")
+        self.kind, self.v, self.P, self.M = kind, v, self.a.P, base.M
+
+    def _p(self, params) -> np.ndarray:
+        p = np.ascontiguousarray(np.atleast_1d(params), dtype=np.float64)
+        if p.shape != (self.P,):
+            raise ValueError(f"expected {self.P} parameters")
+        return p
+
+    def diagonal_element(self, words) -> float:
+        a = self.base._addr(words)
+        return self.L.go_gen_diagonal(C.byref(self.a), C.byref(a))
+
+    def val(self, words, params) -> float:
+        a, p, v = self.base._addr(words), self._p(params), C.c_double()
+        self.L.go_gen_val_and_grad(C.byref(self.a), C.byref(a), _vp(p), C.byref(v), None)
+        return v.value
+
+    def val_and_grad(self, words, params):
+        a, p, v, g = self.base._addr(words), self._p(params), C.c_double(), np.zeros(self.P)
+        self.L.go_gen_val_and_grad(C.byref(self.a), C.byref(a), _vp(p), C.byref(v), _vp(g))
+        return v.value, g
+
+    def kinetic_sample(self, words, params, u01: float):
+        a, new, p = self.base._addr(words), Addr(), self._p(params)
+        buf, gr = np.zeros(2 * self.M), np.zeros(self.P)
+        tau, el, ch, nh = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        rc = self.L.go_gen_kinetic_sample(C.byref(self.a), _vp(p), C.byref(a), u01, _vp(buf), C.byref(new),
+                                          C.byref(tau), C.byref(el), _vp(gr), C.byref(ch), C.byref(nh))
+        if rc:
+            raise FloatingPointError("Infinite residence time")
+        return dict(new_addr=self.base._words(new), tau=tau.value, eloc=el.value, grad=gr, chosen=ch.value,
+                    n_hops=nh.value, cumsum=buf[:nh.value].copy())
+
+    def hop_rates(self, words, params) -> np.ndarray:
+        a, p, r = self.base._addr(words), self._p(params), np.zeros(2 * self.M)
+        h = self.L.go_gen_hop_rates(C.byref(self.a), _vp(p), C.byref(a), _vp(r))
+        return r[:h].copy()
+
+    def lee_terms(self, words, params) -> np.ndarray:
+        a, p, out = self.base._addr(words), self._p(params), np.zeros(2 + 2 * self.P)
+        self.L.go_gen_lee_terms(C.byref(self.a), C.byref(a), _vp(p), _vp(out))
+        return out
+
+    def lee_val_and_grad(self, basis: np.ndarray, params):
+        basis, p = np.ascontiguousarray(basis, dtype=np.uint64), self._p(params)
+        v, g = C.c_double(), np.zeros(self.P)
+        self.L.go_gen_lee_val_and_grad(C.byref(self.a), _vp(basis), basis.shape[0], _vp(p), C.byref(v), _vp(g))
+        return v.value, g
+
+    def kinetic_vqmc(self, params, addrs: np.ndarray, steps: int, seed: int = 0, walker0: int = 0, step0: int = 0,
+                     n_threads: int = 0, series: bool = False):
+        addrs, p = np.ascontiguousarray(addrs, dtype=np.uint64), self._p(params)
+        nw = addrs.shape[0]
+        val_w, grad_w, hops = np.zeros(nw), np.zeros((nw, self.P)), C.c_int64()
+        st = np.zeros((nw, steps)) if series else None
+        se = np.zeros((nw, steps)) if series else None
+        sa = np.zeros((nw, steps, MAXW), dtype=np.uint64) if series else None
+        rc = self.L.go_gen_kinetic_vqmc(C.byref(self.a), _vp(p), _vp(addrs), nw, steps, seed, walker0, step0,
+                                        n_threads, _vp(st) if series else None, _vp(se) if series else None,
+                                        _vp(sa) if series else None, _vp(val_w), _vp(grad_w), C.byref(hops))
+        if rc:
+            raise FloatingPointError("Infinite residence time")
+        return dict(addrs=addrs, val_w=val_w, grad_w=grad_w, val=val_w.mean(), grad=grad_w.mean(axis=0),
+                    hops=hops.value, series_tau=st, series_eloc=se, series_addr=sa)
