@@ -38,6 +38,16 @@ class VqmcResult(C.Structure):
                 ("hops", C.c_uint64), ("acc", C.c_double * NUM_ACC), ("kernel_ms", C.c_float)]
 
 
+class GenResult(C.Structure):
+    _fields_ = [("val", C.c_double), ("err", C.c_double), ("pooled_val", C.c_double), ("pooled_var", C.c_double),
+                ("total_time", C.c_double), ("walkers", C.c_uint64), ("steps", C.c_uint64), ("hops", C.c_uint64),
+                ("kernel_ms", C.c_float), ("np", C.c_int32)]
+
+
+ANSATZ_GUTZWILLER, ANSATZ_EXT_GUTZWILLER, ANSATZ_MULTINOMIAL, ANSATZ_DENSITY_PROFILE, ANSATZ_RELATIVE_JASTROW, \
+    ANSATZ_JASTROW = range(6)
+
+
 class BlockingResult(C.Structure):
     _fields_ = [("mean", C.c_double), ("err", C.c_double), ("err_err", C.c_double), ("p_cov", C.c_double),
                 ("k", C.c_int32), ("blocks", C.c_int64)]
@@ -117,6 +127,32 @@ SIGNATURES = {
                                                 C.POINTER(GdTrace)]),
     "gwz_amsgrad_vqmc": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.c_uint64, C.c_int, C.c_uint, C.POINTER(GdTrace)]),
     "gwz_amsgrad_sweep": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.POINTER(GdTrace)]),
+    # ---- ansatz-generic engine ----
+    "gwz_model_create_ext_hubbard1d": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                                 C.POINTER(_vp)]),
+    "gwz_model_info_ext": (C.c_int, [_vp, _dp]),
+    "gwz_ansatz_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "gwz_ansatz_destroy": (C.c_int, [_vp]),
+    "gwz_ansatz_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gwz_gen_ansatz_eval": (C.c_int, [_vp, _vp, C.c_size_t, _dp, _vp, _vp]),
+    "gwz_gen_probe_addresses": (C.c_int, [_vp, _vp, C.c_size_t, _dp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gwz_gwalkers_create": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _u64p, C.c_uint64, C.POINTER(_vp)]),
+    "gwz_gwalkers_destroy": (C.c_int, [_vp]),
+    "gwz_gwalkers_count": (C.c_int, [_vp, _u64p, _u64p]),
+    "gwz_gwalkers_get_addresses": (C.c_int, [_vp, _vp]),
+    "gwz_gwalkers_set_addresses": (C.c_int, [_vp, _vp]),
+    "gwz_gwalkers_set_step_counter": (C.c_int, [_vp, C.c_uint64]),
+    "gwz_gen_vqmc_run": (C.c_int, [_vp, _dp, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(GenResult), _vp, _vp, _vp]),
+    "gwz_gen_vqmc_run_record": (C.c_int, [_vp, _dp, C.c_uint64, C.c_uint, _vp, _vp, _vp, C.POINTER(GenResult), _vp,
+                                          _vp, _vp]),
+    "gwz_gwalkers_estimates": (C.c_int, [_vp, _vp, _vp]),
+    "gwz_gsweep_create": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
+    "gwz_gsweep_destroy": (C.c_int, [_vp]),
+    "gwz_gsweep_dim": (C.c_int, [_vp, _u64p]),
+    "gwz_gsweep_val_and_grad": (C.c_int, [_vp, _dp, _dp, _vp]),
+    "gwz_gsweep_terms": (C.c_int, [_vp, _dp, C.c_uint64, C.c_uint64, _vp]),
+    "gwz_gsweep_states": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "gwz_gsweep_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
 }
 
 _lib = None

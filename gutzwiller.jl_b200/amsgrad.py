@@ -121,11 +121,12 @@ def adaptive_gradient_descent(use_amsgrad: bool, f, params, *, maxiter=100, verb
         setattr(tr, k, a.ctypes.data_as(C.POINTER(C.c_double)))
     p0c = p0.ctypes.data_as(C.POINTER(C.c_double))
 
-    if isinstance(f, KineticVQMC) and not fkwargs and not f.result.record and n == 1:
+    generic = bool(getattr(getattr(f, 'ansatz', None), 'generic', False))
+    if isinstance(f, KineticVQMC) and not fkwargs and not f.result.record and n == 1 and not generic:
         check(lib().gwz_amsgrad_vqmc(f.result.walkers_handle.handle, p0c, C.byref(o), f.steps, f.result.kernel,
                                      _capi.RUN_POOLED if f.result.estimator == "pooled" else 0, C.byref(tr)))
         f.result.steps = f.steps
-    elif isinstance(f, LocalEnergyEvaluator) and not fkwargs and n == 1:
+    elif isinstance(f, LocalEnergyEvaluator) and not fkwargs and n == 1 and not generic:
         check(lib().gwz_amsgrad_sweep(f.handle, p0c, C.byref(o), C.byref(tr)))
     else:
         errors = []

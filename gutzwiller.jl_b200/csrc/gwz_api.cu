@@ -14,43 +14,23 @@
 #include <string>
 #include <vector>
 
-#include "gwz_internal.h"
-#include "gwz_nccl.h"
+#include "gwz_handles.h"
 
 using namespace gwz;
 
 // ------------------------------------------------------------------------------------------
-// errors
+// errors, launch counter (shared with gwz_api_generic.cu through gwz_handles.h)
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
-static int fail(int code, const std::string& msg) {
+int gwz::api_fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
-#define GWZ_CUDA(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t _e = (expr);                                                                    \
-        if (_e != cudaSuccess)                                                                      \
-            return fail(GWZ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
-    } while (0)
-#define GWZ_NCCL(api, expr)                                                                         \
-    do {                                                                                            \
-        int _r = (expr);                                                                            \
-        if (_r != kNcclSuccess)                                                                     \
-            return fail(GWZ_ERR_NCCL, std::string(#expr) + ": " + (api)->GetErrorString(_r));       \
-    } while (0)
-#define GWZ_REQUIRE(cond, msg)                                   \
-    do {                                                         \
-        if (!(cond)) return fail(GWZ_ERR_INVALID, (msg));        \
-    } while (0)
+static int fail(int code, const std::string& msg) { return gwz::api_fail(code, msg); }
 
 // number of kernels this library has launched (every launch goes through GWZ_LAUNCH)
 static std::atomic<uint64_t> g_launches{0};
-#define GWZ_LAUNCH(expr)   \
-    do {                   \
-        g_launches.fetch_add(1, std::memory_order_relaxed); \
-        GWZ_CUDA(expr);    \
-    } while (0)
+void gwz::api_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" int gwz_launch_count(uint64_t* n) {
     if (!n) return fail(GWZ_ERR_INVALID, "gwz_launch_count: NULL argument");
     *n = g_launches.load(std::memory_order_relaxed);
@@ -59,33 +39,6 @@ extern "C" int gwz_launch_count(uint64_t* n) {
 
 extern "C" const char* gwz_last_error(void) { return g_last_error.c_str(); }
 extern "C" int gwz_version(void) { return GWZ_VERSION; }
-
-// ------------------------------------------------------------------------------------------
-// handles
-// ------------------------------------------------------------------------------------------
-constexpr int GROUP_ROWS = 64;
-
-struct gwz_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaDeviceProp prop{};
-    int clock_khz = 0;
-    ncclComm_t comm = nullptr;
-    int world = 1, rank = 0;
-    double* d_acc = nullptr;    // NUM_ACC doubles: send/recv buffer of the all-reduce
-    double* d_group = nullptr;  // GROUP_ROWS x NUM_ACC scratch
-    double* h_acc = nullptr;    // pinned
-    int* d_err = nullptr;
-    int* h_err = nullptr;  // pinned
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
-
-struct gwz_model {
-    gwz_context* ctx;
-    int N, M, B, W, nw;
-    double u, t;
-    DevModel dm;
-};
 
 struct gwz_walkers {
     gwz_model* m;
@@ -155,10 +108,6 @@ struct gwz_sweep {
     float last_ms = 0.f;
 };
 
-static int use_device(const gwz_context* ctx) {
-    GWZ_CUDA(cudaSetDevice(ctx->device));
-    return GWZ_OK;
-}
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -379,7 +328,7 @@ extern "C" int gwz_model_near_uniform(const gwz_model* m, uint64_t* a) {
     for (int i = 0; i < m->M; ++i) onr[i] = ff + (i < extras ? 1 : 0);
     return gwz_model_from_onr(m, onr.data(), a);
 }
-static void binomial_table(std::vector<uint64_t>& tab) {
+void gwz::binomial_table(std::vector<uint64_t>& tab) {
     tab.assign(65 * 65, 0);
     for (int n = 0; n <= 64; ++n) {
         tab[n * 65 + 0] = 1;
@@ -445,7 +394,7 @@ static void make_tables(const gwz_model* m, double g, int kc, DevTables* tb) {
         }
 }
 
-static int check_err_flag(gwz_context* c) {
+int gwz::api_check_err_flag(gwz_context* c) {
     // caller has synchronised the stream after copying d_err -> h_err
     if (*c->h_err) {
         *c->h_err = 0;
@@ -455,24 +404,18 @@ static int check_err_flag(gwz_context* c) {
     }
     return GWZ_OK;
 }
+static int check_err_flag(gwz_context* c) { return gwz::api_check_err_flag(c); }
 
 // ------------------------------------------------------------------------------------------
 // probe
 // ------------------------------------------------------------------------------------------
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
-};
 
 extern "C" int gwz_probe_addresses(gwz_model* m, const uint64_t* addr_words, size_t n, const double* params,
                                    const double* u01, int kernel_kind, double* e_loc, double* residence_time,
                                    double* grad_ratio, int32_t* n_hops, double* rates, int32_t* chosen,
                                    uint64_t* next_addr) {
     GWZ_REQUIRE(m && params, "gwz_probe_addresses: NULL argument");
+    GWZ_REQUIRE(m->v == 0.0, "gwz_probe_addresses: ExtendedHubbardReal1D models need the gwz_gen_* entry points");
     GWZ_REQUIRE(n == 0 || addr_words, "gwz_probe_addresses: addr_words is NULL");
     GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
                 "gwz_probe_addresses: unknown kernel_kind");
@@ -555,6 +498,7 @@ extern "C" int gwz_ansatz_val_and_grad(gwz_model* m, const uint64_t* addr_words,
 extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t global_offset, const uint64_t* start_addr,
                                   uint64_t seed, gwz_walkers** out) {
     GWZ_REQUIRE(m && start_addr && out, "gwz_walkers_create: NULL argument");
+    GWZ_REQUIRE(m->v == 0.0, "gwz_walkers_create: ExtendedHubbardReal1D models need the gwz_gen_* entry points");
     GWZ_REQUIRE(n_walkers >= 1, "gwz_walkers_create: need at least one walker");
     // validate the start address: exactly N ones within B bits
     {
@@ -945,6 +889,7 @@ extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_
 extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint64_t dim, uint64_t rank_begin,
                                 uint64_t rank_end, gwz_sweep** out) {
     GWZ_REQUIRE(m && out, "gwz_sweep_create: NULL argument");
+    GWZ_REQUIRE(m->v == 0.0, "gwz_sweep_create: ExtendedHubbardReal1D models need the gwz_gen_* entry points");
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
     gwz_sweep* s = new gwz_sweep();

@@ -668,6 +668,24 @@ __device__ __forceinline__ void enumerate_hops(const uint32_t (&a)[NW], const De
     if (!stop && n_pend >= 0) emit(n_prev, n_pend, n1, z_pend);
 }
 
+// colex unranking: the rank-th N-subset of bit positions, as a 64-bit word
+__device__ __forceinline__ uint64_t unrank_colex(uint64_t rank, int N, int B, const uint64_t* __restrict__ binom) {
+    uint64_t x = 0;
+    int p = B - 1;
+    for (int i = N; i >= 1; --i) {
+        while (binom[p * 65 + i] > rank) --p;  // largest p with C(p,i) <= rank
+        x |= 1ull << p;
+        rank -= binom[p * 65 + i];
+        --p;
+    }
+    return x;
+}
+// next integer with the same popcount (Gosper)
+__device__ __forceinline__ uint64_t next_same_popcount(uint64_t x) {
+    const uint64_t t = x | (x - 1);
+    return (t + 1) | (((~t & (0 - ~t)) - 1) >> (__ffsll((long long)x)));
+}
+
 // warp / block reductions of doubles (deterministic order)
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

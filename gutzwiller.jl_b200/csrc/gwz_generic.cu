@@ -1,0 +1,542 @@
+// gwz_generic.cu -- kernels of the ansatz-generic engine (gwz_generic.cuh): per-address probe /
+// ansatz evaluation, the kinetic-VQMC walker kernel and the LocalEnergyEvaluator sweep, one warp per
+// walker / state.  Reference: src/kinetic-vqmc/qmc.jl:14-106, src/kinetic-vqmc/state.jl:42-49,
+// src/localenergy.jl:94-155, src/ansatz/*.jl.
+#include "gwz_generic.cuh"
+#include "gwz_internal.h"
+
+namespace gwz {
+
+// ------------------------------------------------------------------------------------------
+// layout conversion: unary addresses (AoS n x W) <-> occupation bytes (n x Mpad)
+// ------------------------------------------------------------------------------------------
+__global__ void gen_unary_to_occ_kernel(const uint64_t* __restrict__ addr, size_t n, int W, int B, int M, int Mpad,
+                                        uint8_t* __restrict__ occ, int broadcast) {
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const uint64_t* a = addr + (broadcast ? 0 : w * (size_t)W);
+    int mode = 0, cnt = 0;
+    for (int p = 0; p <= B; ++p) {
+        const int bit = (p < B) ? (int)((a[p >> 6] >> (p & 63)) & 1ull) : 0;
+        if (bit) {
+            ++cnt;
+        } else {
+            if (mode < M) occ[w * Mpad + mode] = (uint8_t)cnt;
+            ++mode;
+            cnt = 0;
+        }
+    }
+    for (int k = M; k < Mpad; ++k) occ[w * Mpad + k] = 0;
+}
+__global__ void gen_occ_to_unary_kernel(const uint8_t* __restrict__ occ, size_t n, int W, int M, int Mpad,
+                                        uint64_t* __restrict__ addr) {
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    uint64_t a[4] = {0ull, 0ull, 0ull, 0ull};
+    int pos = 0;
+    for (int k = 0; k < M; ++k) {
+        const int c = occ[w * Mpad + k];
+        for (int q = 0; q < c; ++q, ++pos) a[pos >> 6] |= 1ull << (pos & 63);
+        ++pos;
+    }
+    for (int i = 0; i < W; ++i) addr[w * (size_t)W + i] = a[i];
+}
+
+// phi(n) = 1/2 n^T Q n + b^T n + s (sum log n! - log K)  (psi = exp(-phi))
+__device__ __forceinline__ double gen_phi(const GenModel& gm, const GenWarp& ws, int lane, double lgsum) {
+    double acc = 0.0;
+    for (int k = lane; k < gm.M; k += 32) {
+        const int n = ws.occ[k];
+        if (n) acc = fma((double)n, 0.5 * (ws.V[k] + gm.bvec[k]), acc);
+    }
+    return warp_sum_all(acc) + gm.s * (lgsum - gm.logK);
+}
+
+// ------------------------------------------------------------------------------------------
+// probe: one kinetic_sample! (qmc.jl:14-44) and / or val_and_grad(ansatz, addr, p) per address
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEN_BLOCK)
+gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict__ addr, size_t n,
+                 const double* __restrict__ u01, double* __restrict__ val_out, double* __restrict__ grad_out,
+                 double* __restrict__ e_loc, double* __restrict__ tau_out, double* __restrict__ grad_ratio,
+                 int* __restrict__ n_hops, double* __restrict__ rates, int* __restrict__ chosen,
+                 uint64_t* __restrict__ next_addr, int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GenWarp ws(smem_raw, gm.MP, warp);
+    const size_t nwarps = (size_t)gridDim.x * GEN_WARPS;
+    const int M = gm.M, P = gm.P;
+    for (size_t idx = (size_t)blockIdx.x * GEN_WARPS + warp; idx < n; idx += nwarps) {
+        gen_decode(gm, addr + idx * (size_t)gm.W, ws, lane);
+        gen_potential(gm, ws, lane);
+        long long reg, ext;
+        double lgsum;
+        gen_totals(gm, ws, lane, reg, ext, lgsum);
+        if (val_out || grad_out) {
+            const double val = exp(-gen_phi(gm, ws, lane, lgsum));
+            if (val_out && lane == 0) val_out[idx] = val;
+            if (grad_out)
+                for (int p = lane; p < P; p += 32) {
+                    const double F = gen_feature(gm, ws, p, reg, ext, lgsum);
+                    // MultinomialAnsatz: val * log(y) (multinomial.jl:58); the others: -(feature * val)
+                    grad_out[idx * (size_t)P + p] = (gm.kind == GEN_MULTINOMIAL) ? val * -F : -(F * val);
+                }
+        }
+        if (!(e_loc || tau_out || grad_ratio || n_hops || rates || chosen || next_addr)) continue;
+        double S_lane, E_lane;
+        int nocc_lane;
+        gen_rates(gm, ws, lane, S_lane, E_lane, nocc_lane);
+        __syncwarp();
+        const double cum = warp_scan_incl(S_lane, lane);
+        const double S = __shfl_sync(0xffffffffu, cum, 31);
+        const double Etot = warp_sum_all(E_lane);
+        const int nocc = warp_sum_all(nocc_lane);
+        const double tau = 1.0 / S;
+        const double D = gm.u * (double)reg + gm.v * (double)ext;
+        if (lane == 0) {
+            if (e_loc) e_loc[idx] = D - gm.t * Etot;
+            if (tau_out) tau_out[idx] = tau;
+            if (n_hops) n_hops[idx] = 2 * nocc;
+            if (!(tau < 1.0e300) || !(tau == tau)) atomicOr(err_flag, 1);
+        }
+        if (grad_ratio)
+            for (int p = lane; p < P; p += 32) grad_ratio[idx * (size_t)P + p] = -gen_feature(gm, ws, p, reg, ext, lgsum);
+        if (rates) {
+            double* row = rates + idx * (size_t)(2 * M);
+            for (int h = lane; h < 2 * M; h += 32) row[h] = 0.0;
+            __syncwarp();
+            // exclusive prefix of occupied modes over the lanes (lanes own contiguous mode ranges)
+            int incl = nocc_lane;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int h = 2 * (incl - nocc_lane);
+            for (int q = 0; q < gm.MPL; ++q) {
+                const int k = lane * gm.MPL + q;
+                if (k < M && ws.occ[k] > 0) {
+                    row[h] = ws.rate[2 * k];
+                    row[h + 1] = ws.rate[2 * k + 1];
+                    h += 2;
+                }
+            }
+        }
+        if (chosen || next_addr) {
+            const double u = u01 ? u01[idx] : 0.5;
+            double T = u * S;
+            if (!(T < S)) T = __longlong_as_double(__double_as_longlong(S) - 1);
+            int src, right;
+            gen_select(gm, ws, lane, S_lane, cum, T, src, right);
+            if (chosen) {
+                int below = 0;
+                for (int k = lane; k < src; k += 32) below += ws.occ[k] > 0;
+                below = warp_sum_all(below);
+                if (lane == 0) chosen[idx] = 2 * below + (right ? 1 : 2);
+            }
+            if (next_addr) {
+                const int dst = right ? (src + 1 == M ? 0 : src + 1) : (src == 0 ? M - 1 : src - 1);
+                __syncwarp();
+                if (lane == 0) {
+                    ws.occ[src] -= 1;
+                    ws.occ[dst] += 1;
+                }
+                __syncwarp();
+                gen_encode(gm, ws, lane, next_addr + idx * (size_t)gm.W);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// walkers: kinetic_vqmc!(st; steps) (qmc.jl:73-97), running sums of state.jl:42-49 per walker
+// ------------------------------------------------------------------------------------------
+template <int PPL>
+__global__ void __launch_bounds__(GEN_BLOCK)
+gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ PhiloxKeys pk, uint8_t* __restrict__ occ_g,
+                  int Mpad, double* __restrict__ acc_g, size_t n, uint64_t goff, uint64_t step0, uint64_t steps,
+                  int accumulate, int reset_acc, const double* __restrict__ shift, double* __restrict__ partials,
+                  double* __restrict__ rec_tau, double* __restrict__ rec_eloc, uint64_t* __restrict__ rec_addr,
+                  int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GenWarp ws(smem_raw, gm.MP, warp);
+    const size_t gwarp = (size_t)blockIdx.x * GEN_WARPS + warp, nwarps = (size_t)gridDim.x * GEN_WARPS;
+    const int M = gm.M, P = gm.P;
+    const int AW = 3 + 2 * P;  // per-walker sums in HBM: st, stE, stEE, stG[P], stGE[P]
+    const double E0 = (accumulate && shift) ? shift[0] : 0.0;
+    double G0[PPL];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+        const int p = lane + 32 * q;
+        G0[q] = (accumulate && shift && p < P) ? shift[1 + p] : 0.0;
+    }
+    double ps[GEN_HEAD];
+    double pv[4][PPL];
+#pragma unroll
+    for (int i = 0; i < GEN_HEAD; ++i) ps[i] = 0.0;
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) pv[0][q] = pv[1][q] = pv[2][q] = pv[3][q] = 0.0;
+    bool bad = false;
+
+    for (size_t w = gwarp; w < n; w += nwarps) {
+        for (int k = lane; k < gm.MP; k += 32) ws.occ[k] = (k < M) ? (int)occ_g[w * (size_t)Mpad + k] : 0;
+        __syncwarp();
+        gen_potential(gm, ws, lane);
+        long long reg, ext;
+        double lgsum;
+        gen_totals(gm, ws, lane, reg, ext, lgsum);
+        double F[PPL], aG[PPL], aGE[PPL];
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int p = lane + 32 * q;
+            F[q] = (p < P) ? gen_feature(gm, ws, p, reg, ext, lgsum) : 0.0;
+            aG[q] = aGE[q] = 0.0;
+        }
+        double st = 0.0, ste = 0.0, stee = 0.0;
+        if (accumulate && !reset_acc) {
+            const double* a = acc_g + w * (size_t)AW;
+            st = a[0];
+            ste = a[1];
+            stee = a[2];
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const int p = lane + 32 * q;
+                if (p < P) {
+                    aG[q] = a[3 + p];
+                    aGE[q] = a[3 + P + p];
+                }
+            }
+        }
+        const uint64_t wid = goff + (uint64_t)w;
+        const uint32_t c2 = (uint32_t)wid, c3 = (uint32_t)(wid >> 32);
+        uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+        unsigned long long hops = 0ull;
+
+        for (uint64_t k = 0; k < steps; ++k) {
+            const uint64_t step = step0 + k;
+            if (k != 0 && (k % GEN_REFRESH) == 0) {  // bound the rounding drift of the incremental V and F
+                gen_potential(gm, ws, lane);
+                gen_totals(gm, ws, lane, reg, ext, lgsum);
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const int p = lane + 32 * q;
+                    if (p < P) F[q] = gen_feature(gm, ws, p, reg, ext, lgsum);
+                }
+            }
+            if (k == 0 || (step & 1ull) == 0ull) {
+                const uint64_t blk = step >> 1;
+                philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+            }
+            const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
+            double S_lane, E_lane;
+            int nocc_lane;
+            gen_rates(gm, ws, lane, S_lane, E_lane, nocc_lane);
+            const double cum = warp_scan_incl(S_lane, lane);
+            const double S = __shfl_sync(0xffffffffu, cum, 31);
+            const double Etot = warp_sum_all(E_lane);
+            const int nocc = warp_sum_all(nocc_lane);
+            const double tau = 1.0 / S;
+            const double eloc = gm.u * (double)reg + gm.v * (double)ext - gm.t * Etot;
+            bad |= !(tau < 1.0e300);
+            if (rec_tau && lane == 0) {
+                rec_tau[k * n + w] = tau;
+                rec_eloc[k * n + w] = eloc;
+            }
+            if (rec_addr) gen_encode(gm, ws, lane, rec_addr + (k * n + w) * (size_t)gm.W);
+            const double dE = eloc - E0;
+            const double tE = tau * dE;
+            st += tau;
+            ste += tE;
+            stee = fma(tE, dE, stee);
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const double dG = -F[q] - G0[q];
+                aG[q] = fma(tau, dG, aG[q]);
+                aGE[q] = fma(tE, dG, aGE[q]);
+            }
+            hops += (unsigned)(2 * nocc);
+            double T = u01 * S;
+            if (!(T < S)) T = __longlong_as_double(__double_as_longlong(S) - 1);
+            int src, right;
+            gen_select(gm, ws, lane, S_lane, cum, T, src, right);
+            const int dst = right ? (src + 1 == M ? 0 : src + 1) : (src == 0 ? M - 1 : src - 1);
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const int p = lane + 32 * q;
+                if (p < P) F[q] += gen_dfeature(gm, ws, p, src, dst);
+            }
+            reg += ws.occ[dst] - ws.occ[src] + 1;
+            ext += gen_dext(gm, ws, src, dst);
+            __syncwarp();  // every lane has read the pre-hop occupations
+            for (int m = lane; m < M; m += 32)
+                ws.V[m] += __ldg(gm.Qt + (size_t)dst * M + m) - __ldg(gm.Qt + (size_t)src * M + m);
+            if (lane == 0) {
+                ws.occ[src] -= 1;
+                ws.occ[dst] += 1;
+            }
+            __syncwarp();
+        }
+
+        for (int k = lane; k < M; k += 32) occ_g[w * (size_t)Mpad + k] = (uint8_t)ws.occ[k];
+        if (accumulate) {
+            double* a = acc_g + w * (size_t)AW;
+            if (lane == 0) {
+                a[0] = st;
+                a[1] = ste;
+                a[2] = stee;
+            }
+            const double inv = 1.0 / st;
+            const double mE = ste * inv;
+            const double val_w = E0 + mE;
+            ps[GS_WALKERS] += 1.0;
+            ps[GS_VAL] += val_w;
+            ps[GS_VAL2] = fma(val_w, val_w, ps[GS_VAL2]);
+            ps[GS_T] += st;
+            ps[GS_TE] += st * val_w;
+            ps[GS_TEE] += st * E0 * E0 + 2.0 * E0 * ste + stee;
+            ps[GS_HOPS] += (double)hops;
+            ps[GS_STEPS] += (double)steps;
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const int p = lane + 32 * q;
+                if (p < P) {
+                    a[3 + p] = aG[q];
+                    a[3 + P + p] = aGE[q];
+                    const double mG = aG[q] * inv;
+                    const double grad_w = 2.0 * (aGE[q] * inv - mE * mG);
+                    pv[0][q] += grad_w;
+                    pv[1][q] = fma(grad_w, grad_w, pv[1][q]);
+                    pv[2][q] += st * G0[q] + aG[q];
+                    pv[3][q] += st * G0[q] * E0 + G0[q] * ste + E0 * aG[q] + aGE[q];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (bad && lane == 0) atomicOr(err_flag, 1);
+    if (!accumulate || partials == nullptr) return;
+    double* out = partials + gwarp * (size_t)gen_vec_len(P);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < GEN_HEAD; ++i) out[i] = ps[i];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+        const int p = lane + 32 * q;
+        if (p < P) {
+            out[GEN_HEAD + p] = pv[0][q];
+            out[GEN_HEAD + P + p] = pv[1][q];
+            out[GEN_HEAD + 2 * P + p] = pv[2][q];
+            out[GEN_HEAD + 3 * P + p] = pv[3][q];
+        }
+    }
+}
+
+// val_w[n], grad_w[n x P] from the per-walker sums (state.jl:42-49)
+__global__ void gen_estimates_kernel(const double* __restrict__ acc, size_t n, int P, const double* __restrict__ shift,
+                                     double* __restrict__ val_w, double* __restrict__ grad_w) {
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const double* a = acc + w * (size_t)(3 + 2 * P);
+    const double inv = 1.0 / a[0];
+    const double mE = a[1] * inv;
+    if (val_w) val_w[w] = shift[0] + mE;
+    if (grad_w)
+        for (int p = 0; p < P; ++p) grad_w[w * (size_t)P + p] = 2.0 * (a[3 + P + p] * inv - mE * (a[3 + p] * inv));
+}
+
+// ------------------------------------------------------------------------------------------
+// LocalEnergyEvaluator (localenergy.jl:94-155): one warp per basis state
+// ------------------------------------------------------------------------------------------
+template <int PPL>
+__global__ void __launch_bounds__(GEN_BLOCK)
+gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin,
+                 const uint64_t* __restrict__ binom, uint64_t chunk, int with_grad, double* __restrict__ partials,
+                 double* __restrict__ terms_out, uint64_t* __restrict__ states_out, uint64_t first, uint64_t count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GenWarp ws(smem_raw, gm.MP, warp);
+    uint64_t* aw = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GEN_WARPS * GenWarp::bytes(gm.MP)) + 4 * warp;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * GEN_WARPS + warp;
+    const int M = gm.M, P = gm.P;
+    const bool per_state = terms_out != nullptr || states_out != nullptr;
+    const uint64_t lo = per_state ? first + gwarp * chunk : gwarp * chunk;
+    const uint64_t end = per_state ? first + count : dim;
+    const uint64_t hi = (lo + chunk < end) ? lo + chunk : end;
+    double num = 0.0, den = 0.0, ng[PPL], dg[PPL];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) ng[q] = dg[q] = 0.0;
+    uint64_t x = 0;
+    for (uint64_t sidx = lo; sidx < hi; ++sidx) {
+        if (basis) {
+            if (lane < gm.W) aw[lane] = basis[(uint64_t)lane * dim + sidx];
+        } else {
+            x = (sidx == lo) ? unrank_colex(rank_begin + sidx, gm.N, gm.B, binom) : next_same_popcount(x);
+            if (lane == 0) aw[0] = x;
+        }
+        __syncwarp();
+        if (states_out && lane < gm.W) states_out[(sidx - first) * (uint64_t)gm.W + lane] = aw[lane];
+        gen_decode(gm, aw, ws, lane);
+        gen_potential(gm, ws, lane);
+        long long reg, ext;
+        double lgsum;
+        gen_totals(gm, ws, lane, reg, ext, lgsum);
+        double S_lane, E_lane;
+        int nocc_lane;
+        gen_rates(gm, ws, lane, S_lane, E_lane, nocc_lane);
+        __syncwarp();
+        const double Etot = warp_sum_all(E_lane);
+        const double D = gm.u * (double)reg + gm.v * (double)ext;
+        const double eloc = D - gm.t * Etot;
+        const double psi2 = exp(-2.0 * gen_phi(gm, ws, lane, lgsum));
+        const double s_num = psi2 * eloc;
+        if (per_state) {
+            if (terms_out && lane == 0) {
+                terms_out[(sidx - first) * (uint64_t)(2 + 2 * P)] = s_num;
+                terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 1] = psi2;
+            }
+        } else {
+            num += s_num;
+            den += psi2;
+        }
+        if (with_grad) {
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const int p = lane + 32 * q;
+                if (p < P) {
+                    const double Fp = gen_feature(gm, ws, p, reg, ext, lgsum);
+                    double cross = 0.0;  // sum over hops of melem * ratio * (F_p(n') - F_p(n))
+                    for (int k = 0; k < M; ++k) {
+                        if (ws.occ[k] > 0) {
+                            const int kr = k + 1 == M ? 0 : k + 1, kl = k == 0 ? M - 1 : k - 1;
+                            cross = fma(ws.mr[2 * k], gen_dfeature(gm, ws, p, k, kr), cross);
+                            cross = fma(ws.mr[2 * k + 1], gen_dfeature(gm, ws, p, k, kl), cross);
+                        }
+                    }
+                    // localenergy.jl:109-118 with k_grad = -F psi_k, l_grad = -F(l) psi_l
+                    const double s_ng = -psi2 * (2.0 * Fp * eloc + cross);
+                    const double s_dg = -2.0 * Fp * psi2;
+                    if (per_state) {
+                        if (terms_out) {
+                            terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 2 + p] = s_ng;
+                            terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 2 + P + p] = s_dg;
+                        }
+                    } else {
+                        ng[q] += s_ng;
+                        dg[q] += s_dg;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (per_state || partials == nullptr) return;
+    double* out = partials + gwarp * (uint64_t)(2 + 2 * P);
+    if (lane == 0) {
+        out[0] = num;
+        out[1] = den;
+    }
+#pragma unroll
+    for (int q = 0; q < PPL; ++q) {
+        const int p = lane + 32 * q;
+        if (p < P) {
+            out[2 + p] = ng[q];
+            out[2 + P + p] = dg[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static size_t gen_smem(const GenModel& gm) { return (size_t)GEN_WARPS * GenWarp::bytes(gm.MP) + GEN_WARPS * 4 * sizeof(uint64_t); }
+
+template <typename K>
+static cudaError_t gen_prepare(K kernel, size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+int gen_ppl(int P) {
+    const int need = (P + 31) / 32;
+    return need <= 1 ? 1 : (need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 8 ? 8 : 0)));
+}
+
+cudaError_t gen_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
+    // one resident wave: registers and the small per-warp smem slices allow >= 4 CTAs per SM
+    const size_t smem = gen_smem(gm);
+    int per_sm = (int)((200 * 1024) / (smem ? smem : 1));
+    per_sm = per_sm > 6 ? 6 : (per_sm < 1 ? 1 : per_sm);
+    const size_t resident = (size_t)per_sm * sm_count;
+    const size_t need = (n + GEN_WARPS - 1) / GEN_WARPS;
+    *grid = (int)(need < resident ? need : resident);
+    if (*grid < 1) *grid = 1;
+    return cudaSuccess;
+}
+
+cudaError_t launch_gen_unary_to_occ(const uint64_t* addr, size_t n, const GenModel& gm, int Mpad, uint8_t* occ,
+                                    bool broadcast, cudaStream_t s) {
+    gen_unary_to_occ_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(addr, n, gm.W, gm.B, gm.M, Mpad, occ, broadcast ? 1 : 0);
+    return cudaGetLastError();
+}
+cudaError_t launch_gen_occ_to_unary(const uint8_t* occ, size_t n, const GenModel& gm, int Mpad, uint64_t* addr,
+                                    cudaStream_t s) {
+    gen_occ_to_unary_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(occ, n, gm.W, gm.M, Mpad, addr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gen_probe(const GenProbeLaunch& L, cudaStream_t s) {
+    const size_t smem = gen_smem(L.gm);
+    if (cudaError_t e = gen_prepare(gen_probe_kernel, smem)) return e;
+    size_t grid = (L.n + GEN_WARPS - 1) / GEN_WARPS;
+    if (grid > 65535u * 16u) grid = 65535u * 16u;
+    if (grid < 1) grid = 1;
+    gen_probe_kernel<<<(unsigned)grid, GEN_BLOCK, smem, s>>>(L.gm, L.addr, L.n, L.u01, L.val, L.grad, L.e_loc, L.tau,
+                                                            L.grad_ratio, L.n_hops, L.rates, L.chosen, L.next_addr, L.err_flag);
+    return cudaGetLastError();
+}
+
+template <int PPL>
+static cudaError_t gen_walker_launch(const GenWalkerLaunch& L, cudaStream_t s) {
+    const size_t smem = gen_smem(L.gm);
+    if (cudaError_t e = gen_prepare(gen_walker_kernel<PPL>, smem)) return e;
+    gen_walker_kernel<PPL><<<L.grid, GEN_BLOCK, smem, s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n, L.global_offset,
+                                                         L.step0, L.steps, L.accumulate, L.reset_acc, L.shift, L.partials,
+                                                         L.rec_tau, L.rec_eloc, L.rec_addr, L.err_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_gen_walkers(const GenWalkerLaunch& L, cudaStream_t s) {
+    switch (gen_ppl(L.gm.P)) {
+        case 1: return gen_walker_launch<1>(L, s);
+        case 2: return gen_walker_launch<2>(L, s);
+        case 4: return gen_walker_launch<4>(L, s);
+        case 8: return gen_walker_launch<8>(L, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t launch_gen_estimates(const double* acc, size_t n, int P, const double* shift, double* val_w, double* grad_w,
+                                 cudaStream_t s) {
+    gen_estimates_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(acc, n, P, shift, val_w, grad_w);
+    return cudaGetLastError();
+}
+
+template <int PPL>
+static cudaError_t gen_sweep_launch(const GenSweepLaunch& L, cudaStream_t s) {
+    const size_t smem = gen_smem(L.gm);
+    if (cudaError_t e = gen_prepare(gen_sweep_kernel<PPL>, smem)) return e;
+    gen_sweep_kernel<PPL><<<L.grid, GEN_BLOCK, smem, s>>>(L.gm, L.basis, L.dim, L.rank_begin, L.binom, L.chunk, L.with_grad,
+                                                        L.partials, L.terms_out, L.states_out, L.first, L.count);
+    return cudaGetLastError();
+}
+cudaError_t launch_gen_sweep(const GenSweepLaunch& L, cudaStream_t s) {
+    switch (gen_ppl(L.gm.P)) {
+        case 1: return gen_sweep_launch<1>(L, s);
+        case 2: return gen_sweep_launch<2>(L, s);
+        case 4: return gen_sweep_launch<4>(L, s);
+        case 8: return gen_sweep_launch<8>(L, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace gwz

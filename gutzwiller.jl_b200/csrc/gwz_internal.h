@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "gwz_device.cuh"
+#include "gwz_generic.cuh"
 
 namespace gwz {
 
@@ -117,5 +118,59 @@ struct SweepLaunch {
 cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk);
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s);
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s);
+
+// ---- ansatz-generic engine (gwz_generic.cu) ------------------------------------------------
+struct GenProbeLaunch {
+    GenModel gm;
+    const uint64_t* addr;  // AoS n x W
+    size_t n;
+    const double* u01;
+    double *val, *grad;                 // ansatz(addr, p), val_and_grad(ansatz, addr, p): n, n x P
+    double *e_loc, *tau, *grad_ratio;   // kinetic_sample!: n, n, n x P
+    int32_t* n_hops;
+    double* rates;  // n x 2M, reference hop order
+    int32_t* chosen;
+    uint64_t* next_addr;
+    int* err_flag;
+};
+struct GenWalkerLaunch {
+    GenModel gm;
+    uint8_t* occ;  // [n][Mpad]
+    int Mpad;
+    double* acc;  // [n][3 + 2P]
+    size_t n;
+    uint64_t global_offset, seed, step0, steps;
+    int accumulate, reset_acc;
+    const double* shift;  // [1 + P] reference point (E, G) of the shifted sums
+    double* partials;     // [grid * GEN_WARPS][gen_vec_len(P)]
+    double *rec_tau, *rec_eloc;
+    uint64_t* rec_addr;
+    int grid;
+    int* err_flag;
+};
+struct GenSweepLaunch {
+    GenModel gm;
+    const uint64_t* basis;  // SoA [W][dim] or null => ranked
+    uint64_t dim, rank_begin;
+    const uint64_t* binom;
+    uint64_t chunk;
+    int with_grad;
+    double* partials;  // [grid * GEN_WARPS][2 + 2P]
+    double* terms_out;
+    uint64_t* states_out;
+    uint64_t first, count;
+    int grid;
+};
+int gen_ppl(int P);  // parameter slots per lane (1, 2, 4, 8), 0 if P > 256
+cudaError_t gen_grid(const GenModel& gm, size_t n, int sm_count, int* grid);
+cudaError_t launch_gen_unary_to_occ(const uint64_t* addr, size_t n, const GenModel& gm, int Mpad, uint8_t* occ,
+                                    bool broadcast, cudaStream_t s);
+cudaError_t launch_gen_occ_to_unary(const uint8_t* occ, size_t n, const GenModel& gm, int Mpad, uint64_t* addr,
+                                    cudaStream_t s);
+cudaError_t launch_gen_probe(const GenProbeLaunch& L, cudaStream_t s);
+cudaError_t launch_gen_walkers(const GenWalkerLaunch& L, cudaStream_t s);
+cudaError_t launch_gen_estimates(const double* acc, size_t n, int P, const double* shift, double* val_w, double* grad_w,
+                                 cudaStream_t s);
+cudaError_t launch_gen_sweep(const GenSweepLaunch& L, cudaStream_t s);
 
 }  // namespace gwz

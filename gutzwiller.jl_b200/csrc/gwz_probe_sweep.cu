@@ -93,24 +93,6 @@ __device__ __forceinline__ void state_terms(const uint32_t (&a)[NW], const DevMo
     den_grad = -2.0 * D * psi2;
 }
 
-// colex unranking: the rank-th N-subset of bit positions, as a 64-bit word
-__device__ __forceinline__ uint64_t unrank_colex(uint64_t rank, int N, int B, const uint64_t* __restrict__ binom) {
-    uint64_t x = 0;
-    int p = B - 1;
-    for (int i = N; i >= 1; --i) {
-        while (binom[p * 65 + i] > rank) --p;  // largest p with C(p,i) <= rank
-        x |= 1ull << p;
-        rank -= binom[p * 65 + i];
-        --p;
-    }
-    return x;
-}
-// next integer with the same popcount (Gosper)
-__device__ __forceinline__ uint64_t next_same_popcount(uint64_t x) {
-    const uint64_t t = x | (x - 1);
-    return (t + 1) | (((~t & (0 - ~t)) - 1) >> (__ffsll((long long)x)));
-}
-
 template <int NW, int KC, bool RANKED>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,

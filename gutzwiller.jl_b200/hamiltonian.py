@@ -114,7 +114,7 @@ class HubbardReal1D:
         ctx = ctx or default_context()
         key = id(ctx)
         if key not in self._models:
-            self._models[key] = Model(self.address.N, self.address.M, self.u, self.t, ctx)
+            self._models[key] = Model(self.address.N, self.address.M, self.u, self.t, ctx, v=getattr(self, "v", 0.0))
         return self._models[key]
 
     def __repr__(self):
@@ -134,9 +134,16 @@ class GutzwillerAnsatz(AbstractAnsatz):
     """``G(|f>; g) = exp(-g <f|H|f>)`` (src/ansatz/gutzwiller.jl:14-36); one parameter g."""
     N_PARAMS = 1
 
+    def __new__(cls, hamiltonian=None):
+        # GutzwillerAnsatz(ExtendedHubbardReal1D) runs on the ansatz-generic engine (ansatz.py)
+        if cls is GutzwillerAnsatz and getattr(hamiltonian, "v", 0.0):
+            from .ansatz import GenericGutzwillerAnsatz
+            return GenericGutzwillerAnsatz(hamiltonian)
+        return object.__new__(cls)
+
     def __init__(self, hamiltonian: HubbardReal1D):
         if not isinstance(hamiltonian, HubbardReal1D):
-            raise TypeError("this build covers GutzwillerAnsatz(HubbardReal1D) only")
+            raise TypeError("GutzwillerAnsatz needs a HubbardReal1D / ExtendedHubbardReal1D Hamiltonian")
         self.hamiltonian = hamiltonian
 
     def __call__(self, addr: BoseFS, params) -> float:
@@ -155,7 +162,7 @@ def num_parameters(ansatz: AbstractAnsatz) -> int:
     return ansatz.N_PARAMS
 
 
-def keytype(ansatz: GutzwillerAnsatz):
+def keytype(ansatz: AbstractAnsatz):
     return type(ansatz.hamiltonian.address)
 
 

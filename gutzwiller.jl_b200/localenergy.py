@@ -21,10 +21,28 @@ class LocalEnergyEvaluator:
     """
 
     def __init__(self, hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, *, basis=None, ctx: Context | None = None):
-        if not isinstance(ansatz, GutzwillerAnsatz):
-            raise TypeError("this build covers GutzwillerAnsatz only")
+        self._gen = None
         self.hamiltonian, self.ansatz = hamiltonian, ansatz
         self.model = hamiltonian.model(ctx)
+        self.P = ansatz.N_PARAMS
+        if getattr(ansatz, "generic", False):  # the ansatz-generic engine (ansatz.py)
+            from .ansatz import GenSweep
+            arr = None
+            begin = end = 0
+            if basis is not None:
+                if len(basis) and isinstance(basis[0], BoseFS):
+                    basis = np.stack([b.words for b in basis])
+                arr = np.ascontiguousarray(basis, dtype=np.uint64).reshape(-1, self.model.words)
+                if arr.shape[0] == 0:
+                    raise ValueError("empty basis")
+            else:
+                world, rank = distributed_state() if ctx is None else (1, 0)
+                begin, end = shard_range(self.model.dimension(), world, rank)
+            self._gen = GenSweep(ansatz.handle(ctx), arr, begin, end)
+            self._h = self._gen.handle
+            return
+        if not isinstance(ansatz, GutzwillerAnsatz):
+            raise TypeError(f"unsupported ansatz {type(ansatz).__name__}")
         self._h = C.c_void_p()
         if basis is not None:
             if len(basis) and isinstance(basis[0], BoseFS):
@@ -46,12 +64,16 @@ class LocalEnergyEvaluator:
 
     @property
     def dim(self) -> int:
+        if self._gen is not None:
+            return self._gen.dim()
         d = C.c_uint64()
         check(lib().gwz_sweep_dim(self._h, C.byref(d)))
         return d.value
 
     def val_and_grad(self, params):
         """``val_and_grad(le, params)`` (localenergy.jl:94-129)."""
+        if self._gen is not None:
+            return self._gen.val_and_grad(params)
         p = as_params(params, 1)
         val, grad = C.c_double(), (C.c_double * 1)()
         check(lib().gwz_sweep_val_and_grad(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(val), grad, None))
@@ -65,7 +87,7 @@ class LocalEnergyEvaluator:
         return np.array(acc[:])
 
     def __call__(self, *args):
-        if len(args) == 3:  # one-parameter ansatz: three arguments can only be (F, G, params)
+        if len(args) == 3 and (self.P != 3 or args[0] is None or args[1] is None or not np.isscalar(args[0])):
             F, G, params = args  # le(F, G, params): Optim.only_fg! protocol (localenergy.jl:157-169)
             if G is not None:
                 val, grad = self.val_and_grad(params)
@@ -74,15 +96,19 @@ class LocalEnergyEvaluator:
                 val = self(params)
             return val if F is not None else None
         params = args[0] if len(args) == 1 else args  # le(p...) (localenergy.jl:171-173)
+        if self._gen is not None:
+            return self._gen.val(params)
         p = as_params(params, 1)
         val = C.c_double()
         check(lib().gwz_sweep_val(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(val)))
         return val.value  # localenergy.jl:131-155
 
     def terms(self, params, first: int = 0, count: int | None = None) -> np.ndarray:
-        """Per-state (num, den, num_grad, den_grad) of localenergy.jl:105-120: float64[count, 4]."""
-        p = as_params(params, 1)
+        """Per-state (num, den, num_grad[P], den_grad[P]) of localenergy.jl:105-120: float64[count, 2 + 2P]."""
         count = self.dim - first if count is None else int(count)
+        if self._gen is not None:
+            return self._gen.terms(params, first, count)
+        p = as_params(params, 1)
         out = np.zeros((count, 4))
         check(lib().gwz_sweep_terms(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), int(first), count,
                                     out.ctypes.data_as(C.c_void_p)))
@@ -90,11 +116,15 @@ class LocalEnergyEvaluator:
 
     def states(self, first: int = 0, count: int | None = None) -> np.ndarray:
         count = self.dim - first if count is None else int(count)
+        if self._gen is not None:
+            return self._gen.states(first, count)
         out = np.zeros((count, self.model.words), dtype=np.uint64)
         check(lib().gwz_sweep_states(self._h, int(first), count, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def last_kernel_ms(self) -> float:
+        if self._gen is not None:
+            return self._gen.last_kernel_ms()
         ms = C.c_float()
         check(lib().gwz_sweep_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value

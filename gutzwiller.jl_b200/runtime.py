@@ -127,12 +127,16 @@ def distributed_state() -> tuple[int, int]:
 class Model:
     """gwz_model: HubbardReal1D(BoseFS{N,M}; u, t) + GutzwillerAnsatz on one context."""
 
-    def __init__(self, N: int, M: int, u: float, t: float, ctx: Context | None = None):
+    def __init__(self, N: int, M: int, u: float, t: float, ctx: Context | None = None, v: float = 0.0):
         self.ctx = ctx or default_context()
         self._h = C.c_void_p()
-        check(lib().gwz_model_create_hubbard1d_gutzwiller(self.ctx.handle, int(N), int(M), float(u), float(t),
-                                                          C.byref(self._h)))
-        self.N, self.M, self.u, self.t = int(N), int(M), float(u), float(t)
+        if v:  # ExtendedHubbardReal1D: served by the ansatz-generic engine only
+            check(lib().gwz_model_create_ext_hubbard1d(self.ctx.handle, int(N), int(M), float(u), float(v), float(t),
+                                                       C.byref(self._h)))
+        else:
+            check(lib().gwz_model_create_hubbard1d_gutzwiller(self.ctx.handle, int(N), int(M), float(u), float(t),
+                                                              C.byref(self._h)))
+        self.N, self.M, self.u, self.t, self.v = int(N), int(M), float(u), float(t), float(v)
         bits, words = C.c_int(), C.c_int()
         check(lib().gwz_model_info(self._h, None, None, None, None, C.byref(bits), C.byref(words)))
         self.bits, self.words = bits.value, words.value

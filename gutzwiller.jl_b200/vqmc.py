@@ -249,9 +249,7 @@ def kinetic_vqmc(hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, params, *, 
     they fit in 256 MiB), burn_in (default 0 = reference behaviour), kernel, ctx, estimator ('walker_mean' =
     the reference's mean of per-walker ratio estimates; 'pooled' = one ratio over all walkers and steps, which
     has no per-walker O(tau_corr/steps) bias -- preferable for many short walkers; needs record=False)."""
-    if not isinstance(ansatz, GutzwillerAnsatz) or ansatz.hamiltonian is not hamiltonian and \
-            (ansatz.hamiltonian.u, ansatz.hamiltonian.t) != (hamiltonian.u, hamiltonian.t):
-        raise TypeError("this build covers GutzwillerAnsatz(H) with H::HubbardReal1D")
+    _check_pair(hamiltonian, ansatz)
     if walkers is None:
         walkers = default_walkers(samples)
     walkers = int(walkers)
@@ -262,8 +260,25 @@ def kinetic_vqmc(hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, params, *, 
     return res._run(steps, keep=False)
 
 
+def _is_generic(ansatz) -> bool:
+    """ansaetze served by the ansatz-generic engine (ansatz.py) rather than the Gutzwiller fast path"""
+    return bool(getattr(ansatz, "generic", False))
+
+
+def _check_pair(hamiltonian, ansatz):
+    if not isinstance(ansatz, AbstractAnsatz) or not hasattr(ansatz, "hamiltonian"):
+        raise TypeError("ansatz must be one of the AbstractAnsatz types of this package")
+    h2 = ansatz.hamiltonian
+    if h2 is not hamiltonian and (h2.u, h2.t, getattr(h2, "v", 0.0), h2.address.N, h2.address.M) != \
+            (hamiltonian.u, hamiltonian.t, getattr(hamiltonian, "v", 0.0), hamiltonian.address.N, hamiltonian.address.M):
+        raise TypeError("the ansatz was built for a different Hamiltonian")
+    if not _is_generic(ansatz) and not isinstance(ansatz, GutzwillerAnsatz):
+        raise TypeError(f"unsupported ansatz {type(ansatz).__name__}")
+
+
 def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn_in, kernel, ctx,
                  estimator="walker_mean"):
+    _check_pair(hamiltonian, ansatz)
     model = hamiltonian.model(ctx)
     world, rank = distributed_state() if (ctx is None) else (1, 0)
     begin, end = shard_range(walkers, world, rank)
@@ -275,7 +290,11 @@ def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn
         record = False
     if record is None:
         record = (end - begin) * max(steps, 1) * (16 + 8 * model.words) <= RECORD_LIMIT_BYTES and world == 1
-    w = Walkers(model, end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
+    if _is_generic(ansatz):
+        from .ansatz import GenWalkers
+        w = GenWalkers(ansatz.handle(ctx), end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
+    else:
+        w = Walkers(model, end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
     return KineticVQMCResult(hamiltonian, ansatz, params, w, bool(record), kernel, burn_in, estimator)
 
 
@@ -292,7 +311,7 @@ def _per_walker_estimates(res: KineticVQMCResult):
 def val_and_grad_result(res: KineticVQMCResult):
     """state.jl:137-149: mean over walkers of the per-walker (val, grad) of state.jl:42-49."""
     r = res.last
-    return r.val, np.array([r.grad[0]])
+    return r.val, np.array(r.grad[:], dtype=np.float64)
 
 
 def val_err_and_grad_result(res: KineticVQMCResult):
@@ -311,19 +330,22 @@ def val_err_and_grad_result(res: KineticVQMCResult):
             errs2 += b.err ** 2
             if gr is None:
                 gr = _grad_ratio_series(res)
-            grads += 2.0 * float(np.sum(tau[w] * gr[w] * (el[w] - b.mean)) / np.sum(tau[w]))  # state.jl:57-58
+            grads = grads + 2.0 * ((tau[w] * (el[w] - b.mean)) @ gr[w]) / np.sum(tau[w])  # state.jl:57-58
         nw = tau.shape[0]
-        return vals / nw, math.sqrt(errs2) / nw, np.array([grads / nw])
-    return r.val, (r.err if r.walkers > 1 else float("nan")), np.array([r.grad[0]])
+        return vals / nw, math.sqrt(errs2) / nw, np.atleast_1d(grads / nw)
+    return r.val, (r.err if r.walkers > 1 else float("nan")), np.array(r.grad[:], dtype=np.float64)
 
 
 def _grad_ratio_series(res: KineticVQMCResult) -> np.ndarray:
-    """grad_ratios[walker, step] = grad psi / psi = -diagonal_element for the Gutzwiller ansatz
-    (gutzwiller.jl:30, qmc.jl:38), recomputed on the GPU from the recorded addresses."""
+    """grad_ratios[walker, step, P] = grad psi / psi (qmc.jl:38; -diagonal_element for the Gutzwiller ansatz,
+    gutzwiller.jl:30), recomputed on the GPU from the recorded addresses."""
     ad = res.addresses()
     nw, ns, W = ad.shape
-    out = res.hamiltonian.model(res.walkers_handle.model.ctx).probe(ad.reshape(-1, W), res.params)
-    return out["grad_ratio"][:, 0].reshape(nw, ns)
+    if _is_generic(res.ansatz):
+        out = res.walkers_handle.ansatz_handle.probe(ad.reshape(-1, W), res.params)
+    else:
+        out = res.hamiltonian.model(res.walkers_handle.model.ctx).probe(ad.reshape(-1, W), res.params)
+    return out["grad_ratio"].reshape(nw, ns, -1)
 
 
 def local_energy_estimator(res: KineticVQMCResult, resample_length=None) -> CombinedBlockingResult:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GWZ_VERSION 100
+#define GWZ_VERSION 110
 #define GWZ_MAX_WORDS 4       /* 64-bit words per address (N+M-1 <= 251) */
 #define GWZ_NUM_PARAMS 1      /* GutzwillerAnsatz has one parameter g (gutzwiller.jl:14) */
 #define GWZ_NCCL_ID_BYTES 128 /* sizeof(ncclUniqueId) */
@@ -217,6 +217,74 @@ int gwz_adaptive_gradient_descent(gwz_objective_fn val_and_grad, gwz_objective_f
 int gwz_amsgrad_vqmc(gwz_walkers *w, const double *p0, const gwz_gd_opts *opts, uint64_t steps_per_walker,
                      int kernel_kind, unsigned flags, gwz_gd_trace *trace);
 int gwz_amsgrad_sweep(gwz_sweep *s, const double *p0, const gwz_gd_opts *opts, gwz_gd_trace *trace);
+
+/* ---- ansatz-generic engine ---------------------------------------------
+ * The reference's other single-component ansaetze, and Rimu's ExtendedHubbardReal1D, through the same
+ * three operations (probe / walkers / sweep) with P = num_parameters(ansatz) parameters.  One warp per
+ * walker; hops are visited in the reference's offdiagonals order and the move is the reference's
+ * pick_random_from_cumsum (qmc.jl:52-61), so a walker follows the reference trajectory for the same
+ * uniform stream.  Parameter vectors are P doubles in the reference's order. */
+enum gwz_ansatz_kind {
+    GWZ_ANSATZ_GUTZWILLER = 0,       /* src/ansatz/gutzwiller.jl:14-36:   P = 1 */
+    GWZ_ANSATZ_EXT_GUTZWILLER = 1,   /* src/ansatz/extgutzwiller.jl:14-35 (call operator): P = 2 */
+    GWZ_ANSATZ_MULTINOMIAL = 2,      /* src/ansatz/multinomial.jl:17-59:  P = 1 */
+    GWZ_ANSATZ_DENSITY_PROFILE = 3,  /* src/ansatz/densityprofile.jl:8-28: P = M */
+    GWZ_ANSATZ_RELATIVE_JASTROW = 4, /* src/ansatz/jastrow.jl:71-103:     P = cld(M, 2) */
+    GWZ_ANSATZ_JASTROW = 5           /* src/ansatz/jastrow.jl:13-58:      P = M (M + 1) / 2 */
+};
+typedef struct gwz_ansatz gwz_ansatz;
+typedef struct gwz_gwalkers gwz_gwalkers;
+typedef struct gwz_gsweep gwz_gsweep;
+
+/* Rimu ExtendedHubbardReal1D(addr; u, v, t): diagonal u sum n(n-1)/2 + v sum n_i n_{i+1} (periodic).
+ * Such a model is accepted by the gwz_gen_* / gwz_gwalkers_* / gwz_gsweep_* entry points only. */
+int gwz_model_create_ext_hubbard1d(gwz_context *ctx, int N, int M, double u, double v, double t, gwz_model **out);
+int gwz_model_info_ext(const gwz_model *m, double *v);
+/* `ansatz = XAnsatz(H)`; normalize: MultinomialAnsatz(H; normalize) (multinomial.jl:22-31) */
+int gwz_ansatz_create(gwz_model *m, int kind, int normalize, gwz_ansatz **out);
+int gwz_ansatz_destroy(gwz_ansatz *a);
+int gwz_ansatz_info(const gwz_ansatz *a, int *kind, int *num_parameters);
+/* ansatz(addr, p) and val_and_grad(ansatz, addr, p): val[n], grad[n x P] (either may be NULL) */
+int gwz_gen_ansatz_eval(gwz_ansatz *a, const uint64_t *addr_words, size_t n, const double *params, double *val,
+                        double *grad);
+/* one kinetic_sample! per address (qmc.jl:14-44); outputs as gwz_probe_addresses, grad_ratio[n x P] */
+int gwz_gen_probe_addresses(gwz_ansatz *a, const uint64_t *addr_words, size_t n, const double *params,
+                            const double *u01, double *e_loc, double *residence_time, double *grad_ratio,
+                            int32_t *n_hops, double *rates, int32_t *chosen, uint64_t *next_addr);
+
+int gwz_gwalkers_create(gwz_ansatz *a, uint64_t n_walkers, uint64_t global_offset, const uint64_t *start_addr,
+                        uint64_t seed, gwz_gwalkers **out);
+int gwz_gwalkers_destroy(gwz_gwalkers *w);
+int gwz_gwalkers_count(const gwz_gwalkers *w, uint64_t *n_walkers, uint64_t *steps_done);
+int gwz_gwalkers_get_addresses(gwz_gwalkers *w, uint64_t *addr_words);
+int gwz_gwalkers_set_addresses(gwz_gwalkers *w, const uint64_t *addr_words);
+int gwz_gwalkers_set_step_counter(gwz_gwalkers *w, uint64_t steps_done);
+typedef struct gwz_gen_result {
+    double val, err;        /* mean over walkers of the per-walker estimates, its cross-walker standard error */
+    double pooled_val, pooled_var, total_time;
+    uint64_t walkers, steps, hops;
+    float kernel_ms;
+    int32_t np;
+} gwz_gen_result;
+/* as gwz_vqmc_run; grad, grad_err, pooled_grad: P doubles each (any may be NULL) */
+int gwz_gen_vqmc_run(gwz_gwalkers *w, const double *params, uint64_t steps_per_walker, uint64_t burn_in,
+                     unsigned flags, gwz_gen_result *out, double *grad, double *grad_err, double *pooled_grad);
+int gwz_gen_vqmc_run_record(gwz_gwalkers *w, const double *params, uint64_t steps_per_walker, unsigned flags,
+                            double *tau, double *eloc, uint64_t *addr, gwz_gen_result *out, double *grad,
+                            double *grad_err, double *pooled_grad);
+int gwz_gwalkers_estimates(gwz_gwalkers *w, double *val_w, double *grad_w);
+
+/* LocalEnergyEvaluator(H, ansatz; basis) (localenergy.jl:81-173) for any of the ansaetze above */
+int gwz_gsweep_create(gwz_ansatz *a, const uint64_t *basis_words, uint64_t dim, uint64_t rank_begin,
+                      uint64_t rank_end, gwz_gsweep **out);
+int gwz_gsweep_destroy(gwz_gsweep *s);
+int gwz_gsweep_dim(const gwz_gsweep *s, uint64_t *dim);
+/* grad == NULL: le(p) (localenergy.jl:131-155); else val_and_grad(le, p) (:94-129), grad[P] */
+int gwz_gsweep_val_and_grad(gwz_gsweep *s, const double *params, double *val, double *grad);
+/* per-state (num, den, num_grad[P], den_grad[P]): out[count x (2 + 2P)] */
+int gwz_gsweep_terms(gwz_gsweep *s, const double *params, uint64_t first, uint64_t count, double *out);
+int gwz_gsweep_states(gwz_gsweep *s, uint64_t first, uint64_t count, uint64_t *out);
+int gwz_gsweep_last_kernel_ms(const gwz_gsweep *s, float *ms);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ def test_no_torch_types_in_abi():
 
 def test_version_and_error_channel(gw):
     L = gw.lib()
-    assert L.gwz_version() == 100
+    assert L.gwz_version() == 110
     import ctypes as C
     h = C.c_void_p()
     rc = L.gwz_context_create(0, None)

@@ -1,0 +1,235 @@
+"""GPU parity of the ansatz-generic engine (ExtendedGutzwiller, Multinomial, DensityProfile, RelativeJastrow,
+Jastrow, Gutzwiller on ExtendedHubbardReal1D) against part 2 of the CPU oracle, through the C ABI:
+per-address amplitudes / local energies / rates / moves at 1e-12 relative, step-for-step trajectories,
+LocalEnergyEvaluator values and gradients at 1e-12, statistical containment, AMSGrad (test/amsgrad.jl)."""
+import numpy as np
+import pytest
+
+from conftest import edge_onrs, random_onr
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+KINDS = {"gutzwiller": "GutzwillerAnsatz", "ext_gutzwiller": "ExtendedGutzwillerAnsatz",
+         "multinomial": "MultinomialAnsatz", "density_profile": "DensityProfileAnsatz",
+         "relative_jastrow": "RelativeJastrowAnsatz", "jastrow": "JastrowAnsatz"}
+SHAPES = [  # N, M, u, v, t
+    (5, 5, 1.0, 0.0, 0.1),     # test/ansatz.jl:45
+    (5, 5, 1.0, 1.0, 0.1),     # test/ansatz.jl:46 (ExtendedHubbardReal1D)
+    (4, 6, 2.0, 0.5, 1.0),
+    (7, 3, 0.7, 0.3, 1.0),
+    (3, 2, 1.0, 0.4, 1.0),     # M = 2: both neighbours are the same mode
+    (12, 12, 2.0, 0.0, 1.0),
+    (40, 37, 2.0, 0.25, 1.0),  # two modes per lane, two 64-bit words
+]
+
+
+def _make(gw, oracle_mod, kind, N, M, u, v, t, normalize=False):
+    o = oracle_mod.Oracle(N, M, u, t)
+    ao = oracle_mod.AnsatzOracle(o, kind, v=v, normalize=normalize)
+    addr = gw.near_uniform(N, M)
+    H = gw.ExtendedHubbardReal1D(addr, u=u, v=v, t=t) if v else gw.HubbardReal1D(addr, u=u, t=t)
+    cls = getattr(gw, KINDS[kind])
+    if kind == "gutzwiller":
+        cls = gw.GenericGutzwillerAnsatz  # the generic engine also for plain HubbardReal1D (cross-check of the fast path)
+    ans = cls(H, normalize=True) if (kind == "multinomial" and normalize) else cls(H)
+    return o, ao, H, ans
+
+
+def _params(P, rng, scale=0.3):
+    return rng.random(P) * scale
+
+
+def _addresses(o, N, M, seed, n_random=30):
+    rng = np.random.default_rng(seed)
+    onrs = edge_onrs(N, M)
+    for conc in (0.3, 1.0, 5.0, 50.0):
+        onrs += [random_onr(rng, N, M, conc) for _ in range(n_random // 4)]
+    return np.stack([o.from_onr(x) for x in onrs])
+
+
+def _close(a, b, rtol=RTOL, atol=1e-13):
+    return np.all(np.abs(np.asarray(a) - np.asarray(b)) <= atol + rtol * np.abs(np.asarray(b)))
+
+
+@pytest.mark.parametrize("kind", list(KINDS))
+@pytest.mark.parametrize("N,M,u,v,t", SHAPES)
+def test_eval_and_probe_match_oracle(gw, oracle_mod, kind, N, M, u, v, t):
+    if kind == "jastrow" and M * (M + 1) // 2 > 256:
+        pytest.skip("more than 256 parameters")
+    o, ao, H, ans = _make(gw, oracle_mod, kind, N, M, u, v, t)
+    assert ans.N_PARAMS == ao.P == gw.num_parameters(ans)
+    rng = np.random.default_rng(N * 17 + M)
+    p = _params(ao.P, rng, 0.05 if N > 20 else 0.3)
+    addrs = _addresses(o, N, M, seed=M * 31 + N)
+    h = ans.handle()
+    val, grad = h.eval(addrs[:, :o.W], p)
+    u01 = rng.random(len(addrs))
+    out = h.probe(addrs[:, :o.W], p, u01, want_rates=True)
+    for i, a in enumerate(addrs):
+        v1, g1 = ao.val_and_grad(a, p)
+        if not (1e-280 < abs(v1) < 1e280):
+            continue  # the reference's absolute amplitude under/overflows here
+        assert _close(val[i], v1) and _close(grad[i], g1, atol=1e-13 * abs(v1) * max(1.0, np.abs(g1 / v1).max()))
+        ks = ao.kinetic_sample(a, p, float(u01[i]))
+        assert out["n_hops"][i] == ks["n_hops"]
+        assert _close(out["e_loc"][i], ks["eloc"], atol=1e-12)
+        assert _close(out["residence_time"][i], ks["tau"])
+        assert _close(out["grad_ratio"][i], ks["grad"], atol=1e-12)
+        rates = ao.hop_rates(a, p)
+        assert _close(out["rates"][i][: len(rates)], rates) and np.all(out["rates"][i][len(rates):] == 0)
+        # the move: same hop unless u01*S falls within rounding distance of a boundary of the cumulative sums
+        cs = ks["cumsum"]
+        T = u01[i] * cs[-1]
+        if np.min(np.abs(cs - T)) > 1e-9 * cs[-1]:
+            assert out["chosen"][i] == ks["chosen"]
+            assert np.array_equal(out["next_addr"][i], ks["new_addr"][: o.W])
+
+
+@pytest.mark.parametrize("kind,N,M,u,v,t", [("relative_jastrow", 5, 5, 1.0, 0.0, 0.1), ("density_profile", 4, 6, 2.0, 0.5, 1.0),
+                                            ("jastrow", 5, 5, 1.0, 1.0, 0.1), ("multinomial", 7, 3, 0.7, 0.3, 1.0),
+                                            ("ext_gutzwiller", 12, 12, 2.0, 0.3, 1.0), ("gutzwiller", 3, 2, 1.0, 0.4, 1.0),
+                                            ("relative_jastrow", 40, 37, 2.0, 0.25, 1.0)])
+def test_walkers_follow_the_oracle_step_for_step(gw, oracle_mod, kind, N, M, u, v, t):
+    """Same Philox stream, same hop order, same selection rule => identical trajectories and estimates."""
+    o, ao, H, ans = _make(gw, oracle_mod, kind, N, M, u, v, t)
+    rng = np.random.default_rng(11)
+    p = _params(ao.P, rng, 0.05 if N > 20 else 0.3)
+    nw, steps, seed, off = 9, 300, 12345, 5
+    w = gw.GenWalkers(ans.handle(), nw, H.address.words, seed=seed, global_offset=off)
+    r, tau, eloc, addr = w.run_record(p, steps)
+    ref = ao.kinetic_vqmc(p, np.tile(np.pad(H.address.words, (0, 4 - o.W)), (nw, 1)), steps, seed=seed, walker0=off,
+                          series=True)
+    assert np.array_equal(addr.transpose(1, 0, 2), ref["series_addr"][:, :, : o.W])
+    assert _close(tau.T, ref["series_tau"]) and _close(eloc.T, ref["series_eloc"], atol=1e-11)
+    assert np.array_equal(w.addresses(), ref["addrs"][:, : o.W])
+    vw, gwv = w.estimates()
+    assert _close(vw, ref["val_w"], rtol=1e-10) 
+    assert _close(gwv, ref["grad_w"], rtol=1e-8, atol=1e-9 * max(1.0, np.abs(ref["grad_w"]).max()))
+    assert _close(r.val, ref["val"], rtol=1e-10) and r.walkers == nw and r.steps == nw * steps
+    # continuation (kinetic_vqmc!(res; steps)) keeps the stream and the estimators
+    r2 = w.run(p, 50, keep_acc=True)
+    ref2 = ao.kinetic_vqmc(p, ref["addrs"].copy(), 50, seed=seed, walker0=off, step0=steps)
+    assert np.array_equal(w.addresses(), ref2["addrs"][:, : o.W]) and r2.steps == nw * 50 and w.steps_done() == steps + 50
+
+
+@pytest.mark.parametrize("kind", list(KINDS))
+@pytest.mark.parametrize("N,M,u,v,t", [(5, 5, 1.0, 0.0, 0.1), (5, 5, 1.0, 1.0, 0.1), (4, 6, 2.0, 0.5, 1.0), (3, 2, 1.0, 0.4, 1.0)])
+def test_local_energy_evaluator_matches_oracle(gw, oracle_mod, kind, N, M, u, v, t):
+    o, ao, H, ans = _make(gw, oracle_mod, kind, N, M, u, v, t)
+    rng = np.random.default_rng(5)
+    p = _params(ao.P, rng, 0.5)
+    basis = o.build_basis()
+    ref_val, ref_grad = ao.lee_val_and_grad(basis, p)
+    for le in (gw.LocalEnergyEvaluator(H, ans, basis=basis[:, : o.W]), gw.LocalEnergyEvaluator(H, ans)):
+        assert le.dim == len(basis)
+        val, grad = le.val_and_grad(p)
+        assert _close(val, ref_val) and _close(le(p), ref_val)
+        assert _close(grad, ref_grad, atol=1e-12 * max(1.0, np.abs(ref_grad).max()))
+    le = gw.LocalEnergyEvaluator(H, ans, basis=basis[:, : o.W])
+    terms = le.terms(p)
+    for i in rng.integers(0, len(basis), 20):
+        ref = ao.lee_terms(basis[i], p)
+        assert _close(terms[i], ref, atol=1e-13 * np.abs(ref).max())
+    assert np.array_equal(le.states(), basis[:, : o.W])
+
+
+def test_ranked_sweep_bose12_relative_jastrow(gw, oracle_mod):
+    """BASELINE config 2 shape ({12,12}, 1,352,078 states) with a 6-parameter ansatz: ranked enumeration vs
+    the stored-basis sweep and the oracle on a subsample of per-state terms."""
+    N = M = 12
+    o, ao, H, ans = _make(gw, oracle_mod, "relative_jastrow", N, M, 2.0, 0.0, 1.0)
+    p = np.array([0.3, 0.05, 0.02, 0.01, 0.0, -0.01])
+    le = gw.LocalEnergyEvaluator(H, ans)
+    assert le.dim == 1352078
+    val, grad = le.val_and_grad(p)
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, le.dim, 40)
+    num = den = 0.0
+    for i in idx:
+        st = le.states(int(i), 1)[0]
+        t = le.terms(p, int(i), 1)[0]
+        ref = ao.lee_terms(np.pad(st, (0, 4 - o.W)), p)
+        assert _close(t, ref, atol=1e-13 * np.abs(ref).max())
+    # Gutzwiller limit: p = (g u / 2, 0, ...) reproduces the fast-path sweep exactly (C_0 = sum n^2 = 2 D/u + N)
+    g = 0.3331889106855026
+    pg = np.zeros(6)
+    pg[0] = g * 2.0 / 2
+    fast = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H))
+    assert abs(le(pg) - fast(g)) < 1e-10 * abs(fast(g))
+    assert np.isfinite(val) and np.all(np.isfinite(grad))
+
+
+def test_vqmc_energy_within_error_bars_and_sharding(gw, oracle_mod):
+    o, ao, H, ans = _make(gw, oracle_mod, "relative_jastrow", 6, 6, 2.0, 0.0, 1.0)
+    p = np.array([0.25, 0.05, 0.02])
+    le = gw.LocalEnergyEvaluator(H, ans)
+    exact, egrad = le.val_and_grad(p)
+    qmc = gw.KineticVQMC(H, ans, samples=4096 * 2000, walkers=4096, record=False, burn_in=200, estimator="pooled")
+    val, grad = qmc.val_and_grad(p)
+    r = qmc.result.last
+    assert abs(val - exact) < 5 * r.err + 1e-3
+    assert np.all(np.abs(grad - egrad) < 0.05 * max(1.0, np.abs(egrad).max()))
+    # walker trajectories depend on the global id only: two shards == one set
+    h = ans.handle()
+    a = gw.GenWalkers(h, 64, H.address.words, seed=9, global_offset=0)
+    b1 = gw.GenWalkers(h, 40, H.address.words, seed=9, global_offset=0)
+    b2 = gw.GenWalkers(h, 24, H.address.words, seed=9, global_offset=40)
+    a.run(p, 100); b1.run(p, 100); b2.run(p, 100)
+    assert np.array_equal(a.addresses(), np.concatenate([b1.addresses(), b2.addresses()]))
+    va, ga = a.estimates()
+    vb = np.concatenate([b1.estimates()[0], b2.estimates()[0]])
+    assert np.array_equal(va, vb)
+
+
+@pytest.mark.parametrize("onr", [(1, 1, 1, 1, 1), (1, 2, 1, 1)])
+def test_multinomial_is_exact_for_u0(gw, oracle_mod, onr):
+    """test/ansatz.jl:66-80"""
+    H = gw.HubbardReal1D(gw.BoseFS(onr), u=0.0)
+    o = oracle_mod.Oracle(sum(onr), len(onr), 0.0, 1.0)
+    ao = oracle_mod.AnsatzOracle(o, "multinomial", normalize=True)
+    basis = o.build_basis(o.from_onr(onr))
+    Hm = np.zeros((len(basis), len(basis)))
+    index = {int(b[0]): i for i, b in enumerate(basis)}
+    for i, b in enumerate(basis):
+        for new, me in o.offdiagonals(b):
+            Hm[index[int(new[0])], i] += me
+    e0 = np.linalg.eigvalsh(Hm)[0]
+    le = gw.LocalEnergyEvaluator(H, gw.MultinomialAnsatz(H, normalize=True), basis=basis[:, : o.W])
+    assert abs(le([0.5]) - e0) < 1e-10
+
+
+def test_amsgrad_relative_jastrow_and_fixed_params(gw):
+    """test/amsgrad.jl:23-57: KineticVQMC + RelativeJastrow reaches the LocalEnergyEvaluator optimum; DensityProfile with a
+    fixed parameter converges to the fixed value everywhere."""
+    H = gw.HubbardReal1D(gw.BoseFS(1, 1, 1, 1))
+    ans = gw.RelativeJastrowAnsatz(H)
+    le = gw.LocalEnergyEvaluator(H, ans)
+    ref = gw.amsgrad(le, [0.5, 0.5], maxiter=2000, α=0.02)
+    assert ref.converged
+    qmc = gw.KineticVQMC(H, ans, samples=2e6, walkers=1024, record=False, burn_in=100, estimator="pooled")
+    ams = gw.amsgrad(qmc, [0.5, 0.5], maxiter=100)
+    gd = gw.gradient_descent(qmc, [0.5, 0.5], maxiter=100)
+    assert abs(ams.value[-1] - ref.value[-1]) < 2e-2 and abs(gd.value[-1] - ref.value[-1]) < 2e-2
+    assert ams.param.shape == (101, 2) and ams.gradient.shape == (101, 2)
+    dp = gw.DensityProfileAnsatz(H)
+    led = gw.LocalEnergyEvaluator(H, dp)
+    rng = np.random.default_rng(1)
+    tr = gw.amsgrad(led, [rng.random(), rng.random(), 0.75, rng.random()], fix_params=(False, False, True, False),
+                    maxiter=1000)
+    assert np.all(np.abs(tr.param[-1] - 0.75) < 1e-1) and tr.param[-1][2] == 0.75
+
+
+def test_gen_errors(gw):
+    H = gw.HubbardReal1D(gw.near_uniform(4, 4))
+    ans = gw.RelativeJastrowAnsatz(H)
+    with pytest.raises(ValueError):
+        ans(H.address, [0.1])  # wrong number of parameters
+    big = gw.HubbardReal1D(gw.near_uniform(30, 30))
+    with pytest.raises(ValueError, match="256 parameters"):
+        gw.JastrowAnsatz(big).handle()
+    He = gw.ExtendedHubbardReal1D(gw.near_uniform(4, 4), v=0.5)
+    g = gw.GutzwillerAnsatz(He)
+    assert getattr(g, "generic", False) and isinstance(g, gw.GutzwillerAnsatz)
+    with pytest.raises(ValueError, match="gwz_gen"):
+        gw.Walkers(He.model(), 4, He.address.words)
