@@ -125,7 +125,10 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     gm.kind = kind;
     gm.B = m->B;
     gm.W = m->W;
-    gm.MPL = (M + 31) / 32;
+    {
+        const int need = (M + 31) / 32;  // modes per lane, rounded to the instantiated 1, 2, 4, 8
+        gm.MPL = need <= 1 ? 1 : (need <= 2 ? 2 : (need <= 4 ? 4 : 8));
+    }
     gm.MP = 32 * gm.MPL;
     gm.u = m->u;
     gm.v = m->v;

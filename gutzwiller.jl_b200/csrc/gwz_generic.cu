@@ -7,6 +7,15 @@
 
 namespace gwz {
 
+// runtime modes-per-lane -> compile-time (probe and sweep; the walker kernel is templated on it)
+#define GEN_MPL_SWITCH(mpl, CALL)       \
+    switch (mpl) {                      \
+        case 1: { constexpr int MPL_ = 1; CALL; } break; \
+        case 2: { constexpr int MPL_ = 2; CALL; } break; \
+        case 4: { constexpr int MPL_ = 4; CALL; } break; \
+        default: { constexpr int MPL_ = 8; CALL; } break; \
+    }
+
 // ------------------------------------------------------------------------------------------
 // layout conversion: unary addresses (AoS n x W) <-> occupation bytes (n x Mpad)
 // ------------------------------------------------------------------------------------------
@@ -85,7 +94,7 @@ gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
         if (!(e_loc || tau_out || grad_ratio || n_hops || rates || chosen || next_addr)) continue;
         double S_lane, E_lane;
         int nocc_lane;
-        gen_rates(gm, ws, lane, S_lane, E_lane, nocc_lane);
+        GEN_MPL_SWITCH(gm.MPL, (gen_rates<MPL_, false>(gm, ws, lane, S_lane, E_lane, nocc_lane)));
         __syncwarp();
         const double cum = warp_scan_incl(S_lane, lane);
         const double S = __shfl_sync(0xffffffffu, cum, 31);
@@ -127,7 +136,7 @@ gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
             double T = u * S;
             if (!(T < S)) T = __longlong_as_double(__double_as_longlong(S) - 1);
             int src, right;
-            gen_select(gm, ws, lane, S_lane, cum, T, src, right);
+            GEN_MPL_SWITCH(gm.MPL, (gen_select<MPL_>(gm, ws, lane, S_lane, cum, T, src, right)));
             if (chosen) {
                 int below = 0;
                 for (int k = lane; k < src; k += 32) below += ws.occ[k] > 0;
@@ -152,7 +161,7 @@ gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
 // ------------------------------------------------------------------------------------------
 // walkers: kinetic_vqmc!(st; steps) (qmc.jl:73-97), running sums of state.jl:42-49 per walker
 // ------------------------------------------------------------------------------------------
-template <int PPL>
+template <int PPL, int MPL>
 __global__ void __launch_bounds__(GEN_BLOCK)
 gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ PhiloxKeys pk, uint8_t* __restrict__ occ_g,
                   int Mpad, double* __restrict__ acc_g, size_t n, uint64_t goff, uint64_t step0, uint64_t steps,
@@ -213,6 +222,9 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
         const uint32_t c2 = (uint32_t)wid, c3 = (uint32_t)(wid >> 32);
         uint32_t rnd[4] = {0u, 0u, 0u, 0u};
         unsigned long long hops = 0ull;
+        int nocc = 0;
+        for (int k = lane; k < M; k += 32) nocc += ws.occ[k] > 0;
+        nocc = warp_sum_all(nocc);
 
         for (uint64_t k = 0; k < steps; ++k) {
             const uint64_t step = step0 + k;
@@ -232,11 +244,10 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
             double S_lane, E_lane;
             int nocc_lane;
-            gen_rates(gm, ws, lane, S_lane, E_lane, nocc_lane);
+            gen_rates<MPL, false>(gm, ws, lane, S_lane, E_lane, nocc_lane);
             const double cum = warp_scan_incl(S_lane, lane);
             const double S = __shfl_sync(0xffffffffu, cum, 31);
             const double Etot = warp_sum_all(E_lane);
-            const int nocc = warp_sum_all(nocc_lane);
             const double tau = 1.0 / S;
             const double eloc = gm.u * (double)reg + gm.v * (double)ext - gm.t * Etot;
             bad |= !(tau < 1.0e300);
@@ -260,8 +271,9 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             double T = u01 * S;
             if (!(T < S)) T = __longlong_as_double(__double_as_longlong(S) - 1);
             int src, right;
-            gen_select(gm, ws, lane, S_lane, cum, T, src, right);
+            gen_select<MPL>(gm, ws, lane, S_lane, cum, T, src, right);
             const int dst = right ? (src + 1 == M ? 0 : src + 1) : (src == 0 ? M - 1 : src - 1);
+            nocc += (ws.occ[dst] == 0) - (ws.occ[src] == 1);  // occupied modes, carried exactly
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
                 const int p = lane + 32 * q;
@@ -270,8 +282,15 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             reg += ws.occ[dst] - ws.occ[src] + 1;
             ext += gen_dext(gm, ws, src, dst);
             __syncwarp();  // every lane has read the pre-hop occupations
-            for (int m = lane; m < M; m += 32)
-                ws.V[m] += __ldg(gm.Qt + (size_t)dst * M + m) - __ldg(gm.Qt + (size_t)src * M + m);
+            {
+                const double* qd = gm.Qt + (size_t)dst * M;
+                const double* qs = gm.Qt + (size_t)src * M;
+#pragma unroll
+                for (int q = 0; q < MPL; ++q) {
+                    const int m = lane + 32 * q;
+                    if (m < M) ws.V[m] += __ldg(qd + m) - __ldg(qs + m);
+                }
+            }
             if (lane == 0) {
                 ws.occ[src] -= 1;
                 ws.occ[dst] += 1;
@@ -384,7 +403,7 @@ gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
         gen_totals(gm, ws, lane, reg, ext, lgsum);
         double S_lane, E_lane;
         int nocc_lane;
-        gen_rates(gm, ws, lane, S_lane, E_lane, nocc_lane);
+        GEN_MPL_SWITCH(gm.MPL, (gen_rates<MPL_, true>(gm, ws, lane, S_lane, E_lane, nocc_lane)));
         __syncwarp();
         const double Etot = warp_sum_all(E_lane);
         const double D = gm.u * (double)reg + gm.v * (double)ext;
@@ -497,14 +516,24 @@ cudaError_t launch_gen_probe(const GenProbeLaunch& L, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <int PPL>
-static cudaError_t gen_walker_launch(const GenWalkerLaunch& L, cudaStream_t s) {
+template <int PPL, int MPL>
+static cudaError_t gen_walker_launch2(const GenWalkerLaunch& L, cudaStream_t s) {
     const size_t smem = gen_smem(L.gm);
-    if (cudaError_t e = gen_prepare(gen_walker_kernel<PPL>, smem)) return e;
-    gen_walker_kernel<PPL><<<L.grid, GEN_BLOCK, smem, s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n, L.global_offset,
+    if (cudaError_t e = gen_prepare(gen_walker_kernel<PPL, MPL>, smem)) return e;
+    gen_walker_kernel<PPL, MPL><<<L.grid, GEN_BLOCK, smem, s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n, L.global_offset,
                                                          L.step0, L.steps, L.accumulate, L.reset_acc, L.shift, L.partials,
                                                          L.rec_tau, L.rec_eloc, L.rec_addr, L.err_flag);
     return cudaGetLastError();
+}
+template <int PPL>
+static cudaError_t gen_walker_launch(const GenWalkerLaunch& L, cudaStream_t s) {
+    switch (L.gm.MPL) {
+        case 1: return gen_walker_launch2<PPL, 1>(L, s);
+        case 2: return gen_walker_launch2<PPL, 2>(L, s);
+        case 4: return gen_walker_launch2<PPL, 4>(L, s);
+        case 8: return gen_walker_launch2<PPL, 8>(L, s);
+        default: return cudaErrorInvalidValue;
+    }
 }
 cudaError_t launch_gen_walkers(const GenWalkerLaunch& L, cudaStream_t s) {
     switch (gen_ppl(L.gm.P)) {

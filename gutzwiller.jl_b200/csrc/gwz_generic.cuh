@@ -199,10 +199,17 @@ __device__ __forceinline__ double gen_dfeature(const GenModel& gm, const GenWarp
         case GEN_MULTINOMIAL: return gm.logtab[nj + 1] - gm.logtab[ni];
         case GEN_DENSITY_PROFILE: return (double)((p == j) - (p == i));
         case GEN_RELATIVE_JASTROW: {
+            // C_d(n') - C_d(n) = n_{j+d} + n_{j-d} - n_{i+d} - n_{i-d} + 2[d=0] - [d = i-j] - [d = j-i]  (mod M)
             const int M = gm.M, d = p;
-            auto wrap = [M](int x) { return x >= M ? x - M : (x < 0 ? x + M : x); };
-            int r = ws.occ[wrap(j + d)] + ws.occ[wrap(j - d)] - ws.occ[wrap(i + d)] - ws.occ[wrap(i - d)];
-            r += 2 * (d == 0) - (d == wrap(i - j)) - (d == wrap(j - i));
+            int jp = j + d, jm = j - d, ip = i + d, im = i - d;
+            jp -= (jp >= M) ? M : 0;
+            ip -= (ip >= M) ? M : 0;
+            jm += (jm < 0) ? M : 0;
+            im += (im < 0) ? M : 0;
+            int dij = i - j, dji = j - i;
+            dij += (dij < 0) ? M : 0;
+            dji += (dji < 0) ? M : 0;
+            const int r = ws.occ[jp] + ws.occ[jm] - ws.occ[ip] - ws.occ[im] + 2 * (d == 0) - (d == dij) - (d == dji);
             return (double)r;
         }
         default: {
@@ -216,13 +223,15 @@ __device__ __forceinline__ double gen_dfeature(const GenModel& gm, const GenWarp
 
 // hop rates of the modes this lane owns, in reference order; lane sums of the rates, of
 // sqrt(n_src (n_dst+1)) * rate, and the number of occupied modes
+template <int MPL, bool STORE_MR>
 __device__ __forceinline__ void gen_rates(const GenModel& gm, const GenWarp& ws, int lane, double& S_lane,
                                           double& E_lane, int& nocc_lane) {
     const int M = gm.M;
     double S = 0.0, E = 0.0;
     int nocc = 0;
-    for (int q = 0; q < gm.MPL; ++q) {
-        const int k = lane * gm.MPL + q;
+#pragma unroll
+    for (int q = 0; q < MPL; ++q) {
+        const int k = lane * MPL + q;
         if (k < M) {
             double rr = 0.0, rl = 0.0, mrr = 0.0, mrl = 0.0;
             const int n = ws.occ[k];
@@ -250,8 +259,10 @@ __device__ __forceinline__ void gen_rates(const GenModel& gm, const GenWarp& ws,
             }
             ws.rate[2 * k] = rr;
             ws.rate[2 * k + 1] = rl;
-            ws.mr[2 * k] = -gm.t * mrr;
-            ws.mr[2 * k + 1] = -gm.t * mrl;
+            if (STORE_MR) {
+                ws.mr[2 * k] = -gm.t * mrr;
+                ws.mr[2 * k + 1] = -gm.t * mrl;
+            }
         }
     }
     S_lane = S;
@@ -261,6 +272,7 @@ __device__ __forceinline__ void gen_rates(const GenModel& gm, const GenWarp& ws,
 
 // pick_random_from_cumsum (qmc.jl:52-61) over the hops in reference order: first hop whose inclusive
 // running sum exceeds T = u01 * S.  Returns the source mode and direction (warp-uniform).
+template <int MPL>
 __device__ __forceinline__ void gen_select(const GenModel& gm, const GenWarp& ws, int lane, double S_lane, double cum_incl,
                                            double T, int& src, int& right) {
     const unsigned hit = __ballot_sync(0xffffffffu, (T < cum_incl) && (S_lane > 0.0));
@@ -270,9 +282,10 @@ __device__ __forceinline__ void gen_select(const GenModel& gm, const GenWarp& ws
     int mode = -1, dir = 1;
     if (lane == sel_lane) {
         double acc = cum_incl - S_lane;
-        for (int q = 0; q < gm.MPL && mode < 0; ++q) {
-            const int k = lane * gm.MPL + q;
-            if (k >= gm.M) break;
+#pragma unroll
+        for (int q = 0; q < MPL; ++q) {
+            const int k = lane * MPL + q;
+            if (k >= gm.M || mode >= 0) break;
             const double rr = ws.rate[2 * k], rl = ws.rate[2 * k + 1];
             if (rr > 0.0 || rl > 0.0) {
                 acc += rr;
@@ -290,8 +303,8 @@ __device__ __forceinline__ void gen_select(const GenModel& gm, const GenWarp& ws
             }
         }
         if (mode < 0) {  // clamp: last hop of this lane
-            for (int q = gm.MPL - 1; q >= 0 && mode < 0; --q) {
-                const int k = lane * gm.MPL + q;
+            for (int q = MPL - 1; q >= 0 && mode < 0; --q) {
+                const int k = lane * MPL + q;
                 if (k < gm.M && (ws.rate[2 * k] > 0.0 || ws.rate[2 * k + 1] > 0.0)) {
                     mode = k;
                     dir = 0;

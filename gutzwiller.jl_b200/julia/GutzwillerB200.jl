@@ -15,6 +15,7 @@ using Rimu
 using StaticArrays
 
 export GPUContext, GPUKineticVQMCResult, GPUKineticVQMC, GPULocalEnergyEvaluator
+export GPUAnsatz, GPUGenericVQMC, GPUGenericLocalEnergyEvaluator
 export kinetic_vqmc, kinetic_vqmc!, val_and_grad, val_err_and_grad, amsgrad, gradient_descent
 
 const LIB = get(ENV, "GUTZWILLER_B200_LIB",
@@ -307,5 +308,130 @@ function _descend(f, p0; use_amsgrad, maxiter=100, α=0.01, β1=0.1, β2=0.01, e
 end
 amsgrad(f::Union{GPUKineticVQMC,GPULocalEnergyEvaluator}, p0; kw...) = _descend(f, p0; use_amsgrad=1, kw...)
 gradient_descent(f::Union{GPUKineticVQMC,GPULocalEnergyEvaluator}, p0; kw...) = _descend(f, p0; use_amsgrad=0, kw...)
+
+# ------------------------------------------------------------------------------------------
+# Ansatz-generic engine (gwz_gen_* / gwz_gwalkers_* / gwz_gsweep_*): the reference's other
+# single-component ansaetze and Rimu's ExtendedHubbardReal1D.  P = num_parameters(ansatz).
+#   src/ansatz/{extgutzwiller,multinomial,densityprofile,jastrow}.jl
+# ------------------------------------------------------------------------------------------
+ansatz_kind(::GutzwillerAnsatz) = Cint(0)
+ansatz_kind(::ExtendedGutzwillerAnsatz) = Cint(1)
+ansatz_kind(::MultinomialAnsatz) = Cint(2)
+ansatz_kind(::DensityProfileAnsatz) = Cint(3)
+ansatz_kind(::RelativeJastrowAnsatz) = Cint(4)
+ansatz_kind(::JastrowAnsatz) = Cint(5)
+ansatz_normalize(a::MultinomialAnsatz) = Cint(a.normalization != 1.0)    # multinomial.jl:22-31
+ansatz_normalize(_) = Cint(0)
+
+function GPUModel(H::ExtendedHubbardReal1D, ctx::GPUContext=default_context())
+    addr = starting_address(H)
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_model_create_ext_hubbard1d, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cdouble, Cdouble, Cdouble, Ref{Ptr{Cvoid}}),
+                ctx.ptr, num_particles(addr), num_modes(addr), H.u, H.v, H.t, r))
+    m = GPUModel(r[], ctx, num_particles(addr), num_modes(addr), cld(num_particles(addr) + num_modes(addr) - 1, 64))
+    finalizer(x -> ccall((:gwz_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), m)
+    return m
+end
+
+mutable struct GPUAnsatz
+    ptr::Ptr{Cvoid}
+    model::GPUModel
+    np::Int
+end
+function GPUAnsatz(H, ansatz, ctx::GPUContext=default_context())
+    model = GPUModel(H, ctx)
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_ansatz_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                model.ptr, ansatz_kind(ansatz), ansatz_normalize(ansatz), r))
+    a = GPUAnsatz(r[], model, num_parameters(ansatz))
+    finalizer(x -> ccall((:gwz_ansatz_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), a)
+    return a
+end
+
+struct GenResult                       # gwz_gen_result
+    val::Cdouble; err::Cdouble; pooled_val::Cdouble; pooled_var::Cdouble; total_time::Cdouble
+    walkers::UInt64; steps::UInt64; hops::UInt64; kernel_ms::Cfloat; np::Int32
+end
+
+mutable struct GPUGenericVQMC{H,A}      # KineticVQMC(H, ansatz; samples, walkers, steps) (wrapper.jl:45-63)
+    hamiltonian::H
+    ansatz::A
+    gpu::GPUAnsatz
+    walkers_ptr::Ptr{Cvoid}
+    walkers::Int
+    steps::Int
+    last::GenResult
+    grad::Vector{Float64}
+    grad_err::Vector{Float64}
+end
+function GPUGenericVQMC(H, ansatz; samples=1e6, walkers=2^16, steps=round(Int, samples / walkers),
+                        seed::UInt64=0x9E3779B97F4A7C15, ctx=default_context())
+    gpu = GPUAnsatz(H, ansatz, ctx)
+    start = address_words(gpu.model, starting_address(H))
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_gwalkers_create, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Ptr{UInt64}, UInt64, Ref{Ptr{Cvoid}}),
+                gpu.ptr, walkers, 0, start, seed, r))
+    np = gpu.np
+    q = GPUGenericVQMC(H, ansatz, gpu, r[], Int(walkers), Int(steps),
+                       GenResult(0, 0, 0, 0, 0, 0, 0, 0, 0, np), zeros(np), zeros(np))
+    finalizer(x -> ccall((:gwz_gwalkers_destroy, LIB), Cint, (Ptr{Cvoid},), x.walkers_ptr), q)
+    return q
+end
+function _run!(q::GPUGenericVQMC, params, steps::Integer; keep::Bool=false, burn_in::Integer=0)
+    p = collect(Float64, params)
+    length(p) == q.gpu.np || throw(ArgumentError("expected $(q.gpu.np) parameters"))
+    res = Ref(q.last)
+    check(ccall((:gwz_gen_vqmc_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, UInt64, UInt64, Cuint, Ref{GenResult}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                q.walkers_ptr, p, steps, burn_in, keep ? GWZ_RUN_KEEP_ACC : Cuint(0), res, q.grad, q.grad_err, C_NULL))
+    q.last = res[]
+    return q
+end
+(q::GPUGenericVQMC)(params; samples=q.steps * q.walkers, steps=samples ÷ q.walkers) = _run!(q, params, steps).last.val
+function val_and_grad(q::GPUGenericVQMC, params; samples=q.steps * q.walkers, steps=samples ÷ q.walkers)
+    _run!(q, params, steps)
+    return q.last.val, SVector{q.gpu.np,Float64}(q.grad)                                       # wrapper.jl:90-97
+end
+function val_err_and_grad(q::GPUGenericVQMC, params; samples=q.steps * q.walkers, steps=samples ÷ q.walkers)
+    _run!(q, params, steps)
+    return q.last.val, q.last.err, SVector{q.gpu.np,Float64}(q.grad)                           # wrapper.jl:98-105
+end
+
+mutable struct GPUGenericLocalEnergyEvaluator{H,A}   # LocalEnergyEvaluator(H, ansatz; basis) (localenergy.jl:81-88)
+    hamiltonian::H
+    ansatz::A
+    gpu::GPUAnsatz
+    sweep::Ptr{Cvoid}
+end
+function GPUGenericLocalEnergyEvaluator(H, ansatz; basis=nothing, ctx=default_context())
+    gpu = GPUAnsatz(H, ansatz, ctx)
+    r = Ref{Ptr{Cvoid}}()
+    if basis === nothing
+        check(ccall((:gwz_gsweep_create, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}, UInt64, UInt64, UInt64, Ref{Ptr{Cvoid}}),
+                    gpu.ptr, C_NULL, 0, 0, 0, r))
+    else
+        words = reduce(vcat, (address_words(gpu.model, a) for a in basis))
+        check(ccall((:gwz_gsweep_create, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}, UInt64, UInt64, UInt64, Ref{Ptr{Cvoid}}),
+                    gpu.ptr, words, length(basis), 0, 0, r))
+    end
+    le = GPUGenericLocalEnergyEvaluator(H, ansatz, gpu, r[])
+    finalizer(x -> ccall((:gwz_gsweep_destroy, LIB), Cint, (Ptr{Cvoid},), x.sweep), le)
+    return le
+end
+function val_and_grad(le::GPUGenericLocalEnergyEvaluator, params)                              # localenergy.jl:94-129
+    p = collect(Float64, params); val = Ref(0.0); grad = zeros(le.gpu.np)
+    check(ccall((:gwz_gsweep_val_and_grad, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}),
+                le.sweep, p, val, grad))
+    return val[], SVector{le.gpu.np,Float64}(grad)
+end
+function (le::GPUGenericLocalEnergyEvaluator)(params)                                          # localenergy.jl:131-155
+    p = collect(Float64, params); val = Ref(0.0)
+    check(ccall((:gwz_gsweep_val_and_grad, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}),
+                le.sweep, p, val, C_NULL))
+    return val[]
+end
+# amsgrad / gradient_descent of the reference (amsgrad.jl:105-263) are generic over objectives with
+# val_and_grad / val_err_and_grad, so they drive GPUGenericVQMC and GPUGenericLocalEnergyEvaluator unmodified.
 
 end # module
