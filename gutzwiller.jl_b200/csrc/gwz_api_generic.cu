@@ -418,7 +418,7 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
     std::memset(&K, 0, sizeof(K));
     if (int rc = upload_params(a, params, &K.gm)) return rc;
     int grid = 0;
-    GWZ_CUDA(gen_grid(K.gm, w->n, c->prop.multiProcessorCount, &grid));
+    GWZ_CUDA(gen_walker_grid(K.gm, w->n, c->prop.multiProcessorCount, &grid));
     const size_t rows = (size_t)grid * GEN_WARPS;
     if (rows > w->partials_rows) {
         if (w->d_partials) cudaFree(w->d_partials);
@@ -629,7 +629,7 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     std::memset(&K, 0, sizeof(K));
     if (int rc = upload_params(a, params, &K.gm)) return rc;
     int grid = 0;
-    GWZ_CUDA(gen_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
+    GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
     const size_t rows = (size_t)grid * GEN_WARPS;
     if (rows > s->partials_rows) {
         if (s->d_partials) cudaFree(s->d_partials);
@@ -686,7 +686,7 @@ static int gsweep_terms_impl(gwz_gsweep* s, const double* params, uint64_t first
     if (out) GWZ_CUDA(d_out.alloc(count * L));
     if (states) GWZ_CUDA(d_st.alloc(count * W));
     int grid = 0;
-    GWZ_CUDA(gen_grid(K.gm, (size_t)count, c->prop.multiProcessorCount, &grid));
+    GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)count, c->prop.multiProcessorCount, &grid));
     const size_t rows = (size_t)grid * GEN_WARPS;
     K.basis = s->d_basis;
     K.dim = s->dim;

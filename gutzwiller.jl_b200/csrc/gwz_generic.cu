@@ -161,8 +161,11 @@ gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
 // ------------------------------------------------------------------------------------------
 // walkers: kinetic_vqmc!(st; steps) (qmc.jl:73-97), running sums of state.jl:42-49 per walker
 // ------------------------------------------------------------------------------------------
+#ifndef GWZ_GEN_MIN_BLOCKS
+#define GWZ_GEN_MIN_BLOCKS 24
+#endif
 template <int PPL, int MPL>
-__global__ void __launch_bounds__(GEN_BLOCK)
+__global__ void __launch_bounds__(GEN_BLOCK, PPL <= 2 ? GWZ_GEN_MIN_BLOCKS : (PPL == 4 ? 12 : 8))
 gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ PhiloxKeys pk, uint8_t* __restrict__ occ_g,
                   int Mpad, double* __restrict__ acc_g, size_t n, uint64_t goff, uint64_t step0, uint64_t steps,
                   int accumulate, int reset_acc, const double* __restrict__ shift, double* __restrict__ partials,
@@ -170,7 +173,7 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                   int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const GenWarp ws(smem_raw, gm.MP, warp);
+    const GenWarp ws(smem_raw, 32 * MPL, warp);  // compile-time slice layout: offsets fold into the LDS/STS immediates
     const size_t gwarp = (size_t)blockIdx.x * GEN_WARPS + warp, nwarps = (size_t)gridDim.x * GEN_WARPS;
     const int M = gm.M, P = gm.P;
     const int AW = 3 + 2 * P;  // per-walker sums in HBM: st, stE, stEE, stG[P], stGE[P]
@@ -482,16 +485,47 @@ int gen_ppl(int P) {
     return need <= 1 ? 1 : (need <= 2 ? 2 : (need <= 4 ? 4 : (need <= 8 ? 8 : 0)));
 }
 
-cudaError_t gen_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
-    // one resident wave: registers and the small per-warp smem slices allow >= 4 CTAs per SM
+// one resident wave, from the occupancy of the kernel that will run
+template <typename K>
+static cudaError_t gen_grid_for(K kernel, const GenModel& gm, size_t n, int sm_count, int* grid) {
     const size_t smem = gen_smem(gm);
-    int per_sm = (int)((200 * 1024) / (smem ? smem : 1));
-    per_sm = per_sm > 6 ? 6 : (per_sm < 1 ? 1 : per_sm);
+    if (cudaError_t e = gen_prepare(kernel, smem)) return e;
+    int per_sm = 0;
+    if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GEN_BLOCK, smem)) return e;
+    if (per_sm < 1) per_sm = 1;
     const size_t resident = (size_t)per_sm * sm_count;
     const size_t need = (n + GEN_WARPS - 1) / GEN_WARPS;
     *grid = (int)(need < resident ? need : resident);
     if (*grid < 1) *grid = 1;
     return cudaSuccess;
+}
+template <int PPL>
+static cudaError_t gen_walker_grid_ppl(const GenModel& gm, size_t n, int sm_count, int* grid) {
+    switch (gm.MPL) {
+        case 1: return gen_grid_for(gen_walker_kernel<PPL, 1>, gm, n, sm_count, grid);
+        case 2: return gen_grid_for(gen_walker_kernel<PPL, 2>, gm, n, sm_count, grid);
+        case 4: return gen_grid_for(gen_walker_kernel<PPL, 4>, gm, n, sm_count, grid);
+        case 8: return gen_grid_for(gen_walker_kernel<PPL, 8>, gm, n, sm_count, grid);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t gen_walker_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
+    switch (gen_ppl(gm.P)) {
+        case 1: return gen_walker_grid_ppl<1>(gm, n, sm_count, grid);
+        case 2: return gen_walker_grid_ppl<2>(gm, n, sm_count, grid);
+        case 4: return gen_walker_grid_ppl<4>(gm, n, sm_count, grid);
+        case 8: return gen_walker_grid_ppl<8>(gm, n, sm_count, grid);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t gen_sweep_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
+    switch (gen_ppl(gm.P)) {
+        case 1: return gen_grid_for(gen_sweep_kernel<1>, gm, n, sm_count, grid);
+        case 2: return gen_grid_for(gen_sweep_kernel<2>, gm, n, sm_count, grid);
+        case 4: return gen_grid_for(gen_sweep_kernel<4>, gm, n, sm_count, grid);
+        case 8: return gen_grid_for(gen_sweep_kernel<8>, gm, n, sm_count, grid);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_gen_unary_to_occ(const uint64_t* addr, size_t n, const GenModel& gm, int Mpad, uint8_t* occ,

@@ -33,7 +33,7 @@ enum GenKind {
     GEN_JASTROW = 5
 };
 
-constexpr int GEN_BLOCK = 128;               // 4 warps per CTA
+constexpr int GEN_BLOCK = 32;                // one warp per CTA: the shared-memory slice sits at fixed offsets
 constexpr int GEN_WARPS = GEN_BLOCK / 32;
 constexpr int GEN_HEAD = 8;                  // scalar slots of the accumulator vector
 constexpr int GEN_REFRESH = 256;             // steps between from-scratch re-evaluations of V and F
