@@ -317,6 +317,21 @@ def extra_workloads(gw, np):
         dt = (time.perf_counter() - t0) / reps
         out[f"cfg2_sweep_bose{n}"] = {"states": le.dim, "states_per_s": le.dim / dt, "ms_per_sweep": dt * 1e3,
                                       "kernel_ms": le.last_kernel_ms(), "val": v, "grad": float(g[0])}
+    # ansatz-generic engine: RelativeJastrowAnsatz, 25 parameters, BoseFS{50,50}
+    H = gw.HubbardReal1D(gw.near_uniform(50, 50), u=2.0)
+    ans = gw.RelativeJastrowAnsatz(H)
+    p = np.zeros(ans.N_PARAMS)
+    p[0], p[1:] = 0.33, 0.005
+    q = gw.KineticVQMC(H, ans, walkers=1 << 16, steps=64, record=False)
+    for _ in range(3):
+        gw.val_and_grad(q, p)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        gw.val_and_grad(q, p)
+    dt = (time.perf_counter() - t0) / 5
+    out["generic_relative_jastrow_bose50_2^16walkers_64steps"] = {
+        "walker_steps_per_s": q.steps * q.walkers / dt, "ms_per_call": dt * 1e3, "kernel_ms": q.result.last.kernel_ms,
+        "parameters": ans.N_PARAMS}
     return out
 
 

@@ -40,6 +40,29 @@ def check(r, ref, acc, ref_acc, tag):
     print(f"[{tag}] OK val={r.val:.12f} grad={r.grad[0]:.9f} pooled={r.pooled_val:.12f} sweep_num={acc[0]:.12e}", flush=True)
 
 
+def check_generic(rank, world):
+    """The ansatz-generic engine under the same sharding: 8 + 4P accumulators in one all-reduce per run."""
+    Hg = gw.HubbardReal1D(gw.near_uniform(20, 20), u=U)
+    ans = gw.RelativeJastrowAnsatz(Hg)
+    p = np.linspace(0.3, 0.01, ans.N_PARAMS)
+    total, steps = 1 << 12, 100
+    res = gw.kinetic_vqmc(Hg, ans, p, walkers=total, steps=steps, seed=77, record=False)
+    ctx = gw.Context(int(os.environ.get("LOCAL_RANK", "0")))  # fresh context without communicator
+    w = gw.GenWalkers(ans.handle(ctx), total, Hg.address.words, seed=77)
+    ref = w.run(p, steps)
+    r = res.last
+    assert r.walkers == total and r.steps == total * steps and r.hops == ref.hops, (r.walkers, r.steps, r.hops, ref.hops)
+    assert abs(r.val - ref.val) <= 1e-12 * abs(ref.val) and abs(r.pooled_val - ref.pooled_val) <= 1e-12 * abs(ref.pooled_val)
+    assert np.all(np.abs(r.grad - ref.grad) <= 1e-9 * np.abs(ref.grad).max())
+    H8 = gw.HubbardReal1D(gw.near_uniform(8, 8), u=U)
+    a8 = gw.RelativeJastrowAnsatz(H8)
+    p8 = np.array([0.3, 0.05, 0.02, 0.01])
+    v, g = gw.LocalEnergyEvaluator(H8, a8).val_and_grad(p8)           # rank-range shards + all-reduce
+    v1, g1 = gw.LocalEnergyEvaluator(H8, a8, ctx=ctx).val_and_grad(p8)  # one device, whole range
+    assert abs(v - v1) <= 1e-12 * abs(v1) and np.all(np.abs(g - g1) <= 1e-11 * np.abs(g1).max())
+    print(f"[rank {rank}/{world}] generic OK val={r.val:.12f} grad0={r.grad[0]:.9f} sweep={v:.12f}", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--single-process", type=int, default=0)
@@ -65,6 +88,7 @@ def main():
     acc = gw.LocalEnergyEvaluator(H12, gw.GutzwillerAnsatz(H12)).accumulators(0.4)  # rank-range shards + all-reduce
     ref, ref_acc = reference_single_gpu(int(os.environ.get("LOCAL_RANK", "0")))
     check(res.last, ref, acc, ref_acc, f"rank {rank}/{world}")
+    check_generic(rank, world)
     import torch.distributed as dist
     dist.barrier()
     dist.destroy_process_group()

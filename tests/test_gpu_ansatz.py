@@ -21,6 +21,7 @@ SHAPES = [  # N, M, u, v, t
     (3, 2, 1.0, 0.4, 1.0),     # M = 2: both neighbours are the same mode
     (12, 12, 2.0, 0.0, 1.0),
     (40, 37, 2.0, 0.25, 1.0),  # two modes per lane, two 64-bit words
+    (120, 131, 2.0, 0.1, 0.5),  # eight modes per lane, four words, up to 131 parameters
 ]
 
 
@@ -73,11 +74,14 @@ def test_eval_and_probe_match_oracle(gw, oracle_mod, kind, N, M, u, v, t):
         assert _close(val[i], v1) and _close(grad[i], g1, atol=1e-13 * abs(v1) * max(1.0, np.abs(g1 / v1).max()))
         ks = ao.kinetic_sample(a, p, float(u01[i]))
         assert out["n_hops"][i] == ks["n_hops"]
-        assert _close(out["e_loc"][i], ks["eloc"], atol=1e-12)
-        assert _close(out["residence_time"][i], ks["tau"])
+        # E_loc = D - t * sum(...) cancels for clumped states: the tolerance is relative to the terms, and the
+        # reference's own psi2/psi1 through absolute amplitudes carries ~|log psi| * eps
+        scale = max(1.0, abs(ao.diagonal_element(a)), abs(np.log(abs(v1))))
+        assert _close(out["e_loc"][i], ks["eloc"], atol=1e-12 * scale)
+        assert _close(out["residence_time"][i], ks["tau"], rtol=1e-12 * scale)
         assert _close(out["grad_ratio"][i], ks["grad"], atol=1e-12)
         rates = ao.hop_rates(a, p)
-        assert _close(out["rates"][i][: len(rates)], rates) and np.all(out["rates"][i][len(rates):] == 0)
+        assert _close(out["rates"][i][: len(rates)], rates, rtol=1e-12 * scale) and np.all(out["rates"][i][len(rates):] == 0)
         # the move: same hop unless u01*S falls within rounding distance of a boundary of the cumulative sums
         cs = ks["cumsum"]
         T = u01[i] * cs[-1]
