@@ -944,6 +944,12 @@ extern "C" int gwz_sweep_dim(const gwz_sweep* s, uint64_t* dim) {
     return GWZ_OK;
 }
 
+// GWZ_SWEEP_SYM=0: evaluate every state of a ranked sweep instead of one representative per translation orbit
+static bool sweep_sym_enabled() {
+    const char* e = std::getenv("GWZ_SWEEP_SYM");
+    return !(e && e[0] == '0');
+}
+
 static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     gwz_model* m = s->m;
     gwz_context* c = m->ctx;
@@ -959,6 +965,7 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     L.rank_begin = s->rank_begin;
     L.binom = s->d_binom;
     L.with_grad = 1;
+    L.symmetric = sweep_sym_enabled() ? 1 : 0;
     L.partials = s->d_partials;
     L.grid = s->grid;
     L.chunk = s->chunk;

@@ -686,6 +686,10 @@ __device__ __forceinline__ uint64_t next_same_popcount(uint64_t x) {
     return (t + 1) | (((~t & (0 - ~t)) - 1) >> (__ffsll((long long)x)));
 }
 
+__device__ __forceinline__ uint32_t next_same_popcount32(uint32_t x) {
+    const uint32_t t = x | (x - 1u);
+    return (t + 1u) | (((~t & (0u - ~t)) - 1u) >> (__ffs((int)x)));
+}
 // warp / block reductions of doubles (deterministic order)
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -107,6 +107,7 @@ struct SweepLaunch {
     uint64_t rank_begin;    // first rank (ranked mode)
     const uint64_t* binom;  // [65][65] binomial table in HBM (ranked mode)
     int with_grad;
+    int symmetric;  // ranked mode: evaluate one representative per translation orbit (N+M <= 64)
     double* partials;  // [grid][4]
     int grid;
     uint64_t chunk;  // consecutive ranks per thread (ranked mode)

@@ -157,6 +157,115 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
     }
 }
 
+// Translation-symmetry-reduced ranked sweep.  HubbardReal1D is a periodic chain and the Gutzwiller amplitude only
+// depends on the multiset of occupations, so the four per-state terms are identical for the M cyclic shifts of an
+// occupation vector: evaluate one representative per orbit and weight it with the orbit size.  On the unary string
+// closed by a virtual separator (L = N+M bits, bit L-1 = 0) a mode shift is a cyclic rotation that brings a 0 to the
+// top; the representative is the largest rotation.  Every thread still steps through its ranks (Gosper) and tests
+// each state (a few rotations on average, early exit); representatives are compacted through a per-warp queue so
+// that the expensive evaluation always runs with full warps.  Needs N+M <= 64.
+// T = uint32_t when L <= 32 (half the instructions), else uint64_t.  The largest rotation has the longest run of
+// ones at the top: reject as soon as a longer run exists anywhere (t+1 shift-and steps), then compare only against
+// the rotations that bring an equally long run to the top (ties).
+template <typename T>
+__device__ __forceinline__ bool orbit_representative(T e, int L, T maskL, int M, int& mult) {
+    constexpr int BITS = 8 * (int)sizeof(T);
+    // t = ones directly below the top separator = occupation of mode M (t <= L-2 < BITS)
+    const T inv = ~(T)(e << (BITS - L + 1));  // bit L-2 of e moved to the top, zeros shifted in below
+    const int t = (sizeof(T) == 8) ? __clzll((long long)inv) : __clz((int)inv);
+    // ge[k] has a 1 at the bottom bit of every run of >= k ones; build ge_t and ge_{t+1}
+    T ge = ~(T)0;
+    for (int k = 0; k < t; ++k) ge &= (T)(e >> k);
+    if (ge & (T)(e >> t) & maskL) return false;  // a run of >= t+1 ones: that rotation is larger
+    // zeros (below the top) that sit directly above a run of exactly t ones: bottoms of such runs are ge & e..., the zero
+    // above a run whose bottom is at position b is at b + t
+    T ties = (T)((t == 0 ? ~e : (T)(ge << t)) & ~e) & (T)(maskL >> 1);
+    int same = 0;
+    while (ties) {
+        const int z = (sizeof(T) == 8) ? (__ffsll((long long)ties) - 1) : (__ffs((int)ties) - 1);
+        ties &= ties - 1;
+        const T r = (T)(((T)(e >> (z + 1)) | (T)(e << (L - 1 - z))) & maskL);
+        if (r > e) return false;
+        same += (r == e);
+    }
+    mult = M / (same + 1);
+    return true;
+}
+
+template <int NW, int KC>
+__global__ void __launch_bounds__(SWEEP_BLOCK)
+sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, uint64_t dim,
+                 uint64_t rank_begin, uint64_t chunk, const uint64_t* __restrict__ binom, double* __restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepScratch<NW, KC> sc(smem_raw, dm.N);
+    sc.fill_exptab(dm.N, tb.c);
+    __shared__ uint64_t qx[SWEEP_BLOCK / 32][64];
+    __shared__ int qm[SWEEP_BLOCK / 32][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    const int L = dm.N + dm.M;
+    const uint64_t maskL = (L >= 64) ? ~0ull : ((1ull << L) - 1ull);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int qn = 0;  // warp-uniform fill of the queue
+    auto evaluate = [&](uint64_t x, double w) {
+        uint32_t a[NW];
+        a[0] = (uint32_t)x;
+        if (NW > 1) a[1] = (uint32_t)(x >> 32);
+#pragma unroll
+        for (int i = 2; i < NW; ++i) a[i] = 0u;
+        double num, den, ng, dg;
+        state_terms<NW, KC>(a, dm, tb, sc, num, den, ng, dg);
+        s0 = fma(w, num, s0);
+        s1 = fma(w, den, s1);
+        s2 = fma(w, ng, s2);
+        s3 = fma(w, dg, s3);
+    };
+    for (uint64_t base = (tid - lane) * chunk; base < dim; base += nthreads * chunk) {  // warp-uniform trip count
+        const uint64_t first = base + (uint64_t)lane * chunk;
+        const uint64_t cnt = first < dim ? min(chunk, dim - first) : 0;
+        uint64_t x = cnt ? unrank_colex(rank_begin + first, dm.N, dm.B, binom) : 0ull;
+        for (uint64_t k = 0; k < chunk; ++k) {
+            int mult = 0;
+            const bool rep = (k < cnt) && (L <= 32 ? orbit_representative<uint32_t>((uint32_t)x, L, (uint32_t)maskL, dm.M, mult)
+                                                   : orbit_representative<uint64_t>(x, L, maskL, dm.M, mult));
+            const unsigned b = __ballot_sync(0xffffffffu, rep);
+            if (rep) {
+                const int pos = qn + __popc(b & ((1u << lane) - 1u));
+                qx[warp][pos] = x;
+                qm[warp][pos] = mult;
+            }
+            qn += __popc(b);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                evaluate(qx[warp][qn + lane], (double)qm[warp][qn + lane]);
+                __syncwarp();
+            }
+            if (k + 1 < cnt) x = (L <= 32) ? (uint64_t)next_same_popcount32((uint32_t)x) : next_same_popcount(x);
+        }
+    }
+    if (lane < qn) evaluate(qx[warp][lane], (double)qm[warp][lane]);
+    __shared__ double sm[SWEEP_BLOCK / 32][4];
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    s3 = warp_sum(s3);
+    if (lane == 0) {
+        sm[warp][0] = s0;
+        sm[warp][1] = s1;
+        sm[warp][2] = s2;
+        sm[warp][3] = s3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < SWEEP_BLOCK / 32; ++q) v += sm[q][threadIdx.x];
+        partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+
 // per-state outputs for parity tests: states first..first+count-1
 template <int NW, int KC, bool RANKED>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
@@ -260,7 +369,11 @@ cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
     const bool ranked = (L.basis == nullptr);
     GWZ_DISPATCH_NW(L.nw, L.tb.kc, {
         const size_t smem = StepScratch<NW, KC>::bytes(L.dm.N);
-        if (ranked) {
+        if (ranked && L.symmetric && L.dm.N + L.dm.M <= 64) {
+            if (cudaError_t e = ensure_smem(sweep_sym_kernel<NW, KC>, smem)) return e;
+            sweep_sym_kernel<NW, KC><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.dim, L.rank_begin, L.chunk, L.binom,
+                                                                      L.partials);
+        } else if (ranked) {
             if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, true>, smem)) return e;
             sweep_kernel<NW, KC, true><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
                                                                          L.binom, L.partials);

@@ -180,3 +180,34 @@ def test_amsgrad_driving_vqmc(gw):
     assert abs(tr.param[-1, 0] - m["param"]) < 0.02
     assert abs(tr.value[-1] - m["val"]) < 0.1
     assert np.all(tr.error > 0)
+
+
+@pytest.mark.parametrize("N,M", [(4, 4), (6, 6), (2, 2), (3, 9), (9, 3), (12, 12), (7, 13), (3, 40), (5, 30), (20, 3), (1, 5)])
+def test_orbit_reduced_sweep_equals_full_sweep(gw, N, M, monkeypatch):
+    """Ranked sweeps evaluate one representative per translation orbit (weight = orbit size, including orbits with a
+    non-trivial stabiliser such as |2 0 2 0>); the four sums must agree with the state-by-state sweep, also when the
+    rank range is cut into shards at arbitrary places."""
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=2.0, t=0.7)
+    ans = gw.GutzwillerAnsatz(H)
+    out = {}
+    for sym in ("1", "0"):
+        monkeypatch.setenv("GWZ_SWEEP_SYM", sym)
+        le = gw.LocalEnergyEvaluator(H, ans)
+        out[sym] = (le.accumulators(0.3), le.val_and_grad(0.3))
+    a, b = out["1"], out["0"]
+    assert np.all(np.abs(a[0] - b[0]) <= 1e-12 * np.abs(b[0]))
+    assert abs(a[1][0] - b[1][0]) <= 1e-12 * abs(b[1][0]) and abs(a[1][1][0] - b[1][1][0]) <= 1e-11 * max(1.0, abs(b[1][1][0]))
+    monkeypatch.setenv("GWZ_SWEEP_SYM", "1")
+    dim = H.model().dimension()
+    if dim >= 50:
+        cuts = [0, dim // 7, dim // 3 + 1, dim - 5, dim]
+        acc = np.zeros(4)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            h = gw.capi.C.c_void_p()
+            gw.capi.check(gw.lib().gwz_sweep_create(H.model().handle, None, 0, lo, hi, gw.capi.C.byref(h)))
+            v, g, a4 = gw.capi.C.c_double(), (gw.capi.C.c_double * 1)(), (gw.capi.C.c_double * 4)()
+            p = (gw.capi.C.c_double * 1)(0.3)
+            gw.capi.check(gw.lib().gwz_sweep_val_and_grad(h, p, gw.capi.C.byref(v), g, a4))
+            gw.lib().gwz_sweep_destroy(h)
+            acc += np.array(a4[:])
+        assert np.all(np.abs(acc - b[0]) <= 1e-12 * np.abs(b[0]))
