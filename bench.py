@@ -94,8 +94,14 @@ def cpu_reference_rate(target_seconds: float = 12.0):
     t0 = time.perf_counter()
     out = o.kinetic_vqmc(G, start.copy(), steps, seed=SEED, n_threads=cores)
     dt = time.perf_counter() - t0
+    # the tuned CPU code (closed-form ratios, tables; NOT the reference algorithm): upper bound of the CPU side
+    fsteps = steps * 40
+    t0 = time.perf_counter()
+    o.kinetic_vqmc_fast(G, start.copy(), fsteps, seed=SEED, n_threads=cores)
+    fdt = time.perf_counter() - t0
     return dict(rate=walkers * steps / dt, cores=cores, walkers=walkers, steps=steps, seconds=dt,
-                hops_per_step=out["hops"] / (walkers * steps), val=out["val"])
+                hops_per_step=out["hops"] / (walkers * steps), val=out["val"],
+                tuned_rate=walkers * fsteps / fdt, tuned_seconds=fdt, tuned_steps=fsteps)
 
 
 def run_reference(args):
@@ -229,6 +235,12 @@ def run_ours(args):
                "sample": f"{c['walkers']} walkers x {c['steps']} steps of the same BoseFS{{{N_PART},{N_MODES}}} workload "
                          f"({c['seconds']:.1f} s, C/OpenMP restatement of the reference)"}
 
+    cpu_tuned = None
+    if cpu is not None:
+        cpu_tuned = {"value": c["tuned_rate"], "unit": "walker-steps/s", "cores": c["cores"], "kind": "tuned-cpu",
+                     "sample": f"{c['walkers']} walkers x {c['tuned_steps']} steps ({c['tuned_seconds']:.1f} s)",
+                     "note": "oracle.kinetic_vqmc_fast: closed-form ratios and tables on occupation arrays, the same "
+                             "trajectories as the port; an upper bound of the CPU side, not the reference's algorithm"}
     line = {
         "metric": "kinetic-VQMC walker-steps/s", "value": value, "unit": "walker-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -247,6 +259,7 @@ def run_ours(args):
                              "state per launch; the binding limit is instruction issue, see issue_roofline"},
         "issue_roofline": issue,
         "cpu_baseline": cpu,
+        "cpu_tuned": cpu_tuned,
         "clocks": clocks,
         "hops_per_step": hops_per_step, "hop_evals_per_s": value * hops_per_step,
         "kernel_ms_avg": kavg, "kernel_ms_max": kmax,

@@ -177,6 +177,12 @@ int go_gen_kinetic_vqmc(const go_ansatz *a, const double *params, go_addr *addrs
                         double *series_eloc, go_addr *series_addr, double *val_w, double *grad_w,
                         int64_t *total_hops);
 
+/* tuned CPU code for the Gutzwiller path (closed-form ratios, tables): an upper bound of the CPU side, not a
+ * restatement of the reference */
+int go_kinetic_vqmc_fast(const go_model *m, double g, go_addr *addrs, int64_t n_walkers, int64_t steps, uint64_t seed,
+                         uint64_t walker0, uint64_t step0, int n_threads, double *val_w, double *grad_w,
+                         int64_t *total_hops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -306,3 +306,74 @@ int go_gen_kinetic_vqmc(const go_ansatz *a, const double *params, go_addr *addrs
     if (total_hops) *total_hops = hops;
     return rc;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * "Optimised CPU" bound for the Gutzwiller path: NOT a restatement of the reference but
+ * what a tuned CPU code could do -- occupation arrays, closed-form amplitude ratios exp(-g u Delta)
+ * from a table, sqrt table, incrementally carried diagonal.  Same hop order, same Philox stream and
+ * the same selection rule as go_kinetic_vqmc, so both produce the same trajectories (up to the last
+ * bits of the rates); it is timed next to the faithful port as an honest upper bound of the CPU side
+ * and doubles as a cross-check of the port.
+ * ------------------------------------------------------------------------------------------- */
+int go_kinetic_vqmc_fast(const go_model *m, double g, go_addr *addrs, int64_t n_walkers, int64_t steps, uint64_t seed,
+                         uint64_t walker0, uint64_t step0, int n_threads, double *val_w, double *grad_w,
+                         int64_t *total_hops) {
+    const int M = m->M, N = m->N;
+    double *exptab = (double *)malloc(sizeof(double) * (size_t)(2 * N + 3));
+    double *sqrtab = (double *)malloc(sizeof(double) * (size_t)(N + 2));
+    for (int i = 0; i < 2 * N + 3; ++i) exptab[i] = exp(-g * m->u * (double)(i - N));
+    for (int i = 0; i < N + 2; ++i) sqrtab[i] = sqrt((double)i);
+    int rc = 0;
+    int64_t hops = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : rc) reduction(+ : hops) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int64_t w = 0; w < n_walkers; ++w) {
+        int n[GO_MAXM];
+        double cum[2 * GO_MAXM];
+        int src[2 * GO_MAXM];
+        go_to_onr(m, &addrs[w], n);
+        long d = 0;
+        for (int k = 0; k < M; ++k) d += (long)n[k] * (n[k] - 1) / 2;
+        double st = 0, ste = 0, stg = 0, stge = 0;
+        for (int64_t k = 0; k < steps; ++k) {
+            double S = 0.0, E = 0.0;
+            int h = 0;
+            for (int i = 0; i < M; ++i) {
+                const int ni = n[i];
+                if (ni == 0) continue;
+                const int r = (i + 1 == M) ? 0 : i + 1, l = (i == 0) ? M - 1 : i - 1;
+                const double rr = exptab[n[r] - ni + 1 + N], rl = exptab[n[l] - ni + 1 + N];
+                S += rr;
+                cum[h] = S;
+                src[h++] = 2 * i;
+                S += rl;
+                cum[h] = S;
+                src[h++] = 2 * i + 1;
+                E += sqrtab[ni] * (sqrtab[n[r] + 1] * rr + sqrtab[n[l] + 1] * rl);
+            }
+            const double D = m->u * (double)d;
+            const double tau = 1.0 / S, eloc = D - m->t * E, gr = -D;
+            if (!isfinite(tau)) rc |= 1;
+            st += tau;
+            ste += tau * eloc;
+            stg += tau * gr;
+            stge += tau * gr * eloc;
+            hops += h;
+            const double c = go_u01(seed, walker0 + (uint64_t)w, step0 + (uint64_t)k) * S;
+            int q = 0;
+            while (q < h - 1 && !(c < cum[q])) ++q;
+            const int i = src[q] >> 1;
+            const int j = (src[q] & 1) ? ((i == 0) ? M - 1 : i - 1) : ((i + 1 == M) ? 0 : i + 1);
+            d += n[j] - n[i] + 1;
+            n[i] -= 1;
+            n[j] += 1;
+        }
+        go_from_onr(m, n, &addrs[w]);
+        const double val = ste / st;
+        if (val_w) val_w[w] = val;
+        if (grad_w) grad_w[w] = 2.0 * (stge / st - val * (stg / st));
+    }
+    free(exptab);
+    free(sqrtab);
+    if (total_hops) *total_hops = hops;
+    return rc;
+}

@@ -121,6 +121,8 @@ def lib():
         L.go_gen_kinetic_vqmc.argtypes = [anp, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
                                           C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.POINTER(C.c_int64)]
+        L.go_kinetic_vqmc_fast.argtypes = [mp, C.c_double, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
+                                           C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -256,6 +258,18 @@ class Oracle:
         self.L.go_result_val_and_grad(_vp(val_w), _vp(grad_w), nw, C.byref(v), C.byref(gr))
         return dict(addrs=addrs, val_w=val_w, grad_w=grad_w, val=v.value, grad=gr.value, hops=hops.value,
                     series_addr=sa, series_tau=st, series_eloc=se, series_grad=sg)
+
+    def kinetic_vqmc_fast(self, g: float, addrs: np.ndarray, steps: int, seed: int = 0, walker0: int = 0,
+                          step0: int = 0, n_threads: int = 0):
+        """Tuned CPU code for the same walk (closed-form ratios): an upper bound of the CPU side, not the reference."""
+        addrs = np.ascontiguousarray(addrs, dtype=np.uint64)
+        nw = addrs.shape[0]
+        val_w, grad_w, hops = np.zeros(nw), np.zeros(nw), C.c_int64()
+        rc = self.L.go_kinetic_vqmc_fast(C.byref(self.m), g, _vp(addrs), nw, steps, seed, walker0, step0, n_threads,
+                                         _vp(val_w), _vp(grad_w), C.byref(hops))
+        if rc:
+            raise FloatingPointError("Infinite residence time")
+        return dict(addrs=addrs, val_w=val_w, grad_w=grad_w, val=val_w.mean(), grad=grad_w.mean(), hops=hops.value)
 
     def lee_val_and_grad(self, basis: np.ndarray, g: float, mode: int = 0, n_threads: int = 0):
         basis = np.ascontiguousarray(basis, dtype=np.uint64)

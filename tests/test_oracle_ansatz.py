@@ -100,3 +100,15 @@ def test_generic_walk_reaches_psi_squared(oracle_mod):
     r = ao.kinetic_vqmc(p, addrs, 20000, seed=5, series=True)
     exact, _ = ao.lee_val_and_grad(basis, p)
     assert abs(r["val"] - exact) < 0.05
+
+
+def test_tuned_cpu_walk_follows_the_faithful_port(oracle_mod):
+    """oracle.kinetic_vqmc_fast (closed-form ratios, the CPU upper bound timed in bench.py) walks the same
+    trajectories as the literal restatement."""
+    for N, M, u, g in [(10, 10, 2.0, 1.0), (20, 20, 4.0, 0.25), (7, 3, 1.0, 0.3), (50, 50, 2.0, 0.33)]:
+        o = oracle_mod.Oracle(N, M, u, 1.0)
+        start = np.tile(o.near_uniform(), (4, 1))
+        a = o.kinetic_vqmc(g, start.copy(), 400, seed=3, walker0=2)
+        b = o.kinetic_vqmc_fast(g, start.copy(), 400, seed=3, walker0=2)
+        assert np.array_equal(a["addrs"], b["addrs"]) and a["hops"] == b["hops"]
+        assert np.allclose(a["val_w"], b["val_w"], rtol=1e-11) and np.allclose(a["grad_w"], b["grad_w"], rtol=1e-8, atol=1e-9)
