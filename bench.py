@@ -258,6 +258,12 @@ def run_ours(args):
                      "note": "walker kernel keeps its state in registers: HBM traffic is one load+store of the walker "
                              "state per launch; the binding limit is instruction issue, see issue_roofline"},
         "issue_roofline": issue,
+        "fp64_algorithmic": {"flops_per_walker_step": 3.0 * hops_per_step + 12.0,
+                             "achieved_tflops": steps_per_s_gpu * (3.0 * hops_per_step + 12.0) / 1e12,
+                             "peak_tflops": info["sm_count"] * 64 * 2 * sm_mhz * 1e6 / 1e12,
+                             "note": "algorithmic FP64 work of the reference formulation (SURVEY 8d: 3h+12 per step); the kernel "
+                                     "replaces most of it by integer class counts and tables, so this is a work-equivalent "
+                                     "rate, not executed DFMA"},
         "cpu_baseline": cpu,
         "cpu_tuned": cpu_tuned,
         "clocks": clocks,

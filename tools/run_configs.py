@@ -85,6 +85,12 @@ for g in (0.25, 1.0):
     out[f"g={g}"] = dict(steps_per_walker=qmc.steps, ms_per_call=dt * 1e3, kernel_ms=r.kernel_ms,
                          walker_steps_per_s=qmc.steps * qmc.walkers / dt, val=r.val, err=r.err, pooled_val=r.pooled_val,
                          grad=r.grad[0], pooled_grad=r.pooled_grad[0], hops_per_step=r.hops / r.steps)
+    # raw throughput with the launch amortised over longer blocks (1e3 and 1e4 steps per walker)
+    for long_steps in (1000, 10000):
+        t0 = time.perf_counter()
+        val, grad = gw.val_and_grad(qmc, g, steps=long_steps)
+        dt = time.perf_counter() - t0
+        out[f"g={g}"][f"walker_steps_per_s_{long_steps}_steps"] = long_steps * qmc.walkers / dt
 report["cfg3_bose20_2^20walkers_1e8samples"] = out
 
 # ---- config 4: AMSGrad on KineticVQMC, samples=1e7 per evaluation, BoseFS{50,50} ----
