@@ -112,6 +112,8 @@ SIGNATURES = {
     "gwz_walkers_estimates": (C.c_int, [_vp, _vp, _vp]),
     "gwz_vqmc_run_record": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, C.c_uint, _vp, _vp, _vp,
                                       C.POINTER(VqmcResult)]),
+    "gwz_vqmc_sample_vector": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, C.c_uint, C.c_uint64, _vp, _vp, _u64p,
+                                         C.POINTER(VqmcResult)]),
     "gwz_sweep_create": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
     "gwz_sweep_destroy": (C.c_int, [_vp]),
     "gwz_sweep_dim": (C.c_int, [_vp, _u64p]),

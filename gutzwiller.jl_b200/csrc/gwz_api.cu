@@ -5,6 +5,7 @@
 // There is no CPU implementation of any sampled or swept quantity in this file.
 #include "gutzwiller_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -881,6 +882,68 @@ extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_
         GWZ_CUDA(cudaMemcpyAsync(addr, d_addr.p, sizeof(uint64_t) * cells * w->m->W, cudaMemcpyDeviceToHost, c->stream));
     gwz_walkers* one[1] = {w};
     return combine_and_fetch(one, 1, flags, out);
+}
+
+// DVec(res) (state.jl:303-319) without shipping the per-step series to the host
+extern "C" int gwz_vqmc_sample_vector(gwz_walkers* w, const double* params, uint64_t steps, int kernel_kind, unsigned flags,
+                                      uint64_t cap, uint64_t* addr_out, double* val_out, uint64_t* count,
+                                      gwz_vqmc_result* out) {
+    GWZ_REQUIRE(w && params && count, "gwz_vqmc_sample_vector: NULL argument");
+    GWZ_REQUIRE(cap == 0 || (addr_out && val_out), "gwz_vqmc_sample_vector: NULL output buffer");
+    GWZ_REQUIRE(steps >= 1, "gwz_vqmc_sample_vector: steps_per_walker must be >= 1");
+    GWZ_REQUIRE(w->m->W == 1, "gwz_vqmc_sample_vector: needs single-word addresses (N+M-1 <= 64)");
+    GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
+                "gwz_vqmc_sample_vector: unknown kernel_kind");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const size_t cells = (size_t)steps * w->n;
+    double dimd = 0.0;
+    uint64_t dime = 0;
+    if (int rc = gwz_model_dimension(w->m, &dimd, &dime)) return rc;
+    const double distinct = std::fmin((double)cells, dimd);
+    size_t slots = 1024;
+    while ((double)slots < 2.0 * distinct) slots <<= 1;
+    DevBuf<double> d_tau, d_eloc, d_tv, d_ov;
+    DevBuf<uint64_t> d_addr, d_tk, d_ok;
+    DevBuf<unsigned long long> d_cnt;
+    GWZ_CUDA(d_tau.alloc(cells));
+    GWZ_CUDA(d_eloc.alloc(cells));
+    GWZ_CUDA(d_addr.alloc(cells));
+    GWZ_CUDA(d_tk.alloc(slots));
+    GWZ_CUDA(d_tv.alloc(slots));
+    GWZ_CUDA(d_ok.alloc(cap));
+    GWZ_CUDA(d_ov.alloc(cap));
+    GWZ_CUDA(d_cnt.alloc(1));
+    DevTables tb;
+    make_tables(w->m, params[0], choose_kc(w->m, params[0], false), &tb);
+    if (int rc = enqueue_run(w, tb, steps, 0, kernel_kind, flags, d_tau.p, d_eloc.p, d_addr.p, true)) return rc;
+    GWZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), c->stream));
+    GWZ_LAUNCH(launch_hist_fill(d_tk.p, d_tv.p, slots, c->stream));
+    GWZ_LAUNCH(launch_hist_insert(d_addr.p, d_tau.p, cells, d_tk.p, d_tv.p, (uint64_t)slots - 1, c->stream));
+    GWZ_LAUNCH(launch_hist_compact(d_tk.p, d_tv.p, slots, d_ok.p, d_ov.p, d_cnt.p, cap, c->stream));
+    unsigned long long n_unique = 0;
+    GWZ_CUDA(cudaMemcpyAsync(&n_unique, d_cnt.p, sizeof(n_unique), cudaMemcpyDeviceToHost, c->stream));
+    gwz_walkers* one[1] = {w};
+    if (int rc = combine_and_fetch(one, 1, flags, out)) return rc;  // synchronises the stream
+    *count = n_unique;
+    const size_t m = (size_t)std::min<unsigned long long>(n_unique, cap);
+    std::vector<uint64_t> k(m);
+    std::vector<double> v(m);
+    GWZ_CUDA(cudaMemcpy(k.data(), d_ok.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost));
+    GWZ_CUDA(cudaMemcpy(v.data(), d_ov.p, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    GWZ_REQUIRE(n_unique <= cap, "gwz_vqmc_sample_vector: more distinct addresses than the output capacity");
+    // ascending addresses, normalize!(dv) (2-norm); O(distinct) host work on the histogram, not on the samples
+    std::vector<size_t> order(m);
+    for (size_t i = 0; i < m; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return k[a] < k[b]; });
+    double nrm = 0.0;
+    for (size_t i = 0; i < m; ++i) nrm += v[i] * v[i];
+    nrm = std::sqrt(nrm);
+    for (size_t i = 0; i < m; ++i) {
+        addr_out[i] = k[order[i]];
+        val_out[i] = v[order[i]] / nrm;
+    }
+    return GWZ_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -120,6 +120,13 @@ cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* gri
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s);
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s);
 
+// ---- DVec(result) histogram (gwz_hist.cu) ----------------------------------------------------
+cudaError_t launch_hist_fill(uint64_t* tkeys, double* tvals, size_t slots, cudaStream_t s);
+cudaError_t launch_hist_insert(const uint64_t* keys, const double* tau, size_t cells, uint64_t* tkeys, double* tvals,
+                               uint64_t mask, cudaStream_t s);
+cudaError_t launch_hist_compact(const uint64_t* tkeys, const double* tvals, size_t slots, uint64_t* out_keys,
+                                double* out_vals, unsigned long long* count, uint64_t cap, cudaStream_t s);
+
 // ---- ansatz-generic engine (gwz_generic.cu) ------------------------------------------------
 struct GenProbeLaunch {
     GenModel gm;

@@ -130,6 +130,18 @@ class Walkers:
                                         None if addr is None else addr.ctypes.data_as(C.c_void_p), C.byref(r)))
         return r, tau, eloc, addr
 
+    def sample_vector(self, params, steps: int, kernel: int = _capi.KERNEL_BITPARALLEL, keep_acc: bool = False,
+                      cap: int | None = None):
+        """``DVec(res)`` (state.jl:303-319) histogrammed on the device: (addresses uint64[k, 1], values float64[k])."""
+        p = as_params(params, 1)
+        cap = int(min(int(steps) * self.n, self.model.dimension())) if cap is None else int(cap)
+        addr, val = np.zeros(cap, dtype=np.uint64), np.zeros(cap)
+        cnt, r = C.c_uint64(), _capi.VqmcResult()
+        check(lib().gwz_vqmc_sample_vector(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), int(steps), int(kernel),
+                                           _capi.RUN_KEEP_ACC if keep_acc else 0, cap, addr.ctypes.data_as(C.c_void_p),
+                                           val.ctypes.data_as(C.c_void_p), C.byref(cnt), C.byref(r)))
+        return addr[: cnt.value].reshape(-1, 1), val[: cnt.value], r
+
     def estimates(self):
         v, g = np.zeros(self.n), np.zeros((self.n, 1))
         check(lib().gwz_walkers_estimates(self._h, v.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p)))

@@ -160,6 +160,14 @@ int gwz_walkers_estimates(gwz_walkers *w, double *val_w, double *grad_w);
 int gwz_vqmc_run_record(gwz_walkers *w, const double *params, uint64_t steps_per_walker, int kernel_kind,
                         unsigned flags, double *tau, double *eloc, uint64_t *addr, gwz_vqmc_result *out);
 
+/* DVec(res) (state.jl:303-319): runs steps_per_walker recorded steps and deposits every step's residence time on its
+ * address in an HBM hash table; returns the distinct addresses in ascending order with the 2-norm-normalised
+ * values (normalize!(dv)).  cap = capacity of addr_out / val_out; *count = number of distinct addresses (if it exceeds
+ * cap the call fails with GWZ_ERR_INVALID after setting *count).  Single-word addresses only (N+M-1 <= 64). */
+int gwz_vqmc_sample_vector(gwz_walkers *w, const double *params, uint64_t steps_per_walker, int kernel_kind,
+                           unsigned flags, uint64_t cap, uint64_t *addr_out, double *val_out, uint64_t *count,
+                           gwz_vqmc_result *out);
+
 /* ---- LocalEnergyEvaluator (src/localenergy.jl:81-173) --------------------------------------- */
 /* basis_words: dim x W stored basis (reference layout `basis::Vector{A}`, localenergy.jl:84), copied
  * to HBM once; or NULL => all C(N+M-1,N) states enumerated on the fly by rank in [rank_begin,

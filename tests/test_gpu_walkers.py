@@ -293,3 +293,23 @@ def test_planes_kernel_is_bitwise_identical_to_unary(gw, oracle_mod, N, M, u, g,
         assert np.array_equal(a[0], b[0])
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and a[5] == b[5] == 142
+
+
+@pytest.mark.parametrize("N,M", [(5, 5), (12, 12), (20, 20)])
+def test_device_histogram_equals_host_histogram(gw, N, M):
+    """gwz_vqmc_sample_vector (DVec(res), state.jl:303-319, accumulated in an HBM hash table) against the host-side
+    histogram of the same recorded run."""
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=2.0)
+    ans = gw.GutzwillerAnsatz(H)
+    steps, walkers = 500, 128
+    res = gw.kinetic_vqmc(H, ans, 0.4, walkers=walkers, steps=steps, seed=5, record=True)
+    addrs, vals = gw.sampled_vector(res)
+    w = gw.Walkers(H.model(), walkers, H.address.words, seed=5)
+    a2, v2, r = w.sample_vector([0.4], steps)
+    assert np.array_equal(addrs, a2) and np.allclose(vals, v2, rtol=1e-12, atol=0)
+    assert abs(np.linalg.norm(v2) - 1.0) < 1e-12 and r.val == res.last.val
+    with pytest.raises(ValueError, match="capacity"):
+        w.sample_vector([0.4], steps, cap=3)
+    big = gw.HubbardReal1D(gw.near_uniform(50, 50), u=2.0)
+    with pytest.raises(ValueError, match="single-word"):
+        gw.Walkers(big.model(), 4, big.address.words).sample_vector([0.4], 10)
