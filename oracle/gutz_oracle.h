@@ -152,14 +152,20 @@ enum go_ansatz_kind {
     GO_ANSATZ_MULTINOMIAL = 2,      /* src/ansatz/multinomial.jl */
     GO_ANSATZ_DENSITY_PROFILE = 3,  /* src/ansatz/densityprofile.jl */
     GO_ANSATZ_RELATIVE_JASTROW = 4, /* src/ansatz/jastrow.jl:60-103 */
-    GO_ANSATZ_JASTROW = 5           /* src/ansatz/jastrow.jl:4-58 */
+    GO_ANSATZ_JASTROW = 5,          /* src/ansatz/jastrow.jl:4-58 */
+    GO_ANSATZ_COMBINATION = 6       /* src/ansatz/combination.jl: alpha*a1 + (1-alpha)*a2, params (p1..., p2..., alpha) */
 };
 typedef struct {
     go_model m;
     double v;             /* ExtendedHubbardReal1D nearest-neighbour interaction (0: HubbardReal1D) */
     int kind, P;          /* ansatz kind, num_parameters */
     double normalization; /* MultinomialAnsatz(H; normalize) */
+    int kind1, kind2;     /* CombinationAnsatz: kinds of the two components */
+    int norm1, norm2;     /* ... and their normalize flags */
 } go_ansatz;
+/* a1 + a2 (combination.jl:13-15) */
+int go_ansatz_init_combination(go_ansatz *a, const go_model *m, double v, int kind1, int normalize1, int kind2,
+                               int normalize2);
 int go_ansatz_init(go_ansatz *a, const go_model *m, double v, int kind, int normalize);
 double go_gen_diagonal(const go_ansatz *a, const go_addr *addr);
 /* grad (P doubles) may be NULL: the ansatz call operator */

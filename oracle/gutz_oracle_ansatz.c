@@ -42,6 +42,8 @@ int go_ansatz_init(go_ansatz *a, const go_model *m, double v, int kind, int norm
     a->m = *m;
     a->v = v;
     a->kind = kind;
+    a->kind1 = a->kind2 = -1;
+    a->norm1 = a->norm2 = 0;
     const int M = m->M;
     switch (kind) {
         case GO_ANSATZ_GUTZWILLER: a->P = 1; break;
@@ -54,6 +56,22 @@ int go_ansatz_init(go_ansatz *a, const go_model *m, double v, int kind, int norm
     }
     /* multinomial.jl:29-31: gamma(N + 1) / M^N */
     a->normalization = normalize ? tgamma((double)m->N + 1.0) / pow((double)M, (double)m->N) : 1.0;
+    return 0;
+}
+
+int go_ansatz_init_combination(go_ansatz *a, const go_model *m, double v, int kind1, int normalize1, int kind2,
+                               int normalize2) {
+    go_ansatz c1, c2;
+    if (go_ansatz_init(&c1, m, v, kind1, normalize1) || go_ansatz_init(&c2, m, v, kind2, normalize2)) return 1;
+    a->m = *m;
+    a->v = v;
+    a->kind = GO_ANSATZ_COMBINATION;
+    a->P = c1.P + c2.P + 1; /* combination.jl:14 */
+    a->normalization = 1.0;
+    a->kind1 = kind1;
+    a->kind2 = kind2;
+    a->norm1 = normalize1;
+    a->norm2 = normalize2;
     return 0;
 }
 
@@ -145,6 +163,23 @@ void go_gen_val_and_grad(const go_ansatz *a, const go_addr *addr, const double *
                 k = 0;
                 for (int i = 0; i < M; ++i)
                     for (int j = i; j < M; ++j, ++k) grad[k] = -(double)(o[i] * o[j]) * v;
+            }
+            break;
+        }
+        case GO_ANSATZ_COMBINATION: { /* combination.jl:17-50 */
+            go_ansatz c1, c2;
+            go_ansatz_init(&c1, &a->m, a->v, a->kind1, a->norm1);
+            go_ansatz_init(&c2, &a->m, a->v, a->kind2, a->norm2);
+            const double alpha = p[a->P - 1];
+            double v1, v2;
+            double *g1 = grad ? grad : NULL, *g2 = grad ? grad + c1.P : NULL;
+            go_gen_val_and_grad(&c1, addr, p, &v1, g1);
+            go_gen_val_and_grad(&c2, addr, p + c1.P, &v2, g2);
+            *val = alpha * v1 + (1 - alpha) * v2;
+            if (grad) {
+                for (int k = 0; k < c1.P; ++k) g1[k] *= alpha;
+                for (int k = 0; k < c2.P; ++k) g2[k] *= (1 - alpha);
+                grad[a->P - 1] = v1 - v2;
             }
             break;
         }

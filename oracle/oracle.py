@@ -52,7 +52,8 @@ class GdOpts(C.Structure):
 
 
 class Ansatz(C.Structure):
-    _fields_ = [("m", Model), ("v", C.c_double), ("kind", C.c_int), ("P", C.c_int), ("normalization", C.c_double)]
+    _fields_ = [("m", Model), ("v", C.c_double), ("kind", C.c_int), ("P", C.c_int), ("normalization", C.c_double),
+                ("kind1", C.c_int), ("kind2", C.c_int), ("norm1", C.c_int), ("norm2", C.c_int)]
 
 
 ANSATZ_KINDS = {"gutzwiller": 0, "ext_gutzwiller": 1, "multinomial": 2, "density_profile": 3,
@@ -111,6 +112,7 @@ def lib():
         L.go_lee_objective_val_and_grad.argtypes = [C.c_void_p, dp, C.c_int, dp, dp, dp]
         anp = C.POINTER(Ansatz)
         L.go_ansatz_init.argtypes = [anp, mp, C.c_double, C.c_int, C.c_int]
+        L.go_ansatz_init_combination.argtypes = [anp, mp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
         L.go_gen_diagonal.argtypes = [anp, ap]
         L.go_gen_diagonal.restype = C.c_double
         L.go_gen_val_and_grad.argtypes = [anp, ap, C.c_void_p, dp, C.c_void_p]
@@ -339,10 +341,19 @@ class AnsatzOracle:
     """(Extended)HubbardReal1D + one of the reference's single-component ansaetze, CPU restatement
     (oracle/gutz_oracle_ansatz.c).  `base` is an Oracle (model + address helpers)."""
 
-    def __init__(self, base: Oracle, kind: str, v: float = 0.0, normalize: bool = False):
+    def __init__(self, base: Oracle, kind, v: float = 0.0, normalize=False):
+        """kind: a name from ANSATZ_KINDS, or a pair of names for CombinationAnsatz (a1 + a2, combination.jl);
+        normalize: bool, or a pair of bools for the two components."""
         self.base, self.L = base, base.L
         self.a = Ansatz()
-        if self.L.go_ansatz_init(C.byref(self.a), C.byref(base.m), v, ANSATZ_KINDS[kind], int(normalize)):
+        if isinstance(kind, (tuple, list)):
+            n1, n2 = normalize if isinstance(normalize, (tuple, list)) else (normalize, normalize)
+            rc = self.L.go_ansatz_init_combination(C.byref(self.a), C.byref(base.m), v, ANSATZ_KINDS[kind[0]], int(n1),
+                                                   ANSATZ_KINDS[kind[1]], int(n2))
+            kind = "+".join(kind)
+        else:
+            rc = self.L.go_ansatz_init(C.byref(self.a), C.byref(base.m), v, ANSATZ_KINDS[kind], int(normalize))
+        if rc:
             raise ValueError(f"unknown ansatz kind {kind}")
         self.kind, self.v, self.P, self.M = kind, v, self.a.P, base.M
 

@@ -6,7 +6,9 @@ Hamiltonian Rayleigh quotient for Rimu's `rayleigh_quotient`, exact diagonalisat
 import numpy as np
 import pytest
 
-KINDS = ["gutzwiller", "ext_gutzwiller", "multinomial", "density_profile", "relative_jastrow", "jastrow"]
+KINDS = ["gutzwiller", "ext_gutzwiller", "multinomial", "density_profile", "relative_jastrow", "jastrow",
+         ("gutzwiller", "multinomial"),  # GutzwillerAnsatz(H) + MultinomialAnsatz(H) (test/ansatz.jl:58)
+         ("relative_jastrow", "density_profile")]
 
 
 def _params(ao, rng):
