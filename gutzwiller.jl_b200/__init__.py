@@ -13,7 +13,7 @@ from . import _capi as capi
 from ._capi import (KERNEL_BITPARALLEL, KERNEL_ENUMERATE, GutzwillerError, lib)
 from .amsgrad import (GradientDescentResult, adaptive_gradient_descent, amsgrad, gradient_descent, val_and_grad,
                       val_err_and_grad)
-from .ansatz import (DensityProfileAnsatz, ExtendedGutzwillerAnsatz, ExtendedHubbardReal1D, GenericGutzwillerAnsatz, GenWalkers,
+from .ansatz import (CombinationAnsatz, DensityProfileAnsatz, ExtendedGutzwillerAnsatz, ExtendedHubbardReal1D, GenericGutzwillerAnsatz, GenWalkers,
                      JastrowAnsatz,
                      MultinomialAnsatz, RelativeJastrowAnsatz)
 from .hamiltonian import (AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1D, keytype, near_uniform,

@@ -46,6 +46,7 @@ class GenResult(C.Structure):
 
 ANSATZ_GUTZWILLER, ANSATZ_EXT_GUTZWILLER, ANSATZ_MULTINOMIAL, ANSATZ_DENSITY_PROFILE, ANSATZ_RELATIVE_JASTROW, \
     ANSATZ_JASTROW = range(6)
+ANSATZ_COMBINATION = 6
 
 
 class BlockingResult(C.Structure):
@@ -134,6 +135,7 @@ SIGNATURES = {
                                                  C.POINTER(_vp)]),
     "gwz_model_info_ext": (C.c_int, [_vp, _dp]),
     "gwz_ansatz_create": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "gwz_ansatz_create_combination": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "gwz_ansatz_destroy": (C.c_int, [_vp]),
     "gwz_ansatz_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gwz_gen_ansatz_eval": (C.c_int, [_vp, _vp, C.c_size_t, _dp, _vp, _vp]),

@@ -45,10 +45,15 @@ class ExtendedHubbardReal1D(HubbardReal1D):
 class _AnsatzHandle:
     """gwz_ansatz on one model (one context)."""
 
-    def __init__(self, model, kind: int, normalize: bool):
+    def __init__(self, model, kind, normalize):
+        """kind / normalize: ints, or pairs for a CombinationAnsatz (a1 + a2)."""
         self.model = model
         self._h = C.c_void_p()
-        check(lib().gwz_ansatz_create(model.handle, int(kind), int(bool(normalize)), C.byref(self._h)))
+        if isinstance(kind, tuple):
+            check(lib().gwz_ansatz_create_combination(model.handle, int(kind[0]), int(bool(normalize[0])), int(kind[1]),
+                                                      int(bool(normalize[1])), C.byref(self._h)))
+        else:
+            check(lib().gwz_ansatz_create(model.handle, int(kind), int(bool(normalize)), C.byref(self._h)))
         k, p = C.c_int(), C.c_int()
         check(lib().gwz_ansatz_info(self._h, C.byref(k), C.byref(p)))
         self.kind, self.P = k.value, p.value
@@ -186,6 +191,51 @@ class JastrowAnsatz(GenericAnsatz):
     @staticmethod
     def _num_parameters(M):
         return M * (M + 1) // 2
+
+
+def _kind_of(ansatz):
+    if isinstance(ansatz, GenericAnsatz) and not isinstance(ansatz, CombinationAnsatz):
+        return ansatz.KIND, ansatz.normalize
+    if type(ansatz) is GutzwillerAnsatz:
+        return _capi.ANSATZ_GUTZWILLER, False
+    raise TypeError(f"{type(ansatz).__name__} cannot be a component of a CombinationAnsatz")
+
+
+class CombinationAnsatz(GenericAnsatz):
+    """``ansatz1 + ansatz2`` (combination.jl:1-51): ``alpha * ansatz1 + (1 - alpha) * ansatz2`` with the parameters
+    ``(params1..., params2..., alpha)``."""
+    KIND = _capi.ANSATZ_COMBINATION
+
+    def __init__(self, ansatz1, ansatz2):
+        h1, h2 = ansatz1.hamiltonian, ansatz2.hamiltonian
+        if h1 is not h2 and (h1.u, h1.t, getattr(h1, "v", 0.0), h1.address) != (h2.u, h2.t, getattr(h2, "v", 0.0), h2.address):
+            raise TypeError("both components must be built on the same Hamiltonian")
+        self.ansatz1, self.ansatz2 = ansatz1, ansatz2
+        self._kinds = (_kind_of(ansatz1), _kind_of(ansatz2))
+        self.hamiltonian = h1
+        self.normalize = False
+        self.N_PARAMS = ansatz1.N_PARAMS + ansatz2.N_PARAMS + 1  # combination.jl:14
+        self._handles = {}
+
+    def handle(self, ctx: Context | None = None) -> _AnsatzHandle:
+        ctx = ctx or default_context()
+        key = id(ctx)
+        if key not in self._handles:
+            (k1, n1), (k2, n2) = self._kinds
+            self._handles[key] = _AnsatzHandle(self.hamiltonian.model(ctx), (k1, k2), (n1, n2))
+        return self._handles[key]
+
+    def __repr__(self):
+        return f"CombinationAnsatz({self.ansatz1!r}, {self.ansatz2!r})"
+
+
+def _add(a1, a2):
+    if not isinstance(a2, AbstractAnsatz):
+        return NotImplemented
+    return CombinationAnsatz(a1, a2)
+
+
+AbstractAnsatz.__add__ = _add  # Base.:+(a1::AbstractAnsatz, a2::AbstractAnsatz) (combination.jl:13-15)
 
 
 class GenRunResult:

@@ -21,6 +21,9 @@ struct gwz_ansatz {
     uint16_t* d_pairs = nullptr;
     double* d_par = nullptr;  // Qt[M*M], bvec[M], cR[M], cL[M]
     double* h_par = nullptr;  // pinned staging of d_par
+    // CombinationAnsatz (combination.jl): two owned component handles; kind = GWZ_ANSATZ_COMBINATION, P = P1 + P2 + 1
+    gwz_ansatz* c1 = nullptr;
+    gwz_ansatz* c2 = nullptr;
 };
 
 struct gwz_gwalkers {
@@ -146,8 +149,40 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     *out = a;
     return GWZ_OK;
 }
+extern "C" int gwz_ansatz_create_combination(gwz_model* m, int kind1, int normalize1, int kind2, int normalize2,
+                                             gwz_ansatz** out) {
+    GWZ_REQUIRE(m && out, "gwz_ansatz_create_combination: NULL argument");
+    gwz_ansatz *c1 = nullptr, *c2 = nullptr;
+    if (int rc = gwz_ansatz_create(m, kind1, normalize1, &c1)) return rc;
+    if (int rc = gwz_ansatz_create(m, kind2, normalize2, &c2)) {
+        gwz_ansatz_destroy(c1);
+        return rc;
+    }
+    const int P = c1->P + c2->P + 1;  // combination.jl:14
+    if (gen_ppl(P) <= 0) {
+        gwz_ansatz_destroy(c1);
+        gwz_ansatz_destroy(c2);
+        return api_fail(GWZ_ERR_INVALID, "gwz_ansatz_create_combination: more than 256 parameters are not supported");
+    }
+    gwz_ansatz* a = new gwz_ansatz();
+    a->m = m;
+    a->kind = GWZ_ANSATZ_COMBINATION;
+    a->P = P;
+    a->normalize = 0;
+    a->logK = 0.0;
+    a->Mpad = c1->Mpad;
+    a->gm = c1->gm;  // geometry (N, M, B, W, MP, MPL, u, v, t); the per-component tables are taken from c1 / c2
+    a->gm.P = P;
+    a->c1 = c1;
+    a->c2 = c2;
+    *out = a;
+    return GWZ_OK;
+}
+
 extern "C" int gwz_ansatz_destroy(gwz_ansatz* a) {
     if (!a) return GWZ_OK;
+    if (a->c1) gwz_ansatz_destroy(a->c1);
+    if (a->c2) gwz_ansatz_destroy(a->c2);
     if (use_device(a->m->ctx) == GWZ_OK) {
         if (a->d_static) cudaFree(a->d_static);
         if (a->d_pairs) cudaFree(a->d_pairs);
@@ -241,6 +276,19 @@ static int upload_params(gwz_ansatz* a, const double* p, GenModel* gm_out) {
     return GWZ_OK;
 }
 
+// parameters -> device tables for a plain ansatz (gm) or a combination (cb); *is_combo tells which
+static int prepare_params(gwz_ansatz* a, const double* p, GenModel* gm, GenCombo* cb, bool* is_combo) {
+    *is_combo = a->c1 != nullptr;
+    if (!*is_combo) return upload_params(a, p, gm);
+    for (int k = 0; k < a->P; ++k) GWZ_REQUIRE(std::isfinite(p[k]), "parameters must be finite");
+    if (int rc = upload_params(a->c1, p, &cb->g1)) return rc;
+    if (int rc = upload_params(a->c2, p + a->c1->P, &cb->g2)) return rc;
+    cb->alpha = p[a->P - 1];
+    cb->P = a->P;
+    *gm = a->gm;
+    return GWZ_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // probe / ansatz evaluation
 // ------------------------------------------------------------------------------------------
@@ -255,7 +303,9 @@ static int probe_impl(gwz_ansatz* a, const uint64_t* addr_words, size_t n, const
     const int W = a->m->W, M = a->m->M, P = a->P;
     GenProbeLaunch L;
     std::memset(&L, 0, sizeof(L));
-    if (int rc = upload_params(a, params, &L.gm)) return rc;
+    GenCombo cb;
+    bool combo = false;
+    if (int rc = prepare_params(a, params, &L.gm, &cb, &combo)) return rc;
     DevBuf<uint64_t> d_addr, d_next;
     DevBuf<double> d_u, d_val, d_grad, d_e, d_t, d_g, d_r;
     DevBuf<int32_t> d_h, d_c;
@@ -287,7 +337,8 @@ static int probe_impl(gwz_ansatz* a, const uint64_t* addr_words, size_t n, const
     L.chosen = d_c.p;
     L.next_addr = d_next.p;
     L.err_flag = c->d_err;
-    GWZ_LAUNCH(launch_gen_probe(L, c->stream));
+    if (combo) GWZ_LAUNCH(launch_combo_probe(L, cb, c->stream));
+    else GWZ_LAUNCH(launch_gen_probe(L, c->stream));
     auto back = [&](void* dst, const void* src, size_t bytes) {
         return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
     };
@@ -416,9 +467,12 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
     const int P = a->P, L = gen_vec_len(P), W = a->m->W;
     GenWalkerLaunch K;
     std::memset(&K, 0, sizeof(K));
-    if (int rc = upload_params(a, params, &K.gm)) return rc;
+    GenCombo cb;
+    bool combo = false;
+    if (int rc = prepare_params(a, params, &K.gm, &cb, &combo)) return rc;
     int grid = 0;
-    GWZ_CUDA(gen_walker_grid(K.gm, w->n, c->prop.multiProcessorCount, &grid));
+    if (combo) GWZ_CUDA(combo_walker_grid(cb, w->n, c->prop.multiProcessorCount, &grid));
+    else GWZ_CUDA(gen_walker_grid(K.gm, w->n, c->prop.multiProcessorCount, &grid));
     const size_t rows = (size_t)grid * GEN_WARPS;
     if (rows > w->partials_rows) {
         if (w->d_partials) cudaFree(w->d_partials);
@@ -442,7 +496,8 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
         K.steps = burn_in;
         K.accumulate = 0;
         K.reset_acc = 0;
-        GWZ_LAUNCH(launch_gen_walkers(K, c->stream));
+        if (combo) GWZ_LAUNCH(launch_combo_walkers(K, cb, c->stream));
+        else GWZ_LAUNCH(launch_gen_walkers(K, c->stream));
         w->steps_done += burn_in;
     }
     const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
@@ -460,7 +515,8 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
         Pr.e_loc = d_e.p;
         Pr.grad_ratio = d_g.p;
         Pr.err_flag = c->d_err;
-        GWZ_LAUNCH(launch_gen_probe(Pr, c->stream));
+        if (combo) GWZ_LAUNCH(launch_combo_probe(Pr, cb, c->stream));
+        else GWZ_LAUNCH(launch_gen_probe(Pr, c->stream));
         GWZ_CUDA(cudaMemcpyAsync(w->d_shift, d_e.p, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         GWZ_CUDA(cudaMemcpyAsync(w->d_shift + 1, d_g.p, sizeof(double) * P, cudaMemcpyDeviceToDevice, c->stream));
         GWZ_CUDA(cudaStreamSynchronize(c->stream));
@@ -484,7 +540,8 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
             K.rec_addr = d_ra.p;
         }
     }
-    GWZ_LAUNCH(launch_gen_walkers(K, c->stream));
+    if (combo) GWZ_LAUNCH(launch_combo_walkers(K, cb, c->stream));
+    else GWZ_LAUNCH(launch_gen_walkers(K, c->stream));
     GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
     w->steps_done += steps;
     w->acc_steps = keep ? w->acc_steps + steps : steps;
@@ -627,9 +684,12 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     const int P = a->P, L = 2 + 2 * P;
     GenSweepLaunch K;
     std::memset(&K, 0, sizeof(K));
-    if (int rc = upload_params(a, params, &K.gm)) return rc;
+    GenCombo cb;
+    bool combo = false;
+    if (int rc = prepare_params(a, params, &K.gm, &cb, &combo)) return rc;
     int grid = 0;
-    GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
+    if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
+    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
     const size_t rows = (size_t)grid * GEN_WARPS;
     if (rows > s->partials_rows) {
         if (s->d_partials) cudaFree(s->d_partials);
@@ -647,7 +707,8 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     K.grid = grid;
     if (!grad) GWZ_CUDA(cudaMemsetAsync(s->d_partials, 0, sizeof(double) * rows * L, c->stream));
     GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
-    GWZ_LAUNCH(launch_gen_sweep(K, c->stream));
+    if (combo) GWZ_LAUNCH(launch_combo_sweep(K, cb, c->stream));
+    else GWZ_LAUNCH(launch_gen_sweep(K, c->stream));
     GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
     GWZ_LAUNCH(launch_reduce_partials(s->d_partials, (int)rows, L, s->d_vec, c->stream));
     if (c->comm) {
@@ -675,18 +736,21 @@ static int gsweep_terms_impl(gwz_gsweep* s, const double* params, uint64_t first
     const int P = a->P, L = 2 + 2 * P, W = a->m->W;
     GenSweepLaunch K;
     std::memset(&K, 0, sizeof(K));
+    GenCombo cb;
+    bool combo = false;
     if (params) {
-        if (int rc = upload_params(a, params, &K.gm)) return rc;
+        if (int rc = prepare_params(a, params, &K.gm, &cb, &combo)) return rc;
     } else {
         std::vector<double> zero((size_t)P, 0.0);
-        if (int rc = upload_params(a, zero.data(), &K.gm)) return rc;
+        if (int rc = prepare_params(a, zero.data(), &K.gm, &cb, &combo)) return rc;
     }
     DevBuf<double> d_out;
     DevBuf<uint64_t> d_st;
     if (out) GWZ_CUDA(d_out.alloc(count * L));
     if (states) GWZ_CUDA(d_st.alloc(count * W));
     int grid = 0;
-    GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)count, c->prop.multiProcessorCount, &grid));
+    if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)count, c->prop.multiProcessorCount, &grid));
+    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)count, c->prop.multiProcessorCount, &grid));
     const size_t rows = (size_t)grid * GEN_WARPS;
     K.basis = s->d_basis;
     K.dim = s->dim;
@@ -699,7 +763,8 @@ static int gsweep_terms_impl(gwz_gsweep* s, const double* params, uint64_t first
     K.first = first;
     K.count = count;
     K.grid = grid;
-    GWZ_LAUNCH(launch_gen_sweep(K, c->stream));
+    if (combo) GWZ_LAUNCH(launch_combo_sweep(K, cb, c->stream));
+    else GWZ_LAUNCH(launch_gen_sweep(K, c->stream));
     if (out) GWZ_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * count * L, cudaMemcpyDeviceToHost, c->stream));
     if (states) GWZ_CUDA(cudaMemcpyAsync(states, d_st.p, sizeof(uint64_t) * count * W, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));

@@ -51,16 +51,6 @@ __global__ void gen_occ_to_unary_kernel(const uint8_t* __restrict__ occ, size_t 
     for (int i = 0; i < W; ++i) addr[w * (size_t)W + i] = a[i];
 }
 
-// phi(n) = 1/2 n^T Q n + b^T n + s (sum log n! - log K)  (psi = exp(-phi))
-__device__ __forceinline__ double gen_phi(const GenModel& gm, const GenWarp& ws, int lane, double lgsum) {
-    double acc = 0.0;
-    for (int k = lane; k < gm.M; k += 32) {
-        const int n = ws.occ[k];
-        if (n) acc = fma((double)n, 0.5 * (ws.V[k] + gm.bvec[k]), acc);
-    }
-    return warp_sum_all(acc) + gm.s * (lgsum - gm.logK);
-}
-
 // ------------------------------------------------------------------------------------------
 // probe: one kinetic_sample! (qmc.jl:14-44) and / or val_and_grad(ansatz, addr, p) per address
 // ------------------------------------------------------------------------------------------

@@ -60,19 +60,52 @@ struct GenModel {
     const uint16_t* pair_j;
 };
 
+// CombinationAnsatz (src/ansatz/combination.jl): psi = alpha psi_1 + (1 - alpha) psi_2 with two log-linear components;
+// parameters (p_1..., p_2..., alpha).  Kernels: gwz_generic_combo.cu.
+struct GenCombo {
+    GenModel g1, g2;
+    double alpha;
+    int P;  // g1.P + g2.P + 1
+};
+
 // per-warp shared-memory slice
 struct GenWarp {
     int* occ;      // [MP]   occupation numbers (zero padded)
     double* V;     // [MP]   potential Q n + b
     double* rate;  // [2*MP] psi(n')/psi(n) of the right (2k) and left (2k+1) hop out of mode k; 0 = no hop
     double* mr;    // [2*MP] matrix element * rate (sweep)
+    // combination kernels only: second potential, per-hop exponents of the two components, per-hop alpha-gradient
+    double* V2;    // [MP]
+    double* e1;    // [2*MP]
+    double* e2;    // [2*MP]
+    double* ga;    // [2*MP]
     __host__ __device__ static size_t bytes(int MP) { return (size_t)MP * (sizeof(int) + 5 * sizeof(double)); }
+    __host__ __device__ static size_t bytes_combo(int MP) { return (size_t)MP * (sizeof(int) + 12 * sizeof(double)); }
     __device__ GenWarp(unsigned char* base, int MP, int warp) {
         unsigned char* p = base + (size_t)warp * bytes(MP);
         V = reinterpret_cast<double*>(p);
         rate = V + MP;
         mr = rate + 2 * MP;
         occ = reinterpret_cast<int*>(mr + 2 * MP);
+        V2 = e1 = e2 = ga = nullptr;
+    }
+    // combination layout (one warp per CTA)
+    struct ComboTag {};
+    __device__ GenWarp(unsigned char* base, int MP, ComboTag) {
+        V = reinterpret_cast<double*>(base);
+        rate = V + MP;
+        mr = rate + 2 * MP;
+        V2 = mr + 2 * MP;
+        e1 = V2 + MP;
+        e2 = e1 + 2 * MP;
+        ga = e2 + 2 * MP;
+        occ = reinterpret_cast<int*>(ga + 2 * MP);
+    }
+    // the same slice seen by component 2 (its potential in place of V)
+    __device__ GenWarp second() const {
+        GenWarp w = *this;
+        w.V = V2;
+        return w;
     }
 };
 
@@ -219,6 +252,16 @@ __device__ __forceinline__ double gen_dfeature(const GenModel& gm, const GenWarp
             return (double)(na2 * nb2 - na * nb);
         }
     }
+}
+
+// phi(n) = 1/2 n^T Q n + b^T n + s (sum log n! - log K)  (psi = exp(-phi))
+__device__ __forceinline__ double gen_phi(const GenModel& gm, const GenWarp& ws, int lane, double lgsum) {
+    double acc = 0.0;
+    for (int k = lane; k < gm.M; k += 32) {
+        const int n = ws.occ[k];
+        if (n) acc = fma((double)n, 0.5 * (ws.V[k] + gm.bvec[k]), acc);
+    }
+    return warp_sum_all(acc) + gm.s * (lgsum - gm.logK);
 }
 
 // hop rates of the modes this lane owns, in reference order; lane sums of the rates, of

@@ -181,5 +181,11 @@ cudaError_t launch_gen_walkers(const GenWalkerLaunch& L, cudaStream_t s);
 cudaError_t launch_gen_estimates(const double* acc, size_t n, int P, const double* shift, double* val_w, double* grad_w,
                                  cudaStream_t s);
 cudaError_t launch_gen_sweep(const GenSweepLaunch& L, cudaStream_t s);
+// CombinationAnsatz (gwz_generic_combo.cu): same launch descriptors, L.gm is ignored
+cudaError_t combo_walker_grid(const GenCombo& cb, size_t n, int sm_count, int* grid);
+cudaError_t combo_sweep_grid(const GenCombo& cb, size_t n, int sm_count, int* grid);
+cudaError_t launch_combo_probe(const GenProbeLaunch& L, const GenCombo& cb, cudaStream_t s);
+cudaError_t launch_combo_walkers(const GenWalkerLaunch& L, const GenCombo& cb, cudaStream_t s);
+cudaError_t launch_combo_sweep(const GenSweepLaunch& L, const GenCombo& cb, cudaStream_t s);
 
 }  // namespace gwz

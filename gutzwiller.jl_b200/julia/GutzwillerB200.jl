@@ -342,8 +342,14 @@ end
 function GPUAnsatz(H, ansatz, ctx::GPUContext=default_context())
     model = GPUModel(H, ctx)
     r = Ref{Ptr{Cvoid}}()
-    check(ccall((:gwz_ansatz_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}),
-                model.ptr, ansatz_kind(ansatz), ansatz_normalize(ansatz), r))
+    if ansatz isa CombinationAnsatz                                    # a1 + a2 (combination.jl:13-15)
+        a1, a2 = ansatz.ansatz1, ansatz.ansatz2
+        check(ccall((:gwz_ansatz_create_combination, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                    model.ptr, ansatz_kind(a1), ansatz_normalize(a1), ansatz_kind(a2), ansatz_normalize(a2), r))
+    else
+        check(ccall((:gwz_ansatz_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                    model.ptr, ansatz_kind(ansatz), ansatz_normalize(ansatz), r))
+    end
     a = GPUAnsatz(r[], model, num_parameters(ansatz))
     finalizer(x -> ccall((:gwz_ansatz_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), a)
     return a

@@ -238,7 +238,8 @@ enum gwz_ansatz_kind {
     GWZ_ANSATZ_MULTINOMIAL = 2,      /* src/ansatz/multinomial.jl:17-59:  P = 1 */
     GWZ_ANSATZ_DENSITY_PROFILE = 3,  /* src/ansatz/densityprofile.jl:8-28: P = M */
     GWZ_ANSATZ_RELATIVE_JASTROW = 4, /* src/ansatz/jastrow.jl:71-103:     P = cld(M, 2) */
-    GWZ_ANSATZ_JASTROW = 5           /* src/ansatz/jastrow.jl:13-58:      P = M (M + 1) / 2 */
+    GWZ_ANSATZ_JASTROW = 5,          /* src/ansatz/jastrow.jl:13-58:      P = M (M + 1) / 2 */
+    GWZ_ANSATZ_COMBINATION = 6       /* src/ansatz/combination.jl: a1 + a2, P = P1 + P2 + 1 (gwz_ansatz_create_combination) */
 };
 typedef struct gwz_ansatz gwz_ansatz;
 typedef struct gwz_gwalkers gwz_gwalkers;
@@ -250,6 +251,9 @@ int gwz_model_create_ext_hubbard1d(gwz_context *ctx, int N, int M, double u, dou
 int gwz_model_info_ext(const gwz_model *m, double *v);
 /* `ansatz = XAnsatz(H)`; normalize: MultinomialAnsatz(H; normalize) (multinomial.jl:22-31) */
 int gwz_ansatz_create(gwz_model *m, int kind, int normalize, gwz_ansatz **out);
+/* `a1 + a2` (combination.jl:13-15): alpha a1 + (1 - alpha) a2 with parameters (p1..., p2..., alpha); both components
+ * from the kinds above */
+int gwz_ansatz_create_combination(gwz_model *m, int kind1, int normalize1, int kind2, int normalize2, gwz_ansatz **out);
 int gwz_ansatz_destroy(gwz_ansatz *a);
 int gwz_ansatz_info(const gwz_ansatz *a, int *kind, int *num_parameters);
 /* ansatz(addr, p) and val_and_grad(ansatz, addr, p): val[n], grad[n x P] (either may be NULL) */

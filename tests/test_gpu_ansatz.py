@@ -12,7 +12,9 @@ RTOL = 1e-12
 
 KINDS = {"gutzwiller": "GutzwillerAnsatz", "ext_gutzwiller": "ExtendedGutzwillerAnsatz",
          "multinomial": "MultinomialAnsatz", "density_profile": "DensityProfileAnsatz",
-         "relative_jastrow": "RelativeJastrowAnsatz", "jastrow": "JastrowAnsatz"}
+         "relative_jastrow": "RelativeJastrowAnsatz", "jastrow": "JastrowAnsatz",
+         # CombinationAnsatz: GutzwillerAnsatz(H) + MultinomialAnsatz(H) is the reference's own test (test/ansatz.jl:58)
+         ("gutzwiller", "multinomial"): None, ("relative_jastrow", "density_profile"): None}
 SHAPES = [  # N, M, u, v, t
     (5, 5, 1.0, 0.0, 0.1),     # test/ansatz.jl:45
     (5, 5, 1.0, 1.0, 0.1),     # test/ansatz.jl:46 (ExtendedHubbardReal1D)
@@ -30,6 +32,12 @@ def _make(gw, oracle_mod, kind, N, M, u, v, t, normalize=False):
     ao = oracle_mod.AnsatzOracle(o, kind, v=v, normalize=normalize)
     addr = gw.near_uniform(N, M)
     H = gw.ExtendedHubbardReal1D(addr, u=u, v=v, t=t) if v else gw.HubbardReal1D(addr, u=u, t=t)
+    if isinstance(kind, tuple):
+        parts = []
+        for k in kind:
+            c = gw.GenericGutzwillerAnsatz if (k == "gutzwiller" and v) else getattr(gw, KINDS[k])
+            parts.append(c(H))
+        return o, ao, H, parts[0] + parts[1]
     cls = getattr(gw, KINDS[kind])
     if kind == "gutzwiller":
         cls = gw.GenericGutzwillerAnsatz  # the generic engine also for plain HubbardReal1D (cross-check of the fast path)
@@ -93,7 +101,9 @@ def test_eval_and_probe_match_oracle(gw, oracle_mod, kind, N, M, u, v, t):
 @pytest.mark.parametrize("kind,N,M,u,v,t", [("relative_jastrow", 5, 5, 1.0, 0.0, 0.1), ("density_profile", 4, 6, 2.0, 0.5, 1.0),
                                             ("jastrow", 5, 5, 1.0, 1.0, 0.1), ("multinomial", 7, 3, 0.7, 0.3, 1.0),
                                             ("ext_gutzwiller", 12, 12, 2.0, 0.3, 1.0), ("gutzwiller", 3, 2, 1.0, 0.4, 1.0),
-                                            ("relative_jastrow", 40, 37, 2.0, 0.25, 1.0)])
+                                            ("relative_jastrow", 40, 37, 2.0, 0.25, 1.0),
+                                            (("gutzwiller", "multinomial"), 5, 5, 1.0, 0.0, 0.1),
+                                            (("relative_jastrow", "density_profile"), 7, 6, 2.0, 0.5, 1.0)])
 def test_walkers_follow_the_oracle_step_for_step(gw, oracle_mod, kind, N, M, u, v, t):
     """Same Philox stream, same hop order, same selection rule => identical trajectories and estimates."""
     o, ao, H, ans = _make(gw, oracle_mod, kind, N, M, u, v, t)
