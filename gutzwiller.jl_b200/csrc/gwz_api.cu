@@ -984,7 +984,8 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
         GWZ_CUDA(cudaMalloc(&s->d_binom, sizeof(uint64_t) * 65 * 65));
         GWZ_CUDA(cudaMemcpyAsync(s->d_binom, tab.data(), sizeof(uint64_t) * 65 * 65, cudaMemcpyHostToDevice, c->stream));
     }
-    GWZ_CUDA(sweep_grid(m->nw, s->d_basis == nullptr, s->dim, c->prop.multiProcessorCount, &s->grid, &s->chunk));
+    GWZ_CUDA(sweep_grid(m->nw, choose_kc(m, 0.0, true), m->N, m->M, s->d_basis == nullptr, s->dim, c->prop.multiProcessorCount,
+                        &s->grid, &s->chunk));
     GWZ_CUDA(cudaMalloc(&s->d_partials, sizeof(double) * 4 * (size_t)s->grid));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     *out = s;

@@ -89,6 +89,19 @@ struct StepScratch {
         ew = er + KC * NW * STEP_BLOCK;
         bw = ew + NW * STEP_BLOCK;
     }
+    // sweep kernels never select a move: no prefix sums, no staged class masks (3 KB instead of ~40 KB per CTA)
+    struct SweepLayout {};
+    __host__ __device__ static constexpr size_t bytes_sweep(int N) {
+        return exptab_bytes(N) + sizeof(uint32_t) * (2 * NW) * STEP_BLOCK;
+    }
+    __device__ __forceinline__ StepScratch(unsigned char* base, int N, SweepLayout) {
+        exptab = reinterpret_cast<double*>(base);
+        sqrtab = exptab + (2 * N + 2);
+        cum = nullptr;
+        el = er = nullptr;
+        ew = reinterpret_cast<uint32_t*>(sqrtab + (N + 2));
+        bw = ew + NW * STEP_BLOCK;
+    }
     // CTA-wide: tabulate the hop rates once per launch (keeps exp() out of the step loop)
     __device__ __forceinline__ void fill_exptab(int N, double c) const {
         for (int i = threadIdx.x; i < 2 * N + 2; i += blockDim.x) exptab[i] = exp(-c * (double)(i - N));

@@ -116,7 +116,7 @@ struct SweepLaunch {
     uint64_t* states_out;  // AoS count x W
     uint64_t first, count;
 };
-cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk);
+cudaError_t sweep_grid(int nw, int kc, int N, int M, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk);
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s);
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s);
 

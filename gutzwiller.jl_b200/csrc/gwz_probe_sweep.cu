@@ -99,7 +99,7 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
              const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
              const uint64_t* __restrict__ binom, double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW, KC> sc(smem_raw, dm.N);
+    const StepScratch<NW, KC> sc(smem_raw, dm.N, typename StepScratch<NW, KC>::SweepLayout{});
     sc.fill_exptab(dm.N, tb.c);
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, uint64_t dim,
                  uint64_t rank_begin, uint64_t chunk, const uint64_t* __restrict__ binom, double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW, KC> sc(smem_raw, dm.N);
+    const StepScratch<NW, KC> sc(smem_raw, dm.N, typename StepScratch<NW, KC>::SweepLayout{});
     sc.fill_exptab(dm.N, tb.c);
     __shared__ uint64_t qx[SWEEP_BLOCK / 32][64];
     __shared__ int qm[SWEEP_BLOCK / 32][64];
@@ -274,7 +274,7 @@ sweep_terms_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                    const uint64_t* __restrict__ binom, uint64_t first, uint64_t count,
                    double* __restrict__ out, uint64_t* __restrict__ states_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const StepScratch<NW, KC> sc(smem_raw, dm.N);
+    const StepScratch<NW, KC> sc(smem_raw, dm.N, typename StepScratch<NW, KC>::SweepLayout{});
     sc.fill_exptab(dm.N, tb.c);
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -346,15 +346,19 @@ cudaError_t launch_ansatz(const DevModel& dm, double g, int nw, const uint64_t* 
     return cudaGetLastError();
 }
 
-cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk) {
-    (void)nw;
-    // aim at >= 8 resident CTAs per SM; in ranked mode amortise the unranking over `chunk` states
-    const uint64_t max_threads = (uint64_t)sm_count * 16 * SWEEP_BLOCK;
+cudaError_t sweep_grid(int nw, int kc, int N, int M, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk) {
+    (void)nw; (void)kc; (void)N; (void)M;
     uint64_t c = 1;
+    uint64_t max_threads = (uint64_t)sm_count * 16 * SWEEP_BLOCK;
     if (ranked) {
-        c = (dim + max_threads - 1) / max_threads;
-        if (c < 8) c = 8;
-        if (c > 1024) c = 1024;
+        // Every thread Gosper-steps through runs of `chunk` consecutive ranks (the unranking is amortised over the
+        // run).  The cost of a rank varies along the rank range (the orbit test exits early for most low ranks), so
+        // runs are kept short and CTAs many: the block scheduler balances them (measured: one resident wave of long
+        // runs is 1.8x slower on {16,16} and 3.4x on {18,18}).
+        const uint64_t wave = (uint64_t)sm_count * 16 * SWEEP_BLOCK;  // enough threads to fill the chip
+        c = (dim + wave - 1) / wave;
+        c = c < 8 ? 8 : (c > 256 ? 256 : c);
+        max_threads = (uint64_t)sm_count * 4096 * SWEEP_BLOCK;  // beyond that threads take several runs
     }
     uint64_t threads = (dim + c - 1) / c;
     if (threads > max_threads) threads = max_threads;
@@ -368,7 +372,7 @@ cudaError_t sweep_grid(int nw, bool ranked, uint64_t dim, int sm_count, int* gri
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
     const bool ranked = (L.basis == nullptr);
     GWZ_DISPATCH_NW(L.nw, L.tb.kc, {
-        const size_t smem = StepScratch<NW, KC>::bytes(L.dm.N);
+        const size_t smem = StepScratch<NW, KC>::bytes_sweep(L.dm.N);
         if (ranked && L.symmetric && L.dm.N + L.dm.M <= 64) {
             if (cudaError_t e = ensure_smem(sweep_sym_kernel<NW, KC>, smem)) return e;
             sweep_sym_kernel<NW, KC><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.dim, L.rank_begin, L.chunk, L.binom,
@@ -391,7 +395,7 @@ cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s) {
     const bool ranked = (L.basis == nullptr);
     const unsigned grid = (unsigned)((L.count + SWEEP_BLOCK - 1) / SWEEP_BLOCK);
     GWZ_DISPATCH_NW(L.nw, L.tb.kc, {
-        const size_t smem = StepScratch<NW, KC>::bytes(L.dm.N);
+        const size_t smem = StepScratch<NW, KC>::bytes_sweep(L.dm.N);
         if (ranked) {
             if (cudaError_t e = ensure_smem(sweep_terms_kernel<NW, KC, true>, smem)) return e;
             sweep_terms_kernel<NW, KC, true><<<grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.binom,
