@@ -514,6 +514,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
     gwz_walkers* w = new gwz_walkers();
+    HandleGuard<gwz_walkers, gwz_walkers_destroy> guard(w);
     w->m = m;
     w->n = (size_t)n_walkers;
     w->offset = global_offset;
@@ -530,7 +531,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     GWZ_CUDA(cudaMemcpyAsync(d_start.p, start_addr, sizeof(uint64_t) * m->W, cudaMemcpyHostToDevice, c->stream));
     GWZ_LAUNCH(launch_walker_init(w->d_addr, w->d_acc, w->n, m->W, d_start.p, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
-    *out = w;
+    *out = guard.release();
     return GWZ_OK;
 }
 
@@ -956,6 +957,7 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
     gwz_sweep* s = new gwz_sweep();
+    HandleGuard<gwz_sweep, gwz_sweep_destroy> guard(s);
     s->m = m;
     if (basis_words) {
         GWZ_REQUIRE(dim >= 1, "gwz_sweep_create: empty basis");
@@ -988,7 +990,7 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
                         &s->grid, &s->chunk));
     GWZ_CUDA(cudaMalloc(&s->d_partials, sizeof(double) * 4 * (size_t)s->grid));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
-    *out = s;
+    *out = guard.release();
     return GWZ_OK;
 }
 

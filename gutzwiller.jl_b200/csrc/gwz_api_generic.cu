@@ -90,6 +90,7 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     GWZ_REQUIRE(N <= 255, "gwz_ansatz_create: N must be <= 255");
     if (int rc = use_device(m->ctx)) return rc;
     gwz_ansatz* a = new gwz_ansatz();
+    HandleGuard<gwz_ansatz, gwz_ansatz_destroy> guard(a);
     a->m = m;
     a->kind = kind;
     a->P = P;
@@ -146,7 +147,7 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     gm.sqrtab = a->d_static + 2 * T;
     gm.pair_i = a->d_pairs;
     gm.pair_j = a->d_pairs + P;
-    *out = a;
+    *out = guard.release();
     return GWZ_OK;
 }
 extern "C" int gwz_ansatz_create_combination(gwz_model* m, int kind1, int normalize1, int kind2, int normalize2,
@@ -384,6 +385,7 @@ extern "C" int gwz_gwalkers_create(gwz_ansatz* a, uint64_t n_walkers, uint64_t g
         GWZ_REQUIRE(ones == a->m->N, "gwz_gwalkers_create: start address does not hold N particles");
     }
     gwz_gwalkers* w = new gwz_gwalkers();
+    HandleGuard<gwz_gwalkers, gwz_gwalkers_destroy> guard(w);
     w->a = a;
     w->n = (size_t)n_walkers;
     w->offset = global_offset;
@@ -402,7 +404,7 @@ extern "C" int gwz_gwalkers_create(gwz_ansatz* a, uint64_t n_walkers, uint64_t g
     GWZ_CUDA(cudaMemcpyAsync(w->d_addr1, start_addr, sizeof(uint64_t) * a->m->W, cudaMemcpyHostToDevice, c->stream));
     GWZ_LAUNCH(launch_gen_unary_to_occ(w->d_addr1, w->n, a->gm, a->Mpad, w->d_occ, true, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
-    *out = w;
+    *out = guard.release();
     return GWZ_OK;
 }
 extern "C" int gwz_gwalkers_destroy(gwz_gwalkers* w) {
@@ -410,11 +412,11 @@ extern "C" int gwz_gwalkers_destroy(gwz_gwalkers* w) {
     if (use_device(w->a->m->ctx) == GWZ_OK) {
         cudaFree(w->d_occ);
         cudaFree(w->d_acc);
-        if (w->d_partials) cudaFree(w->d_partials);
+        cudaFree(w->d_partials);
         cudaFree(w->d_vec);
-        cudaFreeHost(w->h_vec);
+        if (w->h_vec) cudaFreeHost(w->h_vec);
         cudaFree(w->d_shift);
-        cudaFreeHost(w->h_shift);
+        if (w->h_shift) cudaFreeHost(w->h_shift);
         cudaFree(w->d_addr1);
     }
     delete w;
@@ -628,6 +630,7 @@ extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uin
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
     gwz_gsweep* s = new gwz_gsweep();
+    HandleGuard<gwz_gsweep, gwz_gsweep_destroy> guard(s);
     s->a = a;
     if (basis_words) {
         GWZ_REQUIRE(dim >= 1, "gwz_gsweep_create: empty basis");
@@ -655,7 +658,7 @@ extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uin
     const int L = 2 + 2 * a->P;
     GWZ_CUDA(cudaMalloc(&s->d_vec, sizeof(double) * L));
     GWZ_CUDA(cudaMallocHost(&s->h_vec, sizeof(double) * L));
-    *out = s;
+    *out = guard.release();
     return GWZ_OK;
 }
 extern "C" int gwz_gsweep_destroy(gwz_gsweep* s) {
@@ -665,7 +668,7 @@ extern "C" int gwz_gsweep_destroy(gwz_gsweep* s) {
         if (s->d_binom) cudaFree(s->d_binom);
         if (s->d_partials) cudaFree(s->d_partials);
         cudaFree(s->d_vec);
-        cudaFreeHost(s->h_vec);
+        if (s->h_vec) cudaFreeHost(s->h_vec);
     }
     delete s;
     return GWZ_OK;

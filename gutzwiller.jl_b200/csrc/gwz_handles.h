@@ -68,6 +68,24 @@ static inline int use_device(const gwz_context* ctx) {
     return GWZ_OK;
 }
 
+// releases a half-built handle when a create function fails midway (the destroy functions accept partially
+// initialised objects: cudaFree(nullptr) is a no-op)
+template <typename H, int (*DESTROY)(H*)>
+struct HandleGuard {
+    H* h;
+    explicit HandleGuard(H* p) : h(p) {}
+    HandleGuard(const HandleGuard&) = delete;
+    HandleGuard& operator=(const HandleGuard&) = delete;
+    ~HandleGuard() {
+        if (h) DESTROY(h);
+    }
+    H* release() {
+        H* t = h;
+        h = nullptr;
+        return t;
+    }
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
