@@ -215,7 +215,6 @@ __device__ __forceinline__ void step_incr(uint32_t (&p)[NP][NWM], const DevModel
     // ---- class-ordered move selection (same partition of [0,S) as select_move) ----
     int z;
     bool right;
-    int lsel = -1, rsel = -1;  // class of the selected bond (regular path): the occupations of modes z and z+1
     if (T < reg_total || !(bigS > 0.0)) {
         if (!(T < reg_total)) T = __longlong_as_double(__double_as_longlong(reg_total) - 1);
         // row: first l with T < rowcum[l]
@@ -264,8 +263,6 @@ __device__ __forceinline__ void step_incr(uint32_t (&p)[NP][NWM], const DevModel
             j -= fnd ? 0 : pc;
         }
         z = pos + nth_set_bit32_lut(word, j, sc.nth);
-        lsel = l;
-        rsel = r;
     } else {
         const BigOut o = big.pass(1, T - reg_total);
         z = o.z;
@@ -280,12 +277,7 @@ __device__ __forceinline__ void step_incr(uint32_t (&p)[NP][NWM], const DevModel
     const int zp = (zn + 1 == M) ? 0 : zn + 1;
     unsigned char* const ob = reinterpret_cast<unsigned char*>(sc.onr + tid);
     auto off = [](int m) { return (m >> 2) * (STEP_BLOCK * 4) + (m & 3); };
-    const int a = ob[off(zm)], b = ob[off(zp)];
-    int x = lsel, y = rsel;  // a regular bond of class (l, r) has exactly n_z = l, n_{z+1} = r
-    if (lsel < 0) {
-        x = ob[off(z)];
-        y = ob[off(zn)];
-    }
+    const int a = ob[off(zm)], x = ob[off(z)], y = ob[off(zn)], b = ob[off(zp)];
     const int x2 = right ? x - 1 : x + 1, y2 = right ? y + 1 : y - 1;
     ob[off(z)] = (unsigned char)x2;
     ob[off(zn)] = (unsigned char)y2;

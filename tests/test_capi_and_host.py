@@ -201,3 +201,29 @@ def test_sharding_is_invariant_under_world_size_gloo(oracle_mod):
     for _, acc in res:
         assert acc[0] == 10
         assert abs(acc[1] / 10 - single["val"]) < 1e-12 and abs(acc[2] / 10 - single["grad"]) < 1e-11
+
+
+def test_generic_ansatz_host_objects(gw):
+    """Host mirrors of the other ansaetze (no device work: handles are created lazily)."""
+    H = gw.HubbardReal1D(gw.BoseFS(1, 1, 1, 1, 1), t=0.1)
+    He = gw.ExtendedHubbardReal1D(gw.near_uniform(5, 5), v=0.5, t=0.1)
+    M = 5
+    assert gw.num_parameters(gw.JastrowAnsatz(H)) == M * (M + 1) // 2          # jastrow.jl:20
+    assert gw.num_parameters(gw.RelativeJastrowAnsatz(H)) == (M + 1) // 2      # cld(M, 2), jastrow.jl:78
+    assert gw.num_parameters(gw.DensityProfileAnsatz(H)) == M                  # densityprofile.jl:15
+    assert gw.num_parameters(gw.MultinomialAnsatz(H, normalize=True)) == 1
+    assert gw.num_parameters(gw.ExtendedGutzwillerAnsatz(He)) == 2
+    g = gw.GutzwillerAnsatz(H)
+    ge = gw.GutzwillerAnsatz(He)
+    assert not getattr(g, "generic", False) and getattr(ge, "generic", False) and isinstance(ge, gw.GutzwillerAnsatz)
+    combo = g + gw.MultinomialAnsatz(H)                                       # test/ansatz.jl:58
+    assert isinstance(combo, gw.CombinationAnsatz) and gw.num_parameters(combo) == 3   # combination.jl:14
+    assert gw.num_parameters(gw.RelativeJastrowAnsatz(H) + gw.DensityProfileAnsatz(H)) == 3 + 5 + 1
+    with pytest.raises(TypeError):
+        g + gw.MultinomialAnsatz(He)      # different Hamiltonians
+    with pytest.raises(TypeError):
+        combo + g                         # nested combinations are not supported
+    with pytest.raises(TypeError):
+        gw.RelativeJastrowAnsatz("not a hamiltonian")
+    assert gw.keytype(combo) is gw.BoseFS and gw.valtype(combo) is float
+    assert repr(He).startswith("ExtendedHubbardReal1D(") and "v=0.5" in repr(He)
