@@ -227,3 +227,9 @@ def test_generic_ansatz_host_objects(gw):
         gw.RelativeJastrowAnsatz("not a hamiltonian")
     assert gw.keytype(combo) is gw.BoseFS and gw.valtype(combo) is float
     assert repr(He).startswith("ExtendedHubbardReal1D(") and "v=0.5" in repr(He)
+
+
+def test_graft_entry_build_is_consistent_with_the_header():
+    """build() (the driver's "does it build" check) must accept the library it has just built."""
+    import __graft_entry__ as g
+    g.build()
