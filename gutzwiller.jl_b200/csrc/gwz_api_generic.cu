@@ -472,10 +472,10 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
     GenCombo cb;
     bool combo = false;
     if (int rc = prepare_params(a, params, &K.gm, &cb, &combo)) return rc;
-    int grid = 0;
+    int grid = 0, per_cta = 1;
     if (combo) GWZ_CUDA(combo_walker_grid(cb, w->n, c->prop.multiProcessorCount, &grid));
-    else GWZ_CUDA(gen_walker_grid(K.gm, w->n, c->prop.multiProcessorCount, &grid));
-    const size_t rows = (size_t)grid * GEN_WARPS;
+    else GWZ_CUDA(gen_walker_grid(K.gm, w->n, c->prop.multiProcessorCount, &grid, &per_cta));
+    const size_t rows = (size_t)grid * per_cta;
     if (rows > w->partials_rows) {
         if (w->d_partials) cudaFree(w->d_partials);
         w->d_partials = nullptr;

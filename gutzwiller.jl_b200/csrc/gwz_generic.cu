@@ -154,7 +154,9 @@ gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
 #ifndef GWZ_GEN_MIN_BLOCKS
 #define GWZ_GEN_MIN_BLOCKS 24
 #endif
-template <int PPL, int MPL>
+// G lanes per walker (32 / G walkers per warp): lane gl of a group owns the modes [gl*MPL, (gl+1)*MPL) for the rates and
+// the parameters gl + G q; the groups of a warp advance in lockstep (same number of steps), each with its own walker.
+template <int G, int PPL, int MPL>
 __global__ void __launch_bounds__(GEN_BLOCK, PPL <= 2 ? GWZ_GEN_MIN_BLOCKS : (PPL == 4 ? 12 : 8))
 gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ PhiloxKeys pk, uint8_t* __restrict__ occ_g,
                   int Mpad, double* __restrict__ acc_g, size_t n, uint64_t goff, uint64_t step0, uint64_t steps,
@@ -162,16 +164,17 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                   double* __restrict__ rec_tau, double* __restrict__ rec_eloc, uint64_t* __restrict__ rec_addr,
                   int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const GenWarp ws(smem_raw, 32 * MPL, warp);  // compile-time slice layout: offsets fold into the LDS/STS immediates
-    const size_t gwarp = (size_t)blockIdx.x * GEN_WARPS + warp, nwarps = (size_t)gridDim.x * GEN_WARPS;
+    constexpr int GROUPS = 32 / G;  // walkers per warp (one warp per CTA)
+    const int lane = threadIdx.x & (G - 1), group = (threadIdx.x & 31) / G;
+    const GenWarp ws(smem_raw, G * MPL, group);  // compile-time slice layout: offsets fold into the LDS/STS immediates
+    const size_t gwarp = (size_t)blockIdx.x * GROUPS + group, nwarps = (size_t)gridDim.x * GROUPS;
     const int M = gm.M, P = gm.P;
     const int AW = 3 + 2 * P;  // per-walker sums in HBM: st, stE, stEE, stG[P], stGE[P]
     const double E0 = (accumulate && shift) ? shift[0] : 0.0;
     double G0[PPL];
 #pragma unroll
     for (int q = 0; q < PPL; ++q) {
-        const int p = lane + 32 * q;
+        const int p = lane + G * q;
         G0[q] = (accumulate && shift && p < P) ? shift[1 + p] : 0.0;
     }
     double ps[GEN_HEAD];
@@ -182,17 +185,19 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
     for (int q = 0; q < PPL; ++q) pv[0][q] = pv[1][q] = pv[2][q] = pv[3][q] = 0.0;
     bool bad = false;
 
-    for (size_t w = gwarp; w < n; w += nwarps) {
-        for (int k = lane; k < gm.MP; k += 32) ws.occ[k] = (k < M) ? (int)occ_g[w * (size_t)Mpad + k] : 0;
+    for (size_t wb = (size_t)blockIdx.x * GROUPS; wb < n; wb += nwarps) {  // warp-uniform trip count
+        const bool live = wb + group < n;
+        const size_t w = live ? wb + group : n - 1;  // a spare group repeats the last walker and writes nothing
+        for (int k = lane; k < G * MPL; k += G) ws.occ[k] = (k < M) ? (int)occ_g[w * (size_t)Mpad + k] : 0;
         __syncwarp();
-        gen_potential(gm, ws, lane);
+        gen_potential<G>(gm, ws, lane);
         long long reg, ext;
         double lgsum;
-        gen_totals(gm, ws, lane, reg, ext, lgsum);
+        gen_totals<G>(gm, ws, lane, reg, ext, lgsum);
         double F[PPL], aG[PPL], aGE[PPL];
 #pragma unroll
         for (int q = 0; q < PPL; ++q) {
-            const int p = lane + 32 * q;
+            const int p = lane + G * q;
             F[q] = (p < P) ? gen_feature(gm, ws, p, reg, ext, lgsum) : 0.0;
             aG[q] = aGE[q] = 0.0;
         }
@@ -204,7 +209,7 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             stee = a[2];
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
-                const int p = lane + 32 * q;
+                const int p = lane + G * q;
                 if (p < P) {
                     aG[q] = a[3 + p];
                     aGE[q] = a[3 + P + p];
@@ -216,17 +221,17 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
         uint32_t rnd[4] = {0u, 0u, 0u, 0u};
         unsigned long long hops = 0ull;
         int nocc = 0;
-        for (int k = lane; k < M; k += 32) nocc += ws.occ[k] > 0;
-        nocc = warp_sum_all(nocc);
+        for (int k = lane; k < M; k += G) nocc += ws.occ[k] > 0;
+        nocc = warp_sum_all<G>(nocc);
 
         for (uint64_t k = 0; k < steps; ++k) {
             const uint64_t step = step0 + k;
             if (k != 0 && (k % GEN_REFRESH) == 0) {  // bound the rounding drift of the incremental V and F
-                gen_potential(gm, ws, lane);
-                gen_totals(gm, ws, lane, reg, ext, lgsum);
+                gen_potential<G>(gm, ws, lane);
+                gen_totals<G>(gm, ws, lane, reg, ext, lgsum);
 #pragma unroll
                 for (int q = 0; q < PPL; ++q) {
-                    const int p = lane + 32 * q;
+                    const int p = lane + G * q;
                     if (p < P) F[q] = gen_feature(gm, ws, p, reg, ext, lgsum);
                 }
             }
@@ -238,17 +243,17 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             double S_lane, E_lane;
             int nocc_lane;
             gen_rates<MPL, false>(gm, ws, lane, S_lane, E_lane, nocc_lane);
-            const double cum = warp_scan_incl(S_lane, lane);
-            const double S = __shfl_sync(0xffffffffu, cum, 31);
-            const double Etot = warp_sum_all(E_lane);
+            const double cum = warp_scan_incl<G>(S_lane, lane);
+            const double S = __shfl_sync(0xffffffffu, cum, G - 1, G);
+            const double Etot = warp_sum_all<G>(E_lane);
             const double tau = 1.0 / S;
             const double eloc = gm.u * (double)reg + gm.v * (double)ext - gm.t * Etot;
             bad |= !(tau < 1.0e300);
-            if (rec_tau && lane == 0) {
+            if (rec_tau && lane == 0 && live) {
                 rec_tau[k * n + w] = tau;
                 rec_eloc[k * n + w] = eloc;
             }
-            if (rec_addr) gen_encode(gm, ws, lane, rec_addr + (k * n + w) * (size_t)gm.W);
+            if (rec_addr && live) gen_encode(gm, ws, lane, rec_addr + (k * n + w) * (size_t)gm.W);
             const double dE = eloc - E0;
             const double tE = tau * dE;
             st += tau;
@@ -264,12 +269,12 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             double T = u01 * S;
             if (!(T < S)) T = __longlong_as_double(__double_as_longlong(S) - 1);
             int src, right;
-            gen_select<MPL>(gm, ws, lane, S_lane, cum, T, src, right);
+            gen_select<MPL, G>(gm, ws, lane, S_lane, cum, T, src, right);
             const int dst = right ? (src + 1 == M ? 0 : src + 1) : (src == 0 ? M - 1 : src - 1);
             nocc += (ws.occ[dst] == 0) - (ws.occ[src] == 1);  // occupied modes, carried exactly
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
-                const int p = lane + 32 * q;
+                const int p = lane + G * q;
                 if (p < P) F[q] += gen_dfeature(gm, ws, p, src, dst);
             }
             reg += ws.occ[dst] - ws.occ[src] + 1;
@@ -280,7 +285,7 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                 const double* qs = gm.Qt + (size_t)src * M;
 #pragma unroll
                 for (int q = 0; q < MPL; ++q) {
-                    const int m = lane + 32 * q;
+                    const int m = lane + G * q;
                     if (m < M) ws.V[m] += __ldg(qd + m) - __ldg(qs + m);
                 }
             }
@@ -291,8 +296,9 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             __syncwarp();
         }
 
-        for (int k = lane; k < M; k += 32) occ_g[w * (size_t)Mpad + k] = (uint8_t)ws.occ[k];
-        if (accumulate) {
+        if (live)
+            for (int k = lane; k < M; k += G) occ_g[w * (size_t)Mpad + k] = (uint8_t)ws.occ[k];
+        if (accumulate && live) {
             double* a = acc_g + w * (size_t)AW;
             if (lane == 0) {
                 a[0] = st;
@@ -312,7 +318,7 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             ps[GS_STEPS] += (double)steps;
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
-                const int p = lane + 32 * q;
+                const int p = lane + G * q;
                 if (p < P) {
                     a[3 + p] = aG[q];
                     a[3 + P + p] = aGE[q];
@@ -335,7 +341,7 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
         for (int i = 0; i < GEN_HEAD; ++i) out[i] = ps[i];
 #pragma unroll
     for (int q = 0; q < PPL; ++q) {
-        const int p = lane + 32 * q;
+        const int p = lane + G * q;
         if (p < P) {
             out[GEN_HEAD + p] = pv[0][q];
             out[GEN_HEAD + P + p] = pv[1][q];
@@ -489,24 +495,92 @@ static cudaError_t gen_grid_for(K kernel, const GenModel& gm, size_t n, int sm_c
     if (*grid < 1) *grid = 1;
     return cudaSuccess;
 }
-template <int PPL>
-static cudaError_t gen_walker_grid_ppl(const GenModel& gm, size_t n, int sm_count, int* grid) {
-    switch (gm.MPL) {
-        case 1: return gen_grid_for(gen_walker_kernel<PPL, 1>, gm, n, sm_count, grid);
-        case 2: return gen_grid_for(gen_walker_kernel<PPL, 2>, gm, n, sm_count, grid);
-        case 4: return gen_grid_for(gen_walker_kernel<PPL, 4>, gm, n, sm_count, grid);
-        case 8: return gen_grid_for(gen_walker_kernel<PPL, 8>, gm, n, sm_count, grid);
+// Lanes per walker: the smallest group with <= 4 modes and <= 2 parameters per lane, else <= 4 modes and <= 8
+// parameters, else the whole warp.  Measured on B200 (tools/gen_bench.py): with 8 modes per lane the serial per-lane work
+// outweighs the amortised scalar work ({50,50}: G=8 0.92e9, G=16 1.21e9, G=32 1.14e9 walker-steps/s), and many parameter
+// slots per lane cost more than the group saves (DensityProfile {50,50}, P=50: G=16 0.99e9, G=32 1.14e9).
+int gen_group(int M, int P) {
+    for (int pass = 0; pass < 2; ++pass)
+        for (int G = 8; G <= 32; G *= 2)
+            if ((M + G - 1) / G <= 4 && (P + G - 1) / G <= (pass == 0 ? 2 : 8)) return G;
+    return (M <= 256 && P <= 256) ? 32 : 0;
+}
+static int gen_slots(int need) { return need <= 1 ? 1 : (need <= 2 ? 2 : (need <= 4 ? 4 : 8)); }
+
+// only the (G, PPL, MPL) combinations gen_group can produce are instantiated
+template <int G, int PPL, int MPL>
+constexpr bool gen_walker_combo_used() {
+    return MPL <= 4 || G == 32;  // groups narrower than the warp are only chosen with <= 4 modes per lane
+}
+
+struct GenWalkerOp {
+    const GenWalkerLaunch* L;  // null: occupancy query
+    const GenModel* gm;
+    size_t n;
+    int sm_count;
+    int* grid;
+    cudaStream_t s;
+};
+template <int G, int PPL, int MPL>
+static cudaError_t gen_walker_do(const GenWalkerOp& op) {
+    if constexpr (!gen_walker_combo_used<G, PPL, MPL>()) {
+        return cudaErrorInvalidValue;
+    } else {
+        const size_t smem = (size_t)(32 / G) * GenWarp::bytes(G * MPL);  // one slice per walker of the warp
+        if (cudaError_t e = gen_prepare(gen_walker_kernel<G, PPL, MPL>, smem)) return e;
+        if (op.L == nullptr) {
+            int per_sm = 0;
+            if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_walker_kernel<G, PPL, MPL>, GEN_BLOCK, smem))
+                return e;
+            if (per_sm < 1) per_sm = 1;
+            const size_t resident = (size_t)per_sm * op.sm_count;
+            const size_t need = (op.n + (32 / G) - 1) / (32 / G);
+            *op.grid = (int)(need < resident ? need : resident);
+            if (*op.grid < 1) *op.grid = 1;
+            return cudaSuccess;
+        }
+        const GenWalkerLaunch& L = *op.L;
+        gen_walker_kernel<G, PPL, MPL><<<L.grid, GEN_BLOCK, smem, op.s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n,
+                                                                         L.global_offset, L.step0, L.steps, L.accumulate, L.reset_acc,
+                                                                         L.shift, L.partials, L.rec_tau, L.rec_eloc, L.rec_addr,
+                                                                         L.err_flag);
+        return cudaGetLastError();
+    }
+}
+template <int G, int PPL>
+static cudaError_t gen_walker_mpl(int mpl, const GenWalkerOp& op) {
+    switch (mpl) {
+        case 1: return gen_walker_do<G, PPL, 1>(op);
+        case 2: return gen_walker_do<G, PPL, 2>(op);
+        case 4: return gen_walker_do<G, PPL, 4>(op);
+        case 8: return gen_walker_do<G, PPL, 8>(op);
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t gen_walker_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
-    switch (gen_ppl(gm.P)) {
-        case 1: return gen_walker_grid_ppl<1>(gm, n, sm_count, grid);
-        case 2: return gen_walker_grid_ppl<2>(gm, n, sm_count, grid);
-        case 4: return gen_walker_grid_ppl<4>(gm, n, sm_count, grid);
-        case 8: return gen_walker_grid_ppl<8>(gm, n, sm_count, grid);
+template <int G>
+static cudaError_t gen_walker_ppl(int ppl, int mpl, const GenWalkerOp& op) {
+    switch (ppl) {
+        case 1: return gen_walker_mpl<G, 1>(mpl, op);
+        case 2: return gen_walker_mpl<G, 2>(mpl, op);
+        case 4: return gen_walker_mpl<G, 4>(mpl, op);
+        case 8: return gen_walker_mpl<G, 8>(mpl, op);
         default: return cudaErrorInvalidValue;
     }
+}
+static cudaError_t gen_walker_dispatch(const GenModel& gm, const GenWalkerOp& op) {
+    const int G = gen_group(gm.M, gm.P);
+    if (G == 0) return cudaErrorInvalidValue;
+    const int ppl = gen_slots((gm.P + G - 1) / G), mpl = gen_slots((gm.M + G - 1) / G);
+    switch (G) {
+        case 8: return gen_walker_ppl<8>(ppl, mpl, op);
+        case 16: return gen_walker_ppl<16>(ppl, mpl, op);
+        default: return gen_walker_ppl<32>(ppl, mpl, op);
+    }
+}
+cudaError_t gen_walker_grid(const GenModel& gm, size_t n, int sm_count, int* grid, int* walkers_per_cta) {
+    GenWalkerOp op{nullptr, &gm, n, sm_count, grid, nullptr};
+    *walkers_per_cta = 32 / gen_group(gm.M, gm.P);
+    return gen_walker_dispatch(gm, op);
 }
 cudaError_t gen_sweep_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
     switch (gen_ppl(gm.P)) {
@@ -540,33 +614,9 @@ cudaError_t launch_gen_probe(const GenProbeLaunch& L, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <int PPL, int MPL>
-static cudaError_t gen_walker_launch2(const GenWalkerLaunch& L, cudaStream_t s) {
-    const size_t smem = gen_smem(L.gm);
-    if (cudaError_t e = gen_prepare(gen_walker_kernel<PPL, MPL>, smem)) return e;
-    gen_walker_kernel<PPL, MPL><<<L.grid, GEN_BLOCK, smem, s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n, L.global_offset,
-                                                         L.step0, L.steps, L.accumulate, L.reset_acc, L.shift, L.partials,
-                                                         L.rec_tau, L.rec_eloc, L.rec_addr, L.err_flag);
-    return cudaGetLastError();
-}
-template <int PPL>
-static cudaError_t gen_walker_launch(const GenWalkerLaunch& L, cudaStream_t s) {
-    switch (L.gm.MPL) {
-        case 1: return gen_walker_launch2<PPL, 1>(L, s);
-        case 2: return gen_walker_launch2<PPL, 2>(L, s);
-        case 4: return gen_walker_launch2<PPL, 4>(L, s);
-        case 8: return gen_walker_launch2<PPL, 8>(L, s);
-        default: return cudaErrorInvalidValue;
-    }
-}
 cudaError_t launch_gen_walkers(const GenWalkerLaunch& L, cudaStream_t s) {
-    switch (gen_ppl(L.gm.P)) {
-        case 1: return gen_walker_launch<1>(L, s);
-        case 2: return gen_walker_launch<2>(L, s);
-        case 4: return gen_walker_launch<4>(L, s);
-        case 8: return gen_walker_launch<8>(L, s);
-        default: return cudaErrorInvalidValue;
-    }
+    GenWalkerOp op{&L, &L.gm, L.n, 0, nullptr, s};
+    return gen_walker_dispatch(L.gm, op);
 }
 cudaError_t launch_gen_estimates(const double* acc, size_t n, int P, const double* shift, double* val_w, double* grad_w,
                                  cudaStream_t s) {

@@ -109,25 +109,32 @@ struct GenWarp {
     }
 };
 
+// Reductions / scans over a group of G consecutive lanes (G = 32: the warp; the walker kernel also runs 2 or 4
+// walkers per warp in groups of 16 or 8 lanes, which amortises the per-step scalar work).  `lane` arguments of the
+// helpers below are lane indices within the group.
+template <int G = 32>
 __device__ __forceinline__ double warp_sum_all(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
     return v;
 }
+template <int G = 32>
 __device__ __forceinline__ long long warp_sum_all(long long v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
     return v;
 }
+template <int G = 32>
 __device__ __forceinline__ int warp_sum_all(int v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
     return v;
 }
+template <int G = 32>
 __device__ __forceinline__ double warp_scan_incl(double v, int lane) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, v, o);
+    for (int o = 1; o < G; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o, G);
         if (lane >= o) v += t;
     }
     return v;
@@ -161,9 +168,10 @@ __device__ __forceinline__ void gen_encode(const GenModel& gm, const GenWarp& ws
 }
 
 // V = Q n + b from scratch (rows of Q are read coalesced: Q is symmetric)
+template <int G = 32>
 __device__ __forceinline__ void gen_potential(const GenModel& gm, const GenWarp& ws, int lane) {
     const int M = gm.M;
-    for (int k = lane; k < M; k += 32) {
+    for (int k = lane; k < M; k += G) {
         double acc = gm.bvec[k];
         for (int a = 0; a < M; ++a) {
             const int na = ws.occ[a];
@@ -175,21 +183,22 @@ __device__ __forceinline__ void gen_potential(const GenModel& gm, const GenWarp&
 }
 
 // sum n(n-1)/2, sum n_k n_{k+1} (periodic; Rimu extended_hubbard_interaction), sum log n_k!
+template <int G = 32>
 __device__ __forceinline__ void gen_totals(const GenModel& gm, const GenWarp& ws, int lane, long long& reg,
                                            long long& ext, double& lgsum) {
     long long r = 0, e = 0;
     double lg = 0.0;
     const int M = gm.M;
-    for (int k = lane; k < M; k += 32) {
+    for (int k = lane; k < M; k += G) {
         const int n = ws.occ[k];
         const int nr = ws.occ[k + 1 == M ? 0 : k + 1];
         r += (long long)n * (n - 1);
         e += (long long)n * nr;
         lg += gm.lgam[n];
     }
-    reg = warp_sum_all(r) / 2;
-    ext = warp_sum_all(e);
-    lgsum = warp_sum_all(lg);
+    reg = warp_sum_all<G>(r) / 2;
+    ext = warp_sum_all<G>(e);
+    lgsum = warp_sum_all<G>(lg);
 }
 
 // change of sum n_k n_{k+1} when one particle moves i -> j (nearest neighbours)
@@ -315,11 +324,16 @@ __device__ __forceinline__ void gen_rates(const GenModel& gm, const GenWarp& ws,
 
 // pick_random_from_cumsum (qmc.jl:52-61) over the hops in reference order: first hop whose inclusive
 // running sum exceeds T = u01 * S.  Returns the source mode and direction (warp-uniform).
-template <int MPL>
+template <int MPL, int G = 32>
 __device__ __forceinline__ void gen_select(const GenModel& gm, const GenWarp& ws, int lane, double S_lane, double cum_incl,
                                            double T, int& src, int& right) {
-    const unsigned hit = __ballot_sync(0xffffffffu, (T < cum_incl) && (S_lane > 0.0));
-    const unsigned live = __ballot_sync(0xffffffffu, S_lane > 0.0);
+    unsigned hit = __ballot_sync(0xffffffffu, (T < cum_incl) && (S_lane > 0.0));
+    unsigned live = __ballot_sync(0xffffffffu, S_lane > 0.0);
+    if (G < 32) {  // this group's share of the ballots
+        const int shift = (int)(threadIdx.x & 31u & ~(unsigned)(G - 1));
+        hit = (hit >> shift) & ((1u << (G & 31)) - 1u);
+        live = (live >> shift) & ((1u << (G & 31)) - 1u);
+    }
     // rounding can leave T >= every running sum: clamp to the last hop
     const int sel_lane = hit ? (__ffs(hit) - 1) : (31 - __clz(live));
     int mode = -1, dir = 1;
@@ -355,8 +369,8 @@ __device__ __forceinline__ void gen_select(const GenModel& gm, const GenWarp& ws
             }
         }
     }
-    src = __shfl_sync(0xffffffffu, mode, sel_lane);
-    right = __shfl_sync(0xffffffffu, dir, sel_lane);
+    src = __shfl_sync(0xffffffffu, mode, sel_lane, G);
+    right = __shfl_sync(0xffffffffu, dir, sel_lane, G);
 }
 
 }  // namespace gwz
