@@ -690,10 +690,10 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     GenCombo cb;
     bool combo = false;
     if (int rc = prepare_params(a, params, &K.gm, &cb, &combo)) return rc;
-    int grid = 0;
+    int grid = 0, per_cta = 1;
     if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
-    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
-    const size_t rows = (size_t)grid * GEN_WARPS;
+    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid, &per_cta));
+    const size_t rows = (size_t)grid * per_cta;
     if (rows > s->partials_rows) {
         if (s->d_partials) cudaFree(s->d_partials);
         s->d_partials = nullptr;
@@ -751,10 +751,10 @@ static int gsweep_terms_impl(gwz_gsweep* s, const double* params, uint64_t first
     DevBuf<uint64_t> d_st;
     if (out) GWZ_CUDA(d_out.alloc(count * L));
     if (states) GWZ_CUDA(d_st.alloc(count * W));
-    int grid = 0;
+    int grid = 0, per_cta = 1;
     if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)count, c->prop.multiProcessorCount, &grid));
-    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)count, c->prop.multiProcessorCount, &grid));
-    const size_t rows = (size_t)grid * GEN_WARPS;
+    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)count, c->prop.multiProcessorCount, &grid, &per_cta));
+    const size_t rows = (size_t)grid * per_cta;
     K.basis = s->d_basis;
     K.dim = s->dim;
     K.rank_begin = s->rank_begin;

@@ -367,61 +367,71 @@ __global__ void gen_estimates_kernel(const double* __restrict__ acc, size_t n, i
 // ------------------------------------------------------------------------------------------
 // LocalEnergyEvaluator (localenergy.jl:94-155): one warp per basis state
 // ------------------------------------------------------------------------------------------
-template <int PPL>
+// G lanes per state (32 / G states per warp); gm.MPL / gm.MP are the per-group values set by the launcher
+template <int G, int PPL>
 __global__ void __launch_bounds__(GEN_BLOCK)
 gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin,
                  const uint64_t* __restrict__ binom, uint64_t chunk, int with_grad, double* __restrict__ partials,
                  double* __restrict__ terms_out, uint64_t* __restrict__ states_out, uint64_t first, uint64_t count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const GenWarp ws(smem_raw, gm.MP, warp);
-    uint64_t* aw = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GEN_WARPS * GenWarp::bytes(gm.MP)) + 4 * warp;
-    const uint64_t gwarp = (uint64_t)blockIdx.x * GEN_WARPS + warp;
+    constexpr int GROUPS = 32 / G;
+    const int lane = threadIdx.x & (G - 1), group = (threadIdx.x & 31) / G;
+    const GenWarp ws(smem_raw, gm.MP, group);
+    uint64_t* aw = reinterpret_cast<uint64_t*>(smem_raw + (size_t)GROUPS * GenWarp::bytes(gm.MP)) + 4 * group;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * GROUPS + group;
     const int M = gm.M, P = gm.P;
     const bool per_state = terms_out != nullptr || states_out != nullptr;
-    const uint64_t lo = per_state ? first + gwarp * chunk : gwarp * chunk;
     const uint64_t end = per_state ? first + count : dim;
+    uint64_t lo = per_state ? first + gwarp * chunk : gwarp * chunk;
+    if (lo > end) lo = end;
     const uint64_t hi = (lo + chunk < end) ? lo + chunk : end;
     double num = 0.0, den = 0.0, ng[PPL], dg[PPL];
 #pragma unroll
     for (int q = 0; q < PPL; ++q) ng[q] = dg[q] = 0.0;
     uint64_t x = 0;
-    for (uint64_t sidx = lo; sidx < hi; ++sidx) {
-        if (basis) {
-            if (lane < gm.W) aw[lane] = basis[(uint64_t)lane * dim + sidx];
-        } else {
-            x = (sidx == lo) ? unrank_colex(rank_begin + sidx, gm.N, gm.B, binom) : next_same_popcount(x);
-            if (lane == 0) aw[0] = x;
+    for (uint64_t it = 0; it < chunk; ++it) {  // warp-uniform trip count; a group past its range idles on a valid state
+        const uint64_t sidx = lo + it;
+        const bool live = sidx < hi;
+        if (live) {
+            if (basis) {
+                if (lane < gm.W) aw[lane] = basis[(uint64_t)lane * dim + sidx];
+            } else {
+                x = (it == 0) ? unrank_colex(rank_begin + sidx, gm.N, gm.B, binom) : next_same_popcount(x);
+                if (lane == 0) aw[0] = x;
+            }
+        } else if (it == 0 && lane == 0) {  // any valid state: all particles in mode 1
+            for (int i = 0; i < gm.W; ++i) aw[i] = 0ull;
+            for (int b = 0; b < gm.N; ++b) aw[b >> 6] |= 1ull << (b & 63);
         }
         __syncwarp();
-        if (states_out && lane < gm.W) states_out[(sidx - first) * (uint64_t)gm.W + lane] = aw[lane];
-        gen_decode(gm, aw, ws, lane);
-        gen_potential(gm, ws, lane);
+        if (states_out && live && lane < gm.W) states_out[(sidx - first) * (uint64_t)gm.W + lane] = aw[lane];
+        gen_decode<G>(gm, aw, ws, lane);
+        gen_potential<G>(gm, ws, lane);
         long long reg, ext;
         double lgsum;
-        gen_totals(gm, ws, lane, reg, ext, lgsum);
+        gen_totals<G>(gm, ws, lane, reg, ext, lgsum);
         double S_lane, E_lane;
         int nocc_lane;
         GEN_MPL_SWITCH(gm.MPL, (gen_rates<MPL_, true>(gm, ws, lane, S_lane, E_lane, nocc_lane)));
         __syncwarp();
-        const double Etot = warp_sum_all(E_lane);
+        const double Etot = warp_sum_all<G>(E_lane);
         const double D = gm.u * (double)reg + gm.v * (double)ext;
         const double eloc = D - gm.t * Etot;
-        const double psi2 = exp(-2.0 * gen_phi(gm, ws, lane, lgsum));
+        const double psi2 = exp(-2.0 * gen_phi<G>(gm, ws, lane, lgsum));
         const double s_num = psi2 * eloc;
         if (per_state) {
-            if (terms_out && lane == 0) {
+            if (terms_out && live && lane == 0) {
                 terms_out[(sidx - first) * (uint64_t)(2 + 2 * P)] = s_num;
                 terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 1] = psi2;
             }
-        } else {
+        } else if (live) {
             num += s_num;
             den += psi2;
         }
         if (with_grad) {
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
-                const int p = lane + 32 * q;
+                const int p = lane + G * q;
                 if (p < P) {
                     const double Fp = gen_feature(gm, ws, p, reg, ext, lgsum);
                     double cross = 0.0;  // sum over hops of melem * ratio * (F_p(n') - F_p(n))
@@ -436,11 +446,11 @@ gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
                     const double s_ng = -psi2 * (2.0 * Fp * eloc + cross);
                     const double s_dg = -2.0 * Fp * psi2;
                     if (per_state) {
-                        if (terms_out) {
+                        if (terms_out && live) {
                             terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 2 + p] = s_ng;
                             terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 2 + P + p] = s_dg;
                         }
-                    } else {
+                    } else if (live) {
                         ng[q] += s_ng;
                         dg[q] += s_dg;
                     }
@@ -457,7 +467,7 @@ gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
     }
 #pragma unroll
     for (int q = 0; q < PPL; ++q) {
-        const int p = lane + 32 * q;
+        const int p = lane + G * q;
         if (p < P) {
             out[2 + p] = ng[q];
             out[2 + P + p] = dg[q];
@@ -582,14 +592,65 @@ cudaError_t gen_walker_grid(const GenModel& gm, size_t n, int sm_count, int* gri
     *walkers_per_cta = 32 / gen_group(gm.M, gm.P);
     return gen_walker_dispatch(gm, op);
 }
-cudaError_t gen_sweep_grid(const GenModel& gm, size_t n, int sm_count, int* grid) {
-    switch (gen_ppl(gm.P)) {
-        case 1: return gen_grid_for(gen_sweep_kernel<1>, gm, n, sm_count, grid);
-        case 2: return gen_grid_for(gen_sweep_kernel<2>, gm, n, sm_count, grid);
-        case 4: return gen_grid_for(gen_sweep_kernel<4>, gm, n, sm_count, grid);
-        case 8: return gen_grid_for(gen_sweep_kernel<8>, gm, n, sm_count, grid);
+// per-group geometry of a sweep launch
+static GenModel gen_sweep_model(const GenModel& gm, int G) {
+    GenModel g = gm;
+    g.MPL = gen_slots((gm.M + G - 1) / G);
+    g.MP = G * g.MPL;
+    return g;
+}
+struct GenSweepOp {
+    const GenSweepLaunch* L;  // null: occupancy query
+    const GenModel* gm;
+    size_t n;
+    int sm_count;
+    int* grid;
+    cudaStream_t s;
+};
+template <int G, int PPL>
+static cudaError_t gen_sweep_do(const GenSweepOp& op) {
+    const GenModel g = gen_sweep_model(*op.gm, G);
+    const size_t smem = (size_t)(32 / G) * (GenWarp::bytes(g.MP) + 4 * sizeof(uint64_t));
+    if (cudaError_t e = gen_prepare(gen_sweep_kernel<G, PPL>, smem)) return e;
+    if (op.L == nullptr) {
+        int per_sm = 0;
+        if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_sweep_kernel<G, PPL>, GEN_BLOCK, smem)) return e;
+        if (per_sm < 1) per_sm = 1;
+        const size_t resident = (size_t)per_sm * op.sm_count;
+        const size_t need = (op.n + (32 / G) - 1) / (32 / G);
+        *op.grid = (int)(need < resident ? need : resident);
+        if (*op.grid < 1) *op.grid = 1;
+        return cudaSuccess;
+    }
+    const GenSweepLaunch& L = *op.L;
+    gen_sweep_kernel<G, PPL><<<L.grid, GEN_BLOCK, smem, op.s>>>(g, L.basis, L.dim, L.rank_begin, L.binom, L.chunk, L.with_grad,
+                                                               L.partials, L.terms_out, L.states_out, L.first, L.count);
+    return cudaGetLastError();
+}
+template <int G>
+static cudaError_t gen_sweep_ppl(int ppl, const GenSweepOp& op) {
+    switch (ppl) {
+        case 1: return gen_sweep_do<G, 1>(op);
+        case 2: return gen_sweep_do<G, 2>(op);
+        case 4: return gen_sweep_do<G, 4>(op);
+        case 8: return gen_sweep_do<G, 8>(op);
         default: return cudaErrorInvalidValue;
     }
+}
+static cudaError_t gen_sweep_dispatch(const GenModel& gm, const GenSweepOp& op) {
+    const int G = gen_group(gm.M, gm.P);
+    if (G == 0) return cudaErrorInvalidValue;
+    const int ppl = gen_slots((gm.P + G - 1) / G);
+    switch (G) {
+        case 8: return gen_sweep_ppl<8>(ppl, op);
+        case 16: return gen_sweep_ppl<16>(ppl, op);
+        default: return gen_sweep_ppl<32>(ppl, op);
+    }
+}
+cudaError_t gen_sweep_grid(const GenModel& gm, size_t n, int sm_count, int* grid, int* states_per_cta) {
+    GenSweepOp op{nullptr, &gm, n, sm_count, grid, nullptr};
+    *states_per_cta = 32 / gen_group(gm.M, gm.P);
+    return gen_sweep_dispatch(gm, op);
 }
 
 cudaError_t launch_gen_unary_to_occ(const uint64_t* addr, size_t n, const GenModel& gm, int Mpad, uint8_t* occ,
@@ -624,22 +685,9 @@ cudaError_t launch_gen_estimates(const double* acc, size_t n, int P, const doubl
     return cudaGetLastError();
 }
 
-template <int PPL>
-static cudaError_t gen_sweep_launch(const GenSweepLaunch& L, cudaStream_t s) {
-    const size_t smem = gen_smem(L.gm);
-    if (cudaError_t e = gen_prepare(gen_sweep_kernel<PPL>, smem)) return e;
-    gen_sweep_kernel<PPL><<<L.grid, GEN_BLOCK, smem, s>>>(L.gm, L.basis, L.dim, L.rank_begin, L.binom, L.chunk, L.with_grad,
-                                                        L.partials, L.terms_out, L.states_out, L.first, L.count);
-    return cudaGetLastError();
-}
 cudaError_t launch_gen_sweep(const GenSweepLaunch& L, cudaStream_t s) {
-    switch (gen_ppl(L.gm.P)) {
-        case 1: return gen_sweep_launch<1>(L, s);
-        case 2: return gen_sweep_launch<2>(L, s);
-        case 4: return gen_sweep_launch<4>(L, s);
-        case 8: return gen_sweep_launch<8>(L, s);
-        default: return cudaErrorInvalidValue;
-    }
+    GenSweepOp op{&L, &L.gm, 0, 0, nullptr, s};
+    return gen_sweep_dispatch(L.gm, op);
 }
 
 }  // namespace gwz

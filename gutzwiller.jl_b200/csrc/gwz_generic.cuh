@@ -141,10 +141,11 @@ __device__ __forceinline__ double warp_scan_incl(double v, int lane) {
 }
 
 // unary BoseFS words (W words in `a`, warp-uniform pointer) -> occupation numbers in shared memory
+template <int G = 32>
 __device__ __forceinline__ void gen_decode(const GenModel& gm, const uint64_t* a, const GenWarp& ws, int lane) {
-    for (int k = lane; k < gm.MP; k += 32) ws.occ[k] = 0;
+    for (int k = lane; k < gm.MP; k += G) ws.occ[k] = 0;
     __syncwarp();
-    for (int p = lane; p < gm.B; p += 32) {
+    for (int p = lane; p < gm.B; p += G) {
         const int w = p >> 6, b = p & 63;
         if ((a[w] >> b) & 1ull) {
             int zeros = __popcll(~a[w] & ((1ull << b) - 1ull));
@@ -264,13 +265,14 @@ __device__ __forceinline__ double gen_dfeature(const GenModel& gm, const GenWarp
 }
 
 // phi(n) = 1/2 n^T Q n + b^T n + s (sum log n! - log K)  (psi = exp(-phi))
+template <int G = 32>
 __device__ __forceinline__ double gen_phi(const GenModel& gm, const GenWarp& ws, int lane, double lgsum) {
     double acc = 0.0;
-    for (int k = lane; k < gm.M; k += 32) {
+    for (int k = lane; k < gm.M; k += G) {
         const int n = ws.occ[k];
         if (n) acc = fma((double)n, 0.5 * (ws.V[k] + gm.bvec[k]), acc);
     }
-    return warp_sum_all(acc) + gm.s * (lgsum - gm.logK);
+    return warp_sum_all<G>(acc) + gm.s * (lgsum - gm.logK);
 }
 
 // hop rates of the modes this lane owns, in reference order; lane sums of the rates, of

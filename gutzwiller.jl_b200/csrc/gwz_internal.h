@@ -172,7 +172,7 @@ struct GenSweepLaunch {
 int gen_ppl(int P);  // parameter slots per lane (1, 2, 4, 8), 0 if P > 256
 int gen_group(int M, int P);  // lanes per walker of the walker kernel (8, 16 or 32)
 cudaError_t gen_walker_grid(const GenModel& gm, size_t n, int sm_count, int* grid, int* walkers_per_cta);
-cudaError_t gen_sweep_grid(const GenModel& gm, size_t n, int sm_count, int* grid);
+cudaError_t gen_sweep_grid(const GenModel& gm, size_t n, int sm_count, int* grid, int* states_per_cta);
 cudaError_t launch_gen_unary_to_occ(const uint64_t* addr, size_t n, const GenModel& gm, int Mpad, uint8_t* occ,
                                     bool broadcast, cudaStream_t s);
 cudaError_t launch_gen_occ_to_unary(const uint8_t* occ, size_t n, const GenModel& gm, int Mpad, uint64_t* addr,
