@@ -114,3 +114,24 @@ def test_tuned_cpu_walk_follows_the_faithful_port(oracle_mod):
         b = o.kinetic_vqmc_fast(g, start.copy(), 400, seed=3, walker0=2)
         assert np.array_equal(a["addrs"], b["addrs"]) and a["hops"] == b["hops"]
         assert np.allclose(a["val_w"], b["val_w"], rtol=1e-11) and np.allclose(a["grad_w"], b["grad_w"], rtol=1e-8, atol=1e-9)
+
+
+def test_oracle_reproduces_committed_ansatz_vectors(oracle_mod):
+    """tests/golden/ansatz_vectors.json (made by tests/golden/make_golden_ansatz.py) pins part 2 of the oracle against drift."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ansatz_vectors.json")
+    for c in json.load(open(path))["cases"]:
+        o = oracle_mod.Oracle(c["N"], c["M"], c["u"], c["t"])
+        kind = tuple(c["kind"]) if isinstance(c["kind"], list) else c["kind"]
+        ao = oracle_mod.AnsatzOracle(o, kind, v=c["v"], normalize=c["normalize"])
+        basis = o.build_basis()
+        assert len(basis) == c["dim"]
+        for r in c["addresses"]:
+            a = np.pad(np.array(r["addr"], dtype=np.uint64), (0, 4 - o.W))
+            val, grad = ao.val_and_grad(a, c["params"])
+            ks = ao.kinetic_sample(a, c["params"], 0.37)
+            assert val == r["val"] and np.array_equal(grad, r["grad"]) and ks["eloc"] == r["e_loc"] and ks["tau"] == r["tau"]
+            assert ks["chosen"] == r["chosen"] and np.array_equal(ao.hop_rates(a, c["params"]), r["rates"])
+        lv, lg = ao.lee_val_and_grad(basis, c["params"])
+        assert lv == c["le_val"] and np.array_equal(lg, c["le_grad"])
