@@ -313,3 +313,21 @@ def test_device_histogram_equals_host_histogram(gw, N, M):
     big = gw.HubbardReal1D(gw.near_uniform(50, 50), u=2.0)
     with pytest.raises(ValueError, match="single-word"):
         gw.Walkers(big.model(), 4, big.address.words).sample_vector([0.4], 10)
+
+
+@pytest.mark.parametrize("N,M,u,g", [(50, 50, 2.0, 0.5), (20, 20, 4.0, 0.25)])
+def test_large_system_energy_agrees_with_the_cpu_walk_within_error_bars(gw, oracle_mod, N, M, u, g):
+    """North-star criterion at the benchmark sizes, where no exact value exists: the production kernel's energy and the
+    CPU walk's (oracle.kinetic_vqmc_fast: the same trajectories as the literal restatement of the reference, see
+    tests/test_oracle_ansatz.py) agree within their combined cross-walker standard errors on identical (H, ansatz, p)."""
+    o = oracle_mod.Oracle(N, M, u, 1.0)
+    nw_cpu, burn, steps = 96, 3000, 12000
+    start = np.tile(o.near_uniform(), (nw_cpu, 1))
+    o.kinetic_vqmc_fast(g, start, burn, seed=11)  # thermalise in place
+    ref = o.kinetic_vqmc_fast(g, start, steps, seed=11, step0=burn)
+    e_cpu, s_cpu = ref["val_w"].mean(), ref["val_w"].std(ddof=1) / np.sqrt(nw_cpu)
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=u)
+    res = gw.kinetic_vqmc(H, gw.GutzwillerAnsatz(H), [g], walkers=1 << 13, steps=steps, burn_in=burn, seed=99, record=False)
+    e_gpu, s_gpu = res.last.val, res.last.err
+    assert abs(e_gpu - e_cpu) < 4.0 * np.hypot(s_cpu, s_gpu), (e_gpu, s_gpu, e_cpu, s_cpu)
+    assert s_gpu < s_cpu  # 85x more walkers
