@@ -192,6 +192,8 @@ __device__ __forceinline__ bool orbit_representative(T e, int L, T maskL, int M,
     return true;
 }
 
+constexpr int SYM_BINOM_SLOTS = 32 * 65;  // rows p = 0..31 of the [65][65] table (16.6 KB): systems with N+M-1 <= 31
+
 template <int NW, int KC>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, uint64_t dim,
@@ -201,6 +203,15 @@ sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ De
     sc.fill_exptab(dm.N, tb.c);
     __shared__ uint64_t qx[SWEEP_BLOCK / 32][64];
     __shared__ int qm[SWEEP_BLOCK / 32][64];
+    // the unranking walks the binomial table with dependent loads: keep the needed corner C(p, i), p <= B, i <= N,
+    // in shared memory when it is small (short runs: the unranking latency is a large part of a small sweep)
+    __shared__ uint64_t sbin[SYM_BINOM_SLOTS];
+    const bool small_table = (dm.B + 1) * 65 <= SYM_BINOM_SLOTS;
+    if (small_table) {
+        for (int i = threadIdx.x; i < (dm.B + 1) * 65; i += blockDim.x) sbin[i] = binom[i];
+        __syncthreads();
+    }
+    const uint64_t* __restrict__ bt = small_table ? sbin : binom;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -224,7 +235,7 @@ sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ De
     for (uint64_t base = (tid - lane) * chunk; base < dim; base += nthreads * chunk) {  // warp-uniform trip count
         const uint64_t first = base + (uint64_t)lane * chunk;
         const uint64_t cnt = first < dim ? min(chunk, dim - first) : 0;
-        uint64_t x = cnt ? unrank_colex(rank_begin + first, dm.N, dm.B, binom) : 0ull;
+        uint64_t x = cnt ? unrank_colex(rank_begin + first, dm.N, dm.B, bt) : 0ull;
         for (uint64_t k = 0; k < chunk; ++k) {
             int mult = 0;
             const bool rep = (k < cnt) && (L <= 32 ? orbit_representative<uint32_t>((uint32_t)x, L, (uint32_t)maskL, dm.M, mult)
@@ -346,6 +357,9 @@ cudaError_t launch_ansatz(const DevModel& dm, double g, int nw, const uint64_t* 
     return cudaGetLastError();
 }
 
+#ifndef GWZ_SWEEP_WAVE_CTAS
+#define GWZ_SWEEP_WAVE_CTAS 32
+#endif
 cudaError_t sweep_grid(int nw, int kc, int N, int M, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk) {
     (void)nw; (void)kc; (void)N; (void)M;
     uint64_t c = 1;
@@ -355,7 +369,7 @@ cudaError_t sweep_grid(int nw, int kc, int N, int M, bool ranked, uint64_t dim, 
         // run).  The cost of a rank varies along the rank range (the orbit test exits early for most low ranks), so
         // runs are kept short and CTAs many: the block scheduler balances them (measured: one resident wave of long
         // runs is 1.8x slower on {16,16} and 3.4x on {18,18}).
-        const uint64_t wave = (uint64_t)sm_count * 16 * SWEEP_BLOCK;  // enough threads to fill the chip
+        const uint64_t wave = (uint64_t)sm_count * GWZ_SWEEP_WAVE_CTAS * SWEEP_BLOCK;  // short runs, several waves: the block scheduler balances the rank-dependent cost
         c = (dim + wave - 1) / wave;
         c = c < 8 ? 8 : (c > 256 ? 256 : c);
         max_threads = (uint64_t)sm_count * 4096 * SWEEP_BLOCK;  // beyond that threads take several runs
