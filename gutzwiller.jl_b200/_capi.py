@@ -157,6 +157,16 @@ SIGNATURES = {
     "gwz_gsweep_terms": (C.c_int, [_vp, _dp, C.c_uint64, C.c_uint64, _vp]),
     "gwz_gsweep_states": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "gwz_gsweep_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    # ---- VectorAnsatz ----
+    "gwz_vector_ansatz_create": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "gwz_vector_ansatz_destroy": (C.c_int, [_vp]),
+    "gwz_vector_ansatz_lookup": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "gwz_vector_ansatz_rayleigh": (C.c_int, [_vp, _dp]),
+    "gwz_vwalkers_create": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _u64p, C.c_uint64, C.POINTER(_vp)]),
+    "gwz_vwalkers_destroy": (C.c_int, [_vp]),
+    "gwz_vwalkers_get_addresses": (C.c_int, [_vp, _vp]),
+    "gwz_vwalkers_run": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(GenResult)]),
+    "gwz_vwalkers_run_record": (C.c_int, [_vp, C.c_uint64, C.c_uint, _vp, _vp, _vp, C.POINTER(GenResult)]),
 }
 
 _lib = None

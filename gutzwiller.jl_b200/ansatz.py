@@ -356,3 +356,114 @@ class GenSweep:
         ms = C.c_float()
         check(lib().gwz_gsweep_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+
+class _VectorHandle:
+    """gwz_vansatz: the (address, amplitude) pairs of a VectorAnsatz as an HBM hash table on one model."""
+
+    def __init__(self, model, addrs: np.ndarray, vals: np.ndarray):
+        self.model = model
+        self._h = C.c_void_p()
+        check(lib().gwz_vector_ansatz_create(model.handle, _vp(addrs), _vp(vals), addrs.shape[0], C.byref(self._h)))
+        self._finalizer = weakref.finalize(self, lib().gwz_vector_ansatz_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def lookup(self, addrs) -> np.ndarray:
+        a = np.ascontiguousarray(addrs, dtype=np.uint64).reshape(-1, self.model.words)
+        out = np.zeros(a.shape[0])
+        check(lib().gwz_vector_ansatz_lookup(self._h, _vp(a), a.shape[0], _vp(out)))
+        return out
+
+    def rayleigh(self) -> float:
+        v = C.c_double()
+        check(lib().gwz_vector_ansatz_rayleigh(self._h, C.byref(v)))
+        return v.value
+
+
+class VectorAnsatz(AbstractAnsatz):
+    """``VectorAnsatz(vector)`` (vector.jl:1-12): use a stored vector as a 0-parameter ansatz.  ``vector`` is a mapping
+    ``{BoseFS: amplitude}`` (a Rimu DVec) or a pair ``(addresses uint64[n, W], values float64[n])``; addresses it does
+    not hold have amplitude 0.  ``kinetic_vqmc(H, VectorAnsatz(v), [])`` samples |v|^2 (test/qmc.jl:22-23)."""
+    N_PARAMS = 0
+    vector_ansatz = True
+
+    def __init__(self, vector):
+        if isinstance(vector, dict):
+            keys = list(vector.keys())
+            if not keys or not all(isinstance(k, BoseFS) for k in keys):
+                raise TypeError("VectorAnsatz needs a non-empty {BoseFS: value} mapping")
+            self.addresses = np.stack([k.words for k in keys]).astype(np.uint64)
+            self.values = np.array([float(vector[k]) for k in keys])
+        else:
+            addrs, vals = vector
+            self.values = np.ascontiguousarray(vals, dtype=np.float64).ravel()
+            self.addresses = np.ascontiguousarray(addrs, dtype=np.uint64).reshape(self.values.size, -1)
+        if self.values.size == 0:
+            raise ValueError("empty vector")
+        self.hamiltonian = None  # bound by the call that uses it (the reference's VectorAnsatz holds no Hamiltonian)
+        self._handles = {}
+
+    def handle(self, hamiltonian, ctx: Context | None = None) -> _VectorHandle:
+        ctx = ctx or default_context()
+        key = (id(hamiltonian), id(ctx))
+        if key not in self._handles:
+            model = hamiltonian.model(ctx)
+            if self.addresses.shape[1] != model.words:
+                raise ValueError("the vector's addresses do not match the Hamiltonian's address type")
+            self._handles[key] = _VectorHandle(model, self.addresses, self.values)
+        return self._handles[key]
+
+    def build_basis(self) -> np.ndarray:
+        """``build_basis(va) = collect(keys(va.vector))`` (vector.jl:10)"""
+        return self.addresses.copy()
+
+    def __call__(self, addr: BoseFS, params=()) -> float:
+        hit = np.all(self.addresses == addr.words[None, :], axis=1)
+        return float(self.values[hit][0]) if hit.any() else 0.0
+
+    def val_and_grad(self, addr: BoseFS, params=()):
+        return self(addr, params), np.zeros(0)  # abstract.jl:50-52
+
+    def __repr__(self):
+        return f"VectorAnsatz({self.values.size} entries)"
+
+
+class VecWalkers:
+    """gwz_vwalkers: walkers of a VectorAnsatz (P = 0)."""
+
+    def __init__(self, vhandle: _VectorHandle, n_walkers: int, start_words, seed: int, global_offset: int = 0):
+        self.vhandle, self.model, self.P = vhandle, vhandle.model, 0
+        self.n, self.offset = int(n_walkers), int(global_offset)
+        self._h = C.c_void_p()
+        sw = np.ascontiguousarray(start_words, dtype=np.uint64)
+        check(lib().gwz_vwalkers_create(vhandle.handle, self.n, self.offset, sw.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(self._h)))
+        self._finalizer = weakref.finalize(self, lib().gwz_vwalkers_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def addresses(self) -> np.ndarray:
+        out = np.zeros((self.n, self.model.words), dtype=np.uint64)
+        check(lib().gwz_vwalkers_get_addresses(self._h, _vp(out)))
+        return out
+
+    def run(self, params, steps: int, burn_in: int = 0, kernel=None, keep_acc: bool = False, pooled: bool = False):
+        as_params(params if np.size(params) else np.zeros(0), 0)
+        r = _capi.GenResult()
+        flags = (_capi.RUN_KEEP_ACC if keep_acc else 0) | (_capi.RUN_POOLED if pooled else 0)
+        check(lib().gwz_vwalkers_run(self._h, int(steps), int(burn_in), flags, C.byref(r)))
+        return GenRunResult(r, np.zeros(0), np.zeros(0), np.zeros(0))
+
+    def run_record(self, params, steps: int, kernel=None, keep_acc: bool = False, want_addresses: bool = True):
+        steps = int(steps)
+        tau, eloc = np.zeros((steps, self.n)), np.zeros((steps, self.n))
+        addr = np.zeros((steps, self.n, self.model.words), dtype=np.uint64) if want_addresses else None
+        r = _capi.GenResult()
+        check(lib().gwz_vwalkers_run_record(self._h, steps, _capi.RUN_KEEP_ACC if keep_acc else 0, _vp(tau), _vp(eloc),
+                                            _vp(addr), C.byref(r)))
+        return GenRunResult(r, np.zeros(0), np.zeros(0), np.zeros(0)), tau, eloc, addr

@@ -172,7 +172,7 @@ def valtype(ansatz: AbstractAnsatz):
 
 def as_params(params, n: int) -> np.ndarray:
     """Accept a scalar, list, tuple or array like ``SVector{N,T}(params)`` does (state.jl:25)."""
-    p = np.atleast_1d(np.asarray(params, dtype=np.float64)).ravel()
+    p = np.atleast_1d(np.asarray(params, dtype=np.float64)).ravel() if np.size(params) else np.zeros(0)
     if p.size != n:
         raise ValueError(f"expected {n} parameter(s), got {p.size}")
     return np.ascontiguousarray(p)

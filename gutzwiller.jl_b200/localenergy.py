@@ -22,6 +22,14 @@ class LocalEnergyEvaluator:
 
     def __init__(self, hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, *, basis=None, ctx: Context | None = None):
         self._gen = None
+        self._vec = None
+        if getattr(ansatz, "vector_ansatz", False):  # basis = keys(vector) (vector.jl:10): the Rayleigh quotient
+            if basis is not None:
+                raise ValueError("LocalEnergyEvaluator(H, VectorAnsatz(v)) sweeps keys(v); do not pass a basis")
+            self.hamiltonian, self.ansatz, self.model, self.P = hamiltonian, ansatz, hamiltonian.model(ctx), 0
+            self._vec = ansatz.handle(hamiltonian, ctx)
+            self._h = self._vec.handle
+            return
         self.hamiltonian, self.ansatz = hamiltonian, ansatz
         self.model = hamiltonian.model(ctx)
         self.P = ansatz.N_PARAMS
@@ -64,6 +72,8 @@ class LocalEnergyEvaluator:
 
     @property
     def dim(self) -> int:
+        if self._vec is not None:
+            return int(self.ansatz.values.size)
         if self._gen is not None:
             return self._gen.dim()
         d = C.c_uint64()
@@ -72,6 +82,8 @@ class LocalEnergyEvaluator:
 
     def val_and_grad(self, params):
         """``val_and_grad(le, params)`` (localenergy.jl:94-129)."""
+        if self._vec is not None:
+            return self._vec.rayleigh(), np.zeros(0)
         if self._gen is not None:
             return self._gen.val_and_grad(params)
         p = as_params(params, 1)
@@ -96,6 +108,8 @@ class LocalEnergyEvaluator:
                 val = self(params)
             return val if F is not None else None
         params = args[0] if len(args) == 1 else args  # le(p...) (localenergy.jl:171-173)
+        if self._vec is not None:
+            return self._vec.rayleigh()
         if self._gen is not None:
             return self._gen.val(params)
         p = as_params(params, 1)

@@ -278,6 +278,8 @@ def _is_generic(ansatz) -> bool:
 
 
 def _check_pair(hamiltonian, ansatz):
+    if getattr(ansatz, "vector_ansatz", False):
+        return  # VectorAnsatz holds no Hamiltonian (vector.jl:6-8)
     if not isinstance(ansatz, AbstractAnsatz) or not hasattr(ansatz, "hamiltonian"):
         raise TypeError("ansatz must be one of the AbstractAnsatz types of this package")
     h2 = ansatz.hamiltonian
@@ -302,7 +304,10 @@ def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn
         record = False
     if record is None:
         record = (end - begin) * max(steps, 1) * (16 + 8 * model.words) <= RECORD_LIMIT_BYTES and world == 1
-    if _is_generic(ansatz):
+    if getattr(ansatz, "vector_ansatz", False):
+        from .ansatz import VecWalkers
+        w = VecWalkers(ansatz.handle(hamiltonian, ctx), end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
+    elif _is_generic(ansatz):
         from .ansatz import GenWalkers
         w = GenWalkers(ansatz.handle(ctx), end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
     else:
@@ -353,6 +358,8 @@ def _grad_ratio_series(res: KineticVQMCResult) -> np.ndarray:
     gutzwiller.jl:30), recomputed on the GPU from the recorded addresses."""
     ad = res.addresses()
     nw, ns, W = ad.shape
+    if getattr(res.ansatz, "vector_ansatz", False):
+        return np.zeros((nw, ns, 0))
     if _is_generic(res.ansatz):
         out = res.walkers_handle.ansatz_handle.probe(ad.reshape(-1, W), res.params)
     else:

@@ -298,6 +298,28 @@ int gwz_gsweep_terms(gwz_gsweep *s, const double *params, uint64_t first, uint64
 int gwz_gsweep_states(gwz_gsweep *s, uint64_t first, uint64_t count, uint64_t *out);
 int gwz_gsweep_last_kernel_ms(const gwz_gsweep *s, float *ms);
 
+/* ---- VectorAnsatz (src/ansatz/vector.jl:1-12): a stored vector as a 0-parameter ansatz --------
+ * The (address, amplitude) pairs are kept in an HBM hash table; addresses the vector does not hold have amplitude 0
+ * (Rimu DVec semantics).  HubbardReal1D only. */
+typedef struct gwz_vansatz gwz_vansatz;
+typedef struct gwz_vwalkers gwz_vwalkers;
+/* `VectorAnsatz(vector)`: addr_words n x W, values n */
+int gwz_vector_ansatz_create(gwz_model *m, const uint64_t *addr_words, const double *values, uint64_t n,
+                             gwz_vansatz **out);
+int gwz_vector_ansatz_destroy(gwz_vansatz *a);
+/* va(addr, _) (vector.jl:12), batched */
+int gwz_vector_ansatz_lookup(gwz_vansatz *a, const uint64_t *addr_words, size_t n, double *val);
+/* LocalEnergyEvaluator(H, VectorAnsatz(v))(): the Rayleigh quotient over basis = keys(v) (vector.jl:10) */
+int gwz_vector_ansatz_rayleigh(gwz_vansatz *a, double *val);
+/* kinetic_vqmc(H, VectorAnsatz(v), Float64[]; ...) (test/qmc.jl:22-23): as gwz_gwalkers_* with P = 0 */
+int gwz_vwalkers_create(gwz_vansatz *a, uint64_t n_walkers, uint64_t global_offset, const uint64_t *start_addr,
+                        uint64_t seed, gwz_vwalkers **out);
+int gwz_vwalkers_destroy(gwz_vwalkers *w);
+int gwz_vwalkers_get_addresses(gwz_vwalkers *w, uint64_t *addr_words);
+int gwz_vwalkers_run(gwz_vwalkers *w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags, gwz_gen_result *out);
+int gwz_vwalkers_run_record(gwz_vwalkers *w, uint64_t steps_per_walker, unsigned flags, double *tau, double *eloc,
+                            uint64_t *addr, gwz_gen_result *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,3 +277,47 @@ def test_generic_engine_against_committed_oracle_vectors(gw):
             assert out["chosen"][i] == r["chosen"] and _close(out["rates"][i][: len(r["rates"])], r["rates"])
         v, g = gw.LocalEnergyEvaluator(H, ans).val_and_grad(p)
         assert _close(v, c["le_val"]) and _close(g, c["le_grad"], atol=1e-12 * max(1.0, np.abs(c["le_grad"]).max()))
+
+
+def test_vector_ansatz_samples_an_eigenvector(gw, oracle_mod):
+    """test/qmc.jl:15-51: with the exact ground state as VectorAnsatz every local energy equals E0 (zero variance), the
+    residence-time histogram converges to |v|^2, the gradient is empty, and a continuation doubles the rows."""
+    N = M = 5
+    o = oracle_mod.Oracle(N, M, 1.0, 0.1)  # HubbardReal1D(near_uniform(BoseFS{5,5}); t=0.1) (test/qmc.jl:11)
+    basis = o.build_basis()
+    index = {int(b[0]): i for i, b in enumerate(basis)}
+    Hm = np.zeros((len(basis), len(basis)))
+    for i, b in enumerate(basis):
+        Hm[i, i] = o.diagonal_element(b)
+        for new, me in o.offdiagonals(b):
+            Hm[index[int(new[0])], i] += me
+    w, vecs = np.linalg.eigh(Hm)
+    E0, gs = w[0], vecs[:, 0] * np.sign(vecs[0, 0])
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), t=0.1)
+    va = gw.VectorAnsatz((basis[:, :1], gs))
+    assert gw.num_parameters(va) == 0
+    res = gw.kinetic_vqmc(H, va, [], samples=1e6, walkers=256, record=True)
+    val, grad = gw.val_and_grad(res)
+    assert len(grad) == 0 and abs(val - E0) < 1e-9
+    el = res.local_energies()
+    assert np.max(np.abs(el - E0)) < 1e-8  # zero-variance property of an eigenvector
+    addrs, vals = gw.sampled_vector(res)
+    sq = gs ** 2 / np.linalg.norm(gs ** 2)
+    lookup = {int(b[0]): s for b, s in zip(basis, sq)}
+    dot = sum(v * lookup[int(a)] for a, v in zip(addrs[:, 0], vals))
+    assert abs(dot - 1.0) < 2e-4
+    n0 = len(res)
+    gw.kinetic_vqmc_continue(res)
+    assert len(res) == 2 * n0
+    # LocalEnergyEvaluator over keys(v) is the Rayleigh quotient; lookups follow DVec semantics (0 for missing keys)
+    le = gw.LocalEnergyEvaluator(H, va)
+    assert abs(le([]) - E0) < 1e-10 and le.dim == len(basis)
+    h = va.handle(H)
+    assert np.allclose(h.lookup(basis[:7, :1]), gs[:7], rtol=0, atol=0)
+    part = gw.VectorAnsatz((basis[:50, :1], gs[:50]))
+    assert part.handle(H).lookup(basis[60:61, :1])[0] == 0.0
+    # a walker on a partial vector never leaves its support
+    if abs(gs[0]) > 0:
+        r2 = gw.kinetic_vqmc(H, part, [], walkers=8, steps=200, record=True)
+        seen = set(int(a) for a in r2.addresses()[:, :, 0].ravel())
+        assert seen <= set(int(b[0]) for b in basis[:50])
