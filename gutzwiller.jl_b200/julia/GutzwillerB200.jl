@@ -440,4 +440,43 @@ end
 # amsgrad / gradient_descent of the reference (amsgrad.jl:105-263) are generic over objectives with
 # val_and_grad / val_err_and_grad, so they drive GPUGenericVQMC and GPUGenericLocalEnergyEvaluator unmodified.
 
+# ------------------------------------------------------------------------------------------
+# VectorAnsatz (src/ansatz/vector.jl:1-12): the pairs of the DVec live in an HBM hash table
+# ------------------------------------------------------------------------------------------
+mutable struct GPUVectorAnsatz
+    ptr::Ptr{Cvoid}
+    model::GPUModel
+end
+function GPUVectorAnsatz(H, va::VectorAnsatz, ctx::GPUContext=default_context())
+    model = GPUModel(H, ctx)
+    ks = collect(keys(va.vector))
+    words = reduce(vcat, (address_words(model, k) for k in ks))
+    vals = Float64[va.vector[k] for k in ks]
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_vector_ansatz_create, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt64}, Ptr{Cdouble}, UInt64, Ref{Ptr{Cvoid}}),
+                model.ptr, words, vals, length(ks), r))
+    a = GPUVectorAnsatz(r[], model)
+    finalizer(x -> ccall((:gwz_vector_ansatz_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), a)
+    return a
+end
+# LocalEnergyEvaluator(H, VectorAnsatz(v))() over basis = keys(v): the Rayleigh quotient
+function rayleigh(a::GPUVectorAnsatz)
+    val = Ref(0.0)
+    check(ccall((:gwz_vector_ansatz_rayleigh, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), a.ptr, val))
+    return val[]
+end
+# kinetic_vqmc(H, VectorAnsatz(v), Float64[]; walkers, steps) (test/qmc.jl:22-23): returns the gwz_gen_result
+function kinetic_vqmc(H, va::VectorAnsatz, ::AbstractVector; walkers=2^12, steps=1000, seed::UInt64=0x9E3779B97F4A7C15,
+                      ctx=default_context())
+    a = GPUVectorAnsatz(H, va, ctx)
+    start = address_words(a.model, starting_address(H))
+    w = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_vwalkers_create, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Ptr{UInt64}, UInt64, Ref{Ptr{Cvoid}}),
+                a.ptr, walkers, 0, start, seed, w))
+    res = Ref(GenResult(0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:gwz_vwalkers_run, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Cuint, Ref{GenResult}), w[], steps, 0, Cuint(0), res))
+    ccall((:gwz_vwalkers_destroy, LIB), Cint, (Ptr{Cvoid},), w[])
+    return res[]
+end
+
 end # module
