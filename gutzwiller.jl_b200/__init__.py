@@ -15,7 +15,7 @@ from .amsgrad import (GradientDescentResult, adaptive_gradient_descent, amsgrad,
                       val_err_and_grad)
 from .ansatz import (CombinationAnsatz, DensityProfileAnsatz, ExtendedGutzwillerAnsatz, ExtendedHubbardReal1D, GenericGutzwillerAnsatz, GenWalkers,
                      JastrowAnsatz,
-                     MultinomialAnsatz, RelativeJastrowAnsatz, VectorAnsatz)
+                     MultinomialAnsatz, RelativeJastrowAnsatz, VectorAnsatz, collect_to_vec)
 from .hamiltonian import (AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1D, keytype, near_uniform,
                           num_modes, num_parameters, starting_address, valtype)
 from .localenergy import LocalEnergyEvaluator

@@ -467,3 +467,24 @@ class VecWalkers:
         check(lib().gwz_vwalkers_run_record(self._h, steps, _capi.RUN_KEEP_ACC if keep_acc else 0, _vp(tau), _vp(eloc),
                                             _vp(addr), C.byref(r)))
         return GenRunResult(r, np.zeros(0), np.zeros(0), np.zeros(0)), tau, eloc, addr
+
+
+def collect_to_vec(ansatz, params, basis=None, ctx: Context | None = None):
+    """``DVec(ansatz, params; basis=build_basis(ansatz))`` (abstract.jl:24-41): the ansatz evaluated on a basis.
+    Returns ``(addresses uint64[dim, W], values float64[dim])``; without ``basis`` all C(N+M-1, N) Fock states are
+    enumerated on the device (needs N+M-1 <= 64)."""
+    if getattr(ansatz, "vector_ansatz", False):
+        return ansatz.addresses.copy(), ansatz.values.copy()
+    H = ansatz.hamiltonian
+    model = H.model(ctx)
+    if basis is None:
+        from .localenergy import LocalEnergyEvaluator
+        basis = LocalEnergyEvaluator(H, ansatz, ctx=ctx).states()
+    elif len(basis) and isinstance(basis[0], BoseFS):
+        basis = np.stack([b.words for b in basis])
+    basis = np.ascontiguousarray(basis, dtype=np.uint64).reshape(-1, model.words)
+    if getattr(ansatz, "generic", False):
+        vals, _ = ansatz.handle(ctx).eval(basis, params, want_grad=False)
+    else:
+        vals, _ = model.ansatz_val_and_grad(basis, as_params(params, 1))
+    return basis, vals

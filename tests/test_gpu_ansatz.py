@@ -321,3 +321,15 @@ def test_vector_ansatz_samples_an_eigenvector(gw, oracle_mod):
         r2 = gw.kinetic_vqmc(H, part, [], walkers=8, steps=200, record=True)
         seen = set(int(a) for a in r2.addresses()[:, :, 0].ravel())
         assert seen <= set(int(b[0]) for b in basis[:50])
+
+
+def test_collect_to_vec_and_vector_ansatz_round_trip(gw):
+    """DVec(ansatz, params) (abstract.jl:24-41) materialised on the device, fed back as a VectorAnsatz: its Rayleigh
+    quotient equals the LocalEnergyEvaluator value of the original ansatz (test/ansatz.jl:37-38)."""
+    H = gw.HubbardReal1D(gw.near_uniform(6, 6), u=2.0)
+    for ans, p in ((gw.GutzwillerAnsatz(H), [0.4]), (gw.RelativeJastrowAnsatz(H), [0.3, 0.05, 0.02])):
+        addrs, vals = gw.collect_to_vec(ans, p)
+        assert addrs.shape == (462, 1) and np.all(vals > 0)
+        rq = gw.LocalEnergyEvaluator(H, gw.VectorAnsatz((addrs, vals)))([])
+        le = gw.LocalEnergyEvaluator(H, ans)(p)
+        assert abs(rq - le) < 1e-11 * abs(le)
