@@ -211,3 +211,13 @@ def test_orbit_reduced_sweep_equals_full_sweep(gw, N, M, monkeypatch):
             gw.lib().gwz_sweep_destroy(h)
             acc += np.array(a4[:])
         assert np.all(np.abs(acc - b[0]) <= 1e-12 * np.abs(b[0]))
+
+
+def test_orbit_reduced_sweep_at_the_64_bit_limit(gw, monkeypatch):
+    """N + M = 64: the closed unary string fills a 64-bit word exactly (largest system the orbit test handles)."""
+    H = gw.HubbardReal1D(gw.near_uniform(60, 4), u=0.5, t=1.0)
+    out = {}
+    for sym in ("1", "0"):
+        monkeypatch.setenv("GWZ_SWEEP_SYM", sym)
+        out[sym] = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H)).accumulators(0.004)
+    assert np.all(np.isfinite(out["0"])) and np.all(np.abs(out["1"] - out["0"]) <= 1e-12 * np.abs(out["0"]))
