@@ -188,7 +188,7 @@ __device__ __forceinline__ bool orbit_representative(T e, int L, T maskL, int M,
         if (r > e) return false;
         same += (r == e);
     }
-    mult = M / (same + 1);
+    mult = same ? M / (same + 1) : M;  // the stabiliser is trivial for almost every orbit: keep the division off the common path
     return true;
 }
 
