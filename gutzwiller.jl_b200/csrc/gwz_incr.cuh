@@ -35,16 +35,18 @@ struct IncrScratch {
         return sizeof(double) * (size_t)(3 * N + 4) + sizeof(double) * 64 + sizeof(uint32_t) * 256 +
                sizeof(uint32_t) * (size_t)(INCR_ROWS + ONR_WORDS) * STEP_BLOCK;
     }
+    // fixed-size regions first: their shared-memory offsets are compile-time constants (immediates of LDS / STS); the
+    // N-dependent rate tables (only used by the rare generic-bond path) come last
     __device__ __forceinline__ IncrScratch(unsigned char* base, int N) {
-        exptab = reinterpret_cast<double*>(base);
-        sqrtab = exptab + (2 * N + 2);
-        FS = sqrtab + (N + 2);
+        FS = reinterpret_cast<double*>(base);
         RR = FS + 16;
         IRR = RR + 16;
         IRL = IRR + 16;
         nth = reinterpret_cast<uint32_t*>(IRL + 16);
         cnt = nth + 256;
         onr = cnt + INCR_ROWS * STEP_BLOCK;
+        exptab = reinterpret_cast<double*>(onr + ONR_WORDS * STEP_BLOCK);
+        sqrtab = exptab + (2 * N + 2);
     }
     __device__ __forceinline__ void fill_tables(int N, const DevTables& tb) const {
         for (int i = threadIdx.x; i < 2 * N + 2; i += blockDim.x) exptab[i] = exp(-tb.c * (double)(i - N));
@@ -139,11 +141,24 @@ struct BigCache {
     bool valid;
 };
 
+// modes with >= 4 particles (OR of the planes >= 2): carried with the walker, refreshed only when a hop ripples into
+// those planes
+template <int NWM, int NP>
+__device__ __forceinline__ void big_plane(const uint32_t (&p)[NP][NWM], uint32_t (&bigP)[NWM]) {
+#pragma unroll
+    for (int i = 0; i < NWM; ++i) {
+        uint32_t b = p[2][i];
+#pragma unroll
+        for (int k = 3; k < NP; ++k) b |= p[k][i];
+        bigP[i] = b;
+    }
+}
+
 // one kinetic_sample! (qmc.jl:14-44) with incremental class counts
 template <int NWM, int NP>
 __device__ __forceinline__ void step_incr(uint32_t (&p)[NP][NWM], const DevModel& dm, const DevTables& tb,
-                                          const IncrScratch<NWM>& sc, BigCache& bc, double u01, double& tau,
-                                          double& eloc, double& gratio, int& nhops) {
+                                          const IncrScratch<NWM>& sc, BigCache& bc, uint32_t (&bigP)[NWM], double u01,
+                                          double& tau, double& eloc, double& gratio, int& nhops) {
     const int tid = threadIdx.x;
     uint32_t* const cntp = sc.cnt + tid;
     // ---- S, E, D, occupied modes from the class counts (same order as bond_sums) ----
@@ -170,16 +185,10 @@ __device__ __forceinline__ void step_incr(uint32_t (&p)[NP][NWM], const DevModel
     }
     const double reg_total = S;
     // ---- generic bonds (a neighbour with >= 4 particles): rare, evaluated from the planes ----
-    uint32_t bigP[NWM], bigm[NWM];
+    uint32_t bigm[NWM];
     uint32_t anyb = 0u;
 #pragma unroll
-    for (int i = 0; i < NWM; ++i) {
-        uint32_t b = p[2][i];
-#pragma unroll
-        for (int k = 3; k < NP; ++k) b |= p[k][i];
-        bigP[i] = b;
-        anyb |= b;
-    }
+    for (int i = 0; i < NWM; ++i) anyb |= bigP[i];
 #pragma unroll
     for (int i = 0; i < NWM; ++i) bigm[i] = 0u;
     long long d = dd;
@@ -290,7 +299,7 @@ __device__ __forceinline__ void step_incr(uint32_t (&p)[NP][NWM], const DevModel
     cntp[x24 * STEP_BLOCK] += count_unit(y24);
     cntp[y4 * STEP_BLOCK] -= ub;                                // bond z+1: (y,b)  -> (y',b)
     cntp[y24 * STEP_BLOCK] += ub;
-    apply_hop_planes<NWM, NP>(p, dm, z, right);
+    if (apply_hop_planes<NWM, NP>(p, dm, z, right)) big_plane<NWM, NP>(p, bigP);
 }
 
 }  // namespace gwz

@@ -147,10 +147,12 @@ __device__ __forceinline__ void bit_words(int pos, uint32_t (&c)[NWM]) {
 }
 
 // n_pos += 1 / -= 1 by a bit-sliced ripple; the carry rarely travels beyond plane 1
+// (both return whether the ripple reached plane 2 or higher, i.e. whether the ">= 4 particles" plane changed)
 template <int NWM, int NP>
-__device__ __forceinline__ void planes_inc(uint32_t (&p)[NP][NWM], int pos) {
+__device__ __forceinline__ bool planes_inc(uint32_t (&p)[NP][NWM], int pos) {
     uint32_t c[NWM];
     bit_words<NWM>(pos, c);
+    bool high = false;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         if (k >= 2) {
@@ -158,6 +160,7 @@ __device__ __forceinline__ void planes_inc(uint32_t (&p)[NP][NWM], int pos) {
 #pragma unroll
             for (int i = 0; i < NWM; ++i) any |= c[i];
             if (!any) break;
+            high = true;
         }
 #pragma unroll
         for (int i = 0; i < NWM; ++i) {
@@ -166,11 +169,13 @@ __device__ __forceinline__ void planes_inc(uint32_t (&p)[NP][NWM], int pos) {
             c[i] = carry;
         }
     }
+    return high;
 }
 template <int NWM, int NP>
-__device__ __forceinline__ void planes_dec(uint32_t (&p)[NP][NWM], int pos) {
+__device__ __forceinline__ bool planes_dec(uint32_t (&p)[NP][NWM], int pos) {
     uint32_t c[NWM];
     bit_words<NWM>(pos, c);
+    bool high = false;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         if (k >= 2) {
@@ -178,6 +183,7 @@ __device__ __forceinline__ void planes_dec(uint32_t (&p)[NP][NWM], int pos) {
 #pragma unroll
             for (int i = 0; i < NWM; ++i) any |= c[i];
             if (!any) break;
+            high = true;
         }
 #pragma unroll
         for (int i = 0; i < NWM; ++i) {
@@ -186,14 +192,16 @@ __device__ __forceinline__ void planes_dec(uint32_t (&p)[NP][NWM], int pos) {
             c[i] = borrow;
         }
     }
+    return high;
 }
 
 // hop across bond z (between mode z and mode z+1 mod M): right = z -> z+1, left = z+1 -> z
 template <int NWM, int NP>
-__device__ __forceinline__ void apply_hop_planes(uint32_t (&p)[NP][NWM], const DevModel& dm, int z, bool right) {
+__device__ __forceinline__ bool apply_hop_planes(uint32_t (&p)[NP][NWM], const DevModel& dm, int z, bool right) {
     const int zn = (z + 1 == dm.M) ? 0 : z + 1;
-    planes_dec<NWM, NP>(p, right ? z : zn);
-    planes_inc<NWM, NP>(p, right ? zn : z);
+    const bool a = planes_dec<NWM, NP>(p, right ? z : zn);
+    const bool b = planes_inc<NWM, NP>(p, right ? zn : z);
+    return a || b;
 }
 
 // one kinetic_sample! (qmc.jl:14-44) on the plane representation

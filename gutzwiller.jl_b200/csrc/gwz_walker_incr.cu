@@ -45,6 +45,8 @@ walker_incr_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
         bc.S = bc.E = 0.0;
         bc.nocc = bc.d = 0;
         bc.valid = false;
+        uint32_t bigP[NWM];
+        big_plane<NWM, NP>(pl, bigP);
         double st, ste, stg, stge, stee;
         if (reset_acc || !accumulate) {
             st = ste = stg = stge = stee = 0.0;
@@ -70,7 +72,7 @@ walker_incr_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
             const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
             double tau, eloc, gr;
             int nh;
-            step_incr<NWM, NP>(pl, dm, tb, sc, bc, u01, tau, eloc, gr, nh);
+            step_incr<NWM, NP>(pl, dm, tb, sc, bc, bigP, u01, tau, eloc, gr, nh);
             hops += (unsigned)nh;
             const double dE = eloc - E0, dG = gr - G0;
             const double tE = tau * dE;
