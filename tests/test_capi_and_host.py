@@ -233,3 +233,11 @@ def test_graft_entry_build_is_consistent_with_the_header():
     """build() (the driver's "does it build" check) must accept the library it has just built."""
     import __graft_entry__ as g
     g.build()
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (what a Julia ccall / cgo / ctypes binding reads)."""
+    src = tmp_path / "c.c"
+    src.write_text('#include "gutzwiller_b200.h"\nint main(void) { gwz_gen_result r; gwz_vqmc_result v; (void)r; (void)v; return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                    str(src), "-o", str(tmp_path / "c.o")], check=True)
