@@ -21,6 +21,7 @@ from .hamiltonian import (AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1
 from .localenergy import LocalEnergyEvaluator
 from .runtime import (Context, Model, comm_init_all, default_context, distributed_state, init_distributed,
                       launch_count, nccl_unique_id, shard_range)
+from .sparse import (SparseGutzwillerAnsatz, SparseHamiltonian, SparseVectorAnsatz, SparseWalkers, TableAnsatz)
 from .vqmc import (BlockingResult, CombinedBlockingResult, KineticVQMC, KineticVQMCResult, Walkers,
                    blocking_analysis, default_walkers, kinetic_vqmc, kinetic_vqmc_continue,
                    local_energy_estimator, mean, resample, run_group, sampled_vector, var)

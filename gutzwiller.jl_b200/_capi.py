@@ -167,6 +167,27 @@ SIGNATURES = {
     "gwz_vwalkers_get_addresses": (C.c_int, [_vp, _vp]),
     "gwz_vwalkers_run": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(GenResult)]),
     "gwz_vwalkers_run_record": (C.c_int, [_vp, C.c_uint64, C.c_uint, _vp, _vp, _vp, C.POINTER(GenResult)]),
+    # ---- stored operators (any Hamiltonian, any ansatz) ----
+    "gwz_sparse_create": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "gwz_sparse_destroy": (C.c_int, [_vp]),
+    "gwz_sparse_info": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gwz_sparse_set_table": (C.c_int, [_vp, _vp, _vp, C.c_int32]),
+    "gwz_sparse_set_gutzwiller": (C.c_int, [_vp, C.c_double]),
+    "gwz_sparse_get_table": (C.c_int, [_vp, _vp, _vp]),
+    "gwz_sparse_probe": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gwz_sparse_sweep": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _dp, _vp]),
+    "gwz_sparse_sweep_terms": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "gwz_sparse_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "gwz_swalkers_create": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
+    "gwz_swalkers_destroy": (C.c_int, [_vp]),
+    "gwz_swalkers_get_indices": (C.c_int, [_vp, _vp]),
+    "gwz_swalkers_set_indices": (C.c_int, [_vp, _vp]),
+    "gwz_swalkers_set_step_counter": (C.c_int, [_vp, C.c_uint64]),
+    "gwz_swalkers_run": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint, C.POINTER(GenResult), _vp, _vp, _vp]),
+    "gwz_swalkers_run_record": (C.c_int, [_vp, C.c_uint64, C.c_uint, _vp, _vp, _vp, C.POINTER(GenResult), _vp, _vp, _vp]),
+    "gwz_swalkers_sample_vector": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint, _vp, C.POINTER(GenResult)]),
+    "gwz_swalkers_estimates": (C.c_int, [_vp, _vp, _vp]),
 }
 
 _lib = None

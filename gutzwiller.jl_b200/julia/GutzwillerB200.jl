@@ -16,6 +16,7 @@ using StaticArrays
 
 export GPUContext, GPUKineticVQMCResult, GPUKineticVQMC, GPULocalEnergyEvaluator
 export GPUAnsatz, GPUGenericVQMC, GPUGenericLocalEnergyEvaluator
+export GPUSparseHamiltonian, GPUSparseVQMC, GPUSparseLocalEnergyEvaluator, sampled_vector
 export kinetic_vqmc, kinetic_vqmc!, val_and_grad, val_err_and_grad, amsgrad, gradient_descent
 
 const LIB = get(ENV, "GUTZWILLER_B200_LIB",
@@ -477,6 +478,123 @@ function kinetic_vqmc(H, va::VectorAnsatz, ::AbstractVector; walkers=2^12, steps
     check(ccall((:gwz_vwalkers_run, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Cuint, Ref{GenResult}), w[], steps, 0, Cuint(0), res))
     ccall((:gwz_vwalkers_destroy, LIB), Cint, (Ptr{Cvoid},), w[])
     return res[]
+end
+
+# ------------------------------------------------------------------------------------------
+# Stored operators: ANY Rimu Hamiltonian and ANY ansatz (HubbardMom1D, HubbardRealSpace, ... of test/qmc.jl:10-14)
+# The operator is materialised over build_basis(H): row k = offdiagonals(H, basis[k]) in Rimu's order, and the
+# ansatz is tabulated over the basis per parameter set (GutzwillerAnsatz is filled on the device).
+# ------------------------------------------------------------------------------------------
+mutable struct GPUSparseHamiltonian{H,A}
+    hamiltonian::H
+    basis::Vector{A}
+    ptr::Ptr{Cvoid}
+    start::UInt32
+end
+function GPUSparseHamiltonian(H; basis=build_basis(H), ctx::GPUContext=default_context())
+    index = Dict(a => UInt32(i - 1) for (i, a) in enumerate(basis))
+    row_ptr = UInt64[0]; col = UInt32[]; melem = Float64[]; diag = Float64[]
+    for k in basis
+        push!(diag, diagonal_element(H, k))
+        for (l, m) in offdiagonals(H, k)                        # reference order (qmc.jl:15,25)
+            push!(col, index[l]); push!(melem, m)
+        end
+        push!(row_ptr, length(col))
+    end
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_sparse_create, LIB), Cint,
+                (Ptr{Cvoid}, UInt64, Ptr{UInt64}, Ptr{UInt32}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                ctx.ptr, length(basis), row_ptr, col, melem, diag, r))
+    s = GPUSparseHamiltonian(H, collect(basis), r[], index[starting_address(H)])
+    finalizer(x -> ccall((:gwz_sparse_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), s)
+    return s
+end
+# tabulate ansatz(., params) over the basis: psi and grad psi / psi (qmc.jl:18,38)
+function load!(s::GPUSparseHamiltonian, ansatz, params)
+    if ansatz isa GutzwillerAnsatz
+        check(ccall((:gwz_sparse_set_gutzwiller, LIB), Cint, (Ptr{Cvoid}, Cdouble), s.ptr, Float64(first(params))))
+        return s
+    end
+    np = num_parameters(ansatz); dim = length(s.basis)
+    psi = Vector{Float64}(undef, dim); gr = Matrix{Float64}(undef, np, dim)   # column k = grad_ratio[k][:]
+    p = SVector{np,Float64}(params)
+    for (i, k) in enumerate(s.basis)
+        v, g = val_and_grad(ansatz, k, p)
+        psi[i] = v
+        gr[:, i] .= g ./ v
+    end
+    check(ccall((:gwz_sparse_set_table, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int32),
+                s.ptr, psi, np == 0 ? C_NULL : gr, np))
+    return s
+end
+mutable struct GPUSparseVQMC{S,A}         # KineticVQMC(H, ansatz; samples, walkers, steps) (wrapper.jl:45-63)
+    op::S
+    ansatz::A
+    walkers_ptr::Ptr{Cvoid}
+    walkers::Int
+    steps::Int
+    last::GenResult
+    grad::Vector{Float64}
+    grad_err::Vector{Float64}
+end
+function GPUSparseVQMC(op::GPUSparseHamiltonian, ansatz; samples=1e6, walkers=2^16,
+                       steps=round(Int, samples / walkers), seed::UInt64=0x9E3779B97F4A7C15)
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:gwz_swalkers_create, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, UInt32, UInt64, Ref{Ptr{Cvoid}}),
+                op.ptr, walkers, 0, op.start, seed, r))
+    np = num_parameters(ansatz)
+    q = GPUSparseVQMC(op, ansatz, r[], Int(walkers), Int(steps), GenResult(0, 0, 0, 0, 0, 0, 0, 0, 0, np),
+                      zeros(max(np, 1)), zeros(max(np, 1)))
+    finalizer(x -> ccall((:gwz_swalkers_destroy, LIB), Cint, (Ptr{Cvoid},), x.walkers_ptr), q)
+    return q
+end
+function _run!(q::GPUSparseVQMC, params, steps::Integer; keep::Bool=false, burn_in::Integer=0)
+    load!(q.op, q.ansatz, params)
+    res = Ref(q.last)
+    check(ccall((:gwz_swalkers_run, LIB), Cint,
+                (Ptr{Cvoid}, UInt64, UInt64, Cuint, Ref{GenResult}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                q.walkers_ptr, steps, burn_in, keep ? GWZ_RUN_KEEP_ACC : Cuint(0), res, q.grad, q.grad_err, C_NULL))
+    q.last = res[]
+    return q
+end
+(q::GPUSparseVQMC)(params; samples=q.steps * q.walkers, steps=samples ÷ q.walkers) = _run!(q, params, steps).last.val
+function val_and_grad(q::GPUSparseVQMC, params; samples=q.steps * q.walkers, steps=samples ÷ q.walkers)
+    _run!(q, params, steps)
+    np = num_parameters(q.ansatz)
+    return q.last.val, SVector{np,Float64}(q.grad[1:np])                                       # wrapper.jl:90-97
+end
+function val_err_and_grad(q::GPUSparseVQMC, params; samples=q.steps * q.walkers, steps=samples ÷ q.walkers)
+    _run!(q, params, steps)
+    np = num_parameters(q.ansatz)
+    return q.last.val, q.last.err, SVector{np,Float64}(q.grad[1:np])                           # wrapper.jl:98-105
+end
+# DVec(res) (state.jl:303-319): residence time per address, accumulated on the device
+function sampled_vector(q::GPUSparseVQMC, params; steps=q.steps, burn_in=0)
+    load!(q.op, q.ansatz, params)
+    hist = zeros(length(q.op.basis)); res = Ref(q.last)
+    check(ccall((:gwz_swalkers_sample_vector, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Cuint, Ptr{Cdouble}, Ref{GenResult}),
+                q.walkers_ptr, steps, burn_in, Cuint(0), hist, res))
+    dv = DVec(zip(q.op.basis, hist)...)
+    return normalize!(dv)
+end
+# LocalEnergyEvaluator(H, ansatz) over the stored rows (localenergy.jl:81-173)
+struct GPUSparseLocalEnergyEvaluator{S,A}
+    op::S
+    ansatz::A
+end
+function val_and_grad(le::GPUSparseLocalEnergyEvaluator, params)                               # localenergy.jl:94-129
+    load!(le.op, le.ansatz, params)
+    np = num_parameters(le.ansatz); val = Ref(0.0); grad = zeros(max(np, 1))
+    check(ccall((:gwz_sparse_sweep, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Ref{Cdouble}, Ptr{Cdouble}),
+                le.op.ptr, 0, length(le.op.basis), val, np == 0 ? C_NULL : grad))
+    return val[], SVector{np,Float64}(grad[1:np])
+end
+function (le::GPUSparseLocalEnergyEvaluator)(params)                                           # localenergy.jl:131-155
+    load!(le.op, le.ansatz, params)
+    val = Ref(0.0)
+    check(ccall((:gwz_sparse_sweep, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Ref{Cdouble}, Ptr{Cdouble}),
+                le.op.ptr, 0, length(le.op.basis), val, C_NULL))
+    return val[]
 end
 
 end # module

@@ -23,6 +23,18 @@ class LocalEnergyEvaluator:
     def __init__(self, hamiltonian: HubbardReal1D, ansatz: AbstractAnsatz, *, basis=None, ctx: Context | None = None):
         self._gen = None
         self._vec = None
+        self._sp = None
+        if getattr(hamiltonian, "sparse_operator", False):  # stored operator (sparse.py): basis = its rows
+            if not getattr(ansatz, "sparse_ansatz", False) or ansatz.hamiltonian is not hamiltonian:
+                raise TypeError("a SparseHamiltonian needs an ansatz tabulated over its basis")
+            if basis is not None:
+                raise ValueError("a SparseHamiltonian is already materialised over its basis; do not pass one")
+            self.hamiltonian, self.ansatz, self.P = hamiltonian, ansatz, ansatz.N_PARAMS
+            self.model = self._sp = hamiltonian.handle(ctx)
+            self._h = self._sp.handle
+            world, rank = distributed_state() if ctx is None else (1, 0)
+            self._rows = shard_range(hamiltonian.dim, world, rank)
+            return
         if getattr(ansatz, "vector_ansatz", False):  # basis = keys(vector) (vector.jl:10): the Rayleigh quotient
             if basis is not None:
                 raise ValueError("LocalEnergyEvaluator(H, VectorAnsatz(v)) sweeps keys(v); do not pass a basis")
@@ -72,6 +84,8 @@ class LocalEnergyEvaluator:
 
     @property
     def dim(self) -> int:
+        if self._sp is not None:
+            return self.hamiltonian.dim
         if self._vec is not None:
             return int(self.ansatz.values.size)
         if self._gen is not None:
@@ -82,6 +96,9 @@ class LocalEnergyEvaluator:
 
     def val_and_grad(self, params):
         """``val_and_grad(le, params)`` (localenergy.jl:94-129)."""
+        if self._sp is not None:
+            self._sp.load(self.ansatz, params)
+            return self._sp.sweep(True, *self._rows)
         if self._vec is not None:
             return self._vec.rayleigh(), np.zeros(0)
         if self._gen is not None:
@@ -108,6 +125,9 @@ class LocalEnergyEvaluator:
                 val = self(params)
             return val if F is not None else None
         params = args[0] if len(args) == 1 else args  # le(p...) (localenergy.jl:171-173)
+        if self._sp is not None:
+            self._sp.load(self.ansatz, params)
+            return self._sp.sweep(False, *self._rows)[0]
         if self._vec is not None:
             return self._vec.rayleigh()
         if self._gen is not None:
@@ -120,6 +140,9 @@ class LocalEnergyEvaluator:
     def terms(self, params, first: int = 0, count: int | None = None) -> np.ndarray:
         """Per-state (num, den, num_grad[P], den_grad[P]) of localenergy.jl:105-120: float64[count, 2 + 2P]."""
         count = self.dim - first if count is None else int(count)
+        if self._sp is not None:
+            self._sp.load(self.ansatz, params)
+            return self._sp.sweep_terms(first, count)
         if self._gen is not None:
             return self._gen.terms(params, first, count)
         p = as_params(params, 1)
@@ -130,6 +153,8 @@ class LocalEnergyEvaluator:
 
     def states(self, first: int = 0, count: int | None = None) -> np.ndarray:
         count = self.dim - first if count is None else int(count)
+        if self._sp is not None:
+            return np.arange(first, first + count, dtype=np.uint64).reshape(-1, 1)  # basis indices
         if self._gen is not None:
             return self._gen.states(first, count)
         out = np.zeros((count, self.model.words), dtype=np.uint64)
@@ -137,6 +162,8 @@ class LocalEnergyEvaluator:
         return out
 
     def last_kernel_ms(self) -> float:
+        if self._sp is not None:
+            return self._sp.last_kernel_ms()
         if self._gen is not None:
             return self._gen.last_kernel_ms()
         ms = C.c_float()

@@ -235,6 +235,14 @@ class KineticVQMCResult:
         """Tables.jl rows (state.jl:91-132): (walker, step, address, residence_time, local_energy)."""
         tau, el, ad = self.residence_times(), self.local_energies(), self.addresses()
         N, M = self.hamiltonian.address.N, self.hamiltonian.address.M
+        if _is_sparse(self.hamiltonian):  # the address of basis index i (or i itself when no addresses were given)
+            names = self.hamiltonian.addresses
+            for w in range(tau.shape[0]):
+                for k in range(tau.shape[1]):
+                    i = int(ad[w, k, 0])
+                    yield dict(walker=w + 1, step=k + 1, address=i if names is None else names[i],
+                               residence_time=tau[w, k], local_energy=el[w, k])
+            return
         for w in range(tau.shape[0]):
             for k in range(tau.shape[1]):
                 yield dict(walker=w + 1, step=k + 1, address=BoseFS.from_words(N, M, ad[w, k]),
@@ -277,7 +285,18 @@ def _is_generic(ansatz) -> bool:
     return bool(getattr(ansatz, "generic", False))
 
 
+def _is_sparse(hamiltonian) -> bool:
+    """stored operators (sparse.py): any Hamiltonian materialised over its basis"""
+    return bool(getattr(hamiltonian, "sparse_operator", False))
+
+
 def _check_pair(hamiltonian, ansatz):
+    if _is_sparse(hamiltonian) or getattr(ansatz, "sparse_ansatz", False):
+        if not (_is_sparse(hamiltonian) and getattr(ansatz, "sparse_ansatz", False)):
+            raise TypeError("a SparseHamiltonian needs an ansatz tabulated over its basis (sparse.py), and vice versa")
+        if ansatz.hamiltonian is not hamiltonian:
+            raise TypeError("the ansatz was built for a different Hamiltonian")
+        return
     if getattr(ansatz, "vector_ansatz", False):
         return  # VectorAnsatz holds no Hamiltonian (vector.jl:6-8)
     if not isinstance(ansatz, AbstractAnsatz) or not hasattr(ansatz, "hamiltonian"):
@@ -294,6 +313,7 @@ def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn
                  estimator="walker_mean"):
     _check_pair(hamiltonian, ansatz)
     model = hamiltonian.model(ctx)
+    words = 1 if _is_sparse(hamiltonian) else model.words
     world, rank = distributed_state() if (ctx is None) else (1, 0)
     begin, end = shard_range(walkers, world, rank)
     if end <= begin:
@@ -303,8 +323,11 @@ def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn
             raise ValueError("estimator='pooled' works on the running sums; use record=False")
         record = False
     if record is None:
-        record = (end - begin) * max(steps, 1) * (16 + 8 * model.words) <= RECORD_LIMIT_BYTES and world == 1
-    if getattr(ansatz, "vector_ansatz", False):
+        record = (end - begin) * max(steps, 1) * (16 + 8 * words) <= RECORD_LIMIT_BYTES and world == 1
+    if _is_sparse(hamiltonian):
+        from .sparse import SparseWalkers
+        w = SparseWalkers(model, ansatz, end - begin, hamiltonian.address.index, seed=seed, global_offset=begin)
+    elif getattr(ansatz, "vector_ansatz", False):
         from .ansatz import VecWalkers
         w = VecWalkers(ansatz.handle(hamiltonian, ctx), end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
     elif _is_generic(ansatz):
@@ -358,6 +381,9 @@ def _grad_ratio_series(res: KineticVQMCResult) -> np.ndarray:
     gutzwiller.jl:30), recomputed on the GPU from the recorded addresses."""
     ad = res.addresses()
     nw, ns, W = ad.shape
+    if _is_sparse(res.hamiltonian):  # the table itself holds grad psi / psi per basis index
+        gr = np.asarray(res.ansatz.table(res.params)[1], dtype=np.float64).reshape(res.hamiltonian.dim, -1)
+        return gr[ad[:, :, 0].astype(np.int64)]
     if getattr(res.ansatz, "vector_ansatz", False):
         return np.zeros((nw, ns, 0))
     if _is_generic(res.ansatz):

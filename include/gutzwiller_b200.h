@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GWZ_VERSION 110
+#define GWZ_VERSION 120
 #define GWZ_MAX_WORDS 4       /* 64-bit words per address (N+M-1 <= 251) */
 #define GWZ_NUM_PARAMS 1      /* GutzwillerAnsatz has one parameter g (gutzwiller.jl:14) */
 #define GWZ_NCCL_ID_BYTES 128 /* sizeof(ncclUniqueId) */
@@ -319,6 +319,56 @@ int gwz_vwalkers_get_addresses(gwz_vwalkers *w, uint64_t *addr_words);
 int gwz_vwalkers_run(gwz_vwalkers *w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags, gwz_gen_result *out);
 int gwz_vwalkers_run_record(gwz_vwalkers *w, uint64_t steps_per_walker, unsigned flags, double *tau, double *eloc,
                             uint64_t *addr, gwz_gen_result *out);
+
+/* ---- Stored operators: the path for ANY Hamiltonian and ANY ansatz --------
+ * kinetic_sample! (src/kinetic-vqmc/qmc.jl:14-44) and LocalEnergyEvaluator (src/localenergy.jl:94-155) only call
+ * offdiagonals(H, k), diagonal_element(H, k) and ansatz(k, params).  For operators other than the Hubbard chain
+ * (HubbardMom1D, HubbardRealSpace, ... of test/qmc.jl:10-14) the caller materialises them over basis =
+ * build_basis(H): row k = offdiagonals(H, basis[k]) in the reference's order as (column index, matrix element),
+ * diag[k] = diagonal_element(H, basis[k]); the ansatz is a table psi[k] = ansatz(basis[k], params) with
+ * grad_ratio[k][p] = (d psi / d p_p) / psi.  Walker state is the basis index.  Results use gwz_gen_result. */
+typedef struct gwz_sparse gwz_sparse;
+typedef struct gwz_swalkers gwz_swalkers;
+/* row_ptr[dim + 1] (row_ptr[0] = 0), col[nnz] < dim, melem[nnz], diag[dim]; dim < 2^32.  Duplicate targets inside a
+ * row are allowed (Rimu lists both directions of a length-2 periodic axis). */
+int gwz_sparse_create(gwz_context *ctx, uint64_t dim, const uint64_t *row_ptr, const uint32_t *col,
+                      const double *melem, const double *diag, gwz_sparse **out);
+int gwz_sparse_destroy(gwz_sparse *h);
+int gwz_sparse_info(const gwz_sparse *h, uint64_t *dim, uint64_t *nnz, uint64_t *max_row, int32_t *num_parameters,
+                    int32_t *lanes_per_walker);
+/* any ansatz as a table (P = num_parameters; grad_ratio may be NULL when P = 0, e.g. VectorAnsatz, vector.jl:6-12) */
+int gwz_sparse_set_table(gwz_sparse *h, const double *psi, const double *grad_ratio, int32_t P);
+/* GutzwillerAnsatz(H) (gutzwiller.jl:25-36) filled on the device: psi = exp(-g diag), grad psi / psi = -diag */
+int gwz_sparse_set_gutzwiller(gwz_sparse *h, double g);
+int gwz_sparse_get_table(gwz_sparse *h, double *psi, double *grad_ratio);
+/* per-index kinetic_sample! outputs; rates: n x max_row (|psi_l / psi_k| in row order, 0 padded), chosen 1-based */
+int gwz_sparse_probe(gwz_sparse *h, const uint32_t *idx, size_t n, const double *u01, double *e_loc,
+                     double *residence_time, double *grad_ratio, int32_t *n_hops, double *rates, int32_t *chosen,
+                     uint32_t *next_idx);
+/* val_and_grad(le, params) (localenergy.jl:94-129; grad == NULL: le(params), :131-155) over rows
+ * [row_begin, row_end); with a communicator the sums are all-reduced, so each rank may pass its slice of the rows */
+int gwz_sparse_sweep(gwz_sparse *h, uint64_t row_begin, uint64_t row_end, double *val, double *grad);
+/* per-row (num, den, num_grad[P], den_grad[P]): out[count x (2 + 2P)] */
+int gwz_sparse_sweep_terms(gwz_sparse *h, uint64_t first, uint64_t count, double *out);
+int gwz_sparse_last_kernel_ms(const gwz_sparse *h, float *ms);
+/* walkers: global ids [global_offset, global_offset + n) key the random streams as everywhere else */
+int gwz_swalkers_create(gwz_sparse *h, uint64_t n_walkers, uint64_t global_offset, uint32_t start_index,
+                        uint64_t seed, gwz_swalkers **out);
+int gwz_swalkers_destroy(gwz_swalkers *w);
+int gwz_swalkers_get_indices(gwz_swalkers *w, uint32_t *idx);
+int gwz_swalkers_set_indices(gwz_swalkers *w, const uint32_t *idx);
+int gwz_swalkers_set_step_counter(gwz_swalkers *w, uint64_t steps_done);
+/* as gwz_gen_vqmc_run, with the table currently set on the operator */
+int gwz_swalkers_run(gwz_swalkers *w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags,
+                     gwz_gen_result *out, double *grad, double *grad_err, double *pooled_grad);
+/* series are [step][walker]; idx (optional) = the index each step was sampled from (qmc.jl:89) */
+int gwz_swalkers_run_record(gwz_swalkers *w, uint64_t steps_per_walker, unsigned flags, double *tau, double *eloc,
+                            uint32_t *idx, gwz_gen_result *out, double *grad, double *grad_err, double *pooled_grad);
+/* DVec(res) (state.jl:303-319): total residence time per basis index, hist[dim] (all-reduced with a communicator) */
+int gwz_swalkers_sample_vector(gwz_swalkers *w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags,
+                               double *hist, gwz_gen_result *out);
+/* per-walker estimates (state.jl:42-49): val_w[n], grad_w[n x P] */
+int gwz_swalkers_estimates(gwz_swalkers *w, double *val_w, double *grad_w);
 
 #ifdef __cplusplus
 }

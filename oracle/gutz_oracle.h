@@ -189,6 +189,23 @@ int go_kinetic_vqmc_fast(const go_model *m, double g, go_addr *addrs, int64_t n_
                          uint64_t walker0, uint64_t step0, int n_threads, double *val_w, double *grad_w,
                          int64_t *total_hops);
 
+/* ---- part 3 (gutz_oracle_sparse.c): the same path over a materialised operator (any Hamiltonian, any ansatz) ----
+ * rows = offdiagonals(H, basis[k]) in reference order as (col, melem); diag[k]; psi[k]; grad_ratio[k][P] */
+int go_sparse_kinetic_sample(const uint64_t *row_ptr, const uint32_t *col, const double *melem, const double *diag,
+                             const double *psi, const double *grad_ratio, int P, uint32_t k, double u01,
+                             double *prob_buffer, uint32_t *new_index, double *residence_time, double *local_energy,
+                             double *gradient, int *chosen, int *n_hops);
+int go_sparse_kinetic_vqmc(const uint64_t *row_ptr, const uint32_t *col, const double *melem, const double *diag,
+                           const double *psi, const double *grad_ratio, int P, uint32_t *idx, int64_t n_walkers,
+                           int64_t steps, uint64_t seed, uint64_t walker0, uint64_t step0, uint32_t *series_idx,
+                           double *series_tau, double *series_eloc, double *val_w, double *grad_w, int64_t *total_hops,
+                           uint64_t dim);
+void go_sparse_lee_terms(const uint64_t *row_ptr, const uint32_t *col, const double *melem, const double *diag,
+                         const double *psi, const double *grad_ratio, int P, uint64_t k, double *out);
+void go_sparse_lee_val_and_grad(const uint64_t *row_ptr, const uint32_t *col, const double *melem, const double *diag,
+                                const double *psi, const double *grad_ratio, int P, uint64_t dim, double *val,
+                                double *grad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ MAXW = 4
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("gutz_oracle.c", "gutz_oracle_ansatz.c", "gutz_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("gutz_oracle.c", "gutz_oracle_ansatz.c", "gutz_oracle_sparse.c", "gutz_oracle.h", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -125,6 +125,16 @@ def lib():
                                           C.c_void_p, C.POINTER(C.c_int64)]
         L.go_kinetic_vqmc_fast.argtypes = [mp, C.c_double, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64,
                                            C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        vp = C.c_void_p
+        L.go_sparse_kinetic_sample.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_uint32, C.c_double, vp,
+                                               C.POINTER(C.c_uint32), dp, dp, vp, ip, ip]
+        L.go_sparse_kinetic_vqmc.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int64, C.c_int64, C.c_uint64,
+                                             C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, C.POINTER(C.c_int64),
+                                             C.c_uint64]
+        L.go_sparse_lee_terms.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_uint64, vp]
+        L.go_sparse_lee_terms.restype = None
+        L.go_sparse_lee_val_and_grad.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, C.c_uint64, dp, vp]
+        L.go_sparse_lee_val_and_grad.restype = None
         _lib = L
     return _lib
 
@@ -419,3 +429,70 @@ class AnsatzOracle:
             raise FloatingPointError("Infinite residence time")
         return dict(addrs=addrs, val_w=val_w, grad_w=grad_w, val=val_w.mean(), grad=grad_w.mean(axis=0),
                     hops=hops.value, series_tau=st, series_eloc=se, series_addr=sa)
+
+
+class SparseOracle:
+    """The hot path over a materialised operator (oracle/gutz_oracle_sparse.c): rows = offdiagonals in reference
+    order as (col, melem), diag, and an ansatz table psi[dim] with grad_ratio[dim, P] = grad psi / psi."""
+
+    def __init__(self, row_ptr, col, melem, diag):
+        self.L = lib()
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        self.col = np.ascontiguousarray(col, dtype=np.uint32)
+        self.melem = np.ascontiguousarray(melem, dtype=np.float64)
+        self.diag = np.ascontiguousarray(diag, dtype=np.float64)
+        self.dim = self.diag.shape[0]
+        assert self.row_ptr.shape == (self.dim + 1,) and self.col.shape == self.melem.shape == (int(self.row_ptr[-1]),)
+        self.maxrow = int(np.diff(self.row_ptr.astype(np.int64)).max())
+        self.set_table(np.ones(self.dim), None)
+
+    def set_table(self, psi, grad_ratio=None):
+        self.psi = np.ascontiguousarray(psi, dtype=np.float64)
+        assert self.psi.shape == (self.dim,)
+        if grad_ratio is None:
+            self.P, self.gr = 0, np.zeros((self.dim, 0))
+        else:
+            self.gr = np.ascontiguousarray(np.asarray(grad_ratio, dtype=np.float64).reshape(self.dim, -1))
+            self.P = self.gr.shape[1]
+
+    def set_gutzwiller(self, g: float):
+        """GutzwillerAnsatz (gutzwiller.jl:25-36): psi = exp(-g D), grad psi / psi = -D"""
+        self.set_table(np.exp(-g * self.diag), -self.diag.reshape(-1, 1))
+
+    def _ops(self):
+        return (_vp(self.row_ptr), _vp(self.col), _vp(self.melem), _vp(self.diag), _vp(self.psi), _vp(self.gr), self.P)
+
+    def kinetic_sample(self, k: int, u01: float):
+        buf, gr = np.zeros(self.maxrow), np.zeros(max(self.P, 1))
+        new, tau, el, ch, nh = C.c_uint32(), C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        rc = self.L.go_sparse_kinetic_sample(*self._ops(), int(k), u01, _vp(buf), C.byref(new), C.byref(tau),
+                                             C.byref(el), _vp(gr), C.byref(ch), C.byref(nh))
+        if rc:
+            raise FloatingPointError("Infinite residence time")
+        return dict(new_index=new.value, tau=tau.value, eloc=el.value, grad=gr[:self.P].copy(), chosen=ch.value,
+                    n_hops=nh.value, cumsum=buf[:nh.value].copy())
+
+    def kinetic_vqmc(self, idx, steps: int, seed: int = 0, walker0: int = 0, step0: int = 0, series: bool = False):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).copy()
+        nw = idx.shape[0]
+        val_w, grad_w, hops = np.zeros(nw), np.zeros((nw, self.P)), C.c_int64()
+        si = np.zeros((nw, steps), dtype=np.uint32) if series else None
+        st = np.zeros((nw, steps)) if series else None
+        se = np.zeros((nw, steps)) if series else None
+        rc = self.L.go_sparse_kinetic_vqmc(*self._ops(), _vp(idx), nw, steps, seed, walker0, step0,
+                                           _vp(si) if series else None, _vp(st) if series else None,
+                                           _vp(se) if series else None, _vp(val_w), _vp(grad_w), C.byref(hops), self.dim)
+        if rc:
+            raise FloatingPointError("Infinite residence time")
+        return dict(idx=idx, val_w=val_w, grad_w=grad_w, val=val_w.mean(), grad=grad_w.mean(axis=0), hops=hops.value,
+                    series_idx=si, series_tau=st, series_eloc=se)
+
+    def lee_terms(self, k: int) -> np.ndarray:
+        out = np.zeros(2 + 2 * self.P)
+        self.L.go_sparse_lee_terms(*self._ops(), int(k), _vp(out))
+        return out
+
+    def lee_val_and_grad(self):
+        v, g = C.c_double(), np.zeros(max(self.P, 1))
+        self.L.go_sparse_lee_val_and_grad(*self._ops(), self.dim, C.byref(v), _vp(g))
+        return v.value, g[:self.P].copy()

@@ -37,7 +37,7 @@ def test_no_torch_types_in_abi():
 
 def test_version_and_error_channel(gw):
     L = gw.lib()
-    assert L.gwz_version() == 110
+    assert L.gwz_version() == 120
     import ctypes as C
     h = C.c_void_p()
     rc = L.gwz_context_create(0, None)
@@ -241,3 +241,33 @@ def test_header_is_plain_c99(tmp_path):
     src.write_text('#include "gutzwiller_b200.h"\nint main(void) { gwz_gen_result r; gwz_vqmc_result v; (void)r; (void)v; return 0; }\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
                     str(src), "-o", str(tmp_path / "c.o")], check=True)
+
+
+def test_sparse_host_objects(gw):
+    """SparseHamiltonian / tabulated ansaetze: host-side validation and tables (no device call)"""
+    import sparse_models as sm
+    rp, col, mel, diag, states = sm.hubbard_2c_lattice((1, 0, 0, 1), (1, 1, 0, 0))
+    H = gw.SparseHamiltonian(rp, col, mel, diag, addresses=states)
+    assert H.dim == 36 and H.address.index == 0 and "dim=36" in repr(H)
+    with pytest.raises(ValueError):
+        gw.SparseHamiltonian(rp[:-1], col, mel, diag)
+    with pytest.raises(ValueError):
+        gw.SparseHamiltonian(rp, col[:-1], mel, diag)
+    with pytest.raises(ValueError):
+        gw.SparseHamiltonian(rp, col, mel, diag, start=36)
+    a = gw.SparseGutzwillerAnsatz(H)
+    assert gw.num_parameters(a) == 1
+    psi, gr = a.table([0.5])
+    assert np.allclose(psi, np.exp(-0.5 * diag)) and np.array_equal(gr[:, 0], -diag)
+    v, g = a.val_and_grad(3, 0.5)
+    assert v == psi[3] and g[0] == -diag[3] * psi[3]  # gutzwiller.jl:25-33
+    va = gw.SparseVectorAnsatz(H, np.arange(36.0))
+    assert gw.num_parameters(va) == 0 and va(5) == 5.0 and va.val_and_grad(5)[1].size == 0
+    with pytest.raises(ValueError):
+        gw.SparseVectorAnsatz(H, np.ones(35))
+    with pytest.raises(TypeError):
+        gw.SparseGutzwillerAnsatz(gw.HubbardReal1D(gw.near_uniform(4, 4)))
+    ta = gw.TableAnsatz(H, lambda p: (np.exp(-p[0] * diag - p[1]), np.stack([-diag, -np.ones(36)], axis=1)), 2)
+    assert gw.num_parameters(ta) == 2 and ta.table([0.1, 0.2])[1].shape == (36, 2)
+    with pytest.raises(TypeError):  # pairs must match
+        gw.kinetic_vqmc(gw.HubbardReal1D(gw.near_uniform(4, 4)), a, 0.5)

@@ -1,0 +1,119 @@
+"""CPU tests of the stored-operator oracle (oracle/gutz_oracle_sparse.c): it must agree bit for bit with the pinned
+HubbardReal1D oracle on rows generated from it, and behave like the reference's tests demand on other operators
+(test/qmc.jl:16-50: eigenvector ansatz => E_loc == E0 and |psi|^2 sampling; test/ansatz.jl:37 Rayleigh quotient)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, SparseOracle
+import sparse_models as sm
+
+
+@pytest.fixture(scope="module")
+def real55():
+    o = Oracle(5, 5, 1.0, 0.1)  # HubbardReal1D(near_uniform(BoseFS{5,5}); t=0.1), test/qmc.jl:11
+    rp, col, mel, diag, basis = sm.hubbard_real1d(o)
+    return o, SparseOracle(rp, col, mel, diag), basis
+
+
+def test_rows_match_pinned_oracle_bitwise(real55):
+    o, so, basis = real55
+    g = 0.5
+    so.set_gutzwiller(g)
+    assert so.dim == 126 == len(basis)
+    rng = np.random.default_rng(1)
+    for k in rng.integers(0, so.dim, size=40):
+        u = float(rng.random())
+        a, b = o.kinetic_sample(basis[k], g, u), so.kinetic_sample(int(k), u)
+        # psi_l / psi_k is exp(-g D_l) / exp(-g D_k) here and exp(-g (D_l - D_k)) nowhere: same literal formula
+        assert b["n_hops"] == a["n_hops"] and b["chosen"] == a["chosen"]
+        assert np.array_equal(basis[b["new_index"]], a["new_addr"])
+        assert b["tau"] == a["tau"] and b["eloc"] == a["eloc"] and b["grad"][0] == a["grad"]
+        assert np.array_equal(so.lee_terms(int(k)), o.lee_terms(basis[k], g))
+
+
+def test_trajectories_match_pinned_oracle(real55):
+    o, so, basis = real55
+    g = 0.3
+    so.set_gutzwiller(g)
+    ref = o.kinetic_vqmc(g, np.stack([basis[0]] * 6), 300, seed=11)
+    got = so.kinetic_vqmc(np.zeros(6, dtype=np.uint32), 300, seed=11)
+    assert np.array_equal(basis[got["idx"]], ref["addrs"])
+    assert np.allclose(got["val_w"], ref["val_w"], rtol=1e-13, atol=0)
+    assert np.allclose(got["grad_w"][:, 0], ref["grad_w"], rtol=1e-11, atol=1e-13)
+    v0, g0 = o.lee_val_and_grad(basis, g, mode=1)
+    v1, g1 = so.lee_val_and_grad()
+    assert abs(v1 - v0) <= 1e-14 * abs(v0) and abs(g1[0] - g0) <= 1e-13 * abs(g0)
+
+
+def test_operators_are_hermitian_and_momentum_space_matches_real_space():
+    o = Oracle(3, 5, 2.0, 1.0)
+    rp, col, mel, diag, _ = sm.hubbard_real1d(o)
+    Hr = sm.dense(rp, col, mel, diag)
+    rpm, colm, melm, diagm, states = sm.hubbard_mom1d((3, 0, 0, 0, 0), u=2.0, t=1.0)
+    Hm = sm.dense(rpm, colm, melm, diagm)
+    rpf, colf, melf, diagf, fstates = sm.hubbard_2c_lattice((1, 0, 0, 1), (1, 1, 0, 0))
+    Hf = sm.dense(rpf, colf, melf, diagf)
+    for H in (Hr, Hm, Hf):
+        assert np.allclose(H, H.T, atol=1e-14)
+    assert len(fstates) == 36 and Hr.shape[0] == 35 and len(states) == 7  # total-momentum-0 sector of 35 states
+    assert abs(np.linalg.eigvalsh(Hm)[0] - np.linalg.eigvalsh(Hr)[0]) < 1e-12
+    # every momentum-sector eigenvalue is an eigenvalue of the full real-space operator
+    er = np.linalg.eigvalsh(Hr)
+    assert all(np.min(np.abs(er - e)) < 1e-11 for e in np.linalg.eigvalsh(Hm))
+    # the periodic 2x2 lattice lists both directions of a length-2 axis: duplicate targets inside a row
+    r0 = colf[int(rpf[0]):int(rpf[1])]
+    assert len(r0) > len(set(r0.tolist()))
+
+
+@pytest.mark.parametrize("name", ["real", "mom", "fermi"])
+def test_eigenvector_table_samples_psi_squared(name):
+    """test/qmc.jl:16-50 on the oracle: VectorAnsatz(groundstate) => E_loc = E0 at every step, and the
+    residence-time histogram converges to |psi|^2."""
+    if name == "real":
+        rp, col, mel, diag, _ = sm.hubbard_real1d(Oracle(5, 5, 1.0, 0.1))
+    elif name == "mom":
+        rp, col, mel, diag, _ = sm.hubbard_mom1d((0, 0, 0, 0, 3, 0, 0, 0, 0, 0), u=4.0)  # BoseFS(10, 5 => 3), qmc.jl:12
+    else:
+        rp, col, mel, diag, _ = sm.hubbard_2c_lattice((1, 0, 0, 1), (1, 1, 0, 0))
+    so = SparseOracle(rp, col, mel, diag)
+    w, v = np.linalg.eigh(sm.dense(rp, col, mel, diag))
+    so.set_table(v[:, 0])
+    res = so.kinetic_vqmc(np.zeros(8, dtype=np.uint32), 20000, seed=5, series=True)
+    assert np.allclose(res["series_eloc"], w[0], rtol=0, atol=1e-9 * max(1.0, abs(w[0])))
+    assert abs(res["val"] - w[0]) < 1e-10 * max(1.0, abs(w[0]))
+    hist = np.bincount(res["series_idx"].ravel(), weights=res["series_tau"].ravel(), minlength=so.dim)
+    hist /= hist.sum()
+    assert abs(np.dot(hist, v[:, 0] ** 2) / np.sqrt(np.dot(hist, hist) * np.sum(v[:, 0] ** 4)) - 1) < 2e-3
+
+
+def test_lee_matches_dense_rayleigh_quotient_and_finite_differences():
+    rp, col, mel, diag, _ = sm.hubbard_mom1d((0, 0, 0, 0, 3, 0, 0, 0, 0, 0), u=4.0)
+    so = SparseOracle(rp, col, mel, diag)
+    H = sm.dense(rp, col, mel, diag)
+
+    def rq(g):
+        psi = np.exp(-g * diag)
+        return psi @ H @ psi / (psi @ psi)
+
+    g = 0.37
+    so.set_gutzwiller(g)
+    val, grad = so.lee_val_and_grad()
+    assert abs(val - rq(g)) < 1e-13 * abs(rq(g))
+    h = 1e-6
+    assert abs(grad[0] - (rq(g + h) - rq(g - h)) / (2 * h)) < 1e-7 * max(1.0, abs(grad[0]))
+    # a P = 3 table: psi = exp(-p . f(k)) with arbitrary features
+    rng = np.random.default_rng(3)
+    F = rng.normal(size=(so.dim, 3))
+    p = np.array([0.2, -0.1, 0.05])
+
+    def rq3(p):
+        psi = np.exp(-F @ p)
+        return psi @ H @ psi / (psi @ psi)
+
+    so.set_table(np.exp(-F @ p), -F)
+    val, grad = so.lee_val_and_grad()
+    assert abs(val - rq3(p)) < 1e-13 * abs(val)
+    for i in range(3):
+        e = np.zeros(3)
+        e[i] = h
+        assert abs(grad[i] - (rq3(p + e) - rq3(p - e)) / (2 * h)) < 1e-7 * max(1.0, abs(grad[i]))
