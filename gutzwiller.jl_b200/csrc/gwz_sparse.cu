@@ -8,14 +8,16 @@
 // (column index, matrix element), diag[k] = diagonal_element, and the ansatz is a table psi[k] with
 // grad_ratio[k][p] = (d psi/d p_p)/psi (uploaded, or filled on the device for GutzwillerAnsatz, gutzwiller.jl:25-36).
 //
-// HBM layout: row_ptr u64[dim+1], col u32[nnz], melem f64[nnz], diag f64[dim], amplitudes f64[dim] (what the walkers
-// gather) and the ansatz table f64[dim][1+P] (psi, then grad_ratio: one state's data in one sector, what the
-// gradient sweep gathers);
+// HBM layout: row_ptr u64[dim+1], col u32[nnz], melem f64[nnz], rpsi f64[nnz] (the amplitude of every row entry's
+// target, gathered once per table so that a walker step STREAMS its row -- 20 B per hop, no gather), diag f64[dim],
+// amplitudes f64[dim] and the ansatz table f64[dim][1+P] (psi, then grad_ratio: one state's data in one sector, what
+// the gradient sweep gathers);
 // walkers: index u32[n], accumulators f64[4+2P][n].  One walker per GROUP of G = 4/8/16/32 lanes (G from the mean row
 // length): the lanes read a row chunk by chunk (coalesced col/melem, gathered psi), an inclusive scan inside each
 // chunk gives the reference's cumulative buffer in row order and the move is the first entry with u*S < cumsum
 // (pick_random_from_cumsum, qmc.jl:52-61); the first R chunks stay in registers for the pick, longer rows are
-// re-read.  This path is gather (L2/HBM latency) bound: 12 B of row data + one 8 B gather per hop.
+// re-read.  The walk is a chain of dependent loads (index -> row_ptr -> row): latency bound, so occupancy (64
+// registers, 8 CTAs/SM) and bytes per hop are what matter.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -34,7 +36,12 @@ struct SparseDev {
     const uint32_t* col;
     const double* melem;
     const double* diag;
-    const double* amp;  // [dim] psi_k alone: the walkers gather only amplitudes, a dense array keeps more of it in L2
+    const double* rpsi;  // [nnz] psi of each row entry's target, gathered once per table (sparse_expand_kernel): a walker
+                         // step streams (col, melem, rpsi) of its row instead of gathering an amplitude per hop
+    const double* rec;  // [dim][RS] what a walker needs of its OWN state in one aligned 64 B block (RS = 8 for P <= 4):
+                        // row begin, row end (as bits), diag, psi, grad_ratio[0..P)
+    int RS;
+    const double* amp;  // [dim] psi_k alone (the expansion and the value-only sweep gather from it)
     const double* tab;  // [dim][1 + P]: psi_k, then grad_ratio[k][0..P) -- one state's ansatz data shares a sector
     unsigned long long dim;
     int P;
@@ -86,8 +93,11 @@ struct SpStep {
 template <int G, bool RATES>
 __device__ __forceinline__ SpStep sp_step(const SparseDev& sd, uint32_t k, int lane, unsigned mask, double u01,
                                           double* rates /* RATES: |psi_l / psi_k| in row order */) {
-    const unsigned long long b = sd.row_ptr[k], e = sd.row_ptr[k + 1];
-    const double v1 = sd.psi(k);
+    const double* rec = sd.rec + (size_t)k * sd.RS;
+    const ulonglong2 be = *reinterpret_cast<const ulonglong2*>(rec);
+    const double2 dv = *reinterpret_cast<const double2*>(rec + 2);
+    const unsigned long long b = be.x, e = be.y;
+    const double v1 = dv.y;
     double num_l = 0.0, base = 0.0;
     double cc[SP_R];
     uint32_t cn[SP_R];
@@ -100,7 +110,7 @@ __device__ __forceinline__ SpStep sp_step(const SparseDev& sd, uint32_t k, int l
             double r = 0.0;
             if (i < e) {
                 cn[c] = sd.col[i];
-                const double v2 = sd.psi(cn[c]);
+                const double v2 = sd.rpsi[i];
                 r = fabs(v2);                       // qmc.jl:27
                 num_l = fma(sd.melem[i], v2, num_l);  // qmc.jl:28
                 if (RATES) rates[i - b] = r / fabs(v1);
@@ -115,7 +125,7 @@ __device__ __forceinline__ SpStep sp_step(const SparseDev& sd, uint32_t k, int l
         const unsigned long long i = i0 + lane;
         double r = 0.0;
         if (i < e) {
-            const double v2 = sd.psi(sd.col[i]);
+            const double v2 = sd.rpsi[i];
             r = fabs(v2);
             num_l = fma(sd.melem[i], v2, num_l);
             if (RATES) rates[i - b] = r / fabs(v1);
@@ -126,7 +136,7 @@ __device__ __forceinline__ SpStep sp_step(const SparseDev& sd, uint32_t k, int l
     SpStep o;
     o.S = base;
     o.tau = fabs(v1) / base;                                        // qmc.jl:33
-    o.eloc = (sd.diag[k] * v1 + sp_sum<G>(num_l, mask)) / v1;        // qmc.jl:21,37
+    o.eloc = (dv.x * v1 + sp_sum<G>(num_l, mask)) / v1;              // qmc.jl:21,37
     o.nhops = (int)(e - b);
     o.chosen = -1;
     o.next = k;
@@ -152,7 +162,7 @@ __device__ __forceinline__ SpStep sp_step(const SparseDev& sd, uint32_t k, int l
             uint32_t cl = 0u;
             if (i < e) {
                 cl = sd.col[i];
-                r = fabs(sd.psi(cl));
+                r = fabs(sd.rpsi[i]);
             }
             const double sc = sp_scan<G>(r, lane, mask);
             const unsigned hit = __ballot_sync(mask, T < run + sc) & mask;
@@ -234,7 +244,7 @@ sparse_walker_kernel(const __grid_constant__ SparseDev sd, const __grid_constant
             for (int q = 0; q < PPL; ++q) {
                 const int p = lane + G * q;
                 if (p < P) {
-                    const double g = sd.gratio(k, p);  // qmc.jl:38
+                    const double g = sd.rec[(size_t)k * sd.RS + 4 + p];  // qmc.jl:38
                     sg[q] = fma(o.tau, g, sg[q]);
                     sge[q] = fma(tE, g, sge[q]);
                 }
@@ -446,6 +456,29 @@ __global__ void sparse_fill_gutzwiller_kernel(const double* __restrict__ diag, u
     }
 }
 
+// rpsi[i] = psi[col[i]]: one gather per stored entry and table, instead of one per hop of every walker step
+__global__ void sparse_expand_kernel(const uint32_t* __restrict__ col, const double* __restrict__ amp,
+                                     unsigned long long nnz, double* __restrict__ rpsi) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        rpsi[i] = amp[col[i]];
+}
+
+// the walkers' per-state record (see SparseDev::rec)
+__global__ void sparse_build_rec_kernel(const unsigned long long* __restrict__ row_ptr, const double* __restrict__ diag,
+                                        const double* __restrict__ amp, const double* __restrict__ tab, int P, int RS,
+                                        unsigned long long dim, double* __restrict__ rec) {
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < dim;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        double* r = rec + k * (unsigned)RS;
+        r[0] = __longlong_as_double((long long)row_ptr[k]);
+        r[1] = __longlong_as_double((long long)row_ptr[k + 1]);
+        r[2] = diag[k];
+        r[3] = amp[k];
+        for (int p = 0; p < P; ++p) r[4 + p] = tab[k * (unsigned)(1 + P) + 1 + p];
+    }
+}
+
 __global__ void sparse_fill_idx_kernel(uint32_t* idx, size_t n, uint32_t v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) idx[i] = v;
 }
@@ -464,6 +497,9 @@ struct gwz_sparse {
     uint32_t* d_col = nullptr;
     double* d_melem = nullptr;
     double* d_diag = nullptr;
+    double* d_rpsi = nullptr;  // [nnz]
+    double* d_rec = nullptr;   // [dim][RS]
+    size_t rec_cap = 0;
     double* d_amp = nullptr;  // [dim]
     double* d_tab = nullptr;  // [dim][1 + P]
     size_t tab_cap = 0;
@@ -532,6 +568,8 @@ extern "C" int gwz_sparse_destroy(gwz_sparse* h) {
         cudaFree(h->d_melem);
         cudaFree(h->d_diag);
         cudaFree(h->d_amp);
+        cudaFree(h->d_rpsi);
+        cudaFree(h->d_rec);
         cudaFree(h->d_tab);
         cudaFree(h->d_partials);
     }
@@ -581,6 +619,8 @@ extern "C" int gwz_sparse_create(gwz_context* ctx, uint64_t dim, const uint64_t*
     h->sd.diag = h->d_diag;
     GWZ_CUDA(cudaMalloc(&h->d_amp, sizeof(double) * dim));
     h->sd.amp = h->d_amp;
+    GWZ_CUDA(cudaMalloc(&h->d_rpsi, sizeof(double) * (nnz ? nnz : 1)));
+    h->sd.rpsi = h->d_rpsi;
     h->sd.tab = nullptr;
     h->sd.dim = dim;
     h->sd.P = 0;
@@ -610,10 +650,35 @@ static int sp_reserve_table(gwz_sparse* h, int P) {
         GWZ_CUDA(cudaMalloc(&h->d_tab, sizeof(double) * need));
         h->tab_cap = need;
     }
+    const int RS = (4 + P + 3) / 4 * 4 <= 8 ? 8 : (4 + P + 3) / 4 * 4;  // whole 32 B sectors; one 64 B block for P <= 4
+    if ((size_t)h->dim * RS > h->rec_cap) {
+        if (h->d_rec) cudaFree(h->d_rec);
+        h->d_rec = nullptr;
+        h->rec_cap = 0;
+        GWZ_CUDA(cudaMalloc(&h->d_rec, sizeof(double) * h->dim * RS));
+        h->rec_cap = (size_t)h->dim * RS;
+    }
+    h->sd.rec = h->d_rec;
+    h->sd.RS = RS;
     h->P = P;
     h->sd.P = P;
     h->sd.tab = h->d_tab;
     h->G = sp_group(h->G_base, P);
+    return GWZ_OK;
+}
+
+static int sp_expand(gwz_sparse* h) {
+    gwz_context* c = h->ctx;
+    const unsigned rgrid = (unsigned)std::min<uint64_t>((h->dim + 255) / 256, (uint64_t)c->prop.multiProcessorCount * 16);
+    api_count_launch();
+    sparse_build_rec_kernel<<<rgrid, 256, 0, c->stream>>>(h->d_row_ptr, h->d_diag, h->d_amp, h->d_tab, h->P, h->sd.RS, h->dim,
+                                                          h->d_rec);
+    GWZ_CUDA(cudaGetLastError());
+    if (h->nnz == 0) return GWZ_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((h->nnz + 255) / 256, (uint64_t)c->prop.multiProcessorCount * 16);
+    api_count_launch();
+    sparse_expand_kernel<<<grid, 256, 0, c->stream>>>(h->d_col, h->d_amp, h->nnz, h->d_rpsi);
+    GWZ_CUDA(cudaGetLastError());
     return GWZ_OK;
 }
 
@@ -636,6 +701,7 @@ extern "C" int gwz_sparse_set_table(gwz_sparse* h, const double* psi, const doub
     }
     GWZ_CUDA(cudaMemcpyAsync(h->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, c->stream));
     GWZ_CUDA(cudaMemcpyAsync(h->d_amp, psi, sizeof(double) * h->dim, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = sp_expand(h)) return rc;
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     ++h->table_version;
     return GWZ_OK;
@@ -651,6 +717,7 @@ extern "C" int gwz_sparse_set_gutzwiller(gwz_sparse* h, double g) {
     api_count_launch();
     sparse_fill_gutzwiller_kernel<<<grid, 256, 0, c->stream>>>(h->d_diag, h->dim, g, h->d_amp, reinterpret_cast<double2*>(h->d_tab));
     GWZ_CUDA(cudaGetLastError());
+    if (int rc = sp_expand(h)) return rc;
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     ++h->table_version;
     return GWZ_OK;

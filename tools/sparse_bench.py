@@ -3,7 +3,7 @@
     python tools/sparse_bench.py [--out gpurun_out/sparse_bench.json]
 
 Rows of fixed length L with uniformly random targets: the gather pattern of a large unstructured basis.  Reports
-walker-steps/s, hops/s and the algorithmic bytes moved (12 B of row data + one 8 B amplitude gather per hop) against
+walker-steps/s, hops/s and the algorithmic bytes moved (20 B of row data per hop: column, matrix element, expanded amplitude) against
 the measured HBM peak when the operator does not fit in L2."""
 import argparse
 import json
@@ -72,7 +72,7 @@ def main():
             print(json.dumps({k: (float(f"{v:.4g}") if isinstance(v, float) else v) for k, v in row.items()}), flush=True)
             rows.append(row)
             del ws, le, H, ans, h
-    out = dict(rows=rows, peaks=peaks, note="algorithmic bytes: walker 12 B row data + 8 B gather per hop; sweep "
+    out = dict(rows=rows, peaks=peaks, note="algorithmic bytes: walker 20 B row data per hop (col, melem, expanded amplitude); sweep "
                "val_and_grad P=1: 12 B row data + two 8 B gathers per entry")
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
