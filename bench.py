@@ -351,6 +351,20 @@ def extra_workloads(gw, np):
     out["generic_relative_jastrow_bose50_2^16walkers_64steps"] = {
         "walker_steps_per_s": q.steps * q.walkers / dt, "ms_per_call": dt * 1e3, "kernel_ms": q.result.last.kernel_ms,
         "parameters": ans.N_PARAMS}
+    # stored-operator path: synthetic operator, dim 1e6 x 16 entries per row, GutzwillerAnsatz table
+    rng = np.random.default_rng(0)
+    dim, L = 1_000_000, 16
+    Hs = gw.SparseHamiltonian(np.arange(dim + 1, dtype=np.uint64) * np.uint64(L),
+                              rng.integers(0, dim, size=dim * L, dtype=np.uint32), -rng.random(dim * L), rng.normal(size=dim))
+    q = gw.KineticVQMC(Hs, gw.SparseGutzwillerAnsatz(Hs), walkers=1 << 18, steps=200, record=False)
+    for _ in range(3):
+        gw.val_and_grad(q, 0.1)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        gw.val_and_grad(q, 0.1)
+    dt = (time.perf_counter() - t0) / 5
+    out["stored_operator_dim1e6_16perrow_2^18walkers_200steps"] = {
+        "walker_steps_per_s": q.steps * q.walkers / dt, "ms_per_call": dt * 1e3, "kernel_ms": q.result.last.kernel_ms}
     return out
 
 

@@ -63,6 +63,34 @@ def check_generic(rank, world):
     print(f"[rank {rank}/{world}] generic OK val={r.val:.12f} grad0={r.grad[0]:.9f} sweep={v:.12f}", flush=True)
 
 
+def check_sparse(rank, world):
+    """The stored-operator path under the same sharding: walkers by global id, sweep by row range."""
+    import sparse_models as sm
+    op = sm.hubbard_mom1d((0, 0, 0, 0, 3, 0, 0, 0, 0, 0), u=4.0)[:4]
+    Hs = gw.SparseHamiltonian(*op)
+    ans = gw.SparseGutzwillerAnsatz(Hs)
+    total, steps = 1 << 12, 100
+    res = gw.kinetic_vqmc(Hs, ans, [0.3], walkers=total, steps=steps, seed=5, record=False)
+    ctx = gw.Context(int(os.environ.get("LOCAL_RANK", "0")))  # fresh context without communicator
+    w = gw.SparseWalkers(Hs.handle(ctx), ans, total, 0, seed=5)
+    ref = w.run([0.3], steps)
+    r = res.last
+    assert r.walkers == total and r.steps == total * steps and r.hops == ref.hops, (r.walkers, r.steps, r.hops, ref.hops)
+    assert abs(r.val - ref.val) <= 1e-12 * abs(ref.val) and abs(r.pooled_val - ref.pooled_val) <= 1e-12 * abs(ref.pooled_val)
+    assert np.all(np.abs(r.grad - ref.grad) <= 1e-9 * np.abs(ref.grad).max())
+    begin, end = gw.shard_range(total, world, rank)
+    assert np.array_equal(res.walkers_handle.indices(), w.indices()[begin:end])  # same trajectories as unsharded
+    big = sm.random_operator(5000, 12, seed=3)
+    Hb = gw.SparseHamiltonian(*big)
+    ab = gw.SparseGutzwillerAnsatz(Hb)
+    v, g = gw.LocalEnergyEvaluator(Hb, ab).val_and_grad(0.2)             # row shards + all-reduce
+    v1, g1 = gw.LocalEnergyEvaluator(Hb, ab, ctx=ctx).val_and_grad(0.2)  # one device, all rows
+    assert abs(v - v1) <= 1e-12 * abs(v1) and np.all(np.abs(g - g1) <= 1e-11 * max(1.0, np.abs(g1).max()))
+    hist, _ = res.walkers_handle.sample_vector([0.3], 50)  # all-reduced residence-time histogram
+    assert abs(hist.sum() - _.total_time) <= 1e-9 * _.total_time and _.walkers == total
+    print(f"[rank {rank}/{world}] stored operator OK val={r.val:.12f} grad0={r.grad[0]:.9f} sweep={v:.12f}", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--single-process", type=int, default=0)
@@ -89,6 +117,7 @@ def main():
     ref, ref_acc = reference_single_gpu(int(os.environ.get("LOCAL_RANK", "0")))
     check(res.last, ref, acc, ref_acc, f"rank {rank}/{world}")
     check_generic(rank, world)
+    check_sparse(rank, world)
     import torch.distributed as dist
     dist.barrier()
     dist.destroy_process_group()
