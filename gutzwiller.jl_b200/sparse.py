@@ -13,6 +13,7 @@ csrc/gwz_sparse.cu behind the ``gwz_sparse_*`` / ``gwz_swalkers_*`` C ABI.
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import weakref
 
 import numpy as np
@@ -25,6 +26,9 @@ from .runtime import Context, default_context
 
 def _vp(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+_ansatz_tokens = itertools.count(1)  # identity of an ansatz object for the table cache (id() values are reused)
 
 
 class _SparseHandle:
@@ -72,7 +76,7 @@ class _SparseHandle:
     def load(self, ansatz, params) -> None:
         """make the device table that of ansatz(., params) (cached: the same (ansatz, params) is not re-uploaded)"""
         p = as_params(params if np.size(params) else np.zeros(0), ansatz.N_PARAMS)
-        key = (id(ansatz), p.tobytes())
+        key = (ansatz._token, p.tobytes())
         if self.loaded == key:
             return
         ansatz._load(self, p)
@@ -127,7 +131,7 @@ class SparseHamiltonian:
     ``row_ptr[dim + 1]``, ``col[nnz]``, ``melem[nnz]``: row k = ``offdiagonals(H, basis[k])`` in the reference's
     order; ``diag[dim]`` = ``diagonal_element(H, basis[k])``; ``addresses`` (optional) = ``build_basis(H)`` for
     reporting; ``start`` = index of ``starting_address(H)`` (0 for a breadth-first ``build_basis``).
-    The Julia shim builds these arrays from any Rimu Hamiltonian (julia/GutzwillerB200.jl, ``SparseHamiltonian(H)``)."""
+    The Julia shim builds these arrays from any Rimu Hamiltonian (julia/GutzwillerB200.jl, ``GPUSparseHamiltonian(H)``)."""
 
     sparse_operator = True
 
@@ -171,6 +175,7 @@ class SparseAnsatz(AbstractAnsatz):
         if not getattr(hamiltonian, "sparse_operator", False):
             raise TypeError("a SparseHamiltonian is required")
         self.hamiltonian = hamiltonian
+        self._token = next(_ansatz_tokens)
 
     def table(self, params):
         raise NotImplementedError
