@@ -119,6 +119,26 @@ def test_trajectories_match_oracle_step_for_step(gw, ops, name):
     assert np.array_equal(ws.indices(), ref2["idx"])
 
 
+@pytest.mark.parametrize("P", [2, 7, 20, 70])
+def test_many_parameter_tables_follow_the_oracle(gw, ops, P):
+    """gradient accumulators for P parameters (several per lane; the lane group widens when P > 8 per lane)"""
+    H, so = _pair(gw, ops["real"])
+    psi, gr = _random_table(H.dim, P, 21 + P)
+    psi = np.abs(psi) + 0.1
+    ans = gw.TableAnsatz(H, lambda p: (psi, gr), P)
+    so.set_table(psi, gr)
+    ws = gw.SparseWalkers(H.handle(), ans, 40, 0, seed=13)
+    r = ws.run(np.zeros(P), 300)
+    assert H.handle().info()["lanes_per_walker"] * 8 >= P
+    ref = so.kinetic_vqmc(np.zeros(40, dtype=np.uint32), 300, seed=13)
+    assert np.array_equal(ws.indices(), ref["idx"])
+    vw, gw_ = ws.estimates()
+    assert np.allclose(vw, ref["val_w"], rtol=1e-10, atol=1e-12)
+    assert gw_.shape == (40, P) and np.allclose(gw_, ref["grad_w"], rtol=1e-7, atol=1e-9)
+    assert np.allclose(r.grad, ref["grad"], rtol=1e-7, atol=1e-9)
+    assert np.all(r.grad_err > 0) and np.allclose(r.pooled_grad, r.pooled_grad)
+
+
 def test_shards_reproduce_the_unsharded_walk(gw, ops):
     H, _ = _pair(gw, ops["mom"])
     ans = gw.SparseGutzwillerAnsatz(H)
