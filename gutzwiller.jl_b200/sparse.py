@@ -151,6 +151,58 @@ class SparseHamiltonian:
         self.address = _IndexAddress(start)
         self._handles = {}
 
+    @classmethod
+    def from_hubbard(cls, H, max_dim: int = 5_000_000) -> "SparseHamiltonian":
+        """Materialise ``HubbardReal1D`` / ``ExtendedHubbardReal1D`` over ALL C(N+M-1, N) Fock states (host-side
+        numpy): what ``build_basis`` + ``offdiagonals`` + ``diagonal_element`` give, rows in
+        the reference's hop order (occupied modes ascending, right hop then left hop).  Basis index = colex rank of
+        the unary bitstring, i.e. the order of the ranked ``LocalEnergyEvaluator`` sweep; ``addresses`` holds the
+        occupation numbers.  This is the route for a user-defined ansatz on the chain: tabulate it over
+        ``Hs.addresses`` (:class:`TableAnsatz`) and every call form works unchanged."""
+        from math import comb
+        N, M = H.address.N, H.address.M
+        dim = comb(N + M - 1, N)
+        if dim > max_dim:
+            raise ValueError(f"BoseFS{{{N},{M}}} has {dim} states: too many to store (max_dim={max_dim})")
+        B = N + M - 1
+        binom = np.array([[comb(p, i) for i in range(N + 1)] for p in range(B + 1)], dtype=np.int64)
+
+        def rank(onr):  # colex rank of the positions of the ones: boson j (sorted by mode) sits at bit mode_j + j
+            modes = np.repeat(np.tile(np.arange(M), onr.shape[0]), onr.ravel()).reshape(onr.shape[0], N)
+            return binom[modes + np.arange(N), np.arange(1, N + 1)].sum(axis=1)
+
+        # all compositions of N into M parts, then sorted by rank
+        onr = np.zeros((1, M), dtype=np.int64)
+        onr[0, 0] = N
+        parts = [np.array([[n]], dtype=np.int64) for n in range(N + 1)]  # compositions of n into 1 part
+        for _ in range(M - 1):
+            nxt = []
+            for n in range(N + 1):
+                nxt.append(np.concatenate([np.hstack([parts[n - k], np.full((parts[n - k].shape[0], 1), k)])
+                                           for k in range(n + 1)]))
+            parts = nxt
+        onr = parts[N]
+        order = np.argsort(rank(onr), kind="stable")
+        onr = np.ascontiguousarray(onr[order])
+        assert onr.shape[0] == dim and np.array_equal(rank(onr), np.arange(dim))
+        u, t, v = float(H.u), float(H.t), float(getattr(H, "v", 0.0))
+        diag = 0.5 * u * (onr * (onr - 1)).sum(axis=1) + v * (onr * np.roll(onr, -1, axis=1)).sum(axis=1)
+        target = np.zeros((dim, M, 2), dtype=np.int64)
+        melem = np.zeros((dim, M, 2))
+        for i in range(M):
+            for d, j in ((0, (i + 1) % M), (1, (i - 1) % M)):  # right hop, then left hop (App. A.4)
+                src = np.flatnonzero(onr[:, i] > 0)
+                new = onr[src].copy()
+                melem[src, i, d] = -t * np.sqrt(new[:, i] * (new[:, j] + 1.0))
+                new[:, i] -= 1
+                new[:, j] += 1
+                target[src, i, d] = rank(new)
+        valid = np.repeat((onr > 0)[:, :, None], 2, axis=2)
+        row_ptr = np.zeros(dim + 1, dtype=np.uint64)
+        row_ptr[1:] = np.cumsum(2 * (onr > 0).sum(axis=1))
+        start = int(rank(np.array([H.address.onr()], dtype=np.int64))[0])
+        return cls(row_ptr, target[valid].astype(np.uint32), melem[valid], diag, addresses=onr, start=start)
+
     def handle(self, ctx: Context | None = None) -> _SparseHandle:
         ctx = ctx or default_context()
         h = self._handles.get(id(ctx))

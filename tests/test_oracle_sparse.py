@@ -117,3 +117,27 @@ def test_lee_matches_dense_rayleigh_quotient_and_finite_differences():
         e = np.zeros(3)
         e[i] = h
         assert abs(grad[i] - (rq3(p + e) - rq3(p - e)) / (2 * h)) < 1e-7 * max(1.0, abs(grad[i]))
+
+
+def test_from_hubbard_reproduces_the_reference_rows(gw):
+    """SparseHamiltonian.from_hubbard (host numpy) against the pinned oracle's build_basis / offdiagonals /
+    diagonal_element: same rows in the same hop order, basis index = colex rank of the unary bitstring"""
+    for (N, M, u, t) in ((5, 5, 1.0, 0.1), (3, 6, 2.0, 1.0), (7, 4, 4.0, 0.5)):
+        o = Oracle(N, M, u, t)
+        rp, col, mel, diag, basis = sm.hubbard_real1d(o)
+        H = gw.HubbardReal1D(gw.BoseFS(o.to_onr(basis[0])), u=u, t=t)
+        Hs = gw.SparseHamiltonian.from_hubbard(H)
+        assert Hs.dim == len(basis) == o.dimension()
+        index = {tuple(r): i for i, r in enumerate(Hs.addresses.tolist())}
+        idx = np.array([index[tuple(o.to_onr(b))] for b in basis])
+        assert idx[0] == Hs.address.index
+        rpi, rps = rp.astype(np.int64), Hs.row_ptr.astype(np.int64)
+        for k in range(len(basis)):
+            a, b = slice(rpi[k], rpi[k + 1]), slice(rps[idx[k]], rps[idx[k] + 1])
+            assert np.array_equal(idx[col[a]], Hs.col[b]) and np.array_equal(mel[a], Hs.melem[b])
+            assert diag[k] == Hs.diag[idx[k]]
+        # index = rank of the bitstring among all N-subsets of N+M-1 bit positions (colex)
+        words = np.array([int(gw.BoseFS(r).words[0]) for r in Hs.addresses.tolist()], dtype=np.uint64)
+        assert np.all(np.diff(words.astype(np.int64)) > 0)
+    with pytest.raises(ValueError, match="too many"):
+        gw.SparseHamiltonian.from_hubbard(gw.HubbardReal1D(gw.near_uniform(20, 20)))
