@@ -178,7 +178,18 @@ def _gloo_worker(rank, world, port, q):
     # the accumulator vector the GPU path all-reduces (walkers, sum val_w, sum grad_w)
     acc = torch.tensor([e - b, out["val_w"].sum(), out["grad_w"].sum()], dtype=torch.float64)
     dist.all_reduce(acc)
-    q.put((rank, acc.tolist()))
+    # the stored-operator path shards the same way: walkers by global id, sweep rows by range
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sparse_models as sm
+    from oracle.oracle import SparseOracle
+    so = SparseOracle(*sm.hubbard_mom1d((0, 0, 3, 0, 0, 0), u=4.0)[:4])
+    so.set_gutzwiller(0.3)
+    outs = so.kinetic_vqmc(np.zeros(e - b, dtype=np.uint32), steps, seed=7, walker0=b)
+    r0, r1 = gw.shard_range(so.dim, world, rank)
+    terms = np.sum([so.lee_terms(k) for k in range(r0, r1)], axis=0)
+    acc2 = torch.tensor([outs["val_w"].sum(), outs["grad_w"].sum(), *terms], dtype=torch.float64)
+    dist.all_reduce(acc2)
+    q.put((rank, acc.tolist() + acc2.tolist()))
     dist.destroy_process_group()
 
 
@@ -201,6 +212,15 @@ def test_sharding_is_invariant_under_world_size_gloo(oracle_mod):
     for _, acc in res:
         assert acc[0] == 10
         assert abs(acc[1] / 10 - single["val"]) < 1e-12 and abs(acc[2] / 10 - single["grad"]) < 1e-11
+    import sparse_models as sm
+    so = oracle_mod.SparseOracle(*sm.hubbard_mom1d((0, 0, 3, 0, 0, 0), u=4.0)[:4])
+    so.set_gutzwiller(0.3)
+    one = so.kinetic_vqmc(np.zeros(10, dtype=np.uint32), 300, seed=7)
+    v, g = so.lee_val_and_grad()
+    for _, acc in res:
+        assert abs(acc[3] / 10 - one["val"]) < 1e-12 * abs(one["val"]) and abs(acc[4] / 10 - one["grad"][0]) < 1e-11
+        num, den, ng, dg = acc[5:9]
+        assert abs(num / den - v) < 1e-12 * abs(v) and abs((ng * den - num * dg) / den ** 2 - g[0]) < 1e-11
 
 
 def test_generic_ansatz_host_objects(gw):
