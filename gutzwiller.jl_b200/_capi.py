@@ -172,6 +172,7 @@ SIGNATURES = {
     "gwz_sparse_destroy": (C.c_int, [_vp]),
     "gwz_sparse_info": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gwz_sparse_layout": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "gwz_sparse_set_table": (C.c_int, [_vp, _vp, _vp, C.c_int32]),
     "gwz_sparse_set_gutzwiller": (C.c_int, [_vp, C.c_double]),
     "gwz_sparse_get_table": (C.c_int, [_vp, _vp, _vp]),

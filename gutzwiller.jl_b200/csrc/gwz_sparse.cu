@@ -41,6 +41,11 @@ struct SparseDev {
     const double* rec;  // [dim][RS] what a walker needs of its OWN state in one aligned 64 B block (RS = 8 for P <= 4):
                         // row begin, row end (as bits), diag, psi, grad_ratio[0..P)
     int RS;
+    const double* blk;  // [dim][BS] row BLOCKS (null: rows too ragged to store at a fixed stride): per state one 128 B
+                        // aligned block = head (row length, diag, psi, grad_ratio[0..min(P,5))) + the row in chunks of G
+                        // entries (col u32[G], melem[G], rpsi[G]), zero padded.  Block address = k * BS: a walker
+                        // step is ONE dependent HBM access (index -> block) instead of index -> record -> row.
+    int BS;
     const double* amp;  // [dim] psi_k alone (the expansion and the value-only sweep gather from it)
     const double* tab;  // [dim][1 + P]: psi_k, then grad_ratio[k][0..P) -- one state's ansatz data shares a sector
     unsigned long long dim;
@@ -178,10 +183,97 @@ __device__ __forceinline__ SpStep sp_step(const SparseDev& sd, uint32_t k, int l
     return o;
 }
 
+// doubles per chunk of G row entries in a block: col u32[G] | melem[G] | rpsi[G]
+__host__ __device__ constexpr int sp_chunk_doubles(int G) { return G / 2 + 2 * G; }
+constexpr int SP_HEAD = 8;  // doubles in the head of a block
+
+// kinetic_sample! at index k from the row block (same arithmetic, same order as sp_step)
+template <int G, bool RATES>
+__device__ __forceinline__ SpStep sp_step_blk(const SparseDev& sd, uint32_t k, int lane, unsigned mask, double u01,
+                                              double* rates) {
+    constexpr int CH = sp_chunk_doubles(G);
+    const double* blk = sd.blk + (size_t)k * sd.BS;
+    // the head and the first SP_R chunks are loaded together: none of their addresses depends on the row length
+    // (blocks hold at least SP_R chunks; entries past the row end are zeros: rate 0, never picked)
+    const double2 h01 = *reinterpret_cast<const double2*>(blk);
+    const double v1 = blk[2];
+    double cc[SP_R], rr[SP_R], mm[SP_R];
+    uint32_t cn[SP_R];
+#pragma unroll
+    for (int c = 0; c < SP_R; ++c) {
+        const double* ch = blk + SP_HEAD + c * CH;
+        cn[c] = reinterpret_cast<const uint32_t*>(ch)[lane];
+        mm[c] = ch[G / 2 + lane];
+        rr[c] = ch[G / 2 + G + lane];
+    }
+    const int len = (int)__double_as_longlong(h01.x);
+    double num_l = 0.0, base = 0.0;
+#pragma unroll
+    for (int c = 0; c < SP_R; ++c) {
+        cc[c] = 0.0;
+        if (c * G < len) {  // uniform in the group
+            const double r = fabs(rr[c]);                // qmc.jl:27
+            num_l = fma(mm[c], rr[c], num_l);            // qmc.jl:28
+            if (RATES && c * G + lane < len) rates[c * G + lane] = r / fabs(v1);
+            const double sc = sp_scan<G>(r, lane, mask);
+            cc[c] = base + sc;  // qmc.jl:30
+            base += __shfl_sync(mask, sc, G - 1, G);
+        }
+    }
+    const double baseR = base;
+    for (int j0 = SP_R * G; j0 < len; j0 += G) {
+        const double* ch = blk + SP_HEAD + (j0 / G) * CH;
+        const double v2 = ch[G / 2 + G + lane];
+        const double r = fabs(v2);
+        num_l = fma(ch[G / 2 + lane], v2, num_l);
+        if (RATES && j0 + lane < len) rates[j0 + lane] = r / fabs(v1);
+        const double sc = sp_scan<G>(r, lane, mask);
+        base += __shfl_sync(mask, sc, G - 1, G);
+    }
+    SpStep o;
+    o.S = base;
+    o.tau = fabs(v1) / base;                                  // qmc.jl:33
+    o.eloc = (h01.y * v1 + sp_sum<G>(num_l, mask)) / v1;      // qmc.jl:21,37
+    o.nhops = len;
+    o.chosen = -1;
+    o.next = k;
+    const double T = u01 * base;  // pick_random_from_cumsum (qmc.jl:52-61)
+    bool found = false;
+#pragma unroll
+    for (int c = 0; c < SP_R; ++c) {
+        if (!found && c * G < len) {
+            const unsigned hit = __ballot_sync(mask, T < cc[c]) & mask;
+            if (hit) {
+                const int src = (__ffs(hit) - 1) & (G - 1);
+                o.next = __shfl_sync(mask, cn[c], src, G);
+                o.chosen = c * G + src;
+                found = true;
+            }
+        }
+    }
+    if (!found) {
+        double run = baseR;
+        for (int j0 = SP_R * G; j0 < len; j0 += G) {
+            const double* ch = blk + SP_HEAD + (j0 / G) * CH;
+            const uint32_t cl = reinterpret_cast<const uint32_t*>(ch)[lane];
+            const double sc = sp_scan<G>(fabs(ch[G / 2 + G + lane]), lane, mask);
+            const unsigned hit = __ballot_sync(mask, T < run + sc) & mask;
+            if (hit) {
+                const int src = (__ffs(hit) - 1) & (G - 1);
+                o.next = __shfl_sync(mask, cl, src, G);
+                o.chosen = j0 + src;
+                break;
+            }
+            run += __shfl_sync(mask, sc, G - 1, G);
+        }
+    }
+    return o;
+}
+
 // accumulator rows per walker: 0 sum tau, 1 sum tau dE, 2 sum tau dE^2, 3 hops, 4+p sum tau G_p, 4+P+p sum tau G_p dE
 __host__ __device__ inline int sp_acc_rows(int P) { return 4 + 2 * P; }
 
-template <int G, int PPL>
+template <int G, int PPL, bool BLK>
 __global__ void __launch_bounds__(SP_BLOCK, PPL == 1 ? GWZ_SP_MINB : (PPL == 2 ? (GWZ_SP_MINB < 6 ? GWZ_SP_MINB : 6) : 1))
 sparse_walker_kernel(const __grid_constant__ SparseDev sd, const __grid_constant__ PhiloxKeys pk, uint32_t* __restrict__ idx,
                      double* __restrict__ acc, size_t n, uint64_t goff, uint64_t step0, uint64_t steps, int accumulate,
@@ -222,7 +314,8 @@ sparse_walker_kernel(const __grid_constant__ SparseDev sd, const __grid_constant
                 philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
             }
             const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
-            const SpStep o = sp_step<G, false>(sd, k, lane, mask, u01, nullptr);
+            const SpStep o = BLK ? sp_step_blk<G, false>(sd, k, lane, mask, u01, nullptr)
+                                 : sp_step<G, false>(sd, k, lane, mask, u01, nullptr);
             if (o.chosen < 0 || !(o.tau < 1.0e300)) {  // qmc.jl:34-36
                 bad = true;
                 break;
@@ -244,7 +337,8 @@ sparse_walker_kernel(const __grid_constant__ SparseDev sd, const __grid_constant
             for (int q = 0; q < PPL; ++q) {
                 const int p = lane + G * q;
                 if (p < P) {
-                    const double g = sd.rec[(size_t)k * sd.RS + 4 + p];  // qmc.jl:38
+                    // qmc.jl:38; the block head holds the first five ratios (same 128 B line as the row's start)
+                    const double g = (BLK && P <= 5) ? sd.blk[(size_t)k * sd.BS + 3 + p] : sd.rec[(size_t)k * sd.RS + 4 + p];
                     sg[q] = fma(o.tau, g, sg[q]);
                     sge[q] = fma(tE, g, sge[q]);
                 }
@@ -417,7 +511,7 @@ sparse_sweep_kernel(const __grid_constant__ SparseDev sd, unsigned long long row
 }
 
 // per-index kinetic_sample! outputs (parity surface)
-template <int G>
+template <int G, bool BLK>
 __global__ void __launch_bounds__(SP_BLOCK)
 sparse_probe_kernel(const __grid_constant__ SparseDev sd, const uint32_t* __restrict__ idx, size_t n,
                     const double* __restrict__ u01, double* __restrict__ e_loc, double* __restrict__ tau,
@@ -430,8 +524,10 @@ sparse_probe_kernel(const __grid_constant__ SparseDev sd, const uint32_t* __rest
     for (size_t i = group; i < n; i += ngroups) {
         const uint32_t k = idx[i];
         const double u = u01 ? u01[i] : 0.5;
-        const SpStep o = rates ? sp_step<G, true>(sd, k, lane, mask, u, rates + i * rates_stride)
-                               : sp_step<G, false>(sd, k, lane, mask, u, nullptr);
+        const SpStep o = BLK ? (rates ? sp_step_blk<G, true>(sd, k, lane, mask, u, rates + i * rates_stride)
+                                      : sp_step_blk<G, false>(sd, k, lane, mask, u, nullptr))
+                             : (rates ? sp_step<G, true>(sd, k, lane, mask, u, rates + i * rates_stride)
+                                      : sp_step<G, false>(sd, k, lane, mask, u, nullptr));
         if (o.chosen < 0 && lane == 0) atomicOr(err_flag, 1);
         if (lane == 0) {
             if (e_loc) e_loc[i] = o.eloc;
@@ -479,6 +575,30 @@ __global__ void sparse_build_rec_kernel(const unsigned long long* __restrict__ r
     }
 }
 
+// row blocks (see SparseDev::blk): one thread per state copies its row; the block memory was zeroed before
+template <int G>
+__global__ void sparse_fill_blocks_kernel(const __grid_constant__ SparseDev sd, double* __restrict__ blk) {
+    constexpr int CH = sp_chunk_doubles(G);
+    const int P = sd.P;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < sd.dim;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        double* b = blk + k * (unsigned)sd.BS;
+        const unsigned long long r0 = sd.row_ptr[k], r1 = sd.row_ptr[k + 1];
+        b[0] = __longlong_as_double((long long)(r1 - r0));
+        b[1] = sd.diag[k];
+        b[2] = sd.amp[k];
+        for (int p = 0; p < P && p < 5; ++p) b[3 + p] = sd.gratio(k, p);
+        for (unsigned long long i = r0; i < r1; ++i) {
+            const int j = (int)(i - r0), c = j / G, l = j % G;
+            double* ch = b + SP_HEAD + c * CH;
+            const uint32_t cl = sd.col[i];
+            reinterpret_cast<uint32_t*>(ch)[l] = cl;
+            ch[G / 2 + l] = sd.melem[i];
+            ch[G / 2 + G + l] = sd.amp[cl];
+        }
+    }
+}
+
 __global__ void sparse_fill_idx_kernel(uint32_t* idx, size_t n, uint32_t v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) idx[i] = v;
 }
@@ -500,6 +620,8 @@ struct gwz_sparse {
     double* d_rpsi = nullptr;  // [nnz]
     double* d_rec = nullptr;   // [dim][RS]
     size_t rec_cap = 0;
+    double* d_blk = nullptr;   // [dim][BS] row blocks, or null
+    size_t blk_cap = 0;
     double* d_amp = nullptr;  // [dim]
     double* d_tab = nullptr;  // [dim][1 + P]
     size_t tab_cap = 0;
@@ -543,6 +665,10 @@ static int sp_ppl(int P, int G) {
         default: { constexpr int PPL = 8; CALL; } break;                                  \
     })
 
+#define GWZ_SP_DISPATCH_BLK(B_, CALL)             \
+    if (B_) { constexpr bool BLK = true; CALL; }  \
+    else { constexpr bool BLK = false; CALL; }
+
 // lanes per walker / row: the smallest power of two that covers a quarter of a mean row -- the path is bound by the
 // latency of its dependent gathers, so more walkers in flight beat fewer chunks per row (measured: L = 24 runs
 // fastest with G = 8, L = 8 with G = 4) -- raised until the parameters fit 8 per lane.  GWZ_SPARSE_GROUP overrides.
@@ -570,6 +696,7 @@ extern "C" int gwz_sparse_destroy(gwz_sparse* h) {
         cudaFree(h->d_amp);
         cudaFree(h->d_rpsi);
         cudaFree(h->d_rec);
+        cudaFree(h->d_blk);
         cudaFree(h->d_tab);
         cudaFree(h->d_partials);
     }
@@ -641,6 +768,13 @@ extern "C" int gwz_sparse_info(const gwz_sparse* h, uint64_t* dim, uint64_t* nnz
     return GWZ_OK;
 }
 
+extern "C" int gwz_sparse_layout(const gwz_sparse* h, int32_t* row_blocks, uint64_t* block_bytes) {
+    GWZ_REQUIRE(h != nullptr, "gwz_sparse_layout: NULL handle");
+    if (row_blocks) *row_blocks = h->sd.blk != nullptr;
+    if (block_bytes) *block_bytes = h->sd.blk ? (uint64_t)h->sd.BS * 8 : 0;
+    return GWZ_OK;
+}
+
 static int sp_reserve_table(gwz_sparse* h, int P) {
     const size_t need = (size_t)h->dim * (size_t)(1 + P);
     if (need > h->tab_cap) {
@@ -667,6 +801,34 @@ static int sp_reserve_table(gwz_sparse* h, int P) {
     return GWZ_OK;
 }
 
+// Row blocks are used when the rows are regular enough: at most twice the bytes of the row-pointer layout (or
+// 64 MiB) and at most a third of the free device memory.  GWZ_SPARSE_BLOCKS=0 keeps the row-pointer layout.
+static int sp_plan_blocks(gwz_sparse* h) {
+    h->sd.blk = nullptr;
+    h->sd.BS = 0;
+    if (const char* e = std::getenv("GWZ_SPARSE_BLOCKS"))
+        if (std::atoi(e) == 0) return GWZ_OK;
+    const int G = h->G;
+    const uint64_t chunks = std::max<uint64_t>((h->max_row + G - 1) / G, SP_R);
+    const uint64_t BS = (SP_HEAD + chunks * sp_chunk_doubles(G) + 15) / 16 * 16;
+    if (BS > (1u << 30)) return GWZ_OK;
+    const uint64_t blk_bytes = h->dim * BS * 8, csr_bytes = h->nnz * 20 + h->dim * 72;
+    size_t free_b = 0, total_b = 0;
+    GWZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t have = free_b + h->blk_cap * 8;
+    if (blk_bytes > std::max<uint64_t>(2 * csr_bytes, 64ull << 20) || blk_bytes > have / 3) return GWZ_OK;
+    if (h->dim * BS > h->blk_cap) {
+        if (h->d_blk) cudaFree(h->d_blk);
+        h->d_blk = nullptr;
+        h->blk_cap = 0;
+        GWZ_CUDA(cudaMalloc(&h->d_blk, blk_bytes));
+        h->blk_cap = h->dim * BS;
+    }
+    h->sd.blk = h->d_blk;
+    h->sd.BS = (int)BS;
+    return GWZ_OK;
+}
+
 static int sp_expand(gwz_sparse* h) {
     gwz_context* c = h->ctx;
     const unsigned rgrid = (unsigned)std::min<uint64_t>((h->dim + 255) / 256, (uint64_t)c->prop.multiProcessorCount * 16);
@@ -679,6 +841,13 @@ static int sp_expand(gwz_sparse* h) {
     api_count_launch();
     sparse_expand_kernel<<<grid, 256, 0, c->stream>>>(h->d_col, h->d_amp, h->nnz, h->d_rpsi);
     GWZ_CUDA(cudaGetLastError());
+    if (int rc = sp_plan_blocks(h)) return rc;
+    if (h->sd.blk) {
+        GWZ_CUDA(cudaMemsetAsync(h->d_blk, 0, sizeof(double) * h->dim * h->sd.BS, c->stream));
+        api_count_launch();
+        GWZ_SP_DISPATCH_G(h->G, (sparse_fill_blocks_kernel<G><<<rgrid, 256, 0, c->stream>>>(h->sd, h->d_blk)));
+        GWZ_CUDA(cudaGetLastError());
+    }
     return GWZ_OK;
 }
 
@@ -842,9 +1011,9 @@ extern "C" int gwz_sparse_probe(gwz_sparse* h, const uint32_t* idx, size_t n, co
     if (u01) GWZ_CUDA(cudaMemcpyAsync(d_u.p, u01, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     const int grid = sp_grid(h, n);
     api_count_launch();
-    GWZ_SP_DISPATCH_G(h->G, (sparse_probe_kernel<G><<<grid, SP_BLOCK, 0, c->stream>>>(
+    GWZ_SP_DISPATCH_BLK(h->sd.blk != nullptr, GWZ_SP_DISPATCH_G(h->G, (sparse_probe_kernel<G, BLK><<<grid, SP_BLOCK, 0, c->stream>>>(
                                 h->sd, d_idx.p, n, u01 ? d_u.p : nullptr, d_e.p, d_t.p, d_g.p, d_nh.p, rates ? d_r.p : nullptr,
-                                stride, d_ch.p, d_next.p, c->d_err)));
+                                stride, d_ch.p, d_next.p, c->d_err))));
     GWZ_CUDA(cudaGetLastError());
     if (e_loc) GWZ_CUDA(cudaMemcpyAsync(e_loc, d_e.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     if (residence_time) GWZ_CUDA(cudaMemcpyAsync(residence_time, d_t.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -919,10 +1088,10 @@ static int sp_walkers_launch(gwz_swalkers* w, uint64_t steps, int accumulate, in
     gwz_context* c = h->ctx;
     const int grid = sp_grid(h, w->n), ppl = sp_ppl(h->P, h->G);
     api_count_launch();
-    GWZ_SP_DISPATCH(h->G, ppl, (sparse_walker_kernel<G, PPL><<<grid, SP_BLOCK, 0, c->stream>>>(
+    GWZ_SP_DISPATCH_BLK(h->sd.blk != nullptr, GWZ_SP_DISPATCH(h->G, ppl, (sparse_walker_kernel<G, PPL, BLK><<<grid, SP_BLOCK, 0, c->stream>>>(
                                    h->sd, philox_keys(w->seed), w->d_idx, w->d_acc, w->n, w->offset, w->steps_done, steps,
                                    accumulate, reset_acc, accumulate ? w->shift_e : 0.0, rec_tau, rec_eloc, rec_idx, hist,
-                                   c->d_err)));
+                                   c->d_err))));
     GWZ_CUDA(cudaGetLastError());
     w->steps_done += steps;
     return GWZ_OK;

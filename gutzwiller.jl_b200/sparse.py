@@ -50,7 +50,10 @@ class _SparseHandle:
         d, nz, mr = C.c_uint64(), C.c_uint64(), C.c_uint64()
         P, G = C.c_int32(), C.c_int32()
         check(lib().gwz_sparse_info(self._h, C.byref(d), C.byref(nz), C.byref(mr), C.byref(P), C.byref(G)))
-        return dict(dim=d.value, nnz=nz.value, max_row=mr.value, num_parameters=P.value, lanes_per_walker=G.value)
+        rb, bb = C.c_int32(), C.c_uint64()
+        check(lib().gwz_sparse_layout(self._h, C.byref(rb), C.byref(bb)))
+        return dict(dim=d.value, nnz=nz.value, max_row=mr.value, num_parameters=P.value, lanes_per_walker=G.value,
+                    row_blocks=bool(rb.value), block_bytes=bb.value)
 
     def set_table(self, psi, grad_ratio=None) -> None:
         psi = np.ascontiguousarray(psi, dtype=np.float64)

@@ -336,6 +336,9 @@ int gwz_sparse_create(gwz_context *ctx, uint64_t dim, const uint64_t *row_ptr, c
 int gwz_sparse_destroy(gwz_sparse *h);
 int gwz_sparse_info(const gwz_sparse *h, uint64_t *dim, uint64_t *nnz, uint64_t *max_row, int32_t *num_parameters,
                     int32_t *lanes_per_walker);
+/* layout the walkers read after the last table was set: row_blocks = 1 when every state's row sits in a fixed-stride
+ * block (one dependent HBM access per step; chosen when the rows are regular enough), block_bytes = its stride */
+int gwz_sparse_layout(const gwz_sparse *h, int32_t *row_blocks, uint64_t *block_bytes);
 /* any ansatz as a table (P = num_parameters; grad_ratio may be NULL when P = 0, e.g. VectorAnsatz, vector.jl:6-12) */
 int gwz_sparse_set_table(gwz_sparse *h, const double *psi, const double *grad_ratio, int32_t P);
 /* GutzwillerAnsatz(H) (gutzwiller.jl:25-36) filled on the device: psi = exp(-g diag), grad psi / psi = -diag */

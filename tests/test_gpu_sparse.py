@@ -29,6 +29,14 @@ def ops():
     return _operators()
 
 
+@pytest.fixture(params=["blocks", "rows"])
+def layout(request, monkeypatch):
+    """both HBM layouts of the walk: fixed-stride row blocks (default when rows are regular enough) and row pointers"""
+    if request.param == "rows":
+        monkeypatch.setenv("GWZ_SPARSE_BLOCKS", "0")
+    return request.param
+
+
 def _pair(gw, op, group=None):
     from oracle.oracle import SparseOracle
     if group is None:
@@ -53,13 +61,14 @@ def _random_table(dim, P, seed):
 
 @pytest.mark.parametrize("name,group", [("real", None), ("mom", None), ("fermi", None), ("ragged", None), ("ragged", 4),
                                         ("ragged", 8), ("mom", 32), ("real", 16)])
-def test_probe_matches_oracle(gw, ops, name, group):
+def test_probe_matches_oracle(gw, ops, name, group, layout):
     H, so = _pair(gw, ops[name], group)
     h = H.handle()
     if group is not None:
         assert h.info()["lanes_per_walker"] == group
     psi, gr = _random_table(H.dim, 3, 7)
     h.set_table(psi, gr)
+    assert h.info()["row_blocks"] == (layout == "blocks")
     so.set_table(psi, gr)
     rng = np.random.default_rng(5)
     idx = np.flatnonzero(psi != 0.0)
@@ -87,7 +96,7 @@ def test_probe_matches_oracle(gw, ops, name, group):
 
 
 @pytest.mark.parametrize("name", ["real", "mom", "fermi", "ragged"])
-def test_trajectories_match_oracle_step_for_step(gw, ops, name):
+def test_trajectories_match_oracle_step_for_step(gw, ops, name, layout):
     H, so = _pair(gw, ops[name])
     if name == "ragged":
         psi, gr = _random_table(H.dim, 2, 3)
@@ -120,7 +129,7 @@ def test_trajectories_match_oracle_step_for_step(gw, ops, name):
 
 
 @pytest.mark.parametrize("P", [2, 7, 20, 70])
-def test_many_parameter_tables_follow_the_oracle(gw, ops, P):
+def test_many_parameter_tables_follow_the_oracle(gw, ops, P, layout):
     """gradient accumulators for P parameters (several per lane; the lane group widens when P > 8 per lane)"""
     H, so = _pair(gw, ops["real"])
     psi, gr = _random_table(H.dim, P, 21 + P)
