@@ -235,11 +235,17 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                     if (p < P) F[q] = gen_feature(gm, ws, p, reg, ext, lgsum);
                 }
             }
-            if (k == 0 || (step & 1ull) == 0ull) {
-                const uint64_t blk = step >> 1;
-                philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+            // one Philox block serves two steps; the G lanes of the walker evaluate G consecutive blocks at once
+            // (lane l: block (blk & ~(G-1)) + l) and hand their words to the group when their step comes
+            const uint64_t blk = step >> 1;
+            if (k == 0 || ((step & 1ull) == 0ull && (blk & (uint64_t)(G - 1)) == 0ull)) {
+                const uint64_t mine = (blk & ~(uint64_t)(G - 1)) + (uint64_t)lane;
+                philox4x32_10_keyed((uint32_t)mine, (uint32_t)(mine >> 32), c2, c3, pk, rnd);
             }
-            const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
+            const int rsrc = (int)(blk & (uint64_t)(G - 1));
+            const uint32_t wlo = __shfl_sync(0xffffffffu, (step & 1ull) ? rnd[2] : rnd[0], rsrc, G);
+            const uint32_t whi = __shfl_sync(0xffffffffu, (step & 1ull) ? rnd[3] : rnd[1], rsrc, G);
+            const double u01 = u01_from_words(wlo, whi);
             double S_lane, E_lane;
             int nocc_lane;
             gen_rates<MPL, false>(gm, ws, lane, S_lane, E_lane, nocc_lane);

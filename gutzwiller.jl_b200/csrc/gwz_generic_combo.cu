@@ -298,11 +298,16 @@ combo_walker_kernel(const __grid_constant__ GenCombo cb, const __grid_constant__
                 for (int q = 0; q < PPL; ++q)
                     if (comp[q] < 2) F[q] = combo_feature(cb, ws, ws2, comp[q], local[q], reg, ext, lgsum);
             }
-            if (k == 0 || (step & 1ull) == 0ull) {
-                const uint64_t blk = step >> 1;
-                philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+            // the 32 lanes evaluate 32 consecutive Philox blocks at once (64 steps); see gen_walker_kernel
+            const uint64_t blk = step >> 1;
+            if (k == 0 || ((step & 1ull) == 0ull && (blk & 31ull) == 0ull)) {
+                const uint64_t mine = (blk & ~31ull) + (uint64_t)lane;
+                philox4x32_10_keyed((uint32_t)mine, (uint32_t)(mine >> 32), c2, c3, pk, rnd);
             }
-            const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
+            const int rsrc = (int)(blk & 31ull);
+            const uint32_t wlo = __shfl_sync(0xffffffffu, (step & 1ull) ? rnd[2] : rnd[0], rsrc);
+            const uint32_t whi = __shfl_sync(0xffffffffu, (step & 1ull) ? rnd[3] : rnd[1], rsrc);
+            const double u01 = u01_from_words(wlo, whi);
             const ComboW cw = combo_weights(cb.alpha, lr);
             double S_lane, E_lane;
             int nocc_lane;

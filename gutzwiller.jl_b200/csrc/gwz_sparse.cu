@@ -309,11 +309,22 @@ sparse_walker_kernel(const __grid_constant__ SparseDev sd, const __grid_constant
         uint32_t rnd[4] = {0u, 0u, 0u, 0u};
         for (uint64_t s = 0; s < steps; ++s) {
             const uint64_t step = step0 + s;
-            if (s == 0 || (step & 1ull) == 0ull) {
-                const uint64_t blk = step >> 1;
-                philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+            // one Philox block serves two steps; with G >= 8 the lanes of the group evaluate G consecutive blocks at
+            // once (lane l: block (blk & ~(G-1)) + l) and hand the words to the group when their step comes
+            // (measured: +3 % at G = 8, -4 % at G = 4, where every lane keeps evaluating its walker's block)
+            constexpr int SH = G >= 8 ? G : 1;
+            const uint64_t blk = step >> 1;
+            if (s == 0 || ((step & 1ull) == 0ull && (blk & (uint64_t)(SH - 1)) == 0ull)) {
+                const uint64_t mine = (blk & ~(uint64_t)(SH - 1)) + (uint64_t)(SH > 1 ? lane : 0);
+                philox4x32_10_keyed((uint32_t)mine, (uint32_t)(mine >> 32), c2, c3, pk, rnd);
             }
-            const double u01 = (step & 1ull) ? u01_from_words(rnd[2], rnd[3]) : u01_from_words(rnd[0], rnd[1]);
+            uint32_t wlo = (step & 1ull) ? rnd[2] : rnd[0], whi = (step & 1ull) ? rnd[3] : rnd[1];
+            if (SH > 1) {
+                const int src = (int)(blk & (uint64_t)(SH - 1));
+                wlo = __shfl_sync(mask, wlo, src, G);
+                whi = __shfl_sync(mask, whi, src, G);
+            }
+            const double u01 = u01_from_words(wlo, whi);
             const SpStep o = BLK ? sp_step_blk<G, false>(sd, k, lane, mask, u01, nullptr)
                                  : sp_step<G, false>(sd, k, lane, mask, u01, nullptr);
             if (o.chosen < 0 || !(o.tau < 1.0e300)) {  // qmc.jl:34-36
