@@ -157,9 +157,10 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
     }
 }
 
-// Translation-symmetry-reduced ranked sweep.  HubbardReal1D is a periodic chain and the Gutzwiller amplitude only
-// depends on the multiset of occupations, so the four per-state terms are identical for the M cyclic shifts of an
-// occupation vector: evaluate one representative per orbit and weight it with the orbit size.  On the unary string
+// Symmetry-reduced ranked sweep.  HubbardReal1D is a periodic chain and the Gutzwiller amplitude only depends on
+// the multiset of occupations, so the four per-state terms are identical for the M cyclic shifts of an occupation
+// vector and for their mirror images: evaluate one representative per orbit of the dihedral group and weight it
+// with the orbit size.  On the unary string
 // closed by a virtual separator (L = N+M bits, bit L-1 = 0) a mode shift is a cyclic rotation that brings a 0 to the
 // top; the representative is the largest rotation.  Every thread still steps through its ranks (Gosper) and tests
 // each state (a few rotations on average, early exit); representatives are compacted through a per-warp queue so
@@ -189,6 +190,29 @@ __device__ __forceinline__ bool orbit_representative(T e, int L, T maskL, int M,
         same += (r == e);
     }
     mult = same ? M / (same + 1) : M;  // the stabiliser is trivial for almost every orbit: keep the division off the common path
+    // Reflection (n_1..n_M -> n_M..n_1 = the bit-reversed string) is a symmetry of the periodic chain and of the
+    // Gutzwiller amplitude too: keep e only if it is also >= every rotation of its mirror image, and count the mirror
+    // orbit in the weight.  Only the ~1/M survivors of the rotation test get here.
+    const T rev = (T)((sizeof(T) == 8 ? (T)__brevll((unsigned long long)e) : (T)__brev((unsigned)e)) >> (BITS - L));
+    // rev = 0 1^t 0 ... read from the bottom; bring the zero above that run to the top: a rotation with t ones on top
+    const int sh = L - 2 - t;
+    const T m = sh ? (T)(((T)(rev << sh) | (T)(rev >> (L - sh))) & maskL) : rev;
+    if (m > e) return false;
+    if (m < e) {
+        // other rotations of the mirror image with a run of t on top (ties): any of them larger than e?
+        T gm = ~(T)0;
+        for (int k = 0; k < t; ++k) gm &= (T)(m >> k);
+        T tm = (T)((t == 0 ? ~m : (T)(gm << t)) & ~m) & (T)(maskL >> 1);
+        bool equal = false;
+        while (tm) {
+            const int z = (sizeof(T) == 8) ? (__ffsll((long long)tm) - 1) : (__ffs((int)tm) - 1);
+            tm &= tm - 1;
+            const T r = (T)(((T)(m >> (z + 1)) | (T)(m << (L - 1 - z))) & maskL);
+            if (r > e) return false;
+            equal = equal || (r == e);
+        }
+        if (!equal) mult *= 2;  // the mirror orbit is a different rotation orbit
+    }
     return true;
 }
 
