@@ -1035,10 +1035,54 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     L.partials = s->d_partials;
     L.grid = s->grid;
     L.chunk = s->chunk;
+    int grid = s->grid;
+    if (L.symmetric && s->d_basis == nullptr && m->N + m->M <= 64) {
+        // An orbit representative carries the largest occupation in mode M, so n_M >= tmin = ceil(N/M): the top tmin
+        // bits of the unary string are set.  In rank (= numeric) order those states are the LAST C(B-tmin, N-tmin)
+        // ranks: the ranks below cannot hold a representative and are not visited at all.
+        std::vector<uint64_t> tab;
+        binomial_table(tab);
+        int tmin = (m->N + m->M - 1) / m->M;
+        const uint64_t total = tab[m->B * 65 + m->N];
+        if (tmin * m->M == m->N && total != UINT64_MAX) {
+            // commensurate filling: the only representative with n_M = tmin is the uniform state |tmin ... tmin>.  It is
+            // handed to the kernel on its own (weight 1, in the shard that holds its rank) and the visited ranks start at
+            // n_M >= tmin + 1 (N = M = 16: 26 % of the states instead of 52 %).
+            uint64_t x = 0, r = 0;
+            int j = 0;
+            for (int i = 0; i < m->M; ++i)
+                for (int q = 0; q < tmin; ++q) {
+                    const int pos = i * (tmin + 1) + q;
+                    x |= 1ull << pos;
+                    r += tab[pos * 65 + (++j)];
+                }
+            if (r >= s->rank_begin && r - s->rank_begin < s->dim) {
+                L.extra_state = x;
+                L.has_extra = 1;
+            }
+            ++tmin;
+        }
+        const uint64_t tail = tab[(m->B - tmin) * 65 + (m->N - tmin)];
+        if (total != UINT64_MAX && tail != UINT64_MAX && tail <= total) {
+            const uint64_t hi = s->rank_begin + s->dim;
+            const uint64_t lo = std::min(std::max(s->rank_begin, total - tail), hi);
+            L.rank_begin = lo;
+            L.dim = hi - lo;
+            uint64_t chunk = 1;
+            GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, true, L.dim ? L.dim : 1, c->prop.multiProcessorCount, &grid, &chunk));
+            if (grid <= s->grid) {
+                L.grid = grid;
+                L.chunk = chunk;
+            } else {  // cannot happen (fewer ranks never need more CTAs); keep the partials buffer safe anyway
+                grid = s->grid;
+                L.chunk = (L.dim + (uint64_t)grid * SWEEP_BLOCK - 1) / ((uint64_t)grid * SWEEP_BLOCK) + 1;
+            }
+        }
+    }
     GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
     GWZ_LAUNCH(launch_sweep(L, c->stream));
     GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
-    GWZ_LAUNCH(launch_reduce_partials(s->d_partials, s->grid, 4, c->d_acc, c->stream));
+    GWZ_LAUNCH(launch_reduce_partials(s->d_partials, grid, 4, c->d_acc, c->stream));
     if (c->comm) {
         const NcclApi* api = nccl_api(nullptr);
         if (!api) return fail(GWZ_ERR_NCCL, "NCCL unavailable");

@@ -111,6 +111,8 @@ struct SweepLaunch {
     double* partials;  // [grid][4]
     int grid;
     uint64_t chunk;  // consecutive ranks per thread (ranked mode)
+    uint64_t extra_state;  // symmetric mode: one more state evaluated with weight 1 (the uniform state, see sweep_run)
+    int has_extra;
     // optional per-state output (terms kernel): out[count][4] for states first..first+count-1
     double* terms_out;
     uint64_t* states_out;  // AoS count x W

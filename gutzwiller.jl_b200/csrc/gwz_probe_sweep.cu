@@ -221,7 +221,8 @@ constexpr int SYM_BINOM_SLOTS = 32 * 65;  // rows p = 0..31 of the [65][65] tabl
 template <int NW, int KC>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb, uint64_t dim,
-                 uint64_t rank_begin, uint64_t chunk, const uint64_t* __restrict__ binom, double* __restrict__ partials) {
+                 uint64_t rank_begin, uint64_t chunk, const uint64_t* __restrict__ binom, double* __restrict__ partials,
+                 uint64_t extra_state, int has_extra) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StepScratch<NW, KC> sc(smem_raw, dm.N, typename StepScratch<NW, KC>::SweepLayout{});
     sc.fill_exptab(dm.N, tb.c);
@@ -256,6 +257,7 @@ sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ De
         s2 = fma(w, ng, s2);
         s3 = fma(w, dg, s3);
     };
+    if (has_extra && tid == 0) evaluate(extra_state, 1.0);  // the uniform state at commensurate filling (see sweep_run)
     for (uint64_t base = (tid - lane) * chunk; base < dim; base += nthreads * chunk) {  // warp-uniform trip count
         const uint64_t first = base + (uint64_t)lane * chunk;
         const uint64_t cnt = first < dim ? min(chunk, dim - first) : 0;
@@ -414,7 +416,7 @@ cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
         if (ranked && L.symmetric && L.dm.N + L.dm.M <= 64) {
             if (cudaError_t e = ensure_smem(sweep_sym_kernel<NW, KC>, smem)) return e;
             sweep_sym_kernel<NW, KC><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.dim, L.rank_begin, L.chunk, L.binom,
-                                                                      L.partials);
+                                                                      L.partials, L.extra_state, L.has_extra);
         } else if (ranked) {
             if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, true>, smem)) return e;
             sweep_kernel<NW, KC, true><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
