@@ -107,6 +107,7 @@ struct gwz_sweep {
     int grid = 0;
     uint64_t chunk = 1;
     float last_ms = 0.f;
+    std::vector<uint64_t> h_binom;     // host copy of the binomial table (ranked mode)
 };
 
 
@@ -985,6 +986,8 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
         s->rank_begin = rank_begin;
         GWZ_CUDA(cudaMalloc(&s->d_binom, sizeof(uint64_t) * 65 * 65));
         GWZ_CUDA(cudaMemcpyAsync(s->d_binom, tab.data(), sizeof(uint64_t) * 65 * 65, cudaMemcpyHostToDevice, c->stream));
+        GWZ_CUDA(cudaStreamSynchronize(c->stream));  // tab is copied from before it moves
+        s->h_binom = std::move(tab);
     }
     GWZ_CUDA(sweep_grid(m->nw, choose_kc(m, 0.0, true), m->N, m->M, s->d_basis == nullptr, s->dim, c->prop.multiProcessorCount,
                         &s->grid, &s->chunk));
@@ -1040,8 +1043,7 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
         // An orbit representative carries the largest occupation in mode M, so n_M >= tmin = ceil(N/M): the top tmin
         // bits of the unary string are set.  In rank (= numeric) order those states are the LAST C(B-tmin, N-tmin)
         // ranks: the ranks below cannot hold a representative and are not visited at all.
-        std::vector<uint64_t> tab;
-        binomial_table(tab);
+        const std::vector<uint64_t>& tab = s->h_binom;
         int tmin = (m->N + m->M - 1) / m->M;
         const uint64_t total = tab[m->B * 65 + m->N];
         if (tmin * m->M == m->N && total != UINT64_MAX) {
