@@ -1,5 +1,7 @@
 // gwz_probe_sweep.cu -- per-address probe (kinetic_sample! for a batch of addresses) and the
 // LocalEnergyEvaluator full-basis sweep (src/localenergy.jl:94-155).
+#include <algorithm>
+#include <cstdlib>
 #include "gwz_internal.h"
 #include "gwz_steps.cuh"
 
@@ -397,7 +399,11 @@ cudaError_t sweep_grid(int nw, int kc, int N, int M, bool ranked, uint64_t dim, 
         // runs is 1.8x slower on {16,16} and 3.4x on {18,18}).
         const uint64_t wave = (uint64_t)sm_count * GWZ_SWEEP_WAVE_CTAS * SWEEP_BLOCK;  // short runs, several waves: the block scheduler balances the rank-dependent cost
         c = (dim + wave - 1) / wave;
-        c = c < 8 ? 8 : (c > 256 ? 256 : c);
+        // run length: >= 8 amortises the unranking; small sweeps (BASELINE config 2 after pruning: 3.5e5 ranks) are
+        // latency bound and do better with more, shorter runs (measured: {12,12} kernel 32 -> 24 us)
+        uint64_t cmin = dim < 1500000ull ? 4 : 8;
+        if (const char* e = std::getenv("GWZ_SWEEP_MIN_CHUNK")) cmin = (uint64_t)std::max(1, std::atoi(e));
+        c = c < cmin ? cmin : (c > 256 ? 256 : c);
         max_threads = (uint64_t)sm_count * 4096 * SWEEP_BLOCK;  // beyond that threads take several runs
     }
     uint64_t threads = (dim + c - 1) / c;
