@@ -107,6 +107,8 @@ struct gwz_sweep {
     int grid = 0;
     uint64_t chunk = 1;
     float last_ms = 0.f;
+    bool ms_pending = false;           // ev0/ev1 hold the last sweep's kernel time, not read yet
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<uint64_t> h_binom;     // host copy of the binomial table (ranked mode)
 };
 
@@ -992,6 +994,8 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
     GWZ_CUDA(sweep_grid(m->nw, choose_kc(m, 0.0, true), m->N, m->M, s->d_basis == nullptr, s->dim, c->prop.multiProcessorCount,
                         &s->grid, &s->chunk));
     GWZ_CUDA(cudaMalloc(&s->d_partials, sizeof(double) * 4 * (size_t)s->grid));
+    GWZ_CUDA(cudaEventCreate(&s->ev0));
+    GWZ_CUDA(cudaEventCreate(&s->ev1));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     *out = guard.release();
     return GWZ_OK;
@@ -1003,6 +1007,8 @@ extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
     cudaFree(s->d_basis);
     cudaFree(s->d_binom);
     cudaFree(s->d_partials);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
     return GWZ_OK;
 }
@@ -1081,9 +1087,9 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
             }
         }
     }
-    GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
+    GWZ_CUDA(cudaEventRecord(s->ev0, c->stream));
     GWZ_LAUNCH(launch_sweep(L, c->stream));
-    GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
+    GWZ_CUDA(cudaEventRecord(s->ev1, c->stream));
     GWZ_LAUNCH(launch_reduce_partials(s->d_partials, grid, 4, c->d_acc, c->stream));
     if (c->comm) {
         const NcclApi* api = nccl_api(nullptr);
@@ -1092,7 +1098,7 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     }
     GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
-    GWZ_CUDA(cudaEventElapsedTime(&s->last_ms, c->ev0, c->ev1));
+    s->ms_pending = true;  // cudaEventElapsedTime costs 5 us: only when gwz_sweep_last_kernel_ms asks (a small sweep is 60 us)
     for (int i = 0; i < 4; ++i) acc4[i] = c->h_acc[i];
     return GWZ_OK;
 }
@@ -1156,6 +1162,12 @@ extern "C" int gwz_sweep_states(gwz_sweep* s, uint64_t first, uint64_t count, ui
 }
 extern "C" int gwz_sweep_last_kernel_ms(const gwz_sweep* s, float* ms) {
     GWZ_REQUIRE(s && ms, "gwz_sweep_last_kernel_ms: NULL argument");
+    if (s->ms_pending) {
+        gwz_sweep* w = const_cast<gwz_sweep*>(s);
+        if (int rc = use_device(s->m->ctx)) return rc;
+        GWZ_CUDA(cudaEventElapsedTime(&w->last_ms, s->ev0, s->ev1));
+        w->ms_pending = false;
+    }
     *ms = s->last_ms;
     return GWZ_OK;
 }
