@@ -107,6 +107,12 @@ struct gwz_sweep {
     int grid = 0;
     uint64_t chunk = 1;
     float last_ms = 0.f;
+    // representative basis of a symmetric ranked sweep (built at the second sweep of a handle, reused afterwards)
+    uint64_t* d_rep = nullptr;
+    uint32_t* d_mult = nullptr;
+    uint64_t nrep = 0;
+    int rep_state = 0;                 // 0 not built, 1 built, -1 not cacheable (too large / disabled)
+    uint64_t sym_calls = 0;
     bool ms_pending = false;           // ev0/ev1 hold the last sweep's kernel time, not read yet
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<uint64_t> h_binom;     // host copy of the binomial table (ranked mode)
@@ -1007,6 +1013,8 @@ extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
     cudaFree(s->d_basis);
     cudaFree(s->d_binom);
     cudaFree(s->d_partials);
+    cudaFree(s->d_rep);
+    cudaFree(s->d_mult);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -1023,6 +1031,48 @@ extern "C" int gwz_sweep_dim(const gwz_sweep* s, uint64_t* dim) {
 static bool sweep_sym_enabled() {
     const char* e = std::getenv("GWZ_SWEEP_SYM");
     return !(e && e[0] == '0');
+}
+
+// GWZ_SWEEP_CACHE=0: never store the representatives (every sweep enumerates and tests its rank range)
+static int sweep_build_representatives(gwz_sweep* s, const SweepLaunch& L) {
+    gwz_model* m = s->m;
+    gwz_context* c = m->ctx;
+    s->rep_state = -1;
+    if (const char* e = std::getenv("GWZ_SWEEP_CACHE"))
+        if (e[0] == '0') return GWZ_OK;
+    DevBuf<unsigned long long> d_cnt;
+    GWZ_CUDA(d_cnt.alloc(1));
+    unsigned long long n = 0;
+    if (L.dim) {
+        GWZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), c->stream));
+        GWZ_LAUNCH(launch_sweep_collect(m->N, m->M, m->B, L.dim, L.rank_begin, L.grid, L.chunk, L.binom, d_cnt.p, nullptr,
+                                        nullptr, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(&n, d_cnt.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+        GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    const uint64_t total = n + (L.has_extra ? 1 : 0);
+    size_t free_b = 0, total_b = 0;
+    GWZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // (8 + 4) B per representative, twice during the sort; keep it to a quarter of the free memory
+    if (total == 0 || total > 0x7fffffffull || total * 24 > free_b / 4) return GWZ_OK;
+    GWZ_CUDA(cudaMalloc(&s->d_rep, sizeof(uint64_t) * total));
+    GWZ_CUDA(cudaMalloc(&s->d_mult, sizeof(uint32_t) * total));
+    if (n) {
+        GWZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), c->stream));
+        GWZ_LAUNCH(launch_sweep_collect(m->N, m->M, m->B, L.dim, L.rank_begin, L.grid, L.chunk, L.binom, d_cnt.p, s->d_rep,
+                                        s->d_mult, c->stream));
+    }
+    if (L.has_extra) {
+        const uint32_t one = 1u;
+        GWZ_CUDA(cudaMemcpyAsync(s->d_rep + n, &L.extra_state, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(s->d_mult + n, &one, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    api_count_launch();
+    GWZ_CUDA(sort_representatives(s->d_rep, s->d_mult, total, c->stream));
+    s->nrep = total;
+    s->rep_state = 1;
+    return GWZ_OK;
 }
 
 static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
@@ -1086,6 +1136,30 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
                 L.chunk = (L.dim + (uint64_t)grid * SWEEP_BLOCK - 1) / ((uint64_t)grid * SWEEP_BLOCK) + 1;
             }
         }
+    }
+    const bool sym_ranked = L.symmetric && s->d_basis == nullptr && m->N + m->M <= 64;
+    if (sym_ranked && s->rep_state == 0 && ++s->sym_calls >= 2) {
+        if (int rc = sweep_build_representatives(s, L)) return rc;
+    }
+    if (sym_ranked && s->rep_state == 1) {
+        // later sweeps of the same handle: evaluate the stored representatives, weighted with their orbit sizes
+        L.basis = s->d_rep;
+        L.dim = s->nrep;
+        L.rank_begin = 0;
+        L.weight = s->d_mult;
+        L.symmetric = 0;
+        L.has_extra = 0;
+        uint64_t chunk = 1;
+        GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, false, L.dim, c->prop.multiProcessorCount, &grid, &chunk));
+        if (grid > s->grid) {
+            cudaFree(s->d_partials);
+            s->d_partials = nullptr;
+            GWZ_CUDA(cudaMalloc(&s->d_partials, sizeof(double) * 4 * (size_t)grid));
+            s->grid = grid;
+            L.partials = s->d_partials;
+        }
+        L.grid = grid;
+        L.chunk = chunk;
     }
     GWZ_CUDA(cudaEventRecord(s->ev0, c->stream));
     GWZ_LAUNCH(launch_sweep(L, c->stream));

@@ -113,6 +113,7 @@ struct SweepLaunch {
     uint64_t chunk;  // consecutive ranks per thread (ranked mode)
     uint64_t extra_state;  // symmetric mode: one more state evaluated with weight 1 (the uniform state, see sweep_run)
     int has_extra;
+    const uint32_t* weight;  // stored mode, optional: orbit sizes of a representative basis
     // optional per-state output (terms kernel): out[count][4] for states first..first+count-1
     double* terms_out;
     uint64_t* states_out;  // AoS count x W
@@ -120,6 +121,10 @@ struct SweepLaunch {
 };
 cudaError_t sweep_grid(int nw, int kc, int N, int M, bool ranked, uint64_t dim, int sm_count, int* grid, uint64_t* chunk);
 cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s);
+cudaError_t launch_sweep_collect(int N, int M, int B, uint64_t dim, uint64_t rank_begin, int grid, uint64_t chunk,
+                                 const uint64_t* binom, unsigned long long* counter, uint64_t* store, uint32_t* mult,
+                                 cudaStream_t s);
+cudaError_t sort_representatives(uint64_t* keys, uint32_t* vals, uint64_t n, cudaStream_t s);
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s);
 
 // ---- DVec(result) histogram (gwz_hist.cu) ----------------------------------------------------

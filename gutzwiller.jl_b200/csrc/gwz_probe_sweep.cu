@@ -1,6 +1,7 @@
 // gwz_probe_sweep.cu -- per-address probe (kinetic_sample! for a batch of addresses) and the
 // LocalEnergyEvaluator full-basis sweep (src/localenergy.jl:94-155).
 #include <algorithm>
+#include <cub/cub.cuh>
 #include <cstdlib>
 #include "gwz_internal.h"
 #include "gwz_steps.cuh"
@@ -99,7 +100,8 @@ template <int NW, int KC, bool RANKED>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
              const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
-             const uint64_t* __restrict__ binom, double* __restrict__ partials) {
+             const uint64_t* __restrict__ binom, double* __restrict__ partials,
+             const uint32_t* __restrict__ weight /* stored mode, optional: orbit sizes of a representative basis */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StepScratch<NW, KC> sc(smem_raw, dm.N, typename StepScratch<NW, KC>::SweepLayout{});
     sc.fill_exptab(dm.N, tb.c);
@@ -132,10 +134,11 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
             load_addr_soa<NW>(basis, dim, idx, dm.W, a);
             double num, den, ng, dg;
             state_terms<NW, KC>(a, dm, tb, sc, num, den, ng, dg);
-            s0 += num;
-            s1 += den;
-            s2 += ng;
-            s3 += dg;
+            const double w = weight ? (double)weight[idx] : 1.0;
+            s0 = fma(w, num, s0);
+            s1 = fma(w, den, s1);
+            s2 = fma(w, ng, s2);
+            s3 = fma(w, dg, s3);
         }
     }
     __shared__ double sm[SWEEP_BLOCK / 32][4];
@@ -305,6 +308,78 @@ sweep_sym_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ De
     }
 }
 
+// The orbit representatives of a rank range do not depend on the parameters: LocalEnergyEvaluator sweeps the same
+// basis again and again (the reference stores build_basis(H) once, localenergy.jl:86), so they are collected once
+// -- (state, orbit size) pairs in HBM -- and later sweeps only evaluate them.  store == nullptr: count only.
+__global__ void __launch_bounds__(SWEEP_BLOCK)
+sweep_collect_kernel(int N, int M, int B, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
+                     const uint64_t* __restrict__ binom, unsigned long long* __restrict__ counter,
+                     uint64_t* __restrict__ store, uint32_t* __restrict__ mult_out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    const int L = N + M;
+    const uint64_t maskL = (L >= 64) ? ~0ull : ((1ull << L) - 1ull);
+    unsigned long long local = 0ull;
+    for (uint64_t base = (tid - lane) * chunk; base < dim; base += nthreads * chunk) {  // warp-uniform trip count
+        const uint64_t first = base + (uint64_t)lane * chunk;
+        const uint64_t cnt = first < dim ? min(chunk, dim - first) : 0;
+        uint64_t x = cnt ? unrank_colex(rank_begin + first, N, B, binom) : 0ull;
+        for (uint64_t k = 0; k < chunk; ++k) {
+            int mult = 0;
+            const bool rep = (k < cnt) && (L <= 32 ? orbit_representative<uint32_t>((uint32_t)x, L, (uint32_t)maskL, M, mult)
+                                                   : orbit_representative<uint64_t>(x, L, maskL, M, mult));
+            if (store) {
+                const unsigned b = __ballot_sync(0xffffffffu, rep);
+                unsigned long long pos = 0ull;
+                if (lane == 0 && b) pos = atomicAdd(counter, (unsigned long long)__popc(b));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (rep) {
+                    const unsigned long long at = pos + __popc(b & ((1u << lane) - 1u));
+                    store[at] = x;
+                    mult_out[at] = (uint32_t)mult;
+                }
+            } else {
+                local += rep ? 1ull : 0ull;
+            }
+            if (k + 1 < cnt) x = (L <= 32) ? (uint64_t)next_same_popcount32((uint32_t)x) : next_same_popcount(x);
+        }
+    }
+    if (!store) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if (lane == 0 && local) atomicAdd(counter, local);
+    }
+}
+
+cudaError_t launch_sweep_collect(int N, int M, int B, uint64_t dim, uint64_t rank_begin, int grid, uint64_t chunk,
+                                 const uint64_t* binom, unsigned long long* counter, uint64_t* store, uint32_t* mult,
+                                 cudaStream_t s) {
+    sweep_collect_kernel<<<grid, SWEEP_BLOCK, 0, s>>>(N, M, B, dim, rank_begin, chunk, binom, counter, store, mult);
+    return cudaGetLastError();
+}
+
+// sort the collected pairs by state (the collection order depends on the scheduling): a fixed summation order
+cudaError_t sort_representatives(uint64_t* keys, uint32_t* vals, uint64_t n, cudaStream_t s) {
+    if (n < 2) return cudaSuccess;
+    if (n > 0x7fffffffull) return cudaErrorInvalidValue;
+    uint64_t* k2 = nullptr;
+    uint32_t* v2 = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaMalloc(&k2, sizeof(uint64_t) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&v2, sizeof(uint32_t) * n);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, k2, vals, v2, (int)n, 0, 64, s);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, k2, vals, v2, (int)n, 0, 64, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(keys, k2, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vals, v2, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(k2);
+    cudaFree(v2);
+    cudaFree(tmp);
+    return e;
+}
+
 // per-state outputs for parity tests: states first..first+count-1
 template <int NW, int KC, bool RANKED>
 __global__ void __launch_bounds__(SWEEP_BLOCK)
@@ -426,11 +501,11 @@ cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
         } else if (ranked) {
             if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, true>, smem)) return e;
             sweep_kernel<NW, KC, true><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
-                                                                         L.binom, L.partials);
+                                                                         L.binom, L.partials, nullptr);
         } else {
             if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, false>, smem)) return e;
             sweep_kernel<NW, KC, false><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
-                                                                          L.binom, L.partials);
+                                                                          L.binom, L.partials, L.weight);
         }
     });
     return cudaGetLastError();

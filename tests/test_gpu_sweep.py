@@ -221,3 +221,42 @@ def test_orbit_reduced_sweep_at_the_64_bit_limit(gw, monkeypatch):
         monkeypatch.setenv("GWZ_SWEEP_SYM", sym)
         out[sym] = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H)).accumulators(0.004)
     assert np.all(np.isfinite(out["0"])) and np.all(np.abs(out["1"] - out["0"]) <= 1e-12 * np.abs(out["0"]))
+
+
+@pytest.mark.parametrize("N,M", [(6, 6), (12, 12), (9, 3), (5, 30), (20, 3), (2, 2)])
+def test_cached_representative_basis_gives_the_same_sums(gw, N, M, monkeypatch):
+    """From its second sweep on a handle evaluates the stored orbit representatives (state, orbit size) instead of
+    enumerating its rank range again: same sums as the first (enumerating) sweep, as GWZ_SWEEP_CACHE=0 and as the
+    state-by-state sweep, for several parameters and across shards."""
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=2.0, t=0.7)
+    ans = gw.GutzwillerAnsatz(H)
+    le = gw.LocalEnergyEvaluator(H, ans)
+    first = le.accumulators(0.3)
+    again = [le.accumulators(0.3) for _ in range(3)]  # built at the second call, reused afterwards
+    for a in again:
+        assert np.all(np.abs(a - first) <= 1e-12 * np.abs(first))
+    assert np.array_equal(again[1], again[2])  # sorted representatives: a fixed summation order
+    monkeypatch.setenv("GWZ_SWEEP_CACHE", "0")
+    le0 = gw.LocalEnergyEvaluator(H, ans)
+    monkeypatch.setenv("GWZ_SWEEP_SYM", "0")
+    le_full = gw.LocalEnergyEvaluator(H, ans)
+    for g in (0.0, 0.7, 1.3):
+        a, b = le.accumulators(g), [le0.accumulators(g) for _ in range(2)][-1]
+        monkeypatch.setenv("GWZ_SWEEP_SYM", "0")
+        c = le_full.accumulators(g)
+        monkeypatch.setenv("GWZ_SWEEP_SYM", "1")
+        assert np.all(np.abs(a - b) <= 1e-12 * np.abs(b)) and np.all(np.abs(a - c) <= 1e-12 * np.abs(c))
+    monkeypatch.delenv("GWZ_SWEEP_CACHE")
+    dim = H.model().dimension()
+    if dim >= 50:
+        acc = np.zeros(4)
+        for lo, hi in ((0, dim // 3), (dim // 3, dim - 7), (dim - 7, dim)):
+            h = gw.capi.C.c_void_p()
+            gw.capi.check(gw.lib().gwz_sweep_create(H.model().handle, None, 0, lo, hi, gw.capi.C.byref(h)))
+            v, gr, a4 = gw.capi.C.c_double(), (gw.capi.C.c_double * 1)(), (gw.capi.C.c_double * 4)()
+            p = (gw.capi.C.c_double * 1)(0.3)
+            for _ in range(3):
+                gw.capi.check(gw.lib().gwz_sweep_val_and_grad(h, p, gw.capi.C.byref(v), gr, a4))
+            gw.lib().gwz_sweep_destroy(h)
+            acc += np.array(a4[:])
+        assert np.all(np.abs(acc - first) <= 1e-12 * np.abs(first))
