@@ -1033,47 +1033,102 @@ static bool sweep_sym_enabled() {
     return !(e && e[0] == '0');
 }
 
-// GWZ_SWEEP_CACHE=0: never store the representatives (every sweep enumerates and tests its rank range)
-static int sweep_build_representatives(gwz_sweep* s, const SweepLaunch& L) {
-    gwz_model* m = s->m;
-    gwz_context* c = m->ctx;
-    s->rep_state = -1;
+// ---- symmetric ranked sweeps: which ranks can hold an orbit representative, and the stored representative basis ----
+namespace gwz {
+// An orbit representative carries the largest occupation in mode M, so n_M >= tmin = ceil(N/M): the top tmin bits of
+// the unary string are set.  In rank (= numeric) order those states are the LAST C(B-tmin, N-tmin) ranks: the ranks
+// below cannot hold a representative and are not visited at all.  At commensurate filling the only representative with
+// n_M = tmin is the uniform state |tmin ... tmin>: it is handed over on its own (weight 1, in the shard that holds its
+// rank) and the visited ranks start at n_M >= tmin + 1 (N = M = 16: 26 % of the states).
+RepRange representative_range(const std::vector<uint64_t>& tab, int N, int M, int B, uint64_t rank_begin, uint64_t dim) {
+    RepRange r{rank_begin, dim, 0ull, 0};
+    int tmin = (N + M - 1) / M;
+    const uint64_t total = tab[(size_t)B * 65 + N];
+    if (total == UINT64_MAX) return r;
+    if (tmin * M == N) {
+        uint64_t x = 0, rk = 0;
+        int j = 0;
+        for (int i = 0; i < M; ++i)
+            for (int q = 0; q < tmin; ++q) {
+                const int pos = i * (tmin + 1) + q;
+                x |= 1ull << pos;
+                rk += tab[(size_t)pos * 65 + (++j)];
+            }
+        if (rk >= rank_begin && rk - rank_begin < dim) {
+            r.extra_state = x;
+            r.has_extra = 1;
+        }
+        ++tmin;
+    }
+    const uint64_t tail = tab[(size_t)(B - tmin) * 65 + (N - tmin)];
+    if (tail == UINT64_MAX || tail > total) {
+        r.has_extra = 0;
+        return r;
+    }
+    const uint64_t hi = rank_begin + dim;
+    r.lo = std::min(std::max(rank_begin, total - tail), hi);
+    r.count = hi - r.lo;
+    return r;
+}
+
+// The representatives of a rank range do not depend on the parameters: count them, collect (state, orbit size) pairs
+// and sort them by state.  *nrep = 0 (and null pointers) when they are not worth / not possible to store.
+// GWZ_SWEEP_CACHE=0: never store them (every sweep enumerates and tests its rank range).
+int build_representative_basis(gwz_context* c, int N, int M, int B, const uint64_t* d_binom, const RepRange& r,
+                               uint64_t** d_rep, uint32_t** d_mult, uint64_t* nrep) {
+    *d_rep = nullptr;
+    *d_mult = nullptr;
+    *nrep = 0;
     if (const char* e = std::getenv("GWZ_SWEEP_CACHE"))
         if (e[0] == '0') return GWZ_OK;
+    int grid = 1;
+    uint64_t chunk = 8;
+    GWZ_CUDA(sweep_grid(1, 4, N, M, true, r.count ? r.count : 1, c->prop.multiProcessorCount, &grid, &chunk));
     DevBuf<unsigned long long> d_cnt;
     GWZ_CUDA(d_cnt.alloc(1));
     unsigned long long n = 0;
-    if (L.dim) {
+    if (r.count) {
         GWZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), c->stream));
-        GWZ_LAUNCH(launch_sweep_collect(m->N, m->M, m->B, L.dim, L.rank_begin, L.grid, L.chunk, L.binom, d_cnt.p, nullptr,
-                                        nullptr, c->stream));
+        GWZ_LAUNCH(launch_sweep_collect(N, M, B, r.count, r.lo, grid, chunk, d_binom, d_cnt.p, nullptr, nullptr, c->stream));
         GWZ_CUDA(cudaMemcpyAsync(&n, d_cnt.p, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
         GWZ_CUDA(cudaStreamSynchronize(c->stream));
     }
-    const uint64_t total = n + (L.has_extra ? 1 : 0);
+    const uint64_t total = n + (r.has_extra ? 1 : 0);
     size_t free_b = 0, total_b = 0;
     GWZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // (8 + 4) B per representative, twice during the sort; keep it to a quarter of the free memory
     if (total == 0 || total > 0x7fffffffull || total * 24 > free_b / 4) return GWZ_OK;
-    GWZ_CUDA(cudaMalloc(&s->d_rep, sizeof(uint64_t) * total));
-    GWZ_CUDA(cudaMalloc(&s->d_mult, sizeof(uint32_t) * total));
+    uint64_t* rep = nullptr;
+    uint32_t* mult = nullptr;
+    GWZ_CUDA(cudaMalloc(&rep, sizeof(uint64_t) * total));
+    if (cudaMalloc(&mult, sizeof(uint32_t) * total) != cudaSuccess) {
+        cudaFree(rep);
+        return api_fail(GWZ_ERR_NOMEM, "representative basis: out of device memory");
+    }
+    DevBuf<uint64_t> own_rep;   // released on an error path
+    DevBuf<uint32_t> own_mult;
+    own_rep.p = rep;
+    own_mult.p = mult;
     if (n) {
         GWZ_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), c->stream));
-        GWZ_LAUNCH(launch_sweep_collect(m->N, m->M, m->B, L.dim, L.rank_begin, L.grid, L.chunk, L.binom, d_cnt.p, s->d_rep,
-                                        s->d_mult, c->stream));
+        GWZ_LAUNCH(launch_sweep_collect(N, M, B, r.count, r.lo, grid, chunk, d_binom, d_cnt.p, rep, mult, c->stream));
     }
-    if (L.has_extra) {
+    if (r.has_extra) {
         const uint32_t one = 1u;
-        GWZ_CUDA(cudaMemcpyAsync(s->d_rep + n, &L.extra_state, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-        GWZ_CUDA(cudaMemcpyAsync(s->d_mult + n, &one, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(rep + n, &r.extra_state, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(mult + n, &one, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     }
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     api_count_launch();
-    GWZ_CUDA(sort_representatives(s->d_rep, s->d_mult, total, c->stream));
-    s->nrep = total;
-    s->rep_state = 1;
+    GWZ_CUDA(sort_representatives(rep, mult, total, c->stream));
+    own_rep.p = nullptr;
+    own_mult.p = nullptr;
+    *d_rep = rep;
+    *d_mult = mult;
+    *nrep = total;
     return GWZ_OK;
 }
+}  // namespace gwz
 
 static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     gwz_model* m = s->m;
@@ -1095,51 +1150,28 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     L.grid = s->grid;
     L.chunk = s->chunk;
     int grid = s->grid;
+    RepRange rr{s->rank_begin, s->dim, 0ull, 0};
     if (L.symmetric && s->d_basis == nullptr && m->N + m->M <= 64) {
-        // An orbit representative carries the largest occupation in mode M, so n_M >= tmin = ceil(N/M): the top tmin
-        // bits of the unary string are set.  In rank (= numeric) order those states are the LAST C(B-tmin, N-tmin)
-        // ranks: the ranks below cannot hold a representative and are not visited at all.
-        const std::vector<uint64_t>& tab = s->h_binom;
-        int tmin = (m->N + m->M - 1) / m->M;
-        const uint64_t total = tab[m->B * 65 + m->N];
-        if (tmin * m->M == m->N && total != UINT64_MAX) {
-            // commensurate filling: the only representative with n_M = tmin is the uniform state |tmin ... tmin>.  It is
-            // handed to the kernel on its own (weight 1, in the shard that holds its rank) and the visited ranks start at
-            // n_M >= tmin + 1 (N = M = 16: 26 % of the states instead of 52 %).
-            uint64_t x = 0, r = 0;
-            int j = 0;
-            for (int i = 0; i < m->M; ++i)
-                for (int q = 0; q < tmin; ++q) {
-                    const int pos = i * (tmin + 1) + q;
-                    x |= 1ull << pos;
-                    r += tab[pos * 65 + (++j)];
-                }
-            if (r >= s->rank_begin && r - s->rank_begin < s->dim) {
-                L.extra_state = x;
-                L.has_extra = 1;
-            }
-            ++tmin;
-        }
-        const uint64_t tail = tab[(m->B - tmin) * 65 + (m->N - tmin)];
-        if (total != UINT64_MAX && tail != UINT64_MAX && tail <= total) {
-            const uint64_t hi = s->rank_begin + s->dim;
-            const uint64_t lo = std::min(std::max(s->rank_begin, total - tail), hi);
-            L.rank_begin = lo;
-            L.dim = hi - lo;
-            uint64_t chunk = 1;
-            GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, true, L.dim ? L.dim : 1, c->prop.multiProcessorCount, &grid, &chunk));
-            if (grid <= s->grid) {
-                L.grid = grid;
-                L.chunk = chunk;
-            } else {  // cannot happen (fewer ranks never need more CTAs); keep the partials buffer safe anyway
-                grid = s->grid;
-                L.chunk = (L.dim + (uint64_t)grid * SWEEP_BLOCK - 1) / ((uint64_t)grid * SWEEP_BLOCK) + 1;
-            }
+        rr = representative_range(s->h_binom, m->N, m->M, m->B, s->rank_begin, s->dim);
+        L.rank_begin = rr.lo;
+        L.dim = rr.count;
+        L.extra_state = rr.extra_state;
+        L.has_extra = rr.has_extra;
+        uint64_t chunk = 1;
+        GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, true, L.dim ? L.dim : 1, c->prop.multiProcessorCount, &grid, &chunk));
+        if (grid <= s->grid) {
+            L.grid = grid;
+            L.chunk = chunk;
+        } else {  // cannot happen (fewer ranks never need more CTAs); keep the partials buffer safe anyway
+            grid = s->grid;
+            L.chunk = (L.dim + (uint64_t)grid * SWEEP_BLOCK - 1) / ((uint64_t)grid * SWEEP_BLOCK) + 1;
         }
     }
     const bool sym_ranked = L.symmetric && s->d_basis == nullptr && m->N + m->M <= 64;
     if (sym_ranked && s->rep_state == 0 && ++s->sym_calls >= 2) {
-        if (int rc = sweep_build_representatives(s, L)) return rc;
+        s->rep_state = -1;
+        if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep)) return rc;
+        if (s->nrep) s->rep_state = 1;
     }
     if (sym_ranked && s->rep_state == 1) {
         // later sweeps of the same handle: evaluate the stored representatives, weighted with their orbit sizes

@@ -52,6 +52,13 @@ struct gwz_gsweep {
     double* d_vec = nullptr;
     double* h_vec = nullptr;
     float last_ms = 0.f;
+    // ranked sweeps of an ansatz that is invariant under translations and reflection of the chain: the orbit
+    // representatives (state, orbit size) are stored at the second sweep of a handle and evaluated from then on
+    std::vector<uint64_t> h_binom;
+    uint64_t* d_rep = nullptr;
+    uint32_t* d_mult = nullptr;
+    uint64_t nrep = 0, calls = 0;
+    int rep_state = 0;  // 0 not built, 1 built, -1 not applicable / not cacheable
 };
 
 // ------------------------------------------------------------------------------------------
@@ -654,6 +661,7 @@ extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uin
         GWZ_CUDA(cudaMemcpy(s->d_binom, tab.data(), sizeof(uint64_t) * tab.size(), cudaMemcpyHostToDevice));
         s->dim = rank_end - rank_begin;
         s->rank_begin = rank_begin;
+        s->h_binom = std::move(tab);
     }
     const int L = 2 + 2 * a->P;
     GWZ_CUDA(cudaMalloc(&s->d_vec, sizeof(double) * L));
@@ -667,6 +675,8 @@ extern "C" int gwz_gsweep_destroy(gwz_gsweep* s) {
         if (s->d_basis) cudaFree(s->d_basis);
         if (s->d_binom) cudaFree(s->d_binom);
         if (s->d_partials) cudaFree(s->d_partials);
+        cudaFree(s->d_rep);
+        cudaFree(s->d_mult);
         cudaFree(s->d_vec);
         if (s->h_vec) cudaFreeHost(s->h_vec);
     }
@@ -690,9 +700,23 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     GenCombo cb;
     bool combo = false;
     if (int rc = prepare_params(a, params, &K.gm, &cb, &combo)) return rc;
+    // Gutzwiller, ExtendedGutzwiller, Multinomial and RelativeJastrow amplitudes and features only depend on the
+    // occupations up to translations and reflection of the periodic chain: one representative per orbit suffices
+    gwz_model* m = a->m;
+    const bool invariant = !combo && s->d_basis == nullptr && m->N + m->M <= 64 &&
+                           (K.gm.kind == GEN_GUTZWILLER || K.gm.kind == GEN_EXT_GUTZWILLER ||
+                            K.gm.kind == GEN_MULTINOMIAL || K.gm.kind == GEN_RELATIVE_JASTROW);
+    if (invariant && s->rep_state == 0 && ++s->calls >= 2) {
+        s->rep_state = -1;
+        const RepRange rr = representative_range(s->h_binom, m->N, m->M, m->B, s->rank_begin, s->dim);
+        if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep)) return rc;
+        if (s->nrep) s->rep_state = 1;
+    }
+    const bool reps = invariant && s->rep_state == 1;
+    const uint64_t ndim = reps ? s->nrep : s->dim;
     int grid = 0, per_cta = 1;
-    if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)s->dim, c->prop.multiProcessorCount, &grid));
-    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)s->dim, c->prop.multiProcessorCount, &grid, &per_cta));
+    if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)ndim, c->prop.multiProcessorCount, &grid));
+    else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)ndim, c->prop.multiProcessorCount, &grid, &per_cta));
     const size_t rows = (size_t)grid * per_cta;
     if (rows > s->partials_rows) {
         if (s->d_partials) cudaFree(s->d_partials);
@@ -700,11 +724,12 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
         GWZ_CUDA(cudaMalloc(&s->d_partials, sizeof(double) * rows * L));
         s->partials_rows = rows;
     }
-    K.basis = s->d_basis;
-    K.dim = s->dim;
-    K.rank_begin = s->rank_begin;
+    K.basis = reps ? s->d_rep : s->d_basis;
+    K.dim = ndim;
+    K.rank_begin = reps ? 0 : s->rank_begin;
     K.binom = s->d_binom;
-    K.chunk = (s->dim + rows - 1) / rows;
+    K.weight = reps ? s->d_mult : nullptr;
+    K.chunk = (ndim + rows - 1) / rows;
     K.with_grad = grad ? 1 : 0;
     K.partials = s->d_partials;
     K.grid = grid;

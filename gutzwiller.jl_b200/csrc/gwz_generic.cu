@@ -378,7 +378,8 @@ template <int G, int PPL>
 __global__ void __launch_bounds__(GEN_BLOCK)
 gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin,
                  const uint64_t* __restrict__ binom, uint64_t chunk, int with_grad, double* __restrict__ partials,
-                 double* __restrict__ terms_out, uint64_t* __restrict__ states_out, uint64_t first, uint64_t count) {
+                 double* __restrict__ terms_out, uint64_t* __restrict__ states_out, uint64_t first, uint64_t count,
+                 const uint32_t* __restrict__ weight /* stored mode, optional: orbit sizes of a representative basis */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GROUPS = 32 / G;
     const int lane = threadIdx.x & (G - 1), group = (threadIdx.x & 31) / G;
@@ -425,14 +426,16 @@ gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
         const double eloc = D - gm.t * Etot;
         const double psi2 = exp(-2.0 * gen_phi<G>(gm, ws, lane, lgsum));
         const double s_num = psi2 * eloc;
+        double wgt = 1.0;
         if (per_state) {
             if (terms_out && live && lane == 0) {
                 terms_out[(sidx - first) * (uint64_t)(2 + 2 * P)] = s_num;
                 terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 1] = psi2;
             }
         } else if (live) {
-            num += s_num;
-            den += psi2;
+            wgt = weight ? (double)weight[sidx] : 1.0;
+            num = fma(wgt, s_num, num);
+            den = fma(wgt, psi2, den);
         }
         if (with_grad) {
 #pragma unroll
@@ -457,8 +460,8 @@ gen_sweep_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
                             terms_out[(sidx - first) * (uint64_t)(2 + 2 * P) + 2 + P + p] = s_dg;
                         }
                     } else if (live) {
-                        ng[q] += s_ng;
-                        dg[q] += s_dg;
+                        ng[q] = fma(wgt, s_ng, ng[q]);
+                        dg[q] = fma(wgt, s_dg, dg[q]);
                     }
                 }
             }
@@ -630,7 +633,7 @@ static cudaError_t gen_sweep_do(const GenSweepOp& op) {
     }
     const GenSweepLaunch& L = *op.L;
     gen_sweep_kernel<G, PPL><<<L.grid, GEN_BLOCK, smem, op.s>>>(g, L.basis, L.dim, L.rank_begin, L.binom, L.chunk, L.with_grad,
-                                                               L.partials, L.terms_out, L.states_out, L.first, L.count);
+                                                               L.partials, L.terms_out, L.states_out, L.first, L.count, L.weight);
     return cudaGetLastError();
 }
 template <int G>

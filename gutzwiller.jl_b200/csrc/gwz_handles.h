@@ -14,6 +14,18 @@ int api_fail(int code, const std::string& msg);   // records the thread-local me
 void api_count_launch();                           // every kernel launch of the library is counted
 int api_check_err_flag(gwz_context* c);            // "Infinite residence time" (qmc.jl:34-36)
 void binomial_table(std::vector<uint64_t>& tab);   // [65][65], saturating
+// symmetric ranked sweeps (gwz_api.cu): the rank sub-range that can hold orbit representatives, and their stored basis
+struct RepRange {
+    uint64_t lo, count;      // ranks [lo, lo + count) are visited
+    uint64_t extra_state;    // the uniform state at commensurate filling, evaluated with weight 1 ...
+    int has_extra;           // ... if its rank lies in the caller's range
+};
+RepRange representative_range(const std::vector<uint64_t>& binom, int N, int M, int B, uint64_t rank_begin, uint64_t dim);
+}  // namespace gwz
+struct gwz_context;
+namespace gwz {
+int build_representative_basis(gwz_context* c, int N, int M, int B, const uint64_t* d_binom, const RepRange& r,
+                               uint64_t** d_rep, uint32_t** d_mult, uint64_t* nrep);
 }  // namespace gwz
 
 #define GWZ_CUDA(expr)                                                                              \

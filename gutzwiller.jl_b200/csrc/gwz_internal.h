@@ -175,6 +175,7 @@ struct GenSweepLaunch {
     uint64_t* states_out;
     uint64_t first, count;
     int grid;
+    const uint32_t* weight;  // stored mode, optional: orbit sizes of a representative basis
 };
 int gen_ppl(int P);  // parameter slots per lane (1, 2, 4, 8), 0 if P > 256
 int gen_group(int M, int P);  // lanes per walker of the walker kernel (8, 16 or 32)

@@ -333,3 +333,29 @@ def test_collect_to_vec_and_vector_ansatz_round_trip(gw):
         rq = gw.LocalEnergyEvaluator(H, gw.VectorAnsatz((addrs, vals)))([])
         le = gw.LocalEnergyEvaluator(H, ans)(p)
         assert abs(rq - le) < 1e-11 * abs(le)
+
+
+@pytest.mark.parametrize("cls,N,M,v", [("RelativeJastrowAnsatz", 8, 8, 0.0), ("GenericGutzwillerAnsatz", 6, 9, 0.5),
+                                       ("ExtendedGutzwillerAnsatz", 7, 5, 0.4), ("MultinomialAnsatz", 10, 4, 0.0),
+                                       ("DensityProfileAnsatz", 6, 6, 0.0), ("JastrowAnsatz", 5, 5, 0.0)])
+def test_generic_sweep_representative_basis(gw, cls, N, M, v, monkeypatch):
+    """Ansaetze that are invariant under translations and reflection of the chain sweep a stored representative basis
+    (orbit-size weights) from the second call of a handle on; the others keep the state-by-state sweep.  Values and
+    gradients must not depend on it."""
+    H = gw.ExtendedHubbardReal1D(gw.near_uniform(N, M), u=2.0, v=v, t=0.8) if v else gw.HubbardReal1D(gw.near_uniform(N, M), u=2.0, t=0.8)
+    ans = getattr(gw, cls)(H)
+    rng = np.random.default_rng(4)
+    p = 0.2 * rng.random(ans.N_PARAMS) + 0.05
+    monkeypatch.setenv("GWZ_SWEEP_CACHE", "0")
+    ref = gw.LocalEnergyEvaluator(H, ans)
+    v0, g0 = [ref.val_and_grad(p) for _ in range(2)][-1]
+    monkeypatch.delenv("GWZ_SWEEP_CACHE")
+    le = gw.LocalEnergyEvaluator(H, ans)
+    outs = [le.val_and_grad(p) for _ in range(4)]
+    for v1, g1 in outs:
+        assert abs(v1 - v0) <= 1e-12 * abs(v0) and np.allclose(g1, g0, rtol=1e-10, atol=1e-12 * max(1.0, np.abs(g0).max()))
+    assert outs[2][0] == outs[3][0] and np.array_equal(outs[2][1], outs[3][1])
+    q = p * 1.3
+    a, b = le.val_and_grad(q), ref.val_and_grad(q)
+    assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and np.allclose(a[1], b[1], rtol=1e-10, atol=1e-12 * max(1.0, np.abs(b[1]).max()))
+    assert abs(le(q) - b[0]) <= 1e-12 * abs(b[0])
