@@ -351,7 +351,15 @@ def extra_workloads(gw, np):
             v, g = le.val_and_grad(1.0)
         dt = (time.perf_counter() - t0) / reps
         out[f"cfg2_sweep_bose{n}"] = {"states": le.dim, "states_per_s": le.dim / dt, "ms_per_sweep": dt * 1e3,
-                                      "kernel_ms": le.last_kernel_ms(), "val": v, "grad": float(g[0])}
+                                      "kernel_ms": le.last_kernel_ms(), "val": v, "grad": float(g[0]),
+                                      "note": "repeated sweeps of one LocalEnergyEvaluator evaluate its stored orbit "
+                                              "representatives (about dim/2M states, weighted with the orbit sizes); "
+                                              "states_per_s counts all states of the space"}
+        le1 = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H))  # a fresh handle: its first sweep enumerates the ranks
+        t0 = time.perf_counter()
+        le1.val_and_grad(1.0)
+        out[f"cfg2_sweep_bose{n}"]["first_sweep_ms"] = (time.perf_counter() - t0) * 1e3
+        out[f"cfg2_sweep_bose{n}"]["first_sweep_kernel_ms"] = le1.last_kernel_ms()
     # ansatz-generic engine: RelativeJastrowAnsatz, 25 parameters, BoseFS{50,50}
     H = gw.HubbardReal1D(gw.near_uniform(50, 50), u=2.0)
     ans = gw.RelativeJastrowAnsatz(H)
