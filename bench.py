@@ -343,7 +343,7 @@ def extra_workloads(gw, np):
     for n in (12, 16):
         H = gw.HubbardReal1D(gw.near_uniform(n, n), u=2.0)
         le = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H))
-        for _ in range(3):
+        for _ in range(64 if n == 12 else 12):  # past the call at which the handle stores its representative basis
             le.val_and_grad(1.0)
         reps = 50 if n == 12 else 5
         t0 = time.perf_counter()

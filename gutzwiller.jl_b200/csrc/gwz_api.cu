@@ -112,7 +112,7 @@ struct gwz_sweep {
     uint32_t* d_mult = nullptr;
     uint64_t nrep = 0;
     int rep_state = 0;                 // 0 not built, 1 built, -1 not cacheable (too large / disabled)
-    uint64_t sym_calls = 0;
+    uint64_t sym_calls = 0, build_at = 2;  // build_at: the sweep at which storing the representatives has paid off
     bool ms_pending = false;           // ev0/ev1 hold the last sweep's kernel time, not read yet
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<uint64_t> h_binom;     // host copy of the binomial table (ranked mode)
@@ -1168,7 +1168,7 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
         }
     }
     const bool sym_ranked = L.symmetric && s->d_basis == nullptr && m->N + m->M <= 64;
-    if (sym_ranked && s->rep_state == 0 && ++s->sym_calls >= 2) {
+    if (sym_ranked && s->rep_state == 0 && ++s->sym_calls >= s->build_at && s->sym_calls >= 2) {
         s->rep_state = -1;
         if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep)) return rc;
         if (s->nrep) s->rep_state = 1;
@@ -1205,6 +1205,17 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     s->ms_pending = true;  // cudaEventElapsedTime costs 5 us: only when gwz_sweep_last_kernel_ms asks (a small sweep is 60 us)
+    if (sym_ranked && s->rep_state == 0 && s->sym_calls == 1) {
+        // rent or buy: storing the representatives costs about 1 ms (allocations, sort) + three enumeration passes and
+        // then saves about 70 % of an enumerating sweep per call; do it once the sweeps so far would have paid for it
+        float t = 0.f;
+        GWZ_CUDA(cudaEventElapsedTime(&t, s->ev0, s->ev1));
+        s->last_ms = t;
+        s->ms_pending = false;
+        const double T = std::max((double)t, 1e-3);
+        s->build_at = (uint64_t)std::ceil((1.0 + 3.0 * T) / (0.7 * T));
+        if (const char* e = std::getenv("GWZ_SWEEP_CACHE_AT")) s->build_at = (uint64_t)std::max(2, std::atoi(e));
+    }
     for (int i = 0; i < 4; ++i) acc4[i] = c->h_acc[i];
     return GWZ_OK;
 }

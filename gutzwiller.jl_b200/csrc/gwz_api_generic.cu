@@ -3,7 +3,9 @@
 // Host-side orchestration only: the parameter-dependent tables of the log-linear form
 // (Q, b, hop constants; O(M^2) doubles per call), HBM buffers, launches, the NCCL all-reduce of the
 // accumulator vector.  No sampled or swept quantity is computed on the host.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -57,7 +59,7 @@ struct gwz_gsweep {
     std::vector<uint64_t> h_binom;
     uint64_t* d_rep = nullptr;
     uint32_t* d_mult = nullptr;
-    uint64_t nrep = 0, calls = 0;
+    uint64_t nrep = 0, calls = 0, build_at = 2;
     int rep_state = 0;  // 0 not built, 1 built, -1 not applicable / not cacheable
 };
 
@@ -706,7 +708,7 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     const bool invariant = !combo && s->d_basis == nullptr && m->N + m->M <= 64 &&
                            (K.gm.kind == GEN_GUTZWILLER || K.gm.kind == GEN_EXT_GUTZWILLER ||
                             K.gm.kind == GEN_MULTINOMIAL || K.gm.kind == GEN_RELATIVE_JASTROW);
-    if (invariant && s->rep_state == 0 && ++s->calls >= 2) {
+    if (invariant && s->rep_state == 0 && ++s->calls >= s->build_at && s->calls >= 2) {
         s->rep_state = -1;
         const RepRange rr = representative_range(s->h_binom, m->N, m->M, m->B, s->rank_begin, s->dim);
         if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep)) return rc;
@@ -747,6 +749,11 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     GWZ_CUDA(cudaMemcpyAsync(s->h_vec, s->d_vec, sizeof(double) * L, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     GWZ_CUDA(cudaEventElapsedTime(&s->last_ms, c->ev0, c->ev1));
+    if (invariant && s->rep_state == 0 && s->calls == 1) {  // rent or buy, as in gwz_sweep (gwz_api.cu)
+        const double T = std::max((double)s->last_ms, 1e-3);
+        s->build_at = (uint64_t)std::ceil((1.0 + 0.3 * T) / (0.7 * T));
+        if (const char* e = std::getenv("GWZ_SWEEP_CACHE_AT")) s->build_at = (uint64_t)std::max(2, std::atoi(e));
+    }
     const double num = s->h_vec[0], den = s->h_vec[1];
     *val = num / den;  // localenergy.jl:124-128
     if (grad)

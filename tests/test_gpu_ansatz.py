@@ -346,6 +346,7 @@ def test_generic_sweep_representative_basis(gw, cls, N, M, v, monkeypatch):
     ans = getattr(gw, cls)(H)
     rng = np.random.default_rng(4)
     p = 0.2 * rng.random(ans.N_PARAMS) + 0.05
+    monkeypatch.setenv("GWZ_SWEEP_CACHE_AT", "2")
     monkeypatch.setenv("GWZ_SWEEP_CACHE", "0")
     ref = gw.LocalEnergyEvaluator(H, ans)
     v0, g0 = [ref.val_and_grad(p) for _ in range(2)][-1]

@@ -187,6 +187,7 @@ def test_orbit_reduced_sweep_equals_full_sweep(gw, N, M, monkeypatch):
     """Ranked sweeps evaluate one representative per translation orbit (weight = orbit size, including orbits with a
     non-trivial stabiliser such as |2 0 2 0>); the four sums must agree with the state-by-state sweep, also when the
     rank range is cut into shards at arbitrary places."""
+    monkeypatch.setenv("GWZ_SWEEP_CACHE_AT", "2")
     H = gw.HubbardReal1D(gw.near_uniform(N, M), u=2.0, t=0.7)
     ans = gw.GutzwillerAnsatz(H)
     out = {}
@@ -228,6 +229,7 @@ def test_cached_representative_basis_gives_the_same_sums(gw, N, M, monkeypatch):
     """From its second sweep on a handle evaluates the stored orbit representatives (state, orbit size) instead of
     enumerating its rank range again: same sums as the first (enumerating) sweep, as GWZ_SWEEP_CACHE=0 and as the
     state-by-state sweep, for several parameters and across shards."""
+    monkeypatch.setenv("GWZ_SWEEP_CACHE_AT", "2")  # default: when the sweeps so far would have paid for it
     H = gw.HubbardReal1D(gw.near_uniform(N, M), u=2.0, t=0.7)
     ans = gw.GutzwillerAnsatz(H)
     le = gw.LocalEnergyEvaluator(H, ans)
