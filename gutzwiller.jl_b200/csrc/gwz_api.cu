@@ -112,7 +112,8 @@ struct gwz_sweep {
     uint32_t* d_mult = nullptr;
     uint64_t nrep = 0;
     int rep_state = 0;                 // 0 not built, 1 built, -1 not cacheable (too large / disabled)
-    uint64_t sym_calls = 0, build_at = 2;  // build_at: the sweep at which storing the representatives has paid off
+    uint64_t sym_calls = 0, build_at = 3;  // build_at: the sweep at which storing the representatives has paid off
+    float t_enum = 0.f;                    // kernel time of an enumerating sweep (faster of the first two)
     bool ms_pending = false;           // ev0/ev1 hold the last sweep's kernel time, not read yet
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<uint64_t> h_binom;     // host copy of the binomial table (ranked mode)
@@ -1072,13 +1073,15 @@ RepRange representative_range(const std::vector<uint64_t>& tab, int N, int M, in
 }
 
 // The representatives of a rank range do not depend on the parameters: count them, collect (state, orbit size) pairs
-// and sort them by state.  *nrep = 0 (and null pointers) when they are not worth / not possible to store.
+// and sort them by state.  *stored = 0 when they are not worth / not possible to store (*stored = 1 with *nrep = 0:
+// the range holds no representative).
 // GWZ_SWEEP_CACHE=0: never store them (every sweep enumerates and tests its rank range).
 int build_representative_basis(gwz_context* c, int N, int M, int B, const uint64_t* d_binom, const RepRange& r,
-                               uint64_t** d_rep, uint32_t** d_mult, uint64_t* nrep) {
+                               uint64_t** d_rep, uint32_t** d_mult, uint64_t* nrep, int* stored) {
     *d_rep = nullptr;
     *d_mult = nullptr;
     *nrep = 0;
+    *stored = 0;
     if (const char* e = std::getenv("GWZ_SWEEP_CACHE"))
         if (e[0] == '0') return GWZ_OK;
     int grid = 1;
@@ -1097,7 +1100,11 @@ int build_representative_basis(gwz_context* c, int N, int M, int B, const uint64
     size_t free_b = 0, total_b = 0;
     GWZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
     // (8 + 4) B per representative, twice during the sort; keep it to a quarter of the free memory
-    if (total == 0 || total > 0x7fffffffull || total * 24 > free_b / 4) return GWZ_OK;
+    if (total == 0) {  // a rank range without representatives: stored, and empty
+        *stored = 1;
+        return GWZ_OK;
+    }
+    if (total > 0x7fffffffull || total * 24 > free_b / 4) return GWZ_OK;
     uint64_t* rep = nullptr;
     uint32_t* mult = nullptr;
     GWZ_CUDA(cudaMalloc(&rep, sizeof(uint64_t) * total));
@@ -1126,6 +1133,7 @@ int build_representative_basis(gwz_context* c, int N, int M, int B, const uint64
     *d_rep = rep;
     *d_mult = mult;
     *nrep = total;
+    *stored = 1;
     return GWZ_OK;
 }
 }  // namespace gwz
@@ -1170,8 +1178,10 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     const bool sym_ranked = L.symmetric && s->d_basis == nullptr && m->N + m->M <= 64;
     if (sym_ranked && s->rep_state == 0 && ++s->sym_calls >= s->build_at && s->sym_calls >= 2) {
         s->rep_state = -1;
-        if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep)) return rc;
-        if (s->nrep) s->rep_state = 1;
+        int stored = 0;
+        if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep, &stored))
+            return rc;
+        if (stored && s->nrep) s->rep_state = 1;  // otherwise every sweep keeps enumerating (same sums either way)
     }
     if (sym_ranked && s->rep_state == 1) {
         // later sweeps of the same handle: evaluate the stored representatives, weighted with their orbit sizes
@@ -1205,15 +1215,17 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
     GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     s->ms_pending = true;  // cudaEventElapsedTime costs 5 us: only when gwz_sweep_last_kernel_ms asks (a small sweep is 60 us)
-    if (sym_ranked && s->rep_state == 0 && s->sym_calls == 1) {
+    if (sym_ranked && s->rep_state == 0 && s->sym_calls <= 2) {
         // rent or buy: storing the representatives costs about 1 ms (allocations, sort) + three enumeration passes and
-        // then saves about 70 % of an enumerating sweep per call; do it once the sweeps so far would have paid for it
+        // then saves about 70 % of an enumerating sweep per call; do it once the sweeps so far would have paid for it.
+        // The sweep time is taken from the faster of the first two calls (the first one may include lazy loading).
         float t = 0.f;
         GWZ_CUDA(cudaEventElapsedTime(&t, s->ev0, s->ev1));
         s->last_ms = t;
         s->ms_pending = false;
-        const double T = std::max((double)t, 1e-3);
-        s->build_at = (uint64_t)std::ceil((1.0 + 3.0 * T) / (0.7 * T));
+        s->t_enum = s->sym_calls == 1 ? t : std::min(s->t_enum, t);
+        const double T = std::max((double)s->t_enum, 1e-3);
+        s->build_at = s->sym_calls == 1 ? 3 : std::max<uint64_t>(3, (uint64_t)std::ceil((1.0 + 3.0 * T) / (0.7 * T)));
         if (const char* e = std::getenv("GWZ_SWEEP_CACHE_AT")) s->build_at = (uint64_t)std::max(2, std::atoi(e));
     }
     for (int i = 0; i < 4; ++i) acc4[i] = c->h_acc[i];

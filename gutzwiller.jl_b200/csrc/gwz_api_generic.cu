@@ -59,7 +59,8 @@ struct gwz_gsweep {
     std::vector<uint64_t> h_binom;
     uint64_t* d_rep = nullptr;
     uint32_t* d_mult = nullptr;
-    uint64_t nrep = 0, calls = 0, build_at = 2;
+    uint64_t nrep = 0, calls = 0, build_at = 3;
+    float t_enum = 0.f;
     int rep_state = 0;  // 0 not built, 1 built, -1 not applicable / not cacheable
 };
 
@@ -705,17 +706,60 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     // Gutzwiller, ExtendedGutzwiller, Multinomial and RelativeJastrow amplitudes and features only depend on the
     // occupations up to translations and reflection of the periodic chain: one representative per orbit suffices
     gwz_model* m = a->m;
-    const bool invariant = !combo && s->d_basis == nullptr && m->N + m->M <= 64 &&
+    // (a handle that sweeps part of the rank range on its own keeps counting single states: its partial sums must
+    // mean the same at every call; with a communicator only the all-reduced total is visible)
+    const bool whole = c->comm != nullptr ||
+                       (s->rank_begin == 0 && !s->h_binom.empty() && s->dim == s->h_binom[(size_t)m->B * 65 + m->N]);
+    const bool invariant = whole && !combo && s->d_basis == nullptr && m->N + m->M <= 64 &&
                            (K.gm.kind == GEN_GUTZWILLER || K.gm.kind == GEN_EXT_GUTZWILLER ||
                             K.gm.kind == GEN_MULTINOMIAL || K.gm.kind == GEN_RELATIVE_JASTROW);
+    // Unlike the Gutzwiller sweep (which counts orbits in every mode), this sweep counts single states until the
+    // representatives are stored: ranks sharing a communicator must switch together -- at a fixed call, and only if
+    // every one of them could store its share.
+    if (c->comm) s->build_at = 3;
     if (invariant && s->rep_state == 0 && ++s->calls >= s->build_at && s->calls >= 2) {
         s->rep_state = -1;
         const RepRange rr = representative_range(s->h_binom, m->N, m->M, m->B, s->rank_begin, s->dim);
-        if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep)) return rc;
-        if (s->nrep) s->rep_state = 1;
+        int stored = 0;
+        if (int rc = build_representative_basis(c, m->N, m->M, m->B, s->d_binom, rr, &s->d_rep, &s->d_mult, &s->nrep, &stored))
+            return rc;
+        double failed = stored ? 0.0 : 1.0;  // summed over the ranks
+        if (c->comm) {
+            const NcclApi* api = nccl_api(nullptr);
+            if (!api) return api_fail(GWZ_ERR_NCCL, "NCCL unavailable");
+            GWZ_CUDA(cudaMemcpyAsync(s->d_vec, &failed, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            GWZ_NCCL(api, api->AllReduce(s->d_vec, s->d_vec, 1, kNcclFloat64, kNcclSum, c->comm, c->stream));
+            GWZ_CUDA(cudaMemcpyAsync(&failed, s->d_vec, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            GWZ_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        if (failed < 0.5) {
+            s->rep_state = 1;  // possibly with nrep == 0: this rank's range holds no representative
+        } else {
+            cudaFree(s->d_rep);
+            cudaFree(s->d_mult);
+            s->d_rep = nullptr;
+            s->d_mult = nullptr;
+            s->nrep = 0;
+        }
     }
     const bool reps = invariant && s->rep_state == 1;
     const uint64_t ndim = reps ? s->nrep : s->dim;
+    if (reps && ndim == 0) {  // this rank's range holds no representative: it contributes zeros to the all-reduce
+        GWZ_CUDA(cudaMemsetAsync(s->d_vec, 0, sizeof(double) * L, c->stream));
+        if (c->comm) {
+            const NcclApi* api = nccl_api(nullptr);
+            if (!api) return api_fail(GWZ_ERR_NCCL, "NCCL unavailable");
+            GWZ_NCCL(api, api->AllReduce(s->d_vec, s->d_vec, L, kNcclFloat64, kNcclSum, c->comm, c->stream));
+        }
+        GWZ_CUDA(cudaMemcpyAsync(s->h_vec, s->d_vec, sizeof(double) * L, cudaMemcpyDeviceToHost, c->stream));
+        GWZ_CUDA(cudaStreamSynchronize(c->stream));
+        s->last_ms = 0.f;
+        const double num0 = s->h_vec[0], den0 = s->h_vec[1];
+        *val = num0 / den0;
+        if (grad)
+            for (int p = 0; p < P; ++p) grad[p] = (s->h_vec[2 + p] * den0 - num0 * s->h_vec[2 + P + p]) / (den0 * den0);
+        return GWZ_OK;
+    }
     int grid = 0, per_cta = 1;
     if (combo) GWZ_CUDA(combo_sweep_grid(cb, (size_t)ndim, c->prop.multiProcessorCount, &grid));
     else GWZ_CUDA(gen_sweep_grid(K.gm, (size_t)ndim, c->prop.multiProcessorCount, &grid, &per_cta));
@@ -749,9 +793,10 @@ extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, doub
     GWZ_CUDA(cudaMemcpyAsync(s->h_vec, s->d_vec, sizeof(double) * L, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     GWZ_CUDA(cudaEventElapsedTime(&s->last_ms, c->ev0, c->ev1));
-    if (invariant && s->rep_state == 0 && s->calls == 1) {  // rent or buy, as in gwz_sweep (gwz_api.cu)
-        const double T = std::max((double)s->last_ms, 1e-3);
-        s->build_at = (uint64_t)std::ceil((1.0 + 0.3 * T) / (0.7 * T));
+    if (invariant && s->rep_state == 0 && s->calls <= 2 && !c->comm) {  // rent or buy, as in gwz_sweep (gwz_api.cu)
+        s->t_enum = s->calls == 1 ? s->last_ms : std::min(s->t_enum, s->last_ms);
+        const double T = std::max((double)s->t_enum, 1e-3);
+        s->build_at = s->calls == 1 ? 3 : std::max<uint64_t>(3, (uint64_t)std::ceil((1.0 + 0.3 * T) / (0.7 * T)));
         if (const char* e = std::getenv("GWZ_SWEEP_CACHE_AT")) s->build_at = (uint64_t)std::max(2, std::atoi(e));
     }
     const double num = s->h_vec[0], den = s->h_vec[1];

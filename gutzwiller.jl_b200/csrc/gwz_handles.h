@@ -25,7 +25,7 @@ RepRange representative_range(const std::vector<uint64_t>& binom, int N, int M, 
 struct gwz_context;
 namespace gwz {
 int build_representative_basis(gwz_context* c, int N, int M, int B, const uint64_t* d_binom, const RepRange& r,
-                               uint64_t** d_rep, uint32_t** d_mult, uint64_t* nrep);
+                               uint64_t** d_rep, uint32_t** d_mult, uint64_t* nrep, int* stored);
 }  // namespace gwz
 
 #define GWZ_CUDA(expr)                                                                              \

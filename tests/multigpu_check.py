@@ -15,6 +15,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("GWZ_SWEEP_CACHE_AT", "2")  # store the representative basis at the second sweep of a handle
 import gutzwiller_b200 as gw  # noqa: E402
 
 N, M, U, G, TOTAL, STEPS = 50, 50, 2.0, 0.5, 1 << 16, 200
@@ -57,7 +58,12 @@ def check_generic(rank, world):
     H8 = gw.HubbardReal1D(gw.near_uniform(8, 8), u=U)
     a8 = gw.RelativeJastrowAnsatz(H8)
     p8 = np.array([0.3, 0.05, 0.02, 0.01])
-    v, g = gw.LocalEnergyEvaluator(H8, a8).val_and_grad(p8)           # rank-range shards + all-reduce
+    le8 = gw.LocalEnergyEvaluator(H8, a8)
+    v, g = le8.val_and_grad(p8)           # rank-range shards + all-reduce
+    for _ in range(3):
+        v2, g2 = le8.val_and_grad(p8)     # shard-wise representative basis
+        ev, eg = abs(v2 - v) / abs(v), np.abs(g2 - g).max() / np.abs(g).max()
+        assert ev <= 1e-12 and eg <= 1e-9, (rank, ev, eg, v, v2, g, g2)
     v1, g1 = gw.LocalEnergyEvaluator(H8, a8, ctx=ctx).val_and_grad(p8)  # one device, whole range
     assert abs(v - v1) <= 1e-12 * abs(v1) and np.all(np.abs(g - g1) <= 1e-11 * np.abs(g1).max())
     print(f"[rank {rank}/{world}] generic OK val={r.val:.12f} grad0={r.grad[0]:.9f} sweep={v:.12f}", flush=True)
@@ -113,7 +119,11 @@ def main():
     H = gw.HubbardReal1D(gw.near_uniform(N, M), u=U)
     res = gw.kinetic_vqmc(H, gw.GutzwillerAnsatz(H), [G], walkers=TOTAL, steps=STEPS, seed=123, record=False)
     H12 = gw.HubbardReal1D(gw.near_uniform(12, 12), u=U)
-    acc = gw.LocalEnergyEvaluator(H12, gw.GutzwillerAnsatz(H12)).accumulators(0.4)  # rank-range shards + all-reduce
+    le12 = gw.LocalEnergyEvaluator(H12, gw.GutzwillerAnsatz(H12))
+    acc = le12.accumulators(0.4)  # rank-range shards + all-reduce
+    for _ in range(3):  # later sweeps run over each shard's stored representative basis (GWZ_SWEEP_CACHE_AT=2 below)
+        again = le12.accumulators(0.4)
+        assert np.all(np.abs(again - acc) <= 1e-12 * np.abs(acc)), (again, acc)
     ref, ref_acc = reference_single_gpu(int(os.environ.get("LOCAL_RANK", "0")))
     check(res.last, ref, acc, ref_acc, f"rank {rank}/{world}")
     check_generic(rank, world)

@@ -26,10 +26,12 @@ def test_readme_values(gw):
     m = GOLDEN["lbfgs_minimum"]
     vmin, gmin = le.val_and_grad(m["param"])
     assert abs(vmin - m["val"]) <= 1e-12 * abs(m["val"]) and abs(gmin[0]) < 1e-7  # README.md:186
-    assert le(1.0) == val and le(*[1.0]) == val  # scalar / varargs forms (localenergy.jl:171-173)
+    # (later sweeps of a handle may run over its stored representative basis: same sums in another order)
+    same = lambda a, b: abs(a - b) <= 1e-14 * abs(b)  # noqa: E731
+    assert same(le(1.0), val) and same(le(*[1.0]), val)  # scalar / varargs forms (localenergy.jl:171-173)
     G = np.zeros(1)
-    assert le(True, G, [1.0]) == val and G[0] == grad[0]  # localenergy.jl:157-169
-    assert le(None, G, [1.0]) is None and le(True, None, [1.0]) == val
+    assert same(le(True, G, [1.0]), val) and same(G[0], grad[0])  # localenergy.jl:157-169
+    assert le(None, G, [1.0]) is None and same(le(True, None, [1.0]), val)
 
 
 @pytest.mark.parametrize("case", SWEEP_GOLDEN["cases"], ids=lambda c: f"N{c['N']}M{c['M']}g{c['g']}")
