@@ -122,6 +122,8 @@ SIGNATURES = {
     "gwz_sweep_val_and_grad": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
     "gwz_sweep_terms": (C.c_int, [_vp, _dp, C.c_uint64, C.c_uint64, _vp]),
     "gwz_sweep_states": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "gwz_sweep_representative_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
+                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "gwz_sweep_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "gwz_resample": (C.c_int, [_vp, C.c_size_t, _vp, _vp, C.c_size_t]),
     "gwz_blocking_analysis": (C.c_int, [_vp, C.c_size_t, C.POINTER(BlockingResult)]),

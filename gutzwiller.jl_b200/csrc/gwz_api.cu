@@ -1244,6 +1244,24 @@ extern "C" int gwz_sweep_val_and_grad(gwz_sweep* s, const double* params, double
     return GWZ_OK;
 }
 
+// host-only: which ranks a symmetric ranked sweep of [rank_begin, rank_begin + dim) visits (see representative_range)
+extern "C" int gwz_sweep_representative_range(int N, int M, uint64_t rank_begin, uint64_t dim, uint64_t* first_rank,
+                                              uint64_t* count, int32_t* has_uniform, uint64_t* uniform_state) {
+    GWZ_REQUIRE(N >= 1 && M >= 2 && N + M <= 64, "gwz_sweep_representative_range: needs N >= 1, M >= 2, N + M <= 64");
+    std::vector<uint64_t> tab;
+    binomial_table(tab);
+    const int B = N + M - 1;
+    const uint64_t total = tab[(size_t)B * 65 + N];
+    GWZ_REQUIRE(total != UINT64_MAX && rank_begin <= total && dim <= total - rank_begin,
+                "gwz_sweep_representative_range: bad rank range");
+    const RepRange r = representative_range(tab, N, M, B, rank_begin, dim);
+    if (first_rank) *first_rank = r.lo;
+    if (count) *count = r.count;
+    if (has_uniform) *has_uniform = r.has_extra;
+    if (uniform_state) *uniform_state = r.extra_state;
+    return GWZ_OK;
+}
+
 extern "C" int gwz_sweep_val(gwz_sweep* s, const double* params, double* val) {
     GWZ_REQUIRE(val != nullptr, "gwz_sweep_val: val is NULL");
     return gwz_sweep_val_and_grad(s, params, val, nullptr, nullptr);

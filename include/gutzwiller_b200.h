@@ -188,6 +188,13 @@ int gwz_sweep_terms(gwz_sweep *s, const double *params, uint64_t first, uint64_t
 int gwz_sweep_states(gwz_sweep *s, uint64_t first, uint64_t count, uint64_t *out);
 /* device time (ms) of the last sweep kernel */
 int gwz_sweep_last_kernel_ms(const gwz_sweep *s, float *ms);
+/* Host-only helper (no device work): a ranked sweep of HubbardReal1D + GutzwillerAnsatz evaluates one representative
+ * per orbit of the chain's translations and reflection (the largest rotation of the unary string and of its mirror
+ * image), weighted with the orbit size.  Representatives carry the largest occupation in mode M, so only the ranks
+ * [*first_rank, *first_rank + *count) of [rank_begin, rank_begin + dim) are visited; at commensurate filling the uniform
+ * state (*uniform_state, if *has_uniform) is evaluated on its own. */
+int gwz_sweep_representative_range(int N, int M, uint64_t rank_begin, uint64_t dim, uint64_t *first_rank,
+                                   uint64_t *count, int32_t *has_uniform, uint64_t *uniform_state);
 
 /* ---- error bars: resample! (state.jl:194-231) + Rimu.StatsTools.blocking_analysis ---------- */
 int gwz_resample(double *result, size_t len, const double *residence_times, const double *values, size_t n);

@@ -291,3 +291,69 @@ def test_sparse_host_objects(gw):
     assert gw.num_parameters(ta) == 2 and ta.table([0.1, 0.2])[1].shape == (36, 2)
     with pytest.raises(TypeError):  # pairs must match
         gw.kinetic_vqmc(gw.HubbardReal1D(gw.near_uniform(4, 4)), a, 0.5)
+
+
+def test_sweep_representative_range_against_brute_force(gw):
+    """Host-only helper behind the symmetric ranked sweep: every representative of a dihedral orbit (largest rotation of
+    the unary string and of its mirror image) lies in the visited rank range, except the uniform state at commensurate
+    filling, which is handed over separately -- also when the rank range is cut into shards."""
+    import ctypes as C
+    import itertools
+    from math import comb
+    L = gw.lib()
+
+    def unary(n):
+        v = pos = 0
+        for k in n:
+            v |= ((1 << k) - 1) << pos
+            pos += k + 1
+        return v
+
+    def rank_of(x):
+        r = j = 0
+        for p in range(64):
+            if (x >> p) & 1:
+                j += 1
+                r += comb(p, j)
+        return r
+
+    def query(N, M, begin, dim):
+        lo, cnt, hu, ux = C.c_uint64(), C.c_uint64(), C.c_int32(), C.c_uint64()
+        gw.capi.check(L.gwz_sweep_representative_range(N, M, begin, dim, C.byref(lo), C.byref(cnt), C.byref(hu), C.byref(ux)))
+        return lo.value, cnt.value, hu.value, ux.value
+
+    for N, M in ((4, 4), (6, 3), (3, 6), (5, 4), (6, 6), (2, 2), (9, 3), (1, 5), (8, 4)):
+        total = comb(N + M - 1, N)
+        reps = []
+        for ones in itertools.combinations(range(N + M - 1), N):
+            x = sum(1 << p for p in ones)
+            n, run = [], 0
+            for p in range(N + M - 1):
+                if (x >> p) & 1:
+                    run += 1
+                else:
+                    n.append(run)
+                    run = 0
+            n = tuple(n + [run])
+            r = tuple(reversed(n))
+            if x == max([unary(n[i:] + n[:i]) for i in range(M)] + [unary(r[i:] + r[:i]) for i in range(M)]):
+                reps.append(x)
+        uniform = unary((N // M,) * M) if N % M == 0 else None
+        cuts = sorted({0, total // 3, (2 * total) // 3 + 1, total} - {total + 1})
+        seen_uniform = 0
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            if e <= b:
+                continue
+            lo, cnt, hu, ux = query(N, M, b, e - b)
+            assert b <= lo and lo + cnt == e
+            if hu:
+                assert ux == uniform and b <= rank_of(ux) < e
+                seen_uniform += 1
+            for x in reps:
+                if x != uniform and b <= rank_of(x) < e:
+                    assert lo <= rank_of(x), (N, M, b, e, x)
+        assert seen_uniform == (1 if uniform is not None else 0)
+        lo, cnt, _, _ = query(N, M, 0, total)
+        assert cnt < total or M == 1  # something is always skipped
+    rc = L.gwz_sweep_representative_range(40, 40, 0, 1, None, None, None, None)
+    assert rc == gw.capi.ERR_INVALID
