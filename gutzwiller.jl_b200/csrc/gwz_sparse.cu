@@ -10,14 +10,16 @@
 //
 // HBM layout: row_ptr u64[dim+1], col u32[nnz], melem f64[nnz], rpsi f64[nnz] (the amplitude of every row entry's
 // target, gathered once per table so that a walker step STREAMS its row -- 20 B per hop, no gather), diag f64[dim],
-// amplitudes f64[dim] and the ansatz table f64[dim][1+P] (psi, then grad_ratio: one state's data in one sector, what
-// the gradient sweep gathers);
-// walkers: index u32[n], accumulators f64[4+2P][n].  One walker per GROUP of G = 4/8/16/32 lanes (G from the mean row
-// length): the lanes read a row chunk by chunk (coalesced col/melem, gathered psi), an inclusive scan inside each
-// chunk gives the reference's cumulative buffer in row order and the move is the first entry with u*S < cumsum
-// (pick_random_from_cumsum, qmc.jl:52-61); the first R chunks stay in registers for the pick, longer rows are
-// re-read.  The walk is a chain of dependent loads (index -> row_ptr -> row): latency bound, so occupancy (64
-// registers, 8 CTAs/SM) and bytes per hop are what matter.
+// amplitudes f64[dim], a 64 B record per state (row bounds, diag, psi, gradient ratios) and the ansatz table
+// f64[dim][1+P] (psi, then grad_ratio: one state's data in one sector, what the gradient sweep gathers).  When the
+// rows are regular enough each state also gets a ROW BLOCK at a fixed stride (head + the row in chunks of G entries,
+// col | melem | rpsi, 128 B aligned): the block address is k * stride, so a walker step is one dependent HBM access
+// (index -> block) instead of three (index -> record -> row).
+// Walkers: index u32[n], accumulators f64[4+2P][n].  One walker per GROUP of G = 4/8/16/32 lanes (G from the mean row
+// length): the lanes read a row chunk by chunk (coalesced), an inclusive scan inside each chunk gives the reference's
+// cumulative buffer in row order and the move is the first entry with u*S < cumsum (pick_random_from_cumsum,
+// qmc.jl:52-61); the first R chunks stay in registers for the pick, longer rows are re-read.  Bound: HBM (random
+// 128 B lines) and issue about evenly; occupancy (64 registers, 8 CTAs/SM) and bytes per hop are what matter.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
