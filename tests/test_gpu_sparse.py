@@ -314,6 +314,42 @@ def test_chain_as_stored_operator_agrees_with_the_bit_level_kernels(gw):
     assert np.all(np.abs(res.last.grad - gb) < 6 * res.last.grad_err + 1e-3)
 
 
+def test_against_committed_golden_vectors(gw, layout):
+    """tests/golden/sparse_vectors.json: per-index outputs, LocalEnergyEvaluator values and final walker positions"""
+    import importlib.util
+    import json
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_sparse", os.path.join(gdir, "make_golden_sparse.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    golden = json.load(open(os.path.join(gdir, "sparse_vectors.json")))
+    operators = mg.operators()
+    for case in golden["cases"]:
+        H = gw.SparseHamiltonian(*operators[case["operator"]])
+        h = H.handle()
+        if case["ansatz"] == "gutzwiller":
+            ans, params = gw.SparseGutzwillerAnsatz(H), [0.4]
+        else:
+            psi, gr = mg.table(H.dim, 3, 77)
+            ans, params = gw.TableAnsatz(H, lambda p, psi=psi, gr=gr: (psi, gr), 3), [0.0, 0.0, 0.0]
+        h.load(ans, params)
+        assert h.info()["row_blocks"] == (layout == "blocks")
+        idx = np.array([r["index"] for r in case["probes"]], dtype=np.uint32)
+        out = h.probe(idx, np.full(idx.size, 0.37))
+        for i, r in enumerate(case["probes"]):
+            assert abs(out["e_loc"][i] - r["e_loc"]) <= 1e-11 * max(1.0, abs(r["e_loc"]))
+            assert abs(out["residence_time"][i] - r["tau"]) <= TOL * r["tau"]
+            assert out["n_hops"][i] == r["n_hops"] and out["chosen"][i] == r["chosen"] and out["next_index"][i] == r["next"]
+            assert np.allclose(out["grad_ratio"][i], r["grad"], rtol=1e-14, atol=0)
+        v, g = h.sweep()
+        assert abs(v - case["lee_val"]) <= TOL * max(1.0, abs(case["lee_val"]))
+        assert np.allclose(g, case["lee_grad"], rtol=1e-10, atol=1e-12)
+        ws = gw.SparseWalkers(h, ans, 8, 0, seed=9)
+        r = ws.run(params, 120)
+        assert list(ws.indices()) == case["final_indices"] and r.hops == case["hops"]
+        assert np.allclose(ws.estimates()[0], case["val_w"], rtol=1e-10, atol=1e-12)
+
+
 def test_argument_checks(gw, ops):
     rp, col, mel, diag = ops["fermi"]
     bad = col.copy()

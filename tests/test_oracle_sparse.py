@@ -141,3 +141,32 @@ def test_from_hubbard_reproduces_the_reference_rows(gw):
         assert np.all(np.diff(words.astype(np.int64)) > 0)
     with pytest.raises(ValueError, match="too many"):
         gw.SparseHamiltonian.from_hubbard(gw.HubbardReal1D(gw.near_uniform(20, 20)))
+
+
+def test_oracle_reproduces_committed_sparse_vectors():
+    """tests/golden/sparse_vectors.json (made by tests/golden/make_golden_sparse.py) pins part 3 of the oracle"""
+    import json
+    import os
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_sparse", os.path.join(sys_path, "make_golden_sparse.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    golden = json.load(open(os.path.join(sys_path, "sparse_vectors.json")))
+    ops = mg.operators()
+    assert len(golden["cases"]) == 6
+    for case in golden["cases"]:
+        so = SparseOracle(*ops[case["operator"]])
+        assert so.dim == case["dim"]
+        if case["ansatz"] == "gutzwiller":
+            so.set_gutzwiller(0.4)
+        else:
+            so.set_table(*mg.table(so.dim, 3, 77))
+        for row in case["probes"]:
+            ks = so.kinetic_sample(row["index"], 0.37)
+            assert ks["eloc"] == row["e_loc"] and ks["tau"] == row["tau"] and ks["chosen"] == row["chosen"]
+            assert ks["new_index"] == row["next"] and ks["n_hops"] == row["n_hops"] and list(ks["grad"]) == row["grad"]
+        v, g = so.lee_val_and_grad()
+        assert v == case["lee_val"] and list(g) == case["lee_grad"]
+        tr = so.kinetic_vqmc(np.zeros(8, dtype=np.uint32), 120, seed=9)
+        assert list(tr["idx"]) == case["final_indices"] and tr["hops"] == case["hops"]
