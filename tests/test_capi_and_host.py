@@ -357,3 +357,35 @@ def test_sweep_representative_range_against_brute_force(gw):
         assert cnt < total or M == 1  # something is always skipped
     rc = L.gwz_sweep_representative_range(40, 40, 0, 1, None, None, None, None)
     assert rc == gw.capi.ERR_INVALID
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """julia/GutzwillerB200.jl cannot run here (no Julia): at least every ccall must name a declared entry point with the
+    right number of arguments of the right kind (pointer / 32- or 64-bit integer / double)."""
+    jl = open(os.path.join(ROOT, "gutzwiller.jl_b200", "julia", "GutzwillerB200.jl")).read()
+    calls = re.findall(r"ccall\(\(:(\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", jl, flags=re.S)
+    assert len(calls) >= 40
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char \*|const char\*)\s*\*?\s*(gwz_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).replace("\n", " ")
+        protos[m.group(1)] = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+
+    def kind_c(a):
+        if "*" in a:
+            return "ptr"
+        t = a.rsplit(" ", 1)[0].replace("const ", "").strip()
+        return {"int": "i32", "int32_t": "i32", "unsigned": "u32", "uint32_t": "u32", "uint64_t": "u64", "size_t": "u64",
+                "double": "f64", "float": "f32"}[t]
+
+    def kind_j(t):
+        if t.startswith(("Ptr", "Ref")) or t == "Cstring":
+            return "ptr"
+        return {"Cint": "i32", "Int32": "i32", "Cuint": "u32", "UInt32": "u32", "UInt64": "u64", "Csize_t": "u64",
+                "Cdouble": "f64", "Cfloat": "f32"}[t]
+
+    for name, ret, types in calls:
+        assert name in protos, f"{name} is not declared in include/gutzwiller_b200.h"
+        jt = [t for t in (x.strip() for x in types.replace("\n", " ").split(",")) if t]
+        assert [kind_c(a) for a in protos[name]] == [kind_j(t) for t in jt], name
+        assert ret in ("Cint", "Cstring")
