@@ -389,3 +389,29 @@ def test_julia_shim_ccalls_match_the_header():
         jt = [t for t in (x.strip() for x in types.replace("\n", " ").split(",")) if t]
         assert [kind_c(a) for a in protos[name]] == [kind_j(t) for t in jt], name
         assert ret in ("Cint", "Cstring")
+
+
+def test_struct_layouts_match_the_header(gw, tmp_path):
+    """sizeof / offsetof of the result structs as gcc sees the header against the ctypes mirrors"""
+    import ctypes as C
+    src = tmp_path / "layout.c"
+    src.write_text("""#include <stdio.h>
+#include <stddef.h>
+#include "gutzwiller_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu\\n", sizeof(gwz_vqmc_result), offsetof(gwz_vqmc_result, walkers), offsetof(gwz_vqmc_result, acc),
+           offsetof(gwz_vqmc_result, kernel_ms));
+    printf("%zu %zu %zu %zu\\n", sizeof(gwz_gen_result), offsetof(gwz_gen_result, walkers), offsetof(gwz_gen_result, kernel_ms),
+           offsetof(gwz_gen_result, np));
+    printf("%zu %zu\\n", sizeof(gwz_gd_opts), offsetof(gwz_gd_opts, first_moment_init));
+    return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    rows = [[int(x) for x in line.split()] for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                                        text=True).stdout.splitlines()]
+    V, G, O = gw.capi.VqmcResult, gw.capi.GenResult, gw.capi.GdOpts
+    assert rows[0] == [C.sizeof(V), V.walkers.offset, V.acc.offset, V.kernel_ms.offset]
+    assert rows[1] == [C.sizeof(G), G.walkers.offset, G.kernel_ms.offset, G.np.offset]
+    assert rows[2] == [C.sizeof(O), O.first_moment_init.offset]
