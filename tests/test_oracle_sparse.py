@@ -170,3 +170,22 @@ def test_oracle_reproduces_committed_sparse_vectors():
         assert v == case["lee_val"] and list(g) == case["lee_grad"]
         tr = so.kinetic_vqmc(np.zeros(8, dtype=np.uint32), 120, seed=9)
         assert list(tr["idx"]) == case["final_indices"] and tr["hops"] == case["hops"]
+
+
+def test_from_hubbard_extended_chain_diagonal(gw):
+    """ExtendedHubbardReal1D: the nearest-neighbour term v sum_i n_i n_{i+1} enters the stored diagonal"""
+    from oracle.oracle import AnsatzOracle
+    o = Oracle(5, 4, 1.5, 0.3)
+    ao = AnsatzOracle(o, "gutzwiller", v=0.7)
+    H = gw.ExtendedHubbardReal1D(gw.near_uniform(5, 4), u=1.5, v=0.7, t=0.3)
+    Hs = gw.SparseHamiltonian.from_hubbard(H)
+    H0 = gw.SparseHamiltonian.from_hubbard(gw.HubbardReal1D(gw.near_uniform(5, 4), u=1.5, t=0.3))
+    assert np.array_equal(Hs.col, H0.col) and np.array_equal(Hs.melem, H0.melem)  # same hops, other diagonal
+    for k, n in enumerate(Hs.addresses.tolist()):
+        assert abs(Hs.diag[k] - ao.diagonal_element(o.from_onr(n))) < 1e-14
+    so = SparseOracle(Hs.row_ptr, Hs.col, Hs.melem, Hs.diag)
+    so.set_gutzwiller(0.3)
+    basis = np.stack([o.from_onr(n) for n in Hs.addresses.tolist()])
+    v0, g0 = ao.lee_val_and_grad(basis, [0.3])
+    v1, g1 = so.lee_val_and_grad()
+    assert abs(v1 - v0) < 1e-13 * abs(v0) and abs(g1[0] - g0[0]) < 1e-12 * max(1.0, abs(g0[0]))
