@@ -24,7 +24,7 @@ from .runtime import (Context, Model, comm_init_all, default_context, distribute
 from .sparse import (SparseGutzwillerAnsatz, SparseHamiltonian, SparseVectorAnsatz, SparseWalkers, TableAnsatz)
 from .vqmc import (BlockingResult, CombinedBlockingResult, KineticVQMC, KineticVQMCResult, Walkers,
                    blocking_analysis, default_walkers, kinetic_vqmc, kinetic_vqmc_continue,
-                   local_energy_estimator, mean, resample, run_group, sampled_vector, var)
+                   local_energy_estimator, mean, resample, run_group, sampled_vector, series_blocking, var)
 
 lib()  # fail at import time if the CUDA library is missing
 

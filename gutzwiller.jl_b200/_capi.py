@@ -15,27 +15,39 @@ LIB_PATH = os.environ.get("GWZ_LIB_PATH") or os.path.join(_HERE, "lib", "libgutz
 MAX_WORDS = 4
 NUM_PARAMS = 1
 NCCL_ID_BYTES = 128
-NUM_ACC = 12
+NUM_ACC = 13
+NUM_BACC = 38
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NONFINITE, ERR_NOMEM = range(6)
 KERNEL_ENUMERATE, KERNEL_BITPARALLEL = 0, 1
 RUN_KEEP_ACC = 1
 RUN_POOLED = 2
+RUN_SERIES = 4
+RUN_BLOCKING = 8
 
 ACC_NAMES = ("walkers", "sum_val", "sum_val2", "sum_grad", "sum_grad2", "sum_t", "sum_tE", "sum_tG",
-             "sum_tGE", "sum_tEE", "hops", "steps")
+             "sum_tGE", "sum_tEE", "hops", "steps", "sum_var")
 
 
 class GutzwillerError(RuntimeError):
     """A CUDA / NCCL failure reported by the library."""
 
 
+class BlockingSummary(C.Structure):
+    """gwz_blocking_summary: val_err_and_grad(::KineticVQMCResult) on the device (state.jl:150-164)"""
+    _fields_ = [("mean", C.c_double), ("err", C.c_double), ("err_err", C.c_double), ("err_ok", C.c_double),
+                ("grad", C.c_double * NUM_PARAMS), ("walkers", C.c_uint64), ("failed", C.c_uint64),
+                ("k_min", C.c_int32), ("k_max", C.c_int32), ("series_steps", C.c_uint64),
+                ("resample_len", C.c_uint64), ("kernel_ms", C.c_float), ("reserved", C.c_float)]
+
+
 class VqmcResult(C.Structure):
     _fields_ = [("val", C.c_double), ("err", C.c_double), ("grad", C.c_double * NUM_PARAMS),
                 ("grad_err", C.c_double * NUM_PARAMS), ("pooled_val", C.c_double),
                 ("pooled_grad", C.c_double * NUM_PARAMS), ("pooled_var", C.c_double),
-                ("total_time", C.c_double), ("walkers", C.c_uint64), ("steps", C.c_uint64),
-                ("hops", C.c_uint64), ("acc", C.c_double * NUM_ACC), ("kernel_ms", C.c_float)]
+                ("walker_var", C.c_double), ("total_time", C.c_double), ("walkers", C.c_uint64), ("steps", C.c_uint64),
+                ("hops", C.c_uint64), ("acc", C.c_double * NUM_ACC), ("kernel_ms", C.c_float),
+                ("reserved", C.c_float), ("blocking", BlockingSummary)]
 
 
 class GenResult(C.Structure):
@@ -113,6 +125,10 @@ SIGNATURES = {
     "gwz_walkers_estimates": (C.c_int, [_vp, _vp, _vp]),
     "gwz_vqmc_run_record": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, C.c_uint, _vp, _vp, _vp,
                                       C.POINTER(VqmcResult)]),
+    "gwz_walkers_blocking": (C.c_int, [_vp, C.c_uint64, C.POINTER(BlockingSummary), _vp, _vp, _vp, _vp, _vp]),
+    "gwz_walkers_series": (C.c_int, [_vp, _u64p, _vp, _vp]),
+    "gwz_series_blocking": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(BlockingSummary),
+                                      _vp, _vp, _vp, _vp, _vp]),
     "gwz_vqmc_sample_vector": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, C.c_uint, C.c_uint64, _vp, _vp, _u64p,
                                          C.POINTER(VqmcResult)]),
     "gwz_sweep_create": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
@@ -130,7 +146,8 @@ SIGNATURES = {
     "gwz_gd_opts_default": (C.c_int, [C.POINTER(GdOpts)]),
     "gwz_adaptive_gradient_descent": (C.c_int, [OBJECTIVE_FN, OBJECTIVE_FN, _vp, _dp, C.c_int, C.POINTER(GdOpts),
                                                 C.POINTER(GdTrace)]),
-    "gwz_amsgrad_vqmc": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.c_uint64, C.c_int, C.c_uint, C.POINTER(GdTrace)]),
+    "gwz_amsgrad_vqmc": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.c_uint64, C.c_uint64, C.c_int, C.c_uint,
+                                   C.POINTER(GdTrace), C.POINTER(VqmcResult)]),
     "gwz_amsgrad_sweep": (C.c_int, [_vp, _dp, C.POINTER(GdOpts), C.POINTER(GdTrace)]),
     # ---- ansatz-generic engine ----
     "gwz_model_create_ext_hubbard1d": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,

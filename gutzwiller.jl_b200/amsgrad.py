@@ -121,12 +121,24 @@ def adaptive_gradient_descent(use_amsgrad: bool, f, params, *, maxiter=100, verb
         setattr(tr, k, a.ctypes.data_as(C.POINTER(C.c_double)))
     p0c = p0.ctypes.data_as(C.POINTER(C.c_double))
 
-    generic = bool(getattr(getattr(f, 'ansatz', None), 'generic', False))
-    if isinstance(f, KineticVQMC) and not fkwargs and not f.result.record and n == 1 and not generic:
-        check(lib().gwz_amsgrad_vqmc(f.result.walkers_handle.handle, p0c, C.byref(o), f.steps, f.result.kernel,
-                                     _capi.RUN_POOLED if f.result.estimator == "pooled" else 0, C.byref(tr)))
-        f.result.steps = f.steps
-    elif isinstance(f, LocalEnergyEvaluator) and not fkwargs and n == 1 and not generic:
+    # The in-library loops take the handles of the bit-level HubbardReal1D + GutzwillerAnsatz engine ONLY (a gwz_walkers
+    # / gwz_sweep); every other engine's handle (generic ansaetze, stored operators, vector ansatz) goes through the
+    # callback path below.  The library checks the handle's type tag as well.
+    from .vqmc import Walkers
+    if isinstance(f, KineticVQMC) and not fkwargs and f.result.record is not True and n == 1 \
+            and type(f.result.walkers_handle) is Walkers:
+        res = f.result
+        pooled = res.estimator == "pooled"
+        flags = _capi.RUN_POOLED if pooled else _capi.RUN_BLOCKING  # val_err_and_grad(qmc, p): state.jl:150-164
+        last = _capi.VqmcResult()
+        check(lib().gwz_amsgrad_vqmc(res.walkers_handle.handle, p0c, C.byref(o), f.steps, res.burn_in, res.kernel,
+                                     flags, C.byref(tr), C.byref(last)))
+        # what the reference leaves behind in qmc.result: the last evaluation
+        res.steps, res.last = f.steps, last
+        res.params = bufs["param"][max(tr.iterations - 1, 0)].copy()
+        res.has_device_series = not pooled
+        res.blocking_summary = last.blocking if not pooled else None
+    elif isinstance(f, LocalEnergyEvaluator) and not fkwargs and n == 1 and f.is_bit_level():
         check(lib().gwz_amsgrad_sweep(f.handle, p0c, C.byref(o), C.byref(tr)))
     else:
         errors = []

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "gwz_handles.h"
+#include "gwz_blocking.cuh"
 
 using namespace gwz;
 
@@ -40,29 +41,6 @@ extern "C" int gwz_launch_count(uint64_t* n) {
 
 extern "C" const char* gwz_last_error(void) { return g_last_error.c_str(); }
 extern "C" int gwz_version(void) { return GWZ_VERSION; }
-
-struct gwz_walkers {
-    gwz_model* m;
-    size_t n;
-    uint64_t offset, seed;
-    uint64_t steps_done;  // Philox step counter
-    uint64_t acc_steps;   // steps currently held in the estimators (per walker)
-    uint64_t* d_addr = nullptr;
-    double* d_acc = nullptr;
-    double* d_partials = nullptr;
-    int partials_cap = 0;
-    double* d_vec = nullptr;  // NUM_ACC doubles: this set's reduced vector
-    double* d_shift = nullptr;  // scratch for the reference-point kernel (first estimator only)
-    double* h_shift = nullptr;  // pinned
-    double shift_e = 0.0, shift_g = 0.0;  // (E_ref, G_ref): reference point of the current estimator's sums
-    double next_e = 0.0, next_g = 0.0;    // pooled (E, G) of the last run: reference point of the next estimator
-    bool have_next = false;
-    // Where the walkers currently live: unary bitstrings (d_addr) or occupation bit-planes (d_planes).
-    // The production kernel works on planes; everything that needs addresses converts back first.
-    uint32_t* d_planes = nullptr;
-    uint64_t* d_ref_addr = nullptr;  // W words: unary copy of walker 0 for the reference-point kernel
-    bool in_planes = false;
-};
 
 static bool planes_enabled() {
     const char* e = std::getenv("GWZ_PLANES");
@@ -99,6 +77,7 @@ static int to_planes(gwz_walkers* w) {
 }
 
 struct gwz_sweep {
+    uint32_t magic = gwz::GWZ_TAG_SWEEP;  // handle type tag, checked by every entry point
     gwz_model* m;
     uint64_t* d_basis = nullptr;  // SoA [W][dim], null => ranked
     uint64_t dim = 0, rank_begin = 0;
@@ -138,20 +117,23 @@ extern "C" int gwz_context_create(int device, gwz_context** out) {
     GWZ_CUDA(cudaGetDeviceProperties(&c->prop, device));
     GWZ_CUDA(cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device));
     GWZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    GWZ_CUDA(cudaMalloc(&c->d_acc, sizeof(double) * NUM_ACC));
-    GWZ_CUDA(cudaMalloc(&c->d_group, sizeof(double) * NUM_ACC * GROUP_ROWS));
-    GWZ_CUDA(cudaMallocHost(&c->h_acc, sizeof(double) * NUM_ACC));
+    GWZ_CUDA(cudaMalloc(&c->d_acc, sizeof(double) * NUM_VEC));
+    GWZ_CUDA(cudaMalloc(&c->d_group, sizeof(double) * NUM_VEC * GROUP_ROWS));
+    GWZ_CUDA(cudaMallocHost(&c->h_acc, sizeof(double) * NUM_VEC));
     GWZ_CUDA(cudaMalloc(&c->d_err, sizeof(int)));
     GWZ_CUDA(cudaMallocHost(&c->h_err, sizeof(int)));
     GWZ_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
     GWZ_CUDA(cudaEventCreate(&c->ev0));
     GWZ_CUDA(cudaEventCreate(&c->ev1));
+    GWZ_CUDA(cudaEventCreate(&c->ev2));
+    GWZ_CUDA(cudaEventCreate(&c->ev3));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return GWZ_OK;
 }
 
 extern "C" int gwz_context_destroy(gwz_context* c) {
+    if (c && c->magic != gwz::GWZ_TAG_CONTEXT) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_context_destroy: not a gwz_context handle");
     if (!c) return GWZ_OK;
     cudaSetDevice(c->device);
     if (c->comm) {
@@ -165,13 +147,17 @@ extern "C" int gwz_context_destroy(gwz_context* c) {
     cudaFreeHost(c->h_err);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
     if (c->stream) cudaStreamDestroy(c->stream);
+    c->magic = 0;
     delete c;
     return GWZ_OK;
 }
 
 extern "C" int gwz_context_info(const gwz_context* c, int* device, int* sm_count, int* sm_clock_khz, int* cc_major,
                                 int* cc_minor, size_t* global_mem_bytes) {
+    GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_context_info: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(c != nullptr, "gwz_context_info: ctx is NULL");
     if (device) *device = c->device;
     if (sm_count) *sm_count = c->prop.multiProcessorCount;
@@ -183,12 +169,14 @@ extern "C" int gwz_context_info(const gwz_context* c, int* device, int* sm_count
 }
 
 extern "C" int gwz_context_stream(const gwz_context* c, void** cuda_stream) {
+    GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_context_stream: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(c && cuda_stream, "gwz_context_stream: NULL argument");
     *cuda_stream = (void*)c->stream;
     return GWZ_OK;
 }
 
 extern "C" int gwz_context_synchronize(gwz_context* c) {
+    GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_context_synchronize: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(c != nullptr, "gwz_context_synchronize: ctx is NULL");
     if (int rc = use_device(c)) return rc;
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
@@ -208,6 +196,7 @@ extern "C" int gwz_nccl_unique_id(uint8_t id[GWZ_NCCL_ID_BYTES]) {
 }
 
 extern "C" int gwz_context_comm_init(gwz_context* c, int world_size, int rank, const uint8_t id[GWZ_NCCL_ID_BYTES]) {
+    GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_context_comm_init: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(c && id, "gwz_context_comm_init: NULL argument");
     GWZ_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "gwz_context_comm_init: bad rank/world_size");
     GWZ_REQUIRE(c->comm == nullptr, "gwz_context_comm_init: communicator already initialised");
@@ -231,7 +220,8 @@ extern "C" int gwz_context_comm_init_all(gwz_context* const* ctxs, int n) {
     std::vector<int> devs(n);
     std::vector<ncclComm_t> comms(n);
     for (int i = 0; i < n; ++i) {
-        GWZ_REQUIRE(ctxs[i] && ctxs[i]->comm == nullptr, "gwz_context_comm_init_all: NULL or already joined context");
+        GWZ_HANDLE(ctxs[i], gwz::GWZ_TAG_CONTEXT, "gwz_context_comm_init_all: NULL or foreign handle (expected gwz_context)");
+        GWZ_REQUIRE(ctxs[i]->comm == nullptr, "gwz_context_comm_init_all: already joined context");
         devs[i] = ctxs[i]->device;
     }
     GWZ_NCCL(api, api->CommInitAll(comms.data(), n, devs.data()));
@@ -244,6 +234,7 @@ extern "C" int gwz_context_comm_init_all(gwz_context* const* ctxs, int n) {
 }
 
 extern "C" int gwz_context_comm_info(const gwz_context* c, int* world_size, int* rank) {
+    GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_context_comm_info: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(c != nullptr, "gwz_context_comm_info: ctx is NULL");
     if (world_size) *world_size = c->world;
     if (rank) *rank = c->rank;
@@ -255,6 +246,7 @@ extern "C" int gwz_context_comm_info(const gwz_context* c, int* world_size, int*
 // ------------------------------------------------------------------------------------------
 extern "C" int gwz_model_create_hubbard1d_gutzwiller(gwz_context* ctx, int N, int M, double u, double t,
                                                      gwz_model** out) {
+    GWZ_HANDLE(ctx, gwz::GWZ_TAG_CONTEXT, "gwz_model_create_hubbard1d_gutzwiller: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(ctx && out, "gwz_model_create: NULL argument");
     GWZ_REQUIRE(N >= 1 && M >= 2, "gwz_model_create: need N >= 1 particles and M >= 2 modes");
     const int B = N + M - 1;
@@ -289,10 +281,13 @@ extern "C" int gwz_model_create_hubbard1d_gutzwiller(gwz_context* ctx, int N, in
     return GWZ_OK;
 }
 extern "C" int gwz_model_destroy(gwz_model* m) {
+    if (m && m->magic != gwz::GWZ_TAG_MODEL) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_model_destroy: not a gwz_model handle");
+    m->magic = 0;
     delete m;
     return GWZ_OK;
 }
 extern "C" int gwz_model_info(const gwz_model* m, int* N, int* M, double* u, double* t, int* bits, int* words) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_model_info: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m != nullptr, "gwz_model_info: model is NULL");
     if (N) *N = m->N;
     if (M) *M = m->M;
@@ -303,6 +298,7 @@ extern "C" int gwz_model_info(const gwz_model* m, int* N, int* M, double* u, dou
     return GWZ_OK;
 }
 extern "C" int gwz_model_from_onr(const gwz_model* m, const int32_t* onr, uint64_t* a) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_model_from_onr: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && onr && a, "gwz_model_from_onr: NULL argument");
     int total = 0;
     for (int i = 0; i < m->M; ++i) {
@@ -319,6 +315,7 @@ extern "C" int gwz_model_from_onr(const gwz_model* m, const int32_t* onr, uint64
     return GWZ_OK;
 }
 extern "C" int gwz_model_to_onr(const gwz_model* m, const uint64_t* a, int32_t* onr) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_model_to_onr: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && onr && a, "gwz_model_to_onr: NULL argument");
     int mode = 0;
     for (int i = 0; i < m->M; ++i) onr[i] = 0;
@@ -333,6 +330,7 @@ extern "C" int gwz_model_to_onr(const gwz_model* m, const uint64_t* a, int32_t* 
     return GWZ_OK;
 }
 extern "C" int gwz_model_near_uniform(const gwz_model* m, uint64_t* a) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_model_near_uniform: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && a, "gwz_model_near_uniform: NULL argument");
     std::vector<int32_t> onr(m->M);
     const int ff = m->N / m->M, extras = m->N % m->M;
@@ -350,6 +348,7 @@ void gwz::binomial_table(std::vector<uint64_t>& tab) {
     }
 }
 extern "C" int gwz_model_dimension(const gwz_model* m, double* dim, uint64_t* dim_exact) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_model_dimension: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m != nullptr, "gwz_model_dimension: model is NULL");
     double r = 1.0;
     const int n = m->B, k = (m->N < m->M - 1) ? m->N : m->M - 1;
@@ -425,6 +424,7 @@ extern "C" int gwz_probe_addresses(gwz_model* m, const uint64_t* addr_words, siz
                                    const double* u01, int kernel_kind, double* e_loc, double* residence_time,
                                    double* grad_ratio, int32_t* n_hops, double* rates, int32_t* chosen,
                                    uint64_t* next_addr) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_probe_addresses: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && params, "gwz_probe_addresses: NULL argument");
     GWZ_REQUIRE(m->v == 0.0, "gwz_probe_addresses: ExtendedHubbardReal1D models need the gwz_gen_* entry points");
     GWZ_REQUIRE(n == 0 || addr_words, "gwz_probe_addresses: addr_words is NULL");
@@ -484,6 +484,7 @@ extern "C" int gwz_probe_addresses(gwz_model* m, const uint64_t* addr_words, siz
 
 extern "C" int gwz_ansatz_val_and_grad(gwz_model* m, const uint64_t* addr_words, size_t n, const double* params,
                                        double* val, double* grad) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_ansatz_val_and_grad: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && params, "gwz_ansatz_val_and_grad: NULL argument");
     GWZ_REQUIRE(n == 0 || addr_words, "gwz_ansatz_val_and_grad: addr_words is NULL");
     if (n == 0) return GWZ_OK;
@@ -508,6 +509,7 @@ extern "C" int gwz_ansatz_val_and_grad(gwz_model* m, const uint64_t* addr_words,
 // ------------------------------------------------------------------------------------------
 extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t global_offset, const uint64_t* start_addr,
                                   uint64_t seed, gwz_walkers** out) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_walkers_create: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && start_addr && out, "gwz_walkers_create: NULL argument");
     GWZ_REQUIRE(m->v == 0.0, "gwz_walkers_create: ExtendedHubbardReal1D models need the gwz_gen_* entry points");
     GWZ_REQUIRE(n_walkers >= 1, "gwz_walkers_create: need at least one walker");
@@ -533,7 +535,8 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     w->acc_steps = 0;
     GWZ_CUDA(cudaMalloc(&w->d_addr, sizeof(uint64_t) * w->n * m->W));
     GWZ_CUDA(cudaMalloc(&w->d_acc, sizeof(double) * w->n * NUM_WALKER_ACC));
-    GWZ_CUDA(cudaMalloc(&w->d_vec, sizeof(double) * NUM_ACC));
+    GWZ_CUDA(cudaMalloc(&w->d_vec, sizeof(double) * NUM_VEC));
+    GWZ_CUDA(cudaMemsetAsync(w->d_vec, 0, sizeof(double) * NUM_VEC, c->stream));
     GWZ_CUDA(cudaMalloc(&w->d_shift, sizeof(double) * 2));
     GWZ_CUDA(cudaMallocHost(&w->h_shift, sizeof(double) * 2));
     DevBuf<uint64_t> d_start;
@@ -546,6 +549,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
 }
 
 extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
+    if (w && w->magic != gwz::GWZ_TAG_WALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_walkers_destroy: not a gwz_walkers handle");
     if (!w) return GWZ_OK;
     cudaSetDevice(w->m->ctx->device);
     cudaFree(w->d_addr);
@@ -556,11 +560,17 @@ extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
     cudaFreeHost(w->h_shift);
     cudaFree(w->d_planes);
     cudaFree(w->d_ref_addr);
+    cudaFree(w->d_ser_tau);
+    cudaFree(w->d_ser_eloc);
+    cudaFree(w->d_blk);
+    cudaFree(w->d_bpartials);
+    w->magic = 0;
     delete w;
     return GWZ_OK;
 }
 
 extern "C" int gwz_walkers_count(const gwz_walkers* w, uint64_t* n_walkers, uint64_t* steps_done) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_count: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_walkers_count: NULL handle");
     if (n_walkers) *n_walkers = w->n;
     if (steps_done) *steps_done = w->steps_done;
@@ -568,6 +578,7 @@ extern "C" int gwz_walkers_count(const gwz_walkers* w, uint64_t* n_walkers, uint
 }
 
 extern "C" int gwz_walkers_get_addresses(gwz_walkers* w, uint64_t* addr_words) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_get_addresses: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w && addr_words, "gwz_walkers_get_addresses: NULL argument");
     gwz_context* c = w->m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -582,6 +593,7 @@ extern "C" int gwz_walkers_get_addresses(gwz_walkers* w, uint64_t* addr_words) {
 }
 
 extern "C" int gwz_walkers_set_addresses(gwz_walkers* w, const uint64_t* addr_words) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_set_addresses: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w && addr_words, "gwz_walkers_set_addresses: NULL argument");
     gwz_context* c = w->m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -596,6 +608,7 @@ extern "C" int gwz_walkers_set_addresses(gwz_walkers* w, const uint64_t* addr_wo
 }
 
 extern "C" int gwz_walkers_set_step_counter(gwz_walkers* w, uint64_t steps_done) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_set_step_counter: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_walkers_set_step_counter: NULL handle");
     w->steps_done = steps_done;
     return GWZ_OK;
@@ -611,19 +624,71 @@ static int ensure_partials(gwz_walkers* w, int grid) {
     return GWZ_OK;
 }
 
-// enqueue burn-in + sampling + per-set reduction on the set's stream (no sync)
+// make room for `rows` more steps of the (tau, E_loc) series behind the `keep_rows` rows that stay valid
+static int ensure_series(gwz_walkers* w, uint64_t keep_rows, uint64_t rows) {
+    gwz_context* c = w->m->ctx;
+    const uint64_t need = keep_rows + rows;
+    if (need <= w->ser_cap) return GWZ_OK;
+    size_t free_b = 0, total_b = 0;
+    GWZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double bytes = 16.0 * (double)need * (double)w->n;
+    const double have = (double)free_b + (keep_rows ? 0.0 : 16.0 * (double)w->ser_cap * (double)w->n);
+    if (bytes > 0.92 * have)
+        return gwz::api_fail(GWZ_ERR_NOMEM, "GWZ_RUN_SERIES: the (tau, E_loc) series of this run (16 B per walker-step) do "
+                                            "not fit in the free device memory; use fewer steps or walkers per call");
+    double *nt = nullptr, *ne = nullptr;
+    if (keep_rows == 0) {  // nothing to carry over: release first
+        cudaFree(w->d_ser_tau);
+        cudaFree(w->d_ser_eloc);
+        w->d_ser_tau = w->d_ser_eloc = nullptr;
+        w->ser_cap = 0;
+    }
+    GWZ_CUDA(cudaMalloc(&nt, sizeof(double) * (size_t)need * w->n));
+    if (cudaMalloc(&ne, sizeof(double) * (size_t)need * w->n) != cudaSuccess) {
+        cudaFree(nt);
+        return gwz::api_fail(GWZ_ERR_NOMEM, "GWZ_RUN_SERIES: out of device memory");
+    }
+    if (keep_rows) {
+        GWZ_CUDA(cudaMemcpyAsync(nt, w->d_ser_tau, sizeof(double) * (size_t)keep_rows * w->n, cudaMemcpyDeviceToDevice, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(ne, w->d_ser_eloc, sizeof(double) * (size_t)keep_rows * w->n, cudaMemcpyDeviceToDevice, c->stream));
+        GWZ_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(w->d_ser_tau);
+        cudaFree(w->d_ser_eloc);
+    }
+    w->d_ser_tau = nt;
+    w->d_ser_eloc = ne;
+    w->ser_cap = need;
+    return GWZ_OK;
+}
+
+// enqueue burn-in + sampling + per-set reduction on the set's stream (no sync).  rec_tau / rec_eloc (+ rec_addr):
+// caller's device buffers for a recording run; GWZ_RUN_SERIES in flags: the set's own series buffers instead.
 static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint64_t burn_in, int kind, unsigned flags,
                        double* rec_tau, double* rec_eloc, uint64_t* rec_addr, bool time_it) {
     gwz_model* m = w->m;
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
+    const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
+    const bool series = (flags & (GWZ_RUN_SERIES | GWZ_RUN_BLOCKING)) != 0 && rec_tau == nullptr;
+    w->blk_valid = false;
+    if (series) {
+        GWZ_REQUIRE(!keep || w->ser_steps == w->acc_steps,
+                    "GWZ_RUN_SERIES with GWZ_RUN_KEEP_ACC: the steps accumulated so far were not recorded");
+        if (!keep) w->ser_steps = 0;
+        if (int rc = ensure_series(w, w->ser_steps, steps)) return rc;
+        rec_tau = w->d_ser_tau + (size_t)w->ser_steps * w->n;
+        rec_eloc = w->d_ser_eloc + (size_t)w->ser_steps * w->n;
+    } else {
+        w->ser_steps = 0;  // whatever was kept no longer covers the estimators
+    }
     const bool record = rec_tau != nullptr;
-    // production sampling runs on the occupation bit-plane representation; recording runs and the
-    // reference-order kernel need the unary addresses step by step
-    const bool planes = (kind == GWZ_KERNEL_BITPARALLEL) && !record && tb.kc == 4 && planes_enabled();
+    // production sampling runs on the occupation bit-plane representation (the incremental kernel can keep the
+    // (tau, E_loc) series); per-step addresses and the reference-order kernel need the unary strings step by step
+    bool planes = (kind == GWZ_KERNEL_BITPARALLEL) && rec_addr == nullptr && tb.kc == 4 && planes_enabled();
+    const bool incr = planes && incr_enabled() && walker_incr_supported(m->N, m->M);
+    if (record && !incr) planes = false;
     if (int rc = planes ? to_planes(w) : to_unary(w)) return rc;
     int grid = 0;
-    const bool incr = planes && incr_enabled() && walker_incr_supported(m->N, m->M);
     if (incr) GWZ_CUDA(walker_incr_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
     else if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
     else GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
@@ -665,7 +730,6 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
         }
         w->steps_done += burn_in;
     }
-    const bool keep = (flags & GWZ_RUN_KEEP_ACC) != 0 && w->acc_steps > 0;
     if (!keep) {
         // New estimator: its reference point (any constant near the mean; it only limits cancellation in
         // the covariance) is the pooled (E, G) of the previous run, or -- the first time -- E_loc and the
@@ -704,8 +768,75 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     if (time_it) GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
     w->steps_done += steps;
     w->acc_steps = keep ? w->acc_steps + steps : steps;
+    if (series) w->ser_steps += steps;
     GWZ_LAUNCH(launch_reduce_partials(w->d_partials, grid, NUM_ACC, w->d_vec, c->stream));
     return GWZ_OK;
+}
+
+// enqueue the per-walker resample + blocking analysis of the set's series and its reduction into d_vec[NUM_ACC..]
+static int enqueue_blocking(gwz_walkers* w, uint64_t len, bool time_it) {
+    gwz_model* m = w->m;
+    gwz_context* c = m->ctx;
+    if (int rc = use_device(c)) return rc;
+    GWZ_REQUIRE(w->ser_steps >= 1, "blocking analysis: no series kept (run with GWZ_RUN_SERIES first)");
+    if (len == 0) len = w->ser_steps;
+    GWZ_REQUIRE(len < (1ull << BLK_MAX_LEVELS), "blocking analysis: resample length too large");
+    int grid = 0;
+    if (blocking_grid(len, w->n, c->prop.multiProcessorCount, &grid) != cudaSuccess)
+        return fail(GWZ_ERR_INVALID, "blocking analysis: resample length too large for the per-level shared-memory store");
+    if (grid > w->bpartials_cap) {
+        cudaFree(w->d_bpartials);
+        w->d_bpartials = nullptr;
+        w->bpartials_cap = 0;
+        GWZ_CUDA(cudaMalloc(&w->d_bpartials, sizeof(double) * NUM_BACC * (size_t)grid));
+        w->bpartials_cap = grid;
+    }
+    if (!w->d_blk) GWZ_CUDA(cudaMalloc(&w->d_blk, sizeof(double) * 5 * w->n));
+    BlockingLaunch L;
+    L.tau = w->d_ser_tau;
+    L.eloc = w->d_ser_eloc;
+    L.stride = w->n;
+    L.n = w->n;
+    L.steps = w->ser_steps;
+    L.len = len;
+    L.acc = (w->ser_steps == w->acc_steps) ? w->d_acc : nullptr;
+    L.acc_stride = w->n;
+    L.shift_e = w->shift_e;
+    L.shift_g = w->shift_g;
+    L.out = w->d_blk;
+    L.out_stride = w->n;
+    L.partials = w->d_bpartials;
+    L.grid = grid;
+    if (time_it) GWZ_CUDA(cudaEventRecord(c->ev2, c->stream));
+    GWZ_LAUNCH(launch_series_blocking(L, c->stream));
+    if (time_it) GWZ_CUDA(cudaEventRecord(c->ev3, c->stream));
+    GWZ_LAUNCH(launch_reduce_partials(w->d_bpartials, grid, NUM_BACC, w->d_vec + NUM_ACC, c->stream));
+    w->blk_valid = true;
+    w->blk_len = len;
+    return GWZ_OK;
+}
+
+static void fill_blocking(const double* b, uint64_t steps, uint64_t len, float ms, bool with_grad,
+                          gwz_blocking_summary* o) {
+    std::memset(o, 0, sizeof(*o));
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    const double nw = b[BACC_WALKERS], nfail = b[BACC_FAIL];
+    o->walkers = (uint64_t)std::llround(nw);
+    o->failed = (uint64_t)std::llround(nfail);
+    o->mean = b[BACC_MEAN] / nw;                       // state.jl:163 / :277
+    o->err_ok = std::sqrt(b[BACC_ERR2]) / nw;          // sqrt(mean(errs)) / walkers with `mean` of a scalar = the scalar
+    o->err = o->failed ? nan : o->err_ok;              // a failed walker contributes NaN to the reference's sum
+    o->err_err = o->failed ? nan : std::sqrt(b[BACC_EE2]) / nw;
+    o->grad[0] = with_grad ? b[BACC_GRAD] / nw : nan;
+    o->k_min = o->k_max = -1;
+    for (int k = 0; k < 32; ++k)
+        if (b[BACC_KHIST + k] > 0.5) {
+            if (o->k_min < 0) o->k_min = k;
+            o->k_max = k;
+        }
+    o->series_steps = steps;
+    o->resample_len = len;
+    o->kernel_ms = ms;
 }
 
 static void fill_result(const double* a, float ms, unsigned flags, gwz_vqmc_result* out) {
@@ -728,12 +859,15 @@ static void fill_result(const double* a, float ms, unsigned flags, gwz_vqmc_resu
     out->pooled_val = pe;
     out->pooled_grad[0] = 2.0 * (a[ACC_TGE] / T - pe * pg);
     out->pooled_var = a[ACC_TEE] / T - pe * pe;
+    out->walker_var = a[ACC_VARW] / nw;
     out->total_time = T;
     out->walkers = (uint64_t)std::llround(nw);
     out->steps = (uint64_t)std::llround(a[ACC_STEPS]);
     out->hops = (uint64_t)std::llround(a[ACC_HOPS]);
     for (int i = 0; i < NUM_ACC; ++i) out->acc[i] = a[i];
     out->kernel_ms = ms;
+    out->reserved = 0.f;
+    std::memset(&out->blocking, 0, sizeof(out->blocking));
     if (flags & GWZ_RUN_POOLED) {  // report the pooled ratio estimator as (val, grad)
         out->val = out->pooled_val;
         out->grad[0] = out->pooled_grad[0];
@@ -741,7 +875,8 @@ static void fill_result(const double* a, float ms, unsigned flags, gwz_vqmc_resu
 }
 
 // combine the per-set vectors: device sum within a context, NCCL all-reduce across contexts/ranks
-static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_vqmc_result* out) {
+// nvec = NUM_ACC, or NUM_VEC when the blocking accumulators travel with the sampling accumulators
+static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_vqmc_result* out, int nvec = NUM_ACC) {
     // group the sets by context (order of first appearance)
     std::vector<gwz_context*> ctxs;
     for (int i = 0; i < n; ++i) {
@@ -761,17 +896,17 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
             }
         GWZ_REQUIRE(rows <= GROUP_ROWS, "gwz_vqmc_run_group: too many walker sets on one device");
         if (rows == 1) {  // the usual case: no second reduction stage
-            GWZ_CUDA(cudaMemcpyAsync(c->d_acc, only->d_vec, sizeof(double) * NUM_ACC, cudaMemcpyDeviceToDevice, c->stream));
+            GWZ_CUDA(cudaMemcpyAsync(c->d_acc, only->d_vec, sizeof(double) * nvec, cudaMemcpyDeviceToDevice, c->stream));
             continue;
         }
         rows = 0;
         for (int i = 0; i < n; ++i)
             if (ws[i]->m->ctx == c) {
-                GWZ_CUDA(cudaMemcpyAsync(c->d_group + (size_t)rows * NUM_ACC, ws[i]->d_vec, sizeof(double) * NUM_ACC,
+                GWZ_CUDA(cudaMemcpyAsync(c->d_group + (size_t)rows * nvec, ws[i]->d_vec, sizeof(double) * nvec,
                                          cudaMemcpyDeviceToDevice, c->stream));
                 ++rows;
             }
-        GWZ_LAUNCH(launch_reduce_partials(c->d_group, rows, NUM_ACC, c->d_acc, c->stream));
+        GWZ_LAUNCH(launch_reduce_partials(c->d_group, rows, nvec, c->d_acc, c->stream));
     }
     bool any_comm = false;
     for (gwz_context* c : ctxs) any_comm |= (c->comm != nullptr);
@@ -784,7 +919,7 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
         GWZ_NCCL(api, api->GroupStart());
         for (gwz_context* c : ctxs) {
             // one ncclAllReduce(sum, float64, NUM_ACC) per run, on the sampling stream
-            int r = api->AllReduce(c->d_acc, c->d_acc, NUM_ACC, kNcclFloat64, kNcclSum, c->comm, c->stream);
+            int r = api->AllReduce(c->d_acc, c->d_acc, nvec, kNcclFloat64, kNcclSum, c->comm, c->stream);
             if (r != kNcclSuccess) {
                 api->GroupEnd();
                 return fail(GWZ_ERR_NCCL, std::string("ncclAllReduce: ") + api->GetErrorString(r));
@@ -794,7 +929,7 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
     }
     for (gwz_context* c : ctxs) {
         if (int rc = use_device(c)) return rc;
-        GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * NUM_ACC, cudaMemcpyDeviceToHost, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * nvec, cudaMemcpyDeviceToHost, c->stream));
         GWZ_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
     int status = GWZ_OK;
@@ -820,6 +955,14 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
         }
     }
     if (out) fill_result(ctxs[0]->h_acc, ms, flags, out);
+    if (out && nvec == NUM_VEC) {
+        gwz_context* c0 = ws[0]->m->ctx;
+        float bms = 0.f;
+        GWZ_CUDA(cudaEventElapsedTime(&bms, c0->ev2, c0->ev3));
+        bool with_grad = true;
+        for (int i = 0; i < n; ++i) with_grad &= (ws[i]->ser_steps == ws[i]->acc_steps);
+        fill_blocking(ctxs[0]->h_acc + NUM_ACC, ws[0]->ser_steps, ws[0]->blk_len, bms, with_grad, &out->blocking);
+    }
     return GWZ_OK;
 }
 
@@ -829,7 +972,8 @@ extern "C" int gwz_vqmc_run_group(gwz_walkers* const* ws, int n, const double* p
     GWZ_REQUIRE(steps_per_walker >= 1, "gwz_vqmc_run: steps_per_walker must be >= 1");
     GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
                 "gwz_vqmc_run: unknown kernel_kind");
-    for (int i = 0; i < n; ++i) GWZ_REQUIRE(ws[i] != nullptr, "gwz_vqmc_run_group: NULL walker set");
+    for (int i = 0; i < n; ++i)
+        GWZ_HANDLE(ws[i], gwz::GWZ_TAG_WALKERS, "gwz_vqmc_run_group: NULL or foreign handle (expected gwz_walkers)");
     GWZ_REQUIRE(std::isfinite(params[0]), "gwz_vqmc_run: non-finite parameter");
     DevTables tb;
     make_tables(ws[0]->m, params[0], choose_kc(ws[0]->m, params[0], false), &tb);
@@ -844,17 +988,21 @@ extern "C" int gwz_vqmc_run_group(gwz_walkers* const* ws, int n, const double* p
         if (int rc = enqueue_run(ws[i], tb, steps_per_walker, burn_in, kernel_kind, flags, nullptr, nullptr, nullptr,
                                  time_it))
             return rc;
+        if (flags & GWZ_RUN_BLOCKING)
+            if (int rc = enqueue_blocking(ws[i], 0, time_it)) return rc;
     }
-    return combine_and_fetch(ws, n, flags, out);
+    return combine_and_fetch(ws, n, flags, out, (flags & GWZ_RUN_BLOCKING) ? NUM_VEC : NUM_ACC);
 }
 
 extern "C" int gwz_vqmc_run(gwz_walkers* w, const double* params, uint64_t steps_per_walker, uint64_t burn_in,
                             int kernel_kind, unsigned flags, gwz_vqmc_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_vqmc_run: NULL or foreign handle (expected a gwz_walkers)");
     gwz_walkers* one[1] = {w};
     return gwz_vqmc_run_group(one, 1, params, steps_per_walker, burn_in, kernel_kind, flags, out);
 }
 
 extern "C" int gwz_walkers_estimates(gwz_walkers* w, double* val_w, double* grad_w) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_estimates: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_walkers_estimates: NULL handle");
     GWZ_REQUIRE(w->acc_steps > 0, "gwz_walkers_estimates: no steps accumulated yet");
     gwz_context* c = w->m->ctx;
@@ -871,6 +1019,7 @@ extern "C" int gwz_walkers_estimates(gwz_walkers* w, double* val_w, double* grad
 
 extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_t steps, int kernel_kind, unsigned flags,
                                    double* tau, double* eloc, uint64_t* addr, gwz_vqmc_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_vqmc_run_record: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w && params && tau && eloc, "gwz_vqmc_run_record: NULL argument");
     GWZ_REQUIRE(steps >= 1, "gwz_vqmc_run_record: steps_per_walker must be >= 1");
     GWZ_REQUIRE(kernel_kind == GWZ_KERNEL_ENUMERATE || kernel_kind == GWZ_KERNEL_BITPARALLEL,
@@ -895,10 +1044,120 @@ extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_
     return combine_and_fetch(one, 1, flags, out);
 }
 
+// ---- device-side error bars (state.jl:50-60, 150-164, 265-285) --------------------------------------------
+// per-walker results [5][stride] -> the caller's arrays
+static int fetch_blocking_rows(gwz_context* c, const double* d_blk, size_t n, double* mean_w, double* err_w,
+                               double* err_err_w, int32_t* k_w, int64_t* blocks_w) {
+    if (mean_w) GWZ_CUDA(cudaMemcpyAsync(mean_w, d_blk, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (err_w) GWZ_CUDA(cudaMemcpyAsync(err_w, d_blk + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (err_err_w) GWZ_CUDA(cudaMemcpyAsync(err_err_w, d_blk + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> kb;
+    if (k_w || blocks_w) {
+        kb.resize(2 * n);
+        GWZ_CUDA(cudaMemcpyAsync(kb.data(), d_blk + 3 * n, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n && k_w; ++i) k_w[i] = (int32_t)kb[i];
+    for (size_t i = 0; i < n && blocks_w; ++i) blocks_w[i] = (int64_t)kb[n + i];
+    return GWZ_OK;
+}
+
+extern "C" int gwz_walkers_blocking(gwz_walkers* w, uint64_t resample_len, gwz_blocking_summary* out, double* mean_w,
+                                    double* err_w, double* err_err_w, int32_t* k_w, int64_t* blocks_w) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_blocking: NULL or foreign handle (expected a gwz_walkers)");
+    GWZ_REQUIRE(w != nullptr, "gwz_walkers_blocking: NULL handle");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const uint64_t len = resample_len ? resample_len : w->ser_steps;
+    if (!(w->blk_valid && w->blk_len == len)) {  // GWZ_RUN_BLOCKING already analysed the default length
+        if (int rc = enqueue_blocking(w, len, true)) return rc;
+    } else {
+        // re-reduce nothing: d_vec[NUM_ACC..] still holds this set's sums
+    }
+    GWZ_CUDA(cudaMemcpyAsync(c->d_acc + NUM_ACC, w->d_vec + NUM_ACC, sizeof(double) * NUM_BACC, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->comm) {
+        const NcclApi* api = nccl_api(nullptr);
+        if (!api) return fail(GWZ_ERR_NCCL, "NCCL unavailable");
+        GWZ_NCCL(api, api->AllReduce(c->d_acc + NUM_ACC, c->d_acc + NUM_ACC, NUM_BACC, kNcclFloat64, kNcclSum, c->comm, c->stream));
+    }
+    GWZ_CUDA(cudaMemcpyAsync(c->h_acc + NUM_ACC, c->d_acc + NUM_ACC, sizeof(double) * NUM_BACC, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    if (out) {
+        float ms = 0.f;
+        GWZ_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+        fill_blocking(c->h_acc + NUM_ACC, w->ser_steps, len, ms, w->ser_steps == w->acc_steps, out);
+    }
+    return fetch_blocking_rows(c, w->d_blk, w->n, mean_w, err_w, err_err_w, k_w, blocks_w);
+}
+
+extern "C" int gwz_walkers_series(gwz_walkers* w, uint64_t* steps, double* tau, double* eloc) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_walkers_series: NULL or foreign handle (expected a gwz_walkers)");
+    GWZ_REQUIRE(w && steps, "gwz_walkers_series: NULL argument");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    *steps = w->ser_steps;
+    const size_t cells = (size_t)w->ser_steps * w->n;
+    if (tau && cells) GWZ_CUDA(cudaMemcpyAsync(tau, w->d_ser_tau, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
+    if (eloc && cells) GWZ_CUDA(cudaMemcpyAsync(eloc, w->d_ser_eloc, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    return GWZ_OK;
+}
+
+extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const double* eloc, uint64_t steps, uint64_t n,
+                                   uint64_t resample_len, gwz_blocking_summary* out, double* mean_w, double* err_w,
+                                   double* err_err_w, int32_t* k_w, int64_t* blocks_w) {
+    GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_series_blocking: NULL or foreign handle (expected a gwz_context)");
+    GWZ_REQUIRE(c && tau && eloc, "gwz_series_blocking: NULL argument");
+    GWZ_REQUIRE(steps >= 1 && n >= 1, "gwz_series_blocking: empty series");  // state.jl:195-197 / "Not enough data"
+    if (int rc = use_device(c)) return rc;
+    const uint64_t len = resample_len ? resample_len : steps;
+    GWZ_REQUIRE(len < (1ull << BLK_MAX_LEVELS), "gwz_series_blocking: resample length too large");
+    int grid = 0;
+    if (blocking_grid(len, (size_t)n, c->prop.multiProcessorCount, &grid) != cudaSuccess)
+        return fail(GWZ_ERR_INVALID, "gwz_series_blocking: resample length too large for the per-level shared-memory store");
+    const size_t cells = (size_t)steps * (size_t)n;
+    DevBuf<double> d_tau, d_eloc, d_out, d_part, d_vec;
+    GWZ_CUDA(d_tau.alloc(cells));
+    GWZ_CUDA(d_eloc.alloc(cells));
+    GWZ_CUDA(d_out.alloc(5 * (size_t)n));
+    GWZ_CUDA(d_part.alloc((size_t)grid * NUM_BACC));
+    GWZ_CUDA(d_vec.alloc(NUM_BACC));
+    GWZ_CUDA(cudaMemcpyAsync(d_tau.p, tau, sizeof(double) * cells, cudaMemcpyHostToDevice, c->stream));
+    GWZ_CUDA(cudaMemcpyAsync(d_eloc.p, eloc, sizeof(double) * cells, cudaMemcpyHostToDevice, c->stream));
+    BlockingLaunch L;
+    L.tau = d_tau.p;
+    L.eloc = d_eloc.p;
+    L.stride = (size_t)n;
+    L.n = (size_t)n;
+    L.steps = steps;
+    L.len = len;
+    L.acc = nullptr;
+    L.acc_stride = 0;
+    L.shift_e = L.shift_g = 0.0;
+    L.out = d_out.p;
+    L.out_stride = (size_t)n;
+    L.partials = d_part.p;
+    L.grid = grid;
+    GWZ_CUDA(cudaEventRecord(c->ev2, c->stream));
+    GWZ_LAUNCH(launch_series_blocking(L, c->stream));
+    GWZ_CUDA(cudaEventRecord(c->ev3, c->stream));
+    GWZ_LAUNCH(launch_reduce_partials(d_part.p, grid, NUM_BACC, d_vec.p, c->stream));
+    double hb[NUM_BACC];
+    GWZ_CUDA(cudaMemcpyAsync(hb, d_vec.p, sizeof(double) * NUM_BACC, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaStreamSynchronize(c->stream));
+    if (out) {
+        float ms = 0.f;
+        GWZ_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
+        fill_blocking(hb, steps, len, ms, false, out);
+    }
+    return fetch_blocking_rows(c, d_out.p, (size_t)n, mean_w, err_w, err_err_w, k_w, blocks_w);
+}
+
 // DVec(res) (state.jl:303-319) without shipping the per-step series to the host
 extern "C" int gwz_vqmc_sample_vector(gwz_walkers* w, const double* params, uint64_t steps, int kernel_kind, unsigned flags,
                                       uint64_t cap, uint64_t* addr_out, double* val_out, uint64_t* count,
                                       gwz_vqmc_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_vqmc_sample_vector: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w && params && count, "gwz_vqmc_sample_vector: NULL argument");
     GWZ_REQUIRE(cap == 0 || (addr_out && val_out), "gwz_vqmc_sample_vector: NULL output buffer");
     GWZ_REQUIRE(steps >= 1, "gwz_vqmc_sample_vector: steps_per_walker must be >= 1");
@@ -962,6 +1221,7 @@ extern "C" int gwz_vqmc_sample_vector(gwz_walkers* w, const double* params, uint
 // ------------------------------------------------------------------------------------------
 extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint64_t dim, uint64_t rank_begin,
                                 uint64_t rank_end, gwz_sweep** out) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_sweep_create: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && out, "gwz_sweep_create: NULL argument");
     GWZ_REQUIRE(m->v == 0.0, "gwz_sweep_create: ExtendedHubbardReal1D models need the gwz_gen_* entry points");
     gwz_context* c = m->ctx;
@@ -1009,6 +1269,7 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
 }
 
 extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
+    if (s && s->magic != gwz::GWZ_TAG_SWEEP) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_sweep_destroy: not a gwz_sweep handle");
     if (!s) return GWZ_OK;
     cudaSetDevice(s->m->ctx->device);
     cudaFree(s->d_basis);
@@ -1018,11 +1279,13 @@ extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
     cudaFree(s->d_mult);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    s->magic = 0;
     delete s;
     return GWZ_OK;
 }
 
 extern "C" int gwz_sweep_dim(const gwz_sweep* s, uint64_t* dim) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_sweep_dim: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(s && dim, "gwz_sweep_dim: NULL argument");
     *dim = s->dim;
     return GWZ_OK;
@@ -1233,6 +1496,7 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
 }
 
 extern "C" int gwz_sweep_val_and_grad(gwz_sweep* s, const double* params, double* val, double* grad, double* acc4) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_sweep_val_and_grad: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(s && params, "gwz_sweep_val_and_grad: NULL argument");
     double a[4];
     if (int rc = sweep_run(s, params, a)) return rc;
@@ -1263,6 +1527,7 @@ extern "C" int gwz_sweep_representative_range(int N, int M, uint64_t rank_begin,
 }
 
 extern "C" int gwz_sweep_val(gwz_sweep* s, const double* params, double* val) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_sweep_val: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(val != nullptr, "gwz_sweep_val: val is NULL");
     return gwz_sweep_val_and_grad(s, params, val, nullptr, nullptr);
 }
@@ -1300,14 +1565,17 @@ static int sweep_terms_impl(gwz_sweep* s, const double* params, uint64_t first, 
 }
 
 extern "C" int gwz_sweep_terms(gwz_sweep* s, const double* params, uint64_t first, uint64_t count, double* out) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_sweep_terms: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(s && params && out, "gwz_sweep_terms: NULL argument");
     return sweep_terms_impl(s, params, first, count, out, nullptr);
 }
 extern "C" int gwz_sweep_states(gwz_sweep* s, uint64_t first, uint64_t count, uint64_t* out) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_sweep_states: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(s && out, "gwz_sweep_states: NULL argument");
     return sweep_terms_impl(s, nullptr, first, count, nullptr, out);
 }
 extern "C" int gwz_sweep_last_kernel_ms(const gwz_sweep* s, float* ms) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_sweep_last_kernel_ms: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(s && ms, "gwz_sweep_last_kernel_ms: NULL argument");
     if (s->ms_pending) {
         gwz_sweep* w = const_cast<gwz_sweep*>(s);
@@ -1396,34 +1664,58 @@ extern "C" int gwz_adaptive_gradient_descent(gwz_objective_fn f_vg, gwz_objectiv
     return GWZ_OK;
 }
 
+static inline bool flags_has_blocking(unsigned f) { return (f & GWZ_RUN_BLOCKING) != 0; }
 struct VqmcObjective {
     gwz_walkers* w;
-    uint64_t steps;
+    uint64_t steps, burn_in;
     int kind;
     unsigned flags;
+    gwz_vqmc_result last;
 };
-static int vqmc_objective(void* user, const double* p, int, double* val, double* err, double* grad) {
-    // val_err_and_grad(qmc::KineticVQMC, p): _reset! keeps walker positions, clears the estimators
-    // (wrapper.jl:74-79,98-105)
+// val_and_grad(qmc::KineticVQMC, p) (wrapper.jl:90-97): _reset! keeps walker positions, clears the estimators
+static int vqmc_objective_vg(void* user, const double* p, int, double* val, double* err, double* grad) {
     VqmcObjective* o = (VqmcObjective*)user;
-    gwz_vqmc_result r;
-    if (int rc = gwz_vqmc_run(o->w, p, o->steps, 0, o->kind, o->flags & ~GWZ_RUN_KEEP_ACC, &r)) return rc;
-    *val = r.val;
-    *err = std::isnan(r.err) ? 0.0 : r.err;
-    grad[0] = r.grad[0];
+    const unsigned fl = o->flags & ~(GWZ_RUN_KEEP_ACC | GWZ_RUN_SERIES | GWZ_RUN_BLOCKING);
+    if (int rc = gwz_vqmc_run(o->w, p, o->steps, o->burn_in, o->kind, fl, &o->last)) return rc;
+    *val = o->last.val;
+    *err = 0.0;
+    grad[0] = o->last.grad[0];
+    return GWZ_OK;
+}
+// val_err_and_grad(qmc::KineticVQMC, p) (wrapper.jl:98-105 -> state.jl:150-164).  With GWZ_RUN_BLOCKING the value, the
+// error bar and the gradient are the reference's (per-walker resample + blocking on the device); without it the
+// error is the cross-walker standard error of the per-walker estimates.
+static int vqmc_objective_veg(void* user, const double* p, int, double* val, double* err, double* grad) {
+    VqmcObjective* o = (VqmcObjective*)user;
+    if (int rc = gwz_vqmc_run(o->w, p, o->steps, o->burn_in, o->kind, o->flags & ~GWZ_RUN_KEEP_ACC, &o->last)) return rc;
+    const gwz_vqmc_result& r = o->last;
+    if ((o->flags & GWZ_RUN_BLOCKING) && !(o->flags & GWZ_RUN_POOLED)) {
+        *val = r.blocking.mean;
+        *err = r.blocking.err;  // NaN when a walker's M test failed: `abs(dval) < err * err_tol` is then false (amsgrad.jl:204)
+        grad[0] = r.blocking.grad[0];
+    } else {
+        *val = r.val;
+        *err = (flags_has_blocking(o->flags) ? r.blocking.err : (std::isnan(r.err) ? 0.0 : r.err));
+        grad[0] = r.grad[0];
+    }
     return GWZ_OK;
 }
 extern "C" int gwz_amsgrad_vqmc(gwz_walkers* w, const double* p0, const gwz_gd_opts* opts, uint64_t steps_per_walker,
-                                int kernel_kind, unsigned flags, gwz_gd_trace* trace) {
+                                uint64_t burn_in, int kernel_kind, unsigned flags, gwz_gd_trace* trace,
+                                gwz_vqmc_result* last) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_amsgrad_vqmc: NULL or foreign handle (expected a gwz_walkers)");
     GWZ_REQUIRE(w && p0 && opts && trace, "gwz_amsgrad_vqmc: NULL argument");
-    VqmcObjective o{w, steps_per_walker, kernel_kind, flags};
-    return gwz_adaptive_gradient_descent(vqmc_objective, vqmc_objective, &o, p0, GWZ_NUM_PARAMS, opts, trace);
+    VqmcObjective o{w, steps_per_walker, burn_in, kernel_kind, flags, {}};
+    const int rc = gwz_adaptive_gradient_descent(vqmc_objective_vg, vqmc_objective_veg, &o, p0, GWZ_NUM_PARAMS, opts, trace);
+    if (last) *last = o.last;
+    return rc;
 }
 static int sweep_objective(void* user, const double* p, int, double* val, double* err, double* grad) {
     *err = 0.0;  // abstract.jl:59-62
     return gwz_sweep_val_and_grad((gwz_sweep*)user, p, val, grad, nullptr);
 }
 extern "C" int gwz_amsgrad_sweep(gwz_sweep* s, const double* p0, const gwz_gd_opts* opts, gwz_gd_trace* trace) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_SWEEP, "gwz_amsgrad_sweep: NULL or foreign handle (expected a gwz_sweep)");
     GWZ_REQUIRE(s && p0 && opts && trace, "gwz_amsgrad_sweep: NULL argument");
     return gwz_adaptive_gradient_descent(sweep_objective, sweep_objective, s, p0, GWZ_NUM_PARAMS, opts, trace);
 }

@@ -14,6 +14,7 @@
 using namespace gwz;
 
 struct gwz_ansatz {
+    uint32_t magic = gwz::GWZ_TAG_ANSATZ;  // handle type tag, checked by every entry point
     gwz_model* m;
     int kind, P, normalize;
     double logK;
@@ -29,6 +30,7 @@ struct gwz_ansatz {
 };
 
 struct gwz_gwalkers {
+    uint32_t magic = gwz::GWZ_TAG_GWALKERS;  // handle type tag, checked by every entry point
     gwz_ansatz* a;
     size_t n;
     uint64_t offset, seed, steps_done, acc_steps;
@@ -45,6 +47,7 @@ struct gwz_gwalkers {
 };
 
 struct gwz_gsweep {
+    uint32_t magic = gwz::GWZ_TAG_GSWEEP;  // handle type tag, checked by every entry point
     gwz_ansatz* a;
     uint64_t* d_basis = nullptr;  // SoA [W][dim]
     uint64_t dim = 0, rank_begin = 0;
@@ -69,11 +72,13 @@ struct gwz_gsweep {
 // ------------------------------------------------------------------------------------------
 extern "C" int gwz_model_create_ext_hubbard1d(gwz_context* ctx, int N, int M, double u, double v, double t,
                                               gwz_model** out) {
+    GWZ_HANDLE(ctx, gwz::GWZ_TAG_CONTEXT, "gwz_model_create_ext_hubbard1d: NULL or foreign handle (expected a gwz_context)");
     if (int rc = gwz_model_create_hubbard1d_gutzwiller(ctx, N, M, u, t, out)) return rc;
     (*out)->v = v;
     return GWZ_OK;
 }
 extern "C" int gwz_model_info_ext(const gwz_model* m, double* v) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_model_info_ext: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && v, "gwz_model_info_ext: NULL argument");
     *v = m->v;
     return GWZ_OK;
@@ -92,6 +97,7 @@ static int ansatz_num_parameters(int kind, int M) {
 }
 
 extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansatz** out) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_ansatz_create: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && out, "gwz_ansatz_create: NULL argument");
     const int M = m->M, N = m->N;
     const int P = ansatz_num_parameters(kind, M);
@@ -162,6 +168,7 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
 }
 extern "C" int gwz_ansatz_create_combination(gwz_model* m, int kind1, int normalize1, int kind2, int normalize2,
                                              gwz_ansatz** out) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_ansatz_create_combination: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && out, "gwz_ansatz_create_combination: NULL argument");
     gwz_ansatz *c1 = nullptr, *c2 = nullptr;
     if (int rc = gwz_ansatz_create(m, kind1, normalize1, &c1)) return rc;
@@ -191,6 +198,7 @@ extern "C" int gwz_ansatz_create_combination(gwz_model* m, int kind1, int normal
 }
 
 extern "C" int gwz_ansatz_destroy(gwz_ansatz* a) {
+    if (a && a->magic != gwz::GWZ_TAG_ANSATZ) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_ansatz_destroy: not a gwz_ansatz handle");
     if (!a) return GWZ_OK;
     if (a->c1) gwz_ansatz_destroy(a->c1);
     if (a->c2) gwz_ansatz_destroy(a->c2);
@@ -200,10 +208,12 @@ extern "C" int gwz_ansatz_destroy(gwz_ansatz* a) {
         if (a->d_par) cudaFree(a->d_par);
         if (a->h_par) cudaFreeHost(a->h_par);
     }
+    a->magic = 0;
     delete a;
     return GWZ_OK;
 }
 extern "C" int gwz_ansatz_info(const gwz_ansatz* a, int* kind, int* num_parameters) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_ANSATZ, "gwz_ansatz_info: NULL or foreign handle (expected a gwz_ansatz)");
     GWZ_REQUIRE(a != nullptr, "gwz_ansatz_info: NULL handle");
     if (kind) *kind = a->kind;
     if (num_parameters) *num_parameters = a->P;
@@ -369,12 +379,14 @@ static int probe_impl(gwz_ansatz* a, const uint64_t* addr_words, size_t n, const
 
 extern "C" int gwz_gen_ansatz_eval(gwz_ansatz* a, const uint64_t* addr_words, size_t n, const double* params, double* val,
                                    double* grad) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_ANSATZ, "gwz_gen_ansatz_eval: NULL or foreign handle (expected a gwz_ansatz)");
     return probe_impl(a, addr_words, n, params, nullptr, val, grad, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                       nullptr);
 }
 extern "C" int gwz_gen_probe_addresses(gwz_ansatz* a, const uint64_t* addr_words, size_t n, const double* params,
                                        const double* u01, double* e_loc, double* residence_time, double* grad_ratio,
                                        int32_t* n_hops, double* rates, int32_t* chosen, uint64_t* next_addr) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_ANSATZ, "gwz_gen_probe_addresses: NULL or foreign handle (expected a gwz_ansatz)");
     return probe_impl(a, addr_words, n, params, u01, nullptr, nullptr, e_loc, residence_time, grad_ratio, n_hops, rates,
                       chosen, next_addr);
 }
@@ -384,6 +396,7 @@ extern "C" int gwz_gen_probe_addresses(gwz_ansatz* a, const uint64_t* addr_words
 // ------------------------------------------------------------------------------------------
 extern "C" int gwz_gwalkers_create(gwz_ansatz* a, uint64_t n_walkers, uint64_t global_offset, const uint64_t* start_addr,
                                    uint64_t seed, gwz_gwalkers** out) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_ANSATZ, "gwz_gwalkers_create: NULL or foreign handle (expected a gwz_ansatz)");
     GWZ_REQUIRE(a && start_addr && out, "gwz_gwalkers_create: NULL argument");
     GWZ_REQUIRE(n_walkers >= 1, "gwz_gwalkers_create: need at least one walker");
     gwz_context* c = a->m->ctx;
@@ -418,6 +431,7 @@ extern "C" int gwz_gwalkers_create(gwz_ansatz* a, uint64_t n_walkers, uint64_t g
     return GWZ_OK;
 }
 extern "C" int gwz_gwalkers_destroy(gwz_gwalkers* w) {
+    if (w && w->magic != gwz::GWZ_TAG_GWALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_gwalkers_destroy: not a gwz_gwalkers handle");
     if (!w) return GWZ_OK;
     if (use_device(w->a->m->ctx) == GWZ_OK) {
         cudaFree(w->d_occ);
@@ -429,16 +443,19 @@ extern "C" int gwz_gwalkers_destroy(gwz_gwalkers* w) {
         if (w->h_shift) cudaFreeHost(w->h_shift);
         cudaFree(w->d_addr1);
     }
+    w->magic = 0;
     delete w;
     return GWZ_OK;
 }
 extern "C" int gwz_gwalkers_count(const gwz_gwalkers* w, uint64_t* n_walkers, uint64_t* steps_done) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gwalkers_count: NULL or foreign handle (expected a gwz_gwalkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_gwalkers_count: NULL handle");
     if (n_walkers) *n_walkers = w->n;
     if (steps_done) *steps_done = w->steps_done;
     return GWZ_OK;
 }
 extern "C" int gwz_gwalkers_get_addresses(gwz_gwalkers* w, uint64_t* addr_words) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gwalkers_get_addresses: NULL or foreign handle (expected a gwz_gwalkers)");
     GWZ_REQUIRE(w && addr_words, "gwz_gwalkers_get_addresses: NULL argument");
     gwz_context* c = w->a->m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -451,6 +468,7 @@ extern "C" int gwz_gwalkers_get_addresses(gwz_gwalkers* w, uint64_t* addr_words)
     return GWZ_OK;
 }
 extern "C" int gwz_gwalkers_set_addresses(gwz_gwalkers* w, const uint64_t* addr_words) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gwalkers_set_addresses: NULL or foreign handle (expected a gwz_gwalkers)");
     GWZ_REQUIRE(w && addr_words, "gwz_gwalkers_set_addresses: NULL argument");
     gwz_context* c = w->a->m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -463,6 +481,7 @@ extern "C" int gwz_gwalkers_set_addresses(gwz_gwalkers* w, const uint64_t* addr_
     return GWZ_OK;
 }
 extern "C" int gwz_gwalkers_set_step_counter(gwz_gwalkers* w, uint64_t steps_done) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gwalkers_set_step_counter: NULL or foreign handle (expected a gwz_gwalkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_gwalkers_set_step_counter: NULL handle");
     w->steps_done = steps_done;
     return GWZ_OK;
@@ -606,15 +625,18 @@ static int gen_run(gwz_gwalkers* w, const double* params, uint64_t steps, uint64
 
 extern "C" int gwz_gen_vqmc_run(gwz_gwalkers* w, const double* params, uint64_t steps_per_walker, uint64_t burn_in,
                                 unsigned flags, gwz_gen_result* out, double* grad, double* grad_err, double* pooled_grad) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gen_vqmc_run: NULL or foreign handle (expected a gwz_gwalkers)");
     return gen_run(w, params, steps_per_walker, burn_in, flags, nullptr, nullptr, nullptr, out, grad, grad_err, pooled_grad);
 }
 extern "C" int gwz_gen_vqmc_run_record(gwz_gwalkers* w, const double* params, uint64_t steps_per_walker, unsigned flags,
                                        double* tau, double* eloc, uint64_t* addr, gwz_gen_result* out, double* grad,
                                        double* grad_err, double* pooled_grad) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gen_vqmc_run_record: NULL or foreign handle (expected a gwz_gwalkers)");
     GWZ_REQUIRE(tau && eloc, "gwz_gen_vqmc_run_record: NULL series buffer");
     return gen_run(w, params, steps_per_walker, 0, flags, tau, eloc, addr, out, grad, grad_err, pooled_grad);
 }
 extern "C" int gwz_gwalkers_estimates(gwz_gwalkers* w, double* val_w, double* grad_w) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_GWALKERS, "gwz_gwalkers_estimates: NULL or foreign handle (expected a gwz_gwalkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_gwalkers_estimates: NULL handle");
     GWZ_REQUIRE(w->acc_steps > 0, "gwz_gwalkers_estimates: no steps accumulated yet");
     gwz_context* c = w->a->m->ctx;
@@ -635,6 +657,7 @@ extern "C" int gwz_gwalkers_estimates(gwz_gwalkers* w, double* val_w, double* gr
 // ------------------------------------------------------------------------------------------
 extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uint64_t dim, uint64_t rank_begin,
                                  uint64_t rank_end, gwz_gsweep** out) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_ANSATZ, "gwz_gsweep_create: NULL or foreign handle (expected a gwz_ansatz)");
     GWZ_REQUIRE(a && out, "gwz_gsweep_create: NULL argument");
     gwz_model* m = a->m;
     gwz_context* c = m->ctx;
@@ -673,6 +696,7 @@ extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uin
     return GWZ_OK;
 }
 extern "C" int gwz_gsweep_destroy(gwz_gsweep* s) {
+    if (s && s->magic != gwz::GWZ_TAG_GSWEEP) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_gsweep_destroy: not a gwz_gsweep handle");
     if (!s) return GWZ_OK;
     if (use_device(s->a->m->ctx) == GWZ_OK) {
         if (s->d_basis) cudaFree(s->d_basis);
@@ -683,16 +707,19 @@ extern "C" int gwz_gsweep_destroy(gwz_gsweep* s) {
         cudaFree(s->d_vec);
         if (s->h_vec) cudaFreeHost(s->h_vec);
     }
+    s->magic = 0;
     delete s;
     return GWZ_OK;
 }
 extern "C" int gwz_gsweep_dim(const gwz_gsweep* s, uint64_t* dim) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_GSWEEP, "gwz_gsweep_dim: NULL or foreign handle (expected a gwz_gsweep)");
     GWZ_REQUIRE(s && dim, "gwz_gsweep_dim: NULL argument");
     *dim = s->dim;
     return GWZ_OK;
 }
 
 extern "C" int gwz_gsweep_val_and_grad(gwz_gsweep* s, const double* params, double* val, double* grad) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_GSWEEP, "gwz_gsweep_val_and_grad: NULL or foreign handle (expected a gwz_gsweep)");
     GWZ_REQUIRE(s && params && val, "gwz_gsweep_val_and_grad: NULL argument");
     gwz_ansatz* a = s->a;
     gwz_context* c = a->m->ctx;
@@ -851,14 +878,17 @@ static int gsweep_terms_impl(gwz_gsweep* s, const double* params, uint64_t first
     return GWZ_OK;
 }
 extern "C" int gwz_gsweep_terms(gwz_gsweep* s, const double* params, uint64_t first, uint64_t count, double* out) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_GSWEEP, "gwz_gsweep_terms: NULL or foreign handle (expected a gwz_gsweep)");
     GWZ_REQUIRE(s && params && out, "gwz_gsweep_terms: NULL argument");
     return gsweep_terms_impl(s, params, first, count, out, nullptr);
 }
 extern "C" int gwz_gsweep_states(gwz_gsweep* s, uint64_t first, uint64_t count, uint64_t* out) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_GSWEEP, "gwz_gsweep_states: NULL or foreign handle (expected a gwz_gsweep)");
     GWZ_REQUIRE(s && out, "gwz_gsweep_states: NULL argument");
     return gsweep_terms_impl(s, nullptr, first, count, nullptr, out);
 }
 extern "C" int gwz_gsweep_last_kernel_ms(const gwz_gsweep* s, float* ms) {
+    GWZ_HANDLE(s, gwz::GWZ_TAG_GSWEEP, "gwz_gsweep_last_kernel_ms: NULL or foreign handle (expected a gwz_gsweep)");
     GWZ_REQUIRE(s && ms, "gwz_gsweep_last_kernel_ms: NULL argument");
     *ms = s->last_ms;
     return GWZ_OK;

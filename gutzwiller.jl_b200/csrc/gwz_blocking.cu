@@ -1,0 +1,182 @@
+// gwz_blocking.cu -- val_err_and_grad(::KineticVQMCWalkerState) (src/kinetic-vqmc/state.jl:50-60) for every
+// walker at once: blocking_analysis(resample(residence_times, local_energies)) on the (tau, E_loc) series the
+// walker kernels keep in HBM (step-major [step][walker]: a warp reads 32 neighbouring walkers of one step as one
+// 256-byte segment), followed by the cross-walker combination of state.jl:150-164 / 265-285.
+//
+// One walker per thread; the algorithm (gwz_blocking.cuh) emits the resampled values in lockstep across the
+// threads and folds them straight into the per-level moments, which live in shared memory in a
+// [level][field][thread] layout (the level index is uniform across the CTA, so it is a broadcast-free,
+// conflict-free access).  Nothing but the series is read and nothing but 5 doubles per walker is written:
+// HBM-bound, algorithmic bytes = 16 per recorded walker-step (+ 40 per walker for the running sums that give the
+// total time, the centre and the gradient).  Interval loads are issued four at a time per thread (a small
+// register window over the strictly sequential consumption) so that one HBM round trip feeds four intervals.
+#include "gwz_internal.h"
+#include "gwz_blocking.cuh"
+
+namespace gwz {
+
+__constant__ double c_chi2_q99[30] = GWZ_CHI2_Q99_TABLE;
+
+struct SmemLevels {
+    double* p;  // already offset by threadIdx.x
+    __device__ __forceinline__ double& operator()(int level, int field) const {
+        return p[(level * BLK_FIELDS + field) * BLOCKING_BLOCK];
+    }
+};
+
+// the window of four consecutive intervals (k & ~3 .. k | 3) held in registers
+struct SeriesWindow {
+    const double* __restrict__ tau;
+    const double* __restrict__ eloc;
+    size_t stride;  // walkers per step row
+    uint64_t n;     // intervals
+    double t0, t1, t2, t3, e0, e1, e2, e3;
+    __device__ __forceinline__ void fill(uint64_t base) {
+        const double* pt = tau + base * stride;
+        const double* pe = eloc + base * stride;
+        const bool b1 = base + 1 < n, b2 = base + 2 < n, b3 = base + 3 < n;
+        t0 = __ldcs(pt);
+        e0 = __ldcs(pe);
+        t1 = b1 ? __ldcs(pt + stride) : 0.0;
+        e1 = b1 ? __ldcs(pe + stride) : 0.0;
+        t2 = b2 ? __ldcs(pt + 2 * stride) : 0.0;
+        e2 = b2 ? __ldcs(pe + 2 * stride) : 0.0;
+        t3 = b3 ? __ldcs(pt + 3 * stride) : 0.0;
+        e3 = b3 ? __ldcs(pe + 3 * stride) : 0.0;
+    }
+    __device__ __forceinline__ void operator()(uint64_t k, double& t, double& e) {
+        const unsigned s = (unsigned)k & 3u;
+        if (s == 0u) fill(k);
+        t = s == 0u ? t0 : (s == 1u ? t1 : (s == 2u ? t2 : t3));
+        e = s == 0u ? e0 : (s == 1u ? e1 : (s == 2u ? e2 : e3));
+    }
+};
+
+__global__ void __launch_bounds__(BLOCKING_BLOCK)
+series_blocking_kernel(const double* __restrict__ tau, const double* __restrict__ eloc, size_t stride, size_t n,
+                       uint64_t steps, uint64_t len, int levels, const double* __restrict__ acc, size_t acc_stride,
+                       double shift_e, double shift_g, double* __restrict__ out, size_t out_stride,
+                       double* __restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* lv = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
+    int* khist = reinterpret_cast<int*>(smem_raw + sizeof(double) * (size_t)(levels > 0 ? levels : 1) * BLK_FIELDS * BLOCKING_BLOCK);
+    if (threadIdx.x < 32) khist[threadIdx.x] = 0;
+    __syncthreads();
+    double a_walkers = 0.0, a_mean = 0.0, a_err2 = 0.0, a_ee2 = 0.0, a_fail = 0.0, a_grad = 0.0;
+
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n; w += nthreads) {
+        const double* tw = tau + w;
+        const double* ew = eloc + w;
+        // total time and the centre of the moments (the time-weighted mean): from the walker's running sums when
+        // they cover exactly this series, else by one pass over the series (same order as the reference's sum)
+        double total, centre, grad_fix_g = 0.0, grad_w = 0.0, val_w = 0.0;
+        if (acc) {
+            const double st = acc[w], ste = acc[acc_stride + w], stg = acc[2 * acc_stride + w],
+                         stge = acc[3 * acc_stride + w];
+            const double inv = 1.0 / st;
+            total = st;
+            val_w = shift_e + ste * inv;
+            centre = val_w;
+            grad_w = 2.0 * (stge * inv - (ste * inv) * (stg * inv));  // state.jl:42-49
+            grad_fix_g = shift_g + stg * inv;                          // mean of the gradient ratio
+        } else {
+            total = 0.0;
+            double te = 0.0;
+            for (uint64_t k = 0; k < steps; ++k) {
+                const double t = tw[k * stride];
+                total = bl_add(total, t);
+                te = fma(t, ew[k * stride], te);
+            }
+            centre = te / total;
+        }
+        BlockingOut o;
+        if (len == 1) {  // blocking_analysis of a single value
+            o.mean = centre;
+            o.err = o.err_err = o.p_cov = NAN;
+            o.k = 0;
+            o.blocks = 1;
+        } else {
+            for (int i = 0; i < levels * BLK_FIELDS; ++i) lv[i * BLOCKING_BLOCK] = 0.0;
+            BlockingStream<SmemLevels> bs(SmemLevels{lv}, levels, centre);
+            SeriesWindow win{tw, ew, stride, steps, 0, 0, 0, 0, 0, 0, 0, 0};
+            resample_stream(steps, len, total, win, [&](double v) { bs.push(v); });
+            bs.finalize(len, c_chi2_q99, o);
+        }
+        // state.jl:57-58: the gradient with val = the blocking mean instead of the weighted mean
+        const double grad_b = grad_w + 2.0 * (val_w - o.mean) * grad_fix_g;
+        if (out) {
+            out[w] = o.mean;
+            out[out_stride + w] = o.err;
+            out[2 * out_stride + w] = o.err_err;
+            out[3 * out_stride + w] = (double)o.k;
+            out[4 * out_stride + w] = (double)o.blocks;
+        }
+        a_walkers += 1.0;
+        a_mean += o.mean;
+        a_grad += grad_b;
+        if (o.k > 0) {
+            a_err2 = fma(o.err, o.err, a_err2);
+            a_ee2 = fma(o.err_err, o.err_err, a_ee2);
+            atomicAdd(&khist[o.k < 32 ? o.k : 31], 1);
+        } else {
+            a_fail += 1.0;
+        }
+    }
+    if (partials == nullptr) return;
+    // block partials in a fixed order (deterministic): warp shuffle -> shared -> thread 0..NUM_BACC-1
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(smem_raw);  // the level store is dead by now
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double vals[6] = {a_walkers, a_mean, a_err2, a_ee2, a_fail, a_grad};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum(vals[i]);
+        if (lane == 0) red[warp * 6 + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NUM_BACC) {
+        double v = 0.0;
+        if (threadIdx.x < 6) {
+            for (int q = 0; q < BLOCKING_BLOCK / 32; ++q) v += red[q * 6 + threadIdx.x];
+        } else {
+            v = (double)khist[threadIdx.x - 6];
+        }
+        partials[(size_t)blockIdx.x * NUM_BACC + threadIdx.x] = v;
+    }
+}
+
+static size_t blocking_smem(int levels) {
+    const size_t lv = sizeof(double) * (size_t)(levels > 0 ? levels : 1) * BLK_FIELDS * BLOCKING_BLOCK;
+    const size_t red = sizeof(double) * 6 * (BLOCKING_BLOCK / 32);
+    return (lv > red ? lv : red) + sizeof(int) * 32;
+}
+
+cudaError_t blocking_grid(uint64_t len, size_t n, int sm_count, int* grid) {
+    const int levels = blocking_levels(len);
+    const size_t smem = blocking_smem(levels);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        if (cudaError_t e = cudaFuncSetAttribute(series_blocking_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+            return e;
+    }
+    int blocks = 0;
+    if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, series_blocking_kernel, BLOCKING_BLOCK, smem))
+        return e;
+    if (blocks < 1) blocks = 1;
+    const size_t resident = (size_t)blocks * (size_t)sm_count;
+    const size_t need = (n + BLOCKING_BLOCK - 1) / BLOCKING_BLOCK;
+    *grid = (int)(need < resident ? need : resident);
+    if (*grid < 1) *grid = 1;
+    return cudaSuccess;
+}
+
+cudaError_t launch_series_blocking(const BlockingLaunch& L, cudaStream_t s) {
+    const int levels = blocking_levels(L.len);
+    series_blocking_kernel<<<L.grid, BLOCKING_BLOCK, blocking_smem(levels), s>>>(
+        L.tau, L.eloc, L.stride, L.n, L.steps, L.len, levels, L.acc, L.acc_stride, L.shift_e, L.shift_g, L.out,
+        L.out_stride, L.partials);
+    return cudaGetLastError();
+}
+
+}  // namespace gwz

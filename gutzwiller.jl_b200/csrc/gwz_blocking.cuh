@@ -1,0 +1,179 @@
+// gwz_blocking.cuh -- error bars of a sampled series: resample! (src/kinetic-vqmc/state.jl:194-231) followed by
+// Rimu.StatsTools.blocking_analysis (Flyvbjerg-Petersen pair averaging + the M test of Jonsson, PRE 98, 043304;
+// called at state.jl:53,273).  ONE implementation, compiled for the device (series_blocking_kernel, gwz_blocking.cu:
+// one walker per thread, series read from HBM) and for the host (gwz_resample / gwz_blocking_analysis on
+// caller-supplied vectors, gwz_stats.cpp).
+//
+// Formulation (differs from the reference's, same numbers):
+//  * resample_stream walks the OUTPUT slots i = 1..len; slot i is either a whole slot covered by the interval that is
+//    still spilling over (reference: first inner loop) or is completed by consuming input intervals (second inner
+//    loop).  Every floating-point operation of state.jl:205-228 is kept, in the same order, without contraction, so
+//    the resampled series is bit-identical to the reference algorithm's for the same total time.  Emission is in
+//    lockstep across walkers (all threads are at the same slot i); only the number of consumed intervals per slot
+//    varies between threads.
+//  * the resampled values are never stored: each is pushed into a BlockingStream, a binary counter of pair averages
+//    that keeps five centred moments per level (sum d, sum d^2, sum d_t d_{t+1}, first d, last d; d = v - centre,
+//    centre = the time-weighted mean).  From them finalize() gets, per level, exactly what Rimu's blocks_with_m
+//    computes: n, var(v; corrected), autocovariance(v, 1; corrected), std_err, std_err_err, the M_j statistic; then
+//    the M test as in the listing published with the paper (quantile indexed by the level: M_k < q[k]).
+// PARITY UNPINNED for blocking_analysis (Rimu's source is not available here); checked against the independent
+// numpy checker tests/blocking_checker.py written from the published listing.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GWZ_HD __host__ __device__ __forceinline__
+#else
+#define GWZ_HD inline
+#endif
+
+namespace gwz {
+
+constexpr int BLK_FIELDS = 5;       // s1, s2, sp, first, last
+constexpr int BLK_MAX_LEVELS = 40;  // series of up to 2^40 values
+
+// uncontracted FP64 arithmetic (the reference is plain Julia: no FMA contraction)
+GWZ_HD double bl_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+GWZ_HD double bl_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+GWZ_HD double bl_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+GWZ_HD double bl_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
+// resample!(result, residence_times, values) with length(result) = len, streamed: emit(v) is called len times, in
+// slot order.  load(k, tau, val) fetches interval k (0-based, k < n); `total` = sum(residence_times).
+template <class LOAD, class EMIT>
+GWZ_HD void resample_stream(uint64_t n, uint64_t len, double total, LOAD&& load, EMIT&& emit) {
+    double t = 0.0;    // state.jl:204  end of the consumed intervals, in slot units
+    double mu = 0.0;   // :206  integral over the part of slot i seen so far
+    double val = 0.0;  // :207  value of the interval that is spilling over
+    uint64_t k = 0;
+    const double dlen = (double)len;
+    for (uint64_t i = 1; i <= len; ++i) {
+        const double di = (double)i;
+        if (t >= di) {  // :212-216  a whole slot inside the spilling interval
+            emit(val);
+            mu = bl_sub(mu, val);
+        } else {
+            while (t < di && k < n) {  // :218-224  consume intervals until slot i is full
+                double tau;
+                load(k, tau, val);
+                const double step = bl_div(bl_mul(dlen, tau), total);  // :220
+                const double room = bl_sub(di, t);
+                mu = bl_add(mu, bl_mul(val, step < room ? step : room));  // :221
+                t = bl_add(t, step);
+                ++k;
+            }
+            emit(mu);                        // :227
+            mu = bl_mul(bl_sub(t, di), val);  // :228  carry the overshoot into the next slot
+        }
+    }
+}
+
+struct BlockingOut {
+    double mean, err, err_err, p_cov;
+    int k;           // 1-based level accepted by the M test; 0: single value; -1: "M test failed, more data needed"
+    int64_t blocks;  // length of the accepted level
+};
+
+// chi-square 0.99 quantiles for 1..30 degrees of freedom, the table printed in Jonsson's listing
+#define GWZ_CHI2_Q99_TABLE                                                                                          \
+    {6.634897,  9.210340,  11.344867, 13.276704, 15.086272, 16.811894, 18.475307, 20.090235, 21.665994, 23.209251, \
+     24.724970, 26.216967, 27.688250, 29.141238, 30.577914, 31.999927, 33.408664, 34.805306, 36.190869, 37.566235, \
+     38.932173, 40.289360, 41.638398, 42.979820, 44.314105, 45.641683, 46.962942, 48.278236, 49.587884, 50.892181}
+
+GWZ_HD int blocking_levels(uint64_t len) {
+    int l = 0;
+    while (l + 1 < 63 && (1ull << (l + 1)) <= len) ++l;  // floor(log2(len))
+    return l;
+}
+
+// STORE: double& operator()(int level, int field); levels x BLK_FIELDS doubles, zero-initialised by the caller.
+template <class STORE>
+struct BlockingStream {
+    STORE st;
+    int levels;
+    uint64_t pushed;
+    double centre;
+
+    GWZ_HD BlockingStream(STORE s, int lv, double c) : st(s), levels(lv), pushed(0), centre(c) {}
+
+    GWZ_HD void push(double v) {
+        double d = v - centre;
+        uint64_t cnt = pushed++;
+        for (int l = 0; l < levels; ++l) {  // cnt = values already seen by level l
+            const double last = st(l, 4);
+            st(l, 0) += d;
+            st(l, 1) += d * d;
+            if (cnt == 0) st(l, 3) = d;
+            else st(l, 2) += last * d;
+            st(l, 4) = d;
+            if (!(cnt & 1ull)) break;  // the first value of a pair waits for its partner
+            d = 0.5 * (last + d);      // Rimu `blocker`: 1/2 (v[2i-1] + v[2i]); an odd last value is dropped
+            cnt >>= 1;
+        }
+    }
+
+    // len = number of values pushed (>= 2); q99 = the quantile table above
+    GWZ_HD void finalize(uint64_t len, const double* q99, BlockingOut& o) {
+        o.mean = centre + st(0, 0) / (double)len;
+        o.err = o.err_err = o.p_cov = NAN;
+        o.k = -1;
+        o.blocks = 0;
+        for (int l = 0; l < levels; ++l) {  // Rimu blocks_with_m, level l+1
+            const double n = (double)(len >> l);
+            const double s1 = st(l, 0), s2 = st(l, 1), sp = st(l, 2), first = st(l, 3), last = st(l, 4);
+            const double m = s1 / n;  // mean of the level, relative to the centre
+            double ss = s2 - n * m * m;
+            ss = ss > 0.0 ? ss : 0.0;
+            const double cs = sp - m * (2.0 * s1 - first - last) + (n - 1.0) * m * m;
+            const double var = ss / (n - 1.0);     // var(v; corrected = true)
+            const double gamma = cs / (n - 1.0);   // autocovariance(v, 1; corrected = true)
+            const double se = sqrt(var / n);
+            const double x = (n - 1.0) * var / (n * n) + gamma;
+            st(l, 0) = n * x * x / (var * var);    // M_j; NaN for a constant series, like the reference
+            st(l, 1) = se;
+            st(l, 2) = se / sqrt(2.0 * (n - 1.0));
+        }
+        double tail = 0.0;
+        for (int l = levels - 1; l >= 0; --l) {  // M_k = sum_{j >= k} M_j  (reverse(cumsum(reverse(mj))))
+            tail += st(l, 0);
+            st(l, 0) = tail;
+        }
+        for (int l = 0; l + 1 < levels; ++l) {  // mtest: k = 1 .. length(m) - 1, m[k] < q[k]
+            if (st(l, 0) < q99[l < 30 ? l : 29]) {
+                o.k = l + 1;
+                o.err = st(l, 1);
+                o.err_err = st(l, 2);
+                o.p_cov = o.err * o.err;
+                o.blocks = (int64_t)(len >> l);
+                break;
+            }
+        }
+    }
+};
+
+}  // namespace gwz

@@ -9,8 +9,10 @@
 
 namespace gwz {
 
-constexpr int NUM_ACC = 12;        // doubles in the cross-device accumulator vector (GWZ_NUM_ACC)
+constexpr int NUM_ACC = 13;        // doubles in the cross-device accumulator vector (GWZ_NUM_ACC)
 constexpr int NUM_WALKER_ACC = 5;  // per-walker running sums kept in HBM: st, stE, stG, stGE, stEE (shifted)
+constexpr int NUM_BACC = 38;       // blocking accumulators (GWZ_NUM_BACC): see BAccSlot
+constexpr int BLOCKING_BLOCK = 128;
 constexpr int WALKER_BLOCK = STEP_BLOCK;
 constexpr int SWEEP_BLOCK = 128;
 
@@ -27,7 +29,19 @@ enum AccSlot {
     ACC_TGE = 8,      // sum tau*G*E
     ACC_TEE = 9,      // sum tau*E^2
     ACC_HOPS = 10,    // hop evaluations of this call
-    ACC_STEPS = 11    // walker-steps of this call
+    ACC_STEPS = 11,   // walker-steps of this call
+    ACC_VARW = 12     // sum_w of the per-walker time-weighted variance of E_loc (state.jl:293-298)
+};
+
+// accumulators of the per-walker blocking analyses (all-reduced with ncclSum next to the vector above)
+enum BAccSlot {
+    BACC_WALKERS = 0,  // walkers analysed
+    BACC_MEAN = 1,     // sum_w b_w.mean                       (state.jl:150-164)
+    BACC_ERR2 = 2,     // sum over the successful walkers of b_w.err^2
+    BACC_EE2 = 3,      // ... of b_w.err_err^2                 (state.jl:279-283)
+    BACC_FAIL = 4,     // walkers whose M test failed (k = -1)
+    BACC_GRAD = 5,     // sum_w grad_w with val = b_w.mean      (state.jl:57-58)
+    BACC_KHIST = 6     // 32 slots: number of walkers accepted at level k (k >= 31 counted in the last slot)
 };
 
 struct WalkerLaunch {
@@ -126,6 +140,23 @@ cudaError_t launch_sweep_collect(int N, int M, int B, uint64_t dim, uint64_t ran
                                  cudaStream_t s);
 cudaError_t sort_representatives(uint64_t* keys, uint32_t* vals, uint64_t n, cudaStream_t s);
 cudaError_t launch_sweep_terms(const SweepLaunch& L, cudaStream_t s);
+
+// ---- per-walker resample + blocking analysis of recorded series (gwz_blocking.cu) -------------
+struct BlockingLaunch {
+    const double* tau;   // [steps][stride]
+    const double* eloc;  // [steps][stride]
+    size_t stride, n;    // walkers per row of the series arrays; walkers analysed (first n columns)
+    uint64_t steps, len; // series length; resample length (state.jl:183 `len`)
+    const double* acc;   // [NUM_WALKER_ACC][acc_stride] running sums of the same steps, or null
+    size_t acc_stride;
+    double shift_e, shift_g;
+    double* out;         // [5][out_stride]: mean, err, err_err, k, blocks per walker, or null
+    size_t out_stride;
+    double* partials;    // [grid][NUM_BACC]
+    int grid;
+};
+cudaError_t blocking_grid(uint64_t len, size_t n, int sm_count, int* grid);
+cudaError_t launch_series_blocking(const BlockingLaunch& L, cudaStream_t s);
 
 // ---- DVec(result) histogram (gwz_hist.cu) ----------------------------------------------------
 cudaError_t launch_hist_fill(uint64_t* tkeys, double* tvals, size_t slots, cudaStream_t s);

@@ -622,6 +622,7 @@ __global__ void sparse_fill_idx_kernel(uint32_t* idx, size_t n, uint32_t v) {
 // C ABI
 // ------------------------------------------------------------------------------------------
 struct gwz_sparse {
+    uint32_t magic = gwz::GWZ_TAG_SPARSE;  // handle type tag, checked by every entry point
     gwz_context* ctx = nullptr;
     uint64_t dim = 0, nnz = 0, max_row = 0;
     int P = 0, G = 8, G_base = 8;  // G_base: lanes per walker from the row lengths; G: raised so that P fits 8 per lane
@@ -644,6 +645,7 @@ struct gwz_sparse {
     SparseDev sd{};
 };
 struct gwz_swalkers {
+    uint32_t magic = gwz::GWZ_TAG_SWALKERS;  // handle type tag, checked by every entry point
     gwz_sparse* h = nullptr;
     size_t n = 0;
     uint64_t offset = 0, seed = 0, steps_done = 0, acc_steps = 0, table_seen = 0;
@@ -700,6 +702,7 @@ static int sp_group(int G, int P) {
 }
 
 extern "C" int gwz_sparse_destroy(gwz_sparse* h) {
+    if (h && h->magic != gwz::GWZ_TAG_SPARSE) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_sparse_destroy: not a gwz_sparse handle");
     if (!h) return GWZ_OK;
     if (use_device(h->ctx) == GWZ_OK) {
         cudaFree(h->d_row_ptr);
@@ -713,12 +716,14 @@ extern "C" int gwz_sparse_destroy(gwz_sparse* h) {
         cudaFree(h->d_tab);
         cudaFree(h->d_partials);
     }
+    h->magic = 0;
     delete h;
     return GWZ_OK;
 }
 
 extern "C" int gwz_sparse_create(gwz_context* ctx, uint64_t dim, const uint64_t* row_ptr, const uint32_t* col,
                                  const double* melem, const double* diag, gwz_sparse** out) {
+    GWZ_HANDLE(ctx, gwz::GWZ_TAG_CONTEXT, "gwz_sparse_create: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(ctx && row_ptr && diag && out, "gwz_sparse_create: NULL argument");
     GWZ_REQUIRE(dim >= 1 && dim <= 0xffffffffull, "gwz_sparse_create: dimension must be in [1, 2^32)");
     GWZ_REQUIRE(row_ptr[0] == 0, "gwz_sparse_create: row_ptr[0] must be 0");
@@ -772,6 +777,7 @@ extern "C" int gwz_sparse_create(gwz_context* ctx, uint64_t dim, const uint64_t*
 
 extern "C" int gwz_sparse_info(const gwz_sparse* h, uint64_t* dim, uint64_t* nnz, uint64_t* max_row, int32_t* num_parameters,
                                int32_t* lanes_per_walker) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_info: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h != nullptr, "gwz_sparse_info: NULL handle");
     if (dim) *dim = h->dim;
     if (nnz) *nnz = h->nnz;
@@ -782,6 +788,7 @@ extern "C" int gwz_sparse_info(const gwz_sparse* h, uint64_t* dim, uint64_t* nnz
 }
 
 extern "C" int gwz_sparse_layout(const gwz_sparse* h, int32_t* row_blocks, uint64_t* block_bytes) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_layout: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h != nullptr, "gwz_sparse_layout: NULL handle");
     if (row_blocks) *row_blocks = h->sd.blk != nullptr;
     if (block_bytes) *block_bytes = h->sd.blk ? (uint64_t)h->sd.BS * 8 : 0;
@@ -867,6 +874,7 @@ static int sp_expand(gwz_sparse* h) {
 // any ansatz as a table: psi[dim] = ansatz(basis[k], params), grad_ratio[dim][P] = grad psi / psi (NULL when P = 0,
 // e.g. VectorAnsatz, vector.jl:6-12)
 extern "C" int gwz_sparse_set_table(gwz_sparse* h, const double* psi, const double* grad_ratio, int32_t P) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_set_table: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h && psi, "gwz_sparse_set_table: NULL argument");
     GWZ_REQUIRE(P >= 0 && P <= 256, "gwz_sparse_set_table: number of parameters must be in [0, 256]");
     GWZ_REQUIRE(P == 0 || grad_ratio, "gwz_sparse_set_table: NULL grad_ratio with P > 0");
@@ -890,6 +898,7 @@ extern "C" int gwz_sparse_set_table(gwz_sparse* h, const double* psi, const doub
 }
 
 extern "C" int gwz_sparse_set_gutzwiller(gwz_sparse* h, double g) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_set_gutzwiller: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h != nullptr, "gwz_sparse_set_gutzwiller: NULL handle");
     GWZ_REQUIRE(std::isfinite(g), "gwz_sparse_set_gutzwiller: non-finite parameter");
     gwz_context* c = h->ctx;
@@ -906,6 +915,7 @@ extern "C" int gwz_sparse_set_gutzwiller(gwz_sparse* h, double g) {
 }
 
 extern "C" int gwz_sparse_get_table(gwz_sparse* h, double* psi, double* grad_ratio) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_get_table: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h != nullptr, "gwz_sparse_get_table: NULL handle");
     GWZ_REQUIRE(h->table_version > 0, "gwz_sparse_get_table: no ansatz table set");
     gwz_context* c = h->ctx;
@@ -966,6 +976,7 @@ static int sp_sweep(gwz_sparse* h, uint64_t row_begin, uint64_t row_end, bool wi
 }
 
 extern "C" int gwz_sparse_sweep(gwz_sparse* h, uint64_t row_begin, uint64_t row_end, double* val, double* grad) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_sweep: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h && val, "gwz_sparse_sweep: NULL argument");
     GWZ_REQUIRE(h->table_version > 0, "gwz_sparse_sweep: no ansatz table set");
     GWZ_REQUIRE(row_begin < row_end && row_end <= h->dim, "gwz_sparse_sweep: bad row range");
@@ -981,6 +992,7 @@ extern "C" int gwz_sparse_sweep(gwz_sparse* h, uint64_t row_begin, uint64_t row_
 }
 
 extern "C" int gwz_sparse_sweep_terms(gwz_sparse* h, uint64_t first, uint64_t count, double* out) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_sweep_terms: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h && out, "gwz_sparse_sweep_terms: NULL argument");
     GWZ_REQUIRE(h->table_version > 0, "gwz_sparse_sweep_terms: no ansatz table set");
     GWZ_REQUIRE(count >= 1 && first + count <= h->dim, "gwz_sparse_sweep_terms: bad row range");
@@ -990,6 +1002,7 @@ extern "C" int gwz_sparse_sweep_terms(gwz_sparse* h, uint64_t first, uint64_t co
 }
 
 extern "C" int gwz_sparse_last_kernel_ms(const gwz_sparse* h, float* ms) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_last_kernel_ms: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h && ms, "gwz_sparse_last_kernel_ms: NULL argument");
     *ms = h->last_ms;
     return GWZ_OK;
@@ -998,6 +1011,7 @@ extern "C" int gwz_sparse_last_kernel_ms(const gwz_sparse* h, float* ms) {
 extern "C" int gwz_sparse_probe(gwz_sparse* h, const uint32_t* idx, size_t n, const double* u01, double* e_loc,
                                 double* residence_time, double* grad_ratio, int32_t* n_hops, double* rates,
                                 int32_t* chosen, uint32_t* next_idx) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_sparse_probe: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h && (n == 0 || idx), "gwz_sparse_probe: NULL argument");
     GWZ_REQUIRE(h->table_version > 0, "gwz_sparse_probe: no ansatz table set");
     if (n == 0) return GWZ_OK;
@@ -1042,6 +1056,7 @@ extern "C" int gwz_sparse_probe(gwz_sparse* h, const uint32_t* idx, size_t n, co
 
 // ---- walkers ---------------------------------------------------------------------------------
 extern "C" int gwz_swalkers_destroy(gwz_swalkers* w) {
+    if (w && w->magic != gwz::GWZ_TAG_SWALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_swalkers_destroy: not a gwz_swalkers handle");
     if (!w) return GWZ_OK;
     if (use_device(w->h->ctx) == GWZ_OK) {
         cudaFree(w->d_idx);
@@ -1050,12 +1065,14 @@ extern "C" int gwz_swalkers_destroy(gwz_swalkers* w) {
         cudaFree(w->d_vec);
         if (w->h_vec) cudaFreeHost(w->h_vec);
     }
+    w->magic = 0;
     delete w;
     return GWZ_OK;
 }
 
 extern "C" int gwz_swalkers_create(gwz_sparse* h, uint64_t n_walkers, uint64_t global_offset, uint32_t start_index,
                                    uint64_t seed, gwz_swalkers** out) {
+    GWZ_HANDLE(h, gwz::GWZ_TAG_SPARSE, "gwz_swalkers_create: NULL or foreign handle (expected a gwz_sparse)");
     GWZ_REQUIRE(h && out, "gwz_swalkers_create: NULL argument");
     GWZ_REQUIRE(n_walkers >= 1, "gwz_swalkers_create: need at least one walker");
     GWZ_REQUIRE(start_index < h->dim, "gwz_swalkers_create: starting index outside the basis");
@@ -1077,12 +1094,14 @@ extern "C" int gwz_swalkers_create(gwz_sparse* h, uint64_t n_walkers, uint64_t g
 }
 
 extern "C" int gwz_swalkers_get_indices(gwz_swalkers* w, uint32_t* idx) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_get_indices: NULL or foreign handle (expected a gwz_swalkers)");
     GWZ_REQUIRE(w && idx, "gwz_swalkers_get_indices: NULL argument");
     if (int rc = use_device(w->h->ctx)) return rc;
     GWZ_CUDA(cudaMemcpy(idx, w->d_idx, sizeof(uint32_t) * w->n, cudaMemcpyDeviceToHost));
     return GWZ_OK;
 }
 extern "C" int gwz_swalkers_set_indices(gwz_swalkers* w, const uint32_t* idx) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_set_indices: NULL or foreign handle (expected a gwz_swalkers)");
     GWZ_REQUIRE(w && idx, "gwz_swalkers_set_indices: NULL argument");
     for (size_t i = 0; i < w->n; ++i) GWZ_REQUIRE(idx[i] < w->h->dim, "gwz_swalkers_set_indices: index outside the basis");
     if (int rc = use_device(w->h->ctx)) return rc;
@@ -1090,6 +1109,7 @@ extern "C" int gwz_swalkers_set_indices(gwz_swalkers* w, const uint32_t* idx) {
     return GWZ_OK;
 }
 extern "C" int gwz_swalkers_set_step_counter(gwz_swalkers* w, uint64_t steps_done) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_set_step_counter: NULL or foreign handle (expected a gwz_swalkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_swalkers_set_step_counter: NULL handle");
     w->steps_done = steps_done;
     return GWZ_OK;
@@ -1224,22 +1244,26 @@ static int sp_run(gwz_swalkers* w, uint64_t steps, uint64_t burn_in, unsigned fl
 
 extern "C" int gwz_swalkers_run(gwz_swalkers* w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags,
                                 gwz_gen_result* out, double* grad, double* grad_err, double* pooled_grad) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_run: NULL or foreign handle (expected a gwz_swalkers)");
     return sp_run(w, steps_per_walker, burn_in, flags, nullptr, nullptr, nullptr, nullptr, out, grad, grad_err, pooled_grad);
 }
 extern "C" int gwz_swalkers_run_record(gwz_swalkers* w, uint64_t steps_per_walker, unsigned flags, double* tau, double* eloc,
                                        uint32_t* idx, gwz_gen_result* out, double* grad, double* grad_err,
                                        double* pooled_grad) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_run_record: NULL or foreign handle (expected a gwz_swalkers)");
     GWZ_REQUIRE(tau && eloc, "gwz_swalkers_run_record: NULL series buffer");
     return sp_run(w, steps_per_walker, 0, flags, tau, eloc, idx, nullptr, out, grad, grad_err, pooled_grad);
 }
 // DVec(res) (state.jl:303-319): total residence time per basis index, hist[dim]
 extern "C" int gwz_swalkers_sample_vector(gwz_swalkers* w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags,
                                           double* hist, gwz_gen_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_sample_vector: NULL or foreign handle (expected a gwz_swalkers)");
     GWZ_REQUIRE(hist != nullptr, "gwz_swalkers_sample_vector: NULL histogram buffer");
     return sp_run(w, steps_per_walker, burn_in, flags, nullptr, nullptr, nullptr, hist, out, nullptr, nullptr, nullptr);
 }
 // per-walker estimates (state.jl:42-49) of the steps accumulated so far
 extern "C" int gwz_swalkers_estimates(gwz_swalkers* w, double* val_w, double* grad_w) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_SWALKERS, "gwz_swalkers_estimates: NULL or foreign handle (expected a gwz_swalkers)");
     GWZ_REQUIRE(w != nullptr, "gwz_swalkers_estimates: NULL handle");
     GWZ_REQUIRE(w->acc_steps > 0 && w->d_acc, "gwz_swalkers_estimates: no steps accumulated yet");
     if (int rc = use_device(w->h->ctx)) return rc;

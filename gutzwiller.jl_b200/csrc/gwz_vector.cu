@@ -257,6 +257,7 @@ vec_rayleigh_kernel(const __grid_constant__ DevModel dm, const __grid_constant__
 // C ABI
 // ------------------------------------------------------------------------------------------
 struct gwz_vansatz {
+    uint32_t magic = gwz::GWZ_TAG_VANSATZ;  // handle type tag, checked by every entry point
     gwz_model* m;
     uint64_t n = 0, slots = 0;
     uint64_t* d_keys = nullptr;
@@ -264,6 +265,7 @@ struct gwz_vansatz {
     VecTable t{};
 };
 struct gwz_vwalkers {
+    uint32_t magic = gwz::GWZ_TAG_VWALKERS;  // handle type tag, checked by every entry point
     gwz_vansatz* a;
     size_t n;
     uint64_t offset, seed, steps_done, acc_steps;
@@ -287,6 +289,7 @@ struct gwz_vwalkers {
 
 extern "C" int gwz_vector_ansatz_create(gwz_model* m, const uint64_t* addr_words, const double* values, uint64_t n,
                                         gwz_vansatz** out) {
+    GWZ_HANDLE(m, gwz::GWZ_TAG_MODEL, "gwz_vector_ansatz_create: NULL or foreign handle (expected a gwz_model)");
     GWZ_REQUIRE(m && addr_words && values && out, "gwz_vector_ansatz_create: NULL argument");
     GWZ_REQUIRE(n >= 1, "gwz_vector_ansatz_create: empty vector");
     GWZ_REQUIRE(m->v == 0.0, "gwz_vector_ansatz_create: HubbardReal1D only");
@@ -338,15 +341,18 @@ extern "C" int gwz_vector_ansatz_create(gwz_model* m, const uint64_t* addr_words
     return GWZ_OK;
 }
 extern "C" int gwz_vector_ansatz_destroy(gwz_vansatz* a) {
+    if (a && a->magic != gwz::GWZ_TAG_VANSATZ) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_vector_ansatz_destroy: not a gwz_vansatz handle");
     if (!a) return GWZ_OK;
     if (use_device(a->m->ctx) == GWZ_OK) {
         cudaFree(a->d_keys);
         cudaFree(a->d_vals);
     }
+    a->magic = 0;
     delete a;
     return GWZ_OK;
 }
 extern "C" int gwz_vector_ansatz_lookup(gwz_vansatz* a, const uint64_t* addr_words, size_t n, double* val) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_VANSATZ, "gwz_vector_ansatz_lookup: NULL or foreign handle (expected a gwz_vansatz)");
     GWZ_REQUIRE(a && val && (n == 0 || addr_words), "gwz_vector_ansatz_lookup: NULL argument");
     if (n == 0) return GWZ_OK;
     gwz_context* c = a->m->ctx;
@@ -366,6 +372,7 @@ extern "C" int gwz_vector_ansatz_lookup(gwz_vansatz* a, const uint64_t* addr_wor
 }
 // LocalEnergyEvaluator(H, VectorAnsatz(v))() over basis = keys(v) (vector.jl:10, localenergy.jl:131-155)
 extern "C" int gwz_vector_ansatz_rayleigh(gwz_vansatz* a, double* val) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_VANSATZ, "gwz_vector_ansatz_rayleigh: NULL or foreign handle (expected a gwz_vansatz)");
     GWZ_REQUIRE(a && val, "gwz_vector_ansatz_rayleigh: NULL argument");
     gwz_context* c = a->m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -386,6 +393,7 @@ extern "C" int gwz_vector_ansatz_rayleigh(gwz_vansatz* a, double* val) {
 
 extern "C" int gwz_vwalkers_create(gwz_vansatz* a, uint64_t n_walkers, uint64_t global_offset, const uint64_t* start_addr,
                                    uint64_t seed, gwz_vwalkers** out) {
+    GWZ_HANDLE(a, gwz::GWZ_TAG_VANSATZ, "gwz_vwalkers_create: NULL or foreign handle (expected a gwz_vansatz)");
     GWZ_REQUIRE(a && start_addr && out, "gwz_vwalkers_create: NULL argument");
     GWZ_REQUIRE(n_walkers >= 1, "gwz_vwalkers_create: need at least one walker");
     gwz_model* m = a->m;
@@ -417,6 +425,7 @@ extern "C" int gwz_vwalkers_create(gwz_vansatz* a, uint64_t n_walkers, uint64_t 
     return GWZ_OK;
 }
 extern "C" int gwz_vwalkers_destroy(gwz_vwalkers* w) {
+    if (w && w->magic != gwz::GWZ_TAG_VWALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_vwalkers_destroy: not a gwz_vwalkers handle");
     if (!w) return GWZ_OK;
     if (use_device(w->a->m->ctx) == GWZ_OK) {
         cudaFree(w->d_addr);
@@ -425,10 +434,12 @@ extern "C" int gwz_vwalkers_destroy(gwz_vwalkers* w) {
         cudaFree(w->d_vec);
         if (w->h_vec) cudaFreeHost(w->h_vec);
     }
+    w->magic = 0;
     delete w;
     return GWZ_OK;
 }
 extern "C" int gwz_vwalkers_get_addresses(gwz_vwalkers* w, uint64_t* addr_words) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_VWALKERS, "gwz_vwalkers_get_addresses: NULL or foreign handle (expected a gwz_vwalkers)");
     GWZ_REQUIRE(w && addr_words, "gwz_vwalkers_get_addresses: NULL argument");
     gwz_context* c = w->a->m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -531,10 +542,12 @@ static int vwalkers_run(gwz_vwalkers* w, uint64_t steps, uint64_t burn_in, unsig
 }
 extern "C" int gwz_vwalkers_run(gwz_vwalkers* w, uint64_t steps_per_walker, uint64_t burn_in, unsigned flags,
                                 gwz_gen_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_VWALKERS, "gwz_vwalkers_run: NULL or foreign handle (expected a gwz_vwalkers)");
     return vwalkers_run(w, steps_per_walker, burn_in, flags, nullptr, nullptr, nullptr, out);
 }
 extern "C" int gwz_vwalkers_run_record(gwz_vwalkers* w, uint64_t steps_per_walker, unsigned flags, double* tau, double* eloc,
                                        uint64_t* addr, gwz_gen_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_VWALKERS, "gwz_vwalkers_run_record: NULL or foreign handle (expected a gwz_vwalkers)");
     GWZ_REQUIRE(tau && eloc, "gwz_vwalkers_run_record: NULL series buffer");
     return vwalkers_run(w, steps_per_walker, 0, flags, tau, eloc, addr, out);
 }

@@ -132,6 +132,7 @@ walker_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTa
             p[ACC_TEE * WALKER_BLOCK] += st * E0 * E0 + 2.0 * E0 * ste + stee;
             p[ACC_HOPS * WALKER_BLOCK] += (double)hops;
             p[ACC_STEPS * WALKER_BLOCK] += (double)steps;
+            p[ACC_VARW * WALKER_BLOCK] += stee * inv - mE * mE;  // var(E_loc, weights tau), uncorrected
         }
     }
 

@@ -17,12 +17,15 @@ __host__ __device__ constexpr size_t incr_smem_bytes(int N) {
     return IncrScratch<NWM>::bytes(N) + sizeof(double) * NUM_ACC * STEP_BLOCK;
 }
 
-template <int NWM, int NP>
+// REC: also keep the (tau, E_loc) series of the launch in HBM, step-major [step][walker] (qmc.jl:89-92 stores them per
+// walker; the device-side blocking analysis of gwz_blocking.cu reads them back)
+template <int NWM, int NP, bool REC>
 __global__ void __launch_bounds__(STEP_BLOCK, NWM <= 2 ? GWZ_INCR_MIN_BLOCKS : (NWM <= 4 ? 4 : 2))
 walker_incr_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
                    const __grid_constant__ PhiloxKeys pk, uint32_t* __restrict__ planes, double* __restrict__ acc, size_t n, uint64_t global_offset,
                    uint64_t step0, uint64_t steps, int accumulate, int reset_acc, double shift_e, double shift_g,
-                   double* __restrict__ partials, int* __restrict__ err_flag) {
+                   double* __restrict__ partials, int* __restrict__ err_flag, double* __restrict__ rec_tau,
+                   double* __restrict__ rec_eloc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const IncrScratch<NWM> sc(smem_raw, dm.N);
     sc.fill_tables(dm.N, tb);
@@ -74,6 +77,10 @@ walker_incr_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
             int nh;
             step_incr<NWM, NP>(pl, dm, tb, sc, bc, bigP, u01, tau, eloc, gr, nh);
             hops += (unsigned)nh;
+            if (REC) {
+                __stcs(rec_tau + (size_t)k * n + w, tau);
+                __stcs(rec_eloc + (size_t)k * n + w, eloc);
+            }
             const double dE = eloc - E0, dG = gr - G0;
             const double tE = tau * dE;
             tcheck += tau;
@@ -111,6 +118,7 @@ walker_incr_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
             p[ACC_TEE * STEP_BLOCK] += st * E0 * E0 + 2.0 * E0 * ste + stee;
             p[ACC_HOPS * STEP_BLOCK] += (double)hops;
             p[ACC_STEPS * STEP_BLOCK] += (double)steps;
+            p[ACC_VARW * STEP_BLOCK] += stee * inv - mE * mE;  // var(E_loc, weights tau), uncorrected
         }
     }
 
@@ -136,24 +144,31 @@ walker_incr_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-template <int NWM, int NP>
+template <int NWM, int NP, bool REC>
 static cudaError_t incr_prepare(int N) {
     const size_t smem = incr_smem_bytes<NWM>(N);
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(walker_incr_kernel<NWM, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(walker_incr_kernel<NWM, NP, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <int NWM, int NP>
 static cudaError_t incr_launch(const WalkerLaunch& L, cudaStream_t s) {
-    if (cudaError_t e = incr_prepare<NWM, NP>(L.dm.N)) return e;
-    walker_incr_kernel<NWM, NP><<<L.grid, STEP_BLOCK, incr_smem_bytes<NWM>(L.dm.N), s>>>(
-        L.dm, L.tb, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate, L.reset_acc,
-        L.accumulate ? L.shift_e : 0.0, L.accumulate ? L.shift_g : 0.0, L.partials, L.err_flag);
+    const bool rec = L.rec_tau != nullptr && L.accumulate;
+    if (cudaError_t e = rec ? incr_prepare<NWM, NP, true>(L.dm.N) : incr_prepare<NWM, NP, false>(L.dm.N)) return e;
+    if (rec)
+        walker_incr_kernel<NWM, NP, true><<<L.grid, STEP_BLOCK, incr_smem_bytes<NWM>(L.dm.N), s>>>(
+            L.dm, L.tb, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate,
+            L.reset_acc, L.shift_e, L.shift_g, L.partials, L.err_flag, L.rec_tau, L.rec_eloc);
+    else
+        walker_incr_kernel<NWM, NP, false><<<L.grid, STEP_BLOCK, incr_smem_bytes<NWM>(L.dm.N), s>>>(
+            L.dm, L.tb, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate,
+            L.reset_acc, L.accumulate ? L.shift_e : 0.0, L.accumulate ? L.shift_g : 0.0, L.partials, L.err_flag, nullptr,
+            nullptr);
     return cudaGetLastError();
 }
 template <int NWM, int NP>
 static cudaError_t incr_occ(int N, int* blocks) {
-    if (cudaError_t e = incr_prepare<NWM, NP>(N)) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, walker_incr_kernel<NWM, NP>, STEP_BLOCK,
+    if (cudaError_t e = incr_prepare<NWM, NP, false>(N)) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, walker_incr_kernel<NWM, NP, false>, STEP_BLOCK,
                                                          incr_smem_bytes<NWM>(N));
 }
 

@@ -110,6 +110,7 @@ walker_planes_kernel(const __grid_constant__ DevModel dm, const __grid_constant_
             p[ACC_TEE * STEP_BLOCK] += st * E0 * E0 + 2.0 * E0 * ste + stee;
             p[ACC_HOPS * STEP_BLOCK] += (double)hops;
             p[ACC_STEPS * STEP_BLOCK] += (double)steps;
+            p[ACC_VARW * STEP_BLOCK] += stee * inv - mE * mE;  // var(E_loc, weights tau), uncorrected
         }
     }
 

@@ -1,23 +1,28 @@
 # GutzwillerB200.jl -- Julia host shim over libgutzwiller_b200.so (C ABI: include/gutzwiller_b200.h).
 #
 # Keeps the call forms of mtsch/Gutzwiller.jl for the HubbardReal1D + GutzwillerAnsatz path:
-#   kinetic_vqmc / kinetic_vqmc! / KineticVQMC / LocalEnergyEvaluator / val_and_grad /
-#   val_err_and_grad / amsgrad / gradient_descent
-# (reference: src/kinetic-vqmc/qmc.jl:129-146, wrapper.jl:45-121, localenergy.jl:81-173,
-#  amsgrad.jl:105-263).  Every method is a thin `ccall`; no arithmetic happens in Julia.
+#   kinetic_vqmc / kinetic_vqmc! / KineticVQMC / LocalEnergyEvaluator / val_and_grad / val_err_and_grad /
+#   local_energy_estimator / mean / var / amsgrad / gradient_descent
+# (reference: src/kinetic-vqmc/qmc.jl:73-146, state.jl:137-164,265-298, wrapper.jl:45-121, localenergy.jl:81-173,
+#  amsgrad.jl:105-263).  Every method is a thin `ccall`; no arithmetic on sampled data happens in Julia.
 #
-# NOTE: Julia is not installed in the build image, so this file has not been executed there.  The
-# Python mirror (gutzwiller.jl_b200/*.py) binds exactly the same symbols and is what the test-suite
-# drives; see INTEGRATION.md for how a maintainer wires this module into Gutzwiller.jl.
+# STATUS: UNEXECUTED.  Julia is not installed in the build image (nor on the GPU boxes), so this file has never been
+# run; it is kept correct by inspection and by tests/test_capi_and_host.py, which checks every `ccall` (symbol,
+# argument count and kinds) and every mirrored struct (field order, types, array lengths) against the C header that
+# gcc compiles for tests/c_consumer.c.  The Python mirror (gutzwiller.jl_b200/*.py) binds exactly the same symbols
+# and is what the GPU test-suite drives; see INTEGRATION.md for how a maintainer wires this module into Gutzwiller.jl.
 module GutzwillerB200
 
 using Rimu
+using Rimu.StatsTools: BlockingResult
 using StaticArrays
+using Statistics
 
-export GPUContext, GPUKineticVQMCResult, GPUKineticVQMC, GPULocalEnergyEvaluator
+export GPUContext, GPUKineticVQMCResult, GPUKineticVQMC, GPULocalEnergyEvaluator, GPUGradientDescentResult
 export GPUAnsatz, GPUGenericVQMC, GPUGenericLocalEnergyEvaluator
-export GPUSparseHamiltonian, GPUSparseVQMC, GPUSparseLocalEnergyEvaluator, sampled_vector
-export kinetic_vqmc, kinetic_vqmc!, val_and_grad, val_err_and_grad, amsgrad, gradient_descent
+export GPUSparseHamiltonian, GPUSparseVQMC, GPUSparseLocalEnergyEvaluator, sampled_vector, recorded_series
+export kinetic_vqmc, kinetic_vqmc!, val_and_grad, val_err_and_grad, local_energy_estimator
+export amsgrad, gradient_descent
 
 const LIB = get(ENV, "GUTZWILLER_B200_LIB",
                 joinpath(@__DIR__, "..", "lib", "libgutzwiller_b200.so"))
@@ -25,30 +30,59 @@ const LIB = get(ENV, "GUTZWILLER_B200_LIB",
 const GWZ_KERNEL_ENUMERATE = Cint(0)
 const GWZ_KERNEL_BITPARALLEL = Cint(1)
 const GWZ_RUN_KEEP_ACC = Cuint(1)
-const GWZ_NUM_ACC = 12
+const GWZ_RUN_POOLED = Cuint(2)
+const GWZ_RUN_SERIES = Cuint(4)
+const GWZ_RUN_BLOCKING = Cuint(8)
+const GWZ_NUM_PARAMS = 1
+const GWZ_NUM_ACC = 13
+const DEFAULT_SEED = 0x9E3779B97F4A7C15
 
-# mirrors `struct gwz_vqmc_result` (P = 1)
+# mirrors `struct gwz_blocking_summary`
+struct BlockingSummary
+    mean::Cdouble
+    err::Cdouble
+    err_err::Cdouble
+    err_ok::Cdouble
+    grad::NTuple{GWZ_NUM_PARAMS,Cdouble}
+    walkers::UInt64
+    failed::UInt64
+    k_min::Int32
+    k_max::Int32
+    series_steps::UInt64
+    resample_len::UInt64
+    kernel_ms::Cfloat
+    reserved::Cfloat
+end
+BlockingSummary() = BlockingSummary(0.0, 0.0, 0.0, 0.0, (0.0,), 0, 0, Int32(-1), Int32(-1), 0, 0, 0f0, 0f0)
+
+# mirrors `struct gwz_vqmc_result`
 struct VqmcResult
     val::Cdouble
     err::Cdouble
-    grad::NTuple{1,Cdouble}
-    grad_err::NTuple{1,Cdouble}
+    grad::NTuple{GWZ_NUM_PARAMS,Cdouble}
+    grad_err::NTuple{GWZ_NUM_PARAMS,Cdouble}
     pooled_val::Cdouble
-    pooled_grad::NTuple{1,Cdouble}
+    pooled_grad::NTuple{GWZ_NUM_PARAMS,Cdouble}
     pooled_var::Cdouble
+    walker_var::Cdouble
     total_time::Cdouble
     walkers::UInt64
     steps::UInt64
     hops::UInt64
     acc::NTuple{GWZ_NUM_ACC,Cdouble}
     kernel_ms::Cfloat
+    reserved::Cfloat
+    blocking::BlockingSummary
 end
+VqmcResult() = VqmcResult(0.0, 0.0, (0.0,), (0.0,), 0.0, (0.0,), 0.0, 0.0, 0.0, 0, 0, 0,
+                          ntuple(_ -> 0.0, GWZ_NUM_ACC), 0f0, 0f0, BlockingSummary())
 
 function check(rc::Integer)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:gwz_last_error, LIB), Cstring, ()))
     rc == 1 && throw(ArgumentError(msg))           # GWZ_ERR_INVALID
     rc == 4 && error(msg)                          # "Infinite residence time" (qmc.jl:34-36)
+    rc == 5 && throw(OutOfMemoryError())           # GWZ_ERR_NOMEM
     error("libgutzwiller_b200 [status $rc]: $msg")
 end
 
@@ -66,7 +100,12 @@ mutable struct GPUContext
     end
 end
 const DEFAULT_CONTEXT = Ref{Union{Nothing,GPUContext}}(nothing)
-default_context() = something(DEFAULT_CONTEXT[], (DEFAULT_CONTEXT[] = GPUContext(0)))
+function default_context()
+    if isnothing(DEFAULT_CONTEXT[])
+        DEFAULT_CONTEXT[] = GPUContext(0)
+    end
+    return DEFAULT_CONTEXT[]::GPUContext
+end
 
 "Join the contexts of several devices of this process in one NCCL communicator."
 function comm_init_all(ctxs::Vector{GPUContext})
@@ -74,6 +113,7 @@ function comm_init_all(ctxs::Vector{GPUContext})
     check(ccall((:gwz_context_comm_init_all, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), ptrs, length(ptrs)))
 end
 
+# u and t are type parameters of Rimu's HubbardReal1D{TT,A,U,T}
 _ut(::HubbardReal1D{<:Any,<:Any,U,T}) where {U,T} = (Float64(U), Float64(T))
 
 mutable struct GPUModel
@@ -109,20 +149,33 @@ function address_from_words(m::GPUModel, ::Type{A}, words::AbstractVector{UInt64
 end
 
 # ---------------------------------------------------------------------------------------------
-# kinetic_vqmc / KineticVQMCResult  (qmc.jl:73-146, state.jl:137-164,287-292)
+# kinetic_vqmc / KineticVQMCResult  (qmc.jl:73-146, state.jl:137-164,265-298)
 # ---------------------------------------------------------------------------------------------
+"""
+    GPUKineticVQMCResult
+
+Stands in for `KineticVQMCResult` (state.jl:75-77): the walkers live in HBM behind `walkers`; the parameters are kept
+with the result like `KineticVQMCWalkerState.params` (state.jl:13), so `kinetic_vqmc!(res; steps)` needs none.
+The (residence_time, local_energy) series of the accumulated steps stay in HBM (`GWZ_RUN_SERIES`) for
+`val_err_and_grad(res)` / `local_energy_estimator(res)`.
+"""
 mutable struct GPUKineticVQMCResult{H,A}
     hamiltonian::H
     ansatz::A
     model::GPUModel
     walkers::Ptr{Cvoid}
     n_walkers::Int
+    params::SVector{GWZ_NUM_PARAMS,Float64}
     steps::Int          # per walker, accumulated in the estimators
+    burn_in::Int
+    keep_series::Bool
     last::VqmcResult
 end
-Base.length(res::GPUKineticVQMCResult) = res.steps * res.n_walkers
+Base.length(res::GPUKineticVQMCResult) = res.steps * res.n_walkers      # sum(length, res.states)
+Base.keytype(res::GPUKineticVQMCResult) = typeof(starting_address(res.hamiltonian))
+Base.valtype(::GPUKineticVQMCResult) = Float64
 
-function _make_walkers(model::GPUModel, H, walkers::Integer; seed::UInt64=0x9E3779B97F4A7C15, offset::Integer=0)
+function _make_walkers(model::GPUModel, H, walkers::Integer; seed::UInt64=DEFAULT_SEED, offset::Integer=0)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     start = address_words(model, starting_address(H))      # state.jl:26
     check(ccall((:gwz_walkers_create, LIB), Cint,
@@ -131,43 +184,166 @@ function _make_walkers(model::GPUModel, H, walkers::Integer; seed::UInt64=0x9E37
     return r[]
 end
 
-function _run!(res::GPUKineticVQMCResult, params, steps::Integer; keep::Bool, burn_in::Integer=0,
-               kernel=GWZ_KERNEL_BITPARALLEL)
-    p = Float64[only(params)]
-    out = Ref{VqmcResult}()
+# one gwz_vqmc_run; flags select what is kept (series) and analysed (blocking) on the device
+function _run!(res::GPUKineticVQMCResult, steps::Integer; keep::Bool, flags::Cuint=Cuint(0),
+               kernel::Cint=GWZ_KERNEL_BITPARALLEL)
+    p = Float64[res.params[1]]
+    out = Ref(VqmcResult())
+    fl = flags | (keep ? GWZ_RUN_KEEP_ACC : Cuint(0)) | (res.keep_series ? GWZ_RUN_SERIES : Cuint(0))
+    burn = (keep && res.steps > 0) ? 0 : res.burn_in
     check(ccall((:gwz_vqmc_run, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cdouble}, UInt64, UInt64, Cint, Cuint, Ref{VqmcResult}),
-                res.walkers, p, steps, burn_in, kernel, keep ? GWZ_RUN_KEEP_ACC : Cuint(0), out))
+                res.walkers, p, steps, burn, kernel, fl, out))
     res.last = out[]
     res.steps = keep ? res.steps + steps : steps
     return res
 end
+
+_default_walkers(samples) = min(2^20, prevpow(2, max(1, round(Int, samples) ÷ 1024)))
 
 """
     kinetic_vqmc(H::HubbardReal1D, ansatz::GutzwillerAnsatz, params; samples=1e6, walkers, steps)
 
 Drop-in for `Gutzwiller.kinetic_vqmc` (qmc.jl:129-146) running on the GPU.  `walkers` defaults to the
 largest power of two leaving >= 1024 steps per walker (the reference default is thread-count derived,
-qmc.jl:132); an explicit `walkers`/`steps`/`samples` is honoured exactly.
+qmc.jl:132); an explicit `walkers`/`steps`/`samples` is honoured exactly.  `keep_series=false` drops the per-step
+series (16 B of HBM per walker-step); `val_err_and_grad(res)` then reports the cross-walker standard error.
 """
 function kinetic_vqmc(H::HubbardReal1D, ansatz, params;
                       samples=1e6,
-                      walkers=min(2^20, prevpow(2, max(1, Int(samples) ÷ 1024))),
+                      walkers=_default_walkers(samples),
                       steps=round(Int, samples / walkers),
-                      burn_in=0, seed=0x9E3779B97F4A7C15, ctx=default_context())
+                      burn_in=0, seed=DEFAULT_SEED, keep_series=true, ctx=default_context())
     model = GPUModel(H, ctx)
     w = _make_walkers(model, H, walkers; seed)
-    res = GPUKineticVQMCResult(H, ansatz, model, w, Int(walkers), 0, VqmcResult(ntuple(_ -> 0, 13)...))
+    res = GPUKineticVQMCResult(H, ansatz, model, w, Int(walkers), SVector{GWZ_NUM_PARAMS,Float64}(params...), 0,
+                               Int(burn_in), keep_series, VqmcResult())
     finalizer(r -> ccall((:gwz_walkers_destroy, LIB), Cint, (Ptr{Cvoid},), r.walkers), res)
-    return _run!(res, params, steps; keep=false, burn_in)
+    return _run!(res, steps; keep=false)
 end
 
-"`kinetic_vqmc!(res; steps)` (qmc.jl:108-111): continue from the walkers' current addresses."
-kinetic_vqmc!(res::GPUKineticVQMCResult, params; steps=res.steps) = _run!(res, params, steps; keep=true)
+"`kinetic_vqmc!(res; steps=length(res.states[1]))` (qmc.jl:108-111): continue from the walkers' current addresses."
+kinetic_vqmc!(res::GPUKineticVQMCResult; steps=res.steps) = _run!(res, steps; keep=true)
 
-val_and_grad(res::GPUKineticVQMCResult) = (res.last.val, SVector(res.last.grad))        # state.jl:137-149
-val_err_and_grad(res::GPUKineticVQMCResult) = (res.last.val, res.last.err, SVector(res.last.grad))
-Statistics_mean(res::GPUKineticVQMCResult) = res.last.val                                 # state.jl:287-292
+# state.jl:137-149
+val_and_grad(res::GPUKineticVQMCResult) = (res.last.val, SVector(res.last.grad))
+
+# gwz_walkers_blocking: per-walker blocking_analysis(resample(tau, E; len)) on the device
+function _blocking(res::GPUKineticVQMCResult; resample_length::Integer=0, per_walker::Bool=false)
+    n = per_walker ? res.n_walkers : 0
+    mean_w, err_w, ee_w = zeros(n), zeros(n), zeros(n)
+    k_w, blocks_w = zeros(Int32, n), zeros(Int64, n)
+    summ = Ref(BlockingSummary())
+    # arrays are passed as such (ccall keeps them alive); C_NULL = "not wanted"
+    check(ccall((:gwz_walkers_blocking, LIB), Cint,
+                (Ptr{Cvoid}, UInt64, Ref{BlockingSummary}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}, Ptr{Int64}),
+                res.walkers, resample_length, summ,
+                per_walker ? mean_w : C_NULL, per_walker ? err_w : C_NULL, per_walker ? ee_w : C_NULL,
+                per_walker ? k_w : C_NULL, per_walker ? blocks_w : C_NULL))
+    return summ[], mean_w, err_w, ee_w, k_w, blocks_w
+end
+
+"""
+    val_err_and_grad(res::GPUKineticVQMCResult)
+
+state.jl:150-164: per walker `blocking_analysis(resample(residence_times, local_energies))`, value = mean of the
+blocking means, error = sqrt(sum of err^2) / walkers, gradient with the blocking mean -- computed by the device kernel
+over the series kept in HBM.  Without kept series (`keep_series=false`) the error is the cross-walker standard error.
+"""
+function val_err_and_grad(res::GPUKineticVQMCResult)
+    if res.keep_series
+        b = res.last.blocking.walkers > 0 ? res.last.blocking : _blocking(res)[1]
+        return b.mean, b.err, SVector(b.grad)
+    end
+    return res.last.val, res.last.err, SVector(res.last.grad)
+end
+
+"`CombinedBlockingResult` (state.jl:238-256) of a GPU run; `results` as in the reference for up to 2^16 walkers."
+struct GPUCombinedBlockingResult
+    mean::Float64
+    err::Float64
+    err_err::Float64
+    results::Vector{BlockingResult{Float64}}
+    k_range::Tuple{Int,Int}
+    failed::Int
+end
+function Base.show(io::IO, r::GPUCombinedBlockingResult)
+    println(io, "CombinedBlockingResult{Float64}")
+    println(io, "  mean = ", r.mean, " ± ", r.err)
+    println(io, "  with uncertainty of ± ", r.err_err)
+    if r.failed > 0
+        print(io, "  Blocking unsuccessful for ", r.failed, " walkers.")
+    else
+        print(io, "  Combined blocking results. (k ∈ ", r.k_range[1], " … ", r.k_range[2], ")")
+    end
+end
+
+"`local_energy_estimator(res; resample_length=length(first(res.states)))` (state.jl:265-285)."
+function local_energy_estimator(res::GPUKineticVQMCResult; resample_length=res.steps)
+    res.keep_series || throw(ArgumentError("this run kept no series (keep_series=false)"))
+    per_walker = res.n_walkers <= 2^16
+    b, m, e, ee, k, blocks = _blocking(res; resample_length, per_walker)
+    results = [BlockingResult(m[i], e[i], ee[i], e[i]^2, Int(k[i]), Int(blocks[i])) for i in 1:length(m)]
+    return GPUCombinedBlockingResult(b.mean, b.err, b.err_err, results, (Int(b.k_min), Int(b.k_max)), Int(b.failed))
+end
+
+Statistics.mean(res::GPUKineticVQMCResult) = res.last.val            # state.jl:287-292
+Statistics.var(res::GPUKineticVQMCResult) = res.last.walker_var      # state.jl:293-298
+
+function Base.show(io::IO, res::GPUKineticVQMCResult)                 # state.jl:78-86
+    v, e, _ = val_err_and_grad(res)
+    println(io, "KineticVQMCResult (GPU)")
+    println(io, "  walkers:      ", res.n_walkers)
+    println(io, "  samples:      ", length(res))
+    print(io, "  local energy: ", round(v; sigdigits=5), " ± ", round(e; sigdigits=5))
+end
+
+"""
+    recorded_series(res; steps) -> (residence_times, local_energies, addresses)
+
+A recording run (`gwz_vqmc_run_record`): `steps` more steps whose per-step rows (state.jl:91-132) are shipped to the
+host: `residence_times[step, walker]`, `local_energies[step, walker]`, `addresses[step, walker]`.
+"""
+function recorded_series(res::GPUKineticVQMCResult{H}; steps::Integer=res.steps) where {H}
+    n, W = res.n_walkers, res.model.W
+    tau = zeros(Cdouble, n, steps)            # C layout [step][walker] = column-major (walker, step)
+    eloc = zeros(Cdouble, n, steps)
+    addr = zeros(UInt64, W, n, steps)
+    out = Ref(VqmcResult())
+    p = Float64[res.params[1]]
+    check(ccall((:gwz_vqmc_run_record, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, UInt64, Cint, Cuint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{UInt64}, Ref{VqmcResult}),
+                res.walkers, p, steps, GWZ_KERNEL_BITPARALLEL, Cuint(0), tau, eloc, addr, out))
+    res.last = out[]
+    res.steps = steps
+    A = typeof(starting_address(res.hamiltonian))
+    addresses = [address_from_words(res.model, A, addr[:, w, k]) for k in 1:steps, w in 1:n]
+    return permutedims(tau), permutedims(eloc), addresses
+end
+
+"""
+    sampled_vector(res; steps) -> DVec
+
+`DVec(res)` (state.jl:303-319) for single-word addresses: `steps` more steps whose residence times are deposited on
+their addresses in an HBM hash table (`gwz_vqmc_sample_vector`), normalised.
+"""
+function sampled_vector(res::GPUKineticVQMCResult; steps::Integer=res.steps)
+    cap = UInt64(min(big(steps) * res.n_walkers, big(dimension(res.hamiltonian))))
+    addr, vals = zeros(UInt64, cap), zeros(Cdouble, cap)
+    count, out = Ref{UInt64}(0), Ref(VqmcResult())
+    p = Float64[res.params[1]]
+    check(ccall((:gwz_vqmc_sample_vector, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, UInt64, Cint, Cuint, UInt64, Ptr{UInt64}, Ptr{Cdouble}, Ref{UInt64}, Ref{VqmcResult}),
+                res.walkers, p, steps, GWZ_KERNEL_BITPARALLEL, Cuint(0), cap, addr, vals, count, out))
+    res.last = out[]
+    res.steps = steps
+    A = typeof(starting_address(res.hamiltonian))
+    dv = DVec{A,Float64}()
+    for i in 1:Int(count[])
+        dv[address_from_words(res.model, A, addr[i:i])] = vals[i]
+    end
+    return dv
+end
 
 # ---------------------------------------------------------------------------------------------
 # KineticVQMC (wrapper.jl:45-121)
@@ -178,22 +354,33 @@ struct GPUKineticVQMC{R}
     result::R
 end
 function GPUKineticVQMC(H::HubbardReal1D, ansatz; samples=1e6,
-                        walkers=min(2^20, prevpow(2, max(1, Int(samples) ÷ 1024))),
-                        steps=round(Int, samples / walkers), kwargs...)
-    res = kinetic_vqmc(H, ansatz, 0.0; walkers, steps=1, kwargs...)   # allocate walkers at starting_address
+                        walkers=_default_walkers(samples),
+                        steps=round(Int, samples / walkers),                               # wrapper.jl:56
+                        burn_in=0, seed=DEFAULT_SEED, ctx=default_context())
+    model = GPUModel(H, ctx)
+    w = _make_walkers(model, H, walkers; seed)              # all walkers at starting_address(H), nothing sampled yet
+    res = GPUKineticVQMCResult(H, ansatz, model, w, Int(walkers), SVector{GWZ_NUM_PARAMS,Float64}(0.0), 0,
+                               Int(burn_in), false, VqmcResult())
+    finalizer(r -> ccall((:gwz_walkers_destroy, LIB), Cint, (Ptr{Cvoid},), r.walkers), res)
     return GPUKineticVQMC(Int(steps), Int(walkers), res)
 end
+# _reset! (wrapper.jl:74-79): new parameters, estimators cleared, walker positions kept
+function _reset_and_run!(ke::GPUKineticVQMC, params, steps; flags::Cuint=Cuint(0))
+    ke.result.params = SVector{GWZ_NUM_PARAMS,Float64}(params...)
+    return _run!(ke.result, steps; keep=false, flags)
+end
 function (ke::GPUKineticVQMC)(params; samples=ke.steps * ke.walkers, steps=samples ÷ ke.walkers)
-    return _run!(ke.result, params, steps; keep=false).last.val                              # wrapper.jl:81-88
+    return _reset_and_run!(ke, params, steps).last.val                                      # wrapper.jl:81-88
 end
 function val_and_grad(ke::GPUKineticVQMC, params; samples=ke.steps * ke.walkers, steps=samples ÷ ke.walkers)
-    return val_and_grad(_run!(ke.result, params, steps; keep=false))                         # wrapper.jl:90-97
+    return val_and_grad(_reset_and_run!(ke, params, steps))                                 # wrapper.jl:90-97
 end
 function val_err_and_grad(ke::GPUKineticVQMC, params; samples=ke.steps * ke.walkers, steps=samples ÷ ke.walkers)
-    return val_err_and_grad(_run!(ke.result, params, steps; keep=false))                     # wrapper.jl:98-105
+    b = _reset_and_run!(ke, params, steps; flags=GWZ_RUN_BLOCKING).last.blocking            # wrapper.jl:98-105
+    return b.mean, b.err, SVector(b.grad)
 end
 function (ke::GPUKineticVQMC)(F, G, params)                                                  # wrapper.jl:107-121
-    res = _run!(ke.result, params, ke.steps; keep=false)
+    res = _reset_and_run!(ke, params, ke.steps)
     !isnothing(G) && (G .= res.last.grad)
     return isnothing(F) ? nothing : res.last.val
 end
@@ -232,12 +419,14 @@ function val_and_grad(le::GPULocalEnergyEvaluator, params)                      
                 (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), le.sweep, p, val, grad, C_NULL))
     return val[], SVector{1,Float64}(grad)
 end
+val_err_and_grad(le::GPULocalEnergyEvaluator, params) = ((v, g) = val_and_grad(le, params); (v, 0.0, g))  # abstract.jl:59-62
 function (le::GPULocalEnergyEvaluator)(params)                                               # localenergy.jl:131-155
     p = Float64[only(params)]
     val = Ref{Cdouble}(0.0)
     check(ccall((:gwz_sweep_val, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ref{Cdouble}), le.sweep, p, val))
     return val[]
 end
+(le::GPULocalEnergyEvaluator)(p1::Number, ps::Number...) = le((p1, ps...))                   # localenergy.jl:171-173
 function (le::GPULocalEnergyEvaluator)(F, G, params)                                         # localenergy.jl:157-169
     if !isnothing(G)
         val, grad = val_and_grad(le, params)
@@ -249,9 +438,10 @@ function (le::GPULocalEnergyEvaluator)(F, G, params)                            
 end
 
 # ---------------------------------------------------------------------------------------------
-# amsgrad / gradient_descent on the two GPU objectives (amsgrad.jl:105-263): the loop runs inside
-# the library; the trace comes back as plain vectors.  (Gutzwiller.amsgrad itself also works
-# unchanged on these objects, since they implement val_and_grad / val_err_and_grad.)
+# amsgrad / gradient_descent (amsgrad.jl:105-263).  The loop runs inside the library: natively for the two bit-level
+# objectives (no Julia code between iterations), through C callbacks for any other objective that implements
+# val_and_grad / val_err_and_grad (any number of parameters).  Gutzwiller.amsgrad itself also works unchanged on all
+# GPU objectives, since they implement those two functions.
 # ---------------------------------------------------------------------------------------------
 struct GdOpts
     maxiter::Int32
@@ -283,32 +473,124 @@ mutable struct GdTrace
     param_delta::Ptr{Cdouble}
 end
 
-function _descend(f, p0; use_amsgrad, maxiter=100, α=0.01, β1=0.1, β2=0.01, early_stop=true,
-                  grad_tol=√eps(Float64), param_tol=√eps(Float64), val_tol=√eps(Float64), err_tol=0.0)
-    rows = maxiter + 1
-    bufs = [zeros(Cdouble, rows) for _ in 1:7]
-    opts = GdOpts(maxiter, use_amsgrad, early_stop, 0, α, β1, β2, grad_tol, param_tol, val_tol, err_tol,
-                  C_NULL, C_NULL, C_NULL)
-    GC.@preserve bufs begin
-        tr = GdTrace(0, 0, 0, 1, (pointer(b) for b in bufs)...)
-        p = Float64[only(p0)]
-        if f isa GPUKineticVQMC
-            check(ccall((:gwz_amsgrad_vqmc, LIB), Cint,
-                        (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, UInt64, Cint, Cuint, Ref{GdTrace}),
-                        f.result.walkers, p, opts, f.steps, GWZ_KERNEL_BITPARALLEL, Cuint(0), tr))
-        else
-            check(ccall((:gwz_amsgrad_sweep, LIB), Cint,
-                        (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, Ref{GdTrace}), f.sweep, p, opts, tr))
-        end
-        n = tr.iterations
-        reason = ("iterations", "params", "gradient", "value", "errorbars")[tr.reason + 1]
-        return (; iterations=Int(n), converged=tr.converged != 0, reason,
-                param=bufs[1][1:n], value=bufs[2][1:n], error=bufs[3][1:n], gradient=bufs[4][1:n],
-                first_moment=bufs[5][1:n], second_moment=bufs[6][1:n], param_delta=bufs[7][1:n])
+"`GradientDescentResult` (amsgrad.jl:9-25) of a GPU-side descent; same field names."
+struct GPUGradientDescentResult{N,F}
+    fun::F
+    hyperparameters::NamedTuple
+    initial_params::SVector{N,Float64}
+    iterations::Int
+    converged::Bool
+    reason::String
+    param::Vector{SVector{N,Float64}}
+    value::Vector{Float64}
+    error::Vector{Float64}
+    gradient::Vector{SVector{N,Float64}}
+    first_moment::Vector{SVector{N,Float64}}
+    second_moment::Vector{SVector{N,Float64}}
+    param_delta::Vector{SVector{N,Float64}}
+end
+
+# callbacks for gwz_adaptive_gradient_descent: `user` points at an ObjectiveState
+mutable struct ObjectiveState
+    f::Any
+    fkwargs::NamedTuple
+    exception::Any
+end
+function _store!(val, err, grad, np, v, e, g)
+    unsafe_store!(val, Float64(v))
+    unsafe_store!(err, Float64(e))
+    for i in 1:np
+        unsafe_store!(grad, Float64(g[i]), i)
+    end
+    return Cint(0)
+end
+function _cb_val_and_grad(user::Ptr{Cvoid}, p::Ptr{Cdouble}, np::Cint, val::Ptr{Cdouble}, err::Ptr{Cdouble},
+                          grad::Ptr{Cdouble})::Cint
+    st = unsafe_pointer_to_objref(user)::ObjectiveState
+    try
+        v, g = val_and_grad(st.f, copy(unsafe_wrap(Array, p, Int(np))); st.fkwargs...)        # amsgrad.jl:136
+        return _store!(val, err, grad, np, v, 0.0, g)
+    catch ex
+        st.exception = ex
+        return Cint(1)
     end
 end
-amsgrad(f::Union{GPUKineticVQMC,GPULocalEnergyEvaluator}, p0; kw...) = _descend(f, p0; use_amsgrad=1, kw...)
-gradient_descent(f::Union{GPUKineticVQMC,GPULocalEnergyEvaluator}, p0; kw...) = _descend(f, p0; use_amsgrad=0, kw...)
+function _cb_val_err_and_grad(user::Ptr{Cvoid}, p::Ptr{Cdouble}, np::Cint, val::Ptr{Cdouble}, err::Ptr{Cdouble},
+                              grad::Ptr{Cdouble})::Cint
+    st = unsafe_pointer_to_objref(user)::ObjectiveState
+    try
+        v, e, g = val_err_and_grad(st.f, copy(unsafe_wrap(Array, p, Int(np))); st.fkwargs...)  # amsgrad.jl:168
+        return _store!(val, err, grad, np, v, e, g)
+    catch ex
+        st.exception = ex
+        return Cint(1)
+    end
+end
+
+_params_vector(p::GPUGradientDescentResult) = collect(Float64, p.param[end])
+_params_vector(p) = collect(Float64, p isa Number ? (p,) : p)
+
+function _descend(f, p_init; use_amsgrad::Bool, maxiter=100, verbose=false, α=0.01, β1=0.1, β2=0.01,
+                  first_moment_init=nothing, second_moment_init=nothing, fix_params=nothing, early_stop=true,
+                  grad_tol=√eps(Float64), param_tol=√eps(Float64), val_tol=√eps(Float64), err_tol=0.0,
+                  fkwargs=(;))
+    if p_init isa GPUGradientDescentResult                       # continue a previous run (amsgrad.jl:109-116)
+        isnothing(first_moment_init) && (first_moment_init = p_init.first_moment[end])
+        isnothing(second_moment_init) && (second_moment_init = p_init.second_moment[end])
+    end
+    p = _params_vector(p_init)
+    N = length(p)
+    m1 = isnothing(first_moment_init) ? nothing : collect(Float64, first_moment_init)
+    m2 = isnothing(second_moment_init) ? nothing : collect(Float64, second_moment_init)
+    fix = isnothing(fix_params) ? nothing : UInt8.(collect(fix_params))
+    for v in (m1, m2, fix)
+        isnothing(v) || length(v) == N || throw(ArgumentError("moment / fix_params length does not match the number of parameters"))
+    end
+    rows = maxiter + 1
+    vecs = [zeros(Cdouble, N, rows) for _ in 1:5]               # param, gradient, first_moment, second_moment, param_delta
+    value, errs = zeros(Cdouble, rows), zeros(Cdouble, rows)
+    st = ObjectiveState(f, NamedTuple(fkwargs), nothing)
+    GC.@preserve vecs value errs p m1 m2 fix st begin
+        opts = GdOpts(maxiter, use_amsgrad, early_stop, 0, α, β1, β2, grad_tol, param_tol, val_tol, err_tol,
+                      isnothing(m1) ? C_NULL : pointer(m1), isnothing(m2) ? C_NULL : pointer(m2),
+                      isnothing(fix) ? C_NULL : pointer(fix))
+        tr = GdTrace(0, 0, 0, N, pointer(vecs[1]), pointer(value), pointer(errs), pointer(vecs[2]),
+                     pointer(vecs[3]), pointer(vecs[4]), pointer(vecs[5]))
+        if f isa GPUKineticVQMC && N == 1 && isempty(st.fkwargs)
+            last = Ref(VqmcResult())
+            check(ccall((:gwz_amsgrad_vqmc, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, UInt64, UInt64, Cint, Cuint, Ref{GdTrace}, Ref{VqmcResult}),
+                        f.result.walkers, p, opts, f.steps, f.result.burn_in, GWZ_KERNEL_BITPARALLEL,
+                        GWZ_RUN_BLOCKING, tr, last))
+            f.result.last = last[]                                # what the reference leaves in qmc.result
+            f.result.steps = f.steps
+        elseif f isa GPULocalEnergyEvaluator && N == 1 && isempty(st.fkwargs)
+            check(ccall((:gwz_amsgrad_sweep, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Cdouble}, Ref{GdOpts}, Ref{GdTrace}), f.sweep, p, opts, tr))
+        else
+            cb1 = @cfunction(_cb_val_and_grad, Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}))
+            cb2 = @cfunction(_cb_val_err_and_grad, Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}))
+            rc = ccall((:gwz_adaptive_gradient_descent, LIB), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Cint, Ref{GdOpts}, Ref{GdTrace}),
+                       cb1, cb2, pointer_from_objref(st), p, N, opts, tr)
+            isnothing(st.exception) || throw(st.exception)
+            check(rc)
+        end
+        n = Int(tr.iterations)
+        if f isa GPUKineticVQMC && n > 0
+            f.result.params = SVector{GWZ_NUM_PARAMS,Float64}(vecs[1][1, n])
+        end
+        reason = ("iterations", "params", "gradient", "value", "errorbars")[tr.reason + 1]
+        sv(m) = [SVector{N,Float64}(m[:, i]) for i in 1:n]
+        hyper = use_amsgrad ? (; α, β1, β2) : (; α)
+        return GPUGradientDescentResult{N,typeof(f)}(f, hyper, SVector{N,Float64}(p), n, tr.converged != 0, reason,
+                                                     sv(vecs[1]), value[1:n], errs[1:n], sv(vecs[2]), sv(vecs[3]),
+                                                     sv(vecs[4]), sv(vecs[5]))
+    end
+end
+const GPUObjective = Union{GPUKineticVQMC,GPULocalEnergyEvaluator}
+amsgrad(f::GPUObjective, p0; kw...) = _descend(f, p0; use_amsgrad=true, kw...)                # amsgrad.jl:259-263
+gradient_descent(f::GPUObjective, p0; kw...) = _descend(f, p0; use_amsgrad=false, kw...)      # amsgrad.jl:240-244
 
 # ------------------------------------------------------------------------------------------
 # Ansatz-generic engine (gwz_gen_* / gwz_gwalkers_* / gwz_gsweep_*): the reference's other
@@ -330,7 +612,8 @@ function GPUModel(H::ExtendedHubbardReal1D, ctx::GPUContext=default_context())
     check(ccall((:gwz_model_create_ext_hubbard1d, LIB), Cint,
                 (Ptr{Cvoid}, Cint, Cint, Cdouble, Cdouble, Cdouble, Ref{Ptr{Cvoid}}),
                 ctx.ptr, num_particles(addr), num_modes(addr), H.u, H.v, H.t, r))
-    m = GPUModel(r[], ctx, num_particles(addr), num_modes(addr), cld(num_particles(addr) + num_modes(addr) - 1, 64))
+    N, M = num_particles(addr), num_modes(addr)
+    m = GPUModel(r[], N, M, cld(N + M - 1, 64), ctx)
     finalizer(x -> ccall((:gwz_model_destroy, LIB), Cint, (Ptr{Cvoid},), x.ptr), m)
     return m
 end

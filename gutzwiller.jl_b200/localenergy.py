@@ -82,6 +82,11 @@ class LocalEnergyEvaluator:
     def handle(self):
         return self._h
 
+    def is_bit_level(self) -> bool:
+        """True when ``handle`` is a ``gwz_sweep`` (HubbardReal1D + GutzwillerAnsatz kernels), i.e. none of the other
+        engines' handles (generic ansatz, stored operator, vector ansatz)."""
+        return self._sp is None and self._gen is None and self._vec is None
+
     @property
     def dim(self) -> int:
         if self._sp is not None:

@@ -18,7 +18,8 @@ from .hamiltonian import AbstractAnsatz, BoseFS, GutzwillerAnsatz, HubbardReal1D
 from .runtime import Context, default_context, distributed_state, shard_range
 
 DEFAULT_SEED = 0x9E3779B97F4A7C15
-RECORD_LIMIT_BYTES = 256 << 20  # kinetic_vqmc keeps per-step series (like the reference) up to this size
+RECORD_LIMIT_BYTES = 256 << 20  # kinetic_vqmc ships per-step series + addresses to the host up to this size
+DEVICE_SERIES_LIMIT_BYTES = 48 << 30  # beyond the host limit the (tau, E_loc) series stay in HBM up to this size
 
 
 def default_walkers(samples: float) -> int:
@@ -108,10 +109,14 @@ class Walkers:
         check(lib().gwz_walkers_set_step_counter(self._h, int(steps_done)))
 
     def run(self, params, steps: int, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
-            keep_acc: bool = False, pooled: bool = False) -> _capi.VqmcResult:
+            keep_acc: bool = False, pooled: bool = False, series: bool = False,
+            blocking: bool = False) -> _capi.VqmcResult:
+        """gwz_vqmc_run.  series: keep the (tau, E_loc) series in HBM (GWZ_RUN_SERIES); blocking: also run the
+        per-walker resample + blocking analysis on the device in the same call (r.blocking, GWZ_RUN_BLOCKING)."""
         p = as_params(params, 1)
         r = _capi.VqmcResult()
-        flags = (_capi.RUN_KEEP_ACC if keep_acc else 0) | (_capi.RUN_POOLED if pooled else 0)
+        flags = (_capi.RUN_KEEP_ACC if keep_acc else 0) | (_capi.RUN_POOLED if pooled else 0) | \
+            (_capi.RUN_SERIES if series else 0) | (_capi.RUN_BLOCKING if blocking else 0)
         check(lib().gwz_vqmc_run(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), int(steps), int(burn_in),
                                  int(kernel), flags, C.byref(r)))
         return r
@@ -147,6 +152,49 @@ class Walkers:
         check(lib().gwz_walkers_estimates(self._h, v.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p)))
         return v, g
 
+    def blocking(self, resample_len: int | None = None, per_walker: bool = False):
+        """gwz_walkers_blocking: per-walker ``blocking_analysis(resample(tau, E_loc; len))`` of the series kept in
+        HBM, combined over all walkers (state.jl:150-164, 265-285).  Returns the summary, and with ``per_walker``
+        also a dict of arrays (mean, err, err_err, k, blocks)."""
+        summ = _capi.BlockingSummary()
+        arrs = None
+        ptrs = [None] * 5
+        if per_walker:
+            arrs = dict(mean=np.zeros(self.n), err=np.zeros(self.n), err_err=np.zeros(self.n),
+                        k=np.zeros(self.n, dtype=np.int32), blocks=np.zeros(self.n, dtype=np.int64))
+            ptrs = [arrs[k].ctypes.data_as(C.c_void_p) for k in ("mean", "err", "err_err", "k", "blocks")]
+        check(lib().gwz_walkers_blocking(self._h, int(resample_len or 0), C.byref(summ), *ptrs))
+        return (summ, arrs) if per_walker else summ
+
+    def series(self):
+        """(tau, eloc), each [steps, n]: host copies of the series kept in HBM by ``run(..., series=True)``."""
+        steps = C.c_uint64()
+        check(lib().gwz_walkers_series(self._h, C.byref(steps), None, None))
+        tau, eloc = np.zeros((steps.value, self.n)), np.zeros((steps.value, self.n))
+        check(lib().gwz_walkers_series(self._h, C.byref(steps), tau.ctypes.data_as(C.c_void_p),
+                                       eloc.ctypes.data_as(C.c_void_p)))
+        return tau, eloc
+
+
+def series_blocking(tau, eloc, resample_len: int | None = None, ctx: Context | None = None):
+    """gwz_series_blocking: the device kernel of ``val_err_and_grad`` on caller-supplied series.
+    tau, eloc: [steps, n] (n independent series in the columns).  Returns (summary, dict of per-series arrays)."""
+    tau = np.ascontiguousarray(tau, dtype=np.float64)
+    eloc = np.ascontiguousarray(eloc, dtype=np.float64)
+    if tau.ndim == 1:
+        tau, eloc = tau[:, None].copy(), eloc[:, None].copy()
+    if tau.shape != eloc.shape:
+        raise ValueError("Lengths of `residence_times` and `values` do not match!")  # state.jl:195-197
+    steps, n = tau.shape
+    ctx = ctx or default_context()
+    summ = _capi.BlockingSummary()
+    arrs = dict(mean=np.zeros(n), err=np.zeros(n), err_err=np.zeros(n), k=np.zeros(n, dtype=np.int32),
+                blocks=np.zeros(n, dtype=np.int64))
+    check(lib().gwz_series_blocking(ctx.handle, tau.ctypes.data_as(C.c_void_p), eloc.ctypes.data_as(C.c_void_p), steps, n,
+                                    int(resample_len or 0), C.byref(summ),
+                                    *[arrs[k].ctypes.data_as(C.c_void_p) for k in ("mean", "err", "err_err", "k", "blocks")]))
+    return summ, arrs
+
 
 def run_group(walker_sets, params, steps: int, burn_in: int = 0, kernel: int = _capi.KERNEL_BITPARALLEL,
               keep_acc: bool = False) -> _capi.VqmcResult:
@@ -178,17 +226,38 @@ class KineticVQMCResult:
         self.kernel = kernel
         self.burn_in = int(burn_in)
         self.last: _capi.VqmcResult | None = None
+        self.blocking_summary = None      # gwz_blocking_summary of the last val_err_and_grad run, if any
+        self.has_device_series = False    # the (tau, E_loc) series of the accumulated steps are in HBM
         self.steps = 0  # per walker
         self._tau: list[np.ndarray] = []
         self._eloc: list[np.ndarray] = []
         self._addr: list[np.ndarray] = []
 
     # -- sampling --
-    def _run(self, steps: int, keep: bool):
+    def _device_series(self) -> bool:
+        return self.record == "device" and isinstance(self.walkers_handle, Walkers)
+
+    def _run(self, steps: int, keep: bool, want_err: bool | None = None):
+        """want_err: the caller is ``val_err_and_grad``: keep the series in HBM and block them in the same call
+        (None: whatever the record mode of this result says)."""
         steps = int(steps)
         w = self.walkers_handle
         burn = self.burn_in if self.steps == 0 or not keep else 0
-        if self.record:
+        self.blocking_summary = None
+        if self.record is not True and isinstance(w, Walkers) and self.estimator != "pooled" and \
+                (want_err or (want_err is None and self.record == "device")):
+            if keep and not self.has_device_series:
+                raise RuntimeError("cannot extend the series: the earlier steps of this result were not recorded")
+            r = w.run(self.params, steps, burn_in=burn, kernel=self.kernel, keep_acc=keep, series=True,
+                      blocking=bool(want_err))
+            self.has_device_series = True
+            if want_err:
+                self.blocking_summary = r.blocking
+            self.steps = self.steps + steps if keep else steps
+            self.last = r
+            return self
+        self.has_device_series = False
+        if self.record is True:
             if burn:
                 w.run(self.params, burn, kernel=self.kernel)  # thermalise; estimators are cleared next
             r, tau, eloc, addr = w.run_record(self.params, steps, kernel=self.kernel, keep_acc=keep)
@@ -214,8 +283,8 @@ class KineticVQMCResult:
         return self.steps * self.walkers_handle.n
 
     def _need_series(self):
-        if not self.record or not self._tau:
-            raise RuntimeError("per-step series were not recorded for this run (record=False)")
+        if self.record is not True or not self._tau:
+            raise RuntimeError("per-step series were not shipped to the host for this run (record=True does that)")
 
     def residence_times(self) -> np.ndarray:
         """[walker, step]"""
@@ -323,7 +392,18 @@ def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn
             raise ValueError("estimator='pooled' works on the running sums; use record=False")
         record = False
     if record is None:
-        record = (end - begin) * max(steps, 1) * (16 + 8 * words) <= RECORD_LIMIT_BYTES and world == 1
+        # like the reference, keep what was sampled: on the host while small (rows / DVec(res) need the addresses),
+        # else the (tau, E_loc) series in HBM (enough for val_err_and_grad / local_energy_estimator), else nothing
+        cells = (end - begin) * max(steps, 1)
+        if cells * (16 + 8 * words) <= RECORD_LIMIT_BYTES and world == 1:
+            record = True
+        elif cells * 16 <= DEVICE_SERIES_LIMIT_BYTES and not _is_sparse(hamiltonian) and not _is_generic(ansatz) \
+                and not getattr(ansatz, "vector_ansatz", False):
+            record = "device"
+        else:
+            record = False
+    if record not in (True, False, "device"):
+        raise ValueError("record must be True (host series), 'device' (series kept in HBM) or False")
     if _is_sparse(hamiltonian):
         from .sparse import SparseWalkers
         w = SparseWalkers(model, ansatz, end - begin, hamiltonian.address.index, seed=seed, global_offset=begin)
@@ -335,7 +415,9 @@ def _make_result(hamiltonian, ansatz, params, walkers, steps, seed, record, burn
         w = GenWalkers(ansatz.handle(ctx), end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
     else:
         w = Walkers(model, end - begin, hamiltonian.address.words, seed=seed, global_offset=begin)
-    return KineticVQMCResult(hamiltonian, ansatz, params, w, bool(record), kernel, burn_in, estimator)
+    if record == "device" and not isinstance(w, Walkers):
+        raise ValueError("record='device' is available for HubbardReal1D + GutzwillerAnsatz walkers")
+    return KineticVQMCResult(hamiltonian, ansatz, params, w, record, kernel, burn_in, estimator)
 
 
 def kinetic_vqmc_continue(res: KineticVQMCResult, *, steps=None) -> KineticVQMCResult:
@@ -355,11 +437,17 @@ def val_and_grad_result(res: KineticVQMCResult):
 
 
 def val_err_and_grad_result(res: KineticVQMCResult):
-    """state.jl:150-164.  With recorded series: per-walker blocking of the resampled local energies,
-    combined as sqrt(sum e_w^2)/walkers (Appendix B.6).  Without series (large runs): the
-    cross-walker standard error of the per-walker estimates (needs >= 2 walkers)."""
+    """state.jl:150-164: per-walker blocking of the resampled local energies, combined as sqrt(sum e_w^2)/walkers
+    (Appendix B.6).  The series are analysed where they are: in HBM by the blocking kernel (record='device', and
+    every ``val_err_and_grad(qmc, p)``), or on the host for small recorded runs.  Only a run that kept no series at
+    all (record=False, other engines) falls back to the cross-walker standard error of the per-walker estimates."""
     r = res.last
-    if res.record and res._tau:
+    if res.has_device_series:  # device-side resample + blocking (gwz_blocking.cu)
+        b = res.blocking_summary
+        if b is None:
+            b = res.blocking_summary = res.walkers_handle.blocking()
+        return b.mean, b.err, np.array(b.grad[:], dtype=np.float64)
+    if res.record is True and res._tau:
         tau, el = res.residence_times(), res.local_energies()
         gr = None
         vals = errs2 = 0.0
@@ -395,7 +483,17 @@ def _grad_ratio_series(res: KineticVQMCResult) -> np.ndarray:
 
 def local_energy_estimator(res: KineticVQMCResult, resample_length=None) -> CombinedBlockingResult:
     """``local_energy_estimator(res; resample_length)`` (state.jl:265-285)."""
-    if res.record and res._tau:
+    if res.has_device_series:
+        summ, a = res.walkers_handle.blocking(resample_length, per_walker=True)
+        if summ.walkers != res.walkers_handle.n:  # sharded run: the per-walker rows of the other ranks are not here
+            results = []
+        elif res.walkers_handle.n <= 4096:
+            results = [BlockingResult(a["mean"][i], a["err"][i], a["err_err"][i], a["err"][i] ** 2, int(a["k"][i]),
+                                      int(a["blocks"][i])) for i in range(res.walkers_handle.n)]
+        else:
+            results = a  # dict of arrays: one Python object per walker would not scale to 2^24 walkers
+        return CombinedBlockingResult(summ.mean, summ.err, summ.err_err, results)
+    if res.record is True and res._tau:
         tau, el = res.residence_times(), res.local_energies()
         n_out = tau.shape[1] if resample_length is None else int(resample_length)
         results = [blocking_analysis(resample(tau[w], el[w], len=n_out)) for w in range(tau.shape[0])]
@@ -415,14 +513,16 @@ def mean(res: KineticVQMCResult) -> float:
 
 def var(res: KineticVQMCResult) -> float:
     """``Statistics.var(res)`` (state.jl:293-298): mean over walkers of the time-weighted variance."""
-    if res.record and res._tau:
+    if res.record is True and res._tau:
         tau, el = res.residence_times(), res.local_energies()
         out = 0.0
         for w in range(tau.shape[0]):
-            m = np.sum(tau[w] * el[w]) / np.sum(tau[w])
             sw = np.sum(tau[w])
-            out += np.sum(tau[w] * (el[w] - m) ** 2) / (sw - 1.0)  # StatsBase FrequencyWeights, corrected
+            m = np.sum(tau[w] * el[w]) / sw
+            out += np.sum(tau[w] * (el[w] - m) ** 2) / sw  # StatsBase var(x, w): corrected = false by default
         return out / tau.shape[0]
+    if hasattr(res.last, "walker_var"):
+        return res.last.walker_var  # the same per-walker variances from the running sums, averaged on the device
     return res.last.pooled_var
 
 
@@ -456,16 +556,16 @@ class KineticVQMC:
         self.walkers = int(walkers)
         self.steps = int(round(samples / self.walkers)) if steps is None else int(steps)  # wrapper.jl:56
         if record is None:
-            record = self.walkers == 1 and estimator != "pooled"  # one walker has no cross-walker error bar
+            record = False  # val_err_and_grad keeps the series in HBM for its own call; nothing is shipped to the host
         self.result = _make_result(hamiltonian, ansatz, np.zeros(ansatz.N_PARAMS), self.walkers, self.steps, seed,
                                    record, burn_in, kernel, ctx, estimator)
 
-    def _reset_and_run(self, params, samples, steps):
+    def _reset_and_run(self, params, samples, steps, want_err=False):
         if steps is None:
             steps = (self.steps * self.walkers if samples is None else int(samples)) // self.walkers  # wrapper.jl:83
         res = self.result
         res.params = as_params(params, self.ansatz.N_PARAMS)  # _reset! (wrapper.jl:74-79)
-        return res._run(int(steps), keep=False)
+        return res._run(int(steps), keep=False, want_err=want_err)
 
     def __call__(self, *args, samples=None, steps=None):
         if len(args) == 3:  # qmc(F, G, params): Optim.only_fg! protocol (wrapper.jl:107-121)
@@ -484,7 +584,7 @@ class KineticVQMC:
         return val_and_grad_result(self._reset_and_run(params, samples, steps))  # wrapper.jl:90-97
 
     def val_err_and_grad(self, params, *, samples=None, steps=None):
-        return val_err_and_grad_result(self._reset_and_run(params, samples, steps))  # wrapper.jl:98-105
+        return val_err_and_grad_result(self._reset_and_run(params, samples, steps, want_err=True))  # wrapper.jl:98-105
 
     def __repr__(self):
         return (f"KineticVQMC(\n  {self.hamiltonian!r},\n  {self.ansatz!r};\n  steps={self.steps},\n"

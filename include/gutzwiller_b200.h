@@ -31,11 +31,12 @@
 extern "C" {
 #endif
 
-#define GWZ_VERSION 120
+#define GWZ_VERSION 200
 #define GWZ_MAX_WORDS 4       /* 64-bit words per address (N+M-1 <= 251) */
 #define GWZ_NUM_PARAMS 1      /* GutzwillerAnsatz has one parameter g (gutzwiller.jl:14) */
 #define GWZ_NCCL_ID_BYTES 128 /* sizeof(ncclUniqueId) */
-#define GWZ_NUM_ACC 12        /* doubles in the cross-device accumulator vector */
+#define GWZ_NUM_ACC 13        /* doubles in the cross-device accumulator vector */
+#define GWZ_NUM_BACC 38       /* doubles in the cross-device vector of the blocking analyses */
 
 enum gwz_status {
     GWZ_OK = 0,
@@ -61,6 +62,12 @@ enum gwz_kernel_kind {
                                instead of the reference's mean of per-walker estimates (state.jl:137-149);
                                the latter carries an O(tau_corr/steps) bias per walker that does not average
                                out over walkers, which matters for many short walkers */
+
+#define GWZ_RUN_SERIES 4u   /* keep the (residence_time, local_energy) series of the accumulated steps in HBM, like
+                               the reference's KineticVQMCWalkerState does on the host (state.jl:15-17, qmc.jl:89-92);
+                               gwz_walkers_blocking analyses them.  16 B of HBM per walker-step. */
+#define GWZ_RUN_BLOCKING 8u /* GWZ_RUN_SERIES + run val_err_and_grad's per-walker resample + blocking_analysis
+                               (state.jl:50-60,150-164) on the device in the same call: fills out->blocking */
 
 typedef struct gwz_context gwz_context;
 typedef struct gwz_model gwz_model;
@@ -128,6 +135,24 @@ int gwz_walkers_get_addresses(gwz_walkers *w, uint64_t *addr_words);
 int gwz_walkers_set_addresses(gwz_walkers *w, const uint64_t *addr_words);
 int gwz_walkers_set_step_counter(gwz_walkers *w, uint64_t steps_done);
 
+/* val_err_and_grad(::KineticVQMCResult) / local_energy_estimator (state.jl:150-164, 265-285): per walker
+ * blocking_analysis(resample(residence_times, local_energies)), combined over ALL walkers of all ranks */
+typedef struct gwz_blocking_summary {
+    double mean;                 /* mean over walkers of the blocking means (state.jl:163 `vals / walkers`) */
+    double err;                  /* sqrt(sum_w err_w^2) / walkers (state.jl:163 = :279); NaN if any walker's M test
+                                    failed, exactly as the reference's sum would be */
+    double err_err;              /* sqrt(sum_w err_err_w^2) / walkers (state.jl:280) */
+    double err_ok;               /* err over the walkers whose M test succeeded (= err when failed == 0) */
+    double grad[GWZ_NUM_PARAMS]; /* mean over walkers of 2 mean_tau(G (E - b_w.mean)) (state.jl:57-58) */
+    uint64_t walkers;            /* walkers analysed (all ranks); 0 = no analysis was run */
+    uint64_t failed;             /* walkers with k = -1 ("M test failed, more data needed") */
+    int32_t k_min, k_max;        /* accepted blocking levels over the successful walkers (-1 if none) */
+    uint64_t series_steps;       /* length of each walker's series */
+    uint64_t resample_len;       /* length it was resampled to (state.jl:183 `len`) */
+    float kernel_ms;             /* device time of the blocking kernel (this rank) */
+    float reserved;
+} gwz_blocking_summary;
+
 typedef struct gwz_vqmc_result {
     double val;                      /* mean over walkers of per-walker ratio estimates (state.jl:137-149) */
     double err;                      /* standard error of that mean across walkers (NaN for 1 walker) */
@@ -135,13 +160,18 @@ typedef struct gwz_vqmc_result {
     double grad_err[GWZ_NUM_PARAMS]; /* cross-walker standard error of grad */
     double pooled_val;               /* sum tau E / sum tau over all walkers and steps */
     double pooled_grad[GWZ_NUM_PARAMS];
-    double pooled_var;               /* time-weighted variance of E_loc (state.jl:293-298 pooled) */
+    double pooled_var;               /* time-weighted variance of E_loc over all walkers and steps */
+    double walker_var;               /* var(res) (state.jl:293-298): mean over walkers of var(E_loc, FrequencyWeights(tau)),
+                                        uncorrected (StatsBase default) */
     double total_time;               /* sum of residence times */
     uint64_t walkers;                /* global walker count (all ranks) */
-    uint64_t steps;                  /* global walker-steps accumulated in the estimators */
-    uint64_t hops;                   /* global hop evaluations = sum over steps of length(offdiagonals) */
+    uint64_t steps;                  /* global walker-steps sampled by THIS call (with GWZ_RUN_KEEP_ACC the estimators
+                                        also hold the earlier calls' steps) */
+    uint64_t hops;                   /* global hop evaluations of this call = sum over its steps of length(offdiagonals) */
     double acc[GWZ_NUM_ACC];         /* raw all-reduced accumulator vector */
     float kernel_ms;                 /* device time of the sampling kernel(s) of this call (this rank) */
+    float reserved;
+    gwz_blocking_summary blocking;   /* filled by GWZ_RUN_BLOCKING, else zero (walkers = 0) */
 } gwz_vqmc_result;
 
 /* kinetic_vqmc!(states; steps) (qmc.jl:73-106) + val_and_grad(result) (state.jl:137-149) + the
@@ -159,6 +189,21 @@ int gwz_walkers_estimates(gwz_walkers *w, double *val_w, double *grad_w);
  * (qmc.jl:89-92): tau[steps x n], eloc[steps x n] (step-major), addr[steps x n x W] (may be NULL). */
 int gwz_vqmc_run_record(gwz_walkers *w, const double *params, uint64_t steps_per_walker, int kernel_kind,
                         unsigned flags, double *tau, double *eloc, uint64_t *addr, gwz_vqmc_result *out);
+
+/* Device-side error bars.  Analyses the series kept by the last GWZ_RUN_SERIES run(s) of this walker set (they must
+ * cover the accumulated steps): per walker resample to resample_len values (0 = the series length, the default of
+ * state.jl:183) and blocking_analysis, then the cross-walker combination.  Collective when the context has a
+ * communicator.  Per-walker outputs (each may be NULL, n local walkers): mean_w, err_w, err_err_w (NaN when the M
+ * test failed), k_w (-1 failed), blocks_w.  One thread per walker, series read from HBM once. */
+int gwz_walkers_blocking(gwz_walkers *w, uint64_t resample_len, gwz_blocking_summary *out, double *mean_w,
+                         double *err_w, double *err_err_w, int32_t *k_w, int64_t *blocks_w);
+/* the series themselves (host copies; tau, eloc: steps x n, step-major; either may be NULL); *steps = series length */
+int gwz_walkers_series(gwz_walkers *w, uint64_t *steps, double *tau, double *eloc);
+/* The same analysis for caller-supplied series (host pointers, step-major steps x n): n independent series through
+ * the same kernel; never collective.  This is the parity surface of the blocking kernel. */
+int gwz_series_blocking(gwz_context *ctx, const double *tau, const double *eloc, uint64_t steps, uint64_t n,
+                        uint64_t resample_len, gwz_blocking_summary *out, double *mean_w, double *err_w,
+                        double *err_err_w, int32_t *k_w, int64_t *blocks_w);
 
 /* DVec(res) (state.jl:303-319): runs steps_per_walker recorded steps and deposits every step's residence time on its
  * address in an HBM hash table; returns the distinct addresses in ascending order with the 2-norm-normalised
@@ -228,9 +273,14 @@ typedef struct gwz_gd_trace {
 /* generic driver: any objective (amsgrad.jl:117-226) */
 int gwz_adaptive_gradient_descent(gwz_objective_fn val_and_grad, gwz_objective_fn val_err_and_grad, void *user,
                                   const double *p0, int np, const gwz_gd_opts *opts, gwz_gd_trace *trace);
-/* built-in objectives: amsgrad(qmc::KineticVQMC, p0) and amsgrad(le::LocalEnergyEvaluator, p0) */
+/* built-in objectives: amsgrad(qmc::KineticVQMC, p0) and amsgrad(le::LocalEnergyEvaluator, p0).
+ * gwz_amsgrad_vqmc: every evaluation is val_err_and_grad(qmc, p) (wrapper.jl:98-105): burn_in unaccumulated steps,
+ * then steps_per_walker steps from the current walker positions.  flags | GWZ_RUN_BLOCKING: value, error bar and
+ * gradient of state.jl:150-164 (device-side blocking; the error feeds the err_tol stop, amsgrad.jl:204); without it
+ * the error column is the cross-walker standard error.  last (may be NULL): result of the final evaluation, what the
+ * reference leaves in qmc.result. */
 int gwz_amsgrad_vqmc(gwz_walkers *w, const double *p0, const gwz_gd_opts *opts, uint64_t steps_per_walker,
-                     int kernel_kind, unsigned flags, gwz_gd_trace *trace);
+                     uint64_t burn_in, int kernel_kind, unsigned flags, gwz_gd_trace *trace, gwz_vqmc_result *last);
 int gwz_amsgrad_sweep(gwz_sweep *s, const double *p0, const gwz_gd_opts *opts, gwz_gd_trace *trace);
 
 /* ---- ansatz-generic engine ---------------------------------------------

@@ -590,17 +590,19 @@ int go_resample(double *result, int64_t len, const double *times, const double *
 }
 
 /* ======================================================================================
- * blocking_analysis (Rimu.StatsTools; Flyvbjerg-Petersen reblocking + Jonsson M-test,
- * PRE 98, 043304).  PARITY UNPINNED: restated from the published algorithm.
+ * blocking_analysis (Rimu.StatsTools: blocks_with_m + mtest; Flyvbjerg-Petersen pair averaging +
+ * the M test of Jonsson, PRE 98, 043304).  PARITY UNPINNED: Rimu's source is not available; restated
+ * from the paper's listing (quantile indexed by the level, M[k] < q[k], the top level never accepted)
+ * with the finite-n M_j of the paper's theorem and corrected (n-1) variance / lag-1 autocovariance,
+ * which is how Rimu's blocks_with_m evaluates them by default.  Two-pass moments in long double; the
+ * product (csrc/gwz_blocking.cuh) uses centred one-pass moments, tests/blocking_checker.py is a third,
+ * independent numpy version written from the published listing.
  * ==================================================================================== */
 static const double CHI2_Q99[] = {
-    /* chi-square 0.99 quantiles, k = 1..30 degrees of freedom */
-    6.634896601021213, 9.210340371976180, 11.344866730144370, 13.276704135987622, 15.086272469388987,
-    16.811893829770927, 18.475306906582357, 20.090235029663233, 21.665994333461924, 23.209251158954356,
-    24.724970311318277, 26.216967305535853, 27.688249610457049, 29.141237740672796, 30.577914166892494,
-    31.999926908815176, 33.408663605004612, 34.805305734705072, 36.190869129270048, 37.566234786625053,
-    38.932172683516072, 40.289360437593864, 41.638398118858476, 42.979820139351631, 44.314104896219156,
-    45.641682666283153, 46.962942124751443, 48.278235770315498, 49.587884472898835, 50.892181311517092};
+    /* the table printed in the listing: chi-square 0.99 quantiles, 1..30 degrees of freedom */
+    6.634897,  9.210340,  11.344867, 13.276704, 15.086272, 16.811894, 18.475307, 20.090235, 21.665994, 23.209251,
+    24.724970, 26.216967, 27.688250, 29.141238, 30.577914, 31.999927, 33.408664, 34.805306, 36.190869, 37.566235,
+    38.932173, 40.289360, 41.638398, 42.979820, 44.314105, 45.641683, 46.962942, 48.278236, 49.587884, 50.892181};
 
 void go_blocking_analysis(const double *v_in, int64_t n, double alpha, go_blocking_result *out) {
     (void)alpha; /* only alpha = 0.01 tabulated */
@@ -633,20 +635,19 @@ void go_blocking_analysis(const double *v_in, int64_t n, double alpha, go_blocki
         long double ss = 0, gam = 0;
         for (int64_t i = 0; i < len; i++) ss += ((long double)v[i] - mean) * ((long double)v[i] - mean);
         for (int64_t i = 0; i + 1 < len; i++) gam += ((long double)v[i] - mean) * ((long double)v[i + 1] - mean);
-        double var_c = len > 1 ? (double)(ss / (len - 1)) : NAN; /* corrected */
-        double var_u = (double)(ss / len);
-        double gamma = (double)(gam / len);
+        double var = (double)(ss / (len - 1));     /* var(v; corrected = true) */
+        double gamma = (double)(gam / (len - 1));  /* autocovariance(v, 1; corrected = true) */
         blocks[s] = len;
-        se[s] = sqrt(var_c / (double)len);
+        se[s] = sqrt(var / (double)len);
         see[s] = se[s] / sqrt(2.0 * (double)(len - 1));
-        /* M-test statistic of level s: n_s * ((n_s-1) var_u / n_s^2 + gamma)^2 / var_u^2 */
-        double q = ((double)(len - 1) * var_u / ((double)len * (double)len) + gamma);
-        mj[s] = var_u > 0 ? (double)len * q * q / (var_u * var_u) : 0.0;
+        /* M_j = n ((n-1) var / n^2 + gamma)^2 / var^2 ; 0/0 = NaN for a constant series */
+        double q = ((double)(len - 1) * var / ((double)len * (double)len) + gamma);
+        mj[s] = (double)len * q * q / (var * var);
         int64_t half = len / 2;
         for (int64_t i = 0; i < half; i++) v[i] = 0.5 * (v[2 * i] + v[2 * i + 1]);
         len = half;
     }
-    /* M_k = sum_{j >= k} mj[j]; first k with M_k < q_{n_steps-k} */
+    /* M_k = sum_{j >= k} mj[j]; first k = 1 .. n_steps-1 with M_k < q[k] */
     int kk = -1;
     double tail = 0;
     double *M = (double *)malloc(sizeof(double) * (size_t)n_steps);
@@ -654,10 +655,8 @@ void go_blocking_analysis(const double *v_in, int64_t n, double alpha, go_blocki
         tail += mj[s];
         M[s] = tail;
     }
-    for (int s = 0; s < n_steps; s++) {
-        int dof = n_steps - s;
-        double q = dof <= 30 ? CHI2_Q99[dof - 1] : CHI2_Q99[29] + 1.3 * (dof - 30);
-        if (M[s] < q) {
+    for (int s = 0; s + 1 < n_steps; s++) {
+        if (M[s] < CHI2_Q99[s < 30 ? s : 29]) {
             kk = s;
             break;
         }
@@ -666,7 +665,7 @@ void go_blocking_analysis(const double *v_in, int64_t n, double alpha, go_blocki
     if (kk >= 0) {
         out->err = se[kk];
         out->err_err = see[kk];
-        out->p_cov = 0.0;
+        out->p_cov = se[kk] * se[kk];
         out->k = kk + 1; /* 1-based level like Julia */
         out->blocks = blocks[kk];
     }

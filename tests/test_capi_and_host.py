@@ -37,7 +37,7 @@ def test_no_torch_types_in_abi():
 
 def test_version_and_error_channel(gw):
     L = gw.lib()
-    assert L.gwz_version() == 120
+    assert L.gwz_version() == 200
     import ctypes as C
     h = C.c_void_p()
     rc = L.gwz_context_create(0, None)
@@ -375,6 +375,8 @@ def test_julia_shim_ccalls_match_the_header():
         if "*" in a:
             return "ptr"
         t = a.rsplit(" ", 1)[0].replace("const ", "").strip()
+        if t == "gwz_objective_fn":  # function pointer typedef
+            return "ptr"
         return {"int": "i32", "int32_t": "i32", "unsigned": "u32", "uint32_t": "u32", "uint64_t": "u64", "size_t": "u64",
                 "double": "f64", "float": "f32"}[t]
 
@@ -415,3 +417,139 @@ int main(void) {
     assert rows[0] == [C.sizeof(V), V.walkers.offset, V.acc.offset, V.kernel_ms.offset]
     assert rows[1] == [C.sizeof(G), G.walkers.offset, G.kernel_ms.offset, G.np.offset]
     assert rows[2] == [C.sizeof(O), O.first_moment_init.offset]
+
+
+def _c_struct_fields(name):
+    """[(field, kind, count)] of `typedef struct name {...} name;` in the header; kind as in the ccall test"""
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+    macros = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (GWZ_\w+) (\d+)", hdr)}
+    kinds = {"double": "f64", "float": "f32", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64",
+             "int": "i32", "unsigned": "u32", "uint8_t": "u8"}
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(\w+)\s+(.*)", decl)
+        ctype, rest = m.group(2), m.group(3)
+        for item in rest.split(","):
+            item = item.strip()
+            arr = re.match(r"(\w+)\[(\w+)\]", item)
+            if item.startswith("*"):
+                out.append((item.lstrip("* "), "ptr", 1))
+            elif arr:
+                cnt = macros[arr.group(2)] if arr.group(2) in macros else int(arr.group(2))
+                out.append((arr.group(1), kinds[ctype], cnt))
+            elif ctype in kinds:
+                out.append((item, kinds[ctype], 1))
+            else:
+                out.append((item, "struct:" + ctype, 1))
+    return out
+
+
+def _julia_struct_fields(jl, name):
+    body = re.search(r"(?:mutable )?struct %s\b[^\n]*\n(.*?)\nend" % name, jl, flags=re.S).group(1)
+    consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"const (GWZ_\w+) = (\d+)", jl)}
+    kinds = {"Cdouble": "f64", "Cfloat": "f32", "Int32": "i32", "UInt32": "u32", "Cint": "i32", "Cuint": "u32",
+             "Int64": "i64", "UInt64": "u64", "UInt8": "u8"}
+    out = []
+    for piece in re.split(r"[;\n]", body):
+        piece = piece.split("#")[0].strip()
+        if not piece:
+            continue
+        fname, ftype = [x.strip() for x in piece.split("::")]
+        tup = re.match(r"NTuple\{(\w+),(\w+)\}", ftype)
+        if ftype.startswith("Ptr"):
+            out.append((fname, "ptr", 1))
+        elif tup:
+            cnt = consts[tup.group(1)] if tup.group(1) in consts else int(tup.group(1))
+            out.append((fname, kinds[tup.group(2)], cnt))
+        elif ftype in kinds:
+            out.append((fname, kinds[ftype], 1))
+        else:
+            out.append((fname, "struct:" + ftype, 1))
+    return out
+
+
+def test_julia_shim_structs_match_the_header():
+    """Field order, types and array lengths of every struct the Julia shim mirrors, against the C header (the shim
+    cannot run here; a layout slip would corrupt memory silently on the first ccall)."""
+    jl = open(os.path.join(ROOT, "gutzwiller.jl_b200", "julia", "GutzwillerB200.jl")).read()
+    pairs = {"VqmcResult": "gwz_vqmc_result", "BlockingSummary": "gwz_blocking_summary", "GdOpts": "gwz_gd_opts",
+             "GdTrace": "gwz_gd_trace", "GenResult": "gwz_gen_result"}
+    for jname, cname in pairs.items():
+        c, j = _c_struct_fields(cname), _julia_struct_fields(jl, jname)
+        cj = [(f, k if not k.startswith("struct:") else "struct:" + {v: kk for kk, v in pairs.items()}[k[7:]], n)
+              for f, k, n in c]
+        assert cj == j, (jname, cj, j)
+    # the constants the shim hard-codes
+    hdr = open(HEADER).read()
+    for name in ("GWZ_NUM_ACC", "GWZ_NUM_PARAMS"):
+        assert re.search(r"const %s = (\d+)" % name, jl).group(1) == re.search(r"#define %s (\d+)" % name, hdr).group(1)
+    for name in ("GWZ_RUN_KEEP_ACC", "GWZ_RUN_POOLED", "GWZ_RUN_SERIES", "GWZ_RUN_BLOCKING"):
+        assert re.search(r"const %s = Cuint\((\d+)\)" % name, jl).group(1) == \
+            re.search(r"#define %s (\d+)u" % name, hdr).group(1)
+    # the zero-argument constructors pass one value per field, each of the field's kind (round 1 passed Int 0 to
+    # tuple-typed fields: a MethodError on the first kinetic_vqmc call)
+    for jname in ("VqmcResult", "BlockingSummary"):
+        start = jl.index("%s() = %s(" % (jname, jname)) + len("%s() = %s(" % (jname, jname))
+        depth, args, cur = 0, [], ""
+        for ch in jl[start:]:
+            if ch in "([{":
+                depth += 1
+            if ch in ")]}":
+                if depth == 0:
+                    break
+                depth -= 1
+            if ch == "," and depth == 0:
+                args.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        args.append(cur.strip())
+        fields = _julia_struct_fields(jl, jname)
+        assert len(args) == len(fields), (jname, args)
+        for a, (fname, kind, cnt) in zip(args, fields):
+            if cnt > 1 or a.startswith(("(", "ntuple")):
+                assert cnt >= 1 and (a.startswith("ntuple") or a.startswith("(")), (jname, fname, a)
+            elif kind.startswith("struct:"):
+                assert a == kind[7:] + "()", (jname, fname, a)
+    # API surface the reference exports for this path (state.jl:265-298, qmc.jl:108-111, amsgrad.jl:105-127)
+    for needle in ("Statistics.mean(res::GPUKineticVQMCResult)", "Statistics.var(res::GPUKineticVQMCResult)",
+                   "kinetic_vqmc!(res::GPUKineticVQMCResult; steps=res.steps)", "function local_energy_estimator(",
+                   "fix_params", "first_moment_init", "second_moment_init", "p_init isa GPUGradientDescentResult",
+                   ":gwz_vqmc_run_record", ":gwz_vqmc_sample_vector", ":gwz_walkers_blocking",
+                   ":gwz_adaptive_gradient_descent"):
+        assert needle in jl, needle
+
+
+def _build_c_consumer(tmp_path):
+    exe = tmp_path / "c_consumer"
+    libdir = os.path.join(ROOT, "gutzwiller.jl_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_consumer.c"), "-o", str(exe), "-L", libdir, "-lgutzwiller_b200",
+                    "-Wl,-rpath," + libdir, "-lm"], check=True)
+    return exe
+
+
+def test_c99_consumer_compiles_links_and_refuses_without_a_gpu(tmp_path):
+    """tests/c_consumer.c: the header is valid C99, every symbol it uses resolves against the shared library, and
+    without a CUDA device the library refuses (exit 77) instead of computing anything on the CPU."""
+    exe = _build_c_consumer(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 77 and "no CUDA device" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_c99_consumer_runs_config1_sweep_and_amsgrad(tmp_path):
+    """the same program on the GPU box: BASELINE config 1 with device-side error bars, the README sweep values,
+    AMSGrad through gwz_gd_opts / gwz_gd_trace, fix_params and moment initialisers"""
+    exe = _build_c_consumer(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "c consumer ok" in r.stdout

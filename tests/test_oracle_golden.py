@@ -182,7 +182,9 @@ def test_blocking_on_correlated_series(oracle_mod):
     assert r.err > 2.5 * naive and abs(r.err - true) < 0.5 * true
     w = rng.standard_normal(4096)
     rw = o.blocking_analysis(w)
-    assert rw.k == 1 and abs(rw.err - w.std(ddof=1) / 64) < 1e-12
+    # white noise: whatever level the M test accepts (its quantile is indexed by the level, so k = 1 is accepted only
+    # when M_1 < 6.63), the blocked error is the naive one within its own uncertainty
+    assert 1 <= rw.k <= 6 and abs(rw.err - w.std(ddof=1) / 64) < 4 * rw.err_err
 
 
 def test_vqmc_statistics_vs_exact(o10, basis10):
