@@ -128,7 +128,7 @@ SIGNATURES = {
     "gwz_walkers_blocking": (C.c_int, [_vp, C.c_uint64, C.POINTER(BlockingSummary), _vp, _vp, _vp, _vp, _vp]),
     "gwz_walkers_series": (C.c_int, [_vp, _u64p, _vp, _vp]),
     "gwz_series_blocking": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(BlockingSummary),
-                                      _vp, _vp, _vp, _vp, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "gwz_vqmc_sample_vector": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, C.c_uint, C.c_uint64, _vp, _vp, _u64p,
                                          C.POINTER(VqmcResult)]),
     "gwz_sweep_create": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),

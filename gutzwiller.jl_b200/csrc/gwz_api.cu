@@ -562,6 +562,7 @@ extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
     cudaFree(w->d_ref_addr);
     cudaFree(w->d_ser_tau);
     cudaFree(w->d_ser_eloc);
+    cudaFree(w->d_ser_v);
     cudaFree(w->d_blk);
     cudaFree(w->d_bpartials);
     w->magic = 0;
@@ -792,6 +793,16 @@ static int enqueue_blocking(gwz_walkers* w, uint64_t len, bool time_it) {
         w->bpartials_cap = grid;
     }
     if (!w->d_blk) GWZ_CUDA(cudaMalloc(&w->d_blk, sizeof(double) * 5 * w->n));
+    if (len > w->scratch_cap) {  // the resampled series pass through this buffer once (8 B per walker and slot)
+        cudaFree(w->d_ser_v);
+        w->d_ser_v = nullptr;
+        w->scratch_cap = 0;
+        if (cudaMalloc(&w->d_ser_v, sizeof(double) * (size_t)len * w->n) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GWZ_ERR_NOMEM, "blocking analysis: no device memory for the resampled series (8 B per walker and slot)");
+        }
+        w->scratch_cap = len;
+    }
     BlockingLaunch L;
     L.tau = w->d_ser_tau;
     L.eloc = w->d_ser_eloc;
@@ -803,6 +814,7 @@ static int enqueue_blocking(gwz_walkers* w, uint64_t len, bool time_it) {
     L.acc_stride = w->n;
     L.shift_e = w->shift_e;
     L.shift_g = w->shift_g;
+    L.scratch = w->d_ser_v;
     L.out = w->d_blk;
     L.out_stride = w->n;
     L.partials = w->d_bpartials;
@@ -1105,7 +1117,7 @@ extern "C" int gwz_walkers_series(gwz_walkers* w, uint64_t* steps, double* tau, 
 
 extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const double* eloc, uint64_t steps, uint64_t n,
                                    uint64_t resample_len, gwz_blocking_summary* out, double* mean_w, double* err_w,
-                                   double* err_err_w, int32_t* k_w, int64_t* blocks_w) {
+                                   double* err_err_w, int32_t* k_w, int64_t* blocks_w, double* resampled) {
     GWZ_HANDLE(c, gwz::GWZ_TAG_CONTEXT, "gwz_series_blocking: NULL or foreign handle (expected a gwz_context)");
     GWZ_REQUIRE(c && tau && eloc, "gwz_series_blocking: NULL argument");
     GWZ_REQUIRE(steps >= 1 && n >= 1, "gwz_series_blocking: empty series");  // state.jl:195-197 / "Not enough data"
@@ -1116,7 +1128,8 @@ extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const doub
     if (blocking_grid(len, (size_t)n, c->prop.multiProcessorCount, &grid) != cudaSuccess)
         return fail(GWZ_ERR_INVALID, "gwz_series_blocking: resample length too large for the per-level shared-memory store");
     const size_t cells = (size_t)steps * (size_t)n;
-    DevBuf<double> d_tau, d_eloc, d_out, d_part, d_vec;
+    DevBuf<double> d_tau, d_eloc, d_out, d_part, d_vec, d_scratch;
+    GWZ_CUDA(d_scratch.alloc((size_t)len * (size_t)n));
     GWZ_CUDA(d_tau.alloc(cells));
     GWZ_CUDA(d_eloc.alloc(cells));
     GWZ_CUDA(d_out.alloc(5 * (size_t)n));
@@ -1134,6 +1147,7 @@ extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const doub
     L.acc = nullptr;
     L.acc_stride = 0;
     L.shift_e = L.shift_g = 0.0;
+    L.scratch = d_scratch.p;
     L.out = d_out.p;
     L.out_stride = (size_t)n;
     L.partials = d_part.p;
@@ -1144,6 +1158,8 @@ extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const doub
     GWZ_LAUNCH(launch_reduce_partials(d_part.p, grid, NUM_BACC, d_vec.p, c->stream));
     double hb[NUM_BACC];
     GWZ_CUDA(cudaMemcpyAsync(hb, d_vec.p, sizeof(double) * NUM_BACC, cudaMemcpyDeviceToHost, c->stream));
+    if (resampled && len > 1)
+        GWZ_CUDA(cudaMemcpyAsync(resampled, d_scratch.p, sizeof(double) * (size_t)len * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     if (out) {
         float ms = 0.f;

@@ -3,13 +3,14 @@
 // walker kernels keep in HBM (step-major [step][walker]: a warp reads 32 neighbouring walkers of one step as one
 // 256-byte segment), followed by the cross-walker combination of state.jl:150-164 / 265-285.
 //
-// One walker per thread; the algorithm (gwz_blocking.cuh) emits the resampled values in lockstep across the
-// threads and folds them straight into the per-level moments, which live in shared memory in a
-// [level][field][thread] layout (the level index is uniform across the CTA, so it is a broadcast-free,
-// conflict-free access).  Nothing but the series is read and nothing but 5 doubles per walker is written:
-// HBM-bound, algorithmic bytes = 16 per recorded walker-step (+ 40 per walker for the running sums that give the
-// total time, the centre and the gradient).  Interval loads are issued four at a time per thread (a small
-// register window over the strictly sequential consumption) so that one HBM round trip feeds four intervals.
+// One walker per thread, two lockstep phases per walker (gwz_blocking.cuh).  Phase A reads step k of every walker's
+// series at the same time (coalesced 256-byte segments per warp) and writes the equal-time resampled values to a
+// scratch column; how many slots a step completes differs between threads, so only the (fire-and-forget) stores
+// diverge.  Phase B reads the scratch column back in lockstep and folds the values into the per-level moments, which
+// live in shared memory in a [level][field][thread] layout (level 0 in registers); all threads are at the same value
+// index, so the carry chain of the pair averaging is uniform across the warp.
+// HBM-bound by design: algorithmic bytes = 16 per recorded walker-step (+ 80 per walker: running sums in, five
+// results out); the scratch round trip adds 16 more per step, most of which stays in the 126 MB L2 for short series.
 #include "gwz_internal.h"
 #include "gwz_blocking.cuh"
 
@@ -24,39 +25,61 @@ struct SmemLevels {
     }
 };
 
-// the window of four consecutive intervals (k & ~3 .. k | 3) held in registers
-struct SeriesWindow {
-    const double* __restrict__ tau;
-    const double* __restrict__ eloc;
-    size_t stride;  // walkers per step row
-    uint64_t n;     // intervals
-    double t0, t1, t2, t3, e0, e1, e2, e3;
-    __device__ __forceinline__ void fill(uint64_t base) {
-        const double* pt = tau + base * stride;
-        const double* pe = eloc + base * stride;
-        const bool b1 = base + 1 < n, b2 = base + 2 < n, b3 = base + 3 < n;
-        t0 = __ldcs(pt);
-        e0 = __ldcs(pe);
-        t1 = b1 ? __ldcs(pt + stride) : 0.0;
-        e1 = b1 ? __ldcs(pe + stride) : 0.0;
-        t2 = b2 ? __ldcs(pt + 2 * stride) : 0.0;
-        e2 = b2 ? __ldcs(pe + 2 * stride) : 0.0;
-        t3 = b3 ? __ldcs(pt + 3 * stride) : 0.0;
-        e3 = b3 ? __ldcs(pe + 3 * stride) : 0.0;
+// Interval k of this thread's series.  Calls come with k = 0, 1, 2, ... and all threads of a warp are at the same k
+// (lockstep).  Rows are fetched SB at a time into registers, one batch ahead of the one being consumed, so that every
+// warp keeps 2 x SB coalesced 256-byte requests in flight (with one row per warp in flight the kernel was bound by
+// memory latency at a quarter of the HBM bandwidth).
+constexpr int SB = 4;
+struct SeriesLoad {
+    const double* __restrict__ pt;  // row of the first interval of the NEXT batch
+    const double* __restrict__ pe;
+    size_t stride;
+    uint64_t n;
+    double ct[SB], ce[SB], nt[SB], ne[SB];
+    __device__ __forceinline__ void fetch(uint64_t first) {  // rows first .. first + SB - 1 -> nt, ne
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+            const bool ok = first + q < n;
+            nt[q] = ok ? __ldcs(pt + q * stride) : 0.0;
+            ne[q] = ok ? __ldcs(pe + q * stride) : 0.0;
+        }
+        pt += SB * stride;
+        pe += SB * stride;
     }
     __device__ __forceinline__ void operator()(uint64_t k, double& t, double& e) {
-        const unsigned s = (unsigned)k & 3u;
-        if (s == 0u) fill(k);
-        t = s == 0u ? t0 : (s == 1u ? t1 : (s == 2u ? t2 : t3));
-        e = s == 0u ? e0 : (s == 1u ? e1 : (s == 2u ? e2 : e3));
+        const unsigned s = (unsigned)k & (SB - 1);
+        if (s == 0u) {  // uniform across the warp
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                ct[q] = nt[q];
+                ce[q] = ne[q];
+            }
+            fetch(k + SB);
+        }
+        t = ct[0];
+        e = ce[0];
+#pragma unroll
+        for (int q = 1; q < SB; ++q) {
+            t = s == (unsigned)q ? ct[q] : t;
+            e = s == (unsigned)q ? ce[q] : e;
+        }
+    }
+};
+// slot i of the resampled series; calls come with i = 0, 1, 2, ...
+struct ScratchStore {
+    double* __restrict__ v;
+    size_t stride;
+    __device__ __forceinline__ void operator()(uint64_t, double x) {
+        *v = x;
+        v += stride;
     }
 };
 
 __global__ void __launch_bounds__(BLOCKING_BLOCK)
 series_blocking_kernel(const double* __restrict__ tau, const double* __restrict__ eloc, size_t stride, size_t n,
                        uint64_t steps, uint64_t len, int levels, const double* __restrict__ acc, size_t acc_stride,
-                       double shift_e, double shift_g, double* __restrict__ out, size_t out_stride,
-                       double* __restrict__ partials) {
+                       double shift_e, double shift_g, double* __restrict__ scratch, double* __restrict__ out,
+                       size_t out_stride, double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* lv = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
     int* khist = reinterpret_cast<int*>(smem_raw + sizeof(double) * (size_t)(levels > 0 ? levels : 1) * BLK_FIELDS * BLOCKING_BLOCK);
@@ -97,10 +120,30 @@ series_blocking_kernel(const double* __restrict__ tau, const double* __restrict_
             o.k = 0;
             o.blocks = 1;
         } else {
+            // phase A: resample, driven by the input intervals (all threads at the same step of their series)
+            double* vw = scratch + w;
+            SeriesLoad src;
+            src.pt = tw;
+            src.pe = ew;
+            src.stride = stride;
+            src.n = steps;
+            src.fetch(0);
+            resample_by_input(steps, len, total, src, ScratchStore{vw, stride});
+            // phase B: the resampled values, in lockstep, into the per-level moments
             for (int i = 0; i < levels * BLK_FIELDS; ++i) lv[i * BLOCKING_BLOCK] = 0.0;
             BlockingStream<SmemLevels> bs(SmemLevels{lv}, levels, centre);
-            SeriesWindow win{tw, ew, stride, steps, 0, 0, 0, 0, 0, 0, 0, 0};
-            resample_stream(steps, len, total, win, [&](double v) { bs.push(v); });
+            {
+                const double* pv = vw;
+                uint64_t i = 0;
+                for (; i + 4 <= len; i += 4, pv += 4 * stride) {  // four loads in flight, then four pushes
+                    const double v0 = pv[0], v1 = pv[stride], v2 = pv[2 * stride], v3 = pv[3 * stride];
+                    bs.push(v0);
+                    bs.push(v1);
+                    bs.push(v2);
+                    bs.push(v3);
+                }
+                for (; i < len; ++i, pv += stride) bs.push(*pv);
+            }
             bs.finalize(len, c_chi2_q99, o);
         }
         // state.jl:57-58: the gradient with val = the blocking mean instead of the weighted mean
@@ -174,8 +217,8 @@ cudaError_t blocking_grid(uint64_t len, size_t n, int sm_count, int* grid) {
 cudaError_t launch_series_blocking(const BlockingLaunch& L, cudaStream_t s) {
     const int levels = blocking_levels(L.len);
     series_blocking_kernel<<<L.grid, BLOCKING_BLOCK, blocking_smem(levels), s>>>(
-        L.tau, L.eloc, L.stride, L.n, L.steps, L.len, levels, L.acc, L.acc_stride, L.shift_e, L.shift_g, L.out,
-        L.out_stride, L.partials);
+        L.tau, L.eloc, L.stride, L.n, L.steps, L.len, levels, L.acc, L.acc_stride, L.shift_e, L.shift_g, L.scratch,
+        L.out, L.out_stride, L.partials);
     return cudaGetLastError();
 }
 

@@ -8,10 +8,11 @@
 //  * resample_stream walks the OUTPUT slots i = 1..len; slot i is either a whole slot covered by the interval that is
 //    still spilling over (reference: first inner loop) or is completed by consuming input intervals (second inner
 //    loop).  Every floating-point operation of state.jl:205-228 is kept, in the same order, without contraction, so
-//    the resampled series is bit-identical to the reference algorithm's for the same total time.  Emission is in
-//    lockstep across walkers (all threads are at the same slot i); only the number of consumed intervals per slot
-//    varies between threads.
-//  * the resampled values are never stored: each is pushed into a BlockingStream, a binary counter of pair averages
+//    the resampled series is bit-identical to the reference algorithm's for the same total time (the host entry
+//    point uses this form).  resample_by_input is the same computation driven by the input intervals: the device
+//    kernel uses it so that all walkers read the same step of their series at the same time.
+//  * on the device the resampled values go through a scratch buffer once (phase A writes them, phase B reads them
+//    in lockstep); each is pushed into a BlockingStream, a binary counter of pair averages
 //    that keeps five centred moments per level (sum d, sum d^2, sum d_t d_{t+1}, first d, last d; d = v - centre,
 //    centre = the time-weighted mean).  From them finalize() gets, per level, exactly what Rimu's blocks_with_m
 //    computes: n, var(v; corrected), autocovariance(v, 1; corrected), std_err, std_err_err, the M_j statistic; then
@@ -63,6 +64,20 @@ GWZ_HD double bl_div(double a, double b) {
 #endif
 }
 
+// a / b for a loop-invariant b with rb = 1 / b (correctly rounded): one Newton correction of a * rb.  By Markstein's
+// theorem the result is the correctly rounded quotient (the exceptional divisors, mantissa all ones, give at most one
+// ulp), i.e. the value the reference's division produces -- without the ~30-instruction IEEE division sequence.
+GWZ_HD double bl_div_by(double a, double b, double rb) {
+#ifdef __CUDA_ARCH__
+    const double q = __dmul_rn(a, rb);
+    const double e = __fma_rn(-b, q, a);
+    return __fma_rn(e, rb, q);
+#else
+    (void)rb;
+    return a / b;
+#endif
+}
+
 // resample!(result, residence_times, values) with length(result) = len, streamed: emit(v) is called len times, in
 // slot order.  load(k, tau, val) fetches interval k (0-based, k < n); `total` = sum(residence_times).
 template <class LOAD, class EMIT>
@@ -72,6 +87,7 @@ GWZ_HD void resample_stream(uint64_t n, uint64_t len, double total, LOAD&& load,
     double val = 0.0;  // :207  value of the interval that is spilling over
     uint64_t k = 0;
     const double dlen = (double)len;
+    const double rtotal = bl_div(1.0, total);
     for (uint64_t i = 1; i <= len; ++i) {
         const double di = (double)i;
         if (t >= di) {  // :212-216  a whole slot inside the spilling interval
@@ -81,7 +97,7 @@ GWZ_HD void resample_stream(uint64_t n, uint64_t len, double total, LOAD&& load,
             while (t < di && k < n) {  // :218-224  consume intervals until slot i is full
                 double tau;
                 load(k, tau, val);
-                const double step = bl_div(bl_mul(dlen, tau), total);  // :220
+                const double step = bl_div_by(bl_mul(dlen, tau), total, rtotal);  // :220  len * tau / total
                 const double room = bl_sub(di, t);
                 mu = bl_add(mu, bl_mul(val, step < room ? step : room));  // :221
                 t = bl_add(t, step);
@@ -90,6 +106,42 @@ GWZ_HD void resample_stream(uint64_t n, uint64_t len, double total, LOAD&& load,
             emit(mu);                        // :227
             mu = bl_mul(bl_sub(t, di), val);  // :228  carry the overshoot into the next slot
         }
+    }
+}
+
+// The same resampling driven by the INPUT intervals k = 0..n-1 (the loop nesting of state.jl:209-230 turned inside
+// out; every floating-point operation and its order per series are unchanged, so the values are identical to
+// resample_stream's).  On the device all threads then read interval k of their walkers at the same time (coalesced,
+// prefetchable); what varies between threads is how many slots an interval completes, i.e. how often emit() runs.
+// emit(i, v): slot i (0-based) of the result is v.
+template <class LOAD, class EMIT>
+GWZ_HD void resample_by_input(uint64_t n, uint64_t len, double total, LOAD&& load, EMIT&& emit) {
+    double t = 0.0, mu = 0.0, val = 0.0;
+    uint64_t i = 1;  // the slot being filled (1-based like the reference)
+    const double dlen = (double)len;
+    const double rtotal = bl_div(1.0, total);
+    for (uint64_t k = 0; k < n && i <= len; ++k) {
+        double tau;
+        load(k, tau, val);
+        const double step = bl_div_by(bl_mul(dlen, tau), total, rtotal);  // state.jl:220
+        const double room = bl_sub((double)i, t);
+        mu = bl_add(mu, bl_mul(val, step < room ? step : room));  // :221
+        t = bl_add(t, step);
+        if (t >= (double)i || k + 1 == n) {  // slot i is full, or the intervals are exhausted (:218 exits)
+            emit(i - 1, mu);                               // :227
+            mu = bl_mul(bl_sub(t, (double)i), val);        // :228
+            ++i;
+            while (t >= (double)i && i <= len) {  // :212-216 whole slots inside the interval that spills over
+                emit(i - 1, val);
+                ++i;
+                mu = bl_sub(mu, val);
+            }
+        }
+    }
+    while (i <= len) {  // only reached through rounding of t: the last slots take what is left (:227-229)
+        emit(i - 1, mu);
+        mu = bl_mul(bl_sub(t, (double)i), val);
+        ++i;
     }
 }
 
@@ -119,27 +171,48 @@ struct BlockingStream {
     uint64_t pushed;
     double centre;
 
-    GWZ_HD BlockingStream(STORE s, int lv, double c) : st(s), levels(lv), pushed(0), centre(c) {}
+    double a0, a1, a2, a3, a4;  // the moments of level 0 (touched by every push) stay in registers
+
+    GWZ_HD BlockingStream(STORE s, int lv, double c)
+        : st(s), levels(lv), pushed(0), centre(c), a0(0.0), a1(0.0), a2(0.0), a3(0.0), a4(0.0) {}
 
     GWZ_HD void push(double v) {
         double d = v - centre;
         uint64_t cnt = pushed++;
-        for (int l = 0; l < levels; ++l) {  // cnt = values already seen by level l
+        {  // level 0
+            const double last = a4;
+            a0 += d;
+            a1 += d * d;
+            if (cnt == 0) a3 = d;
+            else a2 += last * d;
+            a4 = d;
+            if (!(cnt & 1ull)) return;  // the first value of a pair waits for its partner
+            d = 0.5 * (last + d);       // Rimu `blocker`: 1/2 (v[2i-1] + v[2i]); an odd last value is dropped
+            cnt >>= 1;
+        }
+        for (int l = 1; l < levels; ++l) {  // cnt = values already seen by level l
             const double last = st(l, 4);
             st(l, 0) += d;
             st(l, 1) += d * d;
             if (cnt == 0) st(l, 3) = d;
             else st(l, 2) += last * d;
             st(l, 4) = d;
-            if (!(cnt & 1ull)) break;  // the first value of a pair waits for its partner
-            d = 0.5 * (last + d);      // Rimu `blocker`: 1/2 (v[2i-1] + v[2i]); an odd last value is dropped
+            if (!(cnt & 1ull)) break;
+            d = 0.5 * (last + d);
             cnt >>= 1;
         }
     }
 
     // len = number of values pushed (>= 2); q99 = the quantile table above
     GWZ_HD void finalize(uint64_t len, const double* q99, BlockingOut& o) {
-        o.mean = centre + st(0, 0) / (double)len;
+        if (levels > 0) {
+            st(0, 0) = a0;
+            st(0, 1) = a1;
+            st(0, 2) = a2;
+            st(0, 3) = a3;
+            st(0, 4) = a4;
+        }
+        o.mean = centre + a0 / (double)len;
         o.err = o.err_err = o.p_cov = NAN;
         o.k = -1;
         o.blocks = 0;

@@ -150,6 +150,7 @@ struct BlockingLaunch {
     const double* acc;   // [NUM_WALKER_ACC][acc_stride] running sums of the same steps, or null
     size_t acc_stride;
     double shift_e, shift_g;
+    double* scratch;     // [len][stride]: the resampled series pass through here once
     double* out;         // [5][out_stride]: mean, err, err_err, k, blocks per walker, or null
     size_t out_stride;
     double* partials;    // [grid][NUM_BACC]

@@ -176,9 +176,10 @@ class Walkers:
         return tau, eloc
 
 
-def series_blocking(tau, eloc, resample_len: int | None = None, ctx: Context | None = None):
+def series_blocking(tau, eloc, resample_len: int | None = None, ctx: Context | None = None, resampled: bool = False):
     """gwz_series_blocking: the device kernel of ``val_err_and_grad`` on caller-supplied series.
-    tau, eloc: [steps, n] (n independent series in the columns).  Returns (summary, dict of per-series arrays)."""
+    tau, eloc: [steps, n] (n independent series in the columns).  Returns (summary, dict of per-series arrays);
+    with ``resampled=True`` the dict also holds the equal-time series the kernel analysed, [len, n]."""
     tau = np.ascontiguousarray(tau, dtype=np.float64)
     eloc = np.ascontiguousarray(eloc, dtype=np.float64)
     if tau.ndim == 1:
@@ -190,9 +191,13 @@ def series_blocking(tau, eloc, resample_len: int | None = None, ctx: Context | N
     summ = _capi.BlockingSummary()
     arrs = dict(mean=np.zeros(n), err=np.zeros(n), err_err=np.zeros(n), k=np.zeros(n, dtype=np.int32),
                 blocks=np.zeros(n, dtype=np.int64))
+    rs = np.zeros((int(resample_len or steps), n)) if resampled else None
     check(lib().gwz_series_blocking(ctx.handle, tau.ctypes.data_as(C.c_void_p), eloc.ctypes.data_as(C.c_void_p), steps, n,
                                     int(resample_len or 0), C.byref(summ),
-                                    *[arrs[k].ctypes.data_as(C.c_void_p) for k in ("mean", "err", "err_err", "k", "blocks")]))
+                                    *[arrs[k].ctypes.data_as(C.c_void_p) for k in ("mean", "err", "err_err", "k", "blocks")],
+                                    None if rs is None else rs.ctypes.data_as(C.c_void_p)))
+    if rs is not None:
+        arrs["resampled"] = rs
     return summ, arrs
 
 

@@ -200,10 +200,12 @@ int gwz_walkers_blocking(gwz_walkers *w, uint64_t resample_len, gwz_blocking_sum
 /* the series themselves (host copies; tau, eloc: steps x n, step-major; either may be NULL); *steps = series length */
 int gwz_walkers_series(gwz_walkers *w, uint64_t *steps, double *tau, double *eloc);
 /* The same analysis for caller-supplied series (host pointers, step-major steps x n): n independent series through
- * the same kernel; never collective.  This is the parity surface of the blocking kernel. */
+ * the same kernel; never collective.  This is the parity surface of the blocking kernel.  resampled (may be NULL;
+ * resample_len x n, step-major, needs resample_len >= 2): the equal-time series the kernel analysed, i.e.
+ * resample(residence_times, values; len) of state.jl:183-231 per column. */
 int gwz_series_blocking(gwz_context *ctx, const double *tau, const double *eloc, uint64_t steps, uint64_t n,
                         uint64_t resample_len, gwz_blocking_summary *out, double *mean_w, double *err_w,
-                        double *err_err_w, int32_t *k_w, int64_t *blocks_w);
+                        double *err_err_w, int32_t *k_w, int64_t *blocks_w, double *resampled);
 
 /* DVec(res) (state.jl:303-319): runs steps_per_walker recorded steps and deposits every step's residence time on its
  * address in an HBM hash table; returns the distinct addresses in ascending order with the 2-norm-normalised
