@@ -125,6 +125,7 @@ SIGNATURES = {
     "gwz_walkers_estimates": (C.c_int, [_vp, _vp, _vp]),
     "gwz_vqmc_run_record": (C.c_int, [_vp, _dp, C.c_uint64, C.c_int, C.c_uint, _vp, _vp, _vp,
                                       C.POINTER(VqmcResult)]),
+    "gwz_vqmc_run_trace": (C.c_int, [_vp, _dp, C.c_uint64, C.c_uint, _vp, _vp, _vp, _vp, C.POINTER(VqmcResult)]),
     "gwz_walkers_blocking": (C.c_int, [_vp, C.c_uint64, C.POINTER(BlockingSummary), _vp, _vp, _vp, _vp, _vp]),
     "gwz_walkers_series": (C.c_int, [_vp, _u64p, _vp, _vp]),
     "gwz_series_blocking": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(BlockingSummary),

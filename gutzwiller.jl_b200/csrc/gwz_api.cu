@@ -53,6 +53,13 @@ static bool incr_enabled() {
     return !(e && e[0] == '0');
 }
 
+// GWZ_FAST=0 falls back from the round-2 production kernel (gwz_walker_fast.cu: integer hop counts per rate class)
+// to the round-1 incremental kernel (gwz_walker_incr.cu); both sample the same distribution with different u -> hop maps
+static bool fast_enabled() {
+    const char* e = std::getenv("GWZ_FAST");
+    return !(e && e[0] == '0');
+}
+
 // make d_addr (unary) the valid copy
 static int to_unary(gwz_walkers* w) {
     if (!w->in_planes) return GWZ_OK;
@@ -78,6 +85,7 @@ static int to_planes(gwz_walkers* w) {
 
 struct gwz_sweep {
     uint32_t magic = gwz::GWZ_TAG_SWEEP;  // handle type tag, checked by every entry point
+    int device = 0;
     gwz_model* m;
     uint64_t* d_basis = nullptr;  // SoA [W][dim], null => ranked
     uint64_t dim = 0, rank_begin = 0;
@@ -528,6 +536,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
     gwz_walkers* w = new gwz_walkers();
     HandleGuard<gwz_walkers, gwz_walkers_destroy> guard(w);
     w->m = m;
+    w->device = c->device;
     w->n = (size_t)n_walkers;
     w->offset = global_offset;
     w->seed = seed;
@@ -551,7 +560,7 @@ extern "C" int gwz_walkers_create(gwz_model* m, uint64_t n_walkers, uint64_t glo
 extern "C" int gwz_walkers_destroy(gwz_walkers* w) {
     if (w && w->magic != gwz::GWZ_TAG_WALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_walkers_destroy: not a gwz_walkers handle");
     if (!w) return GWZ_OK;
-    cudaSetDevice(w->m->ctx->device);
+    cudaSetDevice(w->device);
     cudaFree(w->d_addr);
     cudaFree(w->d_acc);
     cudaFree(w->d_partials);
@@ -665,7 +674,8 @@ static int ensure_series(gwz_walkers* w, uint64_t keep_rows, uint64_t rows) {
 // enqueue burn-in + sampling + per-set reduction on the set's stream (no sync).  rec_tau / rec_eloc (+ rec_addr):
 // caller's device buffers for a recording run; GWZ_RUN_SERIES in flags: the set's own series buffers instead.
 static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint64_t burn_in, int kind, unsigned flags,
-                       double* rec_tau, double* rec_eloc, uint64_t* rec_addr, bool time_it) {
+                       double* rec_tau, double* rec_eloc, uint64_t* rec_addr, bool time_it, int32_t* rec_hop = nullptr,
+                       const double* u01s = nullptr) {
     gwz_model* m = w->m;
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -686,11 +696,15 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     // production sampling runs on the occupation bit-plane representation (the incremental kernel can keep the
     // (tau, E_loc) series); per-step addresses and the reference-order kernel need the unary strings step by step
     bool planes = (kind == GWZ_KERNEL_BITPARALLEL) && rec_addr == nullptr && tb.kc == 4 && planes_enabled();
-    const bool incr = planes && incr_enabled() && walker_incr_supported(m->N, m->M);
-    if (record && !incr) planes = false;
+    const bool fast = planes && fast_enabled() && walker_fast_supported(m->N, m->M);
+    const bool incr = planes && !fast && incr_enabled() && walker_incr_supported(m->N, m->M);
+    GWZ_REQUIRE(fast || (rec_hop == nullptr && u01s == nullptr),
+                "hop traces / prescribed uniforms need the production kernel (GWZ_KERNEL_BITPARALLEL, 4 <= M <= 250)");
+    if (record && !incr && !fast) planes = false;
     if (int rc = planes ? to_planes(w) : to_unary(w)) return rc;
     int grid = 0;
-    if (incr) GWZ_CUDA(walker_incr_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+    if (fast) GWZ_CUDA(walker_fast_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+    else    if (incr) GWZ_CUDA(walker_incr_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
     else if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
     else GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
     if (int rc = ensure_partials(w, grid)) return rc;
@@ -712,13 +726,17 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.rec_tau = nullptr;
     L.rec_eloc = nullptr;
     L.rec_addr = nullptr;
+    L.rec_hop = nullptr;
+    L.u01s = nullptr;
     if (time_it) GWZ_CUDA(cudaEventRecord(c->ev0, c->stream));
     if (burn_in > 0) {
         L.step0 = w->steps_done;
         L.steps = burn_in;
         L.accumulate = 0;
         L.reset_acc = 0;
-        if (incr) {
+        if (fast) {
+            GWZ_LAUNCH(launch_walkers_fast(L, c->stream));
+        } else if (incr) {
             GWZ_LAUNCH(launch_walkers_incr(L, c->stream));
         } else if (planes) {
             GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
@@ -763,7 +781,10 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     L.rec_tau = rec_tau;
     L.rec_eloc = rec_eloc;
     L.rec_addr = rec_addr;
-    if (incr) GWZ_LAUNCH(launch_walkers_incr(L, c->stream));
+    L.rec_hop = rec_hop;
+    L.u01s = u01s;
+    if (fast) GWZ_LAUNCH(launch_walkers_fast(L, c->stream));
+    else if (incr) GWZ_LAUNCH(launch_walkers_incr(L, c->stream));
     else if (planes) GWZ_LAUNCH(launch_walkers_planes(L, c->stream));
     else GWZ_LAUNCH(launch_walkers(L, c->stream));
     if (time_it) GWZ_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -1056,6 +1077,37 @@ extern "C" int gwz_vqmc_run_record(gwz_walkers* w, const double* params, uint64_
     return combine_and_fetch(one, 1, flags, out);
 }
 
+// parity surface of the production kernel: per step (tau, E_loc, selected hop), optionally with prescribed uniforms
+extern "C" int gwz_vqmc_run_trace(gwz_walkers* w, const double* params, uint64_t steps, unsigned flags, const double* u01,
+                                  double* tau, double* eloc, int32_t* hop, gwz_vqmc_result* out) {
+    GWZ_HANDLE(w, gwz::GWZ_TAG_WALKERS, "gwz_vqmc_run_trace: NULL or foreign handle (expected a gwz_walkers)");
+    GWZ_REQUIRE(params && tau && eloc && hop, "gwz_vqmc_run_trace: NULL argument");
+    GWZ_REQUIRE(steps >= 1, "gwz_vqmc_run_trace: steps_per_walker must be >= 1");
+    GWZ_REQUIRE(std::isfinite(params[0]), "gwz_vqmc_run_trace: non-finite parameter");
+    gwz_context* c = w->m->ctx;
+    if (int rc = use_device(c)) return rc;
+    const size_t cells = (size_t)steps * w->n;
+    DevBuf<double> d_tau, d_eloc, d_u;
+    DevBuf<int32_t> d_hop;
+    GWZ_CUDA(d_tau.alloc(cells));
+    GWZ_CUDA(d_eloc.alloc(cells));
+    GWZ_CUDA(d_hop.alloc(cells));
+    if (u01) {
+        GWZ_CUDA(d_u.alloc(cells));
+        GWZ_CUDA(cudaMemcpyAsync(d_u.p, u01, sizeof(double) * cells, cudaMemcpyHostToDevice, c->stream));
+    }
+    DevTables tb;
+    make_tables(w->m, params[0], choose_kc(w->m, params[0], false), &tb);
+    if (int rc = enqueue_run(w, tb, steps, 0, GWZ_KERNEL_BITPARALLEL, flags & GWZ_RUN_KEEP_ACC, d_tau.p, d_eloc.p, nullptr,
+                             true, d_hop.p, u01 ? d_u.p : nullptr))
+        return rc;
+    GWZ_CUDA(cudaMemcpyAsync(tau, d_tau.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaMemcpyAsync(eloc, d_eloc.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, c->stream));
+    GWZ_CUDA(cudaMemcpyAsync(hop, d_hop.p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, c->stream));
+    gwz_walkers* one[1] = {w};
+    return combine_and_fetch(one, 1, flags, out);
+}
+
 // ---- device-side error bars (state.jl:50-60, 150-164, 265-285) --------------------------------------------
 // per-walker results [5][stride] -> the caller's arrays
 static int fetch_blocking_rows(gwz_context* c, const double* d_blk, size_t n, double* mean_w, double* err_w,
@@ -1245,6 +1297,7 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
     gwz_sweep* s = new gwz_sweep();
     HandleGuard<gwz_sweep, gwz_sweep_destroy> guard(s);
     s->m = m;
+    s->device = c->device;
     if (basis_words) {
         GWZ_REQUIRE(dim >= 1, "gwz_sweep_create: empty basis");
         s->dim = dim;
@@ -1287,7 +1340,7 @@ extern "C" int gwz_sweep_create(gwz_model* m, const uint64_t* basis_words, uint6
 extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
     if (s && s->magic != gwz::GWZ_TAG_SWEEP) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_sweep_destroy: not a gwz_sweep handle");
     if (!s) return GWZ_OK;
-    cudaSetDevice(s->m->ctx->device);
+    cudaSetDevice(s->device);
     cudaFree(s->d_basis);
     cudaFree(s->d_binom);
     cudaFree(s->d_partials);

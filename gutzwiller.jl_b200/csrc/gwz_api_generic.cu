@@ -15,6 +15,7 @@ using namespace gwz;
 
 struct gwz_ansatz {
     uint32_t magic = gwz::GWZ_TAG_ANSATZ;  // handle type tag, checked by every entry point
+    int device = 0;  // destroy must not dereference parent handles (a host GC may release them in any order)
     gwz_model* m;
     int kind, P, normalize;
     double logK;
@@ -31,6 +32,7 @@ struct gwz_ansatz {
 
 struct gwz_gwalkers {
     uint32_t magic = gwz::GWZ_TAG_GWALKERS;  // handle type tag, checked by every entry point
+    int device = 0;
     gwz_ansatz* a;
     size_t n;
     uint64_t offset, seed, steps_done, acc_steps;
@@ -48,6 +50,7 @@ struct gwz_gwalkers {
 
 struct gwz_gsweep {
     uint32_t magic = gwz::GWZ_TAG_GSWEEP;  // handle type tag, checked by every entry point
+    int device = 0;
     gwz_ansatz* a;
     uint64_t* d_basis = nullptr;  // SoA [W][dim]
     uint64_t dim = 0, rank_begin = 0;
@@ -108,6 +111,7 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     gwz_ansatz* a = new gwz_ansatz();
     HandleGuard<gwz_ansatz, gwz_ansatz_destroy> guard(a);
     a->m = m;
+    a->device = m->ctx->device;
     a->kind = kind;
     a->P = P;
     a->normalize = normalize;
@@ -184,6 +188,7 @@ extern "C" int gwz_ansatz_create_combination(gwz_model* m, int kind1, int normal
     }
     gwz_ansatz* a = new gwz_ansatz();
     a->m = m;
+    a->device = m->ctx->device;
     a->kind = GWZ_ANSATZ_COMBINATION;
     a->P = P;
     a->normalize = 0;
@@ -202,7 +207,7 @@ extern "C" int gwz_ansatz_destroy(gwz_ansatz* a) {
     if (!a) return GWZ_OK;
     if (a->c1) gwz_ansatz_destroy(a->c1);
     if (a->c2) gwz_ansatz_destroy(a->c2);
-    if (use_device(a->m->ctx) == GWZ_OK) {
+    if (cudaSetDevice(a->device) == cudaSuccess) {
         if (a->d_static) cudaFree(a->d_static);
         if (a->d_pairs) cudaFree(a->d_pairs);
         if (a->d_par) cudaFree(a->d_par);
@@ -410,6 +415,7 @@ extern "C" int gwz_gwalkers_create(gwz_ansatz* a, uint64_t n_walkers, uint64_t g
     gwz_gwalkers* w = new gwz_gwalkers();
     HandleGuard<gwz_gwalkers, gwz_gwalkers_destroy> guard(w);
     w->a = a;
+    w->device = a->device;
     w->n = (size_t)n_walkers;
     w->offset = global_offset;
     w->seed = seed;
@@ -433,7 +439,7 @@ extern "C" int gwz_gwalkers_create(gwz_ansatz* a, uint64_t n_walkers, uint64_t g
 extern "C" int gwz_gwalkers_destroy(gwz_gwalkers* w) {
     if (w && w->magic != gwz::GWZ_TAG_GWALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_gwalkers_destroy: not a gwz_gwalkers handle");
     if (!w) return GWZ_OK;
-    if (use_device(w->a->m->ctx) == GWZ_OK) {
+    if (cudaSetDevice(w->device) == cudaSuccess) {
         cudaFree(w->d_occ);
         cudaFree(w->d_acc);
         cudaFree(w->d_partials);
@@ -665,6 +671,7 @@ extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uin
     gwz_gsweep* s = new gwz_gsweep();
     HandleGuard<gwz_gsweep, gwz_gsweep_destroy> guard(s);
     s->a = a;
+    s->device = a->device;
     if (basis_words) {
         GWZ_REQUIRE(dim >= 1, "gwz_gsweep_create: empty basis");
         const int W = m->W;
@@ -698,7 +705,7 @@ extern "C" int gwz_gsweep_create(gwz_ansatz* a, const uint64_t* basis_words, uin
 extern "C" int gwz_gsweep_destroy(gwz_gsweep* s) {
     if (s && s->magic != gwz::GWZ_TAG_GSWEEP) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_gsweep_destroy: not a gwz_gsweep handle");
     if (!s) return GWZ_OK;
-    if (use_device(s->a->m->ctx) == GWZ_OK) {
+    if (cudaSetDevice(s->device) == cudaSuccess) {
         if (s->d_basis) cudaFree(s->d_basis);
         if (s->d_binom) cudaFree(s->d_binom);
         if (s->d_partials) cudaFree(s->d_partials);

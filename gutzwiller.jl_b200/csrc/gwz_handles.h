@@ -91,6 +91,7 @@ struct gwz_model {
 
 struct gwz_walkers {
     uint32_t magic = gwz::GWZ_TAG_WALKERS;  // handle type tag, checked by every entry point
+    int device = 0;  // destroy must not dereference the parent handles: a host GC may release them in any order
     gwz_model* m;
     size_t n;
     uint64_t offset, seed;

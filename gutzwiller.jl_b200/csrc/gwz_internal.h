@@ -62,6 +62,8 @@ struct WalkerLaunch {
     double* rec_tau;
     double* rec_eloc;
     uint64_t* rec_addr;  // [steps][n][W]
+    int32_t* rec_hop;    // [steps][n]: 2 z + right of the selected hop (walker_fast_kernel only)
+    const double* u01s;  // [steps][n]: uniforms to use instead of the Philox stream (walker_fast_kernel only)
     // per-block partial accumulator vectors [grid][NUM_ACC]
     double* partials;
     int grid;
@@ -87,6 +89,10 @@ cudaError_t launch_walkers_planes(const WalkerLaunch& L, cudaStream_t s);
 bool walker_incr_supported(int N, int M);
 cudaError_t walker_incr_grid(int N, int M, size_t n, int sm_count, int* grid);
 cudaError_t launch_walkers_incr(const WalkerLaunch& L, cudaStream_t s);
+// round-2 production kernel: integer hop counts per rate class, table-driven updates (gwz_walker_fast.cu)
+bool walker_fast_supported(int N, int M);
+cudaError_t walker_fast_grid(int N, int M, size_t n, int sm_count, int* grid);
+cudaError_t launch_walkers_fast(const WalkerLaunch& L, cudaStream_t s);
 cudaError_t launch_unary_to_planes(const uint64_t* addr, size_t n, const DevModel& dm, uint32_t* planes, cudaStream_t s);
 // walkers first..first+count-1 -> unary SoA addr[W][count]
 cudaError_t launch_planes_to_unary(const uint32_t* planes, size_t n, const DevModel& dm, size_t first, size_t count,

@@ -623,6 +623,7 @@ __global__ void sparse_fill_idx_kernel(uint32_t* idx, size_t n, uint32_t v) {
 // ------------------------------------------------------------------------------------------
 struct gwz_sparse {
     uint32_t magic = gwz::GWZ_TAG_SPARSE;  // handle type tag, checked by every entry point
+    int device = 0;  // destroy must not dereference parent handles (a host GC may release them in any order)
     gwz_context* ctx = nullptr;
     uint64_t dim = 0, nnz = 0, max_row = 0;
     int P = 0, G = 8, G_base = 8;  // G_base: lanes per walker from the row lengths; G: raised so that P fits 8 per lane
@@ -646,6 +647,7 @@ struct gwz_sparse {
 };
 struct gwz_swalkers {
     uint32_t magic = gwz::GWZ_TAG_SWALKERS;  // handle type tag, checked by every entry point
+    int device = 0;
     gwz_sparse* h = nullptr;
     size_t n = 0;
     uint64_t offset = 0, seed = 0, steps_done = 0, acc_steps = 0, table_seen = 0;
@@ -704,7 +706,7 @@ static int sp_group(int G, int P) {
 extern "C" int gwz_sparse_destroy(gwz_sparse* h) {
     if (h && h->magic != gwz::GWZ_TAG_SPARSE) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_sparse_destroy: not a gwz_sparse handle");
     if (!h) return GWZ_OK;
-    if (use_device(h->ctx) == GWZ_OK) {
+    if (cudaSetDevice(h->device) == cudaSuccess) {
         cudaFree(h->d_row_ptr);
         cudaFree(h->d_col);
         cudaFree(h->d_melem);
@@ -745,6 +747,7 @@ extern "C" int gwz_sparse_create(gwz_context* ctx, uint64_t dim, const uint64_t*
     gwz_sparse* h = new gwz_sparse();
     HandleGuard<gwz_sparse, gwz_sparse_destroy> guard(h);
     h->ctx = ctx;
+    h->device = ctx->device;
     h->dim = dim;
     h->nnz = nnz;
     h->max_row = max_row;
@@ -1058,7 +1061,7 @@ extern "C" int gwz_sparse_probe(gwz_sparse* h, const uint32_t* idx, size_t n, co
 extern "C" int gwz_swalkers_destroy(gwz_swalkers* w) {
     if (w && w->magic != gwz::GWZ_TAG_SWALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_swalkers_destroy: not a gwz_swalkers handle");
     if (!w) return GWZ_OK;
-    if (use_device(w->h->ctx) == GWZ_OK) {
+    if (cudaSetDevice(w->device) == cudaSuccess) {
         cudaFree(w->d_idx);
         cudaFree(w->d_acc);
         cudaFree(w->d_partials);
@@ -1081,6 +1084,7 @@ extern "C" int gwz_swalkers_create(gwz_sparse* h, uint64_t n_walkers, uint64_t g
     gwz_swalkers* w = new gwz_swalkers();
     HandleGuard<gwz_swalkers, gwz_swalkers_destroy> guard(w);
     w->h = h;
+    w->device = h->device;
     w->n = (size_t)n_walkers;
     w->offset = global_offset;
     w->seed = seed;

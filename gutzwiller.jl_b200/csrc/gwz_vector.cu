@@ -258,6 +258,7 @@ vec_rayleigh_kernel(const __grid_constant__ DevModel dm, const __grid_constant__
 // ------------------------------------------------------------------------------------------
 struct gwz_vansatz {
     uint32_t magic = gwz::GWZ_TAG_VANSATZ;  // handle type tag, checked by every entry point
+    int device = 0;  // destroy must not dereference parent handles (a host GC may release them in any order)
     gwz_model* m;
     uint64_t n = 0, slots = 0;
     uint64_t* d_keys = nullptr;
@@ -266,6 +267,7 @@ struct gwz_vansatz {
 };
 struct gwz_vwalkers {
     uint32_t magic = gwz::GWZ_TAG_VWALKERS;  // handle type tag, checked by every entry point
+    int device = 0;
     gwz_vansatz* a;
     size_t n;
     uint64_t offset, seed, steps_done, acc_steps;
@@ -327,6 +329,7 @@ extern "C" int gwz_vector_ansatz_create(gwz_model* m, const uint64_t* addr_words
     gwz_vansatz* a = new gwz_vansatz();
     HandleGuard<gwz_vansatz, gwz_vector_ansatz_destroy> guard(a);
     a->m = m;
+    a->device = m->ctx->device;
     a->n = n;
     a->slots = slots;
     GWZ_CUDA(cudaMalloc(&a->d_keys, sizeof(uint64_t) * keys.size()));
@@ -343,7 +346,7 @@ extern "C" int gwz_vector_ansatz_create(gwz_model* m, const uint64_t* addr_words
 extern "C" int gwz_vector_ansatz_destroy(gwz_vansatz* a) {
     if (a && a->magic != gwz::GWZ_TAG_VANSATZ) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_vector_ansatz_destroy: not a gwz_vansatz handle");
     if (!a) return GWZ_OK;
-    if (use_device(a->m->ctx) == GWZ_OK) {
+    if (cudaSetDevice(a->device) == cudaSuccess) {
         cudaFree(a->d_keys);
         cudaFree(a->d_vals);
     }
@@ -405,6 +408,7 @@ extern "C" int gwz_vwalkers_create(gwz_vansatz* a, uint64_t n_walkers, uint64_t 
     gwz_vwalkers* w = new gwz_vwalkers();
     HandleGuard<gwz_vwalkers, gwz_vwalkers_destroy> guard(w);
     w->a = a;
+    w->device = a->device;
     w->n = (size_t)n_walkers;
     w->offset = global_offset;
     w->seed = seed;
@@ -427,7 +431,7 @@ extern "C" int gwz_vwalkers_create(gwz_vansatz* a, uint64_t n_walkers, uint64_t 
 extern "C" int gwz_vwalkers_destroy(gwz_vwalkers* w) {
     if (w && w->magic != gwz::GWZ_TAG_VWALKERS) return gwz::api_fail(GWZ_ERR_INVALID, "gwz_vwalkers_destroy: not a gwz_vwalkers handle");
     if (!w) return GWZ_OK;
-    if (use_device(w->a->m->ctx) == GWZ_OK) {
+    if (cudaSetDevice(w->device) == cudaSuccess) {
         cudaFree(w->d_addr);
         cudaFree(w->d_acc);
         cudaFree(w->d_partials);

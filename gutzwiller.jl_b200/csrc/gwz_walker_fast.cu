@@ -1,0 +1,251 @@
+// gwz_walker_fast.cu -- production walker kernel (round 2): kinetic_vqmc!(st; steps) (src/kinetic-vqmc/qmc.jl:73-97)
+// for every walker with the step of gwz_fast.cuh (integer hop counts per rate class, table-driven updates), the
+// running sums of state.jl:42-49 and per-block partial accumulator vectors.  Same contract and same resident HBM format
+// (occupation bit-planes) as walker_incr_kernel; its own u -> hop map (see gwz_fast.cuh) and its own use of the Philox
+// stream (one 32-bit word per step instead of 53 bits).
+//
+// REC: the recording instantiation keeps the (tau, E_loc) series of the launch in HBM, step-major [step][walker]
+// (qmc.jl:89-92; read back by the blocking kernel, gwz_blocking.cu), optionally the selected hop of every step (the
+// parity surface: a trajectory is its start address plus its hops) and optionally takes the uniforms from the caller
+// instead of the Philox stream (one kinetic_sample! per address with a prescribed u: the stratified-u test).
+#include "gwz_internal.h"
+#include "gwz_fast.cuh"
+
+#ifndef GWZ_FAST_MIN_BLOCKS
+#define GWZ_FAST_MIN_BLOCKS 6
+#endif
+
+namespace gwz {
+
+template <int NWM>
+__host__ __device__ constexpr size_t fast_smem_bytes(int N) {
+    return FastScratch<NWM>::bytes(N) + sizeof(double) * NUM_ACC * (STEP_BLOCK / 32);
+}
+
+template <int NWM, int NP, bool REC>
+__global__ void __launch_bounds__(STEP_BLOCK, NWM <= 2 ? GWZ_FAST_MIN_BLOCKS : (NWM <= 4 ? 4 : 2))
+walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
+                   const __grid_constant__ FastRates fr, const __grid_constant__ PhiloxKeys pk,
+                   uint32_t* __restrict__ planes, double* __restrict__ acc, size_t n, uint64_t global_offset, uint64_t step0,
+                   uint64_t steps, int accumulate, int reset_acc, double shift_e, double shift_g,
+                   double* __restrict__ partials, int* __restrict__ err_flag, double* __restrict__ rec_tau,
+                   double* __restrict__ rec_eloc, int32_t* __restrict__ rec_hop, const double* __restrict__ u01s) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FastScratch<NWM> sc(smem_raw, dm.N);
+    sc.fill_tables(dm.N, tb);
+    // per-warp partial accumulator vectors (shared memory): every finished batch of 32 walkers is reduced by shuffles
+    double(*psum)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(smem_raw + FastScratch<NWM>::bytes(dm.N));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < NUM_ACC) psum[warp][lane] = 0.0;
+    __syncwarp();
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const double E0 = shift_e, G0 = shift_g;  // the launcher passes 0 for burn-in launches
+    bool bad = false;
+
+    for (size_t w0 = (size_t)blockIdx.x * blockDim.x; w0 < n; w0 += nthreads) {  // uniform per CTA
+        const size_t w = w0 + threadIdx.x;
+        const bool live = w < n;
+        double contrib[NUM_ACC];
+#pragma unroll
+        for (int i = 0; i < NUM_ACC; ++i) contrib[i] = 0.0;
+        if (live) {
+            FastState s;
+            {
+                uint32_t pl[NP][NWM];
+#pragma unroll
+                for (int k = 0; k < NP; ++k)
+#pragma unroll
+                    for (int i = 0; i < NWM; ++i) pl[k][i] = planes[((size_t)k * NWM + i) * n + w];
+                fast_init<NWM, NP>(pl, dm, sc, s);
+            }
+            double st, ste, stg, stge, stee;
+            if (reset_acc || !accumulate) {
+                st = ste = stg = stge = stee = 0.0;
+            } else {
+                st = acc[0 * n + w];
+                ste = acc[1 * n + w];
+                stg = acc[2 * n + w];
+                stge = acc[3 * n + w];
+                stee = acc[4 * n + w];
+            }
+            const uint64_t wid = global_offset + (uint64_t)w;
+            const uint32_t c2 = (uint32_t)wid, c3 = (uint32_t)(wid >> 32);
+            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+            unsigned long long hops = 0ull;
+            double tcheck = 0.0;
+
+            for (uint64_t k = 0; k < steps; ++k) {
+                // one Philox4x32-10 block (key = seed, counter = (step / 4, global walker id)) feeds four steps: the
+                // uniform of a step is one 32-bit word, u = word / 2^32
+                const uint64_t step = step0 + k;
+                const unsigned sub = (unsigned)step & 3u;
+                if (k == 0 || sub == 0u) {
+                    const uint64_t blk = step >> 2;
+                    philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+                }
+                const uint32_t rw = sub == 0u ? rnd[0] : (sub == 1u ? rnd[1] : (sub == 2u ? rnd[2] : rnd[3]));
+                double u01 = (__hiloint2double(0x43300000, (int)rw) - 4503599627370496.0) * 0x1.0p-32;
+                if (REC && u01s) u01 = u01s[(size_t)k * n + w];
+                double tau, eloc, gr;
+                int nh, hop;
+                step_fast<NWM>(s, dm, fr, sc, u01, tau, eloc, gr, nh, hop);
+                hops += (unsigned)nh;
+                if (REC) {
+                    if (rec_tau) __stcs(rec_tau + (size_t)k * n + w, tau);
+                    if (rec_eloc) __stcs(rec_eloc + (size_t)k * n + w, eloc);
+                    if (rec_hop) rec_hop[(size_t)k * n + w] = hop;
+                }
+                const double dE = eloc - E0, dG = gr - G0;
+                const double tE = tau * dE;
+                tcheck += tau;
+                st += tau;
+                ste += tE;
+                stg = fma(tau, dG, stg);
+                stge = fma(tE, dG, stge);
+                stee = fma(tE, dE, stee);
+            }
+            bad |= !(tcheck < 1.0e300);  // isfinite(residence_time) for every step (qmc.jl:34-36)
+
+            {
+                uint32_t pl[NP][NWM];
+                fast_store_planes<NWM, NP>(sc, pl);
+#pragma unroll
+                for (int k = 0; k < NP; ++k)
+#pragma unroll
+                    for (int i = 0; i < NWM; ++i) planes[((size_t)k * NWM + i) * n + w] = pl[k][i];
+            }
+            if (accumulate) {
+                acc[0 * n + w] = st;
+                acc[1 * n + w] = ste;
+                acc[2 * n + w] = stg;
+                acc[3 * n + w] = stge;
+                acc[4 * n + w] = stee;
+                const double inv = 1.0 / st;
+                const double mE = ste * inv, mG = stg * inv;
+                const double val_w = E0 + mE;
+                const double grad_w = 2.0 * (stge * inv - mE * mG);
+                contrib[ACC_WALKERS] = 1.0;
+                contrib[ACC_VAL] = val_w;
+                contrib[ACC_VAL2] = val_w * val_w;
+                contrib[ACC_GRAD] = grad_w;
+                contrib[ACC_GRAD2] = grad_w * grad_w;
+                contrib[ACC_T] = st;
+                contrib[ACC_TE] = st * val_w;
+                contrib[ACC_TG] = st * (G0 + mG);
+                contrib[ACC_TGE] = st * G0 * E0 + G0 * ste + E0 * stg + stge;
+                contrib[ACC_TEE] = st * E0 * E0 + 2.0 * E0 * ste + stee;
+                contrib[ACC_HOPS] = (double)hops;
+                contrib[ACC_STEPS] = (double)steps;
+                contrib[ACC_VARW] = stee * inv - mE * mE;  // var(E_loc, weights tau), uncorrected
+            }
+        }
+        if (accumulate) {  // uniform: every lane of the warp is here (dead lanes contribute zeros)
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NUM_ACC; ++i) {
+                const double v = warp_sum(contrib[i]);
+                if (lane == 0) psum[warp][i] += v;
+            }
+        }
+    }
+
+    if (bad) atomicOr(err_flag, 1);
+    if (!accumulate || partials == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x < NUM_ACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < STEP_BLOCK / 32; ++q) v += psum[q][threadIdx.x];
+        partials[(size_t)blockIdx.x * NUM_ACC + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <int NWM, int NP, bool REC>
+static cudaError_t fast_prepare(int N) {
+    const size_t smem = fast_smem_bytes<NWM>(N);
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(walker_fast_kernel<NWM, NP, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int NWM, int NP>
+static cudaError_t fast_launch(const WalkerLaunch& L, cudaStream_t s) {
+    const bool rec = (L.rec_tau != nullptr || L.rec_hop != nullptr || L.u01s != nullptr) && L.accumulate;
+    if (cudaError_t e = rec ? fast_prepare<NWM, NP, true>(L.dm.N) : fast_prepare<NWM, NP, false>(L.dm.N)) return e;
+    const FastRates fr = fast_rates(L.tb.c);
+    if (rec)
+        walker_fast_kernel<NWM, NP, true><<<L.grid, STEP_BLOCK, fast_smem_bytes<NWM>(L.dm.N), s>>>(
+            L.dm, L.tb, fr, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate,
+            L.reset_acc, L.shift_e, L.shift_g, L.partials, L.err_flag, L.rec_tau, L.rec_eloc, L.rec_hop, L.u01s);
+    else
+        walker_fast_kernel<NWM, NP, false><<<L.grid, STEP_BLOCK, fast_smem_bytes<NWM>(L.dm.N), s>>>(
+            L.dm, L.tb, fr, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate,
+            L.reset_acc, L.accumulate ? L.shift_e : 0.0, L.accumulate ? L.shift_g : 0.0, L.partials, L.err_flag, nullptr,
+            nullptr, nullptr, nullptr);
+    return cudaGetLastError();
+}
+template <int NWM, int NP>
+static cudaError_t fast_occ(int N, int* blocks) {
+    if (cudaError_t e = fast_prepare<NWM, NP, false>(N)) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, walker_fast_kernel<NWM, NP, false>, STEP_BLOCK,
+                                                         fast_smem_bytes<NWM>(N));
+}
+
+#define GWZ_FAST_DISPATCH(nwm, np, FN, ...)                \
+    switch ((nwm) * 16 + (np)) {                           \
+        case 1 * 16 + 4: return FN<1, 4>(__VA_ARGS__);     \
+        case 1 * 16 + 6: return FN<1, 6>(__VA_ARGS__);     \
+        case 1 * 16 + 8: return FN<1, 8>(__VA_ARGS__);     \
+        case 2 * 16 + 4: return FN<2, 4>(__VA_ARGS__);     \
+        case 2 * 16 + 6: return FN<2, 6>(__VA_ARGS__);     \
+        case 2 * 16 + 8: return FN<2, 8>(__VA_ARGS__);     \
+        case 3 * 16 + 4: return FN<3, 4>(__VA_ARGS__);     \
+        case 3 * 16 + 6: return FN<3, 6>(__VA_ARGS__);     \
+        case 3 * 16 + 8: return FN<3, 8>(__VA_ARGS__);     \
+        case 4 * 16 + 4: return FN<4, 4>(__VA_ARGS__);     \
+        case 4 * 16 + 6: return FN<4, 6>(__VA_ARGS__);     \
+        case 4 * 16 + 8: return FN<4, 8>(__VA_ARGS__);     \
+        case 5 * 16 + 4: return FN<5, 4>(__VA_ARGS__);     \
+        case 5 * 16 + 6: return FN<5, 6>(__VA_ARGS__);     \
+        case 5 * 16 + 8: return FN<5, 8>(__VA_ARGS__);     \
+        case 6 * 16 + 4: return FN<6, 4>(__VA_ARGS__);     \
+        case 6 * 16 + 6: return FN<6, 6>(__VA_ARGS__);     \
+        case 6 * 16 + 8: return FN<6, 8>(__VA_ARGS__);     \
+        case 7 * 16 + 4: return FN<7, 4>(__VA_ARGS__);     \
+        case 7 * 16 + 6: return FN<7, 6>(__VA_ARGS__);     \
+        case 7 * 16 + 8: return FN<7, 8>(__VA_ARGS__);     \
+        case 8 * 16 + 4: return FN<8, 4>(__VA_ARGS__);     \
+        case 8 * 16 + 6: return FN<8, 6>(__VA_ARGS__);     \
+        case 8 * 16 + 8: return FN<8, 8>(__VA_ARGS__);     \
+        default: return cudaErrorInvalidValue;             \
+    }
+
+// the bookkeeping needs the four modes z-1 .. z+2 around a bond to be distinct, and every count in its field
+bool walker_fast_supported(int N, int M) {
+    (void)N;
+    return M >= 4 && M <= 250;
+}
+
+cudaError_t launch_walkers_fast(const WalkerLaunch& L, cudaStream_t s) {
+    int nwm, np;
+    planes_shape(L.dm.N, L.dm.M, &nwm, &np);
+    GWZ_FAST_DISPATCH(nwm, np, fast_launch, L, s);
+}
+
+static cudaError_t fast_occ_dispatch(int nwm, int np, int N, int* blocks) {
+    GWZ_FAST_DISPATCH(nwm, np, fast_occ, N, blocks);
+}
+cudaError_t walker_fast_grid(int N, int M, size_t n, int sm_count, int* grid) {
+    int nwm, np, blocks = 0;
+    planes_shape(N, M, &nwm, &np);
+    if (cudaError_t e = fast_occ_dispatch(nwm, np, N, &blocks)) return e;
+    if (blocks < 1) blocks = 1;
+    const size_t resident = (size_t)blocks * (size_t)sm_count;
+    const size_t need = (n + STEP_BLOCK - 1) / STEP_BLOCK;
+    *grid = (int)(need < resident ? need : resident);
+    if (*grid < 1) *grid = 1;
+    return cudaSuccess;
+}
+
+}  // namespace gwz

@@ -135,6 +135,23 @@ class Walkers:
                                         None if addr is None else addr.ctypes.data_as(C.c_void_p), C.byref(r)))
         return r, tau, eloc, addr
 
+    def run_trace(self, params, steps: int, u01=None, keep_acc: bool = False):
+        """gwz_vqmc_run_trace: recorded steps of the production kernel.  Returns (result, tau, eloc, hop), each
+        [steps, n]; hop = 2 z + right (see the header).  ``u01`` ([steps, n]) replaces the Philox stream."""
+        p = as_params(params, 1)
+        steps = int(steps)
+        tau, eloc = np.zeros((steps, self.n)), np.zeros((steps, self.n))
+        hop = np.zeros((steps, self.n), dtype=np.int32)
+        up = None
+        if u01 is not None:
+            u = np.ascontiguousarray(u01, dtype=np.float64).reshape(steps, self.n)
+            up = u.ctypes.data_as(C.c_void_p)
+        r = _capi.VqmcResult()
+        check(lib().gwz_vqmc_run_trace(self._h, p.ctypes.data_as(C.POINTER(C.c_double)), steps,
+                                       _capi.RUN_KEEP_ACC if keep_acc else 0, up, tau.ctypes.data_as(C.c_void_p),
+                                       eloc.ctypes.data_as(C.c_void_p), hop.ctypes.data_as(C.c_void_p), C.byref(r)))
+        return r, tau, eloc, hop
+
     def sample_vector(self, params, steps: int, kernel: int = _capi.KERNEL_BITPARALLEL, keep_acc: bool = False,
                       cap: int | None = None):
         """``DVec(res)`` (state.jl:303-319) histogrammed on the device: (addresses uint64[k, 1], values float64[k])."""

@@ -190,6 +190,15 @@ int gwz_walkers_estimates(gwz_walkers *w, double *val_w, double *grad_w);
 int gwz_vqmc_run_record(gwz_walkers *w, const double *params, uint64_t steps_per_walker, int kernel_kind,
                         unsigned flags, double *tau, double *eloc, uint64_t *addr, gwz_vqmc_result *out);
 
+/* Parity surface of the PRODUCTION kernel (GWZ_KERNEL_BITPARALLEL, 4 <= M <= 250): steps_per_walker recorded steps; per
+ * step the residence time, the local energy and the selected hop, hop = 2 z + right with z the 0-based mode on the
+ * left of the bond (z, z+1 mod M), right = 1: a particle moves z -> z+1, 0: z+1 -> z; -1: no move.  A trajectory is
+ * its start address plus its hops (qmc.jl:40-41, 89-92).  u01 (may be NULL): steps x n uniforms in [0,1) used instead
+ * of the walkers' Philox stream, so that one kinetic_sample! per address can be probed with a prescribed u.
+ * tau, eloc, hop: steps x n, step-major. */
+int gwz_vqmc_run_trace(gwz_walkers *w, const double *params, uint64_t steps_per_walker, unsigned flags, const double *u01,
+                       double *tau, double *eloc, int32_t *hop, gwz_vqmc_result *out);
+
 /* Device-side error bars.  Analyses the series kept by the last GWZ_RUN_SERIES run(s) of this walker set (they must
  * cover the accumulated steps): per walker resample to resample_len values (0 = the series length, the default of
  * state.jl:183) and blocking_analysis, then the cross-walker combination.  Collective when the context has a
