@@ -318,8 +318,9 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
-KERNEL_NAME = "walker_incr_kernel: occupation bit-planes + incremental bond-class counts (GWZ_KERNEL_BITPARALLEL)"
-KERNEL_SOURCES = ("gwz_device.cuh", "gwz_planes.cuh", "gwz_incr.cuh", "gwz_walker_incr.cu")
+KERNEL_NAME = ("walker_fast_kernel: integer hop counts per rate class, one-hot occupation masks in shared memory, "
+               "table-driven updates (GWZ_KERNEL_BITPARALLEL)")
+KERNEL_SOURCES = ("gwz_device.cuh", "gwz_planes.cuh", "gwz_incr.cuh", "gwz_fast.cuh", "gwz_walker_fast.cu")
 
 
 def kernel_source_hash():

@@ -70,20 +70,24 @@ struct FastScratch {
     // generic-bond path
     double* exptab;  // [2N+2]
     double* sqrtab;  // [N+2]
-    __host__ __device__ static constexpr size_t bytes(int N) {
-        return sizeof(FastEntry) * (NTL + NTM + NTR) + sizeof(double) * (8 + 16) + sizeof(uint32_t) * 256 +
-               sizeof(uint32_t) * (size_t)(OH_ROWS * NWM + ONR_WORDS) * STEP_BLOCK + sizeof(double) * (size_t)(3 * N + 4);
-    }
+    // byte offsets of the fixed-size regions from the start of the dynamic shared memory (step_fast addresses them
+    // as 32-bit shared-window addresses: base + compile-time constant)
+    static constexpr uint32_t OFF_TL = 0, OFF_TM = OFF_TL + 16 * NTL, OFF_TR = OFF_TM + 16 * NTM,
+                              OFF_IRATE = OFF_TR + 16 * NTR, OFF_FE = OFF_IRATE + 8 * 8, OFF_NTH = OFF_FE + 8 * 16,
+                              OFF_OH = OFF_NTH + 4 * 256, OFF_ONR = OFF_OH + 4 * OH_ROWS * NWM * STEP_BLOCK,
+                              OFF_EXP = OFF_ONR + 4 * ONR_WORDS * STEP_BLOCK;
+    static constexpr uint32_t ROW_BYTES = 4 * NWM * STEP_BLOCK;  // one one-hot row of all threads
+    __host__ __device__ static constexpr size_t bytes(int N) { return OFF_EXP + sizeof(double) * (size_t)(3 * N + 4); }
     __device__ __forceinline__ FastScratch(unsigned char* base, int N) {
-        TL = reinterpret_cast<FastEntry*>(base);
-        TM = TL + NTL;
-        TR = TM + NTM;
-        irate = reinterpret_cast<double*>(TR + NTR);
-        FE = irate + 8;
-        nth = reinterpret_cast<uint32_t*>(FE + 16);
-        oh = nth + 256;
-        onr = oh + OH_ROWS * NWM * STEP_BLOCK;
-        exptab = reinterpret_cast<double*>(onr + ONR_WORDS * STEP_BLOCK);
+        TL = reinterpret_cast<FastEntry*>(base + OFF_TL);
+        TM = reinterpret_cast<FastEntry*>(base + OFF_TM);
+        TR = reinterpret_cast<FastEntry*>(base + OFF_TR);
+        irate = reinterpret_cast<double*>(base + OFF_IRATE);
+        FE = reinterpret_cast<double*>(base + OFF_FE);
+        nth = reinterpret_cast<uint32_t*>(base + OFF_NTH);
+        oh = reinterpret_cast<uint32_t*>(base + OFF_OH);
+        onr = reinterpret_cast<uint32_t*>(base + OFF_ONR);
+        exptab = reinterpret_cast<double*>(base + OFF_EXP);
         sqrtab = exptab + (2 * N + 2);
     }
     // contribution of one bond of capped class (l, r) to (E, np); zero for non-regular classes
@@ -156,9 +160,35 @@ __device__ __forceinline__ int fast_off(int m) { return (m >> 2) * (STEP_BLOCK *
 // word offset (in uint32 units) of one-hot row `row`, word i, for this thread's column
 template <int NWM>
 __device__ __forceinline__ int oh_at(int row, int i) { return (row * NWM + i) * STEP_BLOCK; }
-// one-hot rows of the capped occupation s (0..4): A block 2, 3, 4, 5, 14; Q block 8, 9, 10, 11, 15 (one PRMT each)
-__device__ __forceinline__ int oh_row_a(int s4) { return (int)(__byte_perm(0x05040302u, (uint32_t)OH_A4, (uint32_t)s4) & 0xFFu); }
-__device__ __forceinline__ int oh_row_q(int s4) { return (int)(__byte_perm(0x0B0A0908u, (uint32_t)OH_Q4, (uint32_t)s4) & 0xFFu); }
+// one-hot rows of the capped occupation s (0..4): A block 2, 3, 4, 5, 14; Q block 8, 9, 10, 11, 15.  sel = s | 0x7770:
+// byte s of the table into byte 0, a zero byte (byte 7 of the pair) into the others -- one PRMT each
+__device__ __forceinline__ uint32_t oh_row_a(uint32_t sel) { return __byte_perm(0x05040302u, (uint32_t)OH_A4, sel); }
+__device__ __forceinline__ uint32_t oh_row_q(uint32_t sel) { return __byte_perm(0x0B0A0908u, (uint32_t)OH_Q4, sel); }
+
+// 32-bit shared-window addressing for the step loop: one base register, every region at a compile-time offset
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldsu8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void stsu8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ double lds64f(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ FastEntry lds_entry(uint32_t a) {
+    FastEntry e;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(*reinterpret_cast<unsigned long long*>(&e.dE)), "=l"(e.dn) : "r"(a));
+    return e;
+}
+__device__ __forceinline__ void red_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // sums / selection over the generic bonds (a neighbour with >= 4 particles), from the occupation bytes;
 // same order and arithmetic as PlanesBig::pass
@@ -351,13 +381,15 @@ __device__ __forceinline__ void fast_store_planes(const FastScratch<NWM>& sc, ui
 }
 
 // one kinetic_sample! (qmc.jl:14-44).  hop_code: 2 z + (right ? 1 : 0) of the selected hop, -1 if none.
+// sb = shared-window address of the start of the dynamic shared memory (smem_addr(smem_raw)).
 template <int NWM>
 __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, const FastRates& fr,
-                                          const FastScratch<NWM>& sc, double u01, double& tau, double& eloc,
+                                          const FastScratch<NWM>& sc, uint32_t sb, double u01, double& tau, double& eloc,
                                           double& gratio, int& nhops, int& hop_code) {
-    const int tid = threadIdx.x;
-    unsigned char* const ob = reinterpret_cast<unsigned char*>(sc.onr + tid);
-    uint32_t* const oh = sc.oh + tid;
+    using SC = FastScratch<NWM>;
+    const uint32_t st = sb + 4u * threadIdx.x;  // this thread's column in the [entry][thread] regions
+    const uint32_t oh = st + SC::OFF_OH;        // one-hot row r, word i: oh + (r NWM + i) 512
+    const uint32_t ob = st + SC::OFF_ONR;       // occupation byte of mode m: ob + (m >> 2) 512 + (m & 3)
 
     // ---- S and its running sums over the rate classes, from the integer hop counts ----
     const uint32_t nlo = (uint32_t)s.np, nhi = (uint32_t)(s.np >> 32);
@@ -384,11 +416,13 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
 #pragma unroll
     for (int i = 0; i < NWM; ++i) bigm[i] = 0u;
     double bigS = 0.0, bigE = 0.0;
+    const unsigned char* const obp = reinterpret_cast<const unsigned char*>(sc.onr + threadIdx.x);  // generic-bond path only
     if (s.nbig) {
 #pragma unroll
-        for (int i = 0; i < NWM; ++i) bigm[i] = (oh[oh_at<NWM>(OH_A4, i)] | oh[oh_at<NWM>(OH_Q4, i)]) & dm.mmask[i];
+        for (int i = 0; i < NWM; ++i)
+            bigm[i] = (lds32(oh + (OH_A4 * NWM + i) * 512u) | lds32(oh + (OH_Q4 * NWM + i) * 512u)) & dm.mmask[i];
         if (!s.big_valid) {
-            const BigOut o = fast_big_pass<NWM>(bigm, dm, ob, sc.exptab, sc.sqrtab, 0, 0.0);
+            const BigOut o = fast_big_pass<NWM>(bigm, dm, obp, sc.exptab, sc.sqrtab, 0, 0.0);
             s.bigS = o.S;
             s.bigE = o.E;
             s.big_valid = true;
@@ -418,21 +452,26 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
         if (!(T < c3)) { g = 4; base = c3; }
         if (!(T < c4)) { g = 5; base = c4; }
         const int ng = (int)((s.np >> (g < 3 ? 10 * g : 2 + 10 * g)) & 0x3FFull);  // fast_field_pos(g)
-        int j = (int)((T - base) * sc.irate[g]);
+        int j = (int)((T - base) * lds64f(sb + SC::OFF_IRATE + 8u * (uint32_t)g));
         j = max(0, min(j, ng - 1));
         // level 2: the j-th hop of the rate class in the order (right hops by position, left hops by position)
         //   right hop from a mode with s particles (s = 1..3) to a neighbour with s + g - 3: A_s & Q_(s+g-3)
         //   left hop from a neighbour with s particles onto a mode with s + g - 3:         A_(s+g-3) & Q_s
-        const uint32_t* qd = oh + (OH_Q + g - 2) * (NWM * STEP_BLOCK);  // row of Q_(1+g-3)
-        const uint32_t* ad = oh + (OH_A + g - 2) * (NWM * STEP_BLOCK);  // row of A_(1+g-3)
+        const uint32_t dyn = oh + (uint32_t)(g - 2) * SC::ROW_BYTES;  // + OH_Q rows: Q_(1+g-3); + OH_A rows: A_(1+g-3)
         uint32_t mR[NWM], mL[NWM];
         int nR = 0;
 #pragma unroll
         for (int i = 0; i < NWM; ++i) {
-            const uint32_t a1 = oh[oh_at<NWM>(OH_A + 1, i)], a2 = oh[oh_at<NWM>(OH_A + 2, i)], a3 = oh[oh_at<NWM>(OH_A + 3, i)];
-            const uint32_t q1 = oh[oh_at<NWM>(OH_Q + 1, i)], q2 = oh[oh_at<NWM>(OH_Q + 2, i)], q3 = oh[oh_at<NWM>(OH_Q + 3, i)];
-            mR[i] = (a1 & qd[oh_at<NWM>(0, i)]) | (a2 & qd[oh_at<NWM>(1, i)]) | (a3 & qd[oh_at<NWM>(2, i)]);
-            mL[i] = (q1 & ad[oh_at<NWM>(0, i)]) | (q2 & ad[oh_at<NWM>(1, i)]) | (q3 & ad[oh_at<NWM>(2, i)]);
+            const uint32_t a1 = lds32(oh + ((OH_A + 1) * NWM + i) * 512u), a2 = lds32(oh + ((OH_A + 2) * NWM + i) * 512u),
+                           a3 = lds32(oh + ((OH_A + 3) * NWM + i) * 512u);
+            const uint32_t q1 = lds32(oh + ((OH_Q + 1) * NWM + i) * 512u), q2 = lds32(oh + ((OH_Q + 2) * NWM + i) * 512u),
+                           q3 = lds32(oh + ((OH_Q + 3) * NWM + i) * 512u);
+            const uint32_t dq0 = lds32(dyn + ((OH_Q + 0) * NWM + i) * 512u), dq1 = lds32(dyn + ((OH_Q + 1) * NWM + i) * 512u),
+                           dq2 = lds32(dyn + ((OH_Q + 2) * NWM + i) * 512u);
+            const uint32_t da0 = lds32(dyn + ((OH_A + 0) * NWM + i) * 512u), da1 = lds32(dyn + ((OH_A + 1) * NWM + i) * 512u),
+                           da2 = lds32(dyn + ((OH_A + 2) * NWM + i) * 512u);
+            mR[i] = (a1 & dq0) | (a2 & dq1) | (a3 & dq2);
+            mL[i] = (q1 & da0) | (q2 & da1) | (q3 & da2);
             nR += __popc(mR[i]);
         }
         right = j < nR;
@@ -453,7 +492,7 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
         if (!fnd) jb = max(0, __popc(word) - 1);  // cannot happen while np matches the masks
         z = word ? pos + nth_set_bit32_lut(word, jb, sc.nth) : -1;
     } else {
-        const BigOut o = fast_big_pass<NWM>(bigm, dm, ob, sc.exptab, sc.sqrtab, 1, T - reg_total);
+        const BigOut o = fast_big_pass<NWM>(bigm, dm, obp, sc.exptab, sc.sqrtab, 1, T - reg_total);
         z = o.z;
         right = o.right != 0;
     }
@@ -465,14 +504,17 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
     const int zn = (z + 1 == M) ? 0 : z + 1;
     const int zm = (z == 0) ? M - 1 : z - 1;
     const int zp = (zn + 1 == M) ? 0 : zn + 1;
-    const int oz = fast_off(z), ozn = fast_off(zn);
-    const int a = ob[fast_off(zm)], x = ob[oz], y = ob[ozn], b = ob[fast_off(zp)];
+    const uint32_t az = ob + (uint32_t)fast_off(z), an = ob + (uint32_t)fast_off(zn);
+    const int a = (int)ldsu8(ob + (uint32_t)fast_off(zm)), x = (int)ldsu8(az), y = (int)ldsu8(an),
+              b = (int)ldsu8(ob + (uint32_t)fast_off(zp));
     const int x2 = right ? x - 1 : x + 1, y2 = right ? y + 1 : y - 1;
-    ob[oz] = (unsigned char)x2;
-    ob[ozn] = (unsigned char)y2;
+    stsu8(az, (uint32_t)x2);
+    stsu8(an, (uint32_t)y2);
     const int a4 = min(a, 4), b4 = min(b, 4), x4 = min(x, 4), y4 = min(y, 4), x24 = min(x2, 4), y24 = min(y2, 4);
     const int ix = 2 * x4 + x24 + 1, iy = 2 * y4 + y24 + 1;  // 3 x4 + (x24 - x4 + 1)
-    const FastEntry eL = sc.TL[a4 * 15 + ix], eM = sc.TM[ix * 15 + iy], eR = sc.TR[iy * 5 + b4];
+    const FastEntry eL = lds_entry(sb + SC::OFF_TL + 16u * (uint32_t)(a4 * 15 + ix)),
+                    eM = lds_entry(sb + SC::OFF_TM + 16u * (uint32_t)(ix * 15 + iy)),
+                    eR = lds_entry(sb + SC::OFF_TR + 16u * (uint32_t)(iy * 5 + b4));
     s.E += (eL.dE + eM.dE) + eR.dE;
     s.np += (eL.dn + eM.dn) + eR.dn;
     const int nsrc = right ? x : y, ndst = right ? y : x;
@@ -483,20 +525,18 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
     if (max(max(a4, x4), max(max(y4, b4), max(x24, y24))) == 4) s.big_valid = false;
     {  // one-hot rows: mode z leaves row x4 and enters x24 (A at bit z, Q at bit z-1), mode z+1 likewise (A: z+1, Q: z)
         const uint32_t bz = 1u << (z & 31), bn = 1u << (zn & 31), bm = 1u << (zm & 31);
-        uint32_t* const wz = oh + (z >> 5) * STEP_BLOCK;
-        uint32_t* const wn = oh + (zn >> 5) * STEP_BLOCK;
-        uint32_t* const wm = oh + (zm >> 5) * STEP_BLOCK;
-        constexpr int RS = NWM * STEP_BLOCK;  // words per row
-        const int rx = oh_row_a(x4) * RS, rx2 = oh_row_a(x24) * RS, ry = oh_row_a(y4) * RS, ry2 = oh_row_a(y24) * RS;
-        const int qx = oh_row_q(x4) * RS, qx2 = oh_row_q(x24) * RS, qy = oh_row_q(y4) * RS, qy2 = oh_row_q(y24) * RS;
-        atomicXor(wz + rx, bz);
-        atomicXor(wz + rx2, bz);
-        atomicXor(wm + qx, bm);
-        atomicXor(wm + qx2, bm);
-        atomicXor(wn + ry, bn);
-        atomicXor(wn + ry2, bn);
-        atomicXor(wz + qy, bz);
-        atomicXor(wz + qy2, bz);
+        const uint32_t wz = oh + (uint32_t)(z >> 5) * 512u, wn = oh + (uint32_t)(zn >> 5) * 512u,
+                       wm = oh + (uint32_t)(zm >> 5) * 512u;
+        const uint32_t sx = (uint32_t)x4 | 0x7770u, sx2 = (uint32_t)x24 | 0x7770u, sy = (uint32_t)y4 | 0x7770u,
+                       sy2 = (uint32_t)y24 | 0x7770u;
+        red_xor(wz + oh_row_a(sx) * SC::ROW_BYTES, bz);
+        red_xor(wz + oh_row_a(sx2) * SC::ROW_BYTES, bz);
+        red_xor(wm + oh_row_q(sx) * SC::ROW_BYTES, bm);
+        red_xor(wm + oh_row_q(sx2) * SC::ROW_BYTES, bm);
+        red_xor(wn + oh_row_a(sy) * SC::ROW_BYTES, bn);
+        red_xor(wn + oh_row_a(sy2) * SC::ROW_BYTES, bn);
+        red_xor(wz + oh_row_q(sy) * SC::ROW_BYTES, bz);
+        red_xor(wz + oh_row_q(sy2) * SC::ROW_BYTES, bz);
     }
     // rounding drift of the carried E: re-sum from the integers periodically, and as soon as E has fallen 16-fold
     // below its largest value since the last re-summation (the rounding errors it carries scale with that peak)

@@ -33,6 +33,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastScratch<NWM> sc(smem_raw, dm.N);
     sc.fill_tables(dm.N, tb);
+    const uint32_t sb = smem_addr(smem_raw);
     // per-warp partial accumulator vectors (shared memory): every finished batch of 32 walkers is reduced by shuffles
     double(*psum)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(smem_raw + FastScratch<NWM>::bytes(dm.N));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,7 +89,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                 if (REC && u01s) u01 = u01s[(size_t)k * n + w];
                 double tau, eloc, gr;
                 int nh, hop;
-                step_fast<NWM>(s, dm, fr, sc, u01, tau, eloc, gr, nh, hop);
+                step_fast<NWM>(s, dm, fr, sc, sb, u01, tau, eloc, gr, nh, hop);
                 hops += (unsigned)nh;
                 if (REC) {
                     if (rec_tau) __stcs(rec_tau + (size_t)k * n + w, tau);
