@@ -104,6 +104,9 @@ struct gwz_sweep {
     bool ms_pending = false;           // ev0/ev1 hold the last sweep's kernel time, not read yet
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<uint64_t> h_binom;     // host copy of the binomial table (ranked mode)
+    unsigned* d_done = nullptr;        // arrival counter of the fused last-CTA reduction
+    int enum_grid = 0, rep_grid = 0;   // launch shapes of the enumerating / stored-representative sweeps (cached)
+    uint64_t enum_chunk = 1, rep_chunk = 1;
 };
 
 
@@ -125,11 +128,15 @@ extern "C" int gwz_context_create(int device, gwz_context** out) {
     GWZ_CUDA(cudaGetDeviceProperties(&c->prop, device));
     GWZ_CUDA(cudaDeviceGetAttribute(&c->clock_khz, cudaDevAttrClockRate, device));
     GWZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    GWZ_CUDA(cudaMalloc(&c->d_acc, sizeof(double) * NUM_VEC));
+    // the error flag sits right behind the accumulator vector, on the device and in the pinned host mirror: a run
+    // fetches both with one copy
+    GWZ_CUDA(cudaMalloc(&c->d_acc, sizeof(double) * (NUM_VEC + 1)));
     GWZ_CUDA(cudaMalloc(&c->d_group, sizeof(double) * NUM_VEC * GROUP_ROWS));
-    GWZ_CUDA(cudaMallocHost(&c->h_acc, sizeof(double) * NUM_VEC));
-    GWZ_CUDA(cudaMalloc(&c->d_err, sizeof(int)));
-    GWZ_CUDA(cudaMallocHost(&c->h_err, sizeof(int)));
+    GWZ_CUDA(cudaMallocHost(&c->h_acc, sizeof(double) * (NUM_VEC + 1)));
+    c->d_err = reinterpret_cast<int*>(c->d_acc + NUM_VEC);
+    c->h_err = reinterpret_cast<int*>(c->h_acc + NUM_VEC);
+    std::memset(c->h_acc, 0, sizeof(double) * (NUM_VEC + 1));
+    GWZ_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * (NUM_VEC + 1), c->stream));
     GWZ_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
     GWZ_CUDA(cudaEventCreate(&c->ev0));
     GWZ_CUDA(cudaEventCreate(&c->ev1));
@@ -151,8 +158,6 @@ extern "C" int gwz_context_destroy(gwz_context* c) {
     cudaFree(c->d_acc);
     cudaFree(c->d_group);
     cudaFreeHost(c->h_acc);
-    cudaFree(c->d_err);
-    cudaFreeHost(c->h_err);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
@@ -675,7 +680,7 @@ static int ensure_series(gwz_walkers* w, uint64_t keep_rows, uint64_t rows) {
 // caller's device buffers for a recording run; GWZ_RUN_SERIES in flags: the set's own series buffers instead.
 static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint64_t burn_in, int kind, unsigned flags,
                        double* rec_tau, double* rec_eloc, uint64_t* rec_addr, bool time_it, int32_t* rec_hop = nullptr,
-                       const double* u01s = nullptr) {
+                       const double* u01s = nullptr, double* reduce_dst = nullptr) {
     gwz_model* m = w->m;
     gwz_context* c = m->ctx;
     if (int rc = use_device(c)) return rc;
@@ -703,10 +708,18 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     if (record && !incr && !fast) planes = false;
     if (int rc = planes ? to_planes(w) : to_unary(w)) return rc;
     int grid = 0;
-    if (fast) GWZ_CUDA(walker_fast_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
-    else    if (incr) GWZ_CUDA(walker_incr_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
-    else if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
-    else GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
+    // the persistent grid comes from an occupancy query: once per (walker set, kernel), not once per call
+    const int grid_key = fast ? 1 : incr ? 2 : planes ? 3 : 4 + 4 * kind + 2 * (tb.kc == 5) + (record ? 1 : 0);
+    if (w->grid_key == grid_key) {
+        grid = w->grid_cached;
+    } else {
+        if (fast) GWZ_CUDA(walker_fast_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+        else if (incr) GWZ_CUDA(walker_incr_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+        else if (planes) GWZ_CUDA(walker_planes_grid(m->N, m->M, w->n, c->prop.multiProcessorCount, &grid));
+        else GWZ_CUDA(walker_grid(m->nw, m->N, kind, tb.kc, record, w->n, c->prop.multiProcessorCount, &grid));
+        w->grid_key = grid_key;
+        w->grid_cached = grid;
+    }
     if (int rc = ensure_partials(w, grid)) return rc;
     WalkerLaunch L;
     L.dm = m->dm;
@@ -791,7 +804,13 @@ static int enqueue_run(gwz_walkers* w, const DevTables& tb, uint64_t steps, uint
     w->steps_done += steps;
     w->acc_steps = keep ? w->acc_steps + steps : steps;
     if (series) w->ser_steps += steps;
-    GWZ_LAUNCH(launch_reduce_partials(w->d_partials, grid, NUM_ACC, w->d_vec, c->stream));
+    // reduce_dst: a single walker set reduces straight into the context's all-reduce / fetch buffer
+    // ... and, without a communicator, into its pinned host mirror as well (no copy after the run)
+    const bool mirror = reduce_dst != nullptr && c->comm == nullptr && !(flags & GWZ_RUN_BLOCKING);
+    GWZ_LAUNCH(launch_reduce_partials(w->d_partials, grid, NUM_ACC, reduce_dst ? reduce_dst : w->d_vec, c->stream,
+                                      mirror ? c->h_acc : nullptr, mirror ? c->d_err : nullptr, mirror ? c->h_err : nullptr));
+    w->vec_in_ctx = reduce_dst != nullptr;
+    w->vec_mirrored = mirror;
     return GWZ_OK;
 }
 
@@ -929,7 +948,13 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
             }
         GWZ_REQUIRE(rows <= GROUP_ROWS, "gwz_vqmc_run_group: too many walker sets on one device");
         if (rows == 1) {  // the usual case: no second reduction stage
-            GWZ_CUDA(cudaMemcpyAsync(c->d_acc, only->d_vec, sizeof(double) * nvec, cudaMemcpyDeviceToDevice, c->stream));
+            if (only->vec_in_ctx) {  // the sampling sums are already in c->d_acc
+                if (nvec > NUM_ACC)
+                    GWZ_CUDA(cudaMemcpyAsync(c->d_acc + NUM_ACC, only->d_vec + NUM_ACC, sizeof(double) * (nvec - NUM_ACC),
+                                             cudaMemcpyDeviceToDevice, c->stream));
+            } else {
+                GWZ_CUDA(cudaMemcpyAsync(c->d_acc, only->d_vec, sizeof(double) * nvec, cudaMemcpyDeviceToDevice, c->stream));
+            }
             continue;
         }
         rows = 0;
@@ -962,8 +987,11 @@ static int combine_and_fetch(gwz_walkers* const* ws, int n, unsigned flags, gwz_
     }
     for (gwz_context* c : ctxs) {
         if (int rc = use_device(c)) return rc;
-        GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * nvec, cudaMemcpyDeviceToHost, c->stream));
-        GWZ_CUDA(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        // sums and the error flag (which lives right behind them) in one copy -- unless the reduction kernel has
+        // already written them to the pinned host mirror
+        bool mirrored = (n == 1) && ws[0]->vec_mirrored && nvec == NUM_ACC;
+        if (!mirrored)
+            GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * (NUM_VEC + 1), cudaMemcpyDeviceToHost, c->stream));
     }
     int status = GWZ_OK;
     for (gwz_context* c : ctxs) {
@@ -1019,7 +1047,7 @@ extern "C" int gwz_vqmc_run_group(gwz_walkers* const* ws, int n, const double* p
         const bool time_it = (i == 0);
         timed_first |= time_it;
         if (int rc = enqueue_run(ws[i], tb, steps_per_walker, burn_in, kernel_kind, flags, nullptr, nullptr, nullptr,
-                                 time_it))
+                                 time_it, nullptr, nullptr, n == 1 ? ws[i]->m->ctx->d_acc : nullptr))
             return rc;
         if (flags & GWZ_RUN_BLOCKING)
             if (int rc = enqueue_blocking(ws[i], 0, time_it)) return rc;
@@ -1346,6 +1374,7 @@ extern "C" int gwz_sweep_destroy(gwz_sweep* s) {
     cudaFree(s->d_partials);
     cudaFree(s->d_rep);
     cudaFree(s->d_mult);
+    cudaFree(s->d_done);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     s->magic = 0;
@@ -1498,7 +1527,12 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
         L.extra_state = rr.extra_state;
         L.has_extra = rr.has_extra;
         uint64_t chunk = 1;
-        GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, true, L.dim ? L.dim : 1, c->prop.multiProcessorCount, &grid, &chunk));
+        if (s->enum_grid == 0) {  // occupancy query: once per handle
+            GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, true, L.dim ? L.dim : 1, c->prop.multiProcessorCount,
+                                &s->enum_grid, &s->enum_chunk));
+        }
+        grid = s->enum_grid;
+        chunk = s->enum_chunk;
         if (grid <= s->grid) {
             L.grid = grid;
             L.chunk = chunk;
@@ -1524,7 +1558,12 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
         L.symmetric = 0;
         L.has_extra = 0;
         uint64_t chunk = 1;
-        GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, false, L.dim, c->prop.multiProcessorCount, &grid, &chunk));
+        if (s->rep_grid == 0) {
+            GWZ_CUDA(sweep_grid(m->nw, L.tb.kc, m->N, m->M, false, L.dim, c->prop.multiProcessorCount, &s->rep_grid,
+                                &s->rep_chunk));
+        }
+        grid = s->rep_grid;
+        chunk = s->rep_chunk;
         if (grid > s->grid) {
             cudaFree(s->d_partials);
             s->d_partials = nullptr;
@@ -1535,16 +1574,30 @@ static int sweep_run(gwz_sweep* s, const double* params, double acc4[4]) {
         L.grid = grid;
         L.chunk = chunk;
     }
+    // small grids of the state-by-state kernel reduce inside the sweep kernel (last CTA); without a communicator the
+    // four sums go to the pinned host mirror as well, so that a repeated sweep is one launch and one synchronisation
+    const bool sym_kernel = L.symmetric && L.basis == nullptr && m->N + m->M <= 64;
+    const bool fused = !sym_kernel && grid <= 2048;
+    if (fused) {
+        if (!s->d_done) {
+            GWZ_CUDA(cudaMalloc(&s->d_done, sizeof(unsigned)));
+            GWZ_CUDA(cudaMemsetAsync(s->d_done, 0, sizeof(unsigned), c->stream));
+        }
+        L.done = s->d_done;
+        L.out = c->d_acc;
+        L.mirror = c->comm ? nullptr : c->h_acc;
+    }
     GWZ_CUDA(cudaEventRecord(s->ev0, c->stream));
     GWZ_LAUNCH(launch_sweep(L, c->stream));
     GWZ_CUDA(cudaEventRecord(s->ev1, c->stream));
-    GWZ_LAUNCH(launch_reduce_partials(s->d_partials, grid, 4, c->d_acc, c->stream));
+    if (!fused)
+        GWZ_LAUNCH(launch_reduce_partials(s->d_partials, grid, 4, c->d_acc, c->stream, c->comm ? nullptr : c->h_acc));
     if (c->comm) {
         const NcclApi* api = nccl_api(nullptr);
         if (!api) return fail(GWZ_ERR_NCCL, "NCCL unavailable");
         GWZ_NCCL(api, api->AllReduce(c->d_acc, c->d_acc, 4, kNcclFloat64, kNcclSum, c->comm, c->stream));
+        GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
     }
-    GWZ_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     s->ms_pending = true;  // cudaEventElapsedTime costs 5 us: only when gwz_sweep_last_kernel_ms asks (a small sweep is 60 us)
     if (sym_ranked && s->rep_state == 0 && s->sym_calls <= 2) {

@@ -124,6 +124,9 @@ struct gwz_walkers {
     int bpartials_cap = 0;
     bool blk_valid = false;
     uint64_t blk_len = 0;  // resample length of the last analysis
+    int grid_key = 0, grid_cached = 0;  // persistent grid of the kernel used last (occupancy query cached)
+    bool vec_in_ctx = false;            // the last run reduced its sampling sums straight into ctx->d_acc
+    bool vec_mirrored = false;          // ... and the reduction kernel also wrote them to the pinned host mirror
 };
 
 

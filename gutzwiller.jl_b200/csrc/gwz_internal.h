@@ -74,7 +74,9 @@ struct WalkerLaunch {
 cudaError_t walker_grid(int nw, int N, int kind, int kc, bool record, size_t n, int sm_count, int* grid);
 cudaError_t launch_walkers(const WalkerLaunch& L, cudaStream_t s);
 // out[ncomp] = sum over blocks of partials[block][ncomp], fixed order
-cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s);
+// mirror (optional): pinned host copy of out, written by the kernel; err_dev -> err_host likewise
+cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s,
+                                   double* mirror = nullptr, const int* err_dev = nullptr, int* err_host = nullptr);
 cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, const uint64_t* start_dev, cudaStream_t s);
 cudaError_t launch_walker_estimates(const double* acc, size_t n, double shift_e, double* val_w, double* grad_w,
                                     cudaStream_t s);
@@ -134,6 +136,10 @@ struct SweepLaunch {
     uint64_t extra_state;  // symmetric mode: one more state evaluated with weight 1 (the uniform state, see sweep_run)
     int has_extra;
     const uint32_t* weight;  // stored mode, optional: orbit sizes of a representative basis
+    // optional fused reduction (sweep_kernel, small grids): the last CTA sums the partials into out (+ pinned mirror)
+    unsigned* done;
+    double* out;
+    double* mirror;
     // optional per-state output (terms kernel): out[count][4] for states first..first+count-1
     double* terms_out;
     uint64_t* states_out;  // AoS count x W

@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(SWEEP_BLOCK)
 sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
              const uint64_t* __restrict__ basis, uint64_t dim, uint64_t rank_begin, uint64_t chunk,
              const uint64_t* __restrict__ binom, double* __restrict__ partials,
-             const uint32_t* __restrict__ weight /* stored mode, optional: orbit sizes of a representative basis */) {
+             const uint32_t* __restrict__ weight /* stored mode, optional: orbit sizes of a representative basis */,
+             unsigned* __restrict__ done /* optional: fused reduction by the last CTA (small grids) */,
+             double* __restrict__ out, double* __restrict__ mirror) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StepScratch<NW, KC> sc(smem_raw, dm.N, typename StepScratch<NW, KC>::SweepLayout{});
     sc.fill_exptab(dm.N, tb.c);
@@ -160,6 +162,24 @@ sweep_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTab
         for (int q = 0; q < SWEEP_BLOCK / 32; ++q) v += sm[q][threadIdx.x];
         partials[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
     }
+    if (done == nullptr) return;
+    // Fused reduction for small grids (repeated sweeps over a few thousand stored representatives are latency bound:
+    // a second launch costs as much as the sweep).  The CTA that finishes last sums the per-block partials in a fixed
+    // order (component = warp, blocks strided over the lanes, shuffle tree): bitwise reproducible.
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!last) return;
+    double v = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32u) v += __ldcg(partials + (size_t)b * 4 + warp);
+    v = warp_sum(v);
+    if (lane == 0) {
+        out[warp] = v;
+        if (mirror) mirror[warp] = v;
+    }
+    if (threadIdx.x == 0) *done = 0u;
 }
 
 // Symmetry-reduced ranked sweep.  HubbardReal1D is a periodic chain and the Gutzwiller amplitude only depends on
@@ -501,11 +521,13 @@ cudaError_t launch_sweep(const SweepLaunch& L, cudaStream_t s) {
         } else if (ranked) {
             if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, true>, smem)) return e;
             sweep_kernel<NW, KC, true><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
-                                                                         L.binom, L.partials, nullptr);
+                                                                         L.binom, L.partials, nullptr, L.done, L.out,
+                                                                         L.mirror);
         } else {
             if (cudaError_t e = ensure_smem(sweep_kernel<NW, KC, false>, smem)) return e;
             sweep_kernel<NW, KC, false><<<L.grid, SWEEP_BLOCK, smem, s>>>(L.dm, L.tb, L.basis, L.dim, L.rank_begin, L.chunk,
-                                                                          L.binom, L.partials, L.weight);
+                                                                          L.binom, L.partials, L.weight, L.done, L.out,
+                                                                          L.mirror);
         }
     });
     return cudaGetLastError();

@@ -174,8 +174,11 @@ __global__ void walker_ref_kernel(const __grid_constant__ DevModel dm, const __g
 // ------------------------------------------------------------------------------------------
 // small helper kernels
 // ------------------------------------------------------------------------------------------
+// out[comp] (device) and, when mirror != nullptr, mirror[comp] (pinned host memory, written over the bus so that the
+// host needs no copy after the stream is idle); block 0 also mirrors the error flag.
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int ncomp,
-                                       double* __restrict__ out) {
+                                       double* __restrict__ out, double* __restrict__ mirror,
+                                       const int* __restrict__ err_dev, int* __restrict__ err_host) {
     // one warp per component, fixed summation order
     __shared__ double sm[32];
     const int comp = blockIdx.x;
@@ -189,6 +192,8 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
         double t = 0.0;
         for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += sm[q];
         out[comp] = t;
+        if (mirror) mirror[comp] = t;
+        if (comp == 0 && err_host) *err_host = *err_dev;
     }
 }
 
@@ -312,8 +317,9 @@ cudaError_t launch_walker_ref(const DevModel& dm, const DevTables& tb, int nw, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s) {
-    reduce_partials_kernel<<<ncomp, 256, 0, s>>>(partials, nblocks, ncomp, out);
+cudaError_t launch_reduce_partials(const double* partials, int nblocks, int ncomp, double* out, cudaStream_t s,
+                                   double* mirror, const int* err_dev, int* err_host) {
+    reduce_partials_kernel<<<ncomp, nblocks > 64 ? 256 : 64, 0, s>>>(partials, nblocks, ncomp, out, mirror, err_dev, err_host);
     return cudaGetLastError();
 }
 cudaError_t launch_walker_init(uint64_t* addr, double* acc, size_t n, int W, const uint64_t* start_dev,
