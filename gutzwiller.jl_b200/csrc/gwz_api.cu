@@ -837,7 +837,7 @@ static int enqueue_blocking(gwz_walkers* w, uint64_t len, bool time_it) {
         cudaFree(w->d_ser_v);
         w->d_ser_v = nullptr;
         w->scratch_cap = 0;
-        if (cudaMalloc(&w->d_ser_v, sizeof(double) * (size_t)len * w->n) != cudaSuccess) {
+        if (cudaMalloc(&w->d_ser_v, sizeof(double) * blocking_scratch_stride(len) * w->n) != cudaSuccess) {
             cudaGetLastError();
             return fail(GWZ_ERR_NOMEM, "blocking analysis: no device memory for the resampled series (8 B per walker and slot)");
         }
@@ -1209,7 +1209,8 @@ extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const doub
         return fail(GWZ_ERR_INVALID, "gwz_series_blocking: resample length too large for the per-level shared-memory store");
     const size_t cells = (size_t)steps * (size_t)n;
     DevBuf<double> d_tau, d_eloc, d_out, d_part, d_vec, d_scratch;
-    GWZ_CUDA(d_scratch.alloc((size_t)len * (size_t)n));
+    const size_t srow = blocking_scratch_stride(len);
+    GWZ_CUDA(d_scratch.alloc(srow * (size_t)n));
     GWZ_CUDA(d_tau.alloc(cells));
     GWZ_CUDA(d_eloc.alloc(cells));
     GWZ_CUDA(d_out.alloc(5 * (size_t)n));
@@ -1238,14 +1239,19 @@ extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const doub
     GWZ_LAUNCH(launch_reduce_partials(d_part.p, grid, NUM_BACC, d_vec.p, c->stream));
     double hb[NUM_BACC];
     GWZ_CUDA(cudaMemcpyAsync(hb, d_vec.p, sizeof(double) * NUM_BACC, cudaMemcpyDeviceToHost, c->stream));
-    if (resampled && len > 1)
-        GWZ_CUDA(cudaMemcpyAsync(resampled, d_scratch.p, sizeof(double) * (size_t)len * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> rows;
+    if (resampled && len > 1) {
+        rows.resize(srow * (size_t)n);
+        GWZ_CUDA(cudaMemcpyAsync(rows.data(), d_scratch.p, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost, c->stream));
+    }
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
     if (out) {
         float ms = 0.f;
         GWZ_CUDA(cudaEventElapsedTime(&ms, c->ev2, c->ev3));
         fill_blocking(hb, steps, len, ms, false, out);
     }
+    for (size_t w = 0; w < (size_t)n && !rows.empty(); ++w)  // walker-major scratch -> the caller's step-major layout
+        for (size_t i = 0; i < (size_t)len; ++i) resampled[i * (size_t)n + w] = rows[w * srow + i];
     return fetch_blocking_rows(c, d_out.p, (size_t)n, mean_w, err_w, err_err_w, k_w, blocks_w);
 }
 

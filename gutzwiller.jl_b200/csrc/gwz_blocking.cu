@@ -29,7 +29,13 @@ struct SmemLevels {
 // (lockstep).  Rows are fetched SB at a time into registers, one batch ahead of the one being consumed, so that every
 // warp keeps 2 x SB coalesced 256-byte requests in flight (with one row per warp in flight the kernel was bound by
 // memory latency at a quarter of the HBM bandwidth).
-constexpr int SB = 4;
+#ifndef GWZ_BLK_SB
+#define GWZ_BLK_SB 4
+#endif
+#ifndef GWZ_BLK_MINB
+#define GWZ_BLK_MINB 1
+#endif
+constexpr int SB = GWZ_BLK_SB;
 struct SeriesLoad {
     const double* __restrict__ pt;  // row of the first interval of the NEXT batch
     const double* __restrict__ pe;
@@ -42,6 +48,13 @@ struct SeriesLoad {
             const bool ok = first + q < n;
             nt[q] = ok ? __ldcs(pt + q * stride) : 0.0;
             ne[q] = ok ? __ldcs(pe + q * stride) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {  // and the batch after that into L2 (uniform across the warp: one request per row)
+            if (first + 2 * SB + q < n) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pt + (2 * SB + q) * stride));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + (2 * SB + q) * stride));
+            }
         }
         pt += SB * stride;
         pe += SB * stride;
@@ -65,21 +78,20 @@ struct SeriesLoad {
         }
     }
 };
-// slot i of the resampled series; calls come with i = 0, 1, 2, ...
+// slot i of the resampled series; calls come with i = 0, 1, 2, ...  The scratch is walker-major (each thread fills
+// its own contiguous row): threads reach a given slot at different times, and consecutive 8-byte stores of ONE thread
+// complete a 32-byte sector within four slots, whereas a step-major layout leaves partially written sectors in L2
+// until the slowest neighbour arrives (evicted half-filled for long series).
 struct ScratchStore {
     double* __restrict__ v;
-    size_t stride;
-    __device__ __forceinline__ void operator()(uint64_t, double x) {
-        *v = x;
-        v += stride;
-    }
+    __device__ __forceinline__ void operator()(uint64_t, double x) { *v++ = x; }
 };
 
-__global__ void __launch_bounds__(BLOCKING_BLOCK)
+__global__ void __launch_bounds__(BLOCKING_BLOCK, GWZ_BLK_MINB)
 series_blocking_kernel(const double* __restrict__ tau, const double* __restrict__ eloc, size_t stride, size_t n,
                        uint64_t steps, uint64_t len, int levels, const double* __restrict__ acc, size_t acc_stride,
-                       double shift_e, double shift_g, double* __restrict__ scratch, double* __restrict__ out,
-                       size_t out_stride, double* __restrict__ partials) {
+                       double shift_e, double shift_g, double* __restrict__ scratch, size_t scratch_stride,
+                       double* __restrict__ out, size_t out_stride, double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* lv = reinterpret_cast<double*>(smem_raw) + threadIdx.x;
     int* khist = reinterpret_cast<int*>(smem_raw + sizeof(double) * (size_t)(levels > 0 ? levels : 1) * BLK_FIELDS * BLOCKING_BLOCK);
@@ -121,28 +133,40 @@ series_blocking_kernel(const double* __restrict__ tau, const double* __restrict_
             o.blocks = 1;
         } else {
             // phase A: resample, driven by the input intervals (all threads at the same step of their series)
-            double* vw = scratch + w;
+            double* vw = scratch + w * scratch_stride;
             SeriesLoad src;
             src.pt = tw;
             src.pe = ew;
             src.stride = stride;
             src.n = steps;
             src.fetch(0);
-            resample_by_input(steps, len, total, src, ScratchStore{vw, stride});
+            resample_by_input(steps, len, total, src, ScratchStore{vw});
             // phase B: the resampled values, in lockstep, into the per-level moments
             for (int i = 0; i < levels * BLK_FIELDS; ++i) lv[i * BLOCKING_BLOCK] = 0.0;
             BlockingStream<SmemLevels> bs(SmemLevels{lv}, levels, centre);
             {
                 const double* pv = vw;
                 uint64_t i = 0;
-                for (; i + 4 <= len; i += 4, pv += 4 * stride) {  // four loads in flight, then four pushes
-                    const double v0 = pv[0], v1 = pv[stride], v2 = pv[2 * stride], v3 = pv[3 * stride];
-                    bs.push(v0);
-                    bs.push(v1);
-                    bs.push(v2);
-                    bs.push(v3);
+                if (levels >= 2) {  // groups of four (one 32-byte sector of this thread's row): levels 0 and 1 in registers
+                    double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0;
+                    double2 lo, hi;  // the group being folded; the next one is requested before folding it
+                    if (len >= 4) {
+                        lo = *reinterpret_cast<const double2*>(pv);
+                        hi = *reinterpret_cast<const double2*>(pv + 2);
+                    }
+                    for (; i + 4 <= len; i += 4, pv += 4) {
+                        double2 nlo = lo, nhi = hi;
+                        if (i + 8 <= len) {
+                            nlo = *reinterpret_cast<const double2*>(pv + 4);
+                            nhi = *reinterpret_cast<const double2*>(pv + 6);
+                        }
+                        bs.push4(lo.x, lo.y, hi.x, hi.y, b0, b1, b2, b3, b4);
+                        lo = nlo;
+                        hi = nhi;
+                    }
+                    bs.flush_level1(b0, b1, b2, b3, b4);
                 }
-                for (; i < len; ++i, pv += stride) bs.push(*pv);
+                for (; i < len; ++i, ++pv) bs.push(*pv);
             }
             bs.finalize(len, c_chi2_q99, o);
         }
@@ -189,6 +213,9 @@ series_blocking_kernel(const double* __restrict__ tau, const double* __restrict_
     }
 }
 
+// doubles per walker row of the scratch: the resample length rounded up to whole 32-byte sectors
+size_t blocking_scratch_stride(uint64_t len) { return (size_t)((len + 3) & ~3ull); }
+
 static size_t blocking_smem(int levels) {
     const size_t lv = sizeof(double) * (size_t)(levels > 0 ? levels : 1) * BLK_FIELDS * BLOCKING_BLOCK;
     const size_t red = sizeof(double) * 6 * (BLOCKING_BLOCK / 32);
@@ -218,7 +245,7 @@ cudaError_t launch_series_blocking(const BlockingLaunch& L, cudaStream_t s) {
     const int levels = blocking_levels(L.len);
     series_blocking_kernel<<<L.grid, BLOCKING_BLOCK, blocking_smem(levels), s>>>(
         L.tau, L.eloc, L.stride, L.n, L.steps, L.len, levels, L.acc, L.acc_stride, L.shift_e, L.shift_g, L.scratch,
-        L.out, L.out_stride, L.partials);
+        blocking_scratch_stride(L.len), L.out, L.out_stride, L.partials);
     return cudaGetLastError();
 }
 

@@ -203,6 +203,56 @@ struct BlockingStream {
         }
     }
 
+    // level-l moments update with one value d (cnt = values already seen by that level): registers or store
+    static GWZ_HD void upd(double& m0, double& m1, double& m2, double& m3, double& m4, double d, bool first) {
+        const double last = m4;
+        m0 += d;
+        m1 += d * d;
+        if (first) m3 = d;
+        else m2 += last * d;
+        m4 = d;
+    }
+
+    // Four consecutive values at once, for a stream whose push count is a multiple of four (the device's phase B,
+    // where all threads are at the same value index): the carry pattern of levels 0 and 1 is then static -- level 0
+    // sees all four, level 1 their two pair averages (b0..b4 stay in registers next to a0..a4), level 2 the average
+    // of the four -- and only levels >= 2 touch the store, once per four values.  Needs levels >= 2.
+    GWZ_HD void push4(double v0, double v1, double v2, double v3, double& b0, double& b1, double& b2, double& b3,
+                      double& b4) {
+        const uint64_t cnt = pushed;  // multiple of 4
+        pushed += 4;
+        const double d0 = v0 - centre, d1 = v1 - centre, d2 = v2 - centre, d3 = v3 - centre;
+        upd(a0, a1, a2, a3, a4, d0, cnt == 0);
+        upd(a0, a1, a2, a3, a4, d1, false);
+        upd(a0, a1, a2, a3, a4, d2, false);
+        upd(a0, a1, a2, a3, a4, d3, false);
+        const double p0 = 0.5 * (d0 + d1), p1 = 0.5 * (d2 + d3);
+        upd(b0, b1, b2, b3, b4, p0, cnt == 0);
+        upd(b0, b1, b2, b3, b4, p1, false);
+        double d = 0.5 * (p0 + p1);
+        uint64_t c = cnt >> 2;  // values already seen by level 2
+        for (int l = 2; l < levels; ++l) {
+            const double last = st(l, 4);
+            st(l, 0) += d;
+            st(l, 1) += d * d;
+            if (c == 0) st(l, 3) = d;
+            else st(l, 2) += last * d;
+            st(l, 4) = d;
+            if (!(c & 1ull)) break;
+            d = 0.5 * (last + d);
+            c >>= 1;
+        }
+    }
+    GWZ_HD void flush_level1(double b0, double b1, double b2, double b3, double b4) {
+        if (levels > 1) {
+            st(1, 0) = b0;
+            st(1, 1) = b1;
+            st(1, 2) = b2;
+            st(1, 3) = b3;
+            st(1, 4) = b4;
+        }
+    }
+
     // len = number of values pushed (>= 2); q99 = the quantile table above
     GWZ_HD void finalize(uint64_t len, const double* q99, BlockingOut& o) {
         if (levels > 0) {

@@ -162,13 +162,14 @@ struct BlockingLaunch {
     const double* acc;   // [NUM_WALKER_ACC][acc_stride] running sums of the same steps, or null
     size_t acc_stride;
     double shift_e, shift_g;
-    double* scratch;     // [len][stride]: the resampled series pass through here once
+    double* scratch;     // [n][blocking_scratch_stride(len)] walker-major: the resampled series pass through here once
     double* out;         // [5][out_stride]: mean, err, err_err, k, blocks per walker, or null
     size_t out_stride;
     double* partials;    // [grid][NUM_BACC]
     int grid;
 };
 cudaError_t blocking_grid(uint64_t len, size_t n, int sm_count, int* grid);
+size_t blocking_scratch_stride(uint64_t len);
 cudaError_t launch_series_blocking(const BlockingLaunch& L, cudaStream_t s);
 
 // ---- DVec(result) histogram (gwz_hist.cu) ----------------------------------------------------

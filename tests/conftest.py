@@ -14,6 +14,7 @@ if HERE not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices (skipped otherwise)")
 
 
 @pytest.fixture(scope="session")

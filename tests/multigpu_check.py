@@ -97,6 +97,24 @@ def check_sparse(rank, world):
     print(f"[rank {rank}/{world}] stored operator OK val={r.val:.12f} grad0={r.grad[0]:.9f} sweep={v:.12f}", flush=True)
 
 
+def check_blocking(rank, world):
+    """val_err_and_grad across ranks: every walker's series is blocked on the GPU that owns it, the 38 blocking sums
+    travel in the same all-reduce as the 13 sampling sums; the result must be the single-GPU one."""
+    H = gw.HubbardReal1D(gw.near_uniform(N, M), u=U)
+    qmc = gw.KineticVQMC(H, gw.GutzwillerAnsatz(H), walkers=TOTAL, steps=128, seed=77)
+    val, err, grad = qmc.val_err_and_grad([G])
+    b = qmc.result.blocking_summary
+    ctx = gw.Context(int(os.environ.get("LOCAL_RANK", "0")))
+    w = gw.Walkers(H.model(ctx), TOTAL, H.address.words, seed=77)
+    r = w.run([G], 128, blocking=True)
+    ref = r.blocking
+    assert b.walkers == ref.walkers == TOTAL and b.failed == ref.failed and (b.k_min, b.k_max) == (ref.k_min, ref.k_max)
+    assert abs(b.mean - ref.mean) <= 1e-13 * abs(ref.mean) and abs(b.err_ok - ref.err_ok) <= 1e-12 * ref.err_ok
+    assert abs(b.grad[0] - ref.grad[0]) <= 1e-10 * abs(ref.grad[0])
+    assert val == b.mean and (err == b.err or (err != err and b.err != b.err))
+    print(f"[rank {rank}/{world}] blocking OK mean={b.mean:.12f} err={b.err_ok:.3e} k={b.k_min}..{b.k_max}", flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--single-process", type=int, default=0)
@@ -126,6 +144,7 @@ def main():
         assert np.all(np.abs(again - acc) <= 1e-12 * np.abs(acc)), (again, acc)
     ref, ref_acc = reference_single_gpu(int(os.environ.get("LOCAL_RANK", "0")))
     check(res.last, ref, acc, ref_acc, f"rank {rank}/{world}")
+    check_blocking(rank, world)
     check_generic(rank, world)
     check_sparse(rank, world)
     import torch.distributed as dist
