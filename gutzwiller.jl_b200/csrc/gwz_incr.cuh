@@ -10,8 +10,9 @@
 // enters the estimators stays a pure function of the address and is evaluated in exactly the same
 // floating-point order as bond_sums / select_move (S and E are re-summed from the integer counts
 // each step; only integers are carried from step to step), so this path is bitwise identical to
-// step_planes and to the unary kernel (tests/test_gpu_walkers.py::test_incremental_kernel_is_bitwise_
-// identical).  Reference: kinetic_sample!, src/kinetic-vqmc/qmc.jl:14-44.
+// step_planes and to the unary kernel (tests/test_gpu_walkers.py::test_planes_kernel_is_bitwise_identical_to_unary runs
+// the three of them with GWZ_FAST=0).  Round 2's production kernel is gwz_fast.cuh; this one stays as its
+// independently validated counterpart (GWZ_FAST=0).  Reference: kinetic_sample!, src/kinetic-vqmc/qmc.jl:14-44.
 #pragma once
 #include "gwz_planes.cuh"
 

@@ -283,17 +283,22 @@ def test_planes_kernel_is_bitwise_identical_to_unary(gw, oracle_mod, N, M, u, g,
     starts = [o.near_uniform()[: o.W], o.from_onr(onr)[: o.W]]
     for start in starts:
         out = {}
-        for planes in ("1", "0"):
-            monkeypatch.setenv("GWZ_PLANES", planes)
+        # (GWZ_PLANES, GWZ_INCR): incremental class counts (round-1 production), full re-count on the planes
+        # (walker_planes_kernel, also the fallback for M < 4), unary bitstring
+        for mode in (("1", "1"), ("1", "0"), ("0", "1")):
+            monkeypatch.setenv("GWZ_PLANES", mode[0])
+            monkeypatch.setenv("GWZ_INCR", mode[1])
             w = gw.Walkers(model, 777, start, seed=21, global_offset=3)
             r1 = w.run([g], 97, burn_in=5)
             r2 = w.run([g], 40, keep_acc=True)
             vals, grads = w.estimates()
-            out[planes] = (w.addresses(), np.array(r1.acc[:]), np.array(r2.acc[:]), vals, grads, w.steps_done())
-        a, b = out["1"], out["0"]
-        assert np.array_equal(a[0], b[0])
-        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and a[5] == b[5] == 142
+            out[mode] = (w.addresses(), np.array(r1.acc[:]), np.array(r2.acc[:]), vals, grads, w.steps_done())
+        b = out[("0", "1")]
+        for mode in (("1", "1"), ("1", "0")):
+            a = out[mode]
+            assert np.array_equal(a[0], b[0]), mode
+            assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), mode
+            assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and a[5] == b[5] == 142, mode
 
 
 @pytest.mark.parametrize("N,M", [(5, 5), (12, 12), (20, 20)])
