@@ -1,5 +1,5 @@
 // gwz_fast.cuh -- production kinetic_sample! (src/kinetic-vqmc/qmc.jl:14-44) with everything a hop does not change
-// carried from step to step as exact integers.
+// carried from step to step as exact integers and bit masks.
 //
 // A hop across bond z changes the occupations of modes z and z+1, hence the classes (L,R) of the three bonds z-1, z,
 // z+1 and nothing else.  Regular bonds (both occupations < 4) fall into 16 classes (l, r); their two hops have the
@@ -7,22 +7,27 @@
 // g = Delta + 2 = 0..5.  The walker carries
 //   * np   -- the number of regular hops per rate class g, six 10-bit fields of one 64-bit integer (register);
 //   * E    -- sum over regular bonds of sqrt(n_src (n_dst + 1)) x rate (the off-diagonal part of E_loc), a double
-//             that is updated by table deltas and re-summed from the integer state every FAST_REFRESH steps and
+//             that is updated by table deltas and re-summed from the occupations every FAST_REFRESH steps and
 //             whenever it has fallen 16-fold below its peak since the last re-summation, which bounds its rounding
-//             drift below 2e-13 relative for any dynamic range of the rates; dsum = sum n (n-1) / 2, the number of occupied
-//             modes and the number of modes with >= 4 particles (ints);
-//   * the occupations as bytes and as ONE-HOT bit masks over the modes, A_s = {z : n_z = s} and its ring rotation
-//     Q_s = {z : n_(z+1) = s} for s = 0..3, plus A_4 / Q_4 for "n >= 4" (shared memory, [row][word][thread]).
+//             drift below 5e-13 relative for any dynamic range of the rates; dsum = sum n (n-1) / 2 (int) and the
+//             numbers of occupied modes / of modes with >= 4 particles (two 16-bit fields of one int);
+//   * the occupations as bytes (shared memory, [word of 4 modes][thread]);
+//   * HOP MASKS over the bonds (shared memory, [row][thread][words]): HR_g = {z : the right hop across z is regular
+//     and of rate class g}, HL_g likewise for the left hops, g = 0..5, plus the mask of the bonds that touch a mode
+//     with >= 4 particles ("generic" bonds).
 // Per step: S = sum_g n_g r_g is evaluated from the integers in a fixed order (6 FMA: a pure function of the
 // address).  The move is drawn in two levels.  (1) the rate class g by the running sums of S.  (2) all hops of a rate
-// class are equally likely, so the j-th of them in the order (direction, bond position) is taken: the bonds with a
-// right hop of rate class g are  U_s A_s & Q_(s+g-3)  (source occupation s = 1..3), those with a left hop
-// U_s A_(s+g-3) & Q_s; the rows are stored with zero rows around them, so the out-of-range members of the unions read
-// as empty and the row index needs no branch -- twelve shared-memory loads and six logic operations per 32 modes.
-// The hop then updates np / E by three table look-ups (one per touched bond: 16-byte entries (dE, dnp) indexed by the
-// capped occupations before and after), two occupation bytes and eight one-hot bits (shared-memory reductions).
-// Bonds touching a mode with >= 4 particles ("generic" bonds) are rare; their sums are cached and re-evaluated from
-// the occupation bytes only when a hop touches such a mode, as in gwz_incr.cuh.
+// class are equally likely, so the j-th of them in the order (direction, bond position) is taken: the j-th set bit of
+// the row pair (HR_g, HL_g) -- two vector loads, no logic.  The hop then updates the three touched bonds from tables
+// indexed by the capped occupations before and after: 16-byte entries (dE, dnp) plus one word with the four hop-mask
+// rows the bond leaves and enters, i.e. three additions to (E, np) and twelve single-bit shared-memory XORs; a
+// fourth table gives the change of the occupied / >= 4 counts.  Bonds touching a mode with >= 4 particles are rare;
+// their sums are cached and re-evaluated from the occupation bytes only when a hop touches such a mode, as in
+// gwz_incr.cuh.
+//
+// What bounds the kernel is the shared-memory data pipe (wavefronts per step), then instruction issue: tables that are
+// indexed by data (different entries per lane) cost a wavefront per distinct bank group, so they are kept dense and
+// small (16-byte entries, row ids as bytes), and everything that depends only on the bond position is computed.
 //
 // The partition of [0, S) into hops is ordered by (rate class, direction, bond position), generic bonds last: the same
 // distribution as the reference's pick_random_from_cumsum (qmc.jl:52-61) with a different u -> hop map (tests:
@@ -33,10 +38,20 @@
 
 namespace gwz {
 
-constexpr int FAST_REFRESH = 32;
-// one-hot rows per thread (each NWM words): [0,1] zero | [2..5] A_0..A_3 | [6,7] zero | [8..11] Q_0..Q_3 | [12,13] zero |
-// [14] A_4 (n >= 4) | [15] Q_4.  A row index q + 2 (resp. q + 8 for Q) is valid for every q in -2..5.
-constexpr int OH_ROWS = 16, OH_A = 2, OH_Q = 8, OH_A4 = 14, OH_Q4 = 15;
+// threads per CTA of the production kernel (its own scratch layout) and resident CTAs per SM: 768 threads per SM with
+// up to 85 registers for M <= 64 (1024 threads with 64 registers measured slower: the kernel is bound by the
+// shared-memory pipe and by issue, not by latency)
+#ifndef GWZ_FAST_FB
+#define GWZ_FAST_FB 256
+#endif
+#ifndef GWZ_FAST_MINB
+#define GWZ_FAST_MINB 3
+#endif
+__host__ __device__ constexpr int fast_block(int nwm) { return nwm <= 4 ? GWZ_FAST_FB : 256; }
+__host__ __device__ constexpr int fast_min_blocks(int nwm) { return nwm <= 2 ? GWZ_FAST_MINB : (nwm <= 4 ? 512 / fast_block(nwm) : 1); }
+constexpr int FAST_REFRESH = 64;   // steps between re-summations of E (a power of two)
+// hop-mask rows per thread: [0..5] HR_g | [6..11] HL_g | [12] dummy (absorbs the XORs of absent hops) | [13] generic bonds
+constexpr int HM_R = 0, HM_L = 6, HM_DUMMY = 12, HM_BIG = 13, HM_ROWS = 14;
 
 struct FastEntry {  // what one bond's class change adds to (E, np)
     double dE;
@@ -53,79 +68,158 @@ struct FastRates {
     double rs[6];  // r[g] / 2^(field position inside its 32-bit half): multiplies the masked, unshifted field
 };
 
+// 32-bit shared-window addressing for the step loop: one base register, every region at a compile-time offset
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds64(uint32_t a, uint32_t& v0, uint32_t& v1) {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(a));
+}
+__device__ __forceinline__ void lds128(uint32_t a, uint32_t& v0, uint32_t& v1, uint32_t& v2, uint32_t& v3) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(a));
+}
+__device__ __forceinline__ uint32_t ldsu8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void stsu8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ double lds64f(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_entry_sums(uint32_t a, double& dE, unsigned long long& dn) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(*reinterpret_cast<unsigned long long*>(&dE)), "=l"(dn) : "r"(a));
+}
+__device__ __forceinline__ void red_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// 1 / x for a normal positive x: hardware seed + two Newton steps (relative error < 2^-51)
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int NWM>
 struct FastScratch {
-    static constexpr int ONR_WORDS = 8 * NWM;  // 4 modes per word
+    // hop-mask rows: NWV words per thread (NWM rounded up to a power of two), stored as NCH chunks of VW words so that
+    // a row is read by NCH conflict-free vector loads: [row][chunk][thread][VW]
+    static constexpr int FB = fast_block(NWM);
+    static constexpr int NWV = NWM <= 1 ? 1 : (NWM <= 2 ? 2 : (NWM <= 4 ? 4 : 8));
+    static constexpr int VW = NWV < 4 ? NWV : 4;
+    static constexpr int NCH = NWV / VW;
+    static constexpr uint32_t CH_BYTES = 4u * VW * FB;
+    static constexpr uint32_t ROW_BYTES = CH_BYTES * NCH;
+    static constexpr int ONR_WORDS = 8 * NWM;                 // occupation bytes, 4 modes per word: [word][thread]
+    static constexpr uint32_t ONR_STRIDE = 4u * FB;
+    static constexpr int MMAX = 32 * NWM;
     static constexpr int NTL = 5 * 15, NTM = 15 * 15, NTR = 15 * 5;
-    // shared by the CTA
-    FastEntry* TL;  // [a4][ix]      bond z-1: (a, x) -> (a, x')
-    FastEntry* TM;  // [ix][iy]      bond z:   (x, y) -> (x', y')
-    FastEntry* TR;  // [iy][b4]      bond z+1: (y, b) -> (y', b)
-    double* irate;  // [8]  1 / r_g
-    double* FE;     // [16] class weights for the re-summation of E, index 4 l + r
-    uint32_t* nth;  // [256]
-    // per thread, [entry][thread]
-    uint32_t* oh;   // [OH_ROWS][NWM][STEP_BLOCK]
-    uint32_t* onr;  // [ONR_WORDS][STEP_BLOCK]
-    // generic-bond path
-    double* exptab;  // [2N+2]
-    double* sqrtab;  // [N+2]
-    // byte offsets of the fixed-size regions from the start of the dynamic shared memory (step_fast addresses them
-    // as 32-bit shared-window addresses: base + compile-time constant)
-    static constexpr uint32_t OFF_TL = 0, OFF_TM = OFF_TL + 16 * NTL, OFF_TR = OFF_TM + 16 * NTM,
-                              OFF_IRATE = OFF_TR + 16 * NTR, OFF_FE = OFF_IRATE + 8 * 8, OFF_NTH = OFF_FE + 8 * 16,
-                              OFF_OH = OFF_NTH + 4 * 256, OFF_ONR = OFF_OH + 4 * OH_ROWS * NWM * STEP_BLOCK,
-                              OFF_EXP = OFF_ONR + 4 * ONR_WORDS * STEP_BLOCK;
-    static constexpr uint32_t ROW_BYTES = 4 * NWM * STEP_BLOCK;  // one one-hot row of all threads
+    // byte offsets from the start of the dynamic shared memory (step_fast addresses everything as base + constant)
+    static constexpr uint32_t OFF_TL = 0,                        // [a4][ix]   bond z-1: (a, x) -> (a, x')
+                              OFF_TM = OFF_TL + 16u * NTL,       // [ix][iy]   bond z:   (x, y) -> (x', y')
+                              OFF_TR = OFF_TM + 16u * NTM,       // [iy][b4]   bond z+1: (y, b) -> (y', b)
+                              // the hop-mask rows of the same transitions, one byte each: right hop before | left hop
+                              // before | right hop after | left hop after (same indices as TL, TM, TR)
+                              OFF_RL = OFF_TR + 16u * NTR, OFF_RM = OFF_RL + 4u * 76, OFF_RR = OFF_RM + 4u * 228,
+                              OFF_TC = OFF_RR + 4u * 76,         // [ix][iy]   int32: d(occupied) + 65536 d(modes >= 4)
+                              OFF_IRATE = OFF_TC + 4u * 228,     // [8]        1 / r_g
+                              OFF_FE5 = OFF_IRATE + 8u * 8,      // [5][5]     E weight of a bond of capped class (l, r)
+                              OFF_NTH = OFF_FE5 + 8u * 26,       // [256]      positions of the set bits of a byte
+                              OFF_ROWS = OFF_NTH + 4u * 256,     // hop-mask rows
+                              OFF_ONR = OFF_ROWS + HM_ROWS * ROW_BYTES, OFF_EXP = OFF_ONR + ONR_WORDS * ONR_STRIDE;
     __host__ __device__ static constexpr size_t bytes(int N) { return OFF_EXP + sizeof(double) * (size_t)(3 * N + 4); }
-    __device__ __forceinline__ FastScratch(unsigned char* base, int N) {
-        TL = reinterpret_cast<FastEntry*>(base + OFF_TL);
-        TM = reinterpret_cast<FastEntry*>(base + OFF_TM);
-        TR = reinterpret_cast<FastEntry*>(base + OFF_TR);
-        irate = reinterpret_cast<double*>(base + OFF_IRATE);
-        FE = reinterpret_cast<double*>(base + OFF_FE);
-        nth = reinterpret_cast<uint32_t*>(base + OFF_NTH);
-        oh = reinterpret_cast<uint32_t*>(base + OFF_OH);
-        onr = reinterpret_cast<uint32_t*>(base + OFF_ONR);
-        exptab = reinterpret_cast<double*>(base + OFF_EXP);
+
+    unsigned char* base;
+    double* exptab;  // [2N+2]  generic-bond path
+    double* sqrtab;  // [N+2]
+    __device__ __forceinline__ FastScratch(unsigned char* b, int N) : base(b) {
+        exptab = reinterpret_cast<double*>(b + OFF_EXP);
         sqrtab = exptab + (2 * N + 2);
     }
-    // contribution of one bond of capped class (l, r) to (E, np); zero for non-regular classes
-    __device__ static __forceinline__ FastEntry contrib(const DevTables& tb, int l, int r) {
-        FastEntry e;
-        e.dE = 0.0;
-        e.dn = 0ull;
+    // word i of hop-mask row `row` of this thread / occupation word q of this thread (generic pointers: set-up code)
+    __device__ __forceinline__ uint32_t* row_word(int row, int i) const {
+        return reinterpret_cast<uint32_t*>(base + OFF_ROWS + (uint32_t)row * ROW_BYTES + (uint32_t)(i / VW) * CH_BYTES +
+                                           4u * VW * threadIdx.x + 4u * (uint32_t)(i % VW));
+    }
+    __device__ __forceinline__ uint32_t* onr_word(int q) const {
+        return reinterpret_cast<uint32_t*>(base + OFF_ONR + (uint32_t)q * ONR_STRIDE + 4u * threadIdx.x);
+    }
+    __host__ __device__ static constexpr uint32_t onr_off(int m) { return (uint32_t)(m >> 2) * ONR_STRIDE + (uint32_t)(m & 3); }
+    __host__ __device__ static constexpr uint32_t bond_off(int z) {
+        return (uint32_t)((z >> 5) / VW) * CH_BYTES + 4u * (uint32_t)((z >> 5) % VW);
+    }
+    static_assert(ROW_BYTES * HM_ROWS < (1u << 24) && (ROW_BYTES & 0xFFu) == 0, "row offsets are ids x ROW_BYTES");
+
+    struct Contrib {  // one bond of capped class (l, r): its part of (E, np) and the rows holding its two hops
+        double e;
+        unsigned long long n;
+        int rR, rL;
+    };
+    __device__ static __forceinline__ Contrib contrib(const DevTables& tb, int l, int r) {
+        Contrib c;
+        c.e = 0.0;
+        c.n = 0ull;
+        c.rR = c.rL = HM_DUMMY;
         if (l < 4 && r < 4 && l >= 0 && r >= 0) {
-            e.dE = tb.FE[4 * l + r];
-            if (l >= 1) e.dn += 1ull << fast_field_pos(r - l + 3);
-            if (r >= 1) e.dn += 1ull << fast_field_pos(l - r + 3);
+            c.e = tb.FE[4 * l + r];
+            if (l >= 1) {
+                c.n += 1ull << fast_field_pos(r - l + 3);
+                c.rR = HM_R + (r - l + 3);
+            }
+            if (r >= 1) {
+                c.n += 1ull << fast_field_pos(l - r + 3);
+                c.rL = HM_L + (l - r + 3);
+            }
         }
-        return e;
+        return c;
     }
-    __device__ static __forceinline__ FastEntry delta(const FastEntry& a, const FastEntry& b) {  // a - b
+    __device__ static __forceinline__ FastEntry delta(const Contrib& a, const Contrib& b, uint32_t& rows) {  // b -> a
         FastEntry e;
-        e.dE = a.dE - b.dE;
-        e.dn = a.dn - b.dn;
+        e.dE = a.e - b.e;
+        e.dn = a.n - b.n;
+        rows = (uint32_t)b.rR | ((uint32_t)b.rL << 8) | ((uint32_t)a.rR << 16) | ((uint32_t)a.rL << 24);
         return e;
     }
-    __device__ __forceinline__ void fill_tables(int N, const DevTables& tb) const {
+    __device__ __forceinline__ void fill_tables(int N, int M, const DevTables& tb) const {
+        FastEntry* TL = reinterpret_cast<FastEntry*>(base + OFF_TL);
+        FastEntry* TM = reinterpret_cast<FastEntry*>(base + OFF_TM);
+        FastEntry* TR = reinterpret_cast<FastEntry*>(base + OFF_TR);
+        int32_t* TC = reinterpret_cast<int32_t*>(base + OFF_TC);
+        uint32_t* RL = reinterpret_cast<uint32_t*>(base + OFF_RL);
+        uint32_t* RM = reinterpret_cast<uint32_t*>(base + OFF_RM);
+        uint32_t* RR = reinterpret_cast<uint32_t*>(base + OFF_RR);
+        double* irate = reinterpret_cast<double*>(base + OFF_IRATE);
+        double* FE5 = reinterpret_cast<double*>(base + OFF_FE5);
+        uint32_t* nth = reinterpret_cast<uint32_t*>(base + OFF_NTH);
         for (int i = threadIdx.x; i < 2 * N + 2; i += blockDim.x) exptab[i] = exp(-tb.c * (double)(i - N));
         for (int i = threadIdx.x; i < N + 2; i += blockDim.x) sqrtab[i] = sqrt((double)i);
         // ix = 3 x4 + (x' - x4 + 1) encodes the capped occupation before and after (x' in {x4-1, x4, x4+1})
         for (int i = threadIdx.x; i < NTL; i += blockDim.x) {
             const int a = i / 15, ix = i % 15, x = ix / 3, x2 = x + ix % 3 - 1;
-            TL[i] = delta(contrib(tb, a, x2), contrib(tb, a, x));
+            TL[i] = delta(contrib(tb, a, x2), contrib(tb, a, x), RL[i]);
         }
         for (int i = threadIdx.x; i < NTM; i += blockDim.x) {
             const int ix = i / 15, iy = i % 15, x = ix / 3, x2 = x + ix % 3 - 1, y = iy / 3, y2 = y + iy % 3 - 1;
-            TM[i] = delta(contrib(tb, x2, y2), contrib(tb, x, y));
+            TM[i] = delta(contrib(tb, x2, y2), contrib(tb, x, y), RM[i]);
+            const int docc = (int)(x == 0 && x2 > 0) - (int)(x > 0 && x2 == 0) + (int)(y == 0 && y2 > 0) - (int)(y > 0 && y2 == 0);
+            const int dbig = (int)(x2 == 4) - (int)(x == 4) + (int)(y2 == 4) - (int)(y == 4);
+            TC[i] = docc + 65536 * dbig;
         }
         for (int i = threadIdx.x; i < NTR; i += blockDim.x) {
             const int iy = i / 5, b = i % 5, y = iy / 3, y2 = y + iy % 3 - 1;
-            TR[i] = delta(contrib(tb, y2, b), contrib(tb, y, b));
+            TR[i] = delta(contrib(tb, y2, b), contrib(tb, y, b), RR[i]);
         }
         if (threadIdx.x < 8) irate[threadIdx.x] = exp(tb.c * (double)((int)threadIdx.x - 2));
-        if (threadIdx.x < 16) FE[threadIdx.x] = tb.FE[threadIdx.x];
+        if (threadIdx.x < 25) {
+            const int l = threadIdx.x / 5, r = threadIdx.x % 5;
+            FE5[threadIdx.x] = (l < 4 && r < 4) ? tb.FE[4 * l + r] : 0.0;
+        }
         for (int b = threadIdx.x; b < 256; b += blockDim.x) {
             uint32_t e = 0u;
             int j = 0;
@@ -149,52 +243,20 @@ __host__ inline FastRates fast_rates(double c) {
 struct FastState {
     unsigned long long np;  // regular hops per rate class, 10-bit fields
     double E;
-    int dsum, nocc, nbig, age;
+    int dsum;
+    int cnt;  // occupied modes + 65536 x modes with >= 4 particles
     int epk;  // high word of the largest E since the last re-summation (E >= 0: the high words order like the values)
     double bigS, bigE;  // cached sums over the generic bonds
     bool big_valid;
 };
 
-// byte address of mode m inside the thread's occupation bytes (ob = byte pointer to word 0 of this thread)
-__device__ __forceinline__ int fast_off(int m) { return (m >> 2) * (STEP_BLOCK * 4) + (m & 3); }
-// word offset (in uint32 units) of one-hot row `row`, word i, for this thread's column
-template <int NWM>
-__device__ __forceinline__ int oh_at(int row, int i) { return (row * NWM + i) * STEP_BLOCK; }
-// one-hot rows of the capped occupation s (0..4): A block 2, 3, 4, 5, 14; Q block 8, 9, 10, 11, 15.  sel = s | 0x7770:
-// byte s of the table into byte 0, a zero byte (byte 7 of the pair) into the others -- one PRMT each
-__device__ __forceinline__ uint32_t oh_row_a(uint32_t sel) { return __byte_perm(0x05040302u, (uint32_t)OH_A4, sel); }
-__device__ __forceinline__ uint32_t oh_row_q(uint32_t sel) { return __byte_perm(0x0B0A0908u, (uint32_t)OH_Q4, sel); }
-
-// 32-bit shared-window addressing for the step loop: one base register, every region at a compile-time offset
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldsu8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void stsu8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ double lds64f(uint32_t a) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ FastEntry lds_entry(uint32_t a) {
-    FastEntry e;
-    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(*reinterpret_cast<unsigned long long*>(&e.dE)), "=l"(e.dn) : "r"(a));
-    return e;
-}
-__device__ __forceinline__ void red_xor(uint32_t a, uint32_t v) { asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
 // sums / selection over the generic bonds (a neighbour with >= 4 particles), from the occupation bytes;
 // same order and arithmetic as PlanesBig::pass
 template <int NWM>
-__device__ __forceinline__ BigOut fast_big_pass(const uint32_t (&bigm)[NWM], const DevModel& dm, const unsigned char* ob,
-                                                const double* exptab, const double* sqrtab, int mode, double t) {
+__device__ __forceinline__ BigOut fast_big_pass(const uint32_t (&bigm)[NWM], const DevModel& dm, const FastScratch<NWM>& sc,
+                                                int mode, double t) {
+    using SC = FastScratch<NWM>;
+    const unsigned char* ob = sc.base + SC::OFF_ONR + 4u * threadIdx.x;
     BigOut o;
     o.S = o.E = o.ED = 0.0;
     o.d = 0;
@@ -212,12 +274,12 @@ __device__ __forceinline__ BigOut fast_big_pass(const uint32_t (&bigm)[NWM], con
             m &= m - 1;
             const int z = 32 * i + b;
             const int zn = (z + 1 == M) ? 0 : z + 1;
-            const int L = ob[fast_off(z)], R = ob[fast_off(zn)];
-            const double rr = (L > 0) ? exptab[(R - L + 1) + N] : 0.0;
-            const double rl = (R > 0) ? exptab[(L - R + 1) + N] : 0.0;
+            const int L = ob[SC::onr_off(z)], R = ob[SC::onr_off(zn)];
+            const double rr = (L > 0) ? sc.exptab[(R - L + 1) + N] : 0.0;
+            const double rl = (R > 0) ? sc.exptab[(L - R + 1) + N] : 0.0;
             if (mode == 0) {
-                const double er = sqrtab[L] * sqrtab[R + 1] * rr;
-                const double el = sqrtab[R] * sqrtab[L + 1] * rl;
+                const double er = sc.sqrtab[L] * sc.sqrtab[R + 1] * rr;
+                const double el = sc.sqrtab[R] * sc.sqrtab[L + 1] * rl;
                 o.S += rr;
                 o.S += rl;
                 o.E += er + el;
@@ -240,37 +302,37 @@ __device__ __forceinline__ BigOut fast_big_pass(const uint32_t (&bigm)[NWM], con
     return o;
 }
 
-// E re-summed from the one-hot rows (class counts by popcount), in the order of bond_sums (class id 4 l + r ascending)
+// E re-summed from the occupation bytes: the weights of the bonds 0, 1, ..., M-1 in this order
 template <int NWM>
-__device__ __forceinline__ double fast_resum_E(const FastScratch<NWM>& sc) {
-    const uint32_t* oh = sc.oh + threadIdx.x;
-    uint32_t A[4][NWM], Q[4][NWM];
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int i = 0; i < NWM; ++i) {
-            A[s][i] = oh[oh_at<NWM>(OH_A + s, i)];
-            Q[s][i] = oh[oh_at<NWM>(OH_Q + s, i)];
-        }
+__device__ __forceinline__ double fast_resum_E(uint32_t sb, int M) {
+    using SC = FastScratch<NWM>;
+    const uint32_t ob = sb + SC::OFF_ONR + 4u * threadIdx.x, fe = sb + SC::OFF_FE5;
     double E = 0.0;
-#pragma unroll
-    for (int l = 0; l < 4; ++l)
+    uint32_t first = 0u, prev = 0u;
+#pragma unroll 1
+    for (int q = 0; 4 * q < M; ++q) {
+        const uint32_t w = lds32(ob + (uint32_t)q * SC::ONR_STRIDE);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            if (l == 0 && r == 0) continue;
-            int c = 0;
-#pragma unroll
-            for (int i = 0; i < NWM; ++i) c += __popc(A[l][i] & Q[r][i]);
-            E = fma(int_to_double_fast(c), sc.FE[4 * l + r], E);
+            const int m = 4 * q + r;
+            if (m < M) {  // uniform
+                const uint32_t n = min(__byte_perm(w, 0u, 0x4440u + r), 4u);
+                if (m == 0)
+                    first = n;
+                else
+                    E += lds64f(prev + 8u * n);
+                prev = fe + 40u * n;  // row n of the weight table
+            }
         }
-    return E;
+    }
+    return E + lds64f(prev + 8u * first);
 }
 
 // (re)build the carried state of a walker from its planes
 template <int NWM, int NP>
 __device__ __forceinline__ void fast_init(const uint32_t (&p)[NP][NWM], const DevModel& dm, const FastScratch<NWM>& sc,
-                                          FastState& s) {
-    const int tid = threadIdx.x;
+                                          uint32_t sb, FastState& s) {
+    using SC = FastScratch<NWM>;
     uint32_t BIG[NWM];
     big_plane<NWM, NP>(p, BIG);
     // occupation bytes: planes 0 and 1 everywhere, the higher planes only where n >= 4
@@ -290,10 +352,9 @@ __device__ __forceinline__ void fast_init(const uint32_t (&p)[NP][NWM], const De
                 for (int k = 2; k < NP; ++k) n |= ((p[k][i] >> b) & 1u) << k;
                 word |= n << (8 * t);
             }
-            sc.onr[(8 * i + j) * STEP_BLOCK + tid] = word;
+            *sc.onr_word(8 * i + j) = word;
         }
-    // one-hot rows and their ring rotations
-    uint32_t* oh = sc.oh + tid;
+    // one-hot masks of the occupations and of the right neighbours' occupations
     uint32_t A[5][NWM], Q[5][NWM];
 #pragma unroll
     for (int i = 0; i < NWM; ++i) {
@@ -306,32 +367,38 @@ __device__ __forceinline__ void fast_init(const uint32_t (&p)[NP][NWM], const De
     }
 #pragma unroll
     for (int q = 0; q < 5; ++q) ring_next<NWM>(A[q], dm, Q[q]);
-#pragma unroll
-    for (int i = 0; i < NWM; ++i) {
-        oh[oh_at<NWM>(0, i)] = oh[oh_at<NWM>(1, i)] = oh[oh_at<NWM>(6, i)] = oh[oh_at<NWM>(7, i)] = 0u;
-        oh[oh_at<NWM>(12, i)] = oh[oh_at<NWM>(13, i)] = 0u;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            oh[oh_at<NWM>(OH_A + q, i)] = A[q][i];
-            oh[oh_at<NWM>(OH_Q + q, i)] = Q[q][i];
-        }
-        oh[oh_at<NWM>(OH_A4, i)] = A[4][i];
-        oh[oh_at<NWM>(OH_Q4, i)] = Q[4][i];
-    }
-    // hop counts per rate class, sum n (n - 1) / 2, occupied modes, modes with >= 4 particles
+    // hop masks: right hop of class g from l = 1..3 particles onto r = l + g - 3; left hop from r = 1..3 onto l = r + g - 3
     unsigned long long np = 0ull;
-    int n1 = 0, n2 = 0, n3 = 0, dbig = 0, nbig = 0;
 #pragma unroll
-    for (int l = 0; l < 4; ++l)
+    for (int g = 0; g < 6; ++g) {
+        int c = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int c = 0;
+        for (int i = 0; i < SC::NWV; ++i) {
+            uint32_t hr = 0u, hl = 0u;
+            if (i < NWM) {
 #pragma unroll
-            for (int i = 0; i < NWM; ++i) c += __popc(A[l][i] & Q[r][i]);
-            if (l >= 1) np += (unsigned long long)c << fast_field_pos(r - l + 3);
-            if (r >= 1) np += (unsigned long long)c << fast_field_pos(l - r + 3);
+                for (int l = 1; l < 4; ++l) {
+                    const int o = l + g - 3;
+                    if (o >= 0 && o < 4) {
+                        hr |= A[l][i < NWM ? i : 0] & Q[o][i < NWM ? i : 0];
+                        hl |= A[o][i < NWM ? i : 0] & Q[l][i < NWM ? i : 0];
+                    }
+                }
+            }
+            *sc.row_word(HM_R + g, i) = hr;
+            *sc.row_word(HM_L + g, i) = hl;
+            c += __popc(hr) + __popc(hl);
         }
-    const unsigned char* ob = reinterpret_cast<const unsigned char*>(sc.onr + tid);
+        np += (unsigned long long)c << fast_field_pos(g);
+    }
+#pragma unroll
+    for (int i = 0; i < SC::NWV; ++i) {
+        *sc.row_word(HM_DUMMY, i) = 0u;
+        *sc.row_word(HM_BIG, i) = i < NWM ? ((A[4][i < NWM ? i : 0] | Q[4][i < NWM ? i : 0]) & dm.mmask[i < NWM ? i : 0]) : 0u;
+    }
+    // sum n (n - 1) / 2, occupied modes, modes with >= 4 particles
+    int n1 = 0, n2 = 0, n3 = 0, dbig = 0, nbig = 0;
+    const unsigned char* ob = sc.base + SC::OFF_ONR + 4u * threadIdx.x;
 #pragma unroll
     for (int i = 0; i < NWM; ++i) {
         n1 += __popc(A[1][i]);
@@ -341,67 +408,118 @@ __device__ __forceinline__ void fast_init(const uint32_t (&p)[NP][NWM], const De
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            const int n = ob[fast_off(32 * i + b)];
+            const int n = ob[SC::onr_off(32 * i + b)];
             dbig += n * (n - 1) / 2;
             ++nbig;
         }
     }
     s.np = np;
     s.dsum = n2 + 3 * n3 + dbig;
-    s.nocc = n1 + n2 + n3 + nbig;
-    s.nbig = nbig;
-    s.E = fast_resum_E<NWM>(sc);
+    s.cnt = (n1 + n2 + n3 + nbig) + 65536 * nbig;
+    // E by class counts, in the order of bond_sums (class id 4 l + r ascending)
+    {
+        const double* FE5 = reinterpret_cast<const double*>(sc.base + SC::OFF_FE5);
+        double E = 0.0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (l == 0 && r == 0) continue;
+                int c = 0;
+#pragma unroll
+                for (int i = 0; i < NWM; ++i) c += __popc(A[l][i] & Q[r][i]);
+                E = fma(int_to_double_fast(c), FE5[5 * l + r], E);
+            }
+        s.E = E;
+    }
     s.epk = __double2hiint(s.E);
-    s.age = 0;
     s.bigS = s.bigE = 0.0;
-    s.big_valid = false;
+    s.big_valid = nbig == 0;
 }
 
-// the planes of the walker from its one-hot rows (n < 4) and occupation bytes (n >= 4)
+// the planes of the walker from its occupation bytes
 template <int NWM, int NP>
-__device__ __forceinline__ void fast_store_planes(const FastScratch<NWM>& sc, uint32_t (&p)[NP][NWM]) {
-    const uint32_t* oh = sc.oh + threadIdx.x;
-    const unsigned char* ob = reinterpret_cast<const unsigned char*>(sc.onr + threadIdx.x);
+__device__ __forceinline__ void fast_store_planes(const FastScratch<NWM>& sc, const FastState& s, uint32_t (&p)[NP][NWM]) {
+    const bool any_big = s.cnt > 0xFFFF;
 #pragma unroll
     for (int i = 0; i < NWM; ++i) {
-        const uint32_t a1 = oh[oh_at<NWM>(OH_A + 1, i)], a2 = oh[oh_at<NWM>(OH_A + 2, i)], a3 = oh[oh_at<NWM>(OH_A + 3, i)];
-        p[0][i] = a1 | a3;
-        p[1][i] = a2 | a3;
 #pragma unroll
-        for (int k = 2; k < NP; ++k) p[k][i] = 0u;
-        uint32_t m = oh[oh_at<NWM>(OH_A4, i)];
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t n = ob[fast_off(32 * i + b)];
+        for (int k = 0; k < NP; ++k) p[k][i] = 0u;
 #pragma unroll
-            for (int k = 0; k < NP; ++k) p[k][i] |= ((n >> k) & 1u) << b;
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t w = *sc.onr_word(8 * i + j);
+            // bit 0 (bit 1) of the four bytes gathered into a nibble
+            p[0][i] |= (((w & 0x01010101u) * 0x01020408u) >> 24) << (4 * j);
+            p[1][i] |= ((((w >> 1) & 0x01010101u) * 0x01020408u) >> 24) << (4 * j);
+            if (any_big && (w & 0xFCFCFCFCu)) {
+#pragma unroll
+                for (int k = 2; k < NP; ++k) p[k][i] |= ((((w >> k) & 0x01010101u) * 0x01020408u) >> 24) << (4 * j);
+            }
         }
     }
 }
 
+// j-th (0-based) set bit of x, j < popc(x) (nth_set_bit32_lut with the byte table addressed in the shared window)
+__device__ __forceinline__ int fast_nth_set_bit(uint32_t x, int j, uint32_t nth) {
+    uint32_t b = x - ((x >> 1) & 0x55555555u);
+    b = (b & 0x33333333u) + ((b >> 2) & 0x33333333u);
+    b = (b + (b >> 4)) & 0x0F0F0F0Fu;
+    const uint32_t pre = b * 0x01010100u;  // byte k = number of set bits below byte k
+    const uint32_t f = ((((uint32_t)j * 0x01010101u) | 0x80808080u) - pre) & 0x80808080u;  // byte k: j >= pre_k
+    const int sh = 8 * (__popc(f) - 1);
+    const uint32_t e = lds32(nth + 4u * ((x >> sh) & 0xFFu));
+    const int jj = j - (int)((pre >> sh) & 0xFFu);
+    return sh + (int)((e >> (4 * jj)) & 7u);
+}
+
+// hop-mask row at shared address a (this thread's column) into NWV registers
+template <int NWM>
+__device__ __forceinline__ void fast_load_row(uint32_t a, uint32_t* w) {
+    using SC = FastScratch<NWM>;
+#pragma unroll
+    for (int c = 0; c < SC::NCH; ++c) {
+        if (SC::VW == 1) w[c] = lds32(a + c * SC::CH_BYTES);
+        if (SC::VW == 2) lds64(a + c * SC::CH_BYTES, w[2 * c], w[2 * c + 1]);
+        if (SC::VW == 4) lds128(a + c * SC::CH_BYTES, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    }
+}
+
+// shared address of the occupation byte of mode m (ob = this thread's column): word m >> 2, byte m & 3
+template <int NWM>
+__device__ __forceinline__ uint32_t fast_onr_addr(uint32_t ob, int m) {
+    using SC = FastScratch<NWM>;
+    // (m >> 2) STRIDE + (m & 3) = m (STRIDE / 4) - (m & 3) (STRIDE / 4 - 1)
+    return ((uint32_t)m & 3u) * (1u - SC::ONR_STRIDE / 4u) + ((uint32_t)m * (SC::ONR_STRIDE / 4u) + ob);
+}
+// offset of the hop-mask word of bond z inside a row of this thread
+template <int NWM>
+__device__ __forceinline__ uint32_t fast_bond_off(int z) {
+    using SC = FastScratch<NWM>;
+    if (SC::NWV == 1) return 0u;
+    if (SC::NCH == 1) return ((uint32_t)z >> 3) & (4u * (SC::NWV - 1));  // 4 (z >> 5)
+    const uint32_t w = (uint32_t)z >> 5;
+    return (w / SC::VW) * SC::CH_BYTES + 4u * (w % SC::VW);
+}
+
 // one kinetic_sample! (qmc.jl:14-44).  hop_code: 2 z + (right ? 1 : 0) of the selected hop, -1 if none.
-// sb = shared-window address of the start of the dynamic shared memory (smem_addr(smem_raw)).
+// sb = shared-window address of the start of the dynamic shared memory (smem_addr(smem_raw)); 0 <= u01 < 1 - 2^-33;
+// refresh: re-sum E after this step (every FAST_REFRESH-th step of the walk).
 template <int NWM>
 __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, const FastRates& fr,
-                                          const FastScratch<NWM>& sc, uint32_t sb, double u01, double& tau, double& eloc,
-                                          double& gratio, int& nhops, int& hop_code) {
+                                          const FastScratch<NWM>& sc, uint32_t sb, double u01, bool refresh, double& tau,
+                                          double& eloc, double& gratio, int& nocc, int& hop_code) {
     using SC = FastScratch<NWM>;
-    const uint32_t st = sb + 4u * threadIdx.x;  // this thread's column in the [entry][thread] regions
-    const uint32_t oh = st + SC::OFF_OH;        // one-hot row r, word i: oh + (r NWM + i) 512
-    const uint32_t ob = st + SC::OFF_ONR;       // occupation byte of mode m: ob + (m >> 2) 512 + (m & 3)
+    constexpr int NWV = SC::NWV;
+    const uint32_t rows = sb + SC::OFF_ROWS + 4u * SC::VW * threadIdx.x;  // this thread's column of the hop-mask rows
+    const uint32_t ob = sb + SC::OFF_ONR + 4u * threadIdx.x;              // ... of the occupation bytes
 
     // ---- S and its running sums over the rate classes, from the integer hop counts ----
     const uint32_t nlo = (uint32_t)s.np, nhi = (uint32_t)(s.np >> 32);
     double c0, c1, c2, c3, c4, c5;
     {
-        const double magic = 4503599627370496.0;  // 2^52: (double)x for 0 <= x < 2^32 is hiloint2double(0x43300000, x) - 2^52
-        const double f0 = __hiloint2double(0x43300000, (int)(nlo & 0x3FFu)) - magic;
-        const double f1 = __hiloint2double(0x43300000, (int)(nlo & (0x3FFu << 10))) - magic;
-        const double f2 = __hiloint2double(0x43300000, (int)(nlo & (0x3FFu << 20))) - magic;
-        const double f3 = __hiloint2double(0x43300000, (int)(nhi & 0x3FFu)) - magic;
-        const double f4 = __hiloint2double(0x43300000, (int)(nhi & (0x3FFu << 10))) - magic;
-        const double f5 = __hiloint2double(0x43300000, (int)(nhi & (0x3FFu << 20))) - magic;
+        // the masked, unshifted fields (rs carries the 2^-position): one conversion each on the XU pipe
+        const double f0 = (double)(nlo & 0x3FFu), f1 = (double)(nlo & (0x3FFu << 10)), f2 = (double)(nlo & (0x3FFu << 20));
+        const double f3 = (double)(nhi & 0x3FFu), f4 = (double)(nhi & (0x3FFu << 10)), f5 = (double)(nhi & (0x3FFu << 20));
         c0 = f0 * fr.rs[0];
         c1 = fma(f1, fr.rs[1], c0);
         c2 = fma(f2, fr.rs[2], c1);
@@ -411,38 +529,28 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
     }
     const double reg_total = c5;
 
-    // ---- generic bonds: cached sums ----
-    uint32_t bigm[NWM];
+    // ---- generic bonds: cached sums (zero while no mode has >= 4 particles), re-evaluated after a hop touched one ----
+    if (!s.big_valid) {
+        uint32_t bw[NWV], bigm[NWM];
+        fast_load_row<NWM>(rows + HM_BIG * SC::ROW_BYTES, bw);
 #pragma unroll
-    for (int i = 0; i < NWM; ++i) bigm[i] = 0u;
-    double bigS = 0.0, bigE = 0.0;
-    const unsigned char* const obp = reinterpret_cast<const unsigned char*>(sc.onr + threadIdx.x);  // generic-bond path only
-    if (s.nbig) {
-#pragma unroll
-        for (int i = 0; i < NWM; ++i)
-            bigm[i] = (lds32(oh + (OH_A4 * NWM + i) * 512u) | lds32(oh + (OH_Q4 * NWM + i) * 512u)) & dm.mmask[i];
-        if (!s.big_valid) {
-            const BigOut o = fast_big_pass<NWM>(bigm, dm, obp, sc.exptab, sc.sqrtab, 0, 0.0);
-            s.bigS = o.S;
-            s.bigE = o.E;
-            s.big_valid = true;
-        }
-        bigS = s.bigS;
-        bigE = s.bigE;
+        for (int i = 0; i < NWM; ++i) bigm[i] = bw[i];
+        const BigOut o = fast_big_pass<NWM>(bigm, dm, sc, 0, 0.0);
+        s.bigS = o.S;
+        s.bigE = o.E;
+        s.big_valid = true;
     }
-    const double Stot = reg_total + bigS;
+    const double Stot = reg_total + s.bigS;
     const double D = dm.u * (double)s.dsum;
-    tau = 1.0 / Stot;
-    eloc = D - dm.t * (s.E + bigE);
+    tau = rcp_newton(Stot);
+    eloc = D - dm.t * (s.E + s.bigE);
     gratio = -D;
-    nhops = 2 * s.nocc;
-    double T = u01 * Stot;
-    if (!(T < Stot)) T = __longlong_as_double(__double_as_longlong(Stot) - 1);
+    nocc = s.cnt & 0xFFFF;
+    const double T = u01 * Stot;  // < Stot: u01 is at least 2^-33 below 1
 
     int z;
     bool right;
-    if (T < reg_total || !(bigS > 0.0)) {
-        if (!(T < reg_total)) T = __longlong_as_double(__double_as_longlong(reg_total) - 1);
+    if (T < reg_total) {
         // level 1: rate class g = number of running sums <= T
         int g = 0;
         double base = 0.0;
@@ -455,97 +563,93 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
         int j = (int)((T - base) * lds64f(sb + SC::OFF_IRATE + 8u * (uint32_t)g));
         j = max(0, min(j, ng - 1));
         // level 2: the j-th hop of the rate class in the order (right hops by position, left hops by position)
-        //   right hop from a mode with s particles (s = 1..3) to a neighbour with s + g - 3: A_s & Q_(s+g-3)
-        //   left hop from a neighbour with s particles onto a mode with s + g - 3:         A_(s+g-3) & Q_s
-        const uint32_t dyn = oh + (uint32_t)(g - 2) * SC::ROW_BYTES;  // + OH_Q rows: Q_(1+g-3); + OH_A rows: A_(1+g-3)
-        uint32_t mR[NWM], mL[NWM];
-        int nR = 0;
+        uint32_t W[2 * NWV];
+        const uint32_t ra = rows + (uint32_t)g * SC::ROW_BYTES;
+        fast_load_row<NWM>(ra + HM_R * SC::ROW_BYTES, W);
+        fast_load_row<NWM>(ra + HM_L * SC::ROW_BYTES, W + NWV);
+        uint32_t word = W[0];
+        int jb = j, zb = 0, pre = 0, nR = 0;
 #pragma unroll
-        for (int i = 0; i < NWM; ++i) {
-            const uint32_t a1 = lds32(oh + ((OH_A + 1) * NWM + i) * 512u), a2 = lds32(oh + ((OH_A + 2) * NWM + i) * 512u),
-                           a3 = lds32(oh + ((OH_A + 3) * NWM + i) * 512u);
-            const uint32_t q1 = lds32(oh + ((OH_Q + 1) * NWM + i) * 512u), q2 = lds32(oh + ((OH_Q + 2) * NWM + i) * 512u),
-                           q3 = lds32(oh + ((OH_Q + 3) * NWM + i) * 512u);
-            const uint32_t dq0 = lds32(dyn + ((OH_Q + 0) * NWM + i) * 512u), dq1 = lds32(dyn + ((OH_Q + 1) * NWM + i) * 512u),
-                           dq2 = lds32(dyn + ((OH_Q + 2) * NWM + i) * 512u);
-            const uint32_t da0 = lds32(dyn + ((OH_A + 0) * NWM + i) * 512u), da1 = lds32(dyn + ((OH_A + 1) * NWM + i) * 512u),
-                           da2 = lds32(dyn + ((OH_A + 2) * NWM + i) * 512u);
-            mR[i] = (a1 & dq0) | (a2 & dq1) | (a3 & dq2);
-            mL[i] = (q1 & da0) | (q2 & da1) | (q3 & da2);
-            nR += __popc(mR[i]);
+        for (int i = 0; i + 1 < 2 * NWV; ++i) {
+            pre += __popc(W[i]);
+            if (i + 1 == NWV) nR = pre;
+            if (j >= pre) {  // monotone in i: the last word whose prefix count is <= j holds the j-th hop
+                word = W[i + 1];
+                jb = j - pre;
+                zb = 32 * ((i + 1) % NWV);
+            }
         }
         right = j < nR;
-        int jb = right ? j : j - nR;
-        int pos = 0;
-        uint32_t word = right ? mR[NWM - 1] : mL[NWM - 1];
-        bool fnd = false;
-#pragma unroll
-        for (int i = 0; i < NWM; ++i) {
-            const uint32_t m = right ? mR[i] : mL[i];
-            const int pc = __popc(m);
-            const bool here = !fnd && (jb < pc);
-            word = here ? m : word;
-            pos = here ? 32 * i : pos;
-            fnd = fnd || here;
-            jb -= fnd ? 0 : pc;
-        }
-        if (!fnd) jb = max(0, __popc(word) - 1);  // cannot happen while np matches the masks
-        z = word ? pos + nth_set_bit32_lut(word, jb, sc.nth) : -1;
+        z = zb + fast_nth_set_bit(word, jb, sb + SC::OFF_NTH);
     } else {
-        const BigOut o = fast_big_pass<NWM>(bigm, dm, obp, sc.exptab, sc.sqrtab, 1, T - reg_total);
+        uint32_t bw[NWV], bigm[NWM];
+        fast_load_row<NWM>(rows + HM_BIG * SC::ROW_BYTES, bw);
+#pragma unroll
+        for (int i = 0; i < NWM; ++i) bigm[i] = bw[i];
+        const BigOut o = fast_big_pass<NWM>(bigm, dm, sc, 1, T - reg_total);
         z = o.z;
         right = o.right != 0;
+        if (z < 0) {  // cannot happen: T >= reg_total implies a generic bond with a hop
+            hop_code = -1;
+            return;
+        }
     }
-    hop_code = z < 0 ? -1 : 2 * z + (right ? 1 : 0);
-    if (z < 0) return;
+    hop_code = 2 * z + (right ? 1 : 0);
 
     // ---- the hop: bonds z-1 = (a, x), z = (x, y), z+1 = (y, b) ----
     const int M = dm.M;
     const int zn = (z + 1 == M) ? 0 : z + 1;
     const int zm = (z == 0) ? M - 1 : z - 1;
     const int zp = (zn + 1 == M) ? 0 : zn + 1;
-    const uint32_t az = ob + (uint32_t)fast_off(z), an = ob + (uint32_t)fast_off(zn);
-    const int a = (int)ldsu8(ob + (uint32_t)fast_off(zm)), x = (int)ldsu8(az), y = (int)ldsu8(an),
-              b = (int)ldsu8(ob + (uint32_t)fast_off(zp));
-    const int x2 = right ? x - 1 : x + 1, y2 = right ? y + 1 : y - 1;
+    const uint32_t az = fast_onr_addr<NWM>(ob, z), an = fast_onr_addr<NWM>(ob, zn);
+    const int a = (int)ldsu8(fast_onr_addr<NWM>(ob, zm)), x = (int)ldsu8(az), y = (int)ldsu8(an),
+              b = (int)ldsu8(fast_onr_addr<NWM>(ob, zp));
+    const int dxy = right ? -1 : 1;
+    const int x2 = x + dxy, y2 = y - dxy;
     stsu8(az, (uint32_t)x2);
     stsu8(an, (uint32_t)y2);
     const int a4 = min(a, 4), b4 = min(b, 4), x4 = min(x, 4), y4 = min(y, 4), x24 = min(x2, 4), y24 = min(y2, 4);
     const int ix = 2 * x4 + x24 + 1, iy = 2 * y4 + y24 + 1;  // 3 x4 + (x24 - x4 + 1)
-    const FastEntry eL = lds_entry(sb + SC::OFF_TL + 16u * (uint32_t)(a4 * 15 + ix)),
-                    eM = lds_entry(sb + SC::OFF_TM + 16u * (uint32_t)(ix * 15 + iy)),
-                    eR = lds_entry(sb + SC::OFF_TR + 16u * (uint32_t)(iy * 5 + b4));
-    s.E += (eL.dE + eM.dE) + eR.dE;
-    s.np += (eL.dn + eM.dn) + eR.dn;
-    const int nsrc = right ? x : y, ndst = right ? y : x;
-    s.dsum += ndst - nsrc + 1;
-    s.nocc += (int)(ndst == 0) - (int)(nsrc == 1);
-    s.nbig += (int)(x24 == 4) - (int)(x4 == 4) + (int)(y24 == 4) - (int)(y4 == 4);
-    // a mode with >= 4 particles in the window (before or after): the generic-bond sums change
-    if (max(max(a4, x4), max(max(y4, b4), max(x24, y24))) == 4) s.big_valid = false;
-    {  // one-hot rows: mode z leaves row x4 and enters x24 (A at bit z, Q at bit z-1), mode z+1 likewise (A: z+1, Q: z)
-        const uint32_t bz = 1u << (z & 31), bn = 1u << (zn & 31), bm = 1u << (zm & 31);
-        const uint32_t wz = oh + (uint32_t)(z >> 5) * 512u, wn = oh + (uint32_t)(zn >> 5) * 512u,
-                       wm = oh + (uint32_t)(zm >> 5) * 512u;
-        const uint32_t sx = (uint32_t)x4 | 0x7770u, sx2 = (uint32_t)x24 | 0x7770u, sy = (uint32_t)y4 | 0x7770u,
-                       sy2 = (uint32_t)y24 | 0x7770u;
-        red_xor(wz + oh_row_a(sx) * SC::ROW_BYTES, bz);
-        red_xor(wz + oh_row_a(sx2) * SC::ROW_BYTES, bz);
-        red_xor(wm + oh_row_q(sx) * SC::ROW_BYTES, bm);
-        red_xor(wm + oh_row_q(sx2) * SC::ROW_BYTES, bm);
-        red_xor(wn + oh_row_a(sy) * SC::ROW_BYTES, bn);
-        red_xor(wn + oh_row_a(sy2) * SC::ROW_BYTES, bn);
-        red_xor(wz + oh_row_q(sy) * SC::ROW_BYTES, bz);
-        red_xor(wz + oh_row_q(sy2) * SC::ROW_BYTES, bz);
+    const uint32_t il = (uint32_t)(a4 * 15 + ix), im = (uint32_t)(ix * 15 + iy), ir = (uint32_t)(iy * 5 + b4);
+    double eL, eM, eR;
+    unsigned long long nL, nM, nR2;
+    lds_entry_sums(sb + SC::OFF_TL + 16u * il, eL, nL);
+    lds_entry_sums(sb + SC::OFF_TM + 16u * im, eM, nM);
+    lds_entry_sums(sb + SC::OFF_TR + 16u * ir, eR, nR2);
+    const uint32_t rl = lds32(sb + SC::OFF_RL + 4u * il), rm = lds32(sb + SC::OFF_RM + 4u * im),
+                   rr = lds32(sb + SC::OFF_RR + 4u * ir);
+    s.E += (eL + eM) + eR;
+    s.np += (nL + nM) + nR2;
+    s.cnt += (int)lds32(sb + SC::OFF_TC + 4u * im);
+    s.dsum += (right ? y - x : x - y) + 1;  // n_dst - n_src + 1
+    {  // hop masks: each of the three bonds leaves two rows and enters two (absent hops go to the dummy row)
+        // 1 << (s & 31) as the high word of (1:0) << s (one funnel shift, the hardware wraps the shift amount)
+        const uint32_t bz = __funnelshift_l(0u, 1u, (uint32_t)z), bm = __funnelshift_l(0u, 1u, (uint32_t)zm),
+                       bn = __funnelshift_l(0u, 1u, (uint32_t)zn);
+        const uint32_t xm = rows + fast_bond_off<NWM>(zm), xz = rows + fast_bond_off<NWM>(z), xn = rows + fast_bond_off<NWM>(zn);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // byte q of the row words, zero-extended, times ROW_BYTES
+            red_xor(xm + __byte_perm(rl, 0u, 0x4440u + q) * SC::ROW_BYTES, bm);
+            red_xor(xz + __byte_perm(rm, 0u, 0x4440u + q) * SC::ROW_BYTES, bz);
+            red_xor(xn + __byte_perm(rr, 0u, 0x4440u + q) * SC::ROW_BYTES, bn);
+        }
+        // a mode with >= 4 particles in the window (before or after): the generic-bond sums and mask change
+        if (max(max(a4, x4), max(max(y4, b4), max(x24, y24))) == 4) {
+            s.big_valid = false;
+            const uint32_t big = HM_BIG * SC::ROW_BYTES;
+            if ((a4 == 4 || x4 == 4) != (a4 == 4 || x24 == 4)) red_xor(xm + big, bm);
+            if ((x4 == 4 || y4 == 4) != (x24 == 4 || y24 == 4)) red_xor(xz + big, bz);
+            if ((y4 == 4 || b4 == 4) != (y24 == 4 || b4 == 4)) red_xor(xn + big, bn);
+        }
     }
-    // rounding drift of the carried E: re-sum from the integers periodically, and as soon as E has fallen 16-fold
-    // below its largest value since the last re-summation (the rounding errors it carries scale with that peak)
+    // rounding drift of the carried E: re-sum from the occupations periodically (refresh: the caller's step counter,
+    // uniform over the CTA), and as soon as E has fallen 16-fold below its largest value since the last re-summation
+    // (the rounding errors it carries scale with that peak)
     const int ehi = __double2hiint(s.E);
     s.epk = max(s.epk, ehi);
-    if (++s.age >= FAST_REFRESH || ehi + (4 << 20) < s.epk) {
-        s.E = fast_resum_E<NWM>(sc);
+    if (refresh || ehi + (4 << 20) < s.epk) {
+        s.E = fast_resum_E<NWM>(sb, dm.M);
         s.epk = __double2hiint(s.E);
-        s.age = 0;
     }
 }
 

@@ -1,5 +1,5 @@
 // gwz_walker_fast.cu -- production walker kernel (round 2): kinetic_vqmc!(st; steps) (src/kinetic-vqmc/qmc.jl:73-97)
-// for every walker with the step of gwz_fast.cuh (integer hop counts per rate class, table-driven updates), the
+// for every walker with the step of gwz_fast.cuh (integer hop counts per rate class, hop masks, table-driven updates), the
 // running sums of state.jl:42-49 and per-block partial accumulator vectors.  Same contract and same resident HBM format
 // (occupation bit-planes) as walker_incr_kernel; its own u -> hop map (see gwz_fast.cuh) and its own use of the Philox
 // stream (one 32-bit word per step instead of 53 bits).
@@ -11,19 +11,15 @@
 #include "gwz_internal.h"
 #include "gwz_fast.cuh"
 
-#ifndef GWZ_FAST_MIN_BLOCKS
-#define GWZ_FAST_MIN_BLOCKS 6
-#endif
-
 namespace gwz {
 
 template <int NWM>
 __host__ __device__ constexpr size_t fast_smem_bytes(int N) {
-    return FastScratch<NWM>::bytes(N) + sizeof(double) * NUM_ACC * (STEP_BLOCK / 32);
+    return FastScratch<NWM>::bytes(N) + sizeof(double) * NUM_ACC * (fast_block(NWM) / 32);
 }
 
 template <int NWM, int NP, bool REC>
-__global__ void __launch_bounds__(STEP_BLOCK, NWM <= 2 ? GWZ_FAST_MIN_BLOCKS : (NWM <= 4 ? 4 : 2))
+__global__ void __launch_bounds__(fast_block(NWM), fast_min_blocks(NWM))
 walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ DevTables tb,
                    const __grid_constant__ FastRates fr, const __grid_constant__ PhiloxKeys pk,
                    uint32_t* __restrict__ planes, double* __restrict__ acc, size_t n, uint64_t global_offset, uint64_t step0,
@@ -32,7 +28,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                    double* __restrict__ rec_eloc, int32_t* __restrict__ rec_hop, const double* __restrict__ u01s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastScratch<NWM> sc(smem_raw, dm.N);
-    sc.fill_tables(dm.N, tb);
+    sc.fill_tables(dm.N, dm.M, tb);
     const uint32_t sb = smem_addr(smem_raw);
     // per-warp partial accumulator vectors (shared memory): every finished batch of 32 walkers is reduced by shuffles
     double(*psum)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(smem_raw + FastScratch<NWM>::bytes(dm.N));
@@ -57,7 +53,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                 for (int k = 0; k < NP; ++k)
 #pragma unroll
                     for (int i = 0; i < NWM; ++i) pl[k][i] = planes[((size_t)k * NWM + i) * n + w];
-                fast_init<NWM, NP>(pl, dm, sc, s);
+                fast_init<NWM, NP>(pl, dm, sc, sb, s);
             }
             double st, ste, stg, stge, stee;
             if (reset_acc || !accumulate) {
@@ -71,45 +67,55 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
             }
             const uint64_t wid = global_offset + (uint64_t)w;
             const uint32_t c2 = (uint32_t)wid, c3 = (uint32_t)(wid >> 32);
-            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
-            unsigned long long hops = 0ull;
-            double tcheck = 0.0;
+            unsigned long long occ = 0ull;  // sum over the steps of the number of occupied modes (= hops / 2)
+            const double st0 = st;
+            unsigned occ4 = 0u;
 
-            for (uint64_t k = 0; k < steps; ++k) {
-                // one Philox4x32-10 block (key = seed, counter = (step / 4, global walker id)) feeds four steps: the
-                // uniform of a step is one 32-bit word, u = word / 2^32
-                const uint64_t step = step0 + k;
-                const unsigned sub = (unsigned)step & 3u;
-                if (k == 0 || sub == 0u) {
-                    const uint64_t blk = step >> 2;
-                    philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
-                }
-                const uint32_t rw = sub == 0u ? rnd[0] : (sub == 1u ? rnd[1] : (sub == 2u ? rnd[2] : rnd[3]));
+            // one kinetic_sample! and its contribution to the running sums; rw = the 32-bit random word of the step
+            auto one_step = [&](uint64_t step, uint32_t rw) {
                 double u01 = (__hiloint2double(0x43300000, (int)rw) - 4503599627370496.0) * 0x1.0p-32;
-                if (REC && u01s) u01 = u01s[(size_t)k * n + w];
+                const size_t k = (size_t)(step - step0);
+                if (REC && u01s) u01 = fmin(u01s[k * n + w], 1.0 - 0x1.0p-32);
                 double tau, eloc, gr;
-                int nh, hop;
-                step_fast<NWM>(s, dm, fr, sc, sb, u01, tau, eloc, gr, nh, hop);
-                hops += (unsigned)nh;
+                int no, hop;
+                const bool refresh = ((unsigned)step & (FAST_REFRESH - 1)) == FAST_REFRESH - 1;
+                step_fast<NWM>(s, dm, fr, sc, sb, u01, refresh, tau, eloc, gr, no, hop);
+                occ4 += (unsigned)no;
                 if (REC) {
-                    if (rec_tau) __stcs(rec_tau + (size_t)k * n + w, tau);
-                    if (rec_eloc) __stcs(rec_eloc + (size_t)k * n + w, eloc);
-                    if (rec_hop) rec_hop[(size_t)k * n + w] = hop;
+                    if (rec_tau) __stcs(rec_tau + k * n + w, tau);
+                    if (rec_eloc) __stcs(rec_eloc + k * n + w, eloc);
+                    if (rec_hop) rec_hop[k * n + w] = hop;
                 }
                 const double dE = eloc - E0, dG = gr - G0;
                 const double tE = tau * dE;
-                tcheck += tau;
                 st += tau;
                 ste += tE;
                 stg = fma(tau, dG, stg);
                 stge = fma(tE, dG, stge);
                 stee = fma(tE, dE, stee);
+            };
+            // one Philox4x32-10 block (key = seed, counter = (step / 4, global walker id)) feeds four steps: the uniform
+            // of a step is one 32-bit word, u = word / 2^32.  A launch may start and end inside a block (guards uniform
+            // over the grid).  The four steps are NOT unrolled: four copies of the step body overflow the instruction
+            // cache (measured: 19 % fewer instructions issued per step, 3 - 30 % slower).
+            const uint64_t end = step0 + steps;
+            for (uint64_t blk = step0 >> 2; 4 * blk < end; ++blk) {
+                uint32_t rnd[4];
+                philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+                occ4 = 0u;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    const uint64_t step = 4 * blk + q;
+                    const uint32_t rw = q == 0 ? rnd[0] : (q == 1 ? rnd[1] : (q == 2 ? rnd[2] : rnd[3]));
+                    if (step >= step0 && step < end) one_step(step, rw);
+                }
+                occ += occ4;
             }
-            bad |= !(tcheck < 1.0e300);  // isfinite(residence_time) for every step (qmc.jl:34-36)
+            bad |= !(st - st0 < 1.0e300);  // isfinite(residence_time) for every step (qmc.jl:34-36)
 
             {
                 uint32_t pl[NP][NWM];
-                fast_store_planes<NWM, NP>(sc, pl);
+                fast_store_planes<NWM, NP>(sc, s, pl);
 #pragma unroll
                 for (int k = 0; k < NP; ++k)
 #pragma unroll
@@ -135,7 +141,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                 contrib[ACC_TG] = st * (G0 + mG);
                 contrib[ACC_TGE] = st * G0 * E0 + G0 * ste + E0 * stg + stge;
                 contrib[ACC_TEE] = st * E0 * E0 + 2.0 * E0 * ste + stee;
-                contrib[ACC_HOPS] = (double)hops;
+                contrib[ACC_HOPS] = 2.0 * (double)occ;
                 contrib[ACC_STEPS] = (double)steps;
                 contrib[ACC_VARW] = stee * inv - mE * mE;  // var(E_loc, weights tau), uncorrected
             }
@@ -156,7 +162,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
     if (threadIdx.x < NUM_ACC) {
         double v = 0.0;
 #pragma unroll
-        for (int q = 0; q < STEP_BLOCK / 32; ++q) v += psum[q][threadIdx.x];
+        for (int q = 0; q < fast_block(NWM) / 32; ++q) v += psum[q][threadIdx.x];
         partials[(size_t)blockIdx.x * NUM_ACC + threadIdx.x] = v;
     }
 }
@@ -176,11 +182,11 @@ static cudaError_t fast_launch(const WalkerLaunch& L, cudaStream_t s) {
     if (cudaError_t e = rec ? fast_prepare<NWM, NP, true>(L.dm.N) : fast_prepare<NWM, NP, false>(L.dm.N)) return e;
     const FastRates fr = fast_rates(L.tb.c);
     if (rec)
-        walker_fast_kernel<NWM, NP, true><<<L.grid, STEP_BLOCK, fast_smem_bytes<NWM>(L.dm.N), s>>>(
+        walker_fast_kernel<NWM, NP, true><<<L.grid, fast_block(NWM), fast_smem_bytes<NWM>(L.dm.N), s>>>(
             L.dm, L.tb, fr, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate,
             L.reset_acc, L.shift_e, L.shift_g, L.partials, L.err_flag, L.rec_tau, L.rec_eloc, L.rec_hop, L.u01s);
     else
-        walker_fast_kernel<NWM, NP, false><<<L.grid, STEP_BLOCK, fast_smem_bytes<NWM>(L.dm.N), s>>>(
+        walker_fast_kernel<NWM, NP, false><<<L.grid, fast_block(NWM), fast_smem_bytes<NWM>(L.dm.N), s>>>(
             L.dm, L.tb, fr, philox_keys(L.seed), L.planes, L.acc, L.n, L.global_offset, L.step0, L.steps, L.accumulate,
             L.reset_acc, L.accumulate ? L.shift_e : 0.0, L.accumulate ? L.shift_g : 0.0, L.partials, L.err_flag, nullptr,
             nullptr, nullptr, nullptr);
@@ -189,7 +195,7 @@ static cudaError_t fast_launch(const WalkerLaunch& L, cudaStream_t s) {
 template <int NWM, int NP>
 static cudaError_t fast_occ(int N, int* blocks) {
     if (cudaError_t e = fast_prepare<NWM, NP, false>(N)) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, walker_fast_kernel<NWM, NP, false>, STEP_BLOCK,
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, walker_fast_kernel<NWM, NP, false>, fast_block(NWM),
                                                          fast_smem_bytes<NWM>(N));
 }
 
@@ -243,7 +249,8 @@ cudaError_t walker_fast_grid(int N, int M, size_t n, int sm_count, int* grid) {
     if (cudaError_t e = fast_occ_dispatch(nwm, np, N, &blocks)) return e;
     if (blocks < 1) blocks = 1;
     const size_t resident = (size_t)blocks * (size_t)sm_count;
-    const size_t need = (n + STEP_BLOCK - 1) / STEP_BLOCK;
+    const size_t fb = (size_t)fast_block(nwm);
+    const size_t need = (n + fb - 1) / fb;
     *grid = (int)(need < resident ? need : resident);
     if (*grid < 1) *grid = 1;
     return cudaSuccess;
