@@ -240,6 +240,23 @@ __host__ inline FastRates fast_rates(double c) {
     return fr;
 }
 
+// shared-window addresses kept in registers for the whole kernel: made opaque to the compiler, which would otherwise
+// recompute them from the special registers several times per step
+struct FastAddr {
+    uint32_t sb;    // start of the dynamic shared memory
+    uint32_t tb;    // sb + 4 threadIdx.x:      this thread's column of the [word][thread] regions
+    uint32_t rows;  // sb + 4 VW threadIdx.x:   this thread's column of the hop-mask rows (+ OFF_ROWS)
+};
+template <int VW>
+__device__ __forceinline__ FastAddr fast_addr(const void* smem) {
+    FastAddr a;
+    a.sb = smem_addr(smem);
+    a.tb = a.sb + 4u * threadIdx.x;
+    a.rows = a.sb + 4u * VW * threadIdx.x;
+    asm volatile("" : "+r"(a.sb), "+r"(a.tb), "+r"(a.rows));
+    return a;
+}
+
 struct FastState {
     unsigned long long np;  // regular hops per rate class, 10-bit fields
     double E;
@@ -302,36 +319,45 @@ __device__ __forceinline__ BigOut fast_big_pass(const uint32_t (&bigm)[NWM], con
     return o;
 }
 
-// E re-summed from the occupation bytes: the weights of the bonds 0, 1, ..., M-1 in this order
+// E re-summed from the occupation bytes (the weights of the bonds M-1, 0, 1, ..., M-2 in this order)
 template <int NWM>
-__device__ __forceinline__ double fast_resum_E(uint32_t sb, int M) {
+__device__ __forceinline__ double fast_resum_E(uint32_t tb, int M) {
     using SC = FastScratch<NWM>;
-    const uint32_t ob = sb + SC::OFF_ONR + 4u * threadIdx.x, fe = sb + SC::OFF_FE5;
+    const uint32_t sb = tb - 4u * threadIdx.x;
+    const uint32_t ob = tb + SC::OFF_ONR, fe = sb + SC::OFF_FE5;
+    // E = sum over m of FE[n_(m-1)][n_m]: the bond (M-1, 0) first, then the bonds 0 .. M-2; full words without
+    // per-byte guards, then the last M & 3 modes
+    const int nfull = M >> 2, last = M - 1;
+    const uint32_t wl = lds32(ob + (uint32_t)(last >> 2) * SC::ONR_STRIDE);
+    uint32_t prev = fe + 40u * min((wl >> (8 * (last & 3))) & 0xFFu, 4u);  // row n of the weight table
     double E = 0.0;
-    uint32_t first = 0u, prev = 0u;
 #pragma unroll 1
-    for (int q = 0; 4 * q < M; ++q) {
+    for (int q = 0; q < nfull; ++q) {
         const uint32_t w = lds32(ob + (uint32_t)q * SC::ONR_STRIDE);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int m = 4 * q + r;
-            if (m < M) {  // uniform
-                const uint32_t n = min(__byte_perm(w, 0u, 0x4440u + r), 4u);
-                if (m == 0)
-                    first = n;
-                else
-                    E += lds64f(prev + 8u * n);
-                prev = fe + 40u * n;  // row n of the weight table
-            }
+            const uint32_t n = min(__byte_perm(w, 0u, 0x4440u + r), 4u);
+            E += lds64f(prev + 8u * n);
+            prev = fe + 40u * n;
         }
     }
-    return E + lds64f(prev + 8u * first);
+    if (M & 3) {
+        const uint32_t w = lds32(ob + (uint32_t)nfull * SC::ONR_STRIDE);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            if (r < (M & 3)) {
+                const uint32_t n = min(__byte_perm(w, 0u, 0x4440u + r), 4u);
+                E += lds64f(prev + 8u * n);
+                prev = fe + 40u * n;
+            }
+    }
+    return E;
 }
 
 // (re)build the carried state of a walker from its planes
 template <int NWM, int NP>
 __device__ __forceinline__ void fast_init(const uint32_t (&p)[NP][NWM], const DevModel& dm, const FastScratch<NWM>& sc,
-                                          uint32_t sb, FastState& s) {
+                                          uint32_t tb, FastState& s) {
     using SC = FastScratch<NWM>;
     uint32_t BIG[NWM];
     big_plane<NWM, NP>(p, BIG);
@@ -502,16 +528,17 @@ __device__ __forceinline__ uint32_t fast_bond_off(int z) {
 }
 
 // one kinetic_sample! (qmc.jl:14-44).  hop_code: 2 z + (right ? 1 : 0) of the selected hop, -1 if none.
-// sb = shared-window address of the start of the dynamic shared memory (smem_addr(smem_raw)); 0 <= u01 < 1 - 2^-33;
+// ad = shared-window addresses of the dynamic shared memory (fast_addr); 0 <= u01 < 1 - 2^-33;
 // refresh: re-sum E after this step (every FAST_REFRESH-th step of the walk).
 template <int NWM>
 __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, const FastRates& fr,
-                                          const FastScratch<NWM>& sc, uint32_t sb, double u01, bool refresh, double& tau,
+                                          const FastScratch<NWM>& sc, const FastAddr& ad, double u01, bool refresh, double& tau,
                                           double& eloc, double& gratio, int& nocc, int& hop_code) {
     using SC = FastScratch<NWM>;
     constexpr int NWV = SC::NWV;
-    const uint32_t rows = sb + SC::OFF_ROWS + 4u * SC::VW * threadIdx.x;  // this thread's column of the hop-mask rows
-    const uint32_t ob = sb + SC::OFF_ONR + 4u * threadIdx.x;              // ... of the occupation bytes
+    const uint32_t tb = ad.tb, sb = ad.sb;
+    const uint32_t rows = ad.rows + SC::OFF_ROWS;  // this thread's column of the hop-mask rows
+    const uint32_t ob = tb + SC::OFF_ONR;          // ... of the occupation bytes
 
     // ---- S and its running sums over the rate classes, from the integer hop counts ----
     const uint32_t nlo = (uint32_t)s.np, nhi = (uint32_t)(s.np >> 32);
@@ -648,7 +675,7 @@ __device__ __forceinline__ void step_fast(FastState& s, const DevModel& dm, cons
     const int ehi = __double2hiint(s.E);
     s.epk = max(s.epk, ehi);
     if (refresh || ehi + (4 << 20) < s.epk) {
-        s.E = fast_resum_E<NWM>(sb, dm.M);
+        s.E = fast_resum_E<NWM>(tb, dm.M);
         s.epk = __double2hiint(s.E);
     }
 }

@@ -29,7 +29,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastScratch<NWM> sc(smem_raw, dm.N);
     sc.fill_tables(dm.N, dm.M, tb);
-    const uint32_t sb = smem_addr(smem_raw);
+    const FastAddr ad = fast_addr<FastScratch<NWM>::VW>(smem_raw);
     // per-warp partial accumulator vectors (shared memory): every finished batch of 32 walkers is reduced by shuffles
     double(*psum)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(smem_raw + FastScratch<NWM>::bytes(dm.N));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -53,7 +53,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                 for (int k = 0; k < NP; ++k)
 #pragma unroll
                     for (int i = 0; i < NWM; ++i) pl[k][i] = planes[((size_t)k * NWM + i) * n + w];
-                fast_init<NWM, NP>(pl, dm, sc, sb, s);
+                fast_init<NWM, NP>(pl, dm, sc, ad.tb, s);
             }
             double st, ste, stg, stge, stee;
             if (reset_acc || !accumulate) {
@@ -73,13 +73,13 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
 
             // one kinetic_sample! and its contribution to the running sums; rw = the 32-bit random word of the step
             auto one_step = [&](uint64_t step, uint32_t rw) {
-                double u01 = (__hiloint2double(0x43300000, (int)rw) - 4503599627370496.0) * 0x1.0p-32;
+                double u01 = (double)rw * 0x1.0p-32;
                 const size_t k = (size_t)(step - step0);
                 if (REC && u01s) u01 = fmin(u01s[k * n + w], 1.0 - 0x1.0p-32);
                 double tau, eloc, gr;
                 int no, hop;
                 const bool refresh = ((unsigned)step & (FAST_REFRESH - 1)) == FAST_REFRESH - 1;
-                step_fast<NWM>(s, dm, fr, sc, sb, u01, refresh, tau, eloc, gr, no, hop);
+                step_fast<NWM>(s, dm, fr, sc, ad, u01, refresh, tau, eloc, gr, no, hop);
                 occ4 += (unsigned)no;
                 if (REC) {
                     if (rec_tau) __stcs(rec_tau + k * n + w, tau);
@@ -95,19 +95,31 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                 stee = fma(tE, dE, stee);
             };
             // one Philox4x32-10 block (key = seed, counter = (step / 4, global walker id)) feeds four steps: the uniform
-            // of a step is one 32-bit word, u = word / 2^32.  A launch may start and end inside a block (guards uniform
-            // over the grid).  The four steps are NOT unrolled: four copies of the step body overflow the instruction
-            // cache (measured: 19 % fewer instructions issued per step, 3 - 30 % slower).
+            // of a step is one 32-bit word, u = word / 2^32; the words are consumed by rotating the four registers.  A
+            // launch may start and end inside a block.  The four steps are NOT unrolled: four copies of the step body
+            // overflow the instruction cache (measured: 5 % fewer instructions per step, 3 - 30 % slower).
             const uint64_t end = step0 + steps;
-            for (uint64_t blk = step0 >> 2; 4 * blk < end; ++blk) {
+            uint64_t step = step0;
+            while (step < end) {
                 uint32_t rnd[4];
+                const uint64_t blk = step >> 2;
                 philox4x32_10_keyed((uint32_t)blk, (uint32_t)(blk >> 32), c2, c3, pk, rnd);
+                int q = (int)((unsigned)step & 3u);
+                const uint64_t left = end - step;
+                const int qe = left < (uint64_t)(4 - q) ? q + (int)left : 4;
+                for (int r = 0; r < q; ++r) {  // a launch that starts inside a block: skip the words already used
+                    rnd[0] = rnd[1];
+                    rnd[1] = rnd[2];
+                    rnd[2] = rnd[3];
+                }
                 occ4 = 0u;
 #pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    const uint64_t step = 4 * blk + q;
-                    const uint32_t rw = q == 0 ? rnd[0] : (q == 1 ? rnd[1] : (q == 2 ? rnd[2] : rnd[3]));
-                    if (step >= step0 && step < end) one_step(step, rw);
+                for (; q < qe; ++q) {
+                    one_step(step, rnd[0]);
+                    rnd[0] = rnd[1];
+                    rnd[1] = rnd[2];
+                    rnd[2] = rnd[3];
+                    ++step;
                 }
                 occ += occ4;
             }
