@@ -249,12 +249,14 @@ def run_ours(args):
     inst_per_step = prof.get("inst_per_walker_step")
     roofline = {"bound": "issue", "achieved": None, "peak": issue_peak / 1e9, "unit": "G warp-inst/s", "frac": None,
                 "traffic": None, "inst_per_walker_step": inst_per_step, "kernel_source_sha256": prof["sha"],
-                "profile": prof.get("profile"),
+                "profile": prof.get("profile"), "ncu_issue_active_pct": prof.get("ncu_issue_active_pct"),
+                "ncu_shared_pipe_pct": prof.get("ncu_shared_pipe_pct"),
                 "note": "the walker kernel is register / shared-memory resident: what binds it is instruction issue (4 "
                         "warp-instructions per SM and clock), not HBM (see hbm_roofline) and not tensor cores.  achieved = "
                         "walker-steps/s of the timed kernel / 32 x SASS instructions per walker-step; the instruction "
                         "count comes from the committed ncu capture of THIS kernel source (matched by hash; null when "
-                        "the source has changed since the capture)"}
+                        "the source has changed since the capture); ncu_* = issue-slot and shared-memory data-pipe "
+                        "utilisation of that capture (the second bound of this kernel)"}
     if inst_per_step:
         ach = steps_per_s_gpu / 32.0 * inst_per_step  # warp-instructions/s (32 walkers per warp)
         roofline.update(achieved=ach / 1e9, frac=ach / issue_peak)
@@ -318,8 +320,8 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
-KERNEL_NAME = ("walker_fast_kernel: integer hop counts per rate class, one-hot occupation masks in shared memory, "
-               "table-driven updates (GWZ_KERNEL_BITPARALLEL)")
+KERNEL_NAME = ("walker_fast_kernel: integer hop counts per rate class, hop masks per (rate class, direction) in shared "
+               "memory, table-driven updates (GWZ_KERNEL_BITPARALLEL)")
 KERNEL_SOURCES = ("gwz_device.cuh", "gwz_planes.cuh", "gwz_incr.cuh", "gwz_fast.cuh", "gwz_walker_fast.cu")
 
 

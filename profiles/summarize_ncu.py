@@ -33,6 +33,10 @@ KEYS = [
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__cycles_elapsed.avg",
+    # shared-memory data pipe: what bounds a kernel whose working set lives in shared memory
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
 ]
 print(f"# ncu summary of {rep}")
 print(f"kernel: {val.get('Kernel Name', '?')}")

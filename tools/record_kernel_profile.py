@@ -32,8 +32,10 @@ for key, summary, walkers in zip(args[0::3], args[1::3], args[2::3]):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     dram = float(rd.group(1)) * scale[rd.group(2)] + float(wr.group(1)) * scale[wr.group(2)]
     issue = float(re.search(r"smsp__issue_active.avg.pct_of_peak_sustained_active\s+([0-9.]+)", txt).group(1))
+    shp = re.search(r"l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed\s+([0-9.]+)", txt)
     d["entries"][key] = {"inst_per_walker_step": inst, "dram_bytes_per_walker": dram / float(walkers),
-                         "ncu_issue_active_pct": issue, "profile": summary}
+                         "ncu_issue_active_pct": issue, "ncu_shared_pipe_pct": float(shp.group(1)) if shp else None,
+                         "profile": summary}
 d["_note"] = ("written by tools/record_kernel_profile.py from `ncu --set full` captures; bench.py uses an entry only when "
               "source_sha256 equals the hash of the kernel sources it is timing (bench.kernel_source_hash)")
 json.dump(d, open(path, "w"), indent=1)
