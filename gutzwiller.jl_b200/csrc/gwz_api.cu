@@ -833,15 +833,18 @@ static int enqueue_blocking(gwz_walkers* w, uint64_t len, bool time_it) {
         w->bpartials_cap = grid;
     }
     if (!w->d_blk) GWZ_CUDA(cudaMalloc(&w->d_blk, sizeof(double) * 5 * w->n));
-    if (len > w->scratch_cap) {  // the resampled series pass through this buffer once (8 B per walker and slot)
+    // the resampled series pass through this buffer once: one row per resident thread of the kernel
+    const size_t scratch_rows = (size_t)grid * BLOCKING_BLOCK;
+    const size_t scratch_need = blocking_scratch_stride(len) * scratch_rows;
+    if (scratch_need > w->scratch_cap) {
         cudaFree(w->d_ser_v);
         w->d_ser_v = nullptr;
         w->scratch_cap = 0;
-        if (cudaMalloc(&w->d_ser_v, sizeof(double) * blocking_scratch_stride(len) * w->n) != cudaSuccess) {
+        if (cudaMalloc(&w->d_ser_v, sizeof(double) * scratch_need) != cudaSuccess) {
             cudaGetLastError();
-            return fail(GWZ_ERR_NOMEM, "blocking analysis: no device memory for the resampled series (8 B per walker and slot)");
+            return fail(GWZ_ERR_NOMEM, "blocking analysis: no device memory for the resampled-series scratch rows");
         }
-        w->scratch_cap = len;
+        w->scratch_cap = scratch_need;
     }
     BlockingLaunch L;
     L.tau = w->d_ser_tau;
@@ -855,6 +858,7 @@ static int enqueue_blocking(gwz_walkers* w, uint64_t len, bool time_it) {
     L.shift_e = w->shift_e;
     L.shift_g = w->shift_g;
     L.scratch = w->d_ser_v;
+    L.scratch_per_walker = false;
     L.out = w->d_blk;
     L.out_stride = w->n;
     L.partials = w->d_bpartials;
@@ -1229,6 +1233,7 @@ extern "C" int gwz_series_blocking(gwz_context* c, const double* tau, const doub
     L.acc_stride = 0;
     L.shift_e = L.shift_g = 0.0;
     L.scratch = d_scratch.p;
+    L.scratch_per_walker = true;
     L.out = d_out.p;
     L.out_stride = (size_t)n;
     L.partials = d_part.p;

@@ -117,7 +117,7 @@ struct gwz_walkers {
     double* d_ser_tau = nullptr;
     double* d_ser_eloc = nullptr;
     uint64_t ser_cap = 0, ser_steps = 0;
-    double* d_ser_v = nullptr;  // [scratch_cap][n] scratch of the blocking kernel (resampled series)
+    double* d_ser_v = nullptr;  // scratch_cap doubles: scratch rows of the blocking kernel (one per resident thread)
     uint64_t scratch_cap = 0;
     double* d_blk = nullptr;       // [5][n] per-walker blocking results of the last analysis
     double* d_bpartials = nullptr;  // [bgrid_cap][NUM_BACC]

@@ -162,7 +162,10 @@ struct BlockingLaunch {
     const double* acc;   // [NUM_WALKER_ACC][acc_stride] running sums of the same steps, or null
     size_t acc_stride;
     double shift_e, shift_g;
-    double* scratch;     // [n][blocking_scratch_stride(len)] walker-major: the resampled series pass through here once
+    double* scratch;     // rows of blocking_scratch_stride(len) doubles: the resampled series pass through here once.
+                         // One row per RESIDENT THREAD (grid x BLOCKING_BLOCK rows, reused from walker to walker: the
+                         // round trip stays in L2), or one per walker when the caller wants the resampled series back
+    bool scratch_per_walker;
     double* out;         // [5][out_stride]: mean, err, err_err, k, blocks per walker, or null
     size_t out_stride;
     double* partials;    // [grid][NUM_BACC]
