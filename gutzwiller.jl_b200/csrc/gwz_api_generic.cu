@@ -138,7 +138,7 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     }
     GWZ_CUDA(cudaMalloc(&a->d_pairs, sizeof(uint16_t) * pairs.size()));
     GWZ_CUDA(cudaMemcpy(a->d_pairs, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice));
-    const size_t npar = (size_t)M * M + 3 * (size_t)M;
+    const size_t npar = (size_t)M * M + 5 * (size_t)M + 2 * GEN_FAC_PAD;  // Qt, bvec, cR, cL, facX, facY
     GWZ_CUDA(cudaMalloc(&a->d_par, sizeof(double) * npar));
     GWZ_CUDA(cudaMallocHost(&a->h_par, sizeof(double) * npar));
     GenModel& gm = a->gm;
@@ -162,6 +162,8 @@ extern "C" int gwz_ansatz_create(gwz_model* m, int kind, int normalize, gwz_ansa
     gm.bvec = a->d_par + (size_t)M * M;
     gm.cR = gm.bvec + M;
     gm.cL = gm.cR + M;
+    gm.facX = gm.cL + M;
+    gm.facY = gm.facX + M + GEN_FAC_PAD;
     gm.logtab = a->d_static;
     gm.lgam = a->d_static + T;
     gm.sqrtab = a->d_static + 2 * T;
@@ -234,9 +236,12 @@ static int upload_params(gwz_ansatz* a, const double* p, GenModel* gm_out) {
     double* b = Q + (size_t)M * M;
     double* cR = b + M;
     double* cL = cR + M;
+    double* facX = cL + M;
+    double* facY = facX + M + GEN_FAC_PAD;
+    const size_t npar = (size_t)M * M + 5 * (size_t)M + 2 * GEN_FAC_PAD;
     // the previous upload from this staging buffer must have completed
     GWZ_CUDA(cudaStreamSynchronize(c->stream));
-    std::memset(Q, 0, sizeof(double) * ((size_t)M * M + 3 * (size_t)M));
+    std::memset(Q, 0, sizeof(double) * npar);
     double s = 0.0;
     auto ring = [&](double w) {  // w * (S + S^-1): sum_k n_k n_{k+1} = 1/2 n^T (S + S^-1) n
         for (int k = 0; k < M; ++k) {
@@ -295,10 +300,26 @@ static int upload_params(gwz_ansatz* a, const double* p, GenModel* gm_out) {
         cL[k] = 0.5 * Q[(size_t)l * M + l] + 0.5 * Q[(size_t)k * M + k] - Q[(size_t)k * M + l];
     }
     for (int k = 0; k < a->P; ++k) GWZ_REQUIRE(std::isfinite(p[k]), "parameters must be finite");
-    GWZ_CUDA(cudaMemcpyAsync(a->d_par, a->h_par, sizeof(double) * ((size_t)M * M + 3 * (size_t)M), cudaMemcpyHostToDevice,
-                             c->stream));
+    // translation-invariant couplings (Q[k][l] = q[(l - k) mod M] exactly, no multinomial term): the walker kernel
+    // carries the hop rates and multiplies them by exp(+-D2[distance to the hop]), D2 = second difference of q
+    bool circ = s == 0.0 && M >= 4;
+    for (int k = 1; k < M && circ; ++k)
+        for (int l = 0; l < M; ++l)
+            if (Q[(size_t)k * M + l] != Q[(size_t)((l - k + M) % M)]) {
+                circ = false;
+                break;
+            }
+    if (circ)
+        for (int i = 0; i < M + GEN_FAC_PAD; ++i) {  // entry i: distance (i - 1) mod M
+            const int x = (i - 1 + M) % M;
+            const double d2 = Q[(x + 1) % M] - 2.0 * Q[x] + Q[(x + M - 1) % M];
+            facX[i] = std::exp(d2);
+            facY[i] = std::exp(-d2);
+        }
+    GWZ_CUDA(cudaMemcpyAsync(a->d_par, a->h_par, sizeof(double) * npar, cudaMemcpyHostToDevice, c->stream));
     *gm_out = a->gm;
     gm_out->s = s;
+    gm_out->circ = circ ? 1 : 0;
     return GWZ_OK;
 }
 

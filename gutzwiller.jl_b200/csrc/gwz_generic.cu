@@ -156,7 +156,7 @@ gen_probe_kernel(const __grid_constant__ GenModel gm, const uint64_t* __restrict
 #endif
 // G lanes per walker (32 / G walkers per warp): lane gl of a group owns the modes [gl*MPL, (gl+1)*MPL) for the rates and
 // the parameters gl + G q; the groups of a warp advance in lockstep (same number of steps), each with its own walker.
-template <int G, int PPL, int MPL>
+template <int G, int PPL, int MPL, bool TI>
 __global__ void __launch_bounds__(GEN_BLOCK, PPL <= 2 ? GWZ_GEN_MIN_BLOCKS : (PPL == 4 ? 12 : 8))
 gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ PhiloxKeys pk, uint8_t* __restrict__ occ_g,
                   int Mpad, double* __restrict__ acc_g, size_t n, uint64_t goff, uint64_t step0, uint64_t steps,
@@ -165,8 +165,12 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                   int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GROUPS = 32 / G;  // walkers per warp (one warp per CTA)
-    const int lane = threadIdx.x & (G - 1), group = (threadIdx.x & 31) / G;
-    const GenWarp ws(smem_raw, G * MPL, group);  // compile-time slice layout: offsets fold into the LDS/STS immediates
+    int lane = threadIdx.x & (G - 1);
+    const int group = (threadIdx.x & 31) / G;
+    GenWarp ws(smem_raw, G * MPL, group);  // compile-time slice layout: offsets fold into the LDS/STS immediates
+    // keep the lane index and the slice pointers in registers: left alone, the compiler recomputes them from the special
+    // registers several times per step (50 of 436 instructions per walker-step, ncu source page r02m)
+    asm volatile("" : "+r"(lane), "+l"(ws.occ), "+l"(ws.V), "+l"(ws.rate));
     const size_t gwarp = (size_t)blockIdx.x * GROUPS + group, nwarps = (size_t)gridDim.x * GROUPS;
     const int M = gm.M, P = gm.P;
     const int AW = 3 + 2 * P;  // per-walker sums in HBM: st, stE, stEE, stG[P], stGE[P]
@@ -223,6 +227,28 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
         int nocc = 0;
         for (int k = lane; k < M; k += G) nocc += ws.occ[k] > 0;
         nocc = warp_sum_all<G>(nocc);
+        // translation-invariant couplings: exp(-e) of every hop out of this lane's modes, carried from step to step
+        double rR[MPL], rL[MPL], eR[MPL], eL[MPL], wR[MPL], wL[MPL];
+        unsigned occmask = 0u;
+        // RelativeJastrow: the occupations twice in a row (in the slice's unused rate array), so that n_(j+-d) needs no
+        // index wrap, and the part of gen_dfeature that does not depend on the hop (|i - j| = 1 on the ring)
+        int* o2 = reinterpret_cast<int*>(ws.rate);
+        const bool rj = TI && gm.kind == GEN_RELATIVE_JASTROW && M > 2;
+        int corr[PPL];
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+            const int p = lane + G * q;
+            corr[q] = 2 * (p == 0) - (p == 1) - (p == M - 1);
+        }
+        if (TI) {
+            for (int k = lane; k < 2 * M; k += G) o2[k] = ws.occ[k < M ? k : k - M];
+            gen_raw_rates<MPL>(gm, ws, lane, rR, rL);
+#pragma unroll
+            for (int q = 0; q < MPL; ++q) {
+                wR[q] = wL[q] = 0.0;
+                if (lane * MPL + q < M) gen_weight_ti<MPL>(gm, ws, lane, q, wR[q], wL[q], occmask);
+            }
+        }
 
         for (uint64_t k = 0; k < steps; ++k) {
             const uint64_t step = step0 + k;
@@ -234,6 +260,7 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                     const int p = lane + G * q;
                     if (p < P) F[q] = gen_feature(gm, ws, p, reg, ext, lgsum);
                 }
+                if (TI) gen_raw_rates<MPL>(gm, ws, lane, rR, rL);  // ... and of the multiplicatively carried rates
             }
             // one Philox block serves two steps; the G lanes of the walker evaluate G consecutive blocks at once
             // (lane l: block (blk & ~(G-1)) + l) and hand their words to the group when their step comes
@@ -248,7 +275,10 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             const double u01 = u01_from_words(wlo, whi);
             double S_lane, E_lane;
             int nocc_lane;
-            gen_rates<MPL, false>(gm, ws, lane, S_lane, E_lane, nocc_lane);
+            if (TI)
+                gen_rates_ti<MPL>(rR, rL, wR, wL, occmask, eR, eL, S_lane, E_lane);
+            else
+                gen_rates<MPL, false>(gm, ws, lane, S_lane, E_lane, nocc_lane);
             const double cum = warp_scan_incl<G>(S_lane, lane);
             const double S = __shfl_sync(0xffffffffu, cum, G - 1, G);
             const double Etot = warp_sum_all<G>(E_lane);
@@ -275,18 +305,28 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
             double T = u01 * S;
             if (!(T < S)) T = __longlong_as_double(__double_as_longlong(S) - 1);
             int src, right;
-            gen_select<MPL, G>(gm, ws, lane, S_lane, cum, T, src, right);
+            if (TI)
+                gen_select_ti<MPL, G>(lane, eR, eL, occmask, S_lane, cum, T, src, right);
+            else
+                gen_select<MPL, G>(gm, ws, lane, S_lane, cum, T, src, right);
             const int dst = right ? (src + 1 == M ? 0 : src + 1) : (src == 0 ? M - 1 : src - 1);
             nocc += (ws.occ[dst] == 0) - (ws.occ[src] == 1);  // occupied modes, carried exactly
 #pragma unroll
             for (int q = 0; q < PPL; ++q) {
                 const int p = lane + G * q;
-                if (p < P) F[q] += gen_dfeature(gm, ws, p, src, dst);
+                if (p < P) {
+                    if (rj)  // C_d(n') - C_d(n) = n_(j+d) + n_(j-d) - n_(i+d) - n_(i-d) + 2[d=0] - [d=1] - [d=M-1]
+                        F[q] += (double)(o2[dst + p] + o2[dst - p + M] - o2[src + p] - o2[src - p + M] + corr[q]);
+                    else
+                        F[q] += gen_dfeature(gm, ws, p, src, dst);
+                }
             }
             reg += ws.occ[dst] - ws.occ[src] + 1;
             ext += gen_dext(gm, ws, src, dst);
             __syncwarp();  // every lane has read the pre-hop occupations
-            {
+            if (TI) {  // the potential is only needed at the next re-evaluation, which rebuilds it
+                gen_rates_ti_hop<MPL>(gm, lane, src, right, rR, rL);
+            } else {
                 const double* qd = gm.Qt + (size_t)dst * M;
                 const double* qs = gm.Qt + (size_t)src * M;
 #pragma unroll
@@ -296,10 +336,29 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                 }
             }
             if (lane == 0) {
-                ws.occ[src] -= 1;
-                ws.occ[dst] += 1;
+                const int ns = ws.occ[src] - 1, nd = ws.occ[dst] + 1;
+                ws.occ[src] = ns;
+                ws.occ[dst] = nd;
+                if (TI) {
+                    o2[src] = o2[src + M] = ns;
+                    o2[dst] = o2[dst + M] = nd;
+                }
             }
             __syncwarp();
+            if (TI) {  // the weights of the four modes around the hop change: lo - 1 .. lo + 2, lo = the lower end of the bond
+                const int lo = right ? src : dst;  // (for the bond M-1 -> 0 the "lower" end is M-1)
+                int d0 = lane * MPL - lo + 1;      // distance of this lane's first mode from the window's first, mod M
+                d0 += d0 < 0 ? M : 0;
+                d0 -= d0 >= M ? M : 0;
+                if (d0 < 4 || d0 > M - MPL) {      // one or two lanes of the walker: a real branch, not predication
+#pragma unroll
+                    for (int q = 0; q < MPL; ++q) {
+                        int d = d0 + q;
+                        d -= d >= M ? M : 0;
+                        if (lane * MPL + q < M && d < 4) gen_weight_ti<MPL>(gm, ws, lane, q, wR[q], wL[q], occmask);
+                    }
+                }
+            }
         }
 
         if (live)
@@ -532,6 +591,12 @@ constexpr bool gen_walker_combo_used() {
     return MPL <= 4 || G == 32;  // groups narrower than the warp are only chosen with <= 4 modes per lane
 }
 
+// GWZ_GEN_TI=0: re-evaluate every rate with exp() per step also for translation-invariant couplings (A/B, tests)
+static bool gen_ti_disabled() {
+    const char* e = std::getenv("GWZ_GEN_TI");
+    return e && e[0] == '0';
+}
+
 struct GenWalkerOp {
     const GenWalkerLaunch* L;  // null: occupancy query
     const GenModel* gm;
@@ -540,16 +605,16 @@ struct GenWalkerOp {
     int* grid;
     cudaStream_t s;
 };
-template <int G, int PPL, int MPL>
+template <int G, int PPL, int MPL, bool TI>
 static cudaError_t gen_walker_do(const GenWalkerOp& op) {
     if constexpr (!gen_walker_combo_used<G, PPL, MPL>()) {
         return cudaErrorInvalidValue;
     } else {
         const size_t smem = (size_t)(32 / G) * GenWarp::bytes(G * MPL);  // one slice per walker of the warp
-        if (cudaError_t e = gen_prepare(gen_walker_kernel<G, PPL, MPL>, smem)) return e;
+        if (cudaError_t e = gen_prepare(gen_walker_kernel<G, PPL, MPL, TI>, smem)) return e;
         if (op.L == nullptr) {
             int per_sm = 0;
-            if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_walker_kernel<G, PPL, MPL>, GEN_BLOCK, smem))
+            if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gen_walker_kernel<G, PPL, MPL, TI>, GEN_BLOCK, smem))
                 return e;
             if (per_sm < 1) per_sm = 1;
             const size_t resident = (size_t)per_sm * op.sm_count;
@@ -559,7 +624,7 @@ static cudaError_t gen_walker_do(const GenWalkerOp& op) {
             return cudaSuccess;
         }
         const GenWalkerLaunch& L = *op.L;
-        gen_walker_kernel<G, PPL, MPL><<<L.grid, GEN_BLOCK, smem, op.s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n,
+        gen_walker_kernel<G, PPL, MPL, TI><<<L.grid, GEN_BLOCK, smem, op.s>>>(L.gm, philox_keys(L.seed), L.occ, L.Mpad, L.acc, L.n,
                                                                          L.global_offset, L.step0, L.steps, L.accumulate, L.reset_acc,
                                                                          L.shift, L.partials, L.rec_tau, L.rec_eloc, L.rec_addr,
                                                                          L.err_flag);
@@ -568,11 +633,12 @@ static cudaError_t gen_walker_do(const GenWalkerOp& op) {
 }
 template <int G, int PPL>
 static cudaError_t gen_walker_mpl(int mpl, const GenWalkerOp& op) {
+    const bool ti = op.gm->circ != 0 && op.gm->M >= 4 && !gen_ti_disabled();
     switch (mpl) {
-        case 1: return gen_walker_do<G, PPL, 1>(op);
-        case 2: return gen_walker_do<G, PPL, 2>(op);
-        case 4: return gen_walker_do<G, PPL, 4>(op);
-        case 8: return gen_walker_do<G, PPL, 8>(op);
+        case 1: return ti ? gen_walker_do<G, PPL, 1, true>(op) : gen_walker_do<G, PPL, 1, false>(op);
+        case 2: return ti ? gen_walker_do<G, PPL, 2, true>(op) : gen_walker_do<G, PPL, 2, false>(op);
+        case 4: return ti ? gen_walker_do<G, PPL, 4, true>(op) : gen_walker_do<G, PPL, 4, false>(op);
+        case 8: return ti ? gen_walker_do<G, PPL, 8, true>(op) : gen_walker_do<G, PPL, 8, false>(op);
         default: return cudaErrorInvalidValue;
     }
 }

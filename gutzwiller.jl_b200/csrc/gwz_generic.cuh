@@ -58,7 +58,15 @@ struct GenModel {
     const double* sqrtab;  // [N+2]
     const uint16_t* pair_i;  // [P] Jastrow pair (i <= j) of parameter p (jastrow.jl:34-40 order)
     const uint16_t* pair_j;
+    // translation-invariant couplings (Q circulant, s = 0: every ansatz but Multinomial and Jastrow): a hop changes
+    // EVERY exponent, but by an amount that depends only on the distance to the hop -- facX[a] = exp(+D2[a]),
+    // facY[a] = exp(-D2[a]), D2 = second difference of the first row of Q (see gen_rates_ti)
+    int circ;
+    int pad_;
+    const double* facX;  // [M + GEN_FAC_PAD]: facX[i] = exp(+D2[(i - 1) mod M]) (one entry of wrap-around in front, the
+    const double* facY;  //                      rest behind: the modes of a lane read consecutive entries, no index wrap)
 };
+constexpr int GEN_FAC_PAD = 16;
 
 // CombinationAnsatz (src/ansatz/combination.jl): psi = alpha psi_1 + (1 - alpha) psi_2 with two log-linear components;
 // parameters (p_1..., p_2..., alpha).  Kernels: gwz_generic_combo.cu.
@@ -322,6 +330,104 @@ __device__ __forceinline__ void gen_rates(const GenModel& gm, const GenWarp& ws,
     S_lane = S;
     E_lane = E;
     nocc_lane = nocc;
+}
+
+// ---- translation-invariant couplings: hop rates carried from step to step ----------------------------------------
+// exp(-e) of both hops out of EVERY mode this lane owns (occupied or not), from the potential V
+template <int MPL>
+__device__ __forceinline__ void gen_raw_rates(const GenModel& gm, const GenWarp& ws, int lane, double (&rR)[MPL],
+                                              double (&rL)[MPL]) {
+    const int M = gm.M;
+#pragma unroll
+    for (int q = 0; q < MPL; ++q) {
+        const int k = lane * MPL + q;
+        rR[q] = rL[q] = 0.0;
+        if (k < M) {
+            const int kr = k + 1 == M ? 0 : k + 1, kl = k == 0 ? M - 1 : k - 1;
+            const double vk = ws.V[k];
+            rR[q] = exp(-(ws.V[kr] - vk + gm.cR[k]));  // the arithmetic of gen_rates
+            rL[q] = exp(-(ws.V[kl] - vk + gm.cL[k]));
+        }
+    }
+}
+// matrix-element weights sqrt(n_k (n_kr + 1)), sqrt(n_k (n_kl + 1)) of the hops out of mode k = lane MPL + q (the products
+// gen_rates forms first) and the occupied bit of the mode
+template <int MPL>
+__device__ __forceinline__ void gen_weight_ti(const GenModel& gm, const GenWarp& ws, int lane, int q, double& wR, double& wL,
+                                              unsigned& occmask) {
+    const int M = gm.M, k = lane * MPL + q;
+    const int n = ws.occ[k];
+    const int kr = k + 1 == M ? 0 : k + 1, kl = k == 0 ? M - 1 : k - 1;
+    const double sn = gm.sqrtab[n];
+    wR = sn * gm.sqrtab[ws.occ[kr] + 1];
+    wL = sn * gm.sqrtab[ws.occ[kl] + 1];
+    occmask = (occmask & ~(1u << q)) | ((n > 0 ? 1u : 0u) << q);
+}
+// the sums of gen_rates from the carried rates and weights (same order of additions and products); eR / eL: the rates of
+// the existing hops
+template <int MPL>
+__device__ __forceinline__ void gen_rates_ti(const double (&rR)[MPL], const double (&rL)[MPL], const double (&wR)[MPL],
+                                             const double (&wL)[MPL], unsigned occmask, double (&eR)[MPL], double (&eL)[MPL],
+                                             double& S_lane, double& E_lane) {
+    double S = 0.0, E = 0.0;
+#pragma unroll
+    for (int q = 0; q < MPL; ++q) {
+        const bool ex = (occmask >> q) & 1u;
+        eR[q] = ex ? rR[q] : 0.0;
+        eL[q] = ex ? rL[q] : 0.0;
+        S += eR[q];
+        S += eL[q];
+        E += wR[q] * eR[q];
+        E += wL[q] * eL[q];
+    }
+    S_lane = S;
+    E_lane = E;
+}
+// the hop src -> src +- 1 multiplies the rates out of mode k by factors that depend on a = k - src (mod M) only:
+// right hop done: e_R(k) -= D2[a], e_L(k) += D2[a-1];  left hop done: e_R(k) += D2[a+1], e_L(k) -= D2[a]
+template <int MPL>
+__device__ __forceinline__ void gen_rates_ti_hop(const GenModel& gm, int lane, int src, int right, double (&rR)[MPL],
+                                                 double (&rL)[MPL]) {
+    const int M = gm.M;
+    int a0 = lane * MPL - src;  // distance of this lane's first mode, in [0, M)
+    a0 += a0 < 0 ? M : 0;
+    // table entry i + 1 holds the factor of distance i: X[a], Y[a-1] after a right hop; Y[a+1], X[a] after a left hop
+    const double* pR = (right ? gm.facX + 1 : gm.facY + 2) + a0;
+    const double* pL = (right ? gm.facY : gm.facX + 1) + a0;
+#pragma unroll
+    for (int q = 0; q < MPL; ++q) {
+        if (lane * MPL + q < M) {
+            rR[q] *= __ldg(pR + q);
+            rL[q] *= __ldg(pL + q);
+        }
+    }
+}
+// gen_select over the carried rates (registers instead of the shared-memory rate array): the running sum of
+// gen_select (same additions in the same order; absent hops add 0), the hop = the number of running sums <= T
+template <int MPL, int G = 32>
+__device__ __forceinline__ void gen_select_ti(int lane, const double (&eR)[MPL], const double (&eL)[MPL], unsigned occmask,
+                                              double S_lane, double cum_incl, double T, int& src, int& right) {
+    unsigned hit = __ballot_sync(0xffffffffu, (T < cum_incl) && (S_lane > 0.0));
+    unsigned live = __ballot_sync(0xffffffffu, S_lane > 0.0);
+    if (G < 32) {  // this group's share of the ballots
+        const int shift = (int)(threadIdx.x & 31u & ~(unsigned)(G - 1));
+        hit = (hit >> shift) & ((1u << (G & 31)) - 1u);
+        live = (live >> shift) & ((1u << (G & 31)) - 1u);
+    }
+    const int sel_lane = hit ? (__ffs(hit) - 1) : (31 - __clz(live));  // clamp as gen_select
+    double acc = cum_incl - S_lane;
+    int h = 0;
+#pragma unroll
+    for (int q = 0; q < MPL; ++q) {
+        acc += eR[q];
+        h += !(T < acc);
+        acc += eL[q];
+        h += !(T < acc);
+    }
+    // rounding left T at or above every running sum: the last hop of this lane (left hop of its last occupied mode)
+    if (h >= 2 * MPL) h = 2 * (31 - __clz(occmask | 1u)) + 1;
+    src = __shfl_sync(0xffffffffu, lane * MPL + (h >> 1), sel_lane, G);
+    right = __shfl_sync(0xffffffffu, (h & 1) ^ 1, sel_lane, G);
 }
 
 // pick_random_from_cumsum (qmc.jl:52-61) over the hops in reference order: first hop whose inclusive
