@@ -333,6 +333,11 @@ sparse_walker_kernel(const __grid_constant__ SparseDev sd, const __grid_constant
                 bad = true;
                 break;
             }
+            if (BLK) {  // the move is known: start the next state's row block on its way (one 128-byte line per lane)
+                const double* nb = sd.blk + (size_t)o.next * sd.BS;
+                if (lane * 16 < sd.BS && lane * 16 < SP_HEAD + SP_R * sp_chunk_doubles(G))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + lane * 16));
+            }
             if (lane == 0) {
                 if (rec_tau) {
                     rec_tau[s * n + w] = o.tau;
