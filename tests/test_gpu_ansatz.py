@@ -360,3 +360,29 @@ def test_generic_sweep_representative_basis(gw, cls, N, M, v, monkeypatch):
     a, b = le.val_and_grad(q), ref.val_and_grad(q)
     assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and np.allclose(a[1], b[1], rtol=1e-10, atol=1e-12 * max(1.0, np.abs(b[1]).max()))
     assert abs(le(q) - b[0]) <= 1e-12 * abs(b[0])
+
+
+@pytest.mark.parametrize("cls,N,M,v", [("RelativeJastrowAnsatz", 50, 50, 0.0), ("ExtendedGutzwillerAnsatz", 30, 24, 0.0),
+                                       ("DensityProfileAnsatz", 20, 33, 0.0), ("GenericGutzwillerAnsatz", 24, 24, 0.4)])
+def test_carried_hop_rates_follow_the_re_evaluated_ones(gw, cls, N, M, v, monkeypatch):
+    """Translation-invariant couplings: the walker kernel carries exp(-e) of every hop and multiplies it by tabulated
+    factors (gwz_generic.cuh: gen_rates_ti_hop), re-evaluating with exp() every GEN_REFRESH = 256 steps.  Against the
+    kernel that evaluates every rate with exp() in every step (GWZ_GEN_TI=0; the one the oracle tests pin): same
+    trajectories over several re-evaluation periods, residence times and local energies within 1e-12."""
+    addr = gw.near_uniform(N, M)
+    H = gw.ExtendedHubbardReal1D(addr, u=2.0, v=v) if v else gw.HubbardReal1D(addr, u=2.0)
+    ans = getattr(gw, cls)(H)
+    rng = np.random.default_rng(3)
+    p = 0.02 * rng.random(ans.N_PARAMS)
+    p[0] = 0.4
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("GWZ_GEN_TI", flag)
+        w = gw.GenWalkers(ans.handle(), 40, H.address.words, seed=77, global_offset=3)
+        r, tau, eloc, a = w.run_record(p, 700)
+        out[flag] = (tau, eloc, a, w.addresses(), r.val)
+    (t1, e1, a1, f1, v1), (t0, e0, a0, f0, v0) = out["1"], out["0"]
+    assert np.array_equal(a1, a0) and np.array_equal(f1, f0)
+    assert np.all(np.abs(t1 - t0) <= 1e-12 * np.abs(t0))
+    assert np.all(np.abs(e1 - e0) <= 1e-12 * np.maximum(np.abs(e0), 1.0))
+    assert abs(v1 - v0) <= 1e-12 * abs(v0)

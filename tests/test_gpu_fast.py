@@ -126,3 +126,30 @@ def test_fast_and_incremental_kernels_sample_the_same_distribution(gw, monkeypat
     (v1, e1, g1, ge1), (v0, e0, g0, ge0) = vals["1"], vals["0"]
     assert abs(v1 - v0) < 4.5 * np.hypot(e1, e0) and abs(g1 - g0) < 4.5 * np.hypot(ge1, ge0)
     assert abs(v1 - exact) < 4.5 * e1 and abs(g1 - grad[0]) < 4.5 * ge1
+
+
+@pytest.mark.parametrize("N,M,u,g", [(50, 50, 2.0, 1.0), (50, 50, 2.0, 0.33), (24, 24, 6.0, 1.2)])
+def test_carried_local_energy_does_not_drift_over_long_runs(gw, oracle_mod, N, M, u, g):
+    """E (the off-diagonal part of E_loc) is carried by table deltas and re-summed every FAST_REFRESH = 64 steps or when
+    it has fallen 16-fold below its peak (gwz_fast.cuh): after thousands of steps every recorded E_loc and residence
+    time still equals the oracle's re-evaluation of the address at 1e-12."""
+    o = oracle_mod.Oracle(N, M, u, 1.0)
+    model = gw.Model(N, M, u, 1.0)
+    start = o.near_uniform()
+    nw, steps = 8, 3000
+    w = gw.Walkers(model, nw, start[: o.W], seed=5)
+    _, tau, eloc, hop = w.run_trace([g], steps)
+    onr0 = np.array(o.to_onr(start))
+    for k in range(nw):
+        onr = onr0.copy()
+        for s in range(steps):
+            if s % 61 == 0 or s >= steps - 3:  # every phase of the refresh period, and the end of the run
+                addr = o.from_onr(onr)
+                D = o.diagonal_element(addr)
+                if g * D <= 600:
+                    ks = o.kinetic_sample(addr, g, 0.5)
+                    assert abs(tau[s, k] - ks["tau"]) <= RTOL * ks["tau"], (k, s)
+                    scale = max(abs(ks["eloc"]), D, abs(ks["eloc"] - D))
+                    assert abs(eloc[s, k] - ks["eloc"]) <= RTOL * scale + 1e-12, (k, s)
+            _apply(onr, int(hop[s, k]))
+        assert np.array_equal(o.from_onr(onr)[: o.W], w.addresses()[k]), k
