@@ -72,13 +72,13 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
             unsigned occ4 = 0u;
 
             // one kinetic_sample! and its contribution to the running sums; rw = the 32-bit random word of the step
-            auto one_step = [&](uint64_t step, uint32_t rw) {
+            auto one_step = [&](uint64_t step, unsigned step32, uint32_t rw) {
                 double u01 = (double)rw * 0x1.0p-32;
-                const size_t k = (size_t)(step - step0);
+                const size_t k = (size_t)(step - step0);  // recording instantiation only
                 if (REC && u01s) u01 = fmin(u01s[k * n + w], 1.0 - 0x1.0p-32);
                 double tau, eloc, gr;
                 int no, hop;
-                const bool refresh = ((unsigned)step & (FAST_REFRESH - 1)) == FAST_REFRESH - 1;
+                const bool refresh = (step32 & (FAST_REFRESH - 1)) == FAST_REFRESH - 1;
                 step_fast<NWM>(s, dm, fr, sc, ad, u01, refresh, tau, eloc, gr, no, hop);
                 occ4 += (unsigned)no;
                 if (REC) {
@@ -107,20 +107,23 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                 int q = (int)((unsigned)step & 3u);
                 const uint64_t left = end - step;
                 const int qe = left < (uint64_t)(4 - q) ? q + (int)left : 4;
+#pragma unroll 1
                 for (int r = 0; r < q; ++r) {  // a launch that starts inside a block: skip the words already used
                     rnd[0] = rnd[1];
                     rnd[1] = rnd[2];
                     rnd[2] = rnd[3];
                 }
                 occ4 = 0u;
+                const int nq = qe - q;
+                const unsigned s32 = (unsigned)step;
 #pragma unroll 1
-                for (; q < qe; ++q) {
-                    one_step(step, rnd[0]);
+                for (int r = 0; r < nq; ++r) {
+                    one_step(step + (unsigned)r, s32 + (unsigned)r, rnd[0]);
                     rnd[0] = rnd[1];
                     rnd[1] = rnd[2];
                     rnd[2] = rnd[3];
-                    ++step;
                 }
+                step += (unsigned)nq;
                 occ += occ4;
             }
             bad |= !(st - st0 < 1.0e300);  // isfinite(residence_time) for every step (qmc.jl:34-36)
