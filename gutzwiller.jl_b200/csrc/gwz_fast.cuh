@@ -118,7 +118,6 @@ struct FastScratch {
     static constexpr uint32_t ROW_BYTES = CH_BYTES * NCH;
     static constexpr int ONR_WORDS = 8 * NWM;                 // occupation bytes, 4 modes per word: [word][thread]
     static constexpr uint32_t ONR_STRIDE = 4u * FB;
-    static constexpr int MMAX = 32 * NWM;
     static constexpr int NTL = 5 * 15, NTM = 15 * 15, NTR = 15 * 5;
     // byte offsets from the start of the dynamic shared memory (step_fast addresses everything as base + constant)
     static constexpr uint32_t OFF_TL = 0,                        // [a4][ix]   bond z-1: (a, x) -> (a, x')
@@ -186,7 +185,7 @@ struct FastScratch {
         rows = (uint32_t)b.rR | ((uint32_t)b.rL << 8) | ((uint32_t)a.rR << 16) | ((uint32_t)a.rL << 24);
         return e;
     }
-    __device__ __forceinline__ void fill_tables(int N, int M, const DevTables& tb) const {
+    __device__ __forceinline__ void fill_tables(int N, const DevTables& tb) const {
         FastEntry* TL = reinterpret_cast<FastEntry*>(base + OFF_TL);
         FastEntry* TM = reinterpret_cast<FastEntry*>(base + OFF_TM);
         FastEntry* TR = reinterpret_cast<FastEntry*>(base + OFF_TR);

@@ -28,7 +28,7 @@ walker_fast_kernel(const __grid_constant__ DevModel dm, const __grid_constant__ 
                    double* __restrict__ rec_eloc, int32_t* __restrict__ rec_hop, const double* __restrict__ u01s) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FastScratch<NWM> sc(smem_raw, dm.N);
-    sc.fill_tables(dm.N, dm.M, tb);
+    sc.fill_tables(dm.N, tb);
     const FastAddr ad = fast_addr<FastScratch<NWM>::VW>(smem_raw);
     // per-warp partial accumulator vectors (shared memory): every finished batch of 32 walkers is reduced by shuffles
     double(*psum)[NUM_ACC] = reinterpret_cast<double(*)[NUM_ACC]>(smem_raw + FastScratch<NWM>::bytes(dm.N));
