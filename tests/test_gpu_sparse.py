@@ -378,3 +378,45 @@ def test_argument_checks(gw, ops):
     # the error is reported once; the next run on the same context is clean
     ok = gw.SparseVectorAnsatz(H, np.ones(H.dim))
     assert np.isfinite(gw.SparseWalkers(H.handle(), ok, 8, 0, seed=1).run([], 10).val)
+
+
+def test_amsgrad_on_one_parameter_stored_operator_objectives(gw):
+    """a 1-parameter stored-operator objective must not take the in-library fast path of the bit-level
+    engine (its handles are gwz_swalkers / gwz_sparse, not gwz_walkers / gwz_sweep).  Both objectives descend through
+    the callback path and find the optimum the bit-level evaluator finds."""
+    H = gw.HubbardReal1D(gw.near_uniform(6, 6), u=4.0)
+    Hs = gw.SparseHamiltonian.from_hubbard(H)
+    le_bits = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H))
+    ref = gw.amsgrad(le_bits, [0.5], maxiter=200)
+    le_rows = gw.LocalEnergyEvaluator(Hs, gw.SparseGutzwillerAnsatz(Hs))
+    out = gw.amsgrad(le_rows, [0.5], maxiter=200)
+    assert abs(out.param[-1][0] - ref.param[-1][0]) < 1e-6 and abs(out.value[-1] - ref.value[-1]) < 1e-9
+    qmc = gw.KineticVQMC(Hs, gw.SparseGutzwillerAnsatz(Hs), samples=2e6, walkers=4096, burn_in=50)
+    outq = gw.amsgrad(qmc, [0.5], maxiter=40)
+    assert np.isfinite(outq.value[-1]) and abs(outq.param[-1][0] - ref.param[-1][0]) < 0.1
+    assert qmc.result.last is not None  # the last run stays in the objective, as in the reference (wrapper.jl:74-79)
+
+
+def test_handles_of_another_kind_are_rejected(gw):
+    """Handles carry a type tag: a stored-operator walker set where the bit-level entry points expect theirs (and the
+    other way round) is GWZ_ERR_INVALID (ValueError), never a read through the wrong layout."""
+    import ctypes as C
+    from gutzwiller_b200 import capi
+    L = gw.lib()
+    H = gw.HubbardReal1D(gw.near_uniform(6, 6), u=2.0)
+    Hs = gw.SparseHamiltonian.from_hubbard(H)
+    qs = gw.KineticVQMC(Hs, gw.SparseGutzwillerAnsatz(Hs), samples=1e4, walkers=64)
+    qs.val_and_grad([0.3])
+    qb = gw.KineticVQMC(H, gw.GutzwillerAnsatz(H), samples=1e4, walkers=64)
+    qb.val_and_grad([0.3])
+    p = (C.c_double * 1)(0.3)
+    r = capi.VqmcResult()
+    hs = qs.result.walkers_handle.handle
+    hb = qb.result.walkers_handle.handle
+    assert L.gwz_vqmc_run(hb, p, 10, 0, 1, 0, C.byref(r)) == capi.OK
+    rc = L.gwz_vqmc_run(hs, p, 10, 0, 1, 0, C.byref(r))
+    assert rc == capi.ERR_INVALID and b"handle" in L.gwz_last_error()
+    le = gw.LocalEnergyEvaluator(H, gw.GutzwillerAnsatz(H))
+    v, g = C.c_double(), (C.c_double * 1)()
+    assert L.gwz_sweep_val_and_grad(hb, p, C.byref(v), g, None) == capi.ERR_INVALID
+    assert L.gwz_sweep_val_and_grad(le.handle, p, C.byref(v), g, None) == capi.OK
