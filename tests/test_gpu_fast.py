@@ -27,7 +27,8 @@ def _apply(onr, hop):
 
 CASES = [(10, 10, 2.0, 1.0), (50, 50, 2.0, 1.0), (50, 50, 2.0, 0.33), (100, 100, 2.0, 0.33), (20, 20, 4.0, 1.0),
          (9, 6, 0.5, 0.05), (7, 4, 1.0, 0.3), (33, 32, 2.0, 0.2), (64, 65, 1.0, 0.1), (120, 131, 2.0, 0.1),
-         (17, 40, 3.0, 0.2), (40, 8, 0.3, 0.02), (12, 5, 6.0, 1.5), (6, 240, 1.0, 0.5), (30, 200, 2.0, 0.3)]
+         (17, 40, 3.0, 0.2), (40, 8, 0.3, 0.02), (12, 5, 6.0, 1.5), (6, 240, 1.0, 0.5), (30, 200, 2.0, 0.3),
+         (1, 6, 1.0, 0.5), (2, 4, 3.0, 0.7), (200, 40, 0.05, 0.01)]
 
 
 @pytest.mark.parametrize("N,M,u,g", CASES)
