@@ -345,18 +345,39 @@ gen_walker_kernel(const __grid_constant__ GenModel gm, const __grid_constant__ P
                 }
             }
             __syncwarp();
-            if (TI) {  // the weights of the four modes around the hop change: lo - 1 .. lo + 2, lo = the lower end of the bond
-                const int lo = right ? src : dst;  // (for the bond M-1 -> 0 the "lower" end is M-1)
-                int d0 = lane * MPL - lo + 1;      // distance of this lane's first mode from the window's first, mod M
-                d0 += d0 < 0 ? M : 0;
-                d0 -= d0 >= M ? M : 0;
-                if (d0 < 4 || d0 > M - MPL) {      // one or two lanes of the walker: a real branch, not predication
+            if (TI) {
+                // The weights of the four modes around the hop change: first .. first + 3 (mod M), first = lo - 1, lo = the
+                // lower end of the bond (M-1 for the bond M-1 -> 0).  Lanes 0..3 of the walker's group each evaluate one
+                // of them -- one pass of gen_weight for every walker of the warp at once, instead of one (predicated)
+                // pass per mode on the one or two lanes that own them -- and the owners fetch the results by shuffle.
+                const int lo = right ? src : dst;
+                int first = lo - 1;
+                first += first < 0 ? M : 0;
+                double nwR = 0.0, nwL = 0.0;
+                int nex = 0;
+                if (lane < 4) {
+                    int k = first + lane;
+                    k -= k >= M ? M : 0;
+                    const int n = ws.occ[k];
+                    const int kr = k + 1 == M ? 0 : k + 1, kl = k == 0 ? M - 1 : k - 1;
+                    const double sn = gm.sqrtab[n];
+                    nwR = sn * gm.sqrtab[ws.occ[kr] + 1];
+                    nwL = sn * gm.sqrtab[ws.occ[kl] + 1];
+                    nex = n > 0;
+                }
+                int d = lane * MPL - first;  // distance of this lane's first mode from the window's first, mod M
+                d += d < 0 ? M : 0;
 #pragma unroll
-                    for (int q = 0; q < MPL; ++q) {
-                        int d = d0 + q;
-                        d -= d >= M ? M : 0;
-                        if (lane * MPL + q < M && d < 4) gen_weight_ti<MPL>(gm, ws, lane, q, wR[q], wL[q], occmask);
+                for (int q = 0; q < MPL; ++q) {
+                    const int from = d & 3;  // (any lane when the mode is outside the window: the value is not used)
+                    const double vR = __shfl_sync(0xffffffffu, nwR, from, G), vL = __shfl_sync(0xffffffffu, nwL, from, G);
+                    const int vx = __shfl_sync(0xffffffffu, nex, from, G);
+                    if (d < 4 && lane * MPL + q < M) {
+                        wR[q] = vR;
+                        wL[q] = vL;
+                        occmask = (occmask & ~(1u << q)) | ((unsigned)vx << q);
                     }
+                    d = d + 1 == M ? 0 : d + 1;
                 }
             }
         }
