@@ -553,3 +553,39 @@ def test_c99_consumer_runs_config1_sweep_and_amsgrad(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert "c consumer ok" in r.stdout
+
+
+def test_julia_shim_blocks_and_brackets_balance():
+    """The Julia shim cannot be executed here (no Julia in the image): at least every block opener at bracket depth 0
+    has its `end`, and every bracket closes -- a blatant syntax slip in the unexecuted file fails this test."""
+    import re
+    src = open(os.path.join(ROOT, "gutzwiller.jl_b200", "julia", "GutzwillerB200.jl")).read()
+    code = re.sub(r"#=.*?=#", "", src, flags=re.S)
+    code = re.sub(r'"""(?:.|\n)*?"""', '""', code)
+    code = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', code)
+    code = re.sub(r"'(?:\\.|[^'\\\n])'", "' '", code)
+    code = re.sub(r"#.*", "", code)
+    tok = re.compile(r"[A-Za-z_@!][A-Za-z_0-9!]*|[\(\)\[\]\{\}]|\n|.")
+    openers = {"function", "if", "for", "while", "struct", "let", "begin", "do", "try", "module", "quote", "macro"}
+    pairs = {")": "(", "]": "[", "}": "{"}
+    stack, brackets, line, prev = [], [], 1, None
+    for m in tok.finditer(code):
+        t = m.group(0)
+        if t == "\n":
+            line += 1
+            continue
+        if t in "([{":
+            brackets.append((t, line))
+        elif t in ")]}":
+            assert brackets and brackets[-1][0] == pairs[t], f"unbalanced {t} at line {line}"
+            brackets.pop()
+        elif not brackets and prev not in (".", ":"):  # inside brackets: comprehensions, generators, a[end]
+            if t in openers:
+                stack.append((t, line))
+            elif t == "end":
+                assert stack, f"`end` without an opener at line {line}"
+                stack.pop()
+        if not t.isspace():
+            prev = t
+    assert not brackets, f"unclosed bracket opened at line {brackets[-1][1]}"
+    assert not stack, f"unclosed `{stack[-1][0]}` opened at line {stack[-1][1]}"
